@@ -1,0 +1,129 @@
+// The seam between the host-side frame planner (syntax parsing + orchestration, this directory)
+// and whatever executes the sample-level work. The product implements it with sm_100a CUDA
+// kernels (csrc/cuda_backend.cu); the test oracle implements it with a scalar CPU restatement
+// of the reference (oracle/). It plays the role of the reference's arch-dispatched `impls::`
+// modules (crates/jxl-render/src/vardct/mod.rs:25-46, filter/impls.rs:3-25) plus the entropy
+// seam `decode_pass_group` (crates/jxl-frame/src/data/pass_group.rs:31).
+//
+// All sample storage lives behind the backend as 32-bit "planes" (row-major, stride == width),
+// the device mirror of jxl-grid's AlignedGrid (crates/jxl-grid/src/lib.rs:43-103).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+
+#include "frame_syntax.h"
+#include "headers.h"
+#include "modular_syntax.h"
+
+namespace jxlb {
+
+struct View {  // rectangular window into a plane (MutableSubgrid, mutable_subgrid.rs:7-14)
+  int plane = -1;
+  uint32_t x0 = 0, y0 = 0, w = 0, h = 0;
+};
+
+struct ModularChannelTarget {
+  View view;
+  int32_t hshift = 0, vshift = 0;
+};
+
+// One entropy-coded Modular channel-data stream (jxl-modular/src/image.rs:456-593).
+struct ModularStreamJob {
+  size_t bit_pos = 0;        // absolute bit offset into the codestream where channel data begins
+  size_t bit_limit = 0;      // absolute end (bits) of the enclosing TOC section
+  const MaTree* tree = nullptr;
+  WpHeader wp;
+  uint32_t stream_index = 0;  // MA property 1
+  std::vector<ModularChannelTarget> channels;
+  size_t end_bit = 0;         // out: absolute bit offset after the stream
+};
+
+// One HF coefficient stream (one pass of one 256x256 group), jxl-vardct/src/hf_coeff.rs:21-252.
+struct HfGroupJob {
+  size_t bit_pos = 0, bit_limit = 0;
+  uint32_t group_idx = 0, pass_idx = 0;
+  size_t end_bit = 0;  // out
+};
+
+struct LfGroupRect {  // geometry of one LF group in 8x8-block units
+  uint32_t bx0 = 0, by0 = 0, bw = 0, bh = 0;
+};
+
+// Frame-level state of a VarDCT frame. Planes are allocated by the planner.
+struct VarDctState {
+  uint32_t width = 0, height = 0;      // colour sample size
+  uint32_t bw = 0, bh = 0;             // size in 8x8 blocks (ceil)
+  uint32_t group_dim = 256, groups_per_row = 0, num_groups = 0;
+  // LfGlobal / headers
+  const LfGlobalSyntax* lfg = nullptr;
+  const HfGlobalSyntax* hfg = nullptr;
+  const FrameHeader* fh = nullptr;
+  const ImageHeader* ih = nullptr;
+  // planes
+  int lf_quant[3] = {-1, -1, -1};  // i32, X/Y/B, bw x bh
+  int x_from_y = -1, b_from_y = -1;  // i32, ceil(w/64) x ceil(h/64)
+  int sharpness = -1;                // i32, bw x bh
+  int blk_type = -1;   // i32, bw x bh: dct_select at a varblock's top-left cell, else -(1 + dx + 32*dy)
+  int blk_mul = -1;    // i32, bw x bh: hf_mul at the top-left cell
+  int epf_sigma = -1;  // f32, bw x bh
+  int lf[3] = {-1, -1, -1};     // f32 dequantised LF, bw x bh
+  int coeff[3] = {-1, -1, -1};  // i32 coefficients -> f32 samples in place, (bw*8) x (bh*8)
+};
+
+struct LfDequantJob {  // copy_lf_dequant (jxl-render/src/vardct/mod.rs:387-412)
+  LfGroupRect rect;
+  float scale[3];  // X, Y, B
+};
+
+struct BlockInfoJob {  // HfMetadata post-processing (jxl-vardct/src/hf_metadata.rs:99-230)
+  LfGroupRect rect;
+  int raw_plane = -1;  // nb_blocks x 2
+  uint32_t nb_blocks = 0;
+};
+
+struct ColorParams {  // XYB -> (linear) sRGB, jxl-color/src/{xyb.rs,ciexyz.rs:81,tf/srgb.rs}
+  float opsin_bias[3], cbrt_opsin_bias[3];
+  float itscale;        // 255 / intensity_target
+  float matrix[9];      // opsin inverse
+  bool apply_srgb_tf;
+};
+
+class Backend {
+ public:
+  virtual ~Backend() {}
+  virtual void set_codestream(const uint8_t* data, size_t size) = 0;
+  // planes
+  virtual int alloc_plane(uint32_t w, uint32_t h, bool zero) = 0;
+  virtual void free_plane(int id) = 0;
+  virtual void download_rect(const View& v, void* dst) = 0;  // tightly packed w*h 32-bit words
+  virtual void copy_rect(const View& src, const View& dst) = 0;
+  // Modular (bit-exact integer path)
+  virtual void decode_modular(std::vector<ModularStreamJob>& jobs) = 0;
+  // returns a new plane holding the merged channel (jxl-modular/src/transform/squeeze.rs)
+  virtual int squeeze_inverse(const View& avg, const View& residual, bool horizontal) = 0;
+  virtual void rct_inverse(const View v[3], uint32_t rct_type) = 0;  // transform/rct.rs
+  // palette (transform/palette.rs): `targets[0]` holds indices on entry
+  virtual void palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t,
+                               const WpHeader& wp, uint32_t bit_depth) = 0;
+  // int -> float sample conversion (jxl-render/src/image.rs:93-120, convert_modular_xyb)
+  virtual void int_to_float(const View& v, const BitDepth& depth) = 0;
+  virtual void modular_xyb_to_float(const View yxb[3], const float m_lf_unscaled[3]) = 0;
+  // VarDCT
+  virtual void build_block_info(VarDctState& st, const std::vector<BlockInfoJob>& jobs) = 0;
+  virtual void decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) = 0;
+  virtual void lf_dequant(VarDctState& st, const std::vector<LfDequantJob>& jobs) = 0;
+  virtual void lf_chroma_from_luma(VarDctState& st) = 0;   // vardct/mod.rs:544-568
+  virtual void lf_adaptive_smoothing(VarDctState& st) = 0; // vardct/generic/mod.rs:11-103
+  virtual void hf_dequant_cfl(VarDctState& st) = 0;        // vardct/mod.rs:442-542, 570-603
+  virtual void hf_transform(VarDctState& st) = 0;          // vardct/transform_common.rs:11-75
+  // restoration filters and colour, on the (width x height) window of three planes
+  virtual void gaborish(const View v[3], const float weights[3][2]) = 0;
+  virtual void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) = 0;
+  virtual void upsample(View v[3], uint32_t num_channels, uint32_t factor_log2, const ImageHeader& ih) = 0;
+  virtual void xyb_to_rgb(const View v[3], const ColorParams& p) = 0;
+  // Called by the planner at stage boundaries; a backend may snapshot planes for tests.
+  virtual void stage_marker(const char* /*name*/, const View* /*views*/, int /*n*/) {}
+};
+
+}  // namespace jxlb

@@ -1,0 +1,89 @@
+// Frame-section syntax: LfGlobal, HfGlobal (dequantisation matrices, coefficient orders, HF
+// entropy codes). Everything here is table construction; no sample/coefficient is decoded.
+//
+// Reference: crates/jxl-frame/src/data/{lf_global.rs,hf_global.rs},
+//            crates/jxl-vardct/src/{lf.rs,dequant.rs,hf_pass.rs,dct_select.rs}.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <vector>
+
+#include "bitreader.h"
+#include "entropy.h"
+#include "headers.h"
+#include "modular_syntax.h"
+
+namespace jxlb {
+
+// TransformType (dct_select.rs:1-33). Values are the bitstream's dct_select codes.
+enum TransformType : uint8_t {
+  kDct8 = 0, kHornuss, kDct2, kDct4, kDct16, kDct32, kDct16x8, kDct8x16, kDct32x8, kDct8x32,
+  kDct32x16, kDct16x32, kDct4x8, kDct8x4, kAfv0, kAfv1, kAfv2, kAfv3, kDct64, kDct64x32, kDct32x64,
+  kDct128, kDct128x64, kDct64x128, kDct256, kDct256x128, kDct128x256, kNumTransformTypes
+};
+
+struct TransformTypeInfo {
+  uint8_t w8, h8;        // size in 8x8 blocks (dct_select_size, dct_select.rs:53-77)
+  uint8_t param_index;   // dequant matrix set index (dct_select.rs:79-101)
+  uint8_t order_id;      // coefficient order id (dct_select.rs:124-142)
+  uint8_t transpose;     // need_transpose (dct_select.rs:144-154)
+};
+extern const TransformTypeInfo kTransformInfo[kNumTransformTypes];
+
+struct HfBlockContext {  // lf.rs:52-121
+  std::vector<uint32_t> qf_thresholds;
+  std::vector<int32_t> lf_thresholds[3];
+  std::vector<uint8_t> block_ctx_map;
+  uint32_t num_block_clusters = 0;
+};
+
+struct LfGlobalSyntax {
+  // LfChannelDequantization (lf.rs:8-16)
+  float m_x_lf = 1.0f / 32.0f, m_y_lf = 1.0f / 4.0f, m_b_lf = 1.0f / 2.0f;
+  // Quantizer (lf.rs:18-23)
+  uint32_t global_scale = 0, quant_lf = 0;
+  HfBlockContext hf_block_ctx;
+  // LfChannelCorrelation (lf.rs:25-34)
+  uint32_t colour_factor = 84;
+  float base_correlation_x = 0.0f, base_correlation_b = 1.0f;
+  uint32_t x_factor_lf = 128, b_factor_lf = 128;
+  // GlobalModular (lf_global.rs:204-313)
+  bool has_global_tree = false;
+  MaTree global_tree;
+  std::vector<ChannelInfo> gmodular_image_channels;  // before transforms
+  bool has_gmodular = false;
+  ModularStreamSyntax gmodular;  // header; channel data follows at the reader position
+};
+// Parses LfGlobal up to (not including) the GlobalModular channel data.
+LfGlobalSyntax parse_lf_global(BitReader& br, const ImageHeader& ih, const FrameHeader& fh);
+
+// 17 dequant matrix parameter sets -> raster weight matrices (dequant.rs:159-402, 586-658).
+struct DequantMatrices {
+  // matrices[set][channel] : width*height floats (row-major, `width` = dequant_matrix_size().0)
+  std::vector<float> matrices[17][3];
+  std::vector<float> matrices_tr[17][3];
+  static void matrix_size(uint32_t set, uint32_t* w, uint32_t* h);
+};
+
+struct HfPassSyntax {  // hf_pass.rs:26-76
+  // order[order_id][channel]: (x, y) pairs in the wide orientation; packed x | y << 16
+  std::vector<uint32_t> order[13][3];
+  EntropyCode code;
+};
+
+struct HfGlobalSyntax {
+  DequantMatrices dequant;
+  uint32_t num_hf_presets = 0;
+  std::vector<HfPassSyntax> passes;
+};
+HfGlobalSyntax parse_hf_global(BitReader& br, const ImageHeader& ih, const FrameHeader& fh,
+                               const LfGlobalSyntax& lfg);
+
+// Natural coefficient order for an order id (hf_pass.rs:156-231).
+std::vector<uint32_t> natural_order(uint32_t order_id);
+extern const uint16_t kOrderBlockSize[13][2];  // (bw, bh) in the wide orientation, hf_pass.rs:95-109
+
+// x.powi(n) as computed by Rust on this target (compiler-rt __powisf2).
+float powi_f32(float a, int32_t b);
+
+}  // namespace jxlb

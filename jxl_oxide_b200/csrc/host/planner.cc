@@ -1,0 +1,639 @@
+// See planner.h.
+#include "planner.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+
+namespace jxlb {
+
+std::vector<uint8_t> extract_codestream(const uint8_t* data, size_t size) {
+  static const uint8_t kSig[12] = {0, 0, 0, 0x0c, 'J', 'X', 'L', ' ', 0x0d, 0x0a, 0x87, 0x0a};
+  if (size < 12 || std::memcmp(data, kSig, 12) != 0) return std::vector<uint8_t>(data, data + size);
+  std::vector<uint8_t> out;
+  size_t pos = 0;
+  while (pos + 8 <= size) {
+    uint64_t box_size = (uint64_t(data[pos]) << 24) | (uint64_t(data[pos + 1]) << 16) | (uint64_t(data[pos + 2]) << 8) | data[pos + 3];
+    const uint8_t* ty = data + pos + 4;
+    size_t header = 8;
+    if (box_size == 1) {
+      JXLB_CHECK(pos + 16 <= size, kErrEof, "truncated container box");
+      box_size = 0;
+      for (int i = 0; i < 8; ++i) box_size = (box_size << 8) | data[pos + 8 + i];
+      header = 16;
+    }
+    size_t end = box_size == 0 ? size : pos + size_t(box_size);
+    JXLB_CHECK(end <= size && end >= pos + header, kErrEof, "truncated container box");
+    if (std::memcmp(ty, "jxlc", 4) == 0) {
+      out.insert(out.end(), data + pos + header, data + end);
+    } else if (std::memcmp(ty, "jxlp", 4) == 0) {
+      JXLB_CHECK(end >= pos + header + 4, kErrBitstream, "invalid jxlp box");
+      out.insert(out.end(), data + pos + header + 4, data + end);
+    }
+    pos = end;
+  }
+  JXLB_CHECK(!out.empty(), kErrBitstream, "container without codestream");
+  return out;
+}
+
+namespace {
+
+struct ChanBuf {
+  View view;
+  bool owned = false;
+};
+
+struct GroupChannel {
+  View view;
+  int32_t hshift, vshift;
+};
+
+// A parsed Modular stream whose channel data is about to be (or has been) decoded.
+struct PendingStream {
+  std::unique_ptr<ModularStreamSyntax> syntax;
+  std::vector<ChanBuf> coded;    // buffers of the coded channels
+  std::vector<View> targets;     // where image channels must end up (empty view = stay in `coded`)
+  bool direct = true;            // coded channels alias the targets (no local transforms)
+  size_t job_index = 0;
+};
+
+class FramePlanner {
+ public:
+  FramePlanner(Backend& be, const uint8_t* cs, size_t size, const ImageHeader& ih, const DecodeOptions& opt)
+      : be_(be), cs_(cs), size_(size), ih_(ih), opt_(opt) {}
+
+  DecodedFrame decode_frame(size_t frame_begin_byte, size_t* frame_end_byte);
+
+ private:
+  BitReader reader_at(size_t bit_pos, size_t limit_byte) const { return BitReader(cs_, limit_byte, bit_pos); }
+  void section(size_t logical_idx, size_t* bit_begin, size_t* byte_limit) const {
+    const TocEntry& e = toc_.entries[logical_idx];
+    JXLB_CHECK(e.offset + e.size <= size_, kErrEof, "frame section beyond end of codestream");
+    *bit_begin = e.offset * 8;
+    *byte_limit = e.offset + e.size;
+  }
+  const MaTree* tree_for(const ModularStreamSyntax& s) const {
+    return s.has_local_tree ? &s.local_tree : &lfg_.global_tree;
+  }
+
+  // Prepares a stream: parses its header at `br`, allocates coded buffers, appends a job.
+  PendingStream prepare_stream(BitReader& br, size_t limit_byte, const std::vector<GroupChannel>& image_channels,
+                               uint32_t stream_index, std::vector<ModularStreamJob>* jobs);
+  void finish_stream(PendingStream& ps);
+  void run_inverse_transforms(const ModularStreamSyntax& s, std::vector<ChanBuf>& bufs);
+  void setup_gmodular();
+  void render_vardct(DecodedFrame* out);
+  void finish_colour(std::vector<View>& colour, bool is_xyb, DecodedFrame* out);
+
+  Backend& be_;
+  const uint8_t* cs_;
+  size_t size_;
+  const ImageHeader& ih_;
+  DecodeOptions opt_;
+  FrameHeader fh_;
+  Toc toc_;
+  LfGlobalSyntax lfg_;
+  HfGlobalSyntax hfg_;
+  VarDctState st_;
+  std::vector<int> frame_planes_;  // freed at the end of the frame unless exported
+  // global modular
+  std::vector<ChanBuf> gm_coded_;
+  size_t gm_global_count_ = 0;
+  std::vector<std::vector<GroupChannel>> gm_lf_groups_;               // [lf_group]
+  std::vector<std::vector<std::vector<GroupChannel>>> gm_pass_groups_;  // [pass][group]
+  std::vector<uint32_t> extra_precision_;
+
+  int new_plane(uint32_t w, uint32_t h, bool zero = false) {
+    int id = be_.alloc_plane(std::max(w, 1u), std::max(h, 1u), zero);
+    frame_planes_.push_back(id);
+    return id;
+  }
+  void drop_plane(int id) {
+    auto it = std::find(frame_planes_.begin(), frame_planes_.end(), id);
+    if (it != frame_planes_.end()) frame_planes_.erase(it);
+    be_.free_plane(id);
+  }
+};
+
+PendingStream FramePlanner::prepare_stream(BitReader& br, size_t limit_byte,
+                                           const std::vector<GroupChannel>& image_channels, uint32_t stream_index,
+                                           std::vector<ModularStreamJob>* jobs) {
+  PendingStream ps;
+  std::vector<ChannelInfo> infos;
+  for (const GroupChannel& g : image_channels) infos.push_back({g.view.w, g.view.h, g.hshift, g.vshift});
+  ps.syntax.reset(new ModularStreamSyntax(parse_modular_stream_header(br, infos, lfg_.has_global_tree)));
+  const ModularStreamSyntax& s = *ps.syntax;
+  ps.direct = s.header.transforms.empty();
+  for (const GroupChannel& g : image_channels) ps.targets.push_back(g.view);
+  ModularStreamJob job;
+  job.bit_pos = br.pos();
+  job.bit_limit = limit_byte * 8;
+  job.tree = tree_for(s);
+  job.wp = s.header.wp;
+  job.stream_index = stream_index;
+  if (ps.direct) {
+    for (const GroupChannel& g : image_channels) {
+      ps.coded.push_back({g.view, false});
+      job.channels.push_back({g.view, g.hshift, g.vshift});
+    }
+  } else {
+    for (const ChannelInfo& c : s.channels) {
+      View v;
+      v.w = c.width;
+      v.h = c.height;
+      v.plane = (c.width && c.height) ? new_plane(c.width, c.height) : -1;
+      ps.coded.push_back({v, true});
+      job.channels.push_back({v, c.hshift, c.vshift});
+    }
+  }
+  ps.job_index = jobs->size();
+  jobs->push_back(std::move(job));
+  return ps;
+}
+
+void FramePlanner::run_inverse_transforms(const ModularStreamSyntax& s, std::vector<ChanBuf>& bufs) {
+  // TransformedModularSubimage::finish (image.rs:447-452): transforms are undone last to first.
+  for (size_t ti = s.header.transforms.size(); ti-- > 0;) {
+    const Transform& t = s.header.transforms[ti];
+    if (t.kind == Transform::kSqueeze) {  // transform.rs:439-455
+      for (size_t si = t.squeeze.size(); si-- > 0;) {
+        const SqueezeStep& sp = t.squeeze[si];
+        size_t begin = sp.begin_c, n = sp.num_c, end = begin + n;
+        size_t res0 = sp.in_place ? end : bufs.size() - n;
+        for (size_t c = 0; c < n; ++c) {
+          ChanBuf& avg = bufs[begin + c];
+          ChanBuf& res = bufs[res0 + c];
+          int merged = be_.squeeze_inverse(avg.view, res.view, sp.horizontal);
+          frame_planes_.push_back(merged);
+          View mv;
+          mv.plane = merged;
+          mv.w = sp.horizontal ? avg.view.w + res.view.w : avg.view.w;
+          mv.h = sp.horizontal ? avg.view.h : avg.view.h + res.view.h;
+          if (avg.owned && avg.view.plane >= 0) drop_plane(avg.view.plane);
+          if (res.owned && res.view.plane >= 0) drop_plane(res.view.plane);
+          avg.view = mv;
+          avg.owned = true;
+        }
+        bufs.erase(bufs.begin() + res0, bufs.begin() + res0 + n);
+      }
+    } else if (t.kind == Transform::kRct) {
+      View v[3] = {bufs[t.begin_c].view, bufs[t.begin_c + 1].view, bufs[t.begin_c + 2].view};
+      if (v[0].w && v[0].h) be_.rct_inverse(v, t.rct_type);
+    } else {  // palette, transform.rs:265-283
+      ChanBuf pal = bufs[0];
+      bufs.erase(bufs.begin());
+      std::vector<View> targets;
+      targets.push_back(bufs[t.begin_c].view);
+      std::vector<ChanBuf> added;
+      for (uint32_t c = 1; c < t.num_c; ++c) {
+        View v = bufs[t.begin_c].view;
+        v.plane = new_plane(v.w, v.h);
+        v.x0 = v.y0 = 0;
+        targets.push_back(v);
+        added.push_back({v, true});
+      }
+      be_.palette_inverse(pal.view, targets, t, s.header.wp, fh_.bit_depth.bits_per_sample);
+      bufs.insert(bufs.begin() + t.begin_c + 1, added.begin(), added.end());
+      if (pal.owned && pal.view.plane >= 0) drop_plane(pal.view.plane);
+    }
+  }
+}
+
+void FramePlanner::finish_stream(PendingStream& ps) {
+  if (ps.direct) return;
+  run_inverse_transforms(*ps.syntax, ps.coded);
+  JXLB_CHECK(ps.coded.size() == ps.targets.size(), kErrBitstream, "modular transform channel mismatch");
+  for (size_t i = 0; i < ps.coded.size(); ++i) {
+    const View& src = ps.coded[i].view;
+    const View& dst = ps.targets[i];
+    JXLB_CHECK(src.w == dst.w && src.h == dst.h, kErrBitstream, "modular transform size mismatch");
+    if (src.w && src.h) be_.copy_rect(src, dst);
+    if (ps.coded[i].owned && src.plane >= 0) drop_plane(src.plane);
+  }
+}
+
+void FramePlanner::setup_gmodular() {
+  // ModularImageDestination::{prepare_gmodular,prepare_groups} (image.rs:187-345)
+  const ModularStreamSyntax& s = lfg_.gmodular;
+  const uint32_t gd = fh_.group_dim();
+  const uint32_t gshift = ceil_log2_nonzero(gd);
+  for (const ChannelInfo& c : s.channels) {
+    View v;
+    v.w = c.width;
+    v.h = c.height;
+    v.plane = (c.width && c.height) ? new_plane(c.width, c.height) : -1;
+    gm_coded_.push_back({v, true});
+  }
+  size_t i = 0;
+  for (; i < s.channels.size(); ++i) {
+    const ChannelInfo& c = s.channels[i];
+    if (!(i < s.nb_meta_channels || (c.width <= gd && c.height <= gd))) break;
+  }
+  gm_global_count_ = i;
+  // pass shifts (jxl-frame/src/lib.rs:218-226)
+  std::map<uint32_t, std::pair<int32_t, int32_t>> pass_shifts;
+  int32_t maxshift = 3;
+  for (size_t k = 0; k < fh_.passes.downsample.size() && k < fh_.passes.last_pass.size(); ++k) {
+    int32_t minshift = int32_t(ceil_log2_nonzero(fh_.passes.downsample[k]));
+    pass_shifts[fh_.passes.last_pass[k]] = {minshift, maxshift};
+    maxshift = minshift;
+  }
+  pass_shifts[fh_.passes.num_passes - 1] = {0, maxshift};
+  const uint32_t num_passes = fh_.passes.num_passes;
+  const uint32_t cw = fh_.color_sample_width(), chh = fh_.color_sample_height();
+  gm_lf_groups_.assign(fh_.num_lf_groups(), {});
+  gm_pass_groups_.assign(num_passes, std::vector<std::vector<GroupChannel>>(fh_.num_groups()));
+  for (; i < s.channels.size(); ++i) {
+    const ChannelInfo& c = s.channels[i];
+    JXLB_CHECK(c.hshift >= 0 && c.vshift >= 0, kErrBitstream, "unshiftable channel outside the global stream");
+    // original size of the image channel this coded channel derives from: every non-meta channel
+    // of a frame-level Modular image spans the colour sample grid (possibly dim-shifted extra
+    // channels, whose original size is still the colour size; lf_global.rs:270-290).
+    uint32_t ow = cw, oh = chh;
+    if (c.hshift < 3 || c.vshift < 3) {
+      int32_t shift = std::min(c.hshift, c.vshift);
+      int pass = -1;
+      for (auto& kv : pass_shifts)
+        if (shift >= kv.second.first && shift < kv.second.second) {
+          pass = int(kv.first);
+          break;
+        }
+      JXLB_CHECK(pass >= 0 && uint32_t(pass) < num_passes, kErrBitstream, "no pass for modular channel shift");
+      uint32_t gw = gd >> c.hshift, gh = gd >> c.vshift;
+      JXLB_CHECK(gw && gh, kErrBitstream, "channel shift too large after transform");
+      uint32_t nx = (ow + gd - 1) >> gshift, ny = (oh + gd - 1) >> gshift;
+      JXLB_CHECK(nx * ny == fh_.num_groups(), kErrBitstream, "modular group count mismatch");
+      for (uint32_t gy = 0; gy < ny; ++gy)
+        for (uint32_t gx = 0; gx < nx; ++gx) {
+          uint32_t x0 = gx * gw, y0 = gy * gh;
+          if (x0 >= c.width || y0 >= c.height) continue;
+          View v{gm_coded_[i].view.plane, x0, y0, std::min(gw, c.width - x0), std::min(gh, c.height - y0)};
+          gm_pass_groups_[pass][gy * nx + gx].push_back({v, c.hshift, c.vshift});
+        }
+    } else {
+      uint32_t gw = gd >> (c.hshift - 3), gh = gd >> (c.vshift - 3);
+      JXLB_CHECK(gw && gh, kErrBitstream, "channel shift too large after transform");
+      uint32_t nx = (ow + (gd << 3) - 1) >> (gshift + 3), ny = (oh + (gd << 3) - 1) >> (gshift + 3);
+      JXLB_CHECK(nx * ny == fh_.num_lf_groups(), kErrBitstream, "modular LF group count mismatch");
+      for (uint32_t gy = 0; gy < ny; ++gy)
+        for (uint32_t gx = 0; gx < nx; ++gx) {
+          uint32_t x0 = gx * gw, y0 = gy * gh;
+          if (x0 >= c.width || y0 >= c.height) continue;
+          View v{gm_coded_[i].view.plane, x0, y0, std::min(gw, c.width - x0), std::min(gh, c.height - y0)};
+          gm_lf_groups_[gy * nx + gx].push_back({v, c.hshift, c.vshift});
+        }
+    }
+  }
+}
+
+DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_end_byte) {
+  BitReader br(cs_, size_, frame_begin_byte * 8);
+  fh_ = parse_frame_header(br, ih_);
+  toc_ = parse_toc(br, fh_);
+  *frame_end_byte = toc_.data_begin + toc_.total_size;
+  JXLB_CHECK(*frame_end_byte <= size_, kErrEof, "frame data beyond end of codestream");
+
+  const bool vardct = fh_.encoding == Encoding::kVarDct;
+  JXLB_CHECK(fh_.frame_type == FrameType::kRegular || fh_.frame_type == FrameType::kSkipProgressive, kErrUnsupported,
+             "LF frames / reference-only frames are outside the implemented hot path");
+  JXLB_CHECK(!fh_.use_lf_frame(), kErrUnsupported, "use_lf_frame is outside the implemented hot path");
+  JXLB_CHECK(fh_.is_keyframe(), kErrUnsupported, "non-displayed frames (blending sources) are not supported");
+  JXLB_CHECK(fh_.resets_canvas && fh_.width == ih_.width && fh_.height == ih_.height && fh_.x0 == 0 && fh_.y0 == 0,
+             kErrUnsupported, "cropped / blended frames are outside the implemented hot path");
+  JXLB_CHECK(!fh_.do_ycbcr, kErrUnsupported, "YCbCr (JPEG-transcoded) frames are outside the implemented hot path");
+  for (uint32_t u : fh_.ec_upsampling) JXLB_CHECK(u == fh_.upsampling, kErrUnsupported, "extra-channel upsampling differs from colour");
+  for (const auto& ec : ih_.ec_info) JXLB_CHECK(ec.dim_shift == 0, kErrUnsupported, "dim_shift extra channels not supported");
+
+  const uint32_t num_lf_groups = fh_.num_lf_groups(), num_groups = fh_.num_groups();
+  const uint32_t num_passes = fh_.passes.num_passes;
+  const bool single = toc_.single_entry();
+  const uint32_t cw = fh_.color_sample_width(), chh = fh_.color_sample_height();
+
+  // ---- LfGlobal ----
+  size_t pos, limit;
+  section(0, &pos, &limit);
+  {
+    BitReader r = reader_at(pos, limit);
+    lfg_ = parse_lf_global(r, ih_, fh_);
+    pos = r.pos();
+  }
+  if (lfg_.has_gmodular) {
+    setup_gmodular();
+    std::vector<ModularStreamJob> jobs(1);
+    ModularStreamJob& job = jobs[0];
+    job.bit_pos = pos;
+    job.bit_limit = limit * 8;
+    job.tree = tree_for(lfg_.gmodular);
+    job.wp = lfg_.gmodular.header.wp;
+    job.stream_index = 0;
+    for (size_t i = 0; i < gm_global_count_; ++i) {
+      const ChannelInfo& c = lfg_.gmodular.channels[i];
+      job.channels.push_back({gm_coded_[i].view, c.hshift, c.vshift});
+    }
+    be_.decode_modular(jobs);
+    pos = jobs[0].end_bit;
+  } else {
+    gm_lf_groups_.assign(num_lf_groups, {});
+    gm_pass_groups_.assign(num_passes, std::vector<std::vector<GroupChannel>>(num_groups));
+  }
+
+  // ---- VarDCT frame state ----
+  if (vardct) {
+    st_ = VarDctState();
+    st_.width = cw;
+    st_.height = chh;
+    st_.bw = (cw + 7) / 8;
+    st_.bh = (chh + 7) / 8;
+    st_.group_dim = fh_.group_dim();
+    st_.groups_per_row = fh_.groups_per_row();
+    st_.num_groups = num_groups;
+    st_.lfg = &lfg_;
+    st_.hfg = &hfg_;
+    st_.fh = &fh_;
+    st_.ih = &ih_;
+    for (int c = 0; c < 3; ++c) {
+      st_.lf_quant[c] = new_plane(st_.bw, st_.bh);
+      st_.lf[c] = new_plane(st_.bw, st_.bh);
+      st_.coeff[c] = new_plane(st_.bw * 8, st_.bh * 8, /*zero=*/true);
+    }
+    st_.x_from_y = new_plane((cw + 63) / 64, (chh + 63) / 64);
+    st_.b_from_y = new_plane((cw + 63) / 64, (chh + 63) / 64);
+    st_.sharpness = new_plane(st_.bw, st_.bh);
+    st_.blk_type = new_plane(st_.bw, st_.bh);
+    st_.blk_mul = new_plane(st_.bw, st_.bh);
+    st_.epf_sigma = new_plane(st_.bw, st_.bh);
+  }
+
+  // ---- LfGroups: three entropy-coded streams each, at data-dependent bit offsets ----
+  std::vector<size_t> lf_pos(num_lf_groups), lf_limit(num_lf_groups);
+  std::vector<LfGroupRect> lf_rect(num_lf_groups);
+  for (uint32_t g = 0; g < num_lf_groups; ++g) {
+    if (single) {
+      lf_pos[g] = pos;
+      lf_limit[g] = limit;
+    } else {
+      section(1 + g, &lf_pos[g], &lf_limit[g]);
+    }
+    uint32_t gx = g % fh_.lf_groups_per_row(), gy = g / fh_.lf_groups_per_row();
+    uint32_t lfd = fh_.lf_group_dim();
+    uint32_t lw = std::min(lfd, cw - gx * lfd), lh = std::min(lfd, chh - gy * lfd);
+    lf_rect[g] = {gx * (lfd / 8), gy * (lfd / 8), (lw + 7) / 8, (lh + 7) / 8};
+  }
+  extra_precision_.assign(num_lf_groups, 0);
+  if (vardct) {  // LfCoeff (jxl-vardct/src/lf.rs:138-181)
+    std::vector<ModularStreamJob> jobs;
+    std::vector<PendingStream> pend;
+    for (uint32_t g = 0; g < num_lf_groups; ++g) {
+      BitReader r = reader_at(lf_pos[g], lf_limit[g]);
+      extra_precision_[g] = r.read(2);
+      const LfGroupRect& rc = lf_rect[g];
+      std::vector<GroupChannel> chans;
+      for (int mc : {1, 0, 2})  // modular channel order is Y, X, B
+        chans.push_back({View{st_.lf_quant[mc], rc.bx0, rc.by0, rc.bw, rc.bh}, 0, 0});
+      pend.push_back(prepare_stream(r, lf_limit[g], chans, 1 + g, &jobs));
+    }
+    be_.decode_modular(jobs);
+    for (uint32_t g = 0; g < num_lf_groups; ++g) {
+      finish_stream(pend[g]);
+      lf_pos[g] = jobs[pend[g].job_index].end_bit;
+    }
+  }
+  {  // Modular LF-group channels (jxl-frame/src/data/lf_group.rs:76-91)
+    std::vector<ModularStreamJob> jobs;
+    std::vector<PendingStream> pend;
+    std::vector<uint32_t> owner;
+    for (uint32_t g = 0; g < num_lf_groups; ++g) {
+      if (gm_lf_groups_[g].empty()) continue;
+      BitReader r = reader_at(lf_pos[g], lf_limit[g]);
+      pend.push_back(prepare_stream(r, lf_limit[g], gm_lf_groups_[g], 1 + num_lf_groups + g, &jobs));
+      owner.push_back(g);
+    }
+    if (!jobs.empty()) be_.decode_modular(jobs);
+    for (size_t k = 0; k < pend.size(); ++k) {
+      finish_stream(pend[k]);
+      lf_pos[owner[k]] = jobs[pend[k].job_index].end_bit;
+    }
+  }
+  if (vardct) {  // HfMetadata (jxl-vardct/src/hf_metadata.rs:52-230)
+    std::vector<ModularStreamJob> jobs;
+    std::vector<PendingStream> pend;
+    std::vector<BlockInfoJob> bjobs;
+    for (uint32_t g = 0; g < num_lf_groups; ++g) {
+      BitReader r = reader_at(lf_pos[g], lf_limit[g]);
+      const LfGroupRect& rc = lf_rect[g];
+      uint32_t nb_blocks = 1 + r.read(ceil_log2_nonzero(rc.bw * rc.bh));
+      uint32_t w64 = (rc.bw + 7) / 8, h64 = (rc.bh + 7) / 8;
+      int raw = new_plane(nb_blocks, 2);
+      std::vector<GroupChannel> chans;
+      chans.push_back({View{st_.x_from_y, rc.bx0 / 8, rc.by0 / 8, w64, h64}, 0, 0});
+      chans.push_back({View{st_.b_from_y, rc.bx0 / 8, rc.by0 / 8, w64, h64}, 0, 0});
+      chans.push_back({View{raw, 0, 0, nb_blocks, 2}, 0, 0});
+      chans.push_back({View{st_.sharpness, rc.bx0, rc.by0, rc.bw, rc.bh}, 0, 0});
+      pend.push_back(prepare_stream(r, lf_limit[g], chans, 1 + 2 * num_lf_groups + g, &jobs));
+      bjobs.push_back({rc, raw, nb_blocks});
+    }
+    be_.decode_modular(jobs);
+    for (uint32_t g = 0; g < num_lf_groups; ++g) {
+      finish_stream(pend[g]);
+      lf_pos[g] = jobs[pend[g].job_index].end_bit;
+    }
+    be_.build_block_info(st_, bjobs);
+    for (auto& b : bjobs) drop_plane(b.raw_plane);
+  }
+  if (single) pos = lf_pos[0];
+
+  // ---- HfGlobal ----
+  if (vardct) {
+    size_t hpos = pos, hlimit = limit;
+    if (!single) section(1 + num_lf_groups, &hpos, &hlimit);
+    BitReader r = reader_at(hpos, hlimit);
+    hfg_ = parse_hf_global(r, ih_, fh_, lfg_);
+    if (single) pos = r.pos();
+  }
+
+  // ---- PassGroups ----
+  for (uint32_t p = 0; p < num_passes; ++p) {
+    std::vector<size_t> gpos(num_groups), glimit(num_groups);
+    for (uint32_t g = 0; g < num_groups; ++g) {
+      if (single) {
+        gpos[g] = pos;
+        glimit[g] = limit;
+      } else {
+        section(2 + num_lf_groups + p * num_groups + g, &gpos[g], &glimit[g]);
+      }
+    }
+    if (vardct) {
+      std::vector<HfGroupJob> jobs(num_groups);
+      for (uint32_t g = 0; g < num_groups; ++g) jobs[g] = {gpos[g], glimit[g] * 8, g, p, 0};
+      be_.decode_hf(st_, jobs);
+      for (uint32_t g = 0; g < num_groups; ++g) gpos[g] = jobs[g].end_bit;
+    }
+    std::vector<ModularStreamJob> jobs;
+    std::vector<PendingStream> pend;
+    for (uint32_t g = 0; g < num_groups; ++g) {
+      if (gm_pass_groups_[p][g].empty()) continue;
+      BitReader r = reader_at(gpos[g], glimit[g]);
+      pend.push_back(prepare_stream(r, glimit[g], gm_pass_groups_[p][g],
+                                    1 + 3 * num_lf_groups + 17 + p * num_groups + g, &jobs));
+    }
+    if (!jobs.empty()) be_.decode_modular(jobs);
+    for (auto& ps : pend) finish_stream(ps);
+  }
+
+  // ---- global inverse transforms ----
+  std::vector<ChanBuf> gm_image = gm_coded_;
+  if (lfg_.has_gmodular) run_inverse_transforms(lfg_.gmodular, gm_image);
+
+  // ---- render ----
+  DecodedFrame out;
+  out.header = fh_;
+  out.width = cw;
+  out.height = chh;
+  std::vector<View> colour;
+  size_t ec_from = 0;
+  if (vardct) {
+    render_vardct(&out);
+    for (int c = 0; c < 3; ++c) colour.push_back(View{st_.coeff[c], 0, 0, cw, chh});
+  } else {
+    ec_from = fh_.encoded_color_channels;
+    JXLB_CHECK(gm_image.size() >= ec_from, kErrBitstream, "missing modular colour channels");
+    for (size_t c = 0; c < ec_from; ++c) colour.push_back(gm_image[c].view);
+    if (ih_.xyb_encoded) {
+      JXLB_CHECK(colour.size() == 3, kErrBitstream, "XYB modular frame needs three channels");
+      View yxb[3] = {colour[0], colour[1], colour[2]};
+      const float m[3] = {lfg_.m_x_lf / 128.0f, lfg_.m_y_lf / 128.0f, lfg_.m_b_lf / 128.0f};
+      be_.modular_xyb_to_float(yxb, m);
+    } else {
+      for (View& v : colour) be_.int_to_float(v, ih_.bit_depth);
+    }
+  }
+  be_.stage_marker("pre_filter", colour.data(), int(colour.size()));
+
+  // restoration filters (render.rs:76-131)
+  const RestorationFilter& rf = fh_.restoration_filter;
+  if (rf.gab_enabled || rf.epf.iters > 0) {
+    JXLB_CHECK(colour.size() == 3, kErrUnsupported, "restoration filters on grayscale frames are not supported");
+    View v[3] = {colour[0], colour[1], colour[2]};
+    if (rf.gab_enabled) {
+      be_.gaborish(v, rf.gab_weights);
+      be_.stage_marker("gaborish", v, 3);
+    }
+    if (rf.epf.iters > 0) {
+      View sigma;
+      if (vardct) sigma = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
+      be_.epf(v, sigma, rf.epf, !vardct);
+      be_.stage_marker("epf", v, 3);
+    }
+  }
+  JXLB_CHECK(fh_.upsampling == 1, kErrUnsupported, "non-separable upsampling is not implemented yet");
+
+  finish_colour(colour, ih_.xyb_encoded, &out);
+  for (size_t c = ec_from; c < gm_image.size() && (c - ec_from) < ih_.ec_info.size(); ++c) {
+    View v = gm_image[c].view;
+    be_.int_to_float(v, ih_.ec_info[c - ec_from].bit_depth);
+    out.channels.push_back(v);
+  }
+  // release everything not exported
+  for (int id : frame_planes_) {
+    bool exported = false;
+    for (const View& v : out.channels) exported |= (v.plane == id);
+    if (!exported) be_.free_plane(id);
+  }
+  frame_planes_.clear();
+  gm_coded_.clear();
+  return out;
+}
+
+void FramePlanner::render_vardct(DecodedFrame*) {
+  // LF: dequant, chroma-from-luma, adaptive smoothing (vardct/mod.rs:163-201, util.rs:254-290)
+  std::vector<LfDequantJob> jobs;
+  const uint32_t lfd = fh_.lf_group_dim();
+  for (uint32_t g = 0; g < fh_.num_lf_groups(); ++g) {
+    uint32_t gx = g % fh_.lf_groups_per_row(), gy = g / fh_.lf_groups_per_row();
+    uint32_t lw = std::min(lfd, st_.width - gx * lfd), lh = std::min(lfd, st_.height - gy * lfd);
+    LfDequantJob j;
+    j.rect = {gx * (lfd / 8), gy * (lfd / 8), (lw + 7) / 8, (lh + 7) / 8};
+    const float m[3] = {lfg_.m_x_lf, lfg_.m_y_lf, lfg_.m_b_lf};
+    int32_t precision_scale = 1 << (9 - extra_precision_[g]);
+    uint64_t scale_inv = uint64_t(lfg_.global_scale) * lfg_.quant_lf;
+    for (int c = 0; c < 3; ++c) j.scale[c] = float(double(m[c]) * double(precision_scale) / double(scale_inv));
+    jobs.push_back(j);
+  }
+  be_.lf_dequant(st_, jobs);
+  be_.lf_chroma_from_luma(st_);
+  if (!fh_.skip_adaptive_lf_smoothing()) be_.lf_adaptive_smoothing(st_);
+  {
+    View v[3] = {View{st_.lf[0], 0, 0, st_.bw, st_.bh}, View{st_.lf[1], 0, 0, st_.bw, st_.bh}, View{st_.lf[2], 0, 0, st_.bw, st_.bh}};
+    be_.stage_marker("lf", v, 3);
+    View cf[3];
+    for (int c = 0; c < 3; ++c) cf[c] = View{st_.coeff[c], 0, 0, st_.bw * 8, st_.bh * 8};
+    be_.stage_marker("hf_coeff", cf, 3);
+    be_.hf_dequant_cfl(st_);
+    be_.stage_marker("hf_dequant", cf, 3);
+    be_.hf_transform(st_);
+    be_.stage_marker("idct", cf, 3);
+  }
+}
+
+void FramePlanner::finish_colour(std::vector<View>& colour, bool is_xyb, DecodedFrame* out) {
+  // postprocess_keyframe (jxl-render/src/lib.rs:925-998) for the supported colour set.
+  if (is_xyb && opt_.output_colour != 2) {
+    JXLB_CHECK(colour.size() == 3, kErrBitstream, "XYB needs three channels");
+    const ColourEncoding& ce = ih_.colour_encoding;
+    bool srgb_like = !ce.want_icc && ce.colour_space == ColourSpace::kRgb && ce.white_point == WhitePointKind::kD65 &&
+                     ce.primaries == PrimariesKind::kSrgb &&
+                     (ce.tf == TransferFunctionKind::kSrgb || ce.tf == TransferFunctionKind::kLinear);
+    JXLB_CHECK(srgb_like || opt_.output_colour == 1, kErrUnsupported,
+               "only sRGB-gamut (sRGB/linear transfer) output encodings are implemented");
+    JXLB_CHECK(ih_.tone_mapping.intensity_target <= 255.0f || opt_.output_colour == 1, kErrUnsupported,
+               "HDR tone mapping is outside the implemented hot path");
+    ColorParams p;
+    const OpsinInverseMatrix& oim = ih_.opsin_inverse_matrix;
+    for (int i = 0; i < 3; ++i) {
+      p.opsin_bias[i] = oim.opsin_bias[i];
+      p.cbrt_opsin_bias[i] = cbrtf(oim.opsin_bias[i]);
+      for (int j = 0; j < 3; ++j) p.matrix[i * 3 + j] = oim.inv_mat[i][j];
+    }
+    p.itscale = 255.0f / ih_.tone_mapping.intensity_target;
+    p.apply_srgb_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kSrgb;
+    View v[3] = {colour[0], colour[1], colour[2]};
+    be_.xyb_to_rgb(v, p);
+    be_.stage_marker("rgb", v, 3);
+  }
+  out->num_color = uint32_t(colour.size());
+  out->channels = colour;
+}
+
+}  // namespace
+
+DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, const DecodeOptions& opt) {
+  DecodeResult res;
+  be.set_codestream(cs, size);
+  BitReader br(cs, size);
+  res.image_header = parse_image_header(br);
+  const ImageHeader& ih = res.image_header;
+  if (ih.colour_encoding.want_icc) skip_icc_profile(br);
+  br.zero_pad_to_byte();
+  size_t pos = br.pos() / 8;
+  if (ih.have_preview) {  // skipped, like jxl-oxide/src/lib.rs:384-411
+    BitReader pr(cs, size, pos * 8);
+    FrameHeader pfh = parse_frame_header(pr, ih);
+    (void)pfh;
+    fail(kErrUnsupported, "preview frames are not supported");
+  }
+  while (pos < size && res.frames.size() < opt.max_frames) {
+    FramePlanner planner(be, cs, size, ih, opt);
+    size_t end = 0;
+    DecodedFrame f = planner.decode_frame(pos, &end);
+    bool last = f.header.is_last;
+    res.frames.push_back(std::move(f));
+    pos = end;
+    if (last) break;
+  }
+  return res;
+}
+
+}  // namespace jxlb

@@ -1,0 +1,340 @@
+// TEST INFRASTRUCTURE — see oracle_backend.h.
+// Plane management, sample conversions, Gaborish, edge-preserving filter, upsampling and
+// XYB -> sRGB. Restates crates/jxl-render/src/filter/{gabor.rs,epf.rs},
+// filter/impls/generic/{gabor.rs,epf.rs}, features/upsampling.rs, image.rs:93-189 and
+// crates/jxl-color/src/{xyb.rs:35-60,ciexyz.rs:81-87,tf/srgb.rs:13-48}.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "oracle_backend.h"
+
+namespace jxlo {
+
+int OracleBackend::alloc_plane(uint32_t w, uint32_t h, bool /*zero*/) {
+  int id = next_id_++;
+  Plane& p = planes_[id];
+  p.w = w;
+  p.h = h;
+  p.data.assign(size_t(w) * h, 0);
+  return id;
+}
+void OracleBackend::free_plane(int id) { planes_.erase(id); }
+
+void OracleBackend::download_rect(const View& v, void* dst) {
+  Plane& p = plane(v.plane);
+  uint32_t* o = static_cast<uint32_t*>(dst);
+  for (uint32_t y = 0; y < v.h; ++y)
+    std::memcpy(o + size_t(y) * v.w, p.data.data() + size_t(v.y0 + y) * p.w + v.x0, size_t(v.w) * 4);
+}
+
+void OracleBackend::copy_rect(const View& src, const View& dst) {
+  Plane& s = plane(src.plane);
+  Plane& d = plane(dst.plane);
+  for (uint32_t y = 0; y < src.h; ++y)
+    std::memcpy(d.data.data() + size_t(dst.y0 + y) * d.w + dst.x0, s.data.data() + size_t(src.y0 + y) * s.w + src.x0,
+                size_t(src.w) * 4);
+}
+
+void OracleBackend::stage_marker(const char* name, const View* views, int n) {
+  if (!capture) return;
+  auto& out = stages[name];
+  auto& dims = stage_dims[name];
+  out.clear();
+  dims.clear();
+  for (int i = 0; i < n; ++i) {
+    std::vector<uint32_t> buf(size_t(views[i].w) * views[i].h);
+    download_rect(views[i], buf.data());
+    out.push_back(std::move(buf));
+    dims.push_back({views[i].w, views[i].h});
+  }
+}
+
+// BitDepth::parse_integer_sample (jxl-image/src/lib.rs:458-490)
+void OracleBackend::int_to_float(const View& v, const BitDepth& d) {
+  Plane& p = plane(v.plane);
+  for (uint32_t y = 0; y < v.h; ++y) {
+    uint32_t* row = p.data.data() + size_t(v.y0 + y) * p.w + v.x0;
+    for (uint32_t x = 0; x < v.w; ++x) {
+      int32_t s = int32_t(row[x]);
+      float f;
+      if (!d.float_sample) {
+        int32_t div = int32_t((1u << d.bits_per_sample) - 1);
+        f = float(s) / float(div);
+      } else {
+        uint32_t sample = uint32_t(s);
+        uint32_t mantissa_bits = d.bits_per_sample - d.exp_bits - 1;
+        uint32_t mantissa_mask = (1u << mantissa_bits) - 1;
+        uint32_t exp_mask = ((1u << (d.bits_per_sample - 1)) - 1) ^ mantissa_mask;
+        bool is_signed = (sample & (1u << (d.bits_per_sample - 1))) != 0;
+        uint32_t mantissa = sample & mantissa_mask;
+        int32_t exp = int32_t((sample & exp_mask) >> mantissa_bits);
+        exp = exp - ((1 << (d.exp_bits - 1)) - 1);
+        if (mantissa_bits < 23) mantissa <<= (23 - mantissa_bits);
+        else if (mantissa_bits > 23) mantissa >>= (mantissa_bits - 23);
+        uint32_t bits = (uint32_t(is_signed) << 31) | (uint32_t(exp + 127) << 23) | mantissa;
+        std::memcpy(&f, &bits, 4);
+      }
+      std::memcpy(&row[x], &f, 4);
+    }
+  }
+}
+
+// ImageBuffer::convert_to_float_modular_xyb (jxl-render/src/image.rs:148-189)
+void OracleBackend::modular_xyb_to_float(const View yxb[3], const float m[3]) {
+  Plane& py = plane(yxb[0].plane);
+  Plane& px = plane(yxb[1].plane);
+  Plane& pb = plane(yxb[2].plane);
+  for (uint32_t y = 0; y < yxb[0].h; ++y)
+    for (uint32_t x = 0; x < yxb[0].w; ++x) {
+      uint32_t& ry = py.data[size_t(yxb[0].y0 + y) * py.w + yxb[0].x0 + x];
+      uint32_t& rx = px.data[size_t(yxb[1].y0 + y) * px.w + yxb[1].x0 + x];
+      uint32_t& rb = pb.data[size_t(yxb[2].y0 + y) * pb.w + yxb[2].x0 + x];
+      int64_t bsum = int64_t(int32_t(rb)) + int64_t(int32_t(ry));
+      int32_t bi = int32_t(std::min<int64_t>(std::max<int64_t>(bsum, INT32_MIN), INT32_MAX));
+      float fy = float(int32_t(ry)), fx = float(int32_t(rx)), fb = float(bi);
+      float o0 = fx * m[0], o1 = fy * m[1], o2 = fb * m[2];
+      std::memcpy(&ry, &o0, 4);
+      std::memcpy(&rx, &o1, 4);
+      std::memcpy(&rb, &o2, 4);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gaborish (filter/gabor.rs:59-116, impls/generic/gabor.rs)
+namespace {
+
+void gabor_row_edge(const float* row_c, const float* row_a, float* out, size_t width, float w0, float w1) {
+  const float global_weight = 1.0f / (1.0f + w0 * 4.0f + w1 * 4.0f);
+  if (row_a) {
+    if (width == 1) {
+      float u = row_a[0], c = row_c[0];
+      out[0] = (c * (1.0f + 3.0f * w0 + 2.0f * w1) + u * (w0 + 2.0f * w1)) * global_weight;
+      return;
+    }
+    {
+      float a1 = row_a[0], a0 = row_a[1], c1 = row_c[0], c0 = row_c[1];
+      out[0] = (c1 * (1.0f + 2.0f * w0 + w1) + (a1 + c0) * (w0 + w1) + a0 * w1) * global_weight;
+    }
+    for (size_t x = 1; x + 1 < width; ++x) {
+      float a0 = row_a[x - 1], a1 = row_a[x], a2 = row_a[x + 1];
+      float c0 = row_c[x - 1], c1 = row_c[x], c2 = row_c[x + 1];
+      out[x] = (c1 + (a1 + c0 + c1 + c2) * w0 + (a0 + a2 + c0 + c2) * w1) * global_weight;
+    }
+    {
+      float a0 = row_a[width - 2], a1 = row_a[width - 1], c0 = row_c[width - 2], c1 = row_c[width - 1];
+      out[width - 1] = (c1 * (1.0f + 2.0f * w0 + w1) + (a1 + c0) * (w0 + w1) + a0 * w1) * global_weight;
+    }
+  } else {
+    if (width == 1) {
+      out[0] = row_c[0];
+      return;
+    }
+    float merged_w0 = 1.0f + 2.0f + w0;
+    float merged_w1 = w0 + 2.0f * w1;
+    out[0] = (row_c[0] * (merged_w0 + merged_w1) + row_c[1] * merged_w1) * global_weight;
+    for (size_t x = 1; x + 1 < width; ++x) out[x] = (row_c[x] * merged_w0 + (row_c[x - 1] + row_c[x + 1]) * merged_w1) * global_weight;
+    out[width - 1] = (row_c[width - 1] * (merged_w0 + merged_w1) + row_c[width - 2] * merged_w1) * global_weight;
+  }
+}
+
+void gabor_row(const float* t, const float* c, const float* b, float* out, size_t width, float w0, float w1) {
+  if (width == 0) return;
+  const float global_weight = 1.0f / (1.0f + w0 * 4.0f + w1 * 4.0f);
+  if (width == 1) {
+    float sum_side = t[0] + 2.0f * c[0] + b[0];
+    float sum_diag = 2.0f * (t[0] + b[0]);
+    out[0] = (c[0] + sum_side * w0 + sum_diag * w1) * global_weight;
+    return;
+  }
+  {
+    float t1 = t[0], c1 = c[0], b1 = b[0], t0 = t[1], c0 = c[1], b0 = b[1];
+    float sum_side = t1 + c0 + c1 + b1, sum_diag = t0 + t1 + b0 + b1;
+    out[0] = (c1 + sum_side * w0 + sum_diag * w1) * global_weight;
+  }
+  for (size_t x = 1; x + 1 < width; ++x) {
+    float sum_side = t[x] + c[x - 1] + c[x + 1] + b[x];
+    float sum_diag = t[x - 1] + t[x + 1] + b[x - 1] + b[x + 1];
+    out[x] = (c[x] + sum_side * w0 + sum_diag * w1) * global_weight;
+  }
+  {
+    float t1 = t[width - 1], c1 = c[width - 1], b1 = b[width - 1], t0 = t[width - 2], c0 = c[width - 2], b0 = b[width - 2];
+    float sum_side = t1 + c0 + c1 + b1, sum_diag = t0 + t1 + b0 + b1;
+    out[width - 1] = (c1 + sum_side * w0 + sum_diag * w1) * global_weight;
+  }
+}
+
+}  // namespace
+
+void OracleBackend::gaborish(const View v[3], const float weights[3][2]) {
+  for (int c = 0; c < 3; ++c) {
+    Plane& p = plane(v[c].plane);
+    const size_t width = v[c].w, height = v[c].h, stride = p.w;
+    float* base = p.f32() + size_t(v[c].y0) * stride + v[c].x0;
+    std::vector<float> out(width * height);
+    const float w0 = weights[c][0], w1 = weights[c][1];
+    if (height == 1) {
+      gabor_row_edge(base, nullptr, out.data(), width, w0, w1);
+    } else {
+      gabor_row_edge(base, base + stride, out.data(), width, w0, w1);
+      parallel_for(height - 2, [&](size_t i) {
+        size_t y = i + 1;
+        gabor_row(base + (y - 1) * stride, base + y * stride, base + (y + 1) * stride, &out[y * width], width, w0, w1);
+      });
+      gabor_row_edge(base + (height - 1) * stride, base + (height - 2) * stride, &out[(height - 1) * width], width, w0, w1);
+    }
+    for (size_t y = 0; y < height; ++y) std::memcpy(base + y * stride, &out[y * width], width * 4);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Edge-preserving filter (filter/epf.rs:10-291, impls/generic/epf.rs:3-210)
+namespace {
+
+inline size_t mirror(ptrdiff_t offset, size_t len) {  // util.rs:376-386
+  for (;;) {
+    if (offset < 0) offset = -(offset + 1);
+    else if (size_t(offset) >= len) offset = ptrdiff_t(len * 2) - (offset + 1);
+    else return size_t(offset);
+  }
+}
+
+const int8_t kKernel1[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};
+const int8_t kKernel2[12][2] = {{0, -2}, {-1, -1}, {0, -1}, {1, -1}, {-2, 0}, {-1, 0}, {1, 0}, {2, 0}, {-1, 1}, {0, 1}, {1, 1}, {0, 2}};
+const int8_t kDist0[5][2] = {{0, -1}, {1, 0}, {0, 0}, {-1, 0}, {0, 1}};
+const int8_t kDist1[5][2] = {{0, -1}, {0, 0}, {0, 1}, {-1, 0}, {1, 0}};
+const int8_t kDist2[1][2] = {{0, 0}};
+
+}  // namespace
+
+void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) {
+  const size_t width = v[0].w, height = v[0].h;
+  std::vector<float> bufs[2][3];
+  for (int c = 0; c < 3; ++c) {
+    bufs[0][c].resize(width * height);
+    bufs[1][c].resize(width * height);
+    Plane& pl = plane(v[c].plane);
+    for (size_t y = 0; y < height; ++y)
+      std::memcpy(&bufs[0][c][y * width], pl.f32() + (v[c].y0 + y) * size_t(pl.w) + v[c].x0, width * 4);
+  }
+  const float* sig = nullptr;
+  size_t sig_stride = 0;
+  if (!sigma_is_constant) {
+    Plane& sp = plane(sigma.plane);
+    sig = sp.f32();
+    sig_stride = sp.w;
+  }
+  int cur = 0;
+  auto run_step = [&](int step) {
+    const int8_t(*kernel)[2] = step == 0 ? kKernel2 : kKernel1;
+    const int nk = step == 0 ? 12 : 4;
+    const int8_t(*dist)[2] = step == 0 ? kDist0 : (step == 1 ? kDist1 : kDist2);
+    const int nd = step == 2 ? 1 : 5;
+    const float step_multiplier = step == 0 ? p.pass0_sigma_scale : (step == 2 ? p.pass2_sigma_scale : 1.0f);
+    const float* in[3] = {bufs[cur][0].data(), bufs[cur][1].data(), bufs[cur][2].data()};
+    float* out[3] = {bufs[cur ^ 1][0].data(), bufs[cur ^ 1][1].data(), bufs[cur ^ 1][2].data()};
+    parallel_for(height, [&](size_t y) {
+      const bool is_y_border = ((y + 1) & 6) == 0;
+      float sm[8];
+      for (int i = 0; i < 8; ++i) sm[i] = is_y_border ? step_multiplier * p.border_sad_mul : step_multiplier;
+      if (!is_y_border) {
+        sm[0] *= p.border_sad_mul;
+        sm[7] *= p.border_sad_mul;
+      }
+      for (size_t dx = 0; dx < width; ++dx) {
+        float sigma_val = sigma_is_constant ? p.sigma_for_modular : sig[(y / 8) * sig_stride + dx / 8];
+        if (sigma_val < 0.3f) {
+          for (int c = 0; c < 3; ++c) out[c][y * width + dx] = in[c][y * width + dx];
+          continue;
+        }
+        float sum_weights = 1.0f;
+        float sum_channels[3] = {in[0][y * width + dx], in[1][y * width + dx], in[2][y * width + dx]};
+        for (int k = 0; k < nk; ++k) {
+          ptrdiff_t kx = ptrdiff_t(dx) + kernel[k][0], ky = ptrdiff_t(y) + kernel[k][1];
+          float d = 0.0f;
+          for (int c = 0; c < 3; ++c) {
+            float acc = 0.0f;
+            for (int i = 0; i < nd; ++i) {
+              size_t ay = mirror(ky + dist[i][1], height), ax = mirror(kx + dist[i][0], width);
+              size_t by = mirror(ptrdiff_t(y) + dist[i][1], height), bx = mirror(ptrdiff_t(dx) + dist[i][0], width);
+              acc += std::fabs(in[c][ay * width + ax] - in[c][by * width + bx]);
+            }
+            d += p.channel_scale[c] * acc;
+          }
+          // weight() (impls/generic/epf.rs:205-210)
+          float neg_inv_sigma = 6.6f * (0.70710678118654752440f - 1.0f) / sigma_val * sm[dx & 7];
+          float weight = std::max(1.0f + d * neg_inv_sigma, 0.0f);
+          sum_weights += weight;
+          size_t my = mirror(ky, height), mx = mirror(kx, width);
+          for (int c = 0; c < 3; ++c) sum_channels[c] += weight * in[c][my * width + mx];
+        }
+        for (int c = 0; c < 3; ++c) out[c][y * width + dx] = sum_channels[c] / sum_weights;
+      }
+    });
+    cur ^= 1;
+  };
+  if (p.iters == 3) run_step(0);
+  run_step(1);
+  if (p.iters >= 2) run_step(2);
+  for (int c = 0; c < 3; ++c) {
+    Plane& pl = plane(v[c].plane);
+    for (size_t y = 0; y < height; ++y)
+      std::memcpy(pl.f32() + (v[c].y0 + y) * size_t(pl.w) + v[c].x0, &bufs[cur][c][y * width], width * 4);
+  }
+}
+
+void OracleBackend::upsample(View*, uint32_t, uint32_t, const ImageHeader&) {
+  fail(kErrUnsupported, "upsampling not implemented in the oracle yet");
+}
+
+// ---------------------------------------------------------------------------------------------
+// XYB -> linear sRGB (-> sRGB), jxl-color/src/{xyb.rs:35-60, ciexyz.rs:81-87, tf/srgb.rs:13-48}
+void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
+  static const uint8_t kPowUpper[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c, 0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
+  static const uint8_t kPowLower[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68, 0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};
+  Plane* pl[3] = {&plane(v[0].plane), &plane(v[1].plane), &plane(v[2].plane)};
+  parallel_for(v[0].h, [&](size_t y) {
+    float* r[3];
+    for (int c = 0; c < 3; ++c) r[c] = pl[c]->f32() + (v[c].y0 + y) * size_t(pl[c]->w) + v[c].x0;
+    for (uint32_t x = 0; x < v[0].w; ++x) {
+      float xx = r[0][x], yy = r[1][x], bb = r[2][x];
+      float g_l = yy + xx, g_m = yy - xx, g_s = bb;
+      g_l = g_l - p.cbrt_opsin_bias[0];
+      g_m = g_m - p.cbrt_opsin_bias[1];
+      g_s = g_s - p.cbrt_opsin_bias[2];
+      float a = std::fmaf(g_l * g_l, g_l, p.opsin_bias[0]) * p.itscale;
+      float b = std::fmaf(g_m * g_m, g_m, p.opsin_bias[1]) * p.itscale;
+      float c = std::fmaf(g_s * g_s, g_s, p.opsin_bias[2]) * p.itscale;
+      const float* m = p.matrix;
+      float o[3] = {m[0] * a + m[1] * b + m[2] * c, m[3] * a + m[4] * b + m[5] * c, m[6] * a + m[7] * b + m[8] * c};
+      if (p.apply_srgb_tf) {
+        for (float& s : o) {
+          uint32_t bits;
+          std::memcpy(&bits, &s, 4);
+          uint32_t vb = bits & 0x7fffffffu;
+          uint32_t adj = (vb | 0x3e800000u) & 0x3effffffu;
+          float v_adj;
+          std::memcpy(&v_adj, &adj, 4);
+          float pow = 0.059914046f;
+          pow = pow * v_adj - 0.10889456f;
+          pow = pow * v_adj + 0.107963754f;
+          pow = pow * v_adj + 0.018092343f;
+          uint32_t idx = ((vb >> 23) - 118) & 0xf;
+          uint32_t mulb = 0x40000000u | (uint32_t(kPowUpper[idx]) << 18) | (uint32_t(kPowLower[idx]) << 10);
+          float mul, av;
+          std::memcpy(&mul, &mulb, 4);
+          std::memcpy(&av, &vb, 4);
+          float small = av * 12.92f;
+          float acc = pow * mul - 0.055f;
+          float res = av <= 0.0031308f ? small : acc;
+          s = std::copysign(res, s);
+        }
+      }
+      r[0][x] = o[0];
+      r[1][x] = o[1];
+      r[2][x] = o[2];
+    }
+  });
+}
+
+}  // namespace jxlo
