@@ -1,0 +1,118 @@
+/* jxlb200 — C ABI of the B200-native JPEG XL decode hot path (libjxlb200.so).
+ *
+ * This is the boundary a jxl-oxide maintainer binds from Rust (`extern "C"`).
+ * No C++/torch types cross it: plain pointers, sizes and int status codes. All entry points are
+ * re-entrant per decoder object; one decoder owns one CUDA stream and its HBM planes
+ * (the reference renders frames concurrently behind `&self`, crates/jxl-render/src/state.rs:72-228).
+ *
+ * Error convention (reference: Result<T, jxl_render::Error>, crates/jxl-render/src/error.rs):
+ *   0 = ok, JXLB_ERR_* otherwise; jxlb_last_error() returns the message. JXLB_ERR_UNSUPPORTED
+ *   marks valid streams outside the implemented hot path — the Rust shim would route those to
+ *   its own CPU renderer; this library itself has NO CPU fallback.
+ */
+#ifndef JXLB200_H_
+#define JXLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  JXLB_OK = 0,
+  JXLB_ERR_BITSTREAM = 1,
+  JXLB_ERR_UNSUPPORTED = 2,
+  JXLB_ERR_EOF = 3,
+  JXLB_ERR_CUDA = 4,
+  JXLB_ERR_INVALID_ARG = 5,
+  JXLB_ERR_DEVICE_DECODE = 6
+};
+
+typedef struct jxlb_decoder jxlb_decoder;
+
+typedef struct {
+  /* 0: the image's signalled colour encoding (sRGB transfer), 1: linear sRGB, 2: leave XYB.
+   * Mirrors JxlImage::request_color_encoding (crates/jxl-oxide/src/lib.rs). */
+  int32_t output_colour;
+  uint32_t max_frames; /* 0 = all keyframes */
+} jxlb_options;
+
+typedef struct {
+  uint32_t width, height;
+  uint32_t num_channels; /* colour + extra */
+  uint32_t num_color;
+  uint32_t is_vardct;
+  uint32_t duration;
+} jxlb_frame_info;
+
+typedef struct {
+  uint32_t width, height, bits_per_sample, num_extra_channels, xyb_encoded, grayscale, orientation;
+} jxlb_image_info;
+
+/* Context lifetime. Replaces JxlImageBuilder/RenderContext construction
+ * (crates/jxl-oxide/src/lib.rs:205-279, crates/jxl-render/src/lib.rs:35-130). */
+int32_t jxlb_decoder_create(int32_t cuda_device, jxlb_decoder** out);
+void jxlb_decoder_destroy(jxlb_decoder* dec);
+const char* jxlb_last_error(const jxlb_decoder* dec);
+
+/* Decode every keyframe of a codestream/container held in HOST memory. Replaces
+ * JxlImage::render_frame -> jxl_render::render::render_frame
+ * (crates/jxl-oxide/src/lib.rs:710-740, crates/jxl-render/src/render.rs:14-156) plus
+ * RenderContext::postprocess_keyframe (crates/jxl-render/src/lib.rs:925-998).
+ * Decoded planes (f32, planar, row-major) stay resident in HBM until jxlb_release_frames(). */
+int32_t jxlb_decode(jxlb_decoder* dec, const uint8_t* data, size_t size, const jxlb_options* opt);
+int32_t jxlb_image_get_info(const jxlb_decoder* dec, jxlb_image_info* info);
+int32_t jxlb_num_frames(const jxlb_decoder* dec);
+int32_t jxlb_frame_get_info(const jxlb_decoder* dec, int32_t frame, jxlb_frame_info* info);
+/* Render::image_planar equivalent (crates/jxl-oxide/src/lib.rs:1178-1203): copy one channel to
+ * host memory, `dst_stride` in floats (>= width). */
+int32_t jxlb_frame_channel_to_host(jxlb_decoder* dec, int32_t frame, int32_t channel, float* dst, size_t dst_stride);
+/* Device-resident access: pointer to the channel's top-left sample and its row stride (floats). */
+int32_t jxlb_frame_channel_device(jxlb_decoder* dec, int32_t frame, int32_t channel, float** dptr, uint32_t* stride);
+int32_t jxlb_release_frames(jxlb_decoder* dec);
+/* Blocks until all work queued on the decoder's stream has finished. */
+int32_t jxlb_sync(jxlb_decoder* dec);
+/* Number of kernels this decoder has launched so far. */
+uint64_t jxlb_launch_count(const jxlb_decoder* dec);
+
+/* Test / debugging hook: snapshot intermediate stages ("lf", "hf_coeff", "hf_dequant", "idct",
+ * "pre_filter", "gaborish", "epf", "rgb") of the LAST decoded frame to host memory. */
+int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on);
+int32_t jxlb_stage_count(const jxlb_decoder* dec, const char* name);
+int32_t jxlb_stage_get(const jxlb_decoder* dec, const char* name, int32_t idx, uint32_t* width, uint32_t* height,
+                       uint32_t* out /* may be NULL */);
+
+/* ---- Stage-level entry points on DEVICE memory (planar f32 / i32, row-major, stride in elements).
+ * They replace the reference's arch-dispatched `impls::` functions one-to-one. ---- */
+
+/* filter::impls::apply_gabor_like (crates/jxl-render/src/filter/impls/generic.rs:39).
+ * In-place on three planes; weights[c][0..1]. */
+int32_t jxlb_gaborish(jxlb_decoder* dec, float* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                      const float weights[6]);
+/* filter::impls::epf::<STEP> chain as driven by apply_epf (crates/jxl-render/src/filter/epf.rs:10-104).
+ * sigma: one f32 per 8x8 block (stride sigma_stride) or NULL to use sigma_for_modular. */
+typedef struct {
+  uint32_t iters;
+  float channel_scale[3];
+  float pass0_sigma_scale, pass2_sigma_scale, border_sad_mul, sigma_for_modular;
+} jxlb_epf_params;
+int32_t jxlb_epf(jxlb_decoder* dec, float* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                 const float* sigma, uint32_t sigma_stride, const jxlb_epf_params* params);
+/* ColorTransform XybToMixedLms + Matrix (+ sRGB OETF) (crates/jxl-color/src/convert.rs:287-308). */
+int32_t jxlb_xyb_to_rgb(jxlb_decoder* dec, float* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                        const float opsin_bias[3], const float inv_matrix[9], float intensity_target, int32_t srgb_tf);
+/* squeeze::inverse_h / inverse_v (crates/jxl-modular/src/transform/squeeze.rs:11, 755). `out` is a
+ * separate (avg_w + res_w) x h (horizontal) or w x (avg_h + res_h) plane. */
+int32_t jxlb_squeeze_inverse(jxlb_decoder* dec, const int32_t* avg, uint32_t avg_w, uint32_t avg_h, uint32_t avg_stride,
+                             const int32_t* res, uint32_t res_w, uint32_t res_h, uint32_t res_stride, int32_t* out,
+                             uint32_t out_stride, int32_t horizontal);
+/* rct::inverse_rct (crates/jxl-modular/src/transform/rct.rs:15). In place on three planes. */
+int32_t jxlb_rct_inverse(jxlb_decoder* dec, int32_t* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                         uint32_t rct_type);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JXLB200_H_ */

@@ -1,0 +1,266 @@
+"""jxl_oxide_b200 — B200-native JPEG XL decode hot path behind jxl-oxide's JxlImage / render_frame() API.
+
+Python host-side mirror of the reference's public interface for this path
+(crates/jxl-oxide/src/lib.rs: JxlImage::builder().read(..), image.render_frame(k) -> Render,
+Render::image_planar()). All sample-level work runs in hand-written sm_100a CUDA kernels inside
+libjxlb200.so (C ABI: include/jxlb200.h); this module only marshals bytes and pointers.
+
+There is no CPU fallback: importing works anywhere (so the C ABI can be inspected), but creating a
+decoder without a CUDA device raises JxlError.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjxlb200.so")
+
+OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVICE_DECODE = range(7)
+
+# every symbol include/jxlb200.h declares
+EXPORTED_SYMBOLS = [
+    "jxlb_decoder_create", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_image_get_info",
+    "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_channel_device",
+    "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_capture", "jxlb_stage_count", "jxlb_stage_get",
+    "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse",
+]
+
+
+class JxlError(RuntimeError):
+    """Mirrors jxl_oxide's Result error values (decode errors are values, not crashes)."""
+
+    def __init__(self, code, message):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+        self.message = message
+
+    @property
+    def unsupported(self):
+        return self.code == ERR_UNSUPPORTED
+
+
+class _Options(ctypes.Structure):
+    _fields_ = [("output_colour", ctypes.c_int32), ("max_frames", ctypes.c_uint32)]
+
+
+class _FrameInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in ("width", "height", "num_channels", "num_color", "is_vardct", "duration")]
+
+
+class _ImageInfo(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint32) for n in
+                ("width", "height", "bits_per_sample", "num_extra_channels", "xyb_encoded", "grayscale", "orientation")]
+
+
+class EpfParams(ctypes.Structure):
+    _fields_ = [("iters", ctypes.c_uint32), ("channel_scale", ctypes.c_float * 3), ("pass0_sigma_scale", ctypes.c_float),
+                ("pass2_sigma_scale", ctypes.c_float), ("border_sad_mul", ctypes.c_float),
+                ("sigma_for_modular", ctypes.c_float)]
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libjxlb200.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise JxlError(ERR_CUDA, f"{LIB_PATH} is missing: build it with `python -m jxl_oxide_b200.build` "
+                                 "(there is no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32
+    L.jxlb_decoder_create.argtypes = [i32, ctypes.POINTER(vp)]
+    L.jxlb_decoder_create.restype = i32
+    L.jxlb_decoder_destroy.argtypes = [vp]
+    L.jxlb_decoder_destroy.restype = None
+    L.jxlb_last_error.argtypes = [vp]
+    L.jxlb_last_error.restype = ctypes.c_char_p
+    L.jxlb_decode.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(_Options)]
+    L.jxlb_decode.restype = i32
+    L.jxlb_image_get_info.argtypes = [vp, ctypes.POINTER(_ImageInfo)]
+    L.jxlb_num_frames.argtypes = [vp]
+    L.jxlb_frame_get_info.argtypes = [vp, i32, ctypes.POINTER(_FrameInfo)]
+    L.jxlb_frame_channel_to_host.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
+    L.jxlb_frame_channel_device.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
+    L.jxlb_release_frames.argtypes = [vp]
+    L.jxlb_sync.argtypes = [vp]
+    L.jxlb_launch_count.argtypes = [vp]
+    L.jxlb_launch_count.restype = ctypes.c_uint64
+    L.jxlb_set_capture.argtypes = [vp, i32]
+    L.jxlb_stage_count.argtypes = [vp, ctypes.c_char_p]
+    L.jxlb_stage_get.argtypes = [vp, ctypes.c_char_p, i32, ctypes.POINTER(u32), ctypes.POINTER(u32), vp]
+    L.jxlb_gaborish.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, ctypes.POINTER(ctypes.c_float)]
+    L.jxlb_epf.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, vp, u32, ctypes.POINTER(EpfParams)]
+    L.jxlb_xyb_to_rgb.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, ctypes.POINTER(ctypes.c_float),
+                                  ctypes.POINTER(ctypes.c_float), ctypes.c_float, i32]
+    L.jxlb_squeeze_inverse.argtypes = [vp, vp, u32, u32, u32, vp, u32, u32, u32, vp, u32, i32]
+    L.jxlb_rct_inverse.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, u32]
+    _lib = L
+    return L
+
+
+class Decoder:
+    """One decoder = one CUDA stream + its HBM planes (RenderContext analogue)."""
+
+    def __init__(self, device=0):
+        L = load_library()
+        h = ctypes.c_void_p()
+        rc = L.jxlb_decoder_create(device, ctypes.byref(h))
+        if rc != OK:
+            raise JxlError(rc, "cannot create CUDA decoder (no CUDA device? this path has no CPU fallback)")
+        self._h = h
+        self._L = L
+
+    def _check(self, rc):
+        if rc != OK:
+            raise JxlError(rc, self._L.jxlb_last_error(self._h).decode(errors="replace"))
+
+    def decode(self, data: bytes, output_colour=0, max_frames=0):
+        opt = _Options(output_colour, max_frames)
+        self._check(self._L.jxlb_decode(self._h, data, len(data), ctypes.byref(opt)))
+
+    def image_info(self):
+        info = _ImageInfo()
+        self._check(self._L.jxlb_image_get_info(self._h, ctypes.byref(info)))
+        return info
+
+    def num_frames(self):
+        return self._L.jxlb_num_frames(self._h)
+
+    def frame_info(self, frame):
+        info = _FrameInfo()
+        self._check(self._L.jxlb_frame_get_info(self._h, frame, ctypes.byref(info)))
+        return info
+
+    def frame_planar(self, frame):
+        """numpy (channels, height, width) float32 — Render::image_planar()."""
+        info = self.frame_info(frame)
+        out = np.empty((info.num_channels, info.height, info.width), dtype=np.float32)
+        for c in range(info.num_channels):
+            self._check(self._L.jxlb_frame_channel_to_host(self._h, frame, c, out[c].ctypes.data, info.width))
+        return out
+
+    def frame_channel_device(self, frame, channel):
+        ptr, stride = ctypes.c_void_p(), ctypes.c_uint32()
+        self._check(self._L.jxlb_frame_channel_device(self._h, frame, channel, ctypes.byref(ptr), ctypes.byref(stride)))
+        return ptr.value, stride.value
+
+    def release_frames(self):
+        self._check(self._L.jxlb_release_frames(self._h))
+
+    def sync(self):
+        self._check(self._L.jxlb_sync(self._h))
+
+    def launch_count(self):
+        return int(self._L.jxlb_launch_count(self._h))
+
+    def set_capture(self, on=True):
+        self._L.jxlb_set_capture(self._h, int(on))
+
+    def stage(self, name, dtype=np.float32):
+        n = self._L.jxlb_stage_count(self._h, name.encode())
+        planes = []
+        for i in range(n):
+            w, h = ctypes.c_uint32(), ctypes.c_uint32()
+            self._check(self._L.jxlb_stage_get(self._h, name.encode(), i, ctypes.byref(w), ctypes.byref(h), None))
+            buf = np.empty((h.value, w.value), dtype=np.uint32)
+            self._check(self._L.jxlb_stage_get(self._h, name.encode(), i, ctypes.byref(w), ctypes.byref(h), buf.ctypes.data))
+            planes.append(buf.view(dtype))
+        return planes
+
+    # ---- stage-level entry points on device memory (torch tensors) ----
+    def _plane_ptrs(self, planes):
+        arr = (ctypes.c_void_p * 3)(*[int(p.data_ptr()) for p in planes])
+        return arr
+
+    def gaborish(self, planes, weights):
+        h, w = planes[0].shape
+        wts = (ctypes.c_float * 6)(*[float(x) for row in weights for x in row])
+        self._check(self._L.jxlb_gaborish(self._h, self._plane_ptrs(planes), w, h, planes[0].stride(0), wts))
+
+    def epf(self, planes, sigma, params: EpfParams):
+        h, w = planes[0].shape
+        sp = int(sigma.data_ptr()) if sigma is not None else None
+        ss = sigma.stride(0) if sigma is not None else 0
+        self._check(self._L.jxlb_epf(self._h, self._plane_ptrs(planes), w, h, planes[0].stride(0), sp, ss, ctypes.byref(params)))
+
+    def xyb_to_rgb(self, planes, opsin_bias, inv_matrix, intensity_target=255.0, srgb_tf=True):
+        h, w = planes[0].shape
+        ob = (ctypes.c_float * 3)(*opsin_bias)
+        m = (ctypes.c_float * 9)(*inv_matrix)
+        self._check(self._L.jxlb_xyb_to_rgb(self._h, self._plane_ptrs(planes), w, h, planes[0].stride(0), ob, m,
+                                            float(intensity_target), int(srgb_tf)))
+
+    def squeeze_inverse(self, avg, res, out, horizontal):
+        self._check(self._L.jxlb_squeeze_inverse(self._h, int(avg.data_ptr()), avg.shape[1], avg.shape[0], avg.stride(0),
+                                                 int(res.data_ptr()), res.shape[1], res.shape[0], max(res.stride(0), 1),
+                                                 int(out.data_ptr()), out.stride(0), int(horizontal)))
+
+    def rct_inverse(self, planes, rct_type):
+        h, w = planes[0].shape
+        self._check(self._L.jxlb_rct_inverse(self._h, self._plane_ptrs(planes), w, h, planes[0].stride(0), rct_type))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.jxlb_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Render:
+    """Result of JxlImage.render_frame(): planar f32 channels (crates/jxl-oxide/src/lib.rs:1080-1216)."""
+
+    def __init__(self, planar, num_color, is_vardct):
+        self._planar = planar
+        self.num_color = num_color
+        self.is_vardct = is_vardct
+
+    def image_planar(self):
+        return self._planar
+
+    def color_channels(self):
+        return self._planar[: self.num_color]
+
+    def extra_channels(self):
+        return self._planar[self.num_color:]
+
+
+class JxlImage:
+    """Mirror of jxl_oxide::JxlImage for the decode hot path."""
+
+    def __init__(self, data: bytes, device=0, output_colour=0):
+        self._dec = Decoder(device)
+        self._dec.decode(data, output_colour=output_colour)
+        info = self._dec.image_info()
+        self.width, self.height = info.width, info.height
+        self.bits_per_sample = info.bits_per_sample
+        self.num_extra_channels = info.num_extra_channels
+        self.xyb_encoded = bool(info.xyb_encoded)
+
+    @classmethod
+    def read(cls, data: bytes, **kw):
+        return cls(data, **kw)
+
+    @classmethod
+    def open(cls, path, **kw):
+        with open(path, "rb") as f:
+            return cls(f.read(), **kw)
+
+    def num_loaded_keyframes(self):
+        return self._dec.num_frames()
+
+    def render_frame(self, keyframe_index=0):
+        info = self._dec.frame_info(keyframe_index)
+        return Render(self._dec.frame_planar(keyframe_index), info.num_color, bool(info.is_vardct))
+
+    @property
+    def decoder(self):
+        return self._dec

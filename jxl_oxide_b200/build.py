@@ -1,0 +1,50 @@
+"""Builds libjxlb200.so (sm_100a) in-tree with nvcc. No JIT cache: the .so travels with the repo snapshot."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libjxlb200.so")
+
+SOURCES = [
+    "capi.cu", "cuda_backend.cu",
+    "kernels/modular.cu", "kernels/vardct.cu", "kernels/filters.cu",
+    "host/entropy.cc", "host/headers.cc", "host/modular_syntax.cc", "host/frame_syntax.cc", "host/planner.cc",
+]
+
+# -fmad=false: the reference's generic float path never contracts a*b+c (SimdVector::muladd is
+# mul+add unless built with +fma, crates/jxl-grid/src/simd.rs:177-199); kernels call __fmaf_rn
+# exactly where the reference calls mul_add.
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fno-fast-math,-pthread", "--shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    for root, _, files in os.walk(CSRC):
+        for f in files:
+            if os.path.getmtime(os.path.join(root, f)) > t:
+                return True
+    inc = os.path.join(os.path.dirname(HERE), "include", "jxlb200.h")
+    return os.path.getmtime(inc) > t
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT, "-lcudart"]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd, cwd=CSRC)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(OUT)

@@ -1,0 +1,270 @@
+// extern "C" boundary of libjxlb200.so — see include/jxlb200.h for the contract.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/jxlb200.h"
+#include "cuda_backend.h"
+#include "host/planner.h"
+
+using namespace jxlb;
+
+struct jxlb_decoder {
+  std::unique_ptr<CudaBackend> be;
+  DecodeResult res;
+  bool have_result = false;
+  std::string error;
+  std::vector<uint8_t> codestream;
+};
+
+namespace {
+
+template <typename F>
+int32_t guarded(jxlb_decoder* dec, F f) {
+  try {
+    f();
+    return JXLB_OK;
+  } catch (const Error& e) {
+    if (dec) dec->error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    if (dec) dec->error = e.what();
+    return JXLB_ERR_INVALID_ARG;
+  }
+}
+
+void release(jxlb_decoder* dec) {
+  if (!dec->have_result) return;
+  for (DecodedFrame& f : dec->res.frames)
+    for (View& v : f.channels) dec->be->free_plane(v.plane);
+  dec->res = DecodeResult();
+  dec->have_result = false;
+}
+
+DevView raw_view(void* p, uint32_t w, uint32_t h, uint32_t stride) {
+  DevView v;
+  v.ptr = p;
+  v.w = w;
+  v.h = h;
+  v.stride = stride;
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t jxlb_decoder_create(int32_t device, jxlb_decoder** out) {
+  if (!out) return JXLB_ERR_INVALID_ARG;
+  *out = nullptr;
+  auto dec = std::make_unique<jxlb_decoder>();
+  try {
+    dec->be.reset(new CudaBackend(device));
+  } catch (const Error& e) {
+    return e.code;
+  }
+  *out = dec.release();
+  return JXLB_OK;
+}
+
+void jxlb_decoder_destroy(jxlb_decoder* dec) { delete dec; }
+
+const char* jxlb_last_error(const jxlb_decoder* dec) { return dec ? dec->error.c_str() : "null decoder"; }
+
+int32_t jxlb_decode(jxlb_decoder* dec, const uint8_t* data, size_t size, const jxlb_options* opt) {
+  if (!dec || !data) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    release(dec);
+    dec->codestream = extract_codestream(data, size);
+    DecodeOptions o;
+    if (opt) {
+      o.output_colour = opt->output_colour;
+      if (opt->max_frames) o.max_frames = opt->max_frames;
+    }
+    dec->res = decode_codestream(*dec->be, dec->codestream.data(), dec->codestream.size(), o);
+    dec->have_result = true;
+  });
+}
+
+int32_t jxlb_image_get_info(const jxlb_decoder* dec, jxlb_image_info* info) {
+  if (!dec || !info || !dec->have_result) return JXLB_ERR_INVALID_ARG;
+  const ImageHeader& ih = dec->res.image_header;
+  info->width = ih.width;
+  info->height = ih.height;
+  info->bits_per_sample = ih.bit_depth.bits_per_sample;
+  info->num_extra_channels = uint32_t(ih.ec_info.size());
+  info->xyb_encoded = ih.xyb_encoded;
+  info->grayscale = ih.grayscale();
+  info->orientation = ih.orientation;
+  return JXLB_OK;
+}
+
+int32_t jxlb_num_frames(const jxlb_decoder* dec) { return (dec && dec->have_result) ? int32_t(dec->res.frames.size()) : 0; }
+
+int32_t jxlb_frame_get_info(const jxlb_decoder* dec, int32_t frame, jxlb_frame_info* info) {
+  if (!dec || !info || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return JXLB_ERR_INVALID_ARG;
+  const DecodedFrame& f = dec->res.frames[frame];
+  info->width = f.width;
+  info->height = f.height;
+  info->num_channels = uint32_t(f.channels.size());
+  info->num_color = f.num_color;
+  info->is_vardct = f.header.encoding == Encoding::kVarDct;
+  info->duration = f.header.duration;
+  return JXLB_OK;
+}
+
+int32_t jxlb_frame_channel_to_host(jxlb_decoder* dec, int32_t frame, int32_t channel, float* dst, size_t dst_stride) {
+  if (!dec || !dst || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    const DecodedFrame& f = dec->res.frames[frame];
+    JXLB_CHECK(channel >= 0 && size_t(channel) < f.channels.size(), kErrInvalidArg, "channel out of range");
+    const View& v = f.channels[channel];
+    JXLB_CHECK(dst_stride >= v.w, kErrInvalidArg, "dst_stride too small");
+    DevView d = dec->be->dev_view(v);
+    cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h,
+                                      cudaMemcpyDeviceToHost, dec->be->stream());
+    JXLB_CHECK(e == cudaSuccess, kErrCuda, cudaGetErrorString(e));
+    dec->be->sync();
+  });
+}
+
+int32_t jxlb_frame_channel_device(jxlb_decoder* dec, int32_t frame, int32_t channel, float** dptr, uint32_t* stride) {
+  if (!dec || !dptr || !stride || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    const DecodedFrame& f = dec->res.frames[frame];
+    JXLB_CHECK(channel >= 0 && size_t(channel) < f.channels.size(), kErrInvalidArg, "channel out of range");
+    DevView d = dec->be->dev_view(f.channels[channel]);
+    *dptr = static_cast<float*>(d.ptr);
+    *stride = d.stride;
+  });
+}
+
+int32_t jxlb_release_frames(jxlb_decoder* dec) {
+  if (!dec) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] { release(dec); });
+}
+
+int32_t jxlb_sync(jxlb_decoder* dec) {
+  if (!dec) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] { dec->be->sync(); });
+}
+
+uint64_t jxlb_launch_count(const jxlb_decoder* dec) { return dec ? dec->be->launches : 0; }
+
+int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on) {
+  if (!dec) return JXLB_ERR_INVALID_ARG;
+  dec->be->capture = on != 0;
+  return JXLB_OK;
+}
+
+int32_t jxlb_stage_count(const jxlb_decoder* dec, const char* name) {
+  if (!dec || !name) return 0;
+  auto it = dec->be->stages.find(name);
+  return it == dec->be->stages.end() ? 0 : int32_t(it->second.size());
+}
+
+int32_t jxlb_stage_get(const jxlb_decoder* dec, const char* name, int32_t idx, uint32_t* width, uint32_t* height, uint32_t* out) {
+  if (!dec || !name || !width || !height) return JXLB_ERR_INVALID_ARG;
+  auto it = dec->be->stages.find(name);
+  if (it == dec->be->stages.end() || idx < 0 || size_t(idx) >= it->second.size()) return JXLB_ERR_INVALID_ARG;
+  const auto& dims = dec->be->stage_dims.at(name)[idx];
+  *width = dims.first;
+  *height = dims.second;
+  if (out) std::memcpy(out, it->second[idx].data(), it->second[idx].size() * 4);
+  return JXLB_OK;
+}
+
+int32_t jxlb_gaborish(jxlb_decoder* dec, float* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                      const float weights[6]) {
+  if (!dec || !planes || !weights) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    cudaStream_t s = dec->be->stream();
+    for (int c = 0; c < 3; ++c) {
+      float* tmp = nullptr;
+      JXLB_CHECK(cudaMallocAsync(&tmp, size_t(stride) * height * 4, s) == cudaSuccess, kErrCuda, "cudaMallocAsync failed");
+      launch_gaborish(raw_view(planes[c], width, height, stride), raw_view(tmp, width, height, stride), weights[c * 2],
+                      weights[c * 2 + 1], s);
+      launch_copy_rect(raw_view(tmp, width, height, stride), raw_view(planes[c], width, height, stride), s);
+      cudaFreeAsync(tmp, s);
+      dec->be->launches += 2;
+    }
+  });
+}
+
+int32_t jxlb_epf(jxlb_decoder* dec, float* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                 const float* sigma, uint32_t sigma_stride, const jxlb_epf_params* params) {
+  if (!dec || !planes || !params) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    cudaStream_t s = dec->be->stream();
+    DevView cur[3], alt[3];
+    float* tmp[3];
+    for (int c = 0; c < 3; ++c) {
+      JXLB_CHECK(cudaMallocAsync(&tmp[c], size_t(stride) * height * 4, s) == cudaSuccess, kErrCuda, "cudaMallocAsync failed");
+      cur[c] = raw_view(planes[c], width, height, stride);
+      alt[c] = raw_view(tmp[c], width, height, stride);
+    }
+    DevEpfParams dp;
+    for (int c = 0; c < 3; ++c) dp.channel_scale[c] = params->channel_scale[c];
+    dp.pass0_sigma_scale = params->pass0_sigma_scale;
+    dp.pass2_sigma_scale = params->pass2_sigma_scale;
+    dp.border_sad_mul = params->border_sad_mul;
+    dp.sigma_for_modular = params->sigma_for_modular;
+    bool in_alt = false;
+    auto run = [&](int step) {
+      launch_epf_step(in_alt ? alt : cur, in_alt ? cur : alt, sigma, sigma_stride, dp, step, s);
+      dec->be->launches++;
+      in_alt = !in_alt;
+    };
+    if (params->iters == 3) run(0);
+    if (params->iters >= 1) run(1);
+    if (params->iters >= 2) run(2);
+    for (int c = 0; c < 3; ++c) {
+      if (in_alt) launch_copy_rect(alt[c], cur[c], s);
+      cudaFreeAsync(tmp[c], s);
+    }
+  });
+}
+
+int32_t jxlb_xyb_to_rgb(jxlb_decoder* dec, float* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                        const float opsin_bias[3], const float inv_matrix[9], float intensity_target, int32_t srgb_tf) {
+  if (!dec || !planes || !opsin_bias || !inv_matrix) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    DevColorParams p;
+    for (int i = 0; i < 3; ++i) {
+      p.opsin_bias[i] = opsin_bias[i];
+      p.cbrt_opsin_bias[i] = cbrtf(opsin_bias[i]);
+    }
+    for (int i = 0; i < 9; ++i) p.matrix[i] = inv_matrix[i];
+    p.itscale = 255.0f / intensity_target;
+    p.apply_srgb_tf = srgb_tf;
+    launch_xyb_to_rgb(raw_view(planes[0], width, height, stride), raw_view(planes[1], width, height, stride),
+                      raw_view(planes[2], width, height, stride), p, dec->be->stream());
+    dec->be->launches++;
+  });
+}
+
+int32_t jxlb_squeeze_inverse(jxlb_decoder* dec, const int32_t* avg, uint32_t avg_w, uint32_t avg_h, uint32_t avg_stride,
+                             const int32_t* res, uint32_t res_w, uint32_t res_h, uint32_t res_stride, int32_t* out,
+                             uint32_t out_stride, int32_t horizontal) {
+  if (!dec || !avg || !out) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    uint32_t ow = horizontal ? avg_w + res_w : avg_w, oh = horizontal ? avg_h : avg_h + res_h;
+    launch_squeeze_inverse(raw_view(const_cast<int32_t*>(avg), avg_w, avg_h, avg_stride),
+                           raw_view(const_cast<int32_t*>(res), res_w, res_h, res_stride), raw_view(out, ow, oh, out_stride),
+                           horizontal != 0, dec->be->stream());
+    dec->be->launches++;
+  });
+}
+
+int32_t jxlb_rct_inverse(jxlb_decoder* dec, int32_t* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
+                         uint32_t rct_type) {
+  if (!dec || !planes) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    launch_rct_inverse(raw_view(planes[0], width, height, stride), raw_view(planes[1], width, height, stride),
+                       raw_view(planes[2], width, height, stride), rct_type, dec->be->stream());
+    dec->be->launches++;
+  });
+}
+
+}  // extern "C"

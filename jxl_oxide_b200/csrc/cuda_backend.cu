@@ -1,0 +1,600 @@
+// See cuda_backend.h.
+#include "cuda_backend.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace jxlb {
+
+void upload_sec_large(const float* host224);  // kernels/vardct.cu
+
+#define CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t err__ = (expr);                                                                       \
+    if (err__ != cudaSuccess)                                                                         \
+      fail(kErrCuda, std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " #expr);        \
+  } while (0)
+
+CudaBackend::CudaBackend(int device) : device_(device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    fail(kErrCuda, "no CUDA device available: the jxl_oxide_b200 hot path has no CPU fallback");
+  CUDA_CHECK(cudaSetDevice(device_));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+}
+
+CudaBackend::~CudaBackend() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (auto& kv : planes_) cudaFree(kv.second.ptr);
+  for (void* p : temps_) cudaFree(p);
+  if (d_codestream_) cudaFree(d_codestream_);
+  if (d_natural_orders_) cudaFree(d_natural_orders_);
+  if (d_dequant_) cudaFree(d_dequant_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void* CudaBackend::dmalloc(size_t bytes) {
+  void* p = nullptr;
+  CUDA_CHECK(cudaSetDevice(device_));
+  CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream_));
+  return p;
+}
+void CudaBackend::dfree(void* p) {
+  if (p) CUDA_CHECK(cudaFreeAsync(p, stream_));
+}
+void* CudaBackend::upload_temp(const void* src, size_t bytes) {
+  void* p = dmalloc(bytes);
+  temps_.push_back(p);
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, stream_));
+  return p;
+}
+void CudaBackend::release_temps() {
+  for (void* p : temps_) dfree(p);
+  temps_.clear();
+}
+void CudaBackend::sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+
+void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  size_t need = ((size + 7) & ~size_t(7)) + 32;  // zero padding for the 64-bit bit reader
+  if (need > codestream_cap_) {
+    if (d_codestream_) CUDA_CHECK(cudaFree(d_codestream_));
+    CUDA_CHECK(cudaMalloc(&d_codestream_, need));
+    codestream_cap_ = need;
+  }
+  CUDA_CHECK(cudaMemsetAsync(d_codestream_, 0, need, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(d_codestream_, data, size, cudaMemcpyHostToDevice, stream_));
+  ensure_static_tables();
+}
+
+void CudaBackend::new_frame() {
+  cached_hfg_ = nullptr;
+  if (d_dequant_) {
+    dfree(d_dequant_);
+    d_dequant_ = nullptr;
+  }
+}
+
+void CudaBackend::ensure_static_tables() {
+  if (!d_natural_orders_) {
+    std::vector<uint32_t> all;
+    for (uint32_t id = 0; id < 13; ++id) {
+      natural_order_offset_[id] = uint32_t(all.size());
+      std::vector<uint32_t> o = natural_order(id);
+      all.insert(all.end(), o.begin(), o.end());
+    }
+    CUDA_CHECK(cudaMalloc(&d_natural_orders_, all.size() * 4));
+    CUDA_CHECK(cudaMemcpy(d_natural_orders_, all.data(), all.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (!sec_uploaded_) {
+    // sec_half for n = 64, 128, 256 (dct_common.rs:57-67): f32 arithmetic with libm cosf
+    float tab[224];
+    size_t off = 0;
+    for (int i = 0; i < 3; ++i) {
+      size_t n = size_t(64) << i;
+      for (size_t k = 0; k < n / 2; ++k) {
+        float theta = float(2 * k + 1) / float(2 * n) * 3.14159265358979323846f;
+        tab[off + k] = (1.0f / cosf(theta)) / 2.0f;
+      }
+      off += n / 2;
+    }
+    upload_sec_large(tab);
+    sec_uploaded_ = true;
+  }
+}
+
+int CudaBackend::alloc_plane(uint32_t w, uint32_t h, bool zero) {
+  PlaneRec r;
+  r.w = w;
+  r.h = h;
+  size_t bytes = size_t(w) * h * 4;
+  r.ptr = dmalloc(bytes);
+  if (zero) CUDA_CHECK(cudaMemsetAsync(r.ptr, 0, bytes, stream_));
+  int id = next_id_++;
+  planes_[id] = r;
+  return id;
+}
+
+void CudaBackend::free_plane(int id) {
+  auto it = planes_.find(id);
+  if (it == planes_.end()) return;
+  dfree(it->second.ptr);
+  planes_.erase(it);
+}
+
+DevView CudaBackend::dev_view(const View& v) const {
+  DevView d;
+  d.ptr = nullptr;
+  d.stride = 0;
+  d.w = v.w;
+  d.h = v.h;
+  if (v.plane >= 0) {
+    const PlaneRec& p = planes_.at(v.plane);
+    d.ptr = static_cast<uint32_t*>(p.ptr) + size_t(v.y0) * p.w + v.x0;
+    d.stride = p.w;
+  }
+  return d;
+}
+
+void CudaBackend::download_rect(const View& v, void* dst) {
+  if (!v.w || !v.h) return;
+  DevView d = dev_view(v);
+  CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(v.w) * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h,
+                               cudaMemcpyDeviceToHost, stream_));
+  sync();
+}
+
+void CudaBackend::copy_rect(const View& src, const View& dst) {
+  launch_copy_rect(dev_view(src), dev_view(dst), stream_);
+  ++launches;
+}
+
+void CudaBackend::stage_marker(const char* name, const View* views, int n) {
+  if (!capture) return;
+  auto& out = stages[name];
+  auto& dims = stage_dims[name];
+  out.clear();
+  dims.clear();
+  for (int i = 0; i < n; ++i) {
+    std::vector<uint32_t> buf(size_t(views[i].w) * views[i].h);
+    download_rect(views[i], buf.data());
+    out.push_back(std::move(buf));
+    dims.push_back({views[i].w, views[i].h});
+  }
+}
+
+DevEntropyCode CudaBackend::upload_code(const EntropyCode& c) {
+  DevEntropyCode d;
+  std::memset(&d, 0, sizeof(d));
+  d.cluster_map = static_cast<const uint8_t*>(upload_temp(c.cluster_map.data(), c.cluster_map.size()));
+  std::vector<uint32_t> cfg;
+  for (const HybridUintConfig& h : c.configs) cfg.push_back(h.packed());
+  d.configs = static_cast<const uint32_t*>(upload_temp(cfg.data(), cfg.size() * 4));
+  d.log_alphabet_size = c.log_alphabet_size;
+  d.use_prefix = c.use_prefix ? 1 : 0;
+  if (c.use_prefix) {
+    d.prefix = static_cast<const uint32_t*>(upload_temp(c.prefix_table.data(), c.prefix_table.size() * 4));
+    std::vector<uint32_t> meta;
+    for (const PrefixMeta& m : c.prefix_meta) {
+      meta.push_back(m.table_offset);
+      meta.push_back(m.root_bits);
+    }
+    d.prefix_meta = static_cast<const uint32_t*>(upload_temp(meta.data(), meta.size() * 4));
+  } else {
+    d.ans = static_cast<const uint64_t*>(upload_temp(c.ans_table.data(), c.ans_table.size() * 8));
+  }
+  d.lz77_enabled = c.lz77_enabled ? 1 : 0;
+  d.lz77_min_symbol = c.lz77_min_symbol;
+  d.lz77_min_length = c.lz77_min_length;
+  d.lz_len_conf = c.lz_len_conf.packed();
+  d.lz_dist_cluster = c.cluster_map.empty() ? 0 : c.cluster_map.back();
+  return d;
+}
+
+namespace {
+const char* dev_status_message(int s) {
+  switch (s) {
+    case kDevBadStream: return "invalid entropy-coded stream (ANS final state / LZ77)";
+    case kDevOverrun: return "entropy-coded stream reads past the end of its section";
+    case kDevInvalid: return "semantic validation of a decoded stream failed";
+    default: return "unknown device decode error";
+  }
+}
+bool tree_uses_wp(const MaTree& t) {
+  for (const MaNode& n : t.nodes) {
+    if (n.property == 15) return true;
+    if (n.property < 0 && (n.a & 0xff) == 6) return true;
+  }
+  return false;
+}
+}  // namespace
+
+void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
+  if (jobs.empty()) return;
+  struct TreeDev {
+    const MaNode* nodes;
+    DevEntropyCode code;
+    bool wp;
+  };
+  std::map<const MaTree*, TreeDev> trees;
+  std::vector<DevModularJob> djobs(jobs.size());
+  std::vector<DevChannel> dchans;
+  for (size_t i = 0; i < jobs.size(); ++i) {
+    const ModularStreamJob& j = jobs[i];
+    auto it = trees.find(j.tree);
+    if (it == trees.end()) {
+      TreeDev td;
+      td.nodes = static_cast<const MaNode*>(upload_temp(j.tree->nodes.data(), j.tree->nodes.size() * sizeof(MaNode)));
+      td.code = upload_code(j.tree->code);
+      td.wp = tree_uses_wp(*j.tree);
+      it = trees.emplace(j.tree, td).first;
+    }
+    DevModularJob& d = djobs[i];
+    std::memset(&d, 0, sizeof(d));
+    d.bit_pos = j.bit_pos;
+    d.bit_limit = j.bit_limit;
+    d.tree = it->second.nodes;
+    d.code = it->second.code;
+    const WpHeader& w = j.wp;
+    const uint32_t wpv[11] = {w.p1, w.p2, w.p3a, w.p3b, w.p3c, w.p3d, w.p3e, w.w[0], w.w[1], w.w[2], w.w[3]};
+    std::memcpy(d.wp, wpv, sizeof(wpv));
+    d.stream_index = j.stream_index;
+    d.first_channel = uint32_t(dchans.size());
+    d.num_channels = uint32_t(j.channels.size());
+    uint32_t max_w = 0;
+    uint64_t samples = 0;
+    for (const ModularChannelTarget& c : j.channels) {
+      DevView v = dev_view(c.view);
+      dchans.push_back({static_cast<int32_t*>(v.ptr), v.stride, c.view.w, c.view.h, c.hshift, c.vshift});
+      max_w = std::max(max_w, c.view.w);
+      samples += uint64_t(c.view.w) * c.view.h;
+    }
+    d.dist_multiplier = max_w;
+    d.use_wp = it->second.wp ? 1 : 0;
+    if (d.use_wp && max_w) {
+      d.wp_scratch = static_cast<int32_t*>(dmalloc(size_t(max_w) * 5 * 4));
+      temps_.push_back(d.wp_scratch);
+    }
+    if (d.code.lz77_enabled) {
+      size_t n = size_t(std::min<uint64_t>(1u << 20, std::max<uint64_t>(samples, 1)));
+      d.lz_window = static_cast<uint32_t*>(dmalloc(n * 4));
+      temps_.push_back(d.lz_window);
+    }
+  }
+  const DevModularJob* d_jobs = static_cast<const DevModularJob*>(upload_temp(djobs.data(), djobs.size() * sizeof(DevModularJob)));
+  const DevChannel* d_chans = static_cast<const DevChannel*>(upload_temp(dchans.data(), dchans.size() * sizeof(DevChannel)));
+  uint64_t* d_end = static_cast<uint64_t*>(dmalloc(jobs.size() * 8));
+  int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
+  temps_.push_back(d_end);
+  temps_.push_back(d_status);
+  launch_modular_decode(d_codestream_, d_jobs, d_chans, d_end, d_status, int(jobs.size()), stream_);
+  ++launches;
+  std::vector<uint64_t> end(jobs.size());
+  std::vector<int> status(jobs.size());
+  CUDA_CHECK(cudaMemcpyAsync(end.data(), d_end, jobs.size() * 8, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
+  sync();
+  CUDA_CHECK(cudaGetLastError());
+  release_temps();
+  for (size_t i = 0; i < jobs.size(); ++i) {
+    if (status[i] != kDevOk)
+      fail(status[i] == kDevOverrun ? kErrEof : kErrDeviceDecode,
+           std::string("modular stream ") + std::to_string(jobs[i].stream_index) + ": " + dev_status_message(status[i]));
+    jobs[i].end_bit = size_t(end[i]);
+  }
+}
+
+int CudaBackend::squeeze_inverse(const View& avg, const View& res, bool horizontal) {
+  uint32_t ow = horizontal ? avg.w + res.w : avg.w;
+  uint32_t oh = horizontal ? avg.h : avg.h + res.h;
+  JXLB_CHECK(horizontal ? (res.h == avg.h || res.w == 0) : (res.w == avg.w || res.h == 0), kErrBitstream,
+             "squeeze residual size mismatch");
+  int id = alloc_plane(std::max(ow, 1u), std::max(oh, 1u), false);
+  if (!ow || !oh) return id;
+  View ov{id, 0, 0, ow, oh};
+  launch_squeeze_inverse(dev_view(avg), dev_view(res), dev_view(ov), horizontal, stream_);
+  ++launches;
+  return id;
+}
+
+void CudaBackend::rct_inverse(const View v[3], uint32_t rct_type) {
+  launch_rct_inverse(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), rct_type, stream_);
+  ++launches;
+}
+
+void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t,
+                                  const WpHeader&, uint32_t bit_depth) {
+  JXLB_CHECK(targets.size() <= 4, kErrUnsupported, "palettes with more than 4 channels are not implemented on the device");
+  DevView tv[4];
+  for (size_t i = 0; i < targets.size(); ++i) tv[i] = dev_view(targets[i]);
+  int* d_status = static_cast<int*>(dmalloc(4));
+  CUDA_CHECK(cudaMemsetAsync(d_status, 0, 4, stream_));
+  launch_palette_inverse_simple(dev_view(palette), tv, int(targets.size()), int(t.nb_colours), int(bit_depth),
+                                int(t.nb_deltas), d_status, stream_);
+  ++launches;
+  int status = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, stream_));
+  sync();
+  dfree(d_status);
+  JXLB_CHECK(status == 0, kErrUnsupported, "delta-palette entries are not implemented on the device");
+}
+
+void CudaBackend::int_to_float(const View& v, const BitDepth& d) {
+  launch_int_to_float(dev_view(v), d.bits_per_sample, d.exp_bits, d.float_sample, stream_);
+  ++launches;
+}
+
+void CudaBackend::modular_xyb_to_float(const View yxb[3], const float m[3]) {
+  launch_modular_xyb(dev_view(yxb[0]), dev_view(yxb[1]), dev_view(yxb[2]), m[0], m[1], m[2], stream_);
+  ++launches;
+}
+
+DevFrame CudaBackend::dev_frame(const VarDctState& st) const {
+  DevFrame f;
+  f.width = st.width;
+  f.height = st.height;
+  f.bw = st.bw;
+  f.bh = st.bh;
+  f.cw = st.bw * 8;
+  f.ch = st.bh * 8;
+  f.w64 = (st.width + 63) / 64;
+  for (int c = 0; c < 3; ++c) {
+    f.lf_quant[c] = static_cast<int32_t*>(plane_ptr(st.lf_quant[c]));
+    f.lf[c] = static_cast<float*>(plane_ptr(st.lf[c]));
+    f.coeff[c] = static_cast<uint32_t*>(plane_ptr(st.coeff[c]));
+  }
+  f.x_from_y = static_cast<int32_t*>(plane_ptr(st.x_from_y));
+  f.b_from_y = static_cast<int32_t*>(plane_ptr(st.b_from_y));
+  f.sharpness = static_cast<int32_t*>(plane_ptr(st.sharpness));
+  f.blk_type = static_cast<int32_t*>(plane_ptr(st.blk_type));
+  f.blk_mul = static_cast<int32_t*>(plane_ptr(st.blk_mul));
+  f.epf_sigma = static_cast<float*>(plane_ptr(st.epf_sigma));
+  return f;
+}
+
+void CudaBackend::build_block_info(VarDctState& st, const std::vector<BlockInfoJob>& jobs) {
+  if (jobs.empty()) return;
+  std::vector<DevBlockInfoJob> dj;
+  for (const BlockInfoJob& j : jobs) {
+    const PlaneRec& raw = planes_.at(j.raw_plane);
+    dj.push_back({{j.rect.bx0, j.rect.by0, j.rect.bw, j.rect.bh}, static_cast<const int32_t*>(raw.ptr), raw.w, j.nb_blocks});
+  }
+  const EpfParams& epf = st.fh->restoration_filter.epf;
+  const DevBlockInfoJob* d_jobs = static_cast<const DevBlockInfoJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevBlockInfoJob)));
+  const float* d_lut = static_cast<const float*>(upload_temp(epf.sharp_lut, sizeof(epf.sharp_lut)));
+  int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
+  temps_.push_back(d_status);
+  float quant_mul_base = epf.quant_mul * 65536.0f / float(st.lfg->global_scale);
+  launch_build_block_info(dev_frame(st), d_jobs, int(jobs.size()), quant_mul_base, d_lut, epf.iters > 0 ? 1 : 0, d_status, stream_);
+  ++launches;
+  std::vector<int> status(jobs.size());
+  CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
+  sync();
+  CUDA_CHECK(cudaGetLastError());
+  release_temps();
+  for (int s : status) JXLB_CHECK(s == kDevOk, kErrBitstream, "invalid HfMetadata block layout");
+}
+
+void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
+  if (jobs.empty()) return;
+  const HfBlockContext& hbc = st.lfg->hf_block_ctx;
+  const uint32_t pass = jobs[0].pass_idx;
+  const HfPassSyntax& hp = st.hfg->passes[pass];
+  DevHfParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.code = upload_code(hp.code);
+  // orders: natural (static) unless the pass carries a custom permutation
+  std::vector<uint32_t> custom;
+  bool any_custom = false;
+  for (int id = 0; id < 13; ++id)
+    for (int c = 0; c < 3; ++c) any_custom |= !hp.order[id][c].empty();
+  if (!any_custom) {
+    p.orders = d_natural_orders_;
+    for (int id = 0; id < 13; ++id)
+      for (int c = 0; c < 3; ++c) p.order_offset[id * 3 + c] = natural_order_offset_[id];
+  } else {
+    for (int id = 0; id < 13; ++id)
+      for (int c = 0; c < 3; ++c) {
+        p.order_offset[id * 3 + c] = uint32_t(custom.size());
+        if (hp.order[id][c].empty()) {
+          std::vector<uint32_t> o = natural_order(uint32_t(id));
+          custom.insert(custom.end(), o.begin(), o.end());
+        } else {
+          custom.insert(custom.end(), hp.order[id][c].begin(), hp.order[id][c].end());
+        }
+      }
+    p.orders = static_cast<const uint32_t*>(upload_temp(custom.data(), custom.size() * 4));
+  }
+  p.block_ctx_map = static_cast<const uint8_t*>(upload_temp(hbc.block_ctx_map.data(), hbc.block_ctx_map.size()));
+  std::vector<int32_t> thr;
+  for (int c = 0; c < 3; ++c) {
+    p.num_lf_thr[c] = uint32_t(hbc.lf_thresholds[c].size());
+    thr.insert(thr.end(), hbc.lf_thresholds[c].begin(), hbc.lf_thresholds[c].end());
+  }
+  thr.push_back(0);
+  p.lf_thresholds = static_cast<const int32_t*>(upload_temp(thr.data(), thr.size() * 4));
+  std::vector<uint32_t> qf = hbc.qf_thresholds;
+  p.num_qf_thr = uint32_t(qf.size());
+  qf.push_back(0);
+  p.qf_thresholds = static_cast<const uint32_t*>(upload_temp(qf.data(), qf.size() * 4));
+  p.num_block_clusters = hbc.num_block_clusters;
+  p.num_hf_presets = st.hfg->num_hf_presets;
+  p.coeff_shift = pass < st.fh->passes.shift.size() ? st.fh->passes.shift[pass] : 0;
+  p.group_dim_blocks = st.group_dim / 8;
+  p.groups_per_row = st.groups_per_row;
+  std::vector<DevHfJob> dj;
+  for (const HfGroupJob& j : jobs) dj.push_back({j.bit_pos, j.bit_limit, j.group_idx});
+  const DevHfJob* d_jobs = static_cast<const DevHfJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevHfJob)));
+  uint64_t* d_end = static_cast<uint64_t*>(dmalloc(jobs.size() * 8));
+  int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
+  temps_.push_back(d_end);
+  temps_.push_back(d_status);
+  launch_decode_hf(d_codestream_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), stream_);
+  ++launches;
+  std::vector<uint64_t> end(jobs.size());
+  std::vector<int> status(jobs.size());
+  CUDA_CHECK(cudaMemcpyAsync(end.data(), d_end, jobs.size() * 8, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
+  sync();
+  CUDA_CHECK(cudaGetLastError());
+  release_temps();
+  for (size_t i = 0; i < jobs.size(); ++i) {
+    if (status[i] != kDevOk)
+      fail(status[i] == kDevOverrun ? kErrEof : kErrDeviceDecode,
+           std::string("HF group ") + std::to_string(jobs[i].group_idx) + ": " + dev_status_message(status[i]));
+    jobs[i].end_bit = size_t(end[i]);
+  }
+}
+
+void CudaBackend::lf_dequant(VarDctState& st, const std::vector<LfDequantJob>& jobs) {
+  std::vector<DevLfDequantJob> dj;
+  for (const LfDequantJob& j : jobs)
+    dj.push_back({{j.rect.bx0, j.rect.by0, j.rect.bw, j.rect.bh}, {j.scale[0], j.scale[1], j.scale[2]}});
+  const DevLfDequantJob* d = static_cast<const DevLfDequantJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevLfDequantJob)));
+  launch_lf_dequant(dev_frame(st), d, int(dj.size()), stream_);
+  ++launches;
+}
+
+void CudaBackend::lf_chroma_from_luma(VarDctState& st) {
+  const LfGlobalSyntax& g = *st.lfg;
+  int32_t x_factor = int32_t(g.x_factor_lf) - 128, b_factor = int32_t(g.b_factor_lf) - 128;
+  float kx = g.base_correlation_x + (float(x_factor) / float(g.colour_factor));
+  float kb = g.base_correlation_b + (float(b_factor) / float(g.colour_factor));
+  launch_lf_cfl(dev_frame(st), kx, kb, stream_);
+  ++launches;
+}
+
+void CudaBackend::lf_adaptive_smoothing(VarDctState& st) {
+  const LfGlobalSyntax& g = *st.lfg;
+  uint64_t scale_inv = uint64_t(g.global_scale) * g.quant_lf;
+  float lf_x = float(512.0 * double(g.m_x_lf) / double(scale_inv));
+  float lf_y = float(512.0 * double(g.m_y_lf) / double(scale_inv));
+  float lf_b = float(512.0 * double(g.m_b_lf) / double(scale_inv));
+  float* tmp[3];
+  for (int c = 0; c < 3; ++c) tmp[c] = static_cast<float*>(dmalloc(size_t(st.bw) * st.bh * 4));
+  launch_lf_smooth(dev_frame(st), tmp, lf_x, lf_y, lf_b, stream_);
+  ++launches;
+  for (int c = 0; c < 3; ++c) {  // swap the smoothed planes in
+    PlaneRec& r = planes_.at(st.lf[c]);
+    dfree(r.ptr);
+    r.ptr = tmp[c];
+  }
+}
+
+void CudaBackend::hf_dequant_cfl(VarDctState& st) {
+  if (cached_hfg_ != st.hfg) {
+    std::vector<float> all;
+    std::memset(&dequant_params_, 0, sizeof(dequant_params_));
+    for (int set = 0; set < 17; ++set)
+      for (int c = 0; c < 3; ++c)
+        for (int tr = 0; tr < 2; ++tr) {
+          const std::vector<float>& m = tr ? st.hfg->dequant.matrices_tr[set][c] : st.hfg->dequant.matrices[set][c];
+          dequant_params_.matrix_offset[(set * 3 + c) * 2 + tr] = uint32_t(all.size());
+          all.insert(all.end(), m.begin(), m.end());
+        }
+    if (d_dequant_) dfree(d_dequant_);
+    d_dequant_ = static_cast<float*>(dmalloc(all.size() * 4));
+    CUDA_CHECK(cudaMemcpyAsync(d_dequant_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, stream_));
+    cached_hfg_ = st.hfg;
+  }
+  DevDequantParams p = dequant_params_;
+  p.matrices = d_dequant_;
+  const OpsinInverseMatrix& oim = st.ih->opsin_inverse_matrix;
+  for (int c = 0; c < 3; ++c) p.quant_bias[c] = oim.quant_bias[c];
+  p.quant_bias_numerator = oim.quant_bias_numerator;
+  p.qm_scale[0] = powi_f32(0.8f, int32_t(st.fh->x_qm_scale) - 2);
+  p.qm_scale[1] = 1.0f;
+  p.qm_scale[2] = powi_f32(0.8f, int32_t(st.fh->b_qm_scale) - 2);
+  p.global_scale = float(st.lfg->global_scale);
+  p.base_correlation_x = st.lfg->base_correlation_x;
+  p.base_correlation_b = st.lfg->base_correlation_b;
+  p.colour_factor = float(st.lfg->colour_factor);
+  launch_hf_dequant_cfl(dev_frame(st), p, stream_);
+  ++launches;
+}
+
+void CudaBackend::hf_transform(VarDctState& st) {
+  launch_hf_transform(dev_frame(st), nullptr, nullptr, stream_);
+  ++launches;
+}
+
+void CudaBackend::gaborish(const View v[3], const float weights[3][2]) {
+  for (int c = 0; c < 3; ++c) {
+    PlaneRec& r = planes_.at(v[c].plane);
+    JXLB_CHECK(v[c].x0 == 0 && v[c].y0 == 0, kErrInvalidArg, "gaborish expects a top-left anchored view");
+    void* out = dmalloc(size_t(r.w) * r.h * 4);
+    DevView in = dev_view(v[c]);
+    DevView ov = in;
+    ov.ptr = out;
+    launch_gaborish(in, ov, weights[c][0], weights[c][1], stream_);
+    ++launches;
+    dfree(r.ptr);
+    r.ptr = out;
+  }
+}
+
+void CudaBackend::epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) {
+  DevView cur[3], alt[3];
+  void* alt_ptr[3];
+  for (int c = 0; c < 3; ++c) {
+    PlaneRec& r = planes_.at(v[c].plane);
+    JXLB_CHECK(v[c].x0 == 0 && v[c].y0 == 0, kErrInvalidArg, "epf expects a top-left anchored view");
+    alt_ptr[c] = dmalloc(size_t(r.w) * r.h * 4);
+    cur[c] = dev_view(v[c]);
+    alt[c] = cur[c];
+    alt[c].ptr = alt_ptr[c];
+  }
+  const float* d_sigma = nullptr;
+  uint32_t sigma_stride = 0;
+  if (!sigma_is_constant) {
+    const PlaneRec& s = planes_.at(sigma.plane);
+    d_sigma = static_cast<const float*>(s.ptr);
+    sigma_stride = s.w;
+  }
+  DevEpfParams dp;
+  for (int c = 0; c < 3; ++c) dp.channel_scale[c] = p.channel_scale[c];
+  dp.pass0_sigma_scale = p.pass0_sigma_scale;
+  dp.pass2_sigma_scale = p.pass2_sigma_scale;
+  dp.border_sad_mul = p.border_sad_mul;
+  dp.sigma_for_modular = p.sigma_for_modular;
+  bool in_alt = false;
+  auto run = [&](int step) {
+    launch_epf_step(in_alt ? alt : cur, in_alt ? cur : alt, d_sigma, sigma_stride, dp, step, stream_);
+    ++launches;
+    in_alt = !in_alt;
+  };
+  if (p.iters == 3) run(0);
+  run(1);
+  if (p.iters >= 2) run(2);
+  for (int c = 0; c < 3; ++c) {
+    PlaneRec& r = planes_.at(v[c].plane);
+    if (in_alt) {
+      dfree(r.ptr);
+      r.ptr = alt_ptr[c];
+    } else {
+      dfree(alt_ptr[c]);
+    }
+  }
+}
+
+void CudaBackend::upsample(View*, uint32_t, uint32_t, const ImageHeader&) {
+  fail(kErrUnsupported, "non-separable upsampling is not implemented yet");
+}
+
+void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
+  DevColorParams d;
+  for (int i = 0; i < 3; ++i) {
+    d.opsin_bias[i] = p.opsin_bias[i];
+    d.cbrt_opsin_bias[i] = p.cbrt_opsin_bias[i];
+  }
+  d.itscale = p.itscale;
+  for (int i = 0; i < 9; ++i) d.matrix[i] = p.matrix[i];
+  d.apply_srgb_tf = p.apply_srgb_tf ? 1 : 0;
+  launch_xyb_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
+  ++launches;
+}
+
+}  // namespace jxlb

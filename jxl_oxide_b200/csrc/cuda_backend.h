@@ -1,0 +1,96 @@
+// CUDA (sm_100a) implementation of the planner's Backend seam: every sample-level stage runs as
+// a kernel on one stream; planes live in HBM for the whole frame. There is no CPU fallback: any
+// CUDA failure raises Error(kErrCuda).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "host/backend.h"
+#include "kernels/kernels.h"
+
+namespace jxlb {
+
+class CudaBackend : public Backend {
+ public:
+  explicit CudaBackend(int device);
+  ~CudaBackend() override;
+
+  void set_codestream(const uint8_t* data, size_t size) override;
+  void new_frame() override;
+  int alloc_plane(uint32_t w, uint32_t h, bool zero) override;
+  void free_plane(int id) override;
+  void download_rect(const View& v, void* dst) override;
+  void copy_rect(const View& src, const View& dst) override;
+  void decode_modular(std::vector<ModularStreamJob>& jobs) override;
+  int squeeze_inverse(const View& avg, const View& residual, bool horizontal) override;
+  void rct_inverse(const View v[3], uint32_t rct_type) override;
+  void palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t, const WpHeader& wp,
+                       uint32_t bit_depth) override;
+  void int_to_float(const View& v, const BitDepth& depth) override;
+  void modular_xyb_to_float(const View yxb[3], const float m_lf_unscaled[3]) override;
+  void build_block_info(VarDctState& st, const std::vector<BlockInfoJob>& jobs) override;
+  void decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) override;
+  void lf_dequant(VarDctState& st, const std::vector<LfDequantJob>& jobs) override;
+  void lf_chroma_from_luma(VarDctState& st) override;
+  void lf_adaptive_smoothing(VarDctState& st) override;
+  void hf_dequant_cfl(VarDctState& st) override;
+  void hf_transform(VarDctState& st) override;
+  void gaborish(const View v[3], const float weights[3][2]) override;
+  void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) override;
+  void upsample(View v[3], uint32_t num_channels, uint32_t factor_log2, const ImageHeader& ih) override;
+  void xyb_to_rgb(const View v[3], const ColorParams& p) override;
+  void stage_marker(const char* name, const View* views, int n) override;
+
+  cudaStream_t stream() const { return stream_; }
+  void sync();
+  void* plane_ptr(int id) const { return planes_.at(id).ptr; }
+  // device pointer + stride (elements) of a view's top-left element
+  DevView dev_view(const View& v) const;
+
+  // test hook: when on, stage_marker() snapshots planes to host memory
+  bool capture = false;
+  std::map<std::string, std::vector<std::vector<uint32_t>>> stages;
+  std::map<std::string, std::vector<std::pair<uint32_t, uint32_t>>> stage_dims;
+  // launch accounting for bench.py ("gpu_launches")
+  uint64_t launches = 0;
+
+ private:
+  struct PlaneRec {
+    void* ptr;
+    uint32_t w, h;
+  };
+  struct DevTable {  // device copy of an EntropyCode
+    DevEntropyCode code;
+    std::vector<void*> allocs;
+  };
+  void* dmalloc(size_t bytes);
+  void dfree(void* p);
+  // copies host bytes to a fresh device buffer (freed at the next `release_temps`)
+  void* upload_temp(const void* src, size_t bytes);
+  void release_temps();
+  DevEntropyCode upload_code(const EntropyCode& c);
+  DevFrame dev_frame(const VarDctState& st) const;
+  void ensure_static_tables();
+
+  int device_;
+  cudaStream_t stream_ = nullptr;
+  uint8_t* d_codestream_ = nullptr;
+  size_t codestream_cap_ = 0;
+  std::map<int, PlaneRec> planes_;
+  int next_id_ = 0;
+  std::vector<void*> temps_;
+  std::vector<std::vector<uint8_t>> host_keep_;  // host staging kept alive until the next sync
+  // static tables
+  uint32_t* d_natural_orders_ = nullptr;
+  uint32_t natural_order_offset_[13];
+  bool sec_uploaded_ = false;
+  // per-frame caches
+  const HfGlobalSyntax* cached_hfg_ = nullptr;
+  float* d_dequant_ = nullptr;
+  DevDequantParams dequant_params_;
+};
+
+}  // namespace jxlb

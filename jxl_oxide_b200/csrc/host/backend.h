@@ -93,6 +93,8 @@ class Backend {
  public:
   virtual ~Backend() {}
   virtual void set_codestream(const uint8_t* data, size_t size) = 0;
+  // Called at the start of every frame: table pointers handed over earlier may be stale now.
+  virtual void new_frame() {}
   // planes
   virtual int alloc_plane(uint32_t w, uint32_t h, bool zero) = 0;
   virtual void free_plane(int id) = 0;

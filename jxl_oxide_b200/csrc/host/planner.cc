@@ -291,6 +291,7 @@ void FramePlanner::setup_gmodular() {
 
 DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_end_byte) {
   BitReader br(cs_, size_, frame_begin_byte * 8);
+  be_.new_frame();
   fh_ = parse_frame_header(br, ih_);
   toc_ = parse_toc(br, fh_);
   *frame_end_byte = toc_.data_begin + toc_.total_size;

@@ -1,0 +1,228 @@
+// Restoration filters and colour on the device: Gaborish 3x3, edge-preserving filter (steps
+// 0/1/2), XYB -> linear sRGB (-> sRGB). Float op order follows the reference's generic path:
+// crates/jxl-render/src/filter/{gabor.rs,epf.rs}, filter/impls/generic/{gabor.rs,epf.rs},
+// crates/jxl-color/src/{xyb.rs:35-60, ciexyz.rs:81-87, tf/srgb.rs:13-48}. Compiled with
+// -fmad=false; fused multiply-add only where the reference uses mul_add.
+#include "kernels.h"
+
+namespace jxlb {
+
+namespace {
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// impls/generic/gabor.rs: the formulas differ between interior rows, top/bottom rows, first/last
+// columns and the degenerate 1-row / 1-column cases; each is reproduced literally.
+__global__ void gaborish_kernel(DevView in, DevView out, float w0, float w1) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int width = int(in.w), height = int(in.h);
+  if (x >= width) return;
+  const float* base = static_cast<const float*>(in.ptr);
+  const float gw = fdiv(1.0f, fadd(fadd(1.0f, fmul(w0, 4.0f)), fmul(w1, 4.0f)));
+  auto at = [&](int xx, int yy) { return base[size_t(yy) * in.stride + xx]; };
+  float res;
+  if (height == 1) {
+    if (width == 1) {
+      res = at(0, 0);
+    } else {
+      const float merged_w0 = fadd(fadd(1.0f, 2.0f), w0);
+      const float merged_w1 = fadd(w0, fmul(2.0f, w1));
+      if (x == 0) res = fmul(fadd(fmul(at(0, 0), fadd(merged_w0, merged_w1)), fmul(at(1, 0), merged_w1)), gw);
+      else if (x == width - 1)
+        res = fmul(fadd(fmul(at(width - 1, 0), fadd(merged_w0, merged_w1)), fmul(at(width - 2, 0), merged_w1)), gw);
+      else res = fmul(fadd(fmul(at(x, 0), merged_w0), fmul(fadd(at(x - 1, 0), at(x + 1, 0)), merged_w1)), gw);
+    }
+  } else if (y == 0 || y == height - 1) {
+    const int ya = (y == 0) ? 1 : height - 2;  // the one adjacent row
+    if (width == 1) {
+      float u = at(0, ya), c = at(0, y);
+      res = fmul(fadd(fmul(c, fadd(fadd(1.0f, fmul(3.0f, w0)), fmul(2.0f, w1))), fmul(u, fadd(w0, fmul(2.0f, w1)))), gw);
+    } else if (x == 0 || x == width - 1) {
+      const int xo = (x == 0) ? 1 : width - 2;
+      float a1 = at(x, ya), a0 = at(xo, ya), c1 = at(x, y), c0 = at(xo, y);
+      res = fmul(fadd(fadd(fmul(c1, fadd(fadd(1.0f, fmul(2.0f, w0)), w1)), fmul(fadd(a1, c0), fadd(w0, w1))), fmul(a0, w1)), gw);
+    } else {
+      float a0 = at(x - 1, ya), a1 = at(x, ya), a2 = at(x + 1, ya);
+      float c0 = at(x - 1, y), c1 = at(x, y), c2 = at(x + 1, y);
+      res = fmul(fadd(fadd(c1, fmul(fadd(fadd(fadd(a1, c0), c1), c2), w0)), fmul(fadd(fadd(fadd(a0, a2), c0), c2), w1)), gw);
+    }
+  } else {
+    if (width == 1) {
+      float t = at(0, y - 1), c = at(0, y), b = at(0, y + 1);
+      float sum_side = fadd(fadd(t, fmul(2.0f, c)), b);
+      float sum_diag = fmul(2.0f, fadd(t, b));
+      res = fmul(fadd(fadd(c, fmul(sum_side, w0)), fmul(sum_diag, w1)), gw);
+    } else if (x == 0 || x == width - 1) {
+      const int xo = (x == 0) ? 1 : width - 2;
+      float t1 = at(x, y - 1), c1 = at(x, y), b1 = at(x, y + 1);
+      float t0 = at(xo, y - 1), c0 = at(xo, y), b0 = at(xo, y + 1);
+      float sum_side = fadd(fadd(fadd(t1, c0), c1), b1);
+      float sum_diag = fadd(fadd(fadd(t0, t1), b0), b1);
+      res = fmul(fadd(fadd(c1, fmul(sum_side, w0)), fmul(sum_diag, w1)), gw);
+    } else {
+      float sum_side = fadd(fadd(fadd(at(x, y - 1), at(x - 1, y)), at(x + 1, y)), at(x, y + 1));
+      float sum_diag = fadd(fadd(fadd(at(x - 1, y - 1), at(x + 1, y - 1)), at(x - 1, y + 1)), at(x + 1, y + 1));
+      res = fmul(fadd(fadd(at(x, y), fmul(sum_side, w0)), fmul(sum_diag, w1)), gw);
+    }
+  }
+  static_cast<float*>(out.ptr)[size_t(y) * out.stride + x] = res;
+}
+
+__device__ __forceinline__ int mirror(int offset, int len) {  // util.rs:376-386
+  for (;;) {
+    if (offset < 0) offset = -(offset + 1);
+    else if (offset >= len) offset = 2 * len - (offset + 1);
+    else return offset;
+  }
+}
+
+__device__ __constant__ const int8_t kKernel1[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};
+__device__ __constant__ const int8_t kKernel2[12][2] = {{0, -2}, {-1, -1}, {0, -1}, {1, -1}, {-2, 0}, {-1, 0},
+                                                        {1, 0},  {2, 0},   {-1, 1}, {0, 1},  {1, 1},  {0, 2}};
+__device__ __constant__ const int8_t kDist0[5][2] = {{0, -1}, {1, 0}, {0, 0}, {-1, 0}, {0, 1}};
+__device__ __constant__ const int8_t kDist1[5][2] = {{0, -1}, {0, 0}, {0, 1}, {-1, 0}, {1, 0}};
+
+struct View3 {
+  DevView v[3];
+};
+
+// epf_row<STEP> (impls/generic/epf.rs:3-204): one thread per pixel, all three channels.
+template <int STEP>
+__global__ void epf_kernel(View3 in, View3 out, const float* __restrict__ sigma, uint32_t sigma_stride, DevEpfParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int width = int(in.v[0].w), height = int(in.v[0].h);
+  if (x >= width || y >= height) return;
+  const float* ch[3] = {static_cast<const float*>(in.v[0].ptr), static_cast<const float*>(in.v[1].ptr),
+                        static_cast<const float*>(in.v[2].ptr)};
+  const size_t stride[3] = {in.v[0].stride, in.v[1].stride, in.v[2].stride};
+  const float sigma_val = sigma ? sigma[size_t(y >> 3) * sigma_stride + (x >> 3)] : p.sigma_for_modular;
+  float o[3];
+  if (sigma_val < 0.3f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = ch[c][size_t(y) * stride[c] + x];
+  } else {
+    const float step_multiplier = STEP == 0 ? p.pass0_sigma_scale : (STEP == 2 ? p.pass2_sigma_scale : 1.0f);
+    const bool is_y_border = ((y + 1) & 6) == 0;
+    float sm;
+    if (is_y_border) sm = fmul(step_multiplier, p.border_sad_mul);
+    else sm = ((x & 7) == 0 || (x & 7) == 7) ? fmul(step_multiplier, p.border_sad_mul) : step_multiplier;
+    const float neg_inv_sigma = fmul(fdiv(fmul(6.6f, fsub(0.70710678118654752440f, 1.0f)), sigma_val), sm);
+    float sum_weights = 1.0f;
+    float sum_channels[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sum_channels[c] = ch[c][size_t(y) * stride[c] + x];
+    constexpr int NK = STEP == 0 ? 12 : 4;
+    constexpr int ND = STEP == 2 ? 1 : 5;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int kx = x + (STEP == 0 ? kKernel2[k][0] : kKernel1[k][0]);
+      const int ky = y + (STEP == 0 ? kKernel2[k][1] : kKernel1[k][1]);
+      float dist = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) {
+          const int ox = STEP == 2 ? 0 : (STEP == 0 ? kDist0[i][0] : kDist1[i][0]);
+          const int oy = STEP == 2 ? 0 : (STEP == 0 ? kDist0[i][1] : kDist1[i][1]);
+          const int ay = mirror(ky + oy, height), ax = mirror(kx + ox, width);
+          const int by = mirror(y + oy, height), bx = mirror(x + ox, width);
+          acc = fadd(acc, fabsf(fsub(ch[c][size_t(ay) * stride[c] + ax], ch[c][size_t(by) * stride[c] + bx])));
+        }
+        dist = fadd(dist, fmul(p.channel_scale[c], acc));
+      }
+      const float weight = fmaxf(fadd(1.0f, fmul(dist, neg_inv_sigma)), 0.0f);
+      sum_weights = fadd(sum_weights, weight);
+      const int my = mirror(ky, height), mx = mirror(kx, width);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sum_channels[c] = fadd(sum_channels[c], fmul(weight, ch[c][size_t(my) * stride[c] + mx]));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = fdiv(sum_channels[c], sum_weights);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) static_cast<float*>(out.v[c].ptr)[size_t(y) * out.v[c].stride + x] = o[c];
+}
+
+__device__ __constant__ const uint8_t kPowUpper[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c,
+                                                       0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
+__device__ __constant__ const uint8_t kPowLower[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68,
+                                                       0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};
+
+__device__ __forceinline__ float linear_to_srgb(float s) {  // tf/srgb.rs:28-47 (scalar path)
+  uint32_t bits = __float_as_uint(s);
+  uint32_t vb = bits & 0x7fffffffu;
+  float v_adj = __uint_as_float((vb | 0x3e800000u) & 0x3effffffu);
+  float pow = 0.059914046f;
+  pow = fsub(fmul(pow, v_adj), 0.10889456f);
+  pow = fadd(fmul(pow, v_adj), 0.107963754f);
+  pow = fadd(fmul(pow, v_adj), 0.018092343f);
+  uint32_t idx = ((vb >> 23) - 118) & 0xf;
+  float mul = __uint_as_float(0x40000000u | (uint32_t(kPowUpper[idx]) << 18) | (uint32_t(kPowLower[idx]) << 10));
+  float av = __uint_as_float(vb);
+  float small = fmul(av, 12.92f);
+  float acc = fsub(fmul(pow, mul), 0.055f);
+  float res = av <= 0.0031308f ? small : acc;
+  return copysignf(res, s);
+}
+
+__global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorParams p) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= vx.w) return;
+  float* px = static_cast<float*>(vx.ptr) + size_t(y) * vx.stride + x;
+  float* py = static_cast<float*>(vy.ptr) + size_t(y) * vy.stride + x;
+  float* pb = static_cast<float*>(vb.ptr) + size_t(y) * vb.stride + x;
+  float xx = *px, yy = *py, bb = *pb;
+  float g_l = fsub(fadd(yy, xx), p.cbrt_opsin_bias[0]);
+  float g_m = fsub(fsub(yy, xx), p.cbrt_opsin_bias[1]);
+  float g_s = fsub(bb, p.cbrt_opsin_bias[2]);
+  float a = fmul(__fmaf_rn(fmul(g_l, g_l), g_l, p.opsin_bias[0]), p.itscale);
+  float b = fmul(__fmaf_rn(fmul(g_m, g_m), g_m, p.opsin_bias[1]), p.itscale);
+  float c = fmul(__fmaf_rn(fmul(g_s, g_s), g_s, p.opsin_bias[2]), p.itscale);
+  const float* m = p.matrix;
+  float o0 = fadd(fadd(fmul(m[0], a), fmul(m[1], b)), fmul(m[2], c));
+  float o1 = fadd(fadd(fmul(m[3], a), fmul(m[4], b)), fmul(m[5], c));
+  float o2 = fadd(fadd(fmul(m[6], a), fmul(m[7], b)), fmul(m[8], c));
+  if (p.apply_srgb_tf) {
+    o0 = linear_to_srgb(o0);
+    o1 = linear_to_srgb(o1);
+    o2 = linear_to_srgb(o2);
+  }
+  *px = o0;
+  *py = o1;
+  *pb = o2;
+}
+
+}  // namespace
+
+void launch_gaborish(DevView in, DevView out, float w0, float w1, cudaStream_t stream) {
+  if (!in.w || !in.h) return;
+  dim3 grid((in.w + 127) / 128, in.h);
+  gaborish_kernel<<<grid, 128, 0, stream>>>(in, out, w0, w1);
+}
+
+void launch_epf_step(const DevView in[3], const DevView out[3], const float* sigma, uint32_t sigma_stride, DevEpfParams p,
+                     int step, cudaStream_t stream) {
+  View3 vi, vo;
+  for (int c = 0; c < 3; ++c) {
+    vi.v[c] = in[c];
+    vo.v[c] = out[c];
+  }
+  if (!vi.v[0].w || !vi.v[0].h) return;
+  dim3 block(32, 8);
+  dim3 grid((vi.v[0].w + 31) / 32, (vi.v[0].h + 7) / 8);
+  if (step == 0) epf_kernel<0><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
+  else if (step == 1) epf_kernel<1><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
+  else epf_kernel<2><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
+}
+
+void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream) {
+  if (!x.w || !x.h) return;
+  dim3 grid((x.w + 127) / 128, x.h);
+  xyb_to_rgb_kernel<<<grid, 128, 0, stream>>>(x, y, b, p);
+}
+
+}  // namespace jxlb

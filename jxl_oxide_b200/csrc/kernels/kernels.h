@@ -1,0 +1,129 @@
+// Launch wrappers for the sm_100a kernels. Plain C++ signatures over raw device pointers so that
+// both the CUDA backend (cuda_backend.cu) and the stage-level C ABI (capi.cu) can call them.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../host/frame_syntax.h"
+#include "../host/headers.h"
+#include "../host/modular_syntax.h"
+#include "common.cuh"
+
+namespace jxlb {
+
+struct DevChannel {
+  int32_t* ptr;  // top-left of the view
+  uint32_t stride, w, h;
+  int32_t hshift, vshift;
+};
+
+struct DevModularJob {
+  uint64_t bit_pos, bit_limit;
+  const MaNode* tree;
+  DevEntropyCode code;
+  uint32_t wp[11];  // p1 p2 p3a p3b p3c p3d p3e w0..w3
+  uint32_t stream_index;
+  uint32_t first_channel, num_channels;
+  uint32_t dist_multiplier;
+  uint32_t use_wp;
+  int32_t* wp_scratch;   // 5 * max_width ints when use_wp
+  uint32_t* lz_window;   // when code.lz77_enabled
+};
+
+struct DevView {
+  void* ptr;  // top-left element
+  uint32_t stride, w, h;
+};
+
+// Modular ------------------------------------------------------------------------------------
+void launch_modular_decode(const uint8_t* codestream, const DevModularJob* jobs, const DevChannel* channels,
+                           uint64_t* end_bits, int* status, int num_jobs, cudaStream_t stream);
+void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizontal, cudaStream_t stream);
+void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cudaStream_t stream);
+void launch_palette_inverse_simple(DevView palette, const DevView* targets, int num_c, int nb_colours, int bit_depth,
+                                   int nb_deltas, int* status, cudaStream_t stream);
+void launch_int_to_float(DevView v, uint32_t bits_per_sample, uint32_t exp_bits, bool float_sample, cudaStream_t stream);
+void launch_modular_xyb(DevView y, DevView x, DevView b, float mx, float my, float mb, cudaStream_t stream);
+void launch_fill_u32(uint32_t* p, size_t n, uint32_t value, cudaStream_t stream);
+
+// VarDCT -------------------------------------------------------------------------------------
+struct DevLfGroupRect {
+  uint32_t bx0, by0, bw, bh;
+};
+struct DevBlockInfoJob {
+  DevLfGroupRect rect;
+  const int32_t* raw;  // nb_blocks x 2 (stride raw_stride)
+  uint32_t raw_stride, nb_blocks;
+};
+struct DevFrame {  // frame-global grids (device pointers), all with stride == their width
+  uint32_t width, height, bw, bh;      // pixels / 8x8 blocks
+  uint32_t cw, ch;                     // coefficient plane size (bw*8, bh*8)
+  uint32_t w64;                        // x_from_y / b_from_y stride
+  int32_t* lf_quant[3];
+  int32_t* x_from_y;
+  int32_t* b_from_y;
+  int32_t* sharpness;
+  int32_t* blk_type;
+  int32_t* blk_mul;
+  float* epf_sigma;
+  float* lf[3];
+  uint32_t* coeff[3];
+};
+void launch_build_block_info(DevFrame f, const DevBlockInfoJob* jobs, int num_jobs, float quant_mul_base,
+                             const float* sharp_lut8 /*device*/, int has_epf, int* status, cudaStream_t stream);
+
+struct DevHfParams {
+  DevEntropyCode code;
+  const uint32_t* orders;         // concatenated order tables (x | y << 16)
+  uint32_t order_offset[13 * 3];  // [order_id * 3 + channel] into `orders`
+  const uint8_t* block_ctx_map;
+  const int32_t* lf_thresholds;   // concatenated X, Y, B
+  uint32_t num_lf_thr[3];
+  const uint32_t* qf_thresholds;
+  uint32_t num_qf_thr;
+  uint32_t num_block_clusters, num_hf_presets, coeff_shift;
+  uint32_t group_dim_blocks, groups_per_row;
+};
+struct DevHfJob {
+  uint64_t bit_pos, bit_limit;
+  uint32_t group_idx;
+};
+void launch_decode_hf(const uint8_t* codestream, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
+                      int* status, int num_jobs, cudaStream_t stream);
+
+struct DevLfDequantJob {
+  DevLfGroupRect rect;
+  float scale[3];
+};
+void launch_lf_dequant(DevFrame f, const DevLfDequantJob* jobs, int num_jobs, cudaStream_t stream);
+void launch_lf_cfl(DevFrame f, float kx, float kb, cudaStream_t stream);
+void launch_lf_smooth(DevFrame f, float* tmp[3], float lf_x, float lf_y, float lf_b, cudaStream_t stream);
+
+struct DevDequantParams {
+  const float* matrices;          // all 17 sets x 3 channels x {normal, transposed}
+  uint32_t matrix_offset[17 * 3 * 2];  // [(set * 3 + c) * 2 + transposed]
+  float quant_bias[3], quant_bias_numerator;
+  float qm_scale[3];
+  float global_scale;             // as f32
+  float base_correlation_x, base_correlation_b, colour_factor;
+};
+void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream);
+void launch_hf_transform(DevFrame f, const float* sec_large /*64,128,256 tables: 32+64+128 floats*/,
+                         float* scratch, cudaStream_t stream);
+
+// Filters / colour ----------------------------------------------------------------------------
+void launch_gaborish(DevView in, DevView out, float w0, float w1, cudaStream_t stream);
+struct DevEpfParams {
+  float channel_scale[3];
+  float pass0_sigma_scale, pass2_sigma_scale, border_sad_mul, sigma_for_modular;
+};
+void launch_epf_step(const DevView in[3], const DevView out[3], const float* sigma, uint32_t sigma_stride,
+                     DevEpfParams p, int step, cudaStream_t stream);
+struct DevColorParams {
+  float opsin_bias[3], cbrt_opsin_bias[3], itscale, matrix[9];
+  int apply_srgb_tf;
+};
+void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream);
+void launch_copy_rect(DevView src, DevView dst, cudaStream_t stream);
+
+}  // namespace jxlb

@@ -637,3 +637,9 @@ void OracleBackend::hf_transform(VarDctState& st) {
 }
 
 }  // namespace jxlo
+
+// Known-answer-test hook (tests/test_oracle_golden.py): the reference's own DCT unit tests
+// (crates/jxl-render/src/vardct/generic/dct.rs:295-436) are replayed against this entry point.
+extern "C" void jxlo_dct_2d(float* data, uint32_t width, uint32_t height, int forward) {
+  jxlo::dct_2d(jxlo::Grid{data, width, width, height}, forward != 0);
+}

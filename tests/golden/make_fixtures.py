@@ -1,0 +1,36 @@
+"""Copies the reference's own test inputs / golden outputs used by this repo's tests.
+
+Run in the build container (where /root/reference exists); the GPU box only sees the copies.
+Sources (read-only, data files — no source code is copied):
+  crates/jxl-oxide-tests/decode/<case>/{input.jxl,output.buf.zst}      (tests/decode/mod.rs:122-130)
+  crates/jxl-oxide-tests/conformance/testcases/<case>/{input.jxl,ref.png}
+  crates/jxl-oxide-tests/decode/benchmark-data/*.jxl                    (benches/decode.rs:10-70)
+"""
+import os
+import shutil
+
+REF = "/root/reference/crates/jxl-oxide-tests"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (source dir, files)
+    "grayalpha": ("decode/grayalpha", ["input.jxl", "output.buf.zst"]),
+    "squeeze_edge": ("decode/squeeze_edge", ["input.jxl", "output.buf.zst"]),
+    "issue_311": ("decode/issue_311", ["input.jxl", "output.buf.zst"]),
+    "minecraft_vardct_e7": ("decode/minecraft_vardct_e7", ["input.jxl"]),
+    "opsin_inverse": ("conformance/testcases/opsin_inverse", ["input.jxl", "ref.png"]),
+    "alpha_premultiplied": ("conformance/testcases/alpha_premultiplied", ["input.jxl"]),
+    "alpha_triangles": ("conformance/testcases/alpha_triangles", ["input.jxl"]),
+    "bicycles": ("conformance/testcases/bicycles", ["input.jxl"]),
+    "lz77_flower": ("conformance/testcases/lz77_flower", ["input.jxl", "ref.png"]),
+}
+BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
+
+for name, (src, files) in CASES.items():
+    os.makedirs(os.path.join(HERE, name), exist_ok=True)
+    for f in files:
+        shutil.copyfile(os.path.join(REF, src, f), os.path.join(HERE, name, f))
+os.makedirs(os.path.join(HERE, "benchmark-data"), exist_ok=True)
+for f in BENCH:
+    shutil.copyfile(os.path.join(REF, "decode/benchmark-data", f), os.path.join(HERE, "benchmark-data", f))
+print("fixtures copied")

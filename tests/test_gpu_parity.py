@@ -1,0 +1,119 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): bit-exact for the integer/Modular path, <= 1 ULP for the VarDCT
+float pipeline. The kernels reproduce the reference's float op order, so VarDCT is asserted
+bit-exact too (0 ULP), stage by stage.
+"""
+import numpy as np
+import pytest
+
+from conftest import fixture_bytes
+
+pytestmark = pytest.mark.gpu
+
+MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower"]
+MODULAR_BENCH = ["srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
+VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7"]
+VARDCT_BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl"]
+STAGES_F32 = ["lf", "hf_dequant", "idct", "pre_filter", "gaborish", "epf", "rgb"]
+
+
+def ulp_diff(a, b):
+    a = a.view(np.int32).astype(np.int64)
+    b = b.view(np.int32).astype(np.int64)
+    a = np.where(a < 0, np.int64(-2147483648) - a, a)
+    b = np.where(b < 0, np.int64(-2147483648) - b, b)
+    return np.abs(a - b)
+
+
+@pytest.fixture(scope="module")
+def dec():
+    import jxl_oxide_b200
+    d = jxl_oxide_b200.Decoder(0)
+    yield d
+    d.close()
+
+
+def _decode_both(dec, oracle, data, capture=False, output_colour=0):
+    dec.set_capture(capture)
+    dec.decode(data, output_colour=output_colour)
+    got = dec.frame_planar(0)
+    img = oracle.OracleImage(data, output_colour=output_colour, threads=8, capture=capture)
+    want, ncol, is_vardct = img.frame(0)
+    return got, want, img
+
+
+@pytest.mark.parametrize("name", MODULAR)
+def test_modular_bit_exact(dec, oracle, name):
+    got, want, _ = _decode_both(dec, oracle, fixture_bytes(name, "input.jxl"))
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", MODULAR_BENCH)
+def test_modular_bench_files_bit_exact(dec, oracle, name):
+    got, want, _ = _decode_both(dec, oracle, fixture_bytes("benchmark-data", name))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def _check_vardct(dec, oracle, data):
+    got, want, img = _decode_both(dec, oracle, data, capture=True)
+    # integer stage: HF coefficients must be identical
+    for g, w in zip(dec.stage("hf_coeff", np.int32), img.stage("hf_coeff", np.int32)):
+        assert np.array_equal(g, w), "HF coefficient decode differs"
+    for st in STAGES_F32:
+        gs, ws = dec.stage(st), img.stage(st)
+        assert len(gs) == len(ws), st
+        for c, (g, w) in enumerate(zip(gs, ws)):
+            d = ulp_diff(g, w)
+            assert d.max() == 0, f"stage {st} channel {c}: max ULP diff {d.max()} at {np.unravel_index(d.argmax(), d.shape)}"
+    assert got.shape == want.shape
+    assert ulp_diff(got, want).max() <= 1  # north_star tolerance
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", VARDCT)
+def test_vardct_stagewise_bit_exact(dec, oracle, name):
+    _check_vardct(dec, oracle, fixture_bytes(name, "input.jxl"))
+
+
+@pytest.mark.parametrize("name", VARDCT_BENCH)
+def test_vardct_bench_files_bit_exact(dec, oracle, name):
+    _check_vardct(dec, oracle, fixture_bytes("benchmark-data", name))
+
+
+def test_errors_are_values(dec):
+    import jxl_oxide_b200
+    data = fixture_bytes("squeeze_edge", "input.jxl")
+    for bad in (data[:10], data[: len(data) // 2], b"\x00" * 64):
+        with pytest.raises(jxl_oxide_b200.JxlError):
+            dec.decode(bad)
+    dec.decode(data)  # the decoder stays usable after errors
+    assert dec.frame_planar(0).shape == (4, 513, 513)
+
+
+def test_stage_entry_points_match_pipeline(dec, oracle):
+    """Stage-level C-ABI calls (the reference's impls:: seams) on torch device tensors."""
+    import torch
+    import jxl_oxide_b200
+    data = fixture_bytes("opsin_inverse", "input.jxl")
+    img = oracle.OracleImage(data, threads=8, capture=True)
+    pre = img.stage("pre_filter")
+    gab = img.stage("gaborish")
+    planes = [torch.from_numpy(p.copy()).cuda() for p in pre]
+    dec.gaborish(planes, [[0.115169525, 0.061248592]] * 3)
+    dec.sync()
+    for p, w in zip(planes, gab):
+        assert np.array_equal(p.cpu().numpy().view(np.uint32), w.view(np.uint32))
+    # inverse RCT type 6 (YCgCo) against numpy wrapping arithmetic
+    rng = np.random.default_rng(7)
+    a, b, c = [rng.integers(-2000, 2000, size=(37, 53), dtype=np.int32) for _ in range(3)]
+    t = [torch.from_numpy(x.copy()).cuda() for x in (a, b, c)]
+    dec.rct_inverse(t, 6)
+    dec.sync()
+    tmp = a - (c >> 1)
+    e = c + tmp
+    f = tmp - (b >> 1)
+    d = f + b
+    for got, want in zip(t, (d, e, f)):
+        assert np.array_equal(got.cpu().numpy(), want)

@@ -1,0 +1,102 @@
+"""CPU tests: pin the oracle against the reference's own golden vectors."""
+import ctypes
+import math
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import fixture_bytes
+
+MODULAR_GOLDENS = ["grayalpha", "squeeze_edge", "issue_311"]
+
+
+@pytest.mark.parametrize("name", MODULAR_GOLDENS)
+def test_modular_golden_bit_exact(oracle, name):
+    """crates/jxl-oxide-tests/tests/decode/mod.rs:29-86 with threshold 0 (8-bit modular is exact:
+    v/255*65535+0.5 is injective)."""
+    gold = oracle.zstd_decompress(fixture_bytes(name, "output.buf.zst"))
+    w, h, ch = struct.unpack("<III", gold[:12])
+    img = oracle.OracleImage(fixture_bytes(name, "input.jxl"))
+    planes, _, is_vardct = img.frame(0)
+    assert not is_vardct
+    assert gold[12] == 0 and gold[-1] == 0xFF
+    exp = np.frombuffer(gold, dtype="<u2", count=w * h * ch, offset=13).reshape(ch, h, w)
+    act = (planes * np.float32(65535.0) + np.float32(0.5)).astype(np.uint16)
+    assert planes.shape == (ch, h, w)
+    assert np.array_equal(act, exp)
+
+
+def test_vardct_conformance_opsin_inverse(oracle):
+    """ISO 18181-3 level of agreement with libjxl's reference rendering (8-bit ref.png):
+    crates/jxl-oxide-tests/tests/conformance/mod.rs:139-368 uses peak 0.004 for VarDCT."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("opsin_inverse", "input.jxl"), threads=4)
+    planes, ncol, is_vardct = img.frame(0)
+    assert is_vardct and ncol == 3
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("opsin_inverse", "ref.png")))).astype(np.float32) / 255.0
+    ref = np.moveaxis(ref, 2, 0)
+    diff = np.abs(np.clip(planes, 0.0, 1.0) - ref)
+    assert diff.max() <= 0.004
+    assert math.sqrt(float((diff ** 2).mean())) <= 0.004
+
+
+def test_lz77_modular_vs_png(oracle):
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("lz77_flower", "input.jxl"))
+    planes, ncol, _ = img.frame(0)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("lz77_flower", "ref.png"))))
+    ref = np.moveaxis(ref, 2, 0)[:ncol]
+    act = np.rint(planes[:ncol] * 255.0).astype(np.uint8)
+    assert np.array_equal(act, ref)
+
+
+def _dct2_f64(x):
+    n = len(x)
+    out = []
+    for k in range(n):
+        s = sum(x[i] * math.cos(math.pi * (i + 0.5) * k / n) for i in range(n))
+        scale = (1.0 / n) if k == 0 else (math.sqrt(2.0) / n)
+        out.append(s * scale)
+    return out
+
+
+def _dct3_f64(c):
+    n = len(c)
+    return [c[0] + sum(math.sqrt(2.0) * c[k] * math.cos(math.pi * (i + 0.5) * k / n) for k in range(1, n)) for i in range(n)]
+
+
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32])
+@pytest.mark.parametrize("forward", [True, False])
+def test_dct_known_answers(oracle, n, forward):
+    """Same criterion as the reference's unit tests (generic/dct.rs:295-436): compare against the
+    f64 closed form after quantising to 2^-16."""
+    L = oracle.lib()
+    L.jxlo_dct_2d.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+    rng = np.random.default_rng(n * 2 + int(forward))
+    x = rng.uniform(-1.0, 1.0, size=n).astype(np.float32)
+    buf = x.copy()
+    L.jxlo_dct_2d(buf.ctypes.data, n, 1, int(forward))
+    exp = _dct2_f64([float(v) for v in x]) if forward else _dct3_f64([float(v) for v in x])
+    got = (buf.astype(np.float64) * 65536).astype(np.int64)
+    want = (np.array(exp) * 65536).astype(np.int64)
+    assert np.abs(got - want).max() <= 1
+
+
+def test_threads_do_not_change_results(oracle):
+    data = fixture_bytes("opsin_inverse", "input.jxl")
+    a, _, _ = oracle.OracleImage(data, threads=1).frame(0)
+    b, _, _ = oracle.OracleImage(data, threads=4).frame(0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_truncated_and_garbage_inputs_error_cleanly(oracle):
+    """Decode errors are values, never crashes (reference: fuzz_findings tests)."""
+    data = fixture_bytes("squeeze_edge", "input.jxl")
+    for cut in (2, 10, len(data) // 2):
+        with pytest.raises(oracle.OracleError):
+            oracle.OracleImage(data[:cut])
+    with pytest.raises(oracle.OracleError):
+        oracle.OracleImage(b"\x00" * 64)
