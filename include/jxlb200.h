@@ -63,6 +63,10 @@ const char* jxlb_last_error(const jxlb_decoder* dec);
  * RenderContext::postprocess_keyframe (crates/jxl-render/src/lib.rs:925-998).
  * Decoded planes (f32, planar, row-major) stay resident in HBM until jxlb_release_frames(). */
 int32_t jxlb_decode(jxlb_decoder* dec, const uint8_t* data, size_t size, const jxlb_options* opt);
+/* Keep an encoded image resident in HBM (slot id chosen by the caller) and decode from it: the
+ * timed region of a device-resident benchmark then contains no host->device copy of the input. */
+int32_t jxlb_preload(jxlb_decoder* dec, int32_t slot, const uint8_t* data, size_t size);
+int32_t jxlb_decode_slot(jxlb_decoder* dec, int32_t slot, const jxlb_options* opt);
 int32_t jxlb_image_get_info(const jxlb_decoder* dec, jxlb_image_info* info);
 int32_t jxlb_num_frames(const jxlb_decoder* dec);
 int32_t jxlb_frame_get_info(const jxlb_decoder* dec, int32_t frame, jxlb_frame_info* info);
@@ -76,6 +80,13 @@ int32_t jxlb_release_frames(jxlb_decoder* dec);
 int32_t jxlb_sync(jxlb_decoder* dec);
 /* Number of kernels this decoder has launched so far. */
 uint64_t jxlb_launch_count(const jxlb_decoder* dec);
+
+/* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the decoder's
+ * stream; jxlb_profile_get returns launches and accumulated milliseconds for a kernel family
+ * ("modular_decode", "decode_hf", "hf_transform", "epf_step", ...). Used by bench.py's roofline. */
+int32_t jxlb_set_profile(jxlb_decoder* dec, int32_t on);
+int32_t jxlb_profile_get(jxlb_decoder* dec, const char* name, uint64_t* launches, double* total_ms);
+int32_t jxlb_profile_reset(jxlb_decoder* dec);
 
 /* Test / debugging hook: snapshot intermediate stages ("lf", "hf_coeff", "hf_dequant", "idct",
  * "pre_filter", "gaborish", "epf", "rgb") of the LAST decoded frame to host memory. */

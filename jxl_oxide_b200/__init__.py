@@ -20,9 +20,11 @@ OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVI
 
 # every symbol include/jxlb200.h declares
 EXPORTED_SYMBOLS = [
-    "jxlb_decoder_create", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_image_get_info",
+    "jxlb_decoder_create", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
+    "jxlb_image_get_info",
     "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_channel_device",
-    "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_capture", "jxlb_stage_count", "jxlb_stage_get",
+    "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
+    "jxlb_profile_reset", "jxlb_set_capture", "jxlb_stage_count", "jxlb_stage_get",
     "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse",
 ]
 
@@ -80,6 +82,8 @@ def load_library():
     L.jxlb_last_error.restype = ctypes.c_char_p
     L.jxlb_decode.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(_Options)]
     L.jxlb_decode.restype = i32
+    L.jxlb_preload.argtypes = [vp, i32, ctypes.c_char_p, ctypes.c_size_t]
+    L.jxlb_decode_slot.argtypes = [vp, i32, ctypes.POINTER(_Options)]
     L.jxlb_image_get_info.argtypes = [vp, ctypes.POINTER(_ImageInfo)]
     L.jxlb_num_frames.argtypes = [vp]
     L.jxlb_frame_get_info.argtypes = [vp, i32, ctypes.POINTER(_FrameInfo)]
@@ -90,6 +94,9 @@ def load_library():
     L.jxlb_launch_count.argtypes = [vp]
     L.jxlb_launch_count.restype = ctypes.c_uint64
     L.jxlb_set_capture.argtypes = [vp, i32]
+    L.jxlb_set_profile.argtypes = [vp, i32]
+    L.jxlb_profile_get.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double)]
+    L.jxlb_profile_reset.argtypes = [vp]
     L.jxlb_stage_count.argtypes = [vp, ctypes.c_char_p]
     L.jxlb_stage_get.argtypes = [vp, ctypes.c_char_p, i32, ctypes.POINTER(u32), ctypes.POINTER(u32), vp]
     L.jxlb_gaborish.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, ctypes.POINTER(ctypes.c_float)]
@@ -121,6 +128,13 @@ class Decoder:
     def decode(self, data: bytes, output_colour=0, max_frames=0):
         opt = _Options(output_colour, max_frames)
         self._check(self._L.jxlb_decode(self._h, data, len(data), ctypes.byref(opt)))
+
+    def preload(self, slot, data: bytes):
+        self._check(self._L.jxlb_preload(self._h, slot, data, len(data)))
+
+    def decode_slot(self, slot, output_colour=0, max_frames=0):
+        opt = _Options(output_colour, max_frames)
+        self._check(self._L.jxlb_decode_slot(self._h, slot, ctypes.byref(opt)))
 
     def image_info(self):
         info = _ImageInfo()
@@ -156,6 +170,23 @@ class Decoder:
 
     def launch_count(self):
         return int(self._L.jxlb_launch_count(self._h))
+
+    def set_profile(self, on=True):
+        self._L.jxlb_set_profile(self._h, int(on))
+
+    def profile(self, name):
+        """(launches, total_ms) of a kernel family, timed with CUDA events on the decoder's stream."""
+        n, ms = ctypes.c_uint64(), ctypes.c_double()
+        self._check(self._L.jxlb_profile_get(self._h, name.encode(), ctypes.byref(n), ctypes.byref(ms)))
+        return n.value, ms.value
+
+    def profile_reset(self):
+        self._check(self._L.jxlb_profile_reset(self._h))
+
+    def frame_to_host(self, frame, out):
+        """Copies all channels of a frame into a preallocated (channels, h, w) float32 array."""
+        for c in range(out.shape[0]):
+            self._check(self._L.jxlb_frame_channel_to_host(self._h, frame, c, out[c].ctypes.data, out.shape[2]))
 
     def set_capture(self, on=True):
         self._L.jxlb_set_capture(self._h, int(on))

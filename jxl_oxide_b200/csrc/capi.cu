@@ -1,6 +1,7 @@
 // extern "C" boundary of libjxlb200.so — see include/jxlb200.h for the contract.
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 
@@ -16,6 +17,14 @@ struct jxlb_decoder {
   bool have_result = false;
   std::string error;
   std::vector<uint8_t> codestream;
+  struct Slot {
+    std::vector<uint8_t> codestream;
+    uint8_t* dptr = nullptr;
+  };
+  std::map<int32_t, Slot> slots;
+  ~jxlb_decoder() {
+    for (auto& kv : slots) cudaFree(kv.second.dptr);
+  }
 };
 
 namespace {
@@ -87,6 +96,33 @@ int32_t jxlb_decode(jxlb_decoder* dec, const uint8_t* data, size_t size, const j
   });
 }
 
+int32_t jxlb_preload(jxlb_decoder* dec, int32_t slot, const uint8_t* data, size_t size) {
+  if (!dec || !data) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    jxlb_decoder::Slot& s = dec->slots[slot];
+    if (s.dptr) cudaFree(s.dptr);
+    s.codestream = extract_codestream(data, size);
+    s.dptr = dec->be->upload_resident(s.codestream.data(), s.codestream.size());
+  });
+}
+
+int32_t jxlb_decode_slot(jxlb_decoder* dec, int32_t slot, const jxlb_options* opt) {
+  if (!dec) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    auto it = dec->slots.find(slot);
+    JXLB_CHECK(it != dec->slots.end(), kErrInvalidArg, "unknown preload slot");
+    release(dec);
+    DecodeOptions o;
+    if (opt) {
+      o.output_colour = opt->output_colour;
+      if (opt->max_frames) o.max_frames = opt->max_frames;
+    }
+    dec->be->use_resident_once(it->second.dptr);
+    dec->res = decode_codestream(*dec->be, it->second.codestream.data(), it->second.codestream.size(), o);
+    dec->have_result = true;
+  });
+}
+
 int32_t jxlb_image_get_info(const jxlb_decoder* dec, jxlb_image_info* info) {
   if (!dec || !info || !dec->have_result) return JXLB_ERR_INVALID_ARG;
   const ImageHeader& ih = dec->res.image_header;
@@ -151,6 +187,30 @@ int32_t jxlb_sync(jxlb_decoder* dec) {
 }
 
 uint64_t jxlb_launch_count(const jxlb_decoder* dec) { return dec ? dec->be->launches : 0; }
+
+int32_t jxlb_set_profile(jxlb_decoder* dec, int32_t on) {
+  if (!dec) return JXLB_ERR_INVALID_ARG;
+  dec->be->profile = on != 0;
+  return JXLB_OK;
+}
+
+int32_t jxlb_profile_get(jxlb_decoder* dec, const char* name, uint64_t* launches, double* total_ms) {
+  if (!dec || !name || !launches || !total_ms) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    dec->be->sync();
+    auto it = dec->be->profile_acc.find(name);
+    *launches = it == dec->be->profile_acc.end() ? 0 : it->second.first;
+    *total_ms = it == dec->be->profile_acc.end() ? 0.0 : it->second.second;
+  });
+}
+
+int32_t jxlb_profile_reset(jxlb_decoder* dec) {
+  if (!dec) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    dec->be->sync();
+    dec->be->profile_acc.clear();
+  });
+}
 
 int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on) {
   if (!dec) return JXLB_ERR_INVALID_ARG;

@@ -55,10 +55,59 @@ void CudaBackend::release_temps() {
   for (void* p : temps_) dfree(p);
   temps_.clear();
 }
-void CudaBackend::sync() { CUDA_CHECK(cudaStreamSynchronize(stream_)); }
+void CudaBackend::sync() {
+  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  resolve_profile();
+}
+
+void CudaBackend::begin_k(const char* name) {
+  ++launches;
+  if (!profile) return;
+  PendingTiming t;
+  t.name = name;
+  CUDA_CHECK(cudaEventCreate(&t.e0));
+  CUDA_CHECK(cudaEventCreate(&t.e1));
+  CUDA_CHECK(cudaEventRecord(t.e0, stream_));
+  pending_.push_back(t);
+}
+
+void CudaBackend::end_k() {
+  if (!profile || pending_.empty()) return;
+  CUDA_CHECK(cudaEventRecord(pending_.back().e1, stream_));
+}
+
+void CudaBackend::resolve_profile() {
+  for (PendingTiming& t : pending_) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) {
+      auto& acc = profile_acc[t.name];
+      acc.first += 1;
+      acc.second += double(ms);
+    }
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  pending_.clear();
+}
+
+uint8_t* CudaBackend::upload_resident(const uint8_t* data, size_t size) {
+  CUDA_CHECK(cudaSetDevice(device_));
+  size_t need = ((size + 7) & ~size_t(7)) + 32;
+  uint8_t* p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, need));
+  CUDA_CHECK(cudaMemset(p, 0, need));
+  CUDA_CHECK(cudaMemcpy(p, data, size, cudaMemcpyHostToDevice));
+  return p;
+}
 
 void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
   CUDA_CHECK(cudaSetDevice(device_));
+  if (resident_next_) {  // encoded bytes already live in HBM (jxlb_preload)
+    active_cs_ = resident_next_;
+    resident_next_ = nullptr;
+    ensure_static_tables();
+    return;
+  }
   size_t need = ((size + 7) & ~size_t(7)) + 32;  // zero padding for the 64-bit bit reader
   if (need > codestream_cap_) {
     if (d_codestream_) CUDA_CHECK(cudaFree(d_codestream_));
@@ -67,6 +116,7 @@ void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
   }
   CUDA_CHECK(cudaMemsetAsync(d_codestream_, 0, need, stream_));
   CUDA_CHECK(cudaMemcpyAsync(d_codestream_, data, size, cudaMemcpyHostToDevice, stream_));
+  active_cs_ = d_codestream_;
   ensure_static_tables();
 }
 
@@ -148,8 +198,9 @@ void CudaBackend::download_rect(const View& v, void* dst) {
 }
 
 void CudaBackend::copy_rect(const View& src, const View& dst) {
+  begin_k("copy_rect");
   launch_copy_rect(dev_view(src), dev_view(dst), stream_);
-  ++launches;
+  end_k();
 }
 
 void CudaBackend::stage_marker(const char* name, const View* views, int n) {
@@ -270,8 +321,9 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
   temps_.push_back(d_end);
   temps_.push_back(d_status);
-  launch_modular_decode(d_codestream_, d_jobs, d_chans, d_end, d_status, int(jobs.size()), stream_);
-  ++launches;
+  begin_k("modular_decode");
+  launch_modular_decode(active_cs_, d_jobs, d_chans, d_end, d_status, int(jobs.size()), stream_);
+  end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());
   CUDA_CHECK(cudaMemcpyAsync(end.data(), d_end, jobs.size() * 8, cudaMemcpyDeviceToHost, stream_));
@@ -295,14 +347,16 @@ int CudaBackend::squeeze_inverse(const View& avg, const View& res, bool horizont
   int id = alloc_plane(std::max(ow, 1u), std::max(oh, 1u), false);
   if (!ow || !oh) return id;
   View ov{id, 0, 0, ow, oh};
+  begin_k("squeeze_inverse");
   launch_squeeze_inverse(dev_view(avg), dev_view(res), dev_view(ov), horizontal, stream_);
-  ++launches;
+  end_k();
   return id;
 }
 
 void CudaBackend::rct_inverse(const View v[3], uint32_t rct_type) {
+  begin_k("rct_inverse");
   launch_rct_inverse(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), rct_type, stream_);
-  ++launches;
+  end_k();
 }
 
 void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t,
@@ -312,9 +366,10 @@ void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& 
   for (size_t i = 0; i < targets.size(); ++i) tv[i] = dev_view(targets[i]);
   int* d_status = static_cast<int*>(dmalloc(4));
   CUDA_CHECK(cudaMemsetAsync(d_status, 0, 4, stream_));
+  begin_k("palette_inverse_simple");
   launch_palette_inverse_simple(dev_view(palette), tv, int(targets.size()), int(t.nb_colours), int(bit_depth),
                                 int(t.nb_deltas), d_status, stream_);
-  ++launches;
+  end_k();
   int status = 0;
   CUDA_CHECK(cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, stream_));
   sync();
@@ -323,13 +378,15 @@ void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& 
 }
 
 void CudaBackend::int_to_float(const View& v, const BitDepth& d) {
+  begin_k("int_to_float");
   launch_int_to_float(dev_view(v), d.bits_per_sample, d.exp_bits, d.float_sample, stream_);
-  ++launches;
+  end_k();
 }
 
 void CudaBackend::modular_xyb_to_float(const View yxb[3], const float m[3]) {
+  begin_k("modular_xyb");
   launch_modular_xyb(dev_view(yxb[0]), dev_view(yxb[1]), dev_view(yxb[2]), m[0], m[1], m[2], stream_);
-  ++launches;
+  end_k();
 }
 
 DevFrame CudaBackend::dev_frame(const VarDctState& st) const {
@@ -368,8 +425,9 @@ void CudaBackend::build_block_info(VarDctState& st, const std::vector<BlockInfoJ
   int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
   temps_.push_back(d_status);
   float quant_mul_base = epf.quant_mul * 65536.0f / float(st.lfg->global_scale);
+  begin_k("build_block_info");
   launch_build_block_info(dev_frame(st), d_jobs, int(jobs.size()), quant_mul_base, d_lut, epf.iters > 0 ? 1 : 0, d_status, stream_);
-  ++launches;
+  end_k();
   std::vector<int> status(jobs.size());
   CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
   sync();
@@ -432,8 +490,9 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
   temps_.push_back(d_end);
   temps_.push_back(d_status);
-  launch_decode_hf(d_codestream_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), stream_);
-  ++launches;
+  begin_k("decode_hf");
+  launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), stream_);
+  end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());
   CUDA_CHECK(cudaMemcpyAsync(end.data(), d_end, jobs.size() * 8, cudaMemcpyDeviceToHost, stream_));
@@ -454,8 +513,9 @@ void CudaBackend::lf_dequant(VarDctState& st, const std::vector<LfDequantJob>& j
   for (const LfDequantJob& j : jobs)
     dj.push_back({{j.rect.bx0, j.rect.by0, j.rect.bw, j.rect.bh}, {j.scale[0], j.scale[1], j.scale[2]}});
   const DevLfDequantJob* d = static_cast<const DevLfDequantJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevLfDequantJob)));
+  begin_k("lf_dequant");
   launch_lf_dequant(dev_frame(st), d, int(dj.size()), stream_);
-  ++launches;
+  end_k();
 }
 
 void CudaBackend::lf_chroma_from_luma(VarDctState& st) {
@@ -463,8 +523,9 @@ void CudaBackend::lf_chroma_from_luma(VarDctState& st) {
   int32_t x_factor = int32_t(g.x_factor_lf) - 128, b_factor = int32_t(g.b_factor_lf) - 128;
   float kx = g.base_correlation_x + (float(x_factor) / float(g.colour_factor));
   float kb = g.base_correlation_b + (float(b_factor) / float(g.colour_factor));
+  begin_k("lf_cfl");
   launch_lf_cfl(dev_frame(st), kx, kb, stream_);
-  ++launches;
+  end_k();
 }
 
 void CudaBackend::lf_adaptive_smoothing(VarDctState& st) {
@@ -475,8 +536,9 @@ void CudaBackend::lf_adaptive_smoothing(VarDctState& st) {
   float lf_b = float(512.0 * double(g.m_b_lf) / double(scale_inv));
   float* tmp[3];
   for (int c = 0; c < 3; ++c) tmp[c] = static_cast<float*>(dmalloc(size_t(st.bw) * st.bh * 4));
+  begin_k("lf_smooth");
   launch_lf_smooth(dev_frame(st), tmp, lf_x, lf_y, lf_b, stream_);
-  ++launches;
+  end_k();
   for (int c = 0; c < 3; ++c) {  // swap the smoothed planes in
     PlaneRec& r = planes_.at(st.lf[c]);
     dfree(r.ptr);
@@ -512,13 +574,15 @@ void CudaBackend::hf_dequant_cfl(VarDctState& st) {
   p.base_correlation_x = st.lfg->base_correlation_x;
   p.base_correlation_b = st.lfg->base_correlation_b;
   p.colour_factor = float(st.lfg->colour_factor);
+  begin_k("hf_dequant_cfl");
   launch_hf_dequant_cfl(dev_frame(st), p, stream_);
-  ++launches;
+  end_k();
 }
 
 void CudaBackend::hf_transform(VarDctState& st) {
+  begin_k("hf_transform");
   launch_hf_transform(dev_frame(st), nullptr, nullptr, stream_);
-  ++launches;
+  end_k();
 }
 
 void CudaBackend::gaborish(const View v[3], const float weights[3][2]) {
@@ -529,8 +593,9 @@ void CudaBackend::gaborish(const View v[3], const float weights[3][2]) {
     DevView in = dev_view(v[c]);
     DevView ov = in;
     ov.ptr = out;
+    begin_k("gaborish");
     launch_gaborish(in, ov, weights[c][0], weights[c][1], stream_);
-    ++launches;
+    end_k();
     dfree(r.ptr);
     r.ptr = out;
   }
@@ -562,8 +627,9 @@ void CudaBackend::epf(const View v[3], const View& sigma, const EpfParams& p, bo
   dp.sigma_for_modular = p.sigma_for_modular;
   bool in_alt = false;
   auto run = [&](int step) {
+    begin_k("epf_step");
     launch_epf_step(in_alt ? alt : cur, in_alt ? cur : alt, d_sigma, sigma_stride, dp, step, stream_);
-    ++launches;
+    end_k();
     in_alt = !in_alt;
   };
   if (p.iters == 3) run(0);
@@ -593,8 +659,9 @@ void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   d.itscale = p.itscale;
   for (int i = 0; i < 9; ++i) d.matrix[i] = p.matrix[i];
   d.apply_srgb_tf = p.apply_srgb_tf ? 1 : 0;
+  begin_k("xyb_to_rgb");
   launch_xyb_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
-  ++launches;
+  end_k();
 }
 
 }  // namespace jxlb

@@ -45,6 +45,9 @@ class CudaBackend : public Backend {
   void stage_marker(const char* name, const View* views, int n) override;
 
   cudaStream_t stream() const { return stream_; }
+  // "inputs resident in HBM": upload once, then point the next decode at the device copy
+  uint8_t* upload_resident(const uint8_t* data, size_t size);
+  void use_resident_once(const uint8_t* dptr) { resident_next_ = dptr; }
   void sync();
   void* plane_ptr(int id) const { return planes_.at(id).ptr; }
   // device pointer + stride (elements) of a view's top-left element
@@ -56,6 +59,10 @@ class CudaBackend : public Backend {
   std::map<std::string, std::vector<std::pair<uint32_t, uint32_t>>> stage_dims;
   // launch accounting for bench.py ("gpu_launches")
   uint64_t launches = 0;
+  // per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline
+  bool profile = false;
+  std::map<std::string, std::pair<uint64_t, double>> profile_acc;  // name -> (launches, total ms)
+  void resolve_profile();
 
  private:
   struct PlaneRec {
@@ -74,10 +81,19 @@ class CudaBackend : public Backend {
   DevEntropyCode upload_code(const EntropyCode& c);
   DevFrame dev_frame(const VarDctState& st) const;
   void ensure_static_tables();
+  void begin_k(const char* name);
+  void end_k();
+  struct PendingTiming {
+    const char* name;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<PendingTiming> pending_;
 
   int device_;
   cudaStream_t stream_ = nullptr;
   uint8_t* d_codestream_ = nullptr;
+  const uint8_t* active_cs_ = nullptr;
+  const uint8_t* resident_next_ = nullptr;
   size_t codestream_cap_ = 0;
   std::map<int, PlaneRec> planes_;
   int next_id_ = 0;
