@@ -2,6 +2,7 @@
 #include "cuda_backend.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstring>
 
@@ -226,6 +227,9 @@ DevEntropyCode CudaBackend::upload_code(const EntropyCode& c) {
   d.configs = static_cast<const uint32_t*>(upload_temp(cfg.data(), cfg.size() * 4));
   d.log_alphabet_size = c.log_alphabet_size;
   d.use_prefix = c.use_prefix ? 1 : 0;
+  d.num_clusters = c.num_clusters;
+  d.cluster_map_size = uint32_t(c.cluster_map.size());
+  d.prefix_table_size = uint32_t(c.prefix_table.size());
   if (c.use_prefix) {
     d.prefix = static_cast<const uint32_t*>(upload_temp(c.prefix_table.data(), c.prefix_table.size() * 4));
     std::vector<uint32_t> meta;
@@ -254,6 +258,80 @@ const char* dev_status_message(int s) {
     default: return "unknown device decode error";
   }
 }
+// Resolves the MA-tree nodes that test properties which are constant for a whole channel
+// (channel index, stream index, previous channels that do not exist), like
+// MaTreeNode::next_decision_node (crates/jxl-modular/src/ma.rs:424-470).
+uint32_t resolve_static(const MaTree& t, uint32_t idx, uint32_t ci, uint32_t stream, int nprev) {
+  for (;;) {
+    const MaNode& n = t.nodes[idx];
+    if (n.property < 0) return idx;
+    int32_t v;
+    if (n.property == 0) v = int32_t(ci);
+    else if (n.property == 1) v = int32_t(stream);
+    else if (n.property >= 16 && (n.property - 16) / 4 >= nprev) v = 0;
+    else return idx;
+    idx = v > n.value ? n.a : n.b;
+  }
+}
+
+DevChannelPlan build_channel_plan(const MaTree& t, uint32_t ci, uint32_t stream, int nprev, std::vector<uint16_t>* luts) {
+  DevChannelPlan plan;
+  plan.root = resolve_static(t, 0, ci, stream, nprev);
+  plan.lut_prop = -1;
+  plan.lut_base = 0;
+  plan.lut_len = 0;
+  plan.lut_offset = uint32_t(luts->size());
+  if (t.nodes.size() >= 65536) return plan;
+  // which sample-dependent properties does the reachable subtree test?
+  int prop = -1;
+  bool single = true;
+  int64_t lower = INT64_MAX, upper = INT64_MIN;
+  std::vector<uint32_t> stack = {plan.root};
+  size_t visited = 0;
+  while (!stack.empty() && single) {
+    uint32_t idx = resolve_static(t, stack.back(), ci, stream, nprev);
+    stack.pop_back();
+    if (++visited > 4096) {
+      single = false;
+      break;
+    }
+    const MaNode& n = t.nodes[idx];
+    if (n.property < 0) continue;
+    if (n.property >= 16 || (prop >= 0 && prop != n.property)) {
+      single = false;
+      break;
+    }
+    prop = n.property;
+    lower = std::min<int64_t>(lower, n.value);
+    upper = std::max<int64_t>(upper, n.value);
+    stack.push_back(n.a);
+    stack.push_back(n.b);
+  }
+  if (!single) return plan;
+  if (prop < 0) {  // the channel has a single leaf
+    plan.lut_prop = 6;
+    plan.lut_base = 0;
+    plan.lut_len = 1;
+    luts->push_back(uint16_t(plan.root));
+    return plan;
+  }
+  if (upper - lower > 1022) return plan;
+  plan.lut_prop = prop;
+  plan.lut_base = int32_t(lower);
+  plan.lut_len = uint32_t(upper - lower + 2);
+  for (int64_t v = lower; v <= upper + 1; ++v) {
+    uint32_t idx = plan.root;
+    for (;;) {
+      idx = resolve_static(t, idx, ci, stream, nprev);
+      const MaNode& n = t.nodes[idx];
+      if (n.property < 0) break;
+      idx = v > n.value ? n.a : n.b;
+    }
+    luts->push_back(uint16_t(idx));
+  }
+  return plan;
+}
+
 bool tree_uses_wp(const MaTree& t) {
   for (const MaNode& n : t.nodes) {
     if (n.property == 15) return true;
@@ -273,6 +351,8 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   std::map<const MaTree*, TreeDev> trees;
   std::vector<DevModularJob> djobs(jobs.size());
   std::vector<DevChannel> dchans;
+  std::vector<DevChannelPlan> dplans;
+  size_t max_smem = 0;
   for (size_t i = 0; i < jobs.size(); ++i) {
     const ModularStreamJob& j = jobs[i];
     auto it = trees.find(j.tree);
@@ -305,6 +385,24 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
     }
     d.dist_multiplier = max_w;
     d.use_wp = it->second.wp ? 1 : 0;
+    d.num_tree_nodes = uint32_t(j.tree->nodes.size());
+    {  // per-channel decision plans (+ LUTs) for this job
+      std::vector<uint16_t> luts;
+      for (size_t ci = 0; ci < j.channels.size(); ++ci) {
+        const ModularChannelTarget& c = j.channels[ci];
+        int nprev = 0;
+        for (size_t pj = 0; pj < ci; ++pj) {
+          const ModularChannelTarget& q = j.channels[pj];
+          if (q.view.w && q.view.h && q.view.w == c.view.w && q.view.h == c.view.h && q.hshift == c.hshift && q.vshift == c.vshift) ++nprev;
+        }
+        dplans.push_back(build_channel_plan(*j.tree, uint32_t(ci), j.stream_index, std::min(nprev, 16), &luts));
+      }
+      d.lut_total = uint32_t(luts.size());
+      luts.push_back(0);
+      luts.push_back(0);
+      d.luts = static_cast<const uint16_t*>(upload_temp(luts.data(), luts.size() * 2));
+    }
+    max_smem = std::max(max_smem, modular_job_smem_bytes(d, max_w));
     if (d.use_wp && max_w) {
       d.wp_scratch = static_cast<int32_t*>(dmalloc(size_t(max_w) * 5 * 4));
       temps_.push_back(d.wp_scratch);
@@ -321,8 +419,9 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
   temps_.push_back(d_end);
   temps_.push_back(d_status);
+  const DevChannelPlan* d_plans = static_cast<const DevChannelPlan*>(upload_temp(dplans.data(), dplans.size() * sizeof(DevChannelPlan)));
   begin_k("modular_decode");
-  launch_modular_decode(active_cs_, d_jobs, d_chans, d_end, d_status, int(jobs.size()), stream_);
+  launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, stream_);
   end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());
@@ -426,7 +525,10 @@ void CudaBackend::build_block_info(VarDctState& st, const std::vector<BlockInfoJ
   temps_.push_back(d_status);
   float quant_mul_base = epf.quant_mul * 65536.0f / float(st.lfg->global_scale);
   begin_k("build_block_info");
-  launch_build_block_info(dev_frame(st), d_jobs, int(jobs.size()), quant_mul_base, d_lut, epf.iters > 0 ? 1 : 0, d_status, stream_);
+  void* scratch = dmalloc(build_block_info_scratch_bytes(int(jobs.size())));
+  temps_.push_back(scratch);
+  launch_build_block_info(dev_frame(st), d_jobs, int(jobs.size()), quant_mul_base, d_lut, epf.iters > 0 ? 1 : 0, d_status,
+                          scratch, stream_);
   end_k();
   std::vector<int> status(jobs.size());
   CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
@@ -491,7 +593,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   temps_.push_back(d_end);
   temps_.push_back(d_status);
   begin_k("decode_hf");
-  launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), stream_);
+  launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0, stream_);
   end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());

@@ -22,6 +22,7 @@ struct DevEntropyCode {
   const uint32_t* prefix_meta;  // per cluster: table_offset, root_bits
   uint32_t log_alphabet_size;
   uint32_t use_prefix;
+  uint32_t num_clusters, cluster_map_size, prefix_table_size;
   uint32_t lz77_enabled, lz77_min_symbol, lz77_min_length, lz_len_conf, lz_dist_cluster;
 };
 

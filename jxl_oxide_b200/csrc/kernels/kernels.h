@@ -17,9 +17,23 @@ struct DevChannel {
   int32_t hshift, vshift;
 };
 
+// Host-built per-channel decision plan: MA-tree nodes on the static properties (channel index,
+// stream index, unavailable previous channels) are resolved ahead of time; when the remaining
+// subtree tests a single property it is flattened to a lookup table (the reference does the same
+// in FlatMaTree, crates/jxl-modular/src/ma.rs:241-330, 424-470).
+struct DevChannelPlan {
+  uint32_t root;                 // first node that needs a sample-dependent property
+  int32_t lut_prop;              // -1: walk the tree from `root`; else property index of the LUT
+  int32_t lut_base;
+  uint32_t lut_len, lut_offset;  // u16 leaf-node indices at job.luts[lut_offset ...]
+};
+
 struct DevModularJob {
   uint64_t bit_pos, bit_limit;
   const MaNode* tree;
+  uint32_t num_tree_nodes;
+  const uint16_t* luts;
+  uint32_t lut_total;
   DevEntropyCode code;
   uint32_t wp[11];  // p1 p2 p3a p3b p3c p3d p3e w0..w3
   uint32_t stream_index;
@@ -37,7 +51,10 @@ struct DevView {
 
 // Modular ------------------------------------------------------------------------------------
 void launch_modular_decode(const uint8_t* codestream, const DevModularJob* jobs, const DevChannel* channels,
-                           uint64_t* end_bits, int* status, int num_jobs, cudaStream_t stream);
+                           const DevChannelPlan* plans, uint64_t* end_bits, int* status, int num_jobs,
+                           size_t smem_bytes, cudaStream_t stream);
+// bytes of dynamic shared memory a job wants for its tree / entropy tables / WP rows / LUTs
+size_t modular_job_smem_bytes(const DevModularJob& job, uint32_t max_width);
 void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizontal, cudaStream_t stream);
 void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cudaStream_t stream);
 void launch_palette_inverse_simple(DevView palette, const DevView* targets, int num_c, int nb_colours, int bit_depth,
@@ -70,7 +87,9 @@ struct DevFrame {  // frame-global grids (device pointers), all with stride == t
   uint32_t* coeff[3];
 };
 void launch_build_block_info(DevFrame f, const DevBlockInfoJob* jobs, int num_jobs, float quant_mul_base,
-                             const float* sharp_lut8 /*device*/, int has_epf, int* status, cudaStream_t stream);
+                             const float* sharp_lut8 /*device*/, int has_epf, int* status, void* scratch,
+                             cudaStream_t stream);
+size_t build_block_info_scratch_bytes(int num_jobs);
 
 struct DevHfParams {
   DevEntropyCode code;
@@ -89,7 +108,7 @@ struct DevHfJob {
   uint32_t group_idx;
 };
 void launch_decode_hf(const uint8_t* codestream, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
-                      int* status, int num_jobs, cudaStream_t stream);
+                      int* status, int num_jobs, int first_pass, cudaStream_t stream);
 
 struct DevLfDequantJob {
   DevLfGroupRect rect;

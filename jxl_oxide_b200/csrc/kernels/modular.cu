@@ -447,8 +447,9 @@ inline dim3 grid2d(uint32_t w, uint32_t h, uint32_t bx = 128) { return dim3((w +
 
 }  // namespace
 
-void launch_modular_decode(const uint8_t* cs, const DevModularJob* jobs, const DevChannel* channels, uint64_t* end_bits,
-                           int* status, int num_jobs, cudaStream_t stream) {
+// First (unoptimised, global-memory) version; kept as a debugging reference for entropy.cu.
+void launch_modular_decode_v1(const uint8_t* cs, const DevModularJob* jobs, const DevChannel* channels, uint64_t* end_bits,
+                              int* status, int num_jobs, cudaStream_t stream) {
   if (num_jobs <= 0) return;
   const int warps_per_block = 1;
   modular_decode_kernel<<<(num_jobs + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(

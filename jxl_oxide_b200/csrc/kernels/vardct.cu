@@ -695,14 +695,16 @@ __global__ void __launch_bounds__(kTransformThreads) hf_transform_kernel(DevFram
 
 }  // namespace
 
-void launch_build_block_info(DevFrame f, const DevBlockInfoJob* jobs, int num_jobs, float quant_mul_base,
-                             const float* sharp_lut8, int has_epf, int* status, cudaStream_t stream) {
+// First (single-thread, global-memory) version; superseded by kernels/blockinfo.cu.
+void launch_build_block_info_v1(DevFrame f, const DevBlockInfoJob* jobs, int num_jobs, float quant_mul_base,
+                                const float* sharp_lut8, int has_epf, int* status, cudaStream_t stream) {
   if (num_jobs <= 0) return;
   build_block_info_kernel<<<(num_jobs + 31) / 32, 32, 0, stream>>>(f, jobs, num_jobs, quant_mul_base, sharp_lut8, has_epf, status);
 }
 
-void launch_decode_hf(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,
-                      int num_jobs, cudaStream_t stream) {
+// First (unoptimised, global-memory) version; kept as a debugging reference for entropy.cu.
+void launch_decode_hf_v1(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,
+                         int num_jobs, cudaStream_t stream) {
   if (num_jobs <= 0) return;
   decode_hf_kernel<<<num_jobs, 32, 0, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs);
 }
