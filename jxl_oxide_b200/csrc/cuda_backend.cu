@@ -93,7 +93,7 @@ void CudaBackend::resolve_profile() {
 
 uint8_t* CudaBackend::upload_resident(const uint8_t* data, size_t size) {
   CUDA_CHECK(cudaSetDevice(device_));
-  size_t need = ((size + 7) & ~size_t(7)) + 32;
+  size_t need = ((size + 7) & ~size_t(7)) + 64;
   uint8_t* p = nullptr;
   CUDA_CHECK(cudaMalloc(&p, need));
   CUDA_CHECK(cudaMemset(p, 0, need));
@@ -109,7 +109,7 @@ void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
     ensure_static_tables();
     return;
   }
-  size_t need = ((size + 7) & ~size_t(7)) + 32;  // zero padding for the 64-bit bit reader
+  size_t need = ((size + 7) & ~size_t(7)) + 64;  // zero padding for the 64-bit bit reader
   if (need > codestream_cap_) {
     if (d_codestream_) CUDA_CHECK(cudaFree(d_codestream_));
     CUDA_CHECK(cudaMalloc(&d_codestream_, need));

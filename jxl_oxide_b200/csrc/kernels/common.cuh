@@ -26,46 +26,39 @@ struct DevEntropyCode {
   uint32_t lz77_enabled, lz77_min_symbol, lz77_min_length, lz_len_conf, lz_dist_cluster;
 };
 
-// LSB-first bit reader over the (zero-padded) codestream in global memory. Keeps up to 64 bits
-// buffered; `pos` is the absolute bit offset of the next unread bit.
+// LSB-first bit reader over the (zero-padded) codestream in global memory. 64-bit buffer fed in
+// aligned 32-bit words; the NEXT word is always already in flight (`ahead`), so the global-load
+// latency of a refill is hidden behind the symbols decoded from the current buffer.
 struct DevBitReader {
-  const uint8_t* data;
-  uint64_t pos;        // absolute bit offset of the next unread bit
-  uint64_t next_byte;  // byte offset of the next byte to load into `buf`
+  const uint32_t* next_word;  // word after `ahead`
+  uint64_t pos;               // absolute bit offset of the next unread bit
   uint64_t buf;
+  uint32_t ahead;
   int nbits;
 
-  __device__ __forceinline__ uint64_t load8(uint64_t byte) const {
-    const uint64_t* w = reinterpret_cast<const uint64_t*>(data + (byte & ~uint64_t(7)));
-    uint32_t sh = uint32_t(byte & 7) * 8;
-    uint64_t lo = __ldg(w);
-    if (sh == 0) return lo;
-    uint64_t hi = __ldg(w + 1);
-    return (lo >> sh) | (hi << (64 - sh));
-  }
   __device__ __forceinline__ void init(const uint8_t* d, uint64_t bit_pos) {
-    data = d;
     pos = bit_pos;
-    uint64_t byte = bit_pos >> 3;
-    uint32_t skip = uint32_t(bit_pos & 7);
-    buf = load8(byte) >> skip;
-    nbits = 64 - int(skip);
-    next_byte = byte + 8;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(d) + (bit_pos >> 5);
+    const uint32_t skip = uint32_t(bit_pos & 31);
+    buf = uint64_t(__ldg(w)) >> skip;
+    nbits = 32 - int(skip);
+    buf |= uint64_t(__ldg(w + 1)) << nbits;
+    nbits += 32;
+    ahead = __ldg(w + 2);
+    next_word = w + 3;
   }
-  __device__ __forceinline__ void refill() {  // requires nbits < 32; afterwards nbits >= 56
-    int t = (64 - nbits) & ~7;
-    uint64_t v = load8(next_byte);
-    uint64_t mask = t >= 64 ? ~uint64_t(0) : ((uint64_t(1) << t) - 1);
-    buf |= (v & mask) << nbits;
-    nbits += t;
-    next_byte += uint64_t(t >> 3);
+  __device__ __forceinline__ void refill() {  // requires nbits <= 32; afterwards nbits > 32
+    buf |= uint64_t(ahead) << nbits;
+    nbits += 32;
+    ahead = __ldg(next_word);
+    ++next_word;
   }
   __device__ __forceinline__ uint32_t peek(uint32_t n) {  // n <= 32
     if (nbits < 32) refill();
     return uint32_t(buf) & (n >= 32 ? 0xffffffffu : ((1u << n) - 1));
   }
   __device__ __forceinline__ void consume(uint32_t n) {
-    buf = n >= 64 ? 0 : (buf >> n);
+    buf >>= n;
     nbits -= int(n);
     pos += n;
   }
