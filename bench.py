@@ -30,6 +30,24 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 # ----------------------------------------------------------------------------------------------
 # workloads
+def synth_frame(w, h, seed, distance=1.0, extra=()):
+    """Synthetic encoded frame from tools/synth_enc.cc (built on demand; cached under bench_data/)."""
+    tool = os.path.join(ROOT, "tools", "_build_synth_enc")
+    src = os.path.join(ROOT, "tools", "synth_enc.cc")
+    host = os.path.join(ROOT, "jxl_oxide_b200", "csrc", "host")
+    if not os.path.exists(tool) or os.path.getmtime(tool) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", tool, src] +
+                              [os.path.join(host, f) for f in ("entropy.cc", "frame_syntax.cc", "modular_syntax.cc", "headers.cc")])
+    os.makedirs(os.path.join(ROOT, "bench_data"), exist_ok=True)
+    tag = "".join(extra).replace("-", "")
+    path = os.path.join(ROOT, "bench_data", f"synth_{w}x{h}_d{distance}_s{seed}{tag}.jxl")
+    if not os.path.exists(path):
+        subprocess.check_call([tool, "--width", str(w), "--height", str(h), "--seed", str(seed), "--distance", str(distance),
+                               "-o", path] + list(extra), stderr=subprocess.DEVNULL)
+    with open(path, "rb") as f:
+        return f.read()
+
+
 def load_workload(name):
     """Returns (description, list of encoded frames (bytes) for ONE step on ONE GPU, (w, h) per frame)."""
     if name == "mosaic8k":
@@ -38,16 +56,16 @@ def load_workload(name):
         desc = ("8K-equivalent (33.18 MP/step/GPU): 3x3 mosaic of a real libjxl VarDCT d1.0 2560x1440 frame "
                 "(starrail.d1-e6.jxl, Gaborish + EPF), decoded as 9 independent frames")
         return desc, [tile] * 9, (2560, 1440)
-    if name == "synth8k":
-        path = os.path.join(ROOT, "bench_data", "synth_8k_d1.jxl")
-        if not os.path.exists(path):
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import synth_jxl
-            synth_jxl.generate(path, 7680, 4320, distance=1.0, seed=1)
-        with open(path, "rb") as f:
-            frame = f.read()
-        desc = "7680x4320 VarDCT d1.0 synthetic encoded frame (tools/synth_jxl.py seed 1), Gaborish + EPF(2)"
-        return desc, [frame], (7680, 4320)
+    if name in ("synth8k", "synth4k"):
+        w, h = (7680, 4320) if name == "synth8k" else (3840, 2160)
+        frames = []
+        for seed in (1, 2, 3, 4):
+            frames.append(synth_frame(w, h, seed))
+        frames = frames * 2
+        desc = (f"{w}x{h} VarDCT d1.0 synthetic encoded frames (tools/synth_enc.cc seeds 1-4, ~0.93 bit/px, "
+                "libjxl-like: WP-coded LF, mixed varblocks 8x8..64x64, Gaborish + EPF 2 iters), "
+                f"{len(frames)} independent frames per step")
+        return desc, frames, (w, h)
     if name.startswith("file:"):
         with open(name[5:], "rb") as f:
             data = f.read()
@@ -293,7 +311,7 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": "Megapixels/s decoded (8K VarDCT d1.0)", "value": value, "unit": "MP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "real-file mosaic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if "synth" in args.workload else "real-file mosaic",
         "config": {"workload": desc, "note": "CPU restatement of jxl-oxide's generic render path on all host cores"},
         "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -305,9 +323,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mosaic8k")
-    ap.add_argument("--contexts", type=int, default=9, help="decoder contexts (CUDA streams) per GPU")
-    ap.add_argument("--cpu-sample-frames", type=int, default=3)
+    ap.add_argument("--workload", default="synth8k", help="synth8k | synth4k | mosaic8k | file:PATH")
+    ap.add_argument("--contexts", type=int, default=8, help="decoder contexts (CUDA streams) per GPU")
+    ap.add_argument("--cpu-sample-frames", type=int, default=1)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -100,3 +100,15 @@ def test_truncated_and_garbage_inputs_error_cleanly(oracle):
             oracle.OracleImage(data[:cut])
     with pytest.raises(oracle.OracleError):
         oracle.OracleImage(b"\x00" * 64)
+
+
+def test_synthetic_encoder_roundtrips_through_oracle(oracle):
+    """tools/synth_enc.cc writes a stream whose ANS final states, TOC and block layout the decoder
+    accepts; the generator is deterministic per seed."""
+    import bench
+    a = bench.synth_frame(520, 392, 11)
+    b = bench.synth_frame(520, 392, 11)
+    assert a == b
+    img = oracle.OracleImage(a, threads=4)
+    planes, ncol, is_vardct = img.frame(0)
+    assert is_vardct and planes.shape == (3, 392, 520) and np.isfinite(planes).all()
