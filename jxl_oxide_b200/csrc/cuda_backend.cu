@@ -5,6 +5,8 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <memory>
+#include <tuple>
 
 namespace jxlb {
 
@@ -332,6 +334,78 @@ DevChannelPlan build_channel_plan(const MaTree& t, uint32_t ci, uint32_t stream,
   return plan;
 }
 
+// The part of an MA tree one channel of one stream can reach, with static decisions resolved and
+// node indices renumbered from 0 (the reference prunes the same way when it flattens a tree for a
+// channel, crates/jxl-modular/src/ma.rs:579-645). Small enough to live in shared memory even when
+// the frame's global tree has thousands of nodes.
+struct ChannelTree {
+  std::vector<MaNode> nodes;  // nodes[0] is the root
+  int32_t lut_prop = -1, lut_base = 0;
+  std::vector<uint16_t> lut;  // leaf indices into `nodes`
+  bool stream_dependent = false;
+};
+
+constexpr size_t kMaxChannelTreeNodes = 60000;
+
+bool build_channel_tree(const MaTree& t, uint32_t ci, uint32_t stream, int nprev, ChannelTree* out) {
+  auto resolve = [&](uint32_t idx) {
+    for (;;) {
+      const MaNode& n = t.nodes[idx];
+      if (n.property < 0) return idx;
+      int32_t v;
+      if (n.property == 0) v = int32_t(ci);
+      else if (n.property == 1) {
+        v = int32_t(stream);
+        out->stream_dependent = true;
+      } else if (n.property >= 16 && (n.property - 16) / 4 >= nprev) v = 0;
+      else return idx;
+      idx = v > n.value ? n.a : n.b;
+    }
+  };
+  out->nodes.clear();
+  out->nodes.push_back(t.nodes[resolve(0)]);
+  std::vector<uint32_t> stack = {0};
+  while (!stack.empty()) {
+    const uint32_t cur = stack.back();
+    stack.pop_back();
+    if (out->nodes[cur].property < 0) continue;
+    if (out->nodes.size() + 2 > kMaxChannelTreeNodes) return false;
+    const uint32_t a = resolve(out->nodes[cur].a), b = resolve(out->nodes[cur].b);
+    const uint32_t na = uint32_t(out->nodes.size());
+    out->nodes.push_back(t.nodes[a]);
+    out->nodes.push_back(t.nodes[b]);
+    out->nodes[cur].a = na;
+    out->nodes[cur].b = na + 1;
+    stack.push_back(na);
+    stack.push_back(na + 1);
+  }
+  // single-property subtree -> leaf LUT over [lower, upper + 1] (ma.rs:241-330)
+  int prop = -1;
+  int64_t lower = INT64_MAX, upper = INT64_MIN;
+  for (const MaNode& n : out->nodes) {
+    if (n.property < 0) continue;
+    if (n.property >= 16 || (prop >= 0 && prop != n.property)) return true;  // general walk
+    prop = n.property;
+    lower = std::min<int64_t>(lower, n.value);
+    upper = std::max<int64_t>(upper, n.value);
+  }
+  if (prop < 0) {  // single leaf
+    out->lut_prop = 6;
+    out->lut_base = 0;
+    out->lut.assign(1, 0);
+    return true;
+  }
+  if (upper - lower > 1022) return true;
+  out->lut_prop = prop;
+  out->lut_base = int32_t(lower);
+  for (int64_t v = lower; v <= upper + 1; ++v) {
+    uint32_t idx = 0;
+    while (out->nodes[idx].property >= 0) idx = v > out->nodes[idx].value ? out->nodes[idx].a : out->nodes[idx].b;
+    out->lut.push_back(uint16_t(idx));
+  }
+  return true;
+}
+
 bool tree_uses_wp(const MaTree& t) {
   for (const MaNode& n : t.nodes) {
     if (n.property == 15) return true;
@@ -344,11 +418,21 @@ bool tree_uses_wp(const MaTree& t) {
 void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   if (jobs.empty()) return;
   struct TreeDev {
-    const MaNode* nodes;
+    const MaNode* nodes = nullptr;  // full tree, uploaded only for the uncompacted fallback
     DevEntropyCode code;
+    bool wp = false;
+  };
+  struct JobTables {  // device tables shared by every job with the same per-channel subtrees
+    const MaNode* nodes;
+    uint32_t num_nodes;
+    const uint16_t* luts;
+    uint32_t lut_total;
+    std::vector<DevChannelPlan> plans;
     bool wp;
   };
   std::map<const MaTree*, TreeDev> trees;
+  std::map<std::tuple<const MaTree*, uint32_t, int, int64_t>, std::unique_ptr<ChannelTree>> channel_trees;
+  std::map<std::vector<const ChannelTree*>, JobTables> job_tables;
   std::vector<DevModularJob> djobs(jobs.size());
   std::vector<DevChannel> dchans;
   std::vector<DevChannelPlan> dplans;
@@ -358,16 +442,13 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
     auto it = trees.find(j.tree);
     if (it == trees.end()) {
       TreeDev td;
-      td.nodes = static_cast<const MaNode*>(upload_temp(j.tree->nodes.data(), j.tree->nodes.size() * sizeof(MaNode)));
       td.code = upload_code(j.tree->code);
-      td.wp = tree_uses_wp(*j.tree);
       it = trees.emplace(j.tree, td).first;
     }
     DevModularJob& d = djobs[i];
     std::memset(&d, 0, sizeof(d));
     d.bit_pos = j.bit_pos;
     d.bit_limit = j.bit_limit;
-    d.tree = it->second.nodes;
     d.code = it->second.code;
     const WpHeader& w = j.wp;
     const uint32_t wpv[11] = {w.p1, w.p2, w.p3a, w.p3b, w.p3c, w.p3d, w.p3e, w.w[0], w.w[1], w.w[2], w.w[3]};
@@ -384,19 +465,92 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
       samples += uint64_t(c.view.w) * c.view.h;
     }
     d.dist_multiplier = max_w;
-    d.use_wp = it->second.wp ? 1 : 0;
-    d.num_tree_nodes = uint32_t(j.tree->nodes.size());
-    {  // per-channel decision plans (+ LUTs) for this job
-      std::vector<uint16_t> luts;
-      for (size_t ci = 0; ci < j.channels.size(); ++ci) {
-        const ModularChannelTarget& c = j.channels[ci];
-        int nprev = 0;
-        for (size_t pj = 0; pj < ci; ++pj) {
-          const ModularChannelTarget& q = j.channels[pj];
-          if (q.view.w && q.view.h && q.view.w == c.view.w && q.view.h == c.view.h && q.hshift == c.hshift && q.vshift == c.vshift) ++nprev;
-        }
-        dplans.push_back(build_channel_plan(*j.tree, uint32_t(ci), j.stream_index, std::min(nprev, 16), &luts));
+    // per-channel subtrees (cached across the jobs of this call when they do not depend on the stream index)
+    std::vector<const ChannelTree*> key;
+    bool compact = true;
+    std::vector<int> nprevs(j.channels.size());
+    for (size_t ci = 0; ci < j.channels.size(); ++ci) {
+      const ModularChannelTarget& c = j.channels[ci];
+      int nprev = 0;
+      for (size_t pj = 0; pj < ci; ++pj) {
+        const ModularChannelTarget& q = j.channels[pj];
+        if (q.view.w && q.view.h && q.view.w == c.view.w && q.view.h == c.view.h && q.hshift == c.hshift && q.vshift == c.vshift) ++nprev;
       }
+      nprevs[ci] = nprev = std::min(nprev, 16);
+      if (!compact) continue;
+      auto any = channel_trees.find({j.tree, uint32_t(ci), nprev, -1});
+      if (any == channel_trees.end()) any = channel_trees.find({j.tree, uint32_t(ci), nprev, int64_t(j.stream_index)});
+      if (any == channel_trees.end()) {
+        auto ct = std::make_unique<ChannelTree>();
+        if (!build_channel_tree(*j.tree, uint32_t(ci), j.stream_index, nprev, ct.get())) {
+          compact = false;
+          continue;
+        }
+        const int64_t skey = ct->stream_dependent ? int64_t(j.stream_index) : -1;
+        any = channel_trees.emplace(std::make_tuple(j.tree, uint32_t(ci), nprev, skey), std::move(ct)).first;
+      }
+      key.push_back(any->second.get());
+    }
+    if (compact) {
+      auto jt = job_tables.find(key);
+      if (jt == job_tables.end()) {
+        JobTables t;
+        std::vector<MaNode> nodes;
+        std::vector<uint16_t> luts;
+        t.wp = false;
+        for (const ChannelTree* ct : key) {
+          const uint32_t base = uint32_t(nodes.size());
+          DevChannelPlan plan;
+          plan.root = base;
+          plan.lut_prop = -1;
+          plan.lut_base = 0;
+          plan.lut_len = 0;
+          plan.lut_offset = uint32_t(luts.size());
+          for (MaNode n : ct->nodes) {
+            if (n.property >= 0) {
+              n.a += base;
+              n.b += base;
+              if (n.property == 15) t.wp = true;
+            } else if ((n.a & 0xff) == 6) {
+              t.wp = true;
+            }
+            nodes.push_back(n);
+          }
+          if (ct->lut_prop >= 0 && nodes.size() <= 65536) {
+            plan.lut_prop = ct->lut_prop;
+            plan.lut_base = ct->lut_base;
+            plan.lut_len = uint32_t(ct->lut.size());
+            for (uint16_t l : ct->lut) luts.push_back(uint16_t(l + base));
+          }
+          t.plans.push_back(plan);
+        }
+        t.num_nodes = uint32_t(nodes.size());
+        t.lut_total = uint32_t(luts.size());
+        luts.push_back(0);
+        luts.push_back(0);
+        t.nodes = static_cast<const MaNode*>(upload_temp(nodes.data(), nodes.size() * sizeof(MaNode)));
+        t.luts = static_cast<const uint16_t*>(upload_temp(luts.data(), luts.size() * 2));
+        jt = job_tables.emplace(key, std::move(t)).first;
+      }
+      const JobTables& t = jt->second;
+      d.tree = t.nodes;
+      d.num_tree_nodes = t.num_nodes;
+      d.luts = t.luts;
+      d.lut_total = t.lut_total;
+      d.use_wp = t.wp ? 1 : 0;
+      dplans.insert(dplans.end(), t.plans.begin(), t.plans.end());
+    } else {  // a channel's subtree is too large to copy per job: walk the frame's tree in global memory
+      TreeDev& td = it->second;
+      if (!td.nodes) {
+        td.nodes = static_cast<const MaNode*>(upload_temp(j.tree->nodes.data(), j.tree->nodes.size() * sizeof(MaNode)));
+        td.wp = tree_uses_wp(*j.tree);
+      }
+      d.tree = td.nodes;
+      d.num_tree_nodes = uint32_t(j.tree->nodes.size());
+      d.use_wp = td.wp ? 1 : 0;
+      std::vector<uint16_t> luts;
+      for (size_t ci = 0; ci < j.channels.size(); ++ci)
+        dplans.push_back(build_channel_plan(*j.tree, uint32_t(ci), j.stream_index, nprevs[ci], &luts));
       d.lut_total = uint32_t(luts.size());
       luts.push_back(0);
       luts.push_back(0);
