@@ -2,6 +2,7 @@
 #include "cuda_backend.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -26,6 +27,12 @@ CudaBackend::CudaBackend(int device) : device_(device) {
     fail(kErrCuda, "no CUDA device available: the jxl_oxide_b200 hot path has no CPU fallback");
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  // Keep freed stream-ordered allocations in the pool: a frame's planes are reused by the next
+  // frame instead of being returned to the driver at every synchronisation.
+  cudaMemPool_t pool;
+  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device_));
+  uint64_t keep = UINT64_MAX;
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
 }
 
 CudaBackend::~CudaBackend() {
@@ -36,6 +43,7 @@ CudaBackend::~CudaBackend() {
   if (d_codestream_) cudaFree(d_codestream_);
   if (d_natural_orders_) cudaFree(d_natural_orders_);
   if (d_dequant_) cudaFree(d_dequant_);
+  if (d_dequant_default_) cudaFree(d_dequant_default_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -204,6 +212,17 @@ void CudaBackend::copy_rect(const View& src, const View& dst) {
   begin_k("copy_rect");
   launch_copy_rect(dev_view(src), dev_view(dst), stream_);
   end_k();
+}
+
+void CudaBackend::phase_mark(const char* name) {
+  if (!profile) return;
+  const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (name && phase_t0_ >= 0.0) {
+    auto& acc = profile_acc[std::string("host:") + name];
+    acc.first += 1;
+    acc.second += now - phase_t0_;
+  }
+  phase_t0_ = now;
 }
 
 void CudaBackend::stage_marker(const char* name, const View* views, int n) {
@@ -803,23 +822,31 @@ void CudaBackend::lf_adaptive_smoothing(VarDctState& st) {
 }
 
 void CudaBackend::hf_dequant_cfl(VarDctState& st) {
-  if (cached_hfg_ != st.hfg) {
+  const bool use_default = st.hfg->dequant_all_default;
+  if (use_default ? d_dequant_default_ == nullptr : cached_hfg_ != st.hfg) {
     std::vector<float> all;
-    std::memset(&dequant_params_, 0, sizeof(dequant_params_));
+    DevDequantParams& dp = use_default ? dequant_default_params_ : dequant_params_;
+    std::memset(&dp, 0, sizeof(dp));
     for (int set = 0; set < 17; ++set)
       for (int c = 0; c < 3; ++c)
         for (int tr = 0; tr < 2; ++tr) {
-          const std::vector<float>& m = tr ? st.hfg->dequant.matrices_tr[set][c] : st.hfg->dequant.matrices[set][c];
-          dequant_params_.matrix_offset[(set * 3 + c) * 2 + tr] = uint32_t(all.size());
+          const std::vector<float>& m = tr ? st.hfg->dequant->matrices_tr[set][c] : st.hfg->dequant->matrices[set][c];
+          dp.matrix_offset[(set * 3 + c) * 2 + tr] = uint32_t(all.size());
           all.insert(all.end(), m.begin(), m.end());
         }
-    if (d_dequant_) dfree(d_dequant_);
-    d_dequant_ = static_cast<float*>(dmalloc(all.size() * 4));
-    CUDA_CHECK(cudaMemcpyAsync(d_dequant_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, stream_));
-    cached_hfg_ = st.hfg;
+    if (use_default) {
+      CUDA_CHECK(cudaMalloc(&d_dequant_default_, all.size() * 4));
+      CUDA_CHECK(cudaMemcpyAsync(d_dequant_default_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaStreamSynchronize(stream_));
+    } else {
+      if (d_dequant_) dfree(d_dequant_);
+      d_dequant_ = static_cast<float*>(dmalloc(all.size() * 4));
+      CUDA_CHECK(cudaMemcpyAsync(d_dequant_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, stream_));
+      cached_hfg_ = st.hfg;
+    }
   }
-  DevDequantParams p = dequant_params_;
-  p.matrices = d_dequant_;
+  DevDequantParams p = use_default ? dequant_default_params_ : dequant_params_;
+  p.matrices = use_default ? d_dequant_default_ : d_dequant_;
   const OpsinInverseMatrix& oim = st.ih->opsin_inverse_matrix;
   for (int c = 0; c < 3; ++c) p.quant_bias[c] = oim.quant_bias[c];
   p.quant_bias_numerator = oim.quant_bias_numerator;

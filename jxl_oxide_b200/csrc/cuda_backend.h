@@ -43,6 +43,7 @@ class CudaBackend : public Backend {
   void upsample(View v[3], uint32_t num_channels, uint32_t factor_log2, const ImageHeader& ih) override;
   void xyb_to_rgb(const View v[3], const ColorParams& p) override;
   void stage_marker(const char* name, const View* views, int n) override;
+  void phase_mark(const char* name) override;
 
   cudaStream_t stream() const { return stream_; }
   // "inputs resident in HBM": upload once, then point the next decode at the device copy
@@ -61,6 +62,7 @@ class CudaBackend : public Backend {
   uint64_t launches = 0;
   // per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline
   bool profile = false;
+  double phase_t0_ = -1.0;  // wall clock (ms) of the previous phase_mark
   std::map<std::string, std::pair<uint64_t, double>> profile_acc;  // name -> (launches, total ms)
   void resolve_profile();
 
@@ -106,6 +108,8 @@ class CudaBackend : public Backend {
   // per-frame caches
   const HfGlobalSyntax* cached_hfg_ = nullptr;
   float* d_dequant_ = nullptr;
+  float* d_dequant_default_ = nullptr;  // all-default matrix set, uploaded once per decoder
+  DevDequantParams dequant_default_params_;
   DevDequantParams dequant_params_;
 };
 

@@ -126,6 +126,8 @@ class Backend {
   virtual void xyb_to_rgb(const View v[3], const ColorParams& p) = 0;
   // Called by the planner at stage boundaries; a backend may snapshot planes for tests.
   virtual void stage_marker(const char* /*name*/, const View* /*views*/, int /*n*/) {}
+  // Profiling hook: the planner finished the named host phase (wall clock since the previous mark).
+  virtual void phase_mark(const char* /*name*/) {}
 };
 
 }  // namespace jxlb

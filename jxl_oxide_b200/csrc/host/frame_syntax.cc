@@ -471,22 +471,33 @@ HfGlobalSyntax parse_hf_global(BitReader& br, const ImageHeader& ih, const Frame
   (void)ih;
   HfGlobalSyntax g;
   // DequantMatrixSet (dequant.rs:586-658)
-  bool all_default = br.read_bool();
-  for (uint32_t set = 0; set < 17; ++set) {
-    MatrixParams p = all_default ? default_params(set) : parse_matrix_params(br, set);
-    build_matrix(p, set, g.dequant.matrices[set]);
-    uint32_t w, h;
-    DequantMatrices::matrix_size(set, &w, &h);
-    for (int c = 0; c < 3; ++c) {
-      const std::vector<float>& m = g.dequant.matrices[set][c];
-      std::vector<float>& t = g.dequant.matrices_tr[set][c];
-      t.resize(m.size());
-      for (size_t idx = 0; idx < m.size(); ++idx) {
-        size_t mx = idx % h, my = idx / h;
-        t[idx] = m[mx * w + my];
+  const bool all_default = br.read_bool();
+  auto build_all = [&](bool defaults) {
+    auto dq = std::make_shared<DequantMatrices>();
+    for (uint32_t set = 0; set < 17; ++set) {
+      MatrixParams p = defaults ? default_params(set) : parse_matrix_params(br, set);
+      build_matrix(p, set, dq->matrices[set]);
+      uint32_t w, h;
+      DequantMatrices::matrix_size(set, &w, &h);
+      for (int c = 0; c < 3; ++c) {
+        const std::vector<float>& m = dq->matrices[set][c];
+        std::vector<float>& t = dq->matrices_tr[set][c];
+        t.resize(m.size());
+        for (size_t idx = 0; idx < m.size(); ++idx) {
+          size_t mx = idx % h, my = idx / h;
+          t[idx] = m[mx * w + my];
+        }
       }
     }
+    return std::shared_ptr<const DequantMatrices>(std::move(dq));
+  };
+  if (all_default) {
+    static const std::shared_ptr<const DequantMatrices> kDefault = build_all(true);  // thread-safe one-time init
+    g.dequant = kDefault;
+  } else {
+    g.dequant = build_all(false);
   }
+  g.dequant_all_default = all_default;
   uint32_t num_groups = fh.num_groups();
   g.num_hf_presets = br.read(ceil_log2_nonzero(num_groups)) + 1;
   for (uint32_t pass = 0; pass < fh.passes.num_passes; ++pass) {  // hf_pass.rs:34-76

@@ -6,6 +6,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "bitreader.h"
@@ -72,7 +73,9 @@ struct HfPassSyntax {  // hf_pass.rs:26-76
 };
 
 struct HfGlobalSyntax {
-  DequantMatrices dequant;
+  // Shared, immutable: the all-default set (the usual case) is built once per process.
+  std::shared_ptr<const DequantMatrices> dequant;
+  bool dequant_all_default = false;
   uint32_t num_hf_presets = 0;
   std::vector<HfPassSyntax> passes;
 };

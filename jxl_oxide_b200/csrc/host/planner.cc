@@ -291,6 +291,7 @@ void FramePlanner::setup_gmodular() {
 
 DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_end_byte) {
   BitReader br(cs_, size_, frame_begin_byte * 8);
+  be_.phase_mark(nullptr);
   be_.new_frame();
   fh_ = parse_frame_header(br, ih_);
   toc_ = parse_toc(br, fh_);
@@ -341,6 +342,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     gm_pass_groups_.assign(num_passes, std::vector<std::vector<GroupChannel>>(num_groups));
   }
 
+  be_.phase_mark("lf_global");
   // ---- VarDCT frame state ----
   if (vardct) {
     st_ = VarDctState();
@@ -368,6 +370,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     st_.epf_sigma = new_plane(st_.bw, st_.bh);
   }
 
+  be_.phase_mark("alloc");
   // ---- LfGroups: three entropy-coded streams each, at data-dependent bit offsets ----
   std::vector<size_t> lf_pos(num_lf_groups), lf_limit(num_lf_groups);
   std::vector<LfGroupRect> lf_rect(num_lf_groups);
@@ -402,6 +405,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
       lf_pos[g] = jobs[pend[g].job_index].end_bit;
     }
   }
+  be_.phase_mark("lf_coeff");
   {  // Modular LF-group channels (jxl-frame/src/data/lf_group.rs:76-91)
     std::vector<ModularStreamJob> jobs;
     std::vector<PendingStream> pend;
@@ -418,6 +422,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
       lf_pos[owner[k]] = jobs[pend[k].job_index].end_bit;
     }
   }
+  be_.phase_mark("mlf");
   if (vardct) {  // HfMetadata (jxl-vardct/src/hf_metadata.rs:52-230)
     std::vector<ModularStreamJob> jobs;
     std::vector<PendingStream> pend;
@@ -444,6 +449,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     be_.build_block_info(st_, bjobs);
     for (auto& b : bjobs) drop_plane(b.raw_plane);
   }
+  be_.phase_mark("hf_metadata");
   if (single) pos = lf_pos[0];
 
   // ---- HfGlobal ----
@@ -455,6 +461,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     if (single) pos = r.pos();
   }
 
+  be_.phase_mark("hf_global");
   // ---- PassGroups ----
   for (uint32_t p = 0; p < num_passes; ++p) {
     std::vector<size_t> gpos(num_groups), glimit(num_groups);
@@ -484,10 +491,12 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     for (auto& ps : pend) finish_stream(ps);
   }
 
+  be_.phase_mark("pass_groups");
   // ---- global inverse transforms ----
   std::vector<ChanBuf> gm_image = gm_coded_;
   if (lfg_.has_gmodular) run_inverse_transforms(lfg_.gmodular, gm_image);
 
+  be_.phase_mark("inverse_transforms");
   // ---- render ----
   DecodedFrame out;
   out.header = fh_;
@@ -511,6 +520,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
       for (View& v : colour) be_.int_to_float(v, ih_.bit_depth);
     }
   }
+  be_.phase_mark("render_vardct");
   be_.stage_marker("pre_filter", colour.data(), int(colour.size()));
 
   // restoration filters (render.rs:76-131)
@@ -545,6 +555,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   }
   frame_planes_.clear();
   gm_coded_.clear();
+  be_.phase_mark("filters_colour");
   return out;
 }
 

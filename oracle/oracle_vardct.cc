@@ -256,8 +256,8 @@ void OracleBackend::hf_dequant_cfl(VarDctState& st) {
         const TransformTypeInfo& ti = kTransformInfo[t];
         uint32_t w = ti.w8 * 8u, h = ti.h8 * 8u;
         float mul = 65536.0f / (float(g.global_scale) * float(mulp.i32()[gi])) * qm_scale[c];
-        const std::vector<float>& m = ti.transpose ? st.hfg->dequant.matrices_tr[ti.param_index][c]
-                                                   : st.hfg->dequant.matrices[ti.param_index][c];
+        const std::vector<float>& m = ti.transpose ? st.hfg->dequant->matrices_tr[ti.param_index][c]
+                                                   : st.hfg->dequant->matrices[ti.param_index][c];
         for (uint32_t y = 0; y < h; ++y) {
           uint32_t* row = cp.data.data() + (size_t(by) * 8 + y) * cp.w + size_t(bx) * 8;
           for (uint32_t x = 0; x < w; ++x) {
