@@ -863,9 +863,11 @@ void CudaBackend::hf_dequant_cfl(VarDctState& st) {
 }
 
 void CudaBackend::hf_transform(VarDctState& st) {
+  void* scratch = dmalloc(hf_transform_scratch_bytes(st.bw, st.bh));
   begin_k("hf_transform");
-  launch_hf_transform(dev_frame(st), nullptr, nullptr, stream_);
+  launch_hf_transform(dev_frame(st), scratch, stream_);
   end_k();
+  dfree(scratch);
 }
 
 void CudaBackend::gaborish(const View v[3], const float weights[3][2]) {

@@ -127,8 +127,9 @@ struct DevDequantParams {
   float base_correlation_x, base_correlation_b, colour_factor;
 };
 void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream);
-void launch_hf_transform(DevFrame f, const float* sec_large /*64,128,256 tables: 32+64+128 floats*/,
-                         float* scratch, cudaStream_t stream);
+// `scratch`: hf_transform_scratch_bytes() of device memory for the per-size-class work lists
+void launch_hf_transform(DevFrame f, void* scratch, cudaStream_t stream);
+size_t hf_transform_scratch_bytes(uint32_t bw, uint32_t bh);
 
 // Filters / colour ----------------------------------------------------------------------------
 void launch_gaborish(DevView in, DevView out, float w0, float w1, cudaStream_t stream);

@@ -5,6 +5,8 @@
 // compiled with -fmad=false and fuses only where the reference calls mul_add.
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace jxlb {
 
 #define JXLB_TABLE_QUAL __device__ __constant__ const
@@ -630,66 +632,222 @@ __device__ void transform_special(Grid c, int type, float* scratch /* 64 + 48 fl
 // transform_varblocks_inner (transform_common.rs:11-75): one CTA per (8x8 cell, channel); cells
 // that are not a varblock origin exit immediately. First, correctness-oriented version: rows then
 // columns straight on the coefficient plane (L1/L2 resident), one thread per line.
-constexpr int kTransformThreads = 64;
-__global__ void __launch_bounds__(kTransformThreads) hf_transform_kernel(DevFrame f) {
-  const uint32_t bx = blockIdx.x, by = blockIdx.y, c = blockIdx.z;
+//
+// Varblocks are independent, so the frame is first sorted into three work lists by size class and
+// each class gets a persistent (grid-stride) kernel shaped for it:
+//   small  (8x8 cells: DCT8 and the nine "special" 8x8 transforms): 8 threads per block, one row /
+//          column per thread in registers, 32 blocks per CTA;
+//   medium (16x8 ... 32x32): one warp per block, tile staged in shared memory (stride 33), one
+//          row / column per lane in registers;
+//   large  (64x64 ... 256x256): one 64-thread CTA per block, line buffers in shared memory.
+// Every variant performs exactly the reference's operations per line (rows first, then columns,
+// generic/dct.rs:93-140), so results are bit-identical to the single-threaded formulation.
+
+struct TransformLists {
+  uint32_t* counts;  // [4]: small, medium, large64, large256
+  uint32_t* items[4];
+};
+
+__global__ void classify_varblocks_kernel(DevFrame f, TransformLists L) {
+  const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
+  if (bx >= f.bw || by >= f.bh) return;
   const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
   if (t < 0) return;
-  const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
-  const int w = bw * 8, h = bh * 8;
-  float* plane = reinterpret_cast<float*>(f.coeff[c]);
-  float* block = plane + size_t(by) * 8 * f.cw + size_t(bx) * 8;
-  const int stride = int(f.cw);
-  __shared__ float smem[1024 + 3 * 32 + 160];
-  float* llf = smem;            // up to 32 x 32
-  float* tmp = smem + 1024;     // 96
-  float* special = smem + 1024 + 96;  // 160
+  const int m = max(int(kDevTransformInfo[t][0]), int(kDevTransformInfo[t][1]));
+  const int cls = m == 1 ? 0 : (m <= 4 ? 1 : (m == 8 ? 2 : 3));
+  const uint32_t slot = atomicAdd(L.counts + cls, 1u);
+  L.items[cls][slot] = bx | (by << 16);
+}
+
+// Register-resident inverse DCT: the operation sequence of Dct1D<N>::run(inverse).
+template <int N>
+struct RegIdct {
+  static __device__ __forceinline__ void run(float (&io)[N]) {
+    constexpr int h = N / 2;
+    const float* sec = N == 8 ? kSecHalf8 : (N == 16 ? kSecHalf16 : kSecHalf32);
+    float in0[h], in1[h];
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      in0[i] = io[2 * i];
+      in1[i] = io[2 * i + 1];
+    }
+#pragma unroll
+    for (int i = 1; i < h; ++i) in1[h - i] = __fadd_rn(in1[h - i], in1[h - i - 1]);
+    in1[0] = __fmul_rn(in1[0], SQRT2F);
+    RegIdct<h>::run(in0);
+    RegIdct<h>::run(in1);
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float r = __fmul_rn(in1[i], sec[i]);
+      io[i] = __fadd_rn(in0[i], r);
+      io[N - i - 1] = __fsub_rn(in0[i], r);
+    }
+  }
+};
+template <>
+struct RegIdct<4> {
+  static __device__ __forceinline__ void run(float (&io)[4]) { dct4(io, false); }
+};
+
+// LLF of a multi-cell varblock: forward DCT of its bw x bh LF samples, rescaled
+// (transform_common.rs:33-58). `llf` holds bw*bh floats, `tmp` 3*max(bw,bh).
+__device__ void compute_llf_serial(const DevFrame& f, int c, uint32_t bx, uint32_t by, int bw, int bh, float* llf, float* tmp) {
   const float* lf = f.lf[c];
-  if (threadIdx.x == 0) {
-    if (bw * bh == 1) {
-      llf[0] = lf[size_t(by) * f.bw + bx];
+  for (int y = 0; y < bh; ++y)
+    for (int x = 0; x < bw; ++x) llf[y * bw + x] = lf[size_t(by + y) * f.bw + bx + x];
+  dct_2d_serial(Grid{llf, bw, bw, bh}, true, tmp);
+  const int logbw = 31 - __clz(bw), logbh = 31 - __clz(bh);
+  for (int y = 0; y < bh; ++y)
+    for (int x = 0; x < bw; ++x)
+      llf[y * bw + x] = __fdiv_rn(llf[y * bw + x], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+}
+
+constexpr int kSmallGroups = 32;  // 8-thread groups per CTA
+__global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f, const uint32_t* __restrict__ items,
+                                                                      const uint32_t* __restrict__ count_ptr) {
+  __shared__ float s_tile[kSmallGroups][72];      // 8 x 9
+  __shared__ float s_special[kSmallGroups][192];  // 8 x 8 copy + 128 scratch
+  const uint32_t group = threadIdx.x >> 3, r = threadIdx.x & 7;
+  const uint32_t gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
+  const uint32_t total = *count_ptr * 3;
+  float* tile = s_tile[group];
+  for (uint32_t work = blockIdx.x * kSmallGroups + group; work < total; work += gridDim.x * kSmallGroups) {
+    const uint32_t item = items[work / 3], c = work % 3;
+    const uint32_t bx = item & 0xffff, by = item >> 16;
+    const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
+    float* row = reinterpret_cast<float*>(f.coeff[c]) + (size_t(by) * 8 + r) * f.cw + size_t(bx) * 8;
+    const float4 lo = *reinterpret_cast<const float4*>(row), hi = *reinterpret_cast<const float4*>(row + 4);
+    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (r == 0) v[0] = f.lf[c][size_t(by) * f.bw + bx];
+    if (t == 0) {
+      RegIdct<8>::run(v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[r * 9 + i] = v[i];
+      __syncwarp(gmask);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tile[i * 9 + r];
+      RegIdct<8>::run(v);
+      __syncwarp(gmask);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[i * 9 + r] = v[i];
+      __syncwarp(gmask);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = tile[r * 9 + i];
     } else {
-      for (int y = 0; y < bh; ++y)
-        for (int x = 0; x < bw; ++x) llf[y * bw + x] = lf[size_t(by + y) * f.bw + bx + x];
-      dct_2d_serial(Grid{llf, bw, bw, bh}, true, tmp);
-      int logbw = 31 - __clz(bw), logbh = 31 - __clz(bh);
-      for (int y = 0; y < bh; ++y)
-        for (int x = 0; x < bw; ++x)
-          llf[y * bw + x] = __fdiv_rn(llf[y * bw + x], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+      float* g = s_special[group];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[r * 8 + i] = v[i];
+      __syncwarp(gmask);
+      if (r == 0) transform_special(Grid{g, 8, 8, 8}, t, g + 64);
+      __syncwarp(gmask);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = g[r * 8 + i];
     }
+    __syncwarp(gmask);
+    *reinterpret_cast<float4*>(row) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(row + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void idct_line_smem(float* p, int stride) {
+  float v[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = p[i * stride];
+  RegIdct<N>::run(v);
+#pragma unroll
+  for (int i = 0; i < N; ++i) p[i * stride] = v[i];
+}
+
+__device__ __forceinline__ void idct_line_dispatch(float* p, int stride, int n) {
+  if (n == 8) idct_line_smem<8>(p, stride);
+  else if (n == 16) idct_line_smem<16>(p, stride);
+  else idct_line_smem<32>(p, stride);
+}
+
+constexpr int kMediumWarps = 4;
+__global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame f, const uint32_t* __restrict__ items,
+                                                                        const uint32_t* __restrict__ count_ptr) {
+  __shared__ float s_tile[kMediumWarps][32 * 33];
+  __shared__ float s_llf[kMediumWarps][16 + 12];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t total = *count_ptr * 3;
+  float* tile = s_tile[warp];
+  float* llf = s_llf[warp];
+  for (uint32_t work = blockIdx.x * kMediumWarps + warp; work < total; work += gridDim.x * kMediumWarps) {
+    const uint32_t item = items[work / 3], c = work % 3;
+    const uint32_t bx = item & 0xffff, by = item >> 16;
+    const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
+    const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
+    const int w = bw * 8, h = bh * 8;
+    float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
+    if (lane == 0) compute_llf_serial(f, int(c), bx, by, bw, bh, llf, llf + 16);
+    const int logw = 31 - __clz(w);
+    for (int idx = int(lane); idx < w * h; idx += 32) {
+      const int x = idx & (w - 1), y = idx >> logw;
+      tile[y * 33 + x] = block[size_t(y) * f.cw + x];
+    }
+    __syncwarp();
+    if (int(lane) < bw * bh) tile[(int(lane) / bw) * 33 + (int(lane) % bw)] = llf[lane];
+    __syncwarp();
+    if (int(lane) < h) idct_line_dispatch(tile + lane * 33, 1, w);
+    __syncwarp();
+    if (int(lane) < w) idct_line_dispatch(tile + lane, 33, h);
+    __syncwarp();
+    for (int idx = int(lane); idx < w * h; idx += 32) {
+      const int x = idx & (w - 1), y = idx >> logw;
+      block[size_t(y) * f.cw + x] = tile[y * 33 + x];
+    }
+    __syncwarp();
+  }
+}
+
+// dct_2d (general path: both dimensions >= 4) by a CTA; every thread owns 2*nmax floats of `lines`.
+__device__ void dct_2d_coop(float* p, size_t stride, int width, int height, bool forward, float* lines, int nmax) {
+  float* line = lines + size_t(threadIdx.x) * (2 * nmax + 1);  // odd stride: conflict-free banks
+  float* scratch = line + nmax;
+  for (int y = int(threadIdx.x); y < height; y += int(blockDim.x)) {
+    float* row = p + size_t(y) * stride;
+    for (int x = 0; x < width; ++x) line[x] = row[x];
+    dct1d(line, scratch, width, forward);
+    for (int x = 0; x < width; ++x) row[x] = line[x];
   }
   __syncthreads();
-  const bool is_special = (t == 1 || t == 2 || t == 3 || (t >= 12 && t <= 17));
-  if (is_special) {
-    if (threadIdx.x == 0) {
-      float* g = special;  // 8x8 copy + scratch behind it
-      for (int y = 0; y < 8; ++y)
-        for (int x = 0; x < 8; ++x) g[y * 8 + x] = block[y * stride + x];
-      g[0] = llf[0];
-      __shared__ float sscratch[128];
-      transform_special(Grid{g, 8, 8, 8}, t, sscratch);
-      for (int y = 0; y < 8; ++y)
-        for (int x = 0; x < 8; ++x) block[y * stride + x] = g[y * 8 + x];
-    }
-    return;
-  }
-  // rows
-  float line[256];
-  float scratch[256];
-  for (int r = threadIdx.x; r < h; r += kTransformThreads) {
-    float* row = block + size_t(r) * stride;
-    for (int x = 0; x < w; ++x) line[x] = row[x];
-    if (r < bh)
-      for (int x = 0; x < bw; ++x) line[x] = llf[r * bw + x];
-    dct1d(line, scratch, w, false);
-    for (int x = 0; x < w; ++x) row[x] = line[x];
+  for (int x = int(threadIdx.x); x < width; x += int(blockDim.x)) {
+    float* col = p + x;
+    for (int y = 0; y < height; ++y) line[y] = col[size_t(y) * stride];
+    dct1d(line, scratch, height, forward);
+    for (int y = 0; y < height; ++y) col[size_t(y) * stride] = line[y];
   }
   __syncthreads();
-  for (int col = threadIdx.x; col < w; col += kTransformThreads) {
-    float* cp = block + col;
-    for (int y = 0; y < h; ++y) line[y] = cp[size_t(y) * stride];
-    dct1d(line, scratch, h, false);
-    for (int y = 0; y < h; ++y) cp[size_t(y) * stride] = line[y];
+}
+
+constexpr int kLargeThreads = 64;
+__global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, const uint32_t* __restrict__ items,
+                                                                   const uint32_t* __restrict__ count_ptr, int nmax) {
+  extern __shared__ float s_large[];  // llf (32 x 32) | per-thread line buffers (2 * nmax each)
+  float* llf = s_large;
+  float* lines = s_large + 1024;
+  const uint32_t total = *count_ptr * 3;
+  for (uint32_t work = blockIdx.x; work < total; work += gridDim.x) {
+    const uint32_t item = items[work / 3], c = work % 3;
+    const uint32_t bx = item & 0xffff, by = item >> 16;
+    const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
+    const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
+    const int w = bw * 8, h = bh * 8;
+    float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
+    const float* lf = f.lf[c];
+    for (int i = int(threadIdx.x); i < bw * bh; i += kLargeThreads)
+      llf[i] = lf[size_t(by + i / bw) * f.bw + bx + i % bw];
+    __syncthreads();
+    dct_2d_coop(llf, size_t(bw), bw, bh, true, lines, nmax);
+    const int logbw = 31 - __clz(bw), logbh = 31 - __clz(bh);
+    for (int i = int(threadIdx.x); i < bw * bh; i += kLargeThreads) {
+      const int x = i % bw, y = i / bw;
+      block[size_t(y) * f.cw + x] = __fdiv_rn(llf[i], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+    }
+    __syncthreads();
+    dct_2d_coop(block, f.cw, w, h, false, lines, nmax);
   }
 }
 
@@ -731,9 +889,38 @@ void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream) 
   hf_dequant_cfl_kernel<<<grid, block, 0, stream>>>(f, p);
 }
 
-void launch_hf_transform(DevFrame f, const float*, float*, cudaStream_t stream) {
-  dim3 grid(f.bw, f.bh, 3);
-  hf_transform_kernel<<<grid, kTransformThreads, 0, stream>>>(f);
+size_t hf_transform_scratch_bytes(uint32_t bw, uint32_t bh) {
+  const size_t cells = size_t(bw) * bh;
+  return 256 + (cells + cells / 2 + 2 * (cells / 32 + 1) + 64) * 4;
+}
+
+void launch_hf_transform(DevFrame f, void* scratch, cudaStream_t stream) {
+  const size_t cells = size_t(f.bw) * f.bh;
+  TransformLists L;
+  L.counts = static_cast<uint32_t*>(scratch);
+  uint32_t* base = L.counts + 64;
+  L.items[0] = base;                                   // <= cells
+  L.items[1] = L.items[0] + cells;                     // <= cells / 2
+  L.items[2] = L.items[1] + cells / 2 + 1;             // <= cells / 32
+  L.items[3] = L.items[2] + cells / 32 + 1;            // <= cells / 128
+  cudaMemsetAsync(L.counts, 0, 16, stream);
+  dim3 cb(32, 8), cg((f.bw + 31) / 32, (f.bh + 7) / 8);
+  classify_varblocks_kernel<<<cg, cb, 0, stream>>>(f, L);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(idct_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+  }
+  const int small_grid = int(std::min<size_t>((cells * 3 + kSmallGroups - 1) / kSmallGroups, size_t(num_sms) * 8));
+  idct_small_kernel<<<small_grid, kSmallGroups * 8, 0, stream>>>(f, L.items[0], L.counts + 0);
+  const int medium_grid = int(std::min<size_t>((cells / 2 * 3 + kMediumWarps) / kMediumWarps, size_t(num_sms) * 8));
+  idct_medium_kernel<<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, L.items[1], L.counts + 1);
+  const int large_grid = int(std::min<size_t>((cells / 32 + 1) * 3, size_t(num_sms) * 4));
+  idct_large_kernel<<<large_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 64 + 1)) * 4, stream>>>(f, L.items[2], L.counts + 2, 64);
+  const int huge_grid = int(std::min<size_t>((cells / 128 + 1) * 3, size_t(num_sms)));
+  idct_large_kernel<<<huge_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 256 + 1)) * 4, stream>>>(f, L.items[3], L.counts + 3, 256);
 }
 
 }  // namespace jxlb
