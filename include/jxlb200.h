@@ -91,6 +91,9 @@ int32_t jxlb_profile_reset(jxlb_decoder* dec);
 /* Test / debugging hook: snapshot intermediate stages ("lf", "hf_coeff", "hf_dequant", "idct",
  * "pre_filter", "gaborish", "epf", "rgb") of the LAST decoded frame to host memory. */
 int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on);
+/* Restoration filters + colour as one fused kernel (default, on) or stage by stage (off): the
+ * stage-by-stage form also emits the "gaborish" / "epf" snapshots for stage-level parity tests. */
+int32_t jxlb_set_fuse_filters(jxlb_decoder* dec, int32_t on);
 int32_t jxlb_stage_count(const jxlb_decoder* dec, const char* name);
 int32_t jxlb_stage_get(const jxlb_decoder* dec, const char* name, int32_t idx, uint32_t* width, uint32_t* height,
                        uint32_t* out /* may be NULL */);

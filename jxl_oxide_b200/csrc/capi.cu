@@ -218,6 +218,12 @@ int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on) {
   return JXLB_OK;
 }
 
+int32_t jxlb_set_fuse_filters(jxlb_decoder* dec, int32_t on) {
+  if (!dec) return JXLB_ERR_INVALID_ARG;
+  dec->be->fuse_filters = on != 0;
+  return JXLB_OK;
+}
+
 int32_t jxlb_stage_count(const jxlb_decoder* dec, const char* name) {
   if (!dec || !name) return 0;
   auto it = dec->be->stages.find(name);

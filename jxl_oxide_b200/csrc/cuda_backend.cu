@@ -931,6 +931,58 @@ void CudaBackend::epf(const View v[3], const View& sigma, const EpfParams& p, bo
   }
 }
 
+bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter& rf, const View& sigma,
+                                       bool sigma_is_constant, const ColorParams* colour) {
+  if (!fuse_filters || !fused_filters_supported(v[0].w, v[0].h)) return false;
+  DevView in[3], out[3];
+  void* out_ptr[3];
+  for (int c = 0; c < 3; ++c) {
+    PlaneRec& r = planes_.at(v[c].plane);
+    JXLB_CHECK(v[c].x0 == 0 && v[c].y0 == 0, kErrInvalidArg, "filters expect top-left anchored views");
+    out_ptr[c] = dmalloc(size_t(r.w) * r.h * 4);
+    in[c] = dev_view(v[c]);
+    out[c] = in[c];
+    out[c].ptr = out_ptr[c];
+  }
+  DevFusedFilterParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.gab_enabled = rf.gab_enabled ? 1 : 0;
+  for (int c = 0; c < 3; ++c) {
+    p.gab_w[c][0] = rf.gab_weights[c][0];
+    p.gab_w[c][1] = rf.gab_weights[c][1];
+    p.epf.channel_scale[c] = rf.epf.channel_scale[c];
+  }
+  p.epf_iters = int(rf.epf.iters);
+  p.epf.pass0_sigma_scale = rf.epf.pass0_sigma_scale;
+  p.epf.pass2_sigma_scale = rf.epf.pass2_sigma_scale;
+  p.epf.border_sad_mul = rf.epf.border_sad_mul;
+  p.epf.sigma_for_modular = rf.epf.sigma_for_modular;
+  if (!sigma_is_constant && rf.epf.iters > 0) {
+    const PlaneRec& s = planes_.at(sigma.plane);
+    p.sigma = static_cast<const float*>(s.ptr);
+    p.sigma_stride = s.w;
+  }
+  if (colour) {
+    p.colour = 1;
+    for (int i = 0; i < 3; ++i) {
+      p.col.opsin_bias[i] = colour->opsin_bias[i];
+      p.col.cbrt_opsin_bias[i] = colour->cbrt_opsin_bias[i];
+    }
+    p.col.itscale = colour->itscale;
+    for (int i = 0; i < 9; ++i) p.col.matrix[i] = colour->matrix[i];
+    p.col.apply_srgb_tf = colour->apply_srgb_tf ? 1 : 0;
+  }
+  begin_k("filters_fused");
+  launch_filters_fused(in, out, p, stream_);
+  end_k();
+  for (int c = 0; c < 3; ++c) {
+    PlaneRec& r = planes_.at(v[c].plane);
+    dfree(r.ptr);
+    r.ptr = out_ptr[c];
+  }
+  return true;
+}
+
 void CudaBackend::upsample(View*, uint32_t, uint32_t, const ImageHeader&) {
   fail(kErrUnsupported, "non-separable upsampling is not implemented yet");
 }

@@ -42,6 +42,8 @@ class CudaBackend : public Backend {
   void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) override;
   void upsample(View v[3], uint32_t num_channels, uint32_t factor_log2, const ImageHeader& ih) override;
   void xyb_to_rgb(const View v[3], const ColorParams& p) override;
+  bool filters_colour_fused(const View v[3], const RestorationFilter& rf, const View& sigma, bool sigma_is_constant,
+                            const ColorParams* colour) override;
   void stage_marker(const char* name, const View* views, int n) override;
   void phase_mark(const char* name) override;
 
@@ -61,6 +63,7 @@ class CudaBackend : public Backend {
   // launch accounting for bench.py ("gpu_launches")
   uint64_t launches = 0;
   // per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline
+  bool fuse_filters = true;  // single-kernel Gaborish+EPF+colour (off: stage-by-stage, for stage parity tests)
   bool profile = false;
   double phase_t0_ = -1.0;  // wall clock (ms) of the previous phase_mark
   std::map<std::string, std::pair<uint64_t, double>> profile_acc;  // name -> (launches, total ms)

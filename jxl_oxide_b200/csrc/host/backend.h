@@ -124,6 +124,12 @@ class Backend {
   virtual void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) = 0;
   virtual void upsample(View v[3], uint32_t num_channels, uint32_t factor_log2, const ImageHeader& ih) = 0;
   virtual void xyb_to_rgb(const View v[3], const ColorParams& p) = 0;
+  // Optional single-pass form of gaborish() + epf() + xyb_to_rgb() (`colour` may be null). Returns
+  // false when the backend wants the stages issued one by one.
+  virtual bool filters_colour_fused(const View /*v*/[3], const RestorationFilter& /*rf*/, const View& /*sigma*/,
+                                    bool /*sigma_is_constant*/, const ColorParams* /*colour*/) {
+    return false;
+  }
   // Called by the planner at stage boundaries; a backend may snapshot planes for tests.
   virtual void stage_marker(const char* /*name*/, const View* /*views*/, int /*n*/) {}
   // Profiling hook: the planner finished the named host phase (wall clock since the previous mark).

@@ -86,7 +86,8 @@ class FramePlanner {
   void run_inverse_transforms(const ModularStreamSyntax& s, std::vector<ChanBuf>& bufs);
   void setup_gmodular();
   void render_vardct(DecodedFrame* out);
-  void finish_colour(std::vector<View>& colour, bool is_xyb, DecodedFrame* out);
+  bool colour_params(bool is_xyb, size_t num_colour, ColorParams* p);
+  void finish_colour(std::vector<View>& colour, bool is_xyb, bool already_converted, DecodedFrame* out);
 
   Backend& be_;
   const uint8_t* cs_;
@@ -525,23 +526,32 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
 
   // restoration filters (render.rs:76-131)
   const RestorationFilter& rf = fh_.restoration_filter;
+  JXLB_CHECK(fh_.upsampling == 1, kErrUnsupported, "non-separable upsampling is not implemented yet");
+  bool colour_done = false;
   if (rf.gab_enabled || rf.epf.iters > 0) {
     JXLB_CHECK(colour.size() == 3, kErrUnsupported, "restoration filters on grayscale frames are not supported");
     View v[3] = {colour[0], colour[1], colour[2]};
-    if (rf.gab_enabled) {
-      be_.gaborish(v, rf.gab_weights);
-      be_.stage_marker("gaborish", v, 3);
-    }
-    if (rf.epf.iters > 0) {
-      View sigma;
-      if (vardct) sigma = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
-      be_.epf(v, sigma, rf.epf, !vardct);
-      be_.stage_marker("epf", v, 3);
+    View sigma_view;
+    if (vardct) sigma_view = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
+    ColorParams cp;
+    const bool want_colour = colour_params(ih_.xyb_encoded, colour.size(), &cp);
+    if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
+      colour_done = want_colour;
+      if (want_colour) be_.stage_marker("rgb", v, 3);
+    } else {
+      if (rf.gab_enabled) {
+        be_.gaborish(v, rf.gab_weights);
+        be_.stage_marker("gaborish", v, 3);
+      }
+      if (rf.epf.iters > 0) {
+        be_.epf(v, sigma_view, rf.epf, !vardct);
+        be_.stage_marker("epf", v, 3);
+      }
     }
   }
-  JXLB_CHECK(fh_.upsampling == 1, kErrUnsupported, "non-separable upsampling is not implemented yet");
 
-  finish_colour(colour, ih_.xyb_encoded, &out);
+  be_.phase_mark("filters");
+  finish_colour(colour, ih_.xyb_encoded, colour_done, &out);
   for (size_t c = ec_from; c < gm_image.size() && (c - ec_from) < ih_.ec_info.size(); ++c) {
     View v = gm_image[c].view;
     be_.int_to_float(v, ih_.ec_info[c - ec_from].bit_depth);
@@ -590,27 +600,33 @@ void FramePlanner::render_vardct(DecodedFrame*) {
   }
 }
 
-void FramePlanner::finish_colour(std::vector<View>& colour, bool is_xyb, DecodedFrame* out) {
-  // postprocess_keyframe (jxl-render/src/lib.rs:925-998) for the supported colour set.
-  if (is_xyb && opt_.output_colour != 2) {
-    JXLB_CHECK(colour.size() == 3, kErrBitstream, "XYB needs three channels");
-    const ColourEncoding& ce = ih_.colour_encoding;
-    bool srgb_like = !ce.want_icc && ce.colour_space == ColourSpace::kRgb && ce.white_point == WhitePointKind::kD65 &&
-                     ce.primaries == PrimariesKind::kSrgb &&
-                     (ce.tf == TransferFunctionKind::kSrgb || ce.tf == TransferFunctionKind::kLinear);
-    JXLB_CHECK(srgb_like || opt_.output_colour == 1, kErrUnsupported,
-               "only sRGB-gamut (sRGB/linear transfer) output encodings are implemented");
-    JXLB_CHECK(ih_.tone_mapping.intensity_target <= 255.0f || opt_.output_colour == 1, kErrUnsupported,
-               "HDR tone mapping is outside the implemented hot path");
-    ColorParams p;
-    const OpsinInverseMatrix& oim = ih_.opsin_inverse_matrix;
-    for (int i = 0; i < 3; ++i) {
-      p.opsin_bias[i] = oim.opsin_bias[i];
-      p.cbrt_opsin_bias[i] = cbrtf(oim.opsin_bias[i]);
-      for (int j = 0; j < 3; ++j) p.matrix[i * 3 + j] = oim.inv_mat[i][j];
-    }
-    p.itscale = 255.0f / ih_.tone_mapping.intensity_target;
-    p.apply_srgb_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kSrgb;
+// postprocess_keyframe (jxl-render/src/lib.rs:925-998) for the supported colour set: fills the
+// XYB -> (linear) sRGB parameters; false when the planes are left as they are.
+bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p) {
+  if (!is_xyb || opt_.output_colour == 2) return false;
+  JXLB_CHECK(num_colour == 3, kErrBitstream, "XYB needs three channels");
+  const ColourEncoding& ce = ih_.colour_encoding;
+  bool srgb_like = !ce.want_icc && ce.colour_space == ColourSpace::kRgb && ce.white_point == WhitePointKind::kD65 &&
+                   ce.primaries == PrimariesKind::kSrgb &&
+                   (ce.tf == TransferFunctionKind::kSrgb || ce.tf == TransferFunctionKind::kLinear);
+  JXLB_CHECK(srgb_like || opt_.output_colour == 1, kErrUnsupported,
+             "only sRGB-gamut (sRGB/linear transfer) output encodings are implemented");
+  JXLB_CHECK(ih_.tone_mapping.intensity_target <= 255.0f || opt_.output_colour == 1, kErrUnsupported,
+             "HDR tone mapping is outside the implemented hot path");
+  const OpsinInverseMatrix& oim = ih_.opsin_inverse_matrix;
+  for (int i = 0; i < 3; ++i) {
+    p->opsin_bias[i] = oim.opsin_bias[i];
+    p->cbrt_opsin_bias[i] = cbrtf(oim.opsin_bias[i]);
+    for (int j = 0; j < 3; ++j) p->matrix[i * 3 + j] = oim.inv_mat[i][j];
+  }
+  p->itscale = 255.0f / ih_.tone_mapping.intensity_target;
+  p->apply_srgb_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kSrgb;
+  return true;
+}
+
+void FramePlanner::finish_colour(std::vector<View>& colour, bool is_xyb, bool already_converted, DecodedFrame* out) {
+  ColorParams p;
+  if (!already_converted && colour_params(is_xyb, colour.size(), &p)) {
     View v[3] = {colour[0], colour[1], colour[2]};
     be_.xyb_to_rgb(v, p);
     be_.stage_marker("rgb", v, 3);

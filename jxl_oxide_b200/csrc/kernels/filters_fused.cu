@@ -1,0 +1,326 @@
+// Fused restoration-filter chain: Gaborish -> EPF step 0/1/2 -> XYB->RGB in ONE kernel.
+//
+// Unfused, every stage is an HBM->HBM pass over three f32 planes (24 B/px each: up to 120 B/px
+// for Gaborish + 3 EPF steps + colour). Here a CTA owns a 32x32 output tile, loads the tile plus
+// the halo the enabled stages need (<= 7 px) into shared memory once, runs the stages ping-pong
+// between two shared buffers and writes the final pixels: 12 B/px read (+halo, served by L2) and
+// 12 B/px written.
+//
+// Per-pixel arithmetic and its order are those of the stand-alone kernels in filters.cu, i.e. the
+// reference's generic path (crates/jxl-render/src/filter/impls/generic/{gabor.rs,epf.rs},
+// crates/jxl-color/src/xyb.rs). Border semantics: Gaborish uses its own edge formulas on the image
+// border (gabor.rs:119-167); EPF mirrors coordinates (util.rs:376-386) -- after each stage the part
+// of the halo that lies outside the image is filled by mirroring, so the stencils index plainly.
+#include "kernels.h"
+
+#include <type_traits>
+
+namespace jxlb {
+
+namespace {
+
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+constexpr int kT = 32;            // output tile
+constexpr int kHM = 8;            // shared-memory margin (>= total stencil radius 7)
+constexpr int kS = kT + 2 * kHM;  // 48
+constexpr int kPlane = kS * kS;
+
+struct Rect {  // in shared-memory cell coordinates, half-open
+  int x0, y0, x1, y1;
+};
+
+__device__ __forceinline__ int mirror1(int v, int len) {  // single reflection (|overhang| <= 7 < len)
+  return v < 0 ? -v - 1 : (v >= len ? 2 * len - v - 1 : v);
+}
+
+// Gaborish at one in-image pixel; `a` points at the pixel in a shared plane (gabor.rs:3-167).
+__device__ __forceinline__ float gab_px(const float* a, int x, int y, int width, int height, float w0, float w1, float gw) {
+  auto at = [&](int dx, int dy) { return a[dy * kS + dx]; };
+  if (height == 1) {
+    if (width == 1) return at(0, 0);
+    const float merged_w0 = fadd(fadd(1.0f, 2.0f), w0);
+    const float merged_w1 = fadd(w0, fmul(2.0f, w1));
+    if (x == 0) return fmul(fadd(fmul(at(0, 0), fadd(merged_w0, merged_w1)), fmul(at(1, 0), merged_w1)), gw);
+    if (x == width - 1) return fmul(fadd(fmul(at(0, 0), fadd(merged_w0, merged_w1)), fmul(at(-1, 0), merged_w1)), gw);
+    return fmul(fadd(fmul(at(0, 0), merged_w0), fmul(fadd(at(-1, 0), at(1, 0)), merged_w1)), gw);
+  }
+  if (y == 0 || y == height - 1) {
+    const int ya = (y == 0) ? 1 : -1;  // the one adjacent row
+    if (width == 1) {
+      const float u = at(0, ya), c = at(0, 0);
+      return fmul(fadd(fmul(c, fadd(fadd(1.0f, fmul(3.0f, w0)), fmul(2.0f, w1))), fmul(u, fadd(w0, fmul(2.0f, w1)))), gw);
+    }
+    if (x == 0 || x == width - 1) {
+      const int xo = (x == 0) ? 1 : -1;
+      const float a1 = at(0, ya), a0 = at(xo, ya), c1 = at(0, 0), c0 = at(xo, 0);
+      return fmul(fadd(fadd(fmul(c1, fadd(fadd(1.0f, fmul(2.0f, w0)), w1)), fmul(fadd(a1, c0), fadd(w0, w1))), fmul(a0, w1)), gw);
+    }
+    const float a0 = at(-1, ya), a1 = at(0, ya), a2 = at(1, ya);
+    const float c0 = at(-1, 0), c1 = at(0, 0), c2 = at(1, 0);
+    return fmul(fadd(fadd(c1, fmul(fadd(fadd(fadd(a1, c0), c1), c2), w0)), fmul(fadd(fadd(fadd(a0, a2), c0), c2), w1)), gw);
+  }
+  if (width == 1) {
+    const float t = at(0, -1), c = at(0, 0), b = at(0, 1);
+    const float sum_side = fadd(fadd(t, fmul(2.0f, c)), b);
+    const float sum_diag = fmul(2.0f, fadd(t, b));
+    return fmul(fadd(fadd(c, fmul(sum_side, w0)), fmul(sum_diag, w1)), gw);
+  }
+  if (x == 0 || x == width - 1) {
+    const int xo = (x == 0) ? 1 : -1;
+    const float t1 = at(0, -1), c1 = at(0, 0), b1 = at(0, 1);
+    const float t0 = at(xo, -1), c0 = at(xo, 0), b0 = at(xo, 1);
+    const float sum_side = fadd(fadd(fadd(t1, c0), c1), b1);
+    const float sum_diag = fadd(fadd(fadd(t0, t1), b0), b1);
+    return fmul(fadd(fadd(c1, fmul(sum_side, w0)), fmul(sum_diag, w1)), gw);
+  }
+  const float sum_side = fadd(fadd(fadd(at(0, -1), at(-1, 0)), at(1, 0)), at(0, 1));
+  const float sum_diag = fadd(fadd(fadd(at(-1, -1), at(1, -1)), at(-1, 1)), at(1, 1));
+  return fmul(fadd(fadd(at(0, 0), fmul(sum_side, w0)), fmul(sum_diag, w1)), gw);
+}
+
+__device__ __constant__ const int8_t kFK1[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};
+__device__ __constant__ const int8_t kFK2[12][2] = {{0, -2}, {-1, -1}, {0, -1}, {1, -1}, {-2, 0}, {-1, 0},
+                                                    {1, 0},  {2, 0},   {-1, 1}, {0, 1},  {1, 1},  {0, 2}};
+__device__ __constant__ const int8_t kFD0[5][2] = {{0, -1}, {1, 0}, {0, 0}, {-1, 0}, {0, 1}};
+__device__ __constant__ const int8_t kFD1[5][2] = {{0, -1}, {0, 0}, {0, 1}, {-1, 0}, {1, 0}};
+
+// One EPF step at one pixel (impls/generic/epf.rs:3-210); `a` points at the pixel in channel 0 of
+// the input buffer (channels kPlane apart), halo already mirrored.
+template <int STEP>
+__device__ __forceinline__ void epf_px(const float* a, int x, int y, float sigma_val, const DevEpfParams& p, float o[3]) {
+  if (sigma_val < 0.3f) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = a[c * kPlane];
+    return;
+  }
+  const float step_multiplier = STEP == 0 ? p.pass0_sigma_scale : (STEP == 2 ? p.pass2_sigma_scale : 1.0f);
+  const bool is_y_border = ((y + 1) & 6) == 0;
+  float sm;
+  if (is_y_border) sm = fmul(step_multiplier, p.border_sad_mul);
+  else sm = ((x & 7) == 0 || (x & 7) == 7) ? fmul(step_multiplier, p.border_sad_mul) : step_multiplier;
+  const float neg_inv_sigma = fmul(fdiv(fmul(6.6f, fsub(0.70710678118654752440f, 1.0f)), sigma_val), sm);
+  float sum_weights = 1.0f;
+  float sum_channels[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sum_channels[c] = a[c * kPlane];
+  constexpr int NK = STEP == 0 ? 12 : 4;
+  constexpr int ND = STEP == 2 ? 1 : 5;
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int kx = STEP == 0 ? kFK2[k][0] : kFK1[k][0];
+    const int ky = STEP == 0 ? kFK2[k][1] : kFK1[k][1];
+    float dist = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < ND; ++i) {
+        const int ox = STEP == 2 ? 0 : (STEP == 0 ? kFD0[i][0] : kFD1[i][0]);
+        const int oy = STEP == 2 ? 0 : (STEP == 0 ? kFD0[i][1] : kFD1[i][1]);
+        acc = fadd(acc, fabsf(fsub(a[c * kPlane + (ky + oy) * kS + kx + ox], a[c * kPlane + oy * kS + ox])));
+      }
+      dist = fadd(dist, fmul(p.channel_scale[c], acc));
+    }
+    const float weight = fmaxf(fadd(1.0f, fmul(dist, neg_inv_sigma)), 0.0f);
+    sum_weights = fadd(sum_weights, weight);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sum_channels[c] = fadd(sum_channels[c], fmul(weight, a[c * kPlane + ky * kS + kx]));
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) o[c] = fdiv(sum_channels[c], sum_weights);
+}
+
+__device__ __constant__ const uint8_t kFPowUpper[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c,
+                                                        0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
+__device__ __constant__ const uint8_t kFPowLower[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68,
+                                                        0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};
+
+__device__ __forceinline__ float linear_to_srgb_f(float s) {  // tf/srgb.rs:28-47 (scalar path)
+  const uint32_t bits = __float_as_uint(s);
+  const uint32_t vb = bits & 0x7fffffffu;
+  const float v_adj = __uint_as_float((vb | 0x3e800000u) & 0x3effffffu);
+  float pow = 0.059914046f;
+  pow = fsub(fmul(pow, v_adj), 0.10889456f);
+  pow = fadd(fmul(pow, v_adj), 0.107963754f);
+  pow = fadd(fmul(pow, v_adj), 0.018092343f);
+  const uint32_t idx = ((vb >> 23) - 118) & 0xf;
+  const float mul = __uint_as_float(0x40000000u | (uint32_t(kFPowUpper[idx]) << 18) | (uint32_t(kFPowLower[idx]) << 10));
+  const float av = __uint_as_float(vb);
+  const float small = fmul(av, 12.92f);
+  const float acc = fsub(fmul(pow, mul), 0.055f);
+  const float res = av <= 0.0031308f ? small : acc;
+  return copysignf(res, s);
+}
+
+__device__ __forceinline__ void xyb_px(float o[3], const DevColorParams& p) {  // xyb.rs:35-60, ciexyz.rs:81-87
+  const float xx = o[0], yy = o[1], bb = o[2];
+  const float g_l = fsub(fadd(yy, xx), p.cbrt_opsin_bias[0]);
+  const float g_m = fsub(fsub(yy, xx), p.cbrt_opsin_bias[1]);
+  const float g_s = fsub(bb, p.cbrt_opsin_bias[2]);
+  const float a = fmul(__fmaf_rn(fmul(g_l, g_l), g_l, p.opsin_bias[0]), p.itscale);
+  const float b = fmul(__fmaf_rn(fmul(g_m, g_m), g_m, p.opsin_bias[1]), p.itscale);
+  const float c = fmul(__fmaf_rn(fmul(g_s, g_s), g_s, p.opsin_bias[2]), p.itscale);
+  const float* m = p.matrix;
+  o[0] = fadd(fadd(fmul(m[0], a), fmul(m[1], b)), fmul(m[2], c));
+  o[1] = fadd(fadd(fmul(m[3], a), fmul(m[4], b)), fmul(m[5], c));
+  o[2] = fadd(fadd(fmul(m[6], a), fmul(m[7], b)), fmul(m[8], c));
+  if (p.apply_srgb_tf) {
+    o[0] = linear_to_srgb_f(o[0]);
+    o[1] = linear_to_srgb_f(o[1]);
+    o[2] = linear_to_srgb_f(o[2]);
+  }
+}
+
+struct FusedViews {
+  const float* in[3];
+  float* out[3];
+  uint32_t in_stride[3], out_stride[3];
+  int width, height;
+};
+
+// Cells of `need` that lie outside the image take the value of their mirrored in-image cell.
+__device__ __forceinline__ void mirror_fill(float* buf, Rect need, int gx0, int gy0, int width, int height) {
+  for (int ly = need.y0 + int(threadIdx.y); ly < need.y1; ly += int(blockDim.y))
+    for (int lx = need.x0 + int(threadIdx.x); lx < need.x1; lx += int(blockDim.x)) {
+      const int gx = gx0 + lx, gy = gy0 + ly;
+      if (gx >= 0 && gx < width && gy >= 0 && gy < height) continue;
+      const int sx = mirror1(gx, width) - gx0, sy = mirror1(gy, height) - gy0;
+      // cells further outside than the remaining stencil reach mirror to sources left of / above
+      // the computed region; no stage reads them
+      if (sx < need.x0 || sy < need.y0) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) buf[c * kPlane + ly * kS + lx] = buf[c * kPlane + sy * kS + sx];
+    }
+}
+
+__global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFusedFilterParams p) {
+  extern __shared__ float s_buf[];
+  float* cur = s_buf;               // [3][kS][kS]
+  float* alt = s_buf + 3 * kPlane;
+  const int width = v.width, height = v.height;
+  // shared cell (lx, ly) <-> image pixel (gx0 + lx, gy0 + ly)
+  const int gx0 = int(blockIdx.x) * kT - kHM, gy0 = int(blockIdx.y) * kT - kHM;
+  const bool border_tile = gx0 < 0 || gy0 < 0 || gx0 + kS > width || gy0 + kS > height;
+  const int r_gab = p.gab_enabled ? 1 : 0;
+  const int r0 = p.epf_iters == 3 ? 3 : 0, r1 = p.epf_iters >= 1 ? 2 : 0, r2 = p.epf_iters >= 2 ? 1 : 0;
+  int halo = r_gab + r0 + r1 + r2;
+  auto rect = [&](int h) { return Rect{kHM - h, kHM - h, kHM + kT + h, kHM + kT + h}; };
+  auto clip = [&](Rect r) {  // to the image
+    r.x0 = max(r.x0, -gx0), r.y0 = max(r.y0, -gy0);
+    r.x1 = min(r.x1, width - gx0), r.y1 = min(r.y1, height - gy0);
+    return r;
+  };
+
+  {  // load the input region
+    const Rect r = clip(rect(halo));
+    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
+      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          cur[c * kPlane + ly * kS + lx] = v.in[c][size_t(gy0 + ly) * v.in_stride[c] + gx0 + lx];
+      }
+  }
+  __syncthreads();
+
+  if (p.gab_enabled) {
+    halo -= 1;
+    const Rect r = clip(rect(halo));
+    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
+      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float w0 = p.gab_w[c][0], w1 = p.gab_w[c][1];
+          const float gw = fdiv(1.0f, fadd(fadd(1.0f, fmul(w0, 4.0f)), fmul(w1, 4.0f)));
+          alt[c * kPlane + ly * kS + lx] = gab_px(cur + c * kPlane + ly * kS + lx, gx0 + lx, gy0 + ly, width, height, w0, w1, gw);
+        }
+      }
+    float* t = cur;
+    cur = alt;
+    alt = t;
+    __syncthreads();
+  }
+  if (p.epf_iters > 0 && border_tile) {  // EPF reads mirrored pixels beyond the image border
+    mirror_fill(cur, rect(halo), gx0, gy0, width, height);
+    __syncthreads();
+  }
+
+  auto epf_stage = [&](auto step_tag, int radius, bool last) {
+    constexpr int STEP = decltype(step_tag)::value;
+    halo -= radius;
+    const Rect r = clip(rect(halo));
+    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
+      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
+        const int x = gx0 + lx, y = gy0 + ly;
+        const float sigma_val = p.sigma ? __ldg(p.sigma + size_t(y >> 3) * p.sigma_stride + (x >> 3)) : p.epf.sigma_for_modular;
+        float o[3];
+        epf_px<STEP>(cur + ly * kS + lx, x, y, sigma_val, p.epf, o);
+        if (last) {
+          if (p.colour) xyb_px(o, p.col);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) alt[c * kPlane + ly * kS + lx] = o[c];
+        }
+      }
+    if (!last) {
+      float* t = cur;
+      cur = alt;
+      alt = t;
+      __syncthreads();
+      if (border_tile) {
+        mirror_fill(cur, rect(halo), gx0, gy0, width, height);
+        __syncthreads();
+      }
+    }
+  };
+  if (p.epf_iters == 3) epf_stage(std::integral_constant<int, 0>{}, 3, false);
+  if (p.epf_iters >= 1) epf_stage(std::integral_constant<int, 1>{}, 2, p.epf_iters == 1);
+  if (p.epf_iters >= 2) epf_stage(std::integral_constant<int, 2>{}, 1, true);
+
+  if (p.epf_iters == 0) {  // Gaborish (or nothing) followed by colour only
+    const Rect r = clip(rect(0));
+    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
+      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[c] = cur[c * kPlane + ly * kS + lx];
+        if (p.colour) xyb_px(o, p.col);
+        const int x = gx0 + lx, y = gy0 + ly;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
+      }
+  }
+}
+
+}  // namespace
+
+bool fused_filters_supported(uint32_t width, uint32_t height) { return width >= 16 && height >= 16; }
+
+void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFilterParams p, cudaStream_t stream) {
+  FusedViews v;
+  for (int c = 0; c < 3; ++c) {
+    v.in[c] = static_cast<const float*>(in[c].ptr);
+    v.out[c] = static_cast<float*>(out[c].ptr);
+    v.in_stride[c] = in[c].stride;
+    v.out_stride[c] = out[c].stride;
+  }
+  v.width = int(in[0].w);
+  v.height = int(in[0].h);
+  if (!v.width || !v.height) return;
+  constexpr size_t smem = size_t(2) * 3 * kPlane * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(fused_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attr_set = true;
+  }
+  dim3 block(32, 8);
+  dim3 grid((v.width + kT - 1) / kT, (v.height + kT - 1) / kT);
+  fused_filter_kernel<<<grid, block, smem, stream>>>(v, p);
+}
+
+}  // namespace jxlb

@@ -145,5 +145,18 @@ struct DevColorParams {
 };
 void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream);
 void launch_copy_rect(DevView src, DevView dst, cudaStream_t stream);
+// Gaborish -> EPF -> colour in one kernel (kernels/filters_fused.cu); `in` and `out` must not alias.
+struct DevFusedFilterParams {
+  int gab_enabled;
+  float gab_w[3][2];
+  int epf_iters;  // 0..3
+  DevEpfParams epf;
+  const float* sigma;  // per-8x8-block sigma grid, or nullptr for the constant sigma_for_modular
+  uint32_t sigma_stride;
+  int colour;  // apply XYB -> RGB to the final pixels
+  DevColorParams col;
+};
+void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFilterParams p, cudaStream_t stream);
+bool fused_filters_supported(uint32_t width, uint32_t height);
 
 }  // namespace jxlb

@@ -57,6 +57,20 @@ def test_modular_bench_files_bit_exact(dec, oracle, name):
 
 
 def _check_vardct(dec, oracle, data):
+    # production path: Gaborish + EPF + colour fused into one kernel -> final pixels only
+    dec.set_fuse_filters(True)
+    got, want, img = _decode_both(dec, oracle, data)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "fused filter chain differs"
+    # stage by stage
+    dec.set_fuse_filters(False)
+    try:
+        _check_vardct_stages(dec, oracle, data)
+    finally:
+        dec.set_fuse_filters(True)
+
+
+def _check_vardct_stages(dec, oracle, data):
     got, want, img = _decode_both(dec, oracle, data, capture=True)
     # integer stage: HF coefficients must be identical
     for g, w in zip(dec.stage("hf_coeff", np.int32), img.stage("hf_coeff", np.int32)):
@@ -125,3 +139,12 @@ def test_synthetic_vardct_frames_bit_exact(dec, oracle, size, seed, extra):
     WP- or gradient-coded LF, EPF 2 iterations."""
     import bench
     _check_vardct(dec, oracle, bench.synth_frame(size[0], size[1], seed, extra=extra))
+
+
+@pytest.mark.parametrize("output_colour", [1, 2])
+def test_fused_filters_other_output_encodings(dec, oracle, output_colour):
+    """Linear-sRGB and XYB outputs go through the fused Gaborish+EPF(+colour) kernel as well."""
+    dec.set_fuse_filters(True)
+    for name in ("opsin_inverse",):
+        got, want, _ = _decode_both(dec, oracle, fixture_bytes(name, "input.jxl"), output_colour=output_colour)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -24,10 +24,11 @@ def latency(path, n=5):
         d.release_frames()
     dt = (time.time() - t) / n
     info = {k: round(d.profile(k)[1] / n, 2) for k in ("modular_decode", "build_block_info", "decode_hf", "hf_dequant_cfl",
-                                                          "hf_transform", "gaborish", "epf_step", "xyb_to_rgb")}
+                                                          "hf_transform", "filters_fused", "gaborish", "epf_step", "xyb_to_rgb")}
     print('%s: %.2f ms/frame; kernel ms/frame: %s' % (path.split('/')[-1], dt * 1e3, info))
     host = {k: round(d.profile('host:' + k)[1] / n, 2) for k in ("lf_global", "alloc", "lf_coeff", "mlf", "hf_metadata", "hf_global",
-                                                                  "pass_groups", "inverse_transforms", "render_vardct", "filters_colour")}
+                                                                  "pass_groups", "inverse_transforms", "render_vardct", "filters",
+                                                                  "filters_colour")}
     print('   wall ms per host phase (device waits included): %s' % host)
     d.close()
 
