@@ -83,10 +83,16 @@ uint64_t jxlb_launch_count(const jxlb_decoder* dec);
 
 /* Per-kernel device timing: when on, every launch is bracketed by CUDA events on the decoder's
  * stream; jxlb_profile_get returns launches and accumulated milliseconds for a kernel family
- * ("modular_decode", "decode_hf", "hf_transform", "epf_step", ...). Used by bench.py's roofline. */
+ * ("modular_decode", "decode_hf", "hf_transform", "epf_step", ...). Used by bench.py's roofline.
+ * on == 2 selects a lighter trace instead: no events, the Modular stream kernels stamp the device
+ * clock and the host logs launch / return times (see jxlb_timeline_get). */
 int32_t jxlb_set_profile(jxlb_decoder* dec, int32_t on);
 int32_t jxlb_profile_get(jxlb_decoder* dec, const char* name, uint64_t* launches, double* total_ms);
 int32_t jxlb_profile_reset(jxlb_decoder* dec);
+/* Timeline of the profiled launches / host phases since the last reset: returns the number of
+ * entries; when `index` is valid also its name and [t0, t1] in ms since a process-wide origin that
+ * is common to all decoders (tracing aid, mirrors the reference's `tracing` spans). */
+int32_t jxlb_timeline_get(jxlb_decoder* dec, int32_t index, char* name, size_t name_cap, double* t0_ms, double* t1_ms);
 
 /* Test / debugging hook: snapshot intermediate stages ("lf", "hf_coeff", "hf_dequant", "idct",
  * "pre_filter", "gaborish", "epf", "rgb") of the LAST decoded frame to host memory. */

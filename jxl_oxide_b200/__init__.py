@@ -9,6 +9,11 @@ There is no CPU fallback: importing works anywhere (so the C ABI can be inspecte
 decoder without a CUDA device raises JxlError.
 """
 import ctypes
+import os as _os
+
+# One decoder context = one CUDA stream; give concurrent contexts their own hardware work queues
+# (must be set before the CUDA context is created).
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import os
 
 import numpy as np
@@ -24,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "jxlb_image_get_info",
     "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
-    "jxlb_profile_reset", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_stage_count", "jxlb_stage_get",
+    "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_stage_count", "jxlb_stage_get",
     "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse",
 ]
 
@@ -98,6 +103,7 @@ def load_library():
     L.jxlb_set_profile.argtypes = [vp, i32]
     L.jxlb_profile_get.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double)]
     L.jxlb_profile_reset.argtypes = [vp]
+    L.jxlb_timeline_get.argtypes = [vp, i32, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.jxlb_stage_count.argtypes = [vp, ctypes.c_char_p]
     L.jxlb_stage_get.argtypes = [vp, ctypes.c_char_p, i32, ctypes.POINTER(u32), ctypes.POINTER(u32), vp]
     L.jxlb_gaborish.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, ctypes.POINTER(ctypes.c_float)]
@@ -191,6 +197,17 @@ class Decoder:
 
     def set_capture(self, on=True):
         self._L.jxlb_set_capture(self._h, int(on))
+
+    def timeline(self):
+        """[(name, t0_ms, t1_ms)] of the profiled launches / host phases since profile_reset()."""
+        n = self._L.jxlb_timeline_get(self._h, -1, None, 0, None, None)
+        out = []
+        buf = ctypes.create_string_buffer(64)
+        t0, t1 = ctypes.c_double(), ctypes.c_double()
+        for i in range(max(n, 0)):
+            self._L.jxlb_timeline_get(self._h, i, buf, 64, ctypes.byref(t0), ctypes.byref(t1))
+            out.append((buf.value.decode(), t0.value, t1.value))
+        return out
 
     def set_fuse_filters(self, on=True):
         self._L.jxlb_set_fuse_filters(self._h, int(on))

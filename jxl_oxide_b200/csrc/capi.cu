@@ -1,5 +1,6 @@
 // extern "C" boundary of libjxlb200.so — see include/jxlb200.h for the contract.
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -190,7 +191,8 @@ uint64_t jxlb_launch_count(const jxlb_decoder* dec) { return dec ? dec->be->laun
 
 int32_t jxlb_set_profile(jxlb_decoder* dec, int32_t on) {
   if (!dec) return JXLB_ERR_INVALID_ARG;
-  dec->be->profile = on != 0;
+  dec->be->profile = on == 1;       // CUDA events around every launch + host phase clock
+  dec->be->trace_device = on == 2;  // no events: device-clock stamps in the stream kernels + host launch/return times
   return JXLB_OK;
 }
 
@@ -204,11 +206,28 @@ int32_t jxlb_profile_get(jxlb_decoder* dec, const char* name, uint64_t* launches
   });
 }
 
+int32_t jxlb_timeline_get(jxlb_decoder* dec, int32_t index, char* name, size_t name_cap, double* t0_ms, double* t1_ms) {
+  if (!dec) return -1;
+  int32_t n = -1;
+  guarded(dec, [&] {
+    dec->be->sync();
+    n = int32_t(dec->be->timeline.size());
+    if (index >= 0 && index < n && name && name_cap && t0_ms && t1_ms) {
+      const auto& e = dec->be->timeline[size_t(index)];
+      std::snprintf(name, name_cap, "%s", e.name.c_str());
+      *t0_ms = e.t0_ms;
+      *t1_ms = e.t1_ms;
+    }
+  });
+  return n;
+}
+
 int32_t jxlb_profile_reset(jxlb_decoder* dec) {
   if (!dec) return JXLB_ERR_INVALID_ARG;
   return guarded(dec, [&] {
     dec->be->sync();
     dec->be->profile_acc.clear();
+    dec->be->timeline.clear();
   });
 }
 

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <tuple>
@@ -27,12 +28,26 @@ CudaBackend::CudaBackend(int device) : device_(device) {
     fail(kErrCuda, "no CUDA device available: the jxl_oxide_b200 hot path has no CPU fallback");
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
-  // Keep freed stream-ordered allocations in the pool: a frame's planes are reused by the next
-  // frame instead of being returned to the driver at every synchronisation.
-  cudaMemPool_t pool;
-  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device_));
+  // A private stream-ordered pool per decoder: freed planes are reused by this decoder's next frame
+  // (release threshold = never trim), and an allocation never has to wait on another decoder's
+  // stream the way reuse inside the shared default pool can.
+  if (!std::getenv("JXLB_SHARED_POOL")) {
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device_;
+    CUDA_CHECK(cudaMemPoolCreate(&pool_, &props));
+  } else {
+    CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool_, device_));
+  }
   uint64_t keep = UINT64_MAX;
-  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool_, cudaMemPoolAttrReleaseThreshold, &keep));
+  // All kernels of the library ask for the same (maximum shared memory) L1/shared split: an SM only
+  // changes its split when idle, so kernels with different splits cannot share an SM, and the
+  // long-running one-warp entropy CTAs would otherwise fence other streams' kernels off their SMs.
+  if (!std::getenv("JXLB_NO_CARVEOUT")) CUDA_CHECK(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
 }
 
 CudaBackend::~CudaBackend() {
@@ -45,12 +60,13 @@ CudaBackend::~CudaBackend() {
   if (d_dequant_) cudaFree(d_dequant_);
   if (d_dequant_default_) cudaFree(d_dequant_default_);
   if (stream_) cudaStreamDestroy(stream_);
+  if (pool_ && !std::getenv("JXLB_SHARED_POOL")) cudaMemPoolDestroy(pool_);
 }
 
 void* CudaBackend::dmalloc(size_t bytes) {
   void* p = nullptr;
   CUDA_CHECK(cudaSetDevice(device_));
-  CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream_));
+  CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), pool_, stream_));
   return p;
 }
 void CudaBackend::dfree(void* p) {
@@ -71,9 +87,40 @@ void CudaBackend::sync() {
   resolve_profile();
 }
 
+namespace {
+// Process-wide time origin shared by all decoders: a device event and the host clock sampled
+// together after a device synchronisation.
+struct TimeOrigin {
+  cudaEvent_t ev = nullptr;
+  double host_ms = 0.0;
+  unsigned long long dev_ns = 0;  // %globaltimer at the origin
+};
+double host_now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+TimeOrigin& time_origin() {
+  static TimeOrigin o = [] {
+    TimeOrigin t;
+    cudaEventCreate(&t.ev);
+    cudaDeviceSynchronize();
+    cudaEventRecord(t.ev, 0);
+    cudaEventSynchronize(t.ev);
+    unsigned long long* d = nullptr;
+    cudaMalloc(&d, 8);
+    launch_read_globaltimer(d, 0);
+    cudaMemcpy(&t.dev_ns, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    t.host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    return t;
+  }();
+  return o;
+}
+}  // namespace
+
 void CudaBackend::begin_k(const char* name) {
   ++launches;
   if (!profile) return;
+  time_origin();
   PendingTiming t;
   t.name = name;
   CUDA_CHECK(cudaEventCreate(&t.e0));
@@ -94,6 +141,9 @@ void CudaBackend::resolve_profile() {
       auto& acc = profile_acc[t.name];
       acc.first += 1;
       acc.second += double(ms);
+      float since = 0.0f;
+      if (cudaEventElapsedTime(&since, time_origin().ev, t.e0) == cudaSuccess)
+        timeline.push_back({t.name, double(since), double(since) + double(ms)});
     }
     cudaEventDestroy(t.e0);
     cudaEventDestroy(t.e1);
@@ -221,6 +271,7 @@ void CudaBackend::phase_mark(const char* name) {
     auto& acc = profile_acc[std::string("host:") + name];
     acc.first += 1;
     acc.second += now - phase_t0_;
+    timeline.push_back({std::string("host:") + name, phase_t0_ - time_origin().host_ms, now - time_origin().host_ms});
   }
   phase_t0_ = now;
 }
@@ -593,14 +644,34 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   temps_.push_back(d_end);
   temps_.push_back(d_status);
   const DevChannelPlan* d_plans = static_cast<const DevChannelPlan*>(upload_temp(dplans.data(), dplans.size() * sizeof(DevChannelPlan)));
+  unsigned long long* d_trace = nullptr;
+  double host_launch = 0.0;
+  if (trace_device) {
+    time_origin();
+    d_trace = static_cast<unsigned long long*>(dmalloc(jobs.size() * 16));
+    temps_.push_back(d_trace);
+    host_launch = host_now_ms();
+  }
   begin_k("modular_decode");
-  launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, stream_);
+  launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, stream_, d_trace);
   end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());
   CUDA_CHECK(cudaMemcpyAsync(end.data(), d_end, jobs.size() * 8, cudaMemcpyDeviceToHost, stream_));
   CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
+  std::vector<unsigned long long> trace(d_trace ? jobs.size() * 2 : 0);
+  if (d_trace) CUDA_CHECK(cudaMemcpyAsync(trace.data(), d_trace, trace.size() * 8, cudaMemcpyDeviceToHost, stream_));
   sync();
+  if (d_trace) {
+    const TimeOrigin& o = time_origin();
+    unsigned long long first = ~0ull, last = 0;
+    for (size_t i = 0; i < jobs.size(); ++i) {
+      first = std::min(first, trace[2 * i]);
+      last = std::max(last, trace[2 * i + 1]);
+    }
+    timeline.push_back({"host:launch_to_return modular", host_launch - o.host_ms, host_now_ms() - o.host_ms});
+    timeline.push_back({"dev:modular_decode", (double(first) - double(o.dev_ns)) * 1e-6, (double(last) - double(o.dev_ns)) * 1e-6});
+  }
   CUDA_CHECK(cudaGetLastError());
   release_temps();
   for (size_t i = 0; i < jobs.size(); ++i) {

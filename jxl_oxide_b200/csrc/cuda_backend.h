@@ -65,6 +65,7 @@ class CudaBackend : public Backend {
   // per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline
   bool fuse_filters = true;  // single-kernel Gaborish+EPF+colour (off: stage-by-stage, for stage parity tests)
   bool profile = false;
+  bool trace_device = false;  // modular streams stamp the device clock; host launch/return times are logged
   double phase_t0_ = -1.0;  // wall clock (ms) of the previous phase_mark
   std::map<std::string, std::pair<uint64_t, double>> profile_acc;  // name -> (launches, total ms)
   void resolve_profile();
@@ -94,8 +95,20 @@ class CudaBackend : public Backend {
   };
   std::vector<PendingTiming> pending_;
 
+ public:
+  // Profiling timeline: every kernel launch and host phase with start/end in ms since a
+  // process-wide reference point (device events and host clock are aligned at that point).
+  struct TimelineEntry {
+    std::string name;
+    double t0_ms, t1_ms;
+  };
+  std::vector<TimelineEntry> timeline;
+
+ private:
+
   int device_;
   cudaStream_t stream_ = nullptr;
+  cudaMemPool_t pool_ = nullptr;  // this decoder's own stream-ordered pool (no cross-stream reuse dependencies)
   uint8_t* d_codestream_ = nullptr;
   const uint8_t* active_cs_ = nullptr;
   const uint8_t* resident_next_ = nullptr;

@@ -52,7 +52,9 @@ struct DevView {
 // Modular ------------------------------------------------------------------------------------
 void launch_modular_decode(const uint8_t* codestream, const DevModularJob* jobs, const DevChannel* channels,
                            const DevChannelPlan* plans, uint64_t* end_bits, int* status, int num_jobs,
-                           size_t smem_bytes, cudaStream_t stream);
+                           size_t smem_bytes, cudaStream_t stream, unsigned long long* trace = nullptr);
+// tracing aid: writes the device's %globaltimer (ns)
+void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream);
 // bytes of dynamic shared memory a job wants for its tree / entropy tables / WP rows / LUTs
 size_t modular_job_smem_bytes(const DevModularJob& job, uint32_t max_width);
 void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizontal, cudaStream_t stream);

@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
                                                             const DevChannel* __restrict__ channels,
                                                             const DevChannelPlan* __restrict__ plans,
                                                             uint64_t* __restrict__ end_bits, int* __restrict__ status,
-                                                            int num_jobs) {
+                                                            int num_jobs, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int job_idx = blockIdx.x;
   if (job_idx >= num_jobs) return;
@@ -543,6 +543,11 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
   int32_t* wp_rows = (L.wp != 0xffffffffu) ? reinterpret_cast<int32_t*>(smem + L.wp) : job.wp_scratch;
   __syncwarp();
   if (lane != 0) return;
+  if (trace) {  // tracing aid: device clock (ns) when this stream starts / ends decoding
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    trace[2 * job_idx] = now;
+  }
 
   // ---- serial decode (lane 0) ----
   StreamState s;
@@ -579,6 +584,17 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
   if (s.err == kDevOk && s.br.pos > job.bit_limit) s.err = kDevOverrun;
   end_bits[job_idx] = s.br.pos;
   status[job_idx] = s.err;
+  if (trace) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    trace[2 * job_idx + 1] = now;
+  }
+}
+
+__global__ void read_globaltimer_kernel(unsigned long long* out) {
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  *out = now;
 }
 
 }  // namespace
@@ -589,14 +605,16 @@ size_t modular_job_smem_bytes(const DevModularJob& job, uint32_t max_width) {
 
 void launch_modular_decode(const uint8_t* cs, const DevModularJob* jobs, const DevChannel* channels,
                            const DevChannelPlan* plans, uint64_t* end_bits, int* status, int num_jobs, size_t smem_bytes,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, unsigned long long* trace) {
   if (num_jobs <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(modular_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  modular_stream_kernel<<<num_jobs, 32, smem_bytes, stream>>>(cs, jobs, channels, plans, end_bits, status, num_jobs);
+  modular_stream_kernel<<<num_jobs, 32, smem_bytes, stream>>>(cs, jobs, channels, plans, end_bits, status, num_jobs, trace);
 }
+
+void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream) { read_globaltimer_kernel<<<1, 1, 0, stream>>>(out); }
 
 }  // namespace jxlb
