@@ -813,6 +813,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     p.orders = static_cast<const uint32_t*>(upload_temp(custom.data(), custom.size() * 4));
   }
   p.block_ctx_map = static_cast<const uint8_t*>(upload_temp(hbc.block_ctx_map.data(), hbc.block_ctx_map.size()));
+  p.block_ctx_map_size = uint32_t(hbc.block_ctx_map.size());
   std::vector<int32_t> thr;
   for (int c = 0; c < 3; ++c) {
     p.num_lf_thr[c] = uint32_t(hbc.lf_thresholds[c].size());

@@ -33,10 +33,14 @@ __device__ __constant__ const uint8_t kTInfo[27][5] = {
     {32, 32, 15, 11, 1}, {16, 32, 16, 12, 1}, {32, 16, 16, 12, 0},
 };
 
-constexpr int kHfWarpsPerCta = 2;
+constexpr int kHfWarpsPerCta = 4;
+constexpr uint32_t kHfAnsSmemBytes = 128 * 1024;
 
+// Shared-memory layout of one CTA (4 streams): everything a coefficient symbol touches is staged --
+// the two context LUTs, hybrid-uint configs, the block-context map, each warp's own preset slice of
+// the cluster map, and the ANS alias tables (up to 128 KB; real libjxl d1 frames need ~86 KB).
 struct HfSmem {
-  uint32_t cmap, configs, ans, ctxlut, total;
+  uint32_t ctxlut, configs, bctx, cmap, cmap_stride, ans, total;
 };
 __host__ __device__ inline HfSmem hf_layout(const DevHfParams& p) {
   HfSmem L;
@@ -48,10 +52,11 @@ __host__ __device__ inline HfSmem hf_layout(const DevHfParams& p) {
   };
   L.ctxlut = take(128);
   L.configs = take(p.code.num_clusters * 4);
-  // the per-preset cluster map slice: shared only when a single preset exists
-  L.cmap = (p.num_hf_presets == 1) ? take(495 * p.num_block_clusters) : 0xffffffffu;
+  L.bctx = take(p.block_ctx_map_size);
+  L.cmap_stride = (495 * p.num_block_clusters + 15) & ~15u;
+  L.cmap = take(L.cmap_stride * kHfWarpsPerCta);
   uint32_t ab = p.code.use_prefix ? 0 : (p.code.num_clusters << p.code.log_alphabet_size) * 8;
-  L.ans = (!p.code.use_prefix && ab <= 48 * 1024) ? take(ab) : 0xffffffffu;
+  L.ans = (!p.code.use_prefix && ab <= kHfAnsSmemBytes) ? take(ab) : 0xffffffffu;
   L.total = off;
   return L;
 }
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ uint32_t s_nz[kHfWarpsPerCta][3][32];
   const HfSmem L = hf_layout(p);
-  const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
+  const uint32_t tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
   // ---- stage tables (whole CTA) ----
   uint8_t* s_ctx = smem + L.ctxlut;  // [0..63): freq ctx, [64..127): nonzero ctx
   for (uint32_t i = tid; i < 63; i += nthreads) {
@@ -74,12 +79,8 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
   }
   uint32_t* s_cfg = reinterpret_cast<uint32_t*>(smem + L.configs);
   for (uint32_t i = tid; i < p.code.num_clusters; i += nthreads) s_cfg[i] = __ldg(p.code.configs + i);
-  const uint8_t* cmap_base = p.code.cluster_map;
-  if (L.cmap != 0xffffffffu) {
-    uint8_t* s_cmap = smem + L.cmap;
-    for (uint32_t i = tid; i < 495 * p.num_block_clusters; i += nthreads) s_cmap[i] = __ldg(p.code.cluster_map + i);
-    cmap_base = s_cmap;
-  }
+  uint8_t* s_bctx = smem + L.bctx;
+  for (uint32_t i = tid; i < p.block_ctx_map_size; i += nthreads) s_bctx[i] = __ldg(p.block_ctx_map + i);
   CodeView cv;
   cv.log_alphabet_size = p.code.log_alphabet_size;
   cv.use_prefix = p.code.use_prefix;
@@ -88,35 +89,48 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
   cv.prefix = p.code.prefix;
   cv.prefix_meta = p.code.prefix_meta;
   if (L.ans != 0xffffffffu) {
-    uint32_t* s_ans = reinterpret_cast<uint32_t*>(smem + L.ans);
-    const uint32_t words = (p.code.num_clusters << p.code.log_alphabet_size) * 2;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.code.ans);
-    for (uint32_t i = tid; i < words; i += nthreads) s_ans[i] = __ldg(src + i);
+    uint4* s_ans = reinterpret_cast<uint4*>(smem + L.ans);
+    const uint32_t quads = (p.code.num_clusters << p.code.log_alphabet_size) / 2;  // 2 buckets per 16 bytes
+    const uint4* src = reinterpret_cast<const uint4*>(p.code.ans);
+    for (uint32_t i = tid; i < quads; i += nthreads) s_ans[i] = __ldg(src + i);
     cv.ans = reinterpret_cast<const uint64_t*>(s_ans);
   }
-  __syncthreads();
-  const int job_idx = blockIdx.x * kHfWarpsPerCta + int(tid >> 5);
-  if (job_idx >= num_jobs || (tid & 31) != 0) return;
-
-  const DevHfJob job = jobs[job_idx];
+  // ---- per-warp: stream header (HF preset) and that preset's cluster-map slice ----
+  const int job_idx = blockIdx.x * kHfWarpsPerCta + int(warp);
+  const bool active = job_idx < num_jobs;
   const uint32_t nbc = p.num_block_clusters;
+  DevBitReader br;
+  int err = kDevOk;
+  uint32_t hfp = 0;
+  DevHfJob job;
+  job.bit_pos = 0, job.bit_limit = 0, job.group_idx = 0;
+  if (active) {
+    job = jobs[job_idx];
+    br.init(cs, job.bit_pos);
+    uint32_t hfp_bits = 0;
+    while ((1u << hfp_bits) < p.num_hf_presets) ++hfp_bits;
+    hfp = br.read(hfp_bits);  // every lane reads the same bits
+    if (hfp >= p.num_hf_presets) {
+      err = kDevInvalid;
+      hfp = 0;
+    }
+    uint8_t* dst = smem + L.cmap + warp * L.cmap_stride;
+    const uint8_t* src = p.code.cluster_map + size_t(495) * nbc * hfp;
+    for (uint32_t i = lane; i < 495 * nbc; i += 32) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  if (!active || lane != 0) return;
+
+  const uint8_t* cluster_map = smem + L.cmap + warp * L.cmap_stride;
   const uint32_t lf_idx_mul = (p.num_lf_thr[0] + 1) * (p.num_lf_thr[1] + 1) * (p.num_lf_thr[2] + 1);
   const uint32_t hf_idx_mul = p.num_qf_thr + 1;
-  DevBitReader br;
-  br.init(cs, job.bit_pos);
-  int err = kDevOk;
-  uint32_t hfp_bits = 0;
-  while ((1u << hfp_bits) < p.num_hf_presets) ++hfp_bits;
-  const uint32_t hfp = br.read(hfp_bits);
-  if (hfp >= p.num_hf_presets) err = kDevInvalid;
-  const uint8_t* cluster_map = (L.cmap != 0xffffffffu) ? cmap_base : cmap_base + size_t(495) * nbc * (err ? 0 : hfp);
   uint32_t ans_state = p.code.use_prefix ? 0x130000u : br.read(32);
 
   const uint32_t gx = job.group_idx % p.groups_per_row, gy = job.group_idx / p.groups_per_row;
   const uint32_t gb = p.group_dim_blocks;
   const uint32_t bx0 = gx * gb, by0 = gy * gb;
   const uint32_t width = min(gb, f.bw - bx0), height = min(gb, f.bh - by0);
-  uint32_t(*nz_row)[32] = s_nz[tid >> 5];
+  uint32_t(*nz_row)[32] = s_nz[warp];
   for (int c = 0; c < 3; ++c)
     for (int i = 0; i < 32; ++i) nz_row[c][i] = 0;
   const int32_t* thr_base[3] = {p.lf_thresholds, p.lf_thresholds + p.num_lf_thr[0],
@@ -140,9 +154,11 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
         for (int k = 0; k < 3; ++k) {
           const int c = cs3[k];
           lf_idx *= p.num_lf_thr[c] + 1;
-          const int32_t q = f.lf_quant[c][gi];
-          for (uint32_t i = 0; i < p.num_lf_thr[c]; ++i)
-            if (q > thr_base[c][i]) ++lf_idx;
+          if (p.num_lf_thr[c]) {
+            const int32_t q = f.lf_quant[c][gi];
+            for (uint32_t i = 0; i < p.num_lf_thr[c]; ++i)
+              if (q > thr_base[c][i]) ++lf_idx;
+          }
         }
       }
       uint32_t hf_idx = 0;
@@ -153,7 +169,7 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
         const uint32_t ch_idx = uint32_t(ci) * 13 + order_id;
         const int c = (ci == 0) ? 1 : (ci == 1 ? 0 : 2);
         const uint32_t idx = (ch_idx * hf_idx_mul + hf_idx) * lf_idx_mul + lf_idx;
-        const uint32_t block_ctx = p.block_ctx_map[idx];
+        const uint32_t block_ctx = s_bctx[idx];
         uint32_t predicted;
         const uint32_t nz_here = nz_row[c][x];
         const uint32_t nz_left = x ? nz_row[c][x - 1] : 0;
@@ -177,13 +193,10 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
         const uint8_t* cmap = cluster_map + block_ctx * 458 + 37 * nbc;
         uint32_t* plane = f.coeff[c];
         const size_t base = (size_t(by0 + y) * 8) * f.cw + size_t(bx0 + x) * 8;
-        uint32_t o_next = __ldg(order + num_blocks);
+        // context term of the remaining-non-zeros count; changes only after a non-zero coefficient
+        uint32_t nzc_ctx = s_ctx[64 + ((non_zeros - 1) >> num_blocks_log)];
         for (uint32_t k = num_blocks, i = 0; k < size; ++k, ++i) {
-          const uint32_t o = o_next;
-          if (k + 1 < size) o_next = __ldg(order + k + 1);
-          const uint32_t nzc = (non_zeros - 1) >> num_blocks_log;
-          const uint32_t fi = i >> num_blocks_log;
-          const uint32_t cctx = (uint32_t(s_ctx[64 + nzc]) + uint32_t(s_ctx[fi])) * 2 + prev_nonzero;
+          const uint32_t cctx = (nzc_ctx + uint32_t(s_ctx[i >> num_blocks_log])) * 2 + prev_nonzero;
           if (cctx >= 458) {
             err = kDevInvalid;
             break;
@@ -194,6 +207,8 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
             prev_nonzero = 0;
             continue;
           }
+          // the coefficient's position feeds only the store, never the decode chain
+          const uint32_t o = __ldg(order + k);
           const uint32_t cvv = uint32_t(dev_unpack_signed(ucoeff)) << p.coeff_shift;
           uint32_t dx = o & 0xffff, dy = o >> 16;
           if (transpose) {
@@ -206,6 +221,7 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
           else *dst += cvv;
           prev_nonzero = 1;
           if (--non_zeros == 0) break;
+          nzc_ctx = s_ctx[64 + ((non_zeros - 1) >> num_blocks_log)];
         }
         if (br.pos > job.bit_limit) err = kDevOverrun;
       }
@@ -223,7 +239,7 @@ void launch_decode_hf(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJ
   if (num_jobs <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(decode_hf_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(decode_hf_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   const HfSmem L = hf_layout(p);

@@ -98,6 +98,7 @@ struct DevHfParams {
   const uint32_t* orders;         // concatenated order tables (x | y << 16)
   uint32_t order_offset[13 * 3];  // [order_id * 3 + channel] into `orders`
   const uint8_t* block_ctx_map;
+  uint32_t block_ctx_map_size;
   const int32_t* lf_thresholds;   // concatenated X, Y, B
   uint32_t num_lf_thr[3];
   const uint32_t* qf_thresholds;
