@@ -241,6 +241,9 @@ def run_ours(args, rank, world, local_rank):
     total_px = px_per_frame * len(frames) * world
     value = total_px / (ms / args.steps / 1e3) / 1e6
     e2e_value = total_px / (ms_e2e / args.steps / 1e3) / 1e6
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peaks = {}

@@ -1055,8 +1055,51 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
   return true;
 }
 
-void CudaBackend::upsample(View*, uint32_t, uint32_t, const ImageHeader&) {
-  fail(kErrUnsupported, "non-separable upsampling is not implemented yet");
+int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) {
+  DevView cur = dev_view(v);
+  void* cur_owned = nullptr;
+  uint32_t w = v.w, h = v.h;
+  auto pass = [&](uint32_t k, const std::vector<float>& weights) {
+    // per-phase 5x5 kernels from the symmetric weight list (upsampling.rs:66-92)
+    const uint32_t mat_n = k / 2;
+    std::vector<float> quarter(size_t(k) * k / 4 * 25, 0.0f);
+    size_t weight_idx = 0;
+    for (uint32_t y = 0; y < 5 * mat_n; ++y) {
+      const uint32_t mat_y = y / 5, ky = y % 5;
+      for (uint32_t x = y; x < 5 * mat_n; ++x) {
+        const uint32_t mat_x = x / 5, kx = x % 5;
+        const float wv = weights[weight_idx++];
+        quarter[size_t(mat_y * mat_n + mat_x) * 25 + ky * 5 + kx] = wv;
+        quarter[size_t(mat_x * mat_n + mat_y) * 25 + kx * 5 + ky] = wv;
+      }
+    }
+    const float* d_quarter = static_cast<const float*>(upload_temp(quarter.data(), quarter.size() * 4));
+    DevView out;
+    out.w = w * k;
+    out.h = h * k;
+    out.stride = out.w;
+    out.ptr = dmalloc(size_t(out.w) * out.h * 4);
+    begin_k("upsample");
+    launch_upsample(cur, out, int(k), d_quarter, stream_);
+    end_k();
+    if (cur_owned) dfree(cur_owned);
+    cur = out;
+    cur_owned = out.ptr;
+    w *= k;
+    h *= k;
+  };
+  JXLB_CHECK(v.w >= 2 && v.h >= 2, kErrUnsupported, "upsampling of images narrower than 2 samples is not implemented");
+  for (uint32_t i = 0; i < factor_log2 / 3; ++i) pass(8, ih.up8_weight);
+  if (factor_log2 % 3 == 1) pass(2, ih.up2_weight);
+  if (factor_log2 % 3 == 2) pass(4, ih.up4_weight);
+  JXLB_CHECK(cur_owned != nullptr, kErrInvalidArg, "upsample called with factor 1");
+  PlaneRec r;
+  r.w = w;
+  r.h = h;
+  r.ptr = cur_owned;
+  int id = next_id_++;
+  planes_[id] = r;
+  return id;
 }
 
 void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {

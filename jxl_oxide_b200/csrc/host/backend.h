@@ -122,7 +122,8 @@ class Backend {
   // restoration filters and colour, on the (width x height) window of three planes
   virtual void gaborish(const View v[3], const float weights[3][2]) = 0;
   virtual void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) = 0;
-  virtual void upsample(View v[3], uint32_t num_channels, uint32_t factor_log2, const ImageHeader& ih) = 0;
+  // features/upsampling.rs: returns a new plane of (v.w << factor_log2) x (v.h << factor_log2) f32 samples
+  virtual int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) = 0;
   virtual void xyb_to_rgb(const View v[3], const ColorParams& p) = 0;
   // Optional single-pass form of gaborish() + epf() + xyb_to_rgb() (`colour` may be null). Returns
   // false when the backend wants the stages issued one by one.

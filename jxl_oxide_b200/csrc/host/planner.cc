@@ -526,7 +526,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
 
   // restoration filters (render.rs:76-131)
   const RestorationFilter& rf = fh_.restoration_filter;
-  JXLB_CHECK(fh_.upsampling == 1, kErrUnsupported, "non-separable upsampling is not implemented yet");
+  const bool upsampled = fh_.upsampling > 1;
   bool colour_done = false;
   if (rf.gab_enabled || rf.epf.iters > 0) {
     JXLB_CHECK(colour.size() == 3, kErrUnsupported, "restoration filters on grayscale frames are not supported");
@@ -534,7 +534,8 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     View sigma_view;
     if (vardct) sigma_view = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
     ColorParams cp;
-    const bool want_colour = colour_params(ih_.xyb_encoded, colour.size(), &cp);
+    // colour conversion follows upsampling (render.rs:136-149), so it is fused only without it
+    const bool want_colour = !upsampled && colour_params(ih_.xyb_encoded, colour.size(), &cp);
     if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
       colour_done = want_colour;
       if (want_colour) be_.stage_marker("rgb", v, 3);
@@ -551,10 +552,24 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   }
 
   be_.phase_mark("filters");
+  // non-separable upsampling of every channel (render.rs:136-183), cropped to the frame size
+  auto upsample_view = [&](View& v) {
+    const uint32_t factor_log2 = ceil_log2_nonzero(fh_.upsampling);
+    int id = be_.upsample(v, factor_log2, ih_);
+    frame_planes_.push_back(id);
+    v = View{id, 0, 0, std::min(v.w << factor_log2, fh_.width), std::min(v.h << factor_log2, fh_.height)};
+  };
+  if (upsampled) {
+    for (View& v : colour) upsample_view(v);
+    out.width = fh_.width;
+    out.height = fh_.height;
+    be_.stage_marker("upsampled", colour.data(), int(colour.size()));
+  }
   finish_colour(colour, ih_.xyb_encoded, colour_done, &out);
   for (size_t c = ec_from; c < gm_image.size() && (c - ec_from) < ih_.ec_info.size(); ++c) {
     View v = gm_image[c].view;
     be_.int_to_float(v, ih_.ec_info[c - ec_from].bit_depth);
+    if (upsampled) upsample_view(v);
     out.channels.push_back(v);
   }
   // release everything not exported

@@ -196,7 +196,46 @@ __global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorPa
   *pb = o2;
 }
 
+// upsample_inner<K, NW> (features/upsampling.rs:45-132): one thread per output sample; the 5x5
+// neighbourhood is read with mirrored coordinates (== the reference's mirror-padded copy).
+__global__ void upsample_kernel(DevView in, DevView out, int k, const float* __restrict__ quarter) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= int(out.w) || y >= int(out.h)) return;
+  const int gw = int(in.w), gh = int(in.h), mat_n = k / 2;
+  const int ref_x = x / k, ref_y = y / k, px = x % k, py = y % k;
+  const int mat_x = min(px, k - px - 1), mat_y = min(py, k - py - 1);
+  const bool flip_h = px >= mat_n, flip_v = py >= mat_n;
+  const float* kernel = quarter + (mat_y * mat_n + mat_x) * 25;
+  const float* src = static_cast<const float*>(in.ptr);
+  float sum = 0.0f, mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int iy = 0; iy < 5; ++iy) {
+    const int ky = flip_v ? 4 - iy : iy;
+    const int sy = mirror(ref_y + iy - 2, gh);
+#pragma unroll
+    for (int ix = 0; ix < 5; ++ix) {
+      const int kx = flip_h ? 4 - ix : ix;
+      const int sx = mirror(ref_x + ix - 2, gw);
+      const float sample = src[size_t(sy) * in.stride + sx];
+      sum = fadd(sum, fmul(__ldg(kernel + ky * 5 + kx), sample));
+      mn = fminf(mn, sample);
+      mx = fmaxf(mx, sample);
+    }
+  }
+  float r;
+  if (!isfinite(mn)) r = __int_as_float(0x7fc00000);
+  else r = sum < mn ? mn : (sum > mx ? mx : sum);
+  static_cast<float*>(out.ptr)[size_t(y) * out.stride + x] = r;
+}
+
 }  // namespace
+
+void launch_upsample(DevView in, DevView out, int k, const float* quarter, cudaStream_t stream) {
+  if (!out.w || !out.h) return;
+  dim3 block(32, 8);
+  dim3 grid((out.w + 31) / 32, (out.h + 7) / 8);
+  upsample_kernel<<<grid, block, 0, stream>>>(in, out, k, quarter);
+}
 
 void launch_gaborish(DevView in, DevView out, float w0, float w1, cudaStream_t stream) {
   if (!in.w || !in.h) return;

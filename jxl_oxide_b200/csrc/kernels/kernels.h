@@ -148,6 +148,8 @@ struct DevColorParams {
 };
 void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream);
 void launch_copy_rect(DevView src, DevView dst, cudaStream_t stream);
+// One k-times upsampling pass (k = 2, 4, 8); `quarter`: (k/2)^2 kernels of 25 weights (device).
+void launch_upsample(DevView in, DevView out, int k, const float* quarter, cudaStream_t stream);
 // Gaborish -> EPF -> colour in one kernel (kernels/filters_fused.cu); `in` and `out` must not alias.
 struct DevFusedFilterParams {
   int gab_enabled;

@@ -4,6 +4,7 @@
 // filter/impls/generic/{gabor.rs,epf.rs}, features/upsampling.rs, image.rs:93-189 and
 // crates/jxl-color/src/{xyb.rs:35-60,ciexyz.rs:81-87,tf/srgb.rs:13-48}.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 
@@ -283,8 +284,84 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
   }
 }
 
-void OracleBackend::upsample(View*, uint32_t, uint32_t, const ImageHeader&) {
-  fail(kErrUnsupported, "upsampling not implemented in the oracle yet");
+// Non-separable upsampling (crates/jxl-render/src/features/upsampling.rs:5-132): log2 factor 3 is
+// one 8x pass, then at most one 2x / 4x pass; each pass is a 5x5 kernel per output phase built from
+// the symmetric weight list, mirror padding of 2 (util.rs:423-454), clamped to the local min/max.
+namespace {
+std::vector<float> upsample_pass(const std::vector<float>& in, size_t gw, size_t gh, size_t k,
+                                 const std::vector<float>& weights, OracleBackend* be) {
+  const size_t pad = 2, pw = gw + 2 * pad, ph = gh + 2 * pad;
+  std::vector<float> padded(pw * ph, 0.0f);
+  for (size_t y = 0; y < gh; ++y) std::memcpy(&padded[(y + pad) * pw + pad], &in[y * gw], gw * 4);
+  // mirror_edges_padding, literally
+  for (size_t y = pad; y < gh + pad; ++y)
+    for (size_t x = 0; x < pad; ++x) {
+      padded[y * pw + x] = padded[y * pw + pad * 2 - x - 1];
+      padded[(y + 1) * pw - x - 1] = padded[(y + 1) * pw - pad * 2 + x];
+    }
+  for (size_t r = 0; r < pad; ++r) {
+    std::memcpy(&padded[r * pw], &padded[(2 * pad - 1 - r) * pw], pw * 4);
+    std::memcpy(&padded[(gh + pad + r) * pw], &padded[(gh + pad - 1 - r) * pw], pw * 4);
+  }
+  const size_t mat_n = k / 2;
+  std::vector<std::array<float, 25>> quarter(k * k / 4);
+  for (auto& q : quarter) q.fill(0.0f);
+  size_t weight_idx = 0;
+  for (size_t y = 0; y < 5 * mat_n; ++y) {
+    const size_t mat_y = y / 5, ky = y % 5;
+    for (size_t x = y; x < 5 * mat_n; ++x) {
+      const size_t mat_x = x / 5, kx = x % 5;
+      const float w = weights[weight_idx++];
+      quarter[mat_y * mat_n + mat_x][ky * 5 + kx] = w;
+      quarter[mat_x * mat_n + mat_y][kx * 5 + ky] = w;
+    }
+  }
+  const size_t fw = gw * k, fh = gh * k;
+  std::vector<float> out(fw * fh);
+  be->parallel_for(fh, [&](size_t y) {
+    const size_t ref_y = y / k, mat_y = std::min(y % k, k - y % k - 1);
+    const bool flip_v = y % k >= mat_n;
+    for (size_t x = 0; x < fw; ++x) {
+      const size_t ref_x = x / k, mat_x = std::min(x % k, k - x % k - 1);
+      const bool flip_h = x % k >= mat_n;
+      const std::array<float, 25>& kernel = quarter[mat_y * mat_n + mat_x];
+      float sum = 0.0f, mn = INFINITY, mx = -INFINITY;
+      for (size_t iy = 0; iy < 5; ++iy) {
+        const size_t ky = flip_v ? 4 - iy : iy;
+        for (size_t ix = 0; ix < 5; ++ix) {
+          const size_t kx = flip_h ? 4 - ix : ix;
+          const float sample = padded[(ref_y + iy) * pw + (ref_x + ix)];
+          sum = sum + kernel[ky * 5 + kx] * sample;
+          mn = std::fmin(mn, sample);  // f32::min / f32::max ignore NaN operands, like fmin / fmax
+          mx = std::fmax(mx, sample);
+        }
+      }
+      float r;
+      if (!std::isfinite(mn)) r = NAN;
+      else r = sum < mn ? mn : (sum > mx ? mx : sum);  // f32::clamp
+      out[y * fw + x] = r;
+    }
+  });
+  return out;
+}
+}  // namespace
+
+int OracleBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) {
+  Plane& src = plane(v.plane);
+  size_t w = v.w, h = v.h;
+  std::vector<float> cur(w * h);
+  for (size_t y = 0; y < h; ++y) std::memcpy(&cur[y * w], src.f32() + (v.y0 + y) * size_t(src.w) + v.x0, w * 4);
+  auto pass = [&](size_t k, const std::vector<float>& weights) {
+    cur = upsample_pass(cur, w, h, k, weights, this);
+    w *= k;
+    h *= k;
+  };
+  for (uint32_t i = 0; i < factor_log2 / 3; ++i) pass(8, ih.up8_weight);
+  if (factor_log2 % 3 == 1) pass(2, ih.up2_weight);
+  if (factor_log2 % 3 == 2) pass(4, ih.up4_weight);
+  int id = alloc_plane(uint32_t(w), uint32_t(h), false);
+  std::memcpy(plane(id).f32(), cur.data(), cur.size() * 4);
+  return id;
 }
 
 // ---------------------------------------------------------------------------------------------

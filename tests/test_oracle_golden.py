@@ -42,6 +42,20 @@ def test_vardct_conformance_opsin_inverse(oracle):
     assert math.sqrt(float((diff ** 2).mean())) <= 0.004
 
 
+def test_vardct_conformance_upsampling(oracle):
+    """2x non-separable upsampling (features/upsampling.rs) + alpha, against libjxl's 8-bit rendering."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("upsampling", "input.jxl"), threads=4)
+    planes, ncol, is_vardct = img.frame(0)
+    assert is_vardct and planes.shape == (4, 600, 800)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("upsampling", "ref.png")))).astype(np.float32) / 255.0
+    ref = np.moveaxis(ref, 2, 0)
+    diff = np.abs(np.clip(planes, 0.0, 1.0) - ref)
+    assert diff.max() <= 0.004
+    assert math.sqrt(float((diff ** 2).mean())) <= 0.004
+
+
 def test_lz77_modular_vs_png(oracle):
     from PIL import Image
     import io
