@@ -28,6 +28,7 @@ CudaBackend::CudaBackend(int device) : device_(device) {
     fail(kErrCuda, "no CUDA device available: the jxl_oxide_b200 hot path has no CPU fallback");
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaEventCreateWithFlags(&sync_event_, cudaEventBlockingSync | cudaEventDisableTiming));
   // A private stream-ordered pool per decoder: freed planes are reused by this decoder's next frame
   // (release threshold = never trim), and an allocation never has to wait on another decoder's
   // stream the way reuse inside the shared default pool can.
@@ -59,6 +60,7 @@ CudaBackend::~CudaBackend() {
   if (d_natural_orders_) cudaFree(d_natural_orders_);
   if (d_dequant_) cudaFree(d_dequant_);
   if (d_dequant_default_) cudaFree(d_dequant_default_);
+  if (sync_event_) cudaEventDestroy(sync_event_);
   if (stream_) cudaStreamDestroy(stream_);
   if (pool_ && !std::getenv("JXLB_SHARED_POOL")) cudaMemPoolDestroy(pool_);
 }
@@ -83,7 +85,10 @@ void CudaBackend::release_temps() {
   temps_.clear();
 }
 void CudaBackend::sync() {
-  CUDA_CHECK(cudaStreamSynchronize(stream_));
+  // Wait on a blocking-sync event instead of spinning in cudaStreamSynchronize: a box drives many
+  // decoder contexts (x 8 GPUs) from host threads that mostly wait for 10-100 ms entropy kernels.
+  CUDA_CHECK(cudaEventRecord(sync_event_, stream_));
+  CUDA_CHECK(cudaEventSynchronize(sync_event_));
   resolve_profile();
 }
 
@@ -163,6 +168,8 @@ uint8_t* CudaBackend::upload_resident(const uint8_t* data, size_t size) {
 
 void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
   CUDA_CHECK(cudaSetDevice(device_));
+  stages.clear();  // stage snapshots belong to one decode call
+  stage_dims.clear();
   if (resident_next_) {  // encoded bytes already live in HBM (jxlb_preload)
     active_cs_ = resident_next_;
     resident_next_ = nullptr;

@@ -108,6 +108,7 @@ class CudaBackend : public Backend {
 
   int device_;
   cudaStream_t stream_ = nullptr;
+  cudaEvent_t sync_event_ = nullptr;
   cudaMemPool_t pool_ = nullptr;  // this decoder's own stream-ordered pool (no cross-stream reuse dependencies)
   uint8_t* d_codestream_ = nullptr;
   const uint8_t* active_cs_ = nullptr;
