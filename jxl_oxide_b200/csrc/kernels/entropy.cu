@@ -223,12 +223,12 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
           if (--non_zeros == 0) break;
           nzc_ctx = s_ctx[64 + ((non_zeros - 1) >> num_blocks_log)];
         }
-        if (br.pos > job.bit_limit) err = kDevOverrun;
+        if (br.pos() > job.bit_limit) err = kDevOverrun;
       }
     }
   if (err == kDevOk && !p.code.use_prefix && ans_state != 0x130000u) err = kDevBadStream;
-  if (err == kDevOk && br.pos > job.bit_limit) err = kDevOverrun;
-  end_bits[job_idx] = br.pos;
+  if (err == kDevOk && br.pos() > job.bit_limit) err = kDevOverrun;
+  end_bits[job_idx] = br.pos();
   status[job_idx] = err;
 }
 

@@ -254,9 +254,15 @@ struct StreamState {
   int err;
 };
 
-// read_varint_with_multiplier_clustered (lib.rs:476-569)
+// read_varint_with_multiplier_clustered (lib.rs:476-569). FAST: the stream is ANS-coded without LZ77
+// (what libjxl emits for LF / HfMetadata), decided once per stream instead of per sample.
+template <bool FAST>
 __device__ __forceinline__ uint32_t read_token_value(const CodeView& cv, const DevEntropyCode& code, StreamState& s,
                                                      uint32_t cluster, bool lz77, uint32_t dist_multiplier) {
+  if (FAST) {
+    const uint32_t token = cv_read_symbol_ans(cv, s.ans_state, s.br, cluster);
+    return cv_read_uint(s.br, cv.configs[cluster], token);
+  }
   if (!lz77) {
     const uint32_t token = cv_read_symbol(cv, s.ans_state, s.br, cluster);
     return cv_read_uint(s.br, cv.configs[cluster], token);
@@ -336,8 +342,9 @@ __device__ __noinline__ int32_t prev_channel_property(const DevChannel* prev, in
 }
 
 // One channel of a stream. WP: the stream's tree uses the weighted predictor (property 15 or
-// predictor 6); LUT: the channel's subtree tests one property (leaf LUT) instead of a tree walk.
-template <bool WP, bool LUT>
+// predictor 6); LUT: 0 = tree walk, 1 = the channel's subtree tests one property (leaf LUT over a
+// linear form), 2 = that property is the weighted predictor's max_error (libjxl's fixed LF tree).
+template <bool WP, int LUT, bool FAST>
 __device__ __forceinline__ void decode_channel(const DevModularJob& job, const DevEntropyCode& code, const CodeView& cv,
                                                const MaNode* tree, const uint16_t* lut, const DevChannelPlan plan,
                                                const DevChannel out, const DevChannel* prev, int nprev, uint32_t ci,
@@ -349,7 +356,7 @@ __device__ __forceinline__ void decode_channel(const DevModularJob& job, const D
   // prev_grad x y max_error), optionally |v|  (property list: predictor.rs:453-490)
   int32_t cw = 0, cn = 0, cnw = 0, cne = 0, cnn = 0, cww = 0, cpg = 0, cx = 0, cy = 0, cme = 0;
   bool use_abs = false;
-  if (LUT) {
+  if (LUT == 1) {
     switch (plan.lut_prop) {
       case 2: cy = 1; break;
       case 3: cx = 1; break;
@@ -409,7 +416,11 @@ __device__ __forceinline__ void decode_channel(const DevModularJob& job, const D
       const int32_t grad = wadd(w_nw, n);
       // ---- leaf selection ----
       uint32_t node_idx;
-      if (LUT) {
+      if (LUT == 2) {
+        const int32_t v = wp.max_error;
+        const uint32_t li = v < lut_base ? 0u : min(uint32_t(v) - uint32_t(lut_base), lut_last);
+        node_idx = lut[li];
+      } else if (LUT == 1) {
         const int32_t pre = cn * n + cnw * nw + cne * ne + cnn * nn + cx * int32_t(x) + cyy;
         int32_t v = pre + cw * wv + cww * wwv + cpg * prev_grad + (WP ? cme * wp.max_error : 0);
         if (use_abs) v = v < 0 ? int32_t(0u - uint32_t(v)) : v;
@@ -446,7 +457,7 @@ __device__ __forceinline__ void decode_channel(const DevModularJob& job, const D
       const MaNode leaf = tree[node_idx];
       const uint32_t predictor = leaf.a & 0xff, cluster = leaf.a >> 8;
       // ---- entropy decode (lib.rs:476-605) ----
-      const uint32_t token_value = read_token_value(cv, code, s, cluster, lz77, dist_multiplier);
+      const uint32_t token_value = read_token_value<FAST>(cv, code, s, cluster, lz77, dist_multiplier);
       const int32_t diff = wadd(wmul(dev_unpack_signed(token_value), int32_t(leaf.b)), leaf.value);
       int32_t pred;
       if (WP && predictor == 6) {
@@ -483,7 +494,7 @@ __device__ __forceinline__ void decode_channel(const DevModularJob& job, const D
     } else {
       for (uint32_t x = 0; x < width && s.err == kDevOk; ++x) sample(std::false_type{}, x);
     }
-    if (s.br.pos > job.bit_limit) s.err = kDevOverrun;
+    if (s.br.pos() > job.bit_limit) s.err = kDevOverrun;
   }
 }
 
@@ -571,18 +582,35 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
       if (p.w == out.w && p.h == out.h && p.hshift == out.hshift && p.vshift == out.vshift && p.w && p.h) prev[nprev++] = p;
     }
     const uint16_t* lut = luts + plan.lut_offset;
-    const bool use_lut = plan.lut_prop >= 0;
+    const int lut_kind = plan.lut_prop < 0 ? 0 : ((use_wp && plan.lut_prop == 15) ? 2 : 1);
+    const bool fast = !lz77 && !code.use_prefix;
+#define JXLB_DECODE_CHANNEL(WP_, LUT_, FAST_) \
+  decode_channel<WP_, LUT_, FAST_>(job, code, cv, tree, lut, plan, out, prev, nprev, ci, wp_rows, s_div, wp, s, lz77)
     if (use_wp) {
-      if (use_lut) decode_channel<true, true>(job, code, cv, tree, lut, plan, out, prev, nprev, ci, wp_rows, s_div, wp, s, lz77);
-      else decode_channel<true, false>(job, code, cv, tree, lut, plan, out, prev, nprev, ci, wp_rows, s_div, wp, s, lz77);
+      if (lut_kind == 2) {
+        if (fast) JXLB_DECODE_CHANNEL(true, 2, true);
+        else JXLB_DECODE_CHANNEL(true, 2, false);
+      } else if (lut_kind == 1) {
+        if (fast) JXLB_DECODE_CHANNEL(true, 1, true);
+        else JXLB_DECODE_CHANNEL(true, 1, false);
+      } else {
+        if (fast) JXLB_DECODE_CHANNEL(true, 0, true);
+        else JXLB_DECODE_CHANNEL(true, 0, false);
+      }
     } else {
-      if (use_lut) decode_channel<false, true>(job, code, cv, tree, lut, plan, out, prev, nprev, ci, wp_rows, s_div, wp, s, lz77);
-      else decode_channel<false, false>(job, code, cv, tree, lut, plan, out, prev, nprev, ci, wp_rows, s_div, wp, s, lz77);
+      if (lut_kind == 1) {
+        if (fast) JXLB_DECODE_CHANNEL(false, 1, true);
+        else JXLB_DECODE_CHANNEL(false, 1, false);
+      } else {
+        if (fast) JXLB_DECODE_CHANNEL(false, 0, true);
+        else JXLB_DECODE_CHANNEL(false, 0, false);
+      }
     }
+#undef JXLB_DECODE_CHANNEL
   }
   if (s.err == kDevOk && !code.use_prefix && s.ans_state != 0x130000u) s.err = kDevBadStream;
-  if (s.err == kDevOk && s.br.pos > job.bit_limit) s.err = kDevOverrun;
-  end_bits[job_idx] = s.br.pos;
+  if (s.err == kDevOk && s.br.pos() > job.bit_limit) s.err = kDevOverrun;
+  end_bits[job_idx] = s.br.pos();
   status[job_idx] = s.err;
   if (trace) {
     unsigned long long now;

@@ -31,18 +31,8 @@ struct CodeView {
   uint32_t log_alphabet_size, use_prefix;
 };
 
-__device__ __forceinline__ uint32_t cv_read_symbol(const CodeView& c, uint32_t& ans_state, DevBitReader& br, uint32_t cluster) {
-  if (c.use_prefix) {
-    uint32_t off = c.prefix_meta[cluster * 2], root_bits = c.prefix_meta[cluster * 2 + 1];
-    uint32_t peeked = br.peek(15);
-    uint32_t e = c.prefix[off + (peeked & ((1u << root_bits) - 1))];
-    if (e & 0x80000000u) {
-      uint32_t sb = (e >> 16) & 0xff;
-      e = c.prefix[off + (1u << root_bits) + (e & 0xffff) + ((peeked >> root_bits) & ((1u << sb) - 1))];
-    }
-    br.consume((e >> 16) & 0xff);
-    return e & 0xffff;
-  }
+// ANS symbol (ans.rs:276-330): alias-table lookup, state update, 16-bit refill.
+__device__ __forceinline__ uint32_t cv_read_symbol_ans(const CodeView& c, uint32_t& ans_state, DevBitReader& br, uint32_t cluster) {
   const uint32_t log_bucket = 12 - c.log_alphabet_size;
   uint32_t state = ans_state;
   uint32_t idx = state & 0xfff;
@@ -62,6 +52,21 @@ __device__ __forceinline__ uint32_t cv_read_symbol(const CodeView& c, uint32_t& 
   if (next < (1u << 16)) next = (next << 16) | br.read(16);
   ans_state = next;
   return symbol;
+}
+
+__device__ __forceinline__ uint32_t cv_read_symbol(const CodeView& c, uint32_t& ans_state, DevBitReader& br, uint32_t cluster) {
+  if (c.use_prefix) {  // prefix.rs:335-357
+    uint32_t off = c.prefix_meta[cluster * 2], root_bits = c.prefix_meta[cluster * 2 + 1];
+    uint32_t peeked = br.peek(15);
+    uint32_t e = c.prefix[off + (peeked & ((1u << root_bits) - 1))];
+    if (e & 0x80000000u) {
+      uint32_t sb = (e >> 16) & 0xff;
+      e = c.prefix[off + (1u << root_bits) + (e & 0xffff) + ((peeked >> root_bits) & ((1u << sb) - 1))];
+    }
+    br.consume((e >> 16) & 0xff);
+    return e & 0xffff;
+  }
+  return cv_read_symbol_ans(c, ans_state, br, cluster);
 }
 
 __device__ __forceinline__ uint32_t cv_read_uint(DevBitReader& br, uint32_t cfg, uint32_t token) {

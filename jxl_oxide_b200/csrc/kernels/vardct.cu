@@ -1,5 +1,4 @@
-// VarDCT stages on the device: HfMetadata placement scan, HF coefficient entropy decode, LF
-// dequant / chroma-from-luma / adaptive smoothing, HF dequant + chroma-from-luma, LLF insertion
+// VarDCT stages on the device: LF dequant / chroma-from-luma / adaptive smoothing, HF dequant + chroma-from-luma, LLF insertion
 // and the 27 inverse transforms. Float op order follows the reference's generic code path
 // (crates/jxl-render/src/vardct/{mod.rs,transform_common.rs,generic/*.rs}); this file is
 // compiled with -fmad=false and fuses only where the reference calls mul_add.
@@ -38,182 +37,6 @@ __device__ __forceinline__ const float* sec_half(int n) {
     case 128: return kSecLarge + 32;
     default: return kSecLarge + 96;
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// HfMetadata::parse placement scan (hf_metadata.rs:99-230): one thread per LF group.
-__global__ void build_block_info_kernel(DevFrame f, const DevBlockInfoJob* jobs, int num_jobs, float quant_mul_base,
-                                        const float* sharp_lut, int has_epf, int* status) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= num_jobs) return;
-  const DevBlockInfoJob job = jobs[j];
-  const DevLfGroupRect rc = job.rect;
-  const int32_t kUninit = INT32_MIN;
-  for (uint32_t y = 0; y < rc.bh; ++y)
-    for (uint32_t x = 0; x < rc.bw; ++x) f.blk_type[size_t(rc.by0 + y) * f.bw + rc.bx0 + x] = kUninit;
-  uint32_t data_idx = 0;
-  for (uint32_t y = 0; y < rc.bh; ++y) {
-    for (uint32_t x = 0; x < rc.bw;) {
-      if (f.blk_type[size_t(rc.by0 + y) * f.bw + rc.bx0 + x] != kUninit) {
-        ++x;
-        continue;
-      }
-      if (data_idx >= job.nb_blocks) {
-        status[j] = kDevInvalid;
-        return;
-      }
-      int32_t dct_select = job.raw[data_idx];
-      int32_t hf_mul = job.raw[job.raw_stride + data_idx] + 1;
-      if (dct_select < 0 || dct_select >= 27 || hf_mul <= 0) {
-        status[j] = kDevInvalid;
-        return;
-      }
-      uint32_t dw = kDevTransformInfo[dct_select][0], dh = kDevTransformInfo[dct_select][1];
-      if ((x % 32) + dw > 32 || (y % 32) + dh > 32 || x + dw > rc.bw || y + dh > rc.bh) {
-        status[j] = kDevInvalid;
-        return;
-      }
-      float sigma_q = __fdiv_rn(quant_mul_base, float(hf_mul));
-      for (uint32_t dy = 0; dy < dh; ++dy)
-        for (uint32_t dx = 0; dx < dw; ++dx) {
-          size_t gi = size_t(rc.by0 + y + dy) * f.bw + rc.bx0 + x + dx;
-          if (f.blk_type[gi] != kUninit) {
-            status[j] = kDevInvalid;
-            return;
-          }
-          f.blk_type[gi] = (dx == 0 && dy == 0) ? dct_select : -int32_t(1 + dx + 32 * dy);
-          f.blk_mul[gi] = hf_mul;
-          if (has_epf) {
-            int32_t s = f.sharpness[gi];
-            if (s < 0 || s >= 8) {
-              status[j] = kDevInvalid;
-              return;
-            }
-            f.epf_sigma[gi] = __fmul_rn(sigma_q, sharp_lut[s]);
-          }
-        }
-      ++data_idx;
-      x += dw;
-    }
-  }
-  status[j] = kDevOk;
-}
-
-// ---------------------------------------------------------------------------------------------
-// write_hf_coeff (jxl-vardct/src/hf_coeff.rs:21-252): one warp per (pass, 256x256 group); lane 0
-// runs the serial ANS / context chain.
-__global__ void decode_hf_kernel(const uint8_t* __restrict__ cs, DevFrame f, DevHfParams p,
-                                 const DevHfJob* __restrict__ jobs, uint64_t* __restrict__ end_bits,
-                                 int* __restrict__ status, int num_jobs) {
-  int job_idx = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32);
-  if (job_idx >= num_jobs || (threadIdx.x & 31) != 0) return;
-  const DevHfJob job = jobs[job_idx];
-  const uint32_t nbc = p.num_block_clusters;
-  const uint32_t lf_idx_mul = (p.num_lf_thr[0] + 1) * (p.num_lf_thr[1] + 1) * (p.num_lf_thr[2] + 1);
-  const uint32_t hf_idx_mul = p.num_qf_thr + 1;
-  DevBitReader br;
-  br.init(cs, job.bit_pos);
-  int err = kDevOk;
-  uint32_t hfp_bits = 0;
-  while ((1u << hfp_bits) < p.num_hf_presets) ++hfp_bits;
-  uint32_t hfp = br.read(hfp_bits);
-  if (hfp >= p.num_hf_presets) err = kDevInvalid;
-  const uint8_t* cluster_map = p.code.cluster_map + size_t(495) * nbc * (err ? 0 : hfp);
-  DevEntropyState es;
-  entropy_begin(p.code, es, br, nullptr);
-
-  const uint32_t gx = job.group_idx % p.groups_per_row, gy = job.group_idx / p.groups_per_row;
-  const uint32_t gb = p.group_dim_blocks;
-  const uint32_t bx0 = gx * gb, by0 = gy * gb;
-  const uint32_t width = min(gb, f.bw - bx0), height = min(gb, f.bh - by0);
-  uint32_t nz_row[3][32];
-  for (int c = 0; c < 3; ++c)
-    for (int i = 0; i < 32; ++i) nz_row[c][i] = 0;
-  const int32_t* thr_base[3] = {p.lf_thresholds, p.lf_thresholds + p.num_lf_thr[0],
-                                p.lf_thresholds + p.num_lf_thr[0] + p.num_lf_thr[1]};
-
-  for (uint32_t y = 0; y < height && err == kDevOk; ++y)
-    for (uint32_t x = 0; x < width && err == kDevOk; ++x) {
-      size_t gi = size_t(by0 + y) * f.bw + bx0 + x;
-      int32_t t = f.blk_type[gi];
-      if (t < 0) continue;
-      int32_t qf = f.blk_mul[gi];
-      const uint32_t w8 = kDevTransformInfo[t][0], h8 = kDevTransformInfo[t][1];
-      const uint32_t order_id = kDevTransformInfo[t][3];
-      const bool transpose = kDevTransformInfo[t][4] != 0;
-      const uint32_t num_blocks = w8 * h8;
-      const uint32_t num_blocks_log = 31u - uint32_t(__clz(int(num_blocks)));
-      uint32_t lf_idx = 0;
-      {
-        const int cs3[3] = {0, 2, 1};
-        for (int k = 0; k < 3; ++k) {
-          int c = cs3[k];
-          lf_idx *= p.num_lf_thr[c] + 1;
-          int32_t q = f.lf_quant[c][gi];
-          for (uint32_t i = 0; i < p.num_lf_thr[c]; ++i)
-            if (q > thr_base[c][i]) ++lf_idx;
-        }
-      }
-      uint32_t hf_idx = 0;
-      for (uint32_t i = 0; i < p.num_qf_thr; ++i)
-        if (qf > int32_t(p.qf_thresholds[i])) ++hf_idx;
-      for (int ci = 0; ci < 3 && err == kDevOk; ++ci) {
-        const uint32_t ch_idx = uint32_t(ci) * 13 + order_id;
-        const int c = (ci == 0) ? 1 : (ci == 1 ? 0 : 2);
-        const uint32_t idx = (ch_idx * hf_idx_mul + hf_idx) * lf_idx_mul + lf_idx;
-        const uint32_t block_ctx = p.block_ctx_map[idx];
-        uint32_t predicted;
-        if (y == 0) predicted = x == 0 ? 32 : nz_row[c][x - 1];
-        else if (x == 0) predicted = nz_row[c][x];
-        else predicted = (nz_row[c][x] + nz_row[c][x - 1] + 1) >> 1;
-        const uint32_t pidx = predicted >= 8 ? 4 + predicted / 2 : predicted;
-        const uint32_t nz_ctx = block_ctx + pidx * nbc;
-        uint32_t non_zeros = entropy_read_varint(p.code, es, br, cluster_map[nz_ctx], 0, err);
-        if (non_zeros > (63u << num_blocks_log)) {
-          err = kDevInvalid;
-          break;
-        }
-        const uint32_t nz_val = (non_zeros + num_blocks - 1) >> num_blocks_log;
-        for (uint32_t dx = 0; dx < w8; ++dx) nz_row[c][x + dx] = nz_val;
-        if (non_zeros == 0) continue;
-        uint32_t prev_nonzero = (non_zeros <= num_blocks * 4) ? 1 : 0;
-        const uint32_t* order = p.orders + p.order_offset[order_id * 3 + c];
-        const uint32_t size = num_blocks * 64;
-        const uint8_t* cmap = cluster_map + block_ctx * 458 + 37 * nbc;
-        uint32_t* plane = f.coeff[c];
-        for (uint32_t k = num_blocks, i = 0; k < size; ++k, ++i) {
-          const uint32_t nzc = (non_zeros - 1) >> num_blocks_log;
-          const uint32_t fi = i >> num_blocks_log;
-          const uint32_t cctx = (uint32_t(kCoeffNumNonzeroContext[nzc]) + uint32_t(kCoeffFreqContext[fi])) * 2 + prev_nonzero;
-          if (cctx >= 458) {
-            err = kDevInvalid;
-            break;
-          }
-          const uint32_t ucoeff = entropy_read_varint(p.code, es, br, cmap[cctx], 0, err);
-          if (ucoeff == 0) {
-            prev_nonzero = 0;
-            continue;
-          }
-          const uint32_t cv = uint32_t(dev_unpack_signed(ucoeff)) << p.coeff_shift;
-          const uint32_t o = __ldg(order + k);
-          uint32_t dx = o & 0xffff, dy = o >> 16;
-          if (transpose) {
-            uint32_t tmp = dx;
-            dx = dy;
-            dy = tmp;
-          }
-          const size_t px = size_t(bx0 + x) * 8 + dx, py = size_t(by0 + y) * 8 + dy;
-          plane[py * f.cw + px] += cv;
-          prev_nonzero = 1;
-          if (--non_zeros == 0) break;
-        }
-        if (br.pos > job.bit_limit) err = kDevOverrun;
-      }
-    }
-  if (err == kDevOk && !entropy_final_ok(p.code, es)) err = kDevBadStream;
-  if (err == kDevOk && br.pos > job.bit_limit) err = kDevOverrun;
-  end_bits[job_idx] = br.pos;
-  status[job_idx] = err;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -691,15 +514,207 @@ struct RegIdct<4> {
 
 // LLF of a multi-cell varblock: forward DCT of its bw x bh LF samples, rescaled
 // (transform_common.rs:33-58). `llf` holds bw*bh floats, `tmp` 3*max(bw,bh).
-__device__ void compute_llf_serial(const DevFrame& f, int c, uint32_t bx, uint32_t by, int bw, int bh, float* llf, float* tmp) {
-  const float* lf = f.lf[c];
-  for (int y = 0; y < bh; ++y)
-    for (int x = 0; x < bw; ++x) llf[y * bw + x] = lf[size_t(by + y) * f.bw + bx + x];
-  dct_2d_serial(Grid{llf, bw, bw, bh}, true, tmp);
+// Shapes up to 4x4 cells, by one thread in registers: exactly the branches dct_2d_serial() takes for
+// these sizes (generic/dct.rs:5-141), unrolled.
+__device__ __forceinline__ void llf_fwd4(float* a, int stride) {  // forward DCT-4 on a[0], a[stride], ...
+  float v[4] = {a[0], a[stride], a[2 * stride], a[3 * stride]};
+  dct4(v, true);
+  a[0] = v[0], a[stride] = v[1], a[2 * stride] = v[2], a[3 * stride] = v[3];
+}
+__device__ void compute_llf_small(const DevFrame& f, int c, uint32_t bx, uint32_t by, int bw, int bh, float* llf) {
+  const float* lf = f.lf[c] + size_t(by) * f.bw + bx;
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 0.0f;
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+      if (y < bh && x < bw) a[y * 4 + x] = lf[size_t(y) * f.bw + x];  // a[] has row stride 4 whatever bw is
+  const float mul = 0.5f;
+  if (bw == 2 && bh == 1) {
+    const float v0 = a[0], v1 = a[1];
+    a[0] = __fmul_rn(__fadd_rn(v0, v1), mul);
+    a[1] = __fmul_rn(__fsub_rn(v0, v1), mul);
+  } else if (bw == 1 && bh == 2) {
+    const float v0 = a[0], v1 = a[4];
+    a[0] = __fmul_rn(__fadd_rn(v0, v1), mul);
+    a[4] = __fmul_rn(__fsub_rn(v0, v1), mul);
+  } else if (bw == 2 && bh == 2) {
+    const float v00 = a[0], v01 = a[1], v10 = a[4], v11 = a[5];
+    a[0] = __fmul_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v00, v01), v10), v11), mul), mul);
+    a[1] = __fmul_rn(__fmul_rn(__fsub_rn(__fadd_rn(__fsub_rn(v00, v01), v10), v11), mul), mul);
+    a[4] = __fmul_rn(__fmul_rn(__fsub_rn(__fsub_rn(__fadd_rn(v00, v01), v10), v11), mul), mul);
+    a[5] = __fmul_rn(__fmul_rn(__fadd_rn(__fsub_rn(__fsub_rn(v00, v01), v10), v11), mul), mul);
+  } else if (bh == 1) {  // 4 x 1
+    llf_fwd4(a, 1);
+  } else if (bw == 1) {  // 1 x 4
+    llf_fwd4(a, 4);
+  } else if (bh == 2) {  // 4 x 2: butterflies down the columns, then the two rows
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      const float t0 = a[x], t1 = a[4 + x];
+      a[x] = __fmul_rn(__fadd_rn(t0, t1), mul);
+      a[4 + x] = __fmul_rn(__fsub_rn(t0, t1), mul);
+    }
+    llf_fwd4(a, 1);
+    llf_fwd4(a + 4, 1);
+  } else if (bw == 2) {  // 2 x 4: butterflies along the rows, then the two columns
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const float v0 = a[y * 4], v1 = a[y * 4 + 1];
+      a[y * 4] = __fmul_rn(__fadd_rn(v0, v1), mul);
+      a[y * 4 + 1] = __fmul_rn(__fsub_rn(v0, v1), mul);
+    }
+    llf_fwd4(a, 4);
+    llf_fwd4(a + 1, 4);
+  } else {  // 4 x 4: rows, then columns
+#pragma unroll
+    for (int y = 0; y < 4; ++y) llf_fwd4(a + y * 4, 1);
+#pragma unroll
+    for (int x = 0; x < 4; ++x) llf_fwd4(a + x, 4);
+  }
   const int logbw = 31 - __clz(bw), logbh = 31 - __clz(bh);
-  for (int y = 0; y < bh; ++y)
-    for (int x = 0; x < bw; ++x)
-      llf[y * bw + x] = __fdiv_rn(llf[y * bw + x], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+      if (y < bh && x < bw)
+        llf[y * bw + x] = __fdiv_rn(a[y * 4 + x], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+}
+
+// The nine "special" 8x8 transforms (generic/transform.rs:50-240) by the 8 threads of a group:
+// the same per-element operation sequences as transform_special(), with the independent 1-D
+// transforms / butterflies / dot products spread over the threads. `g`: the 8x8 block (row-major,
+// stride 8), `s`: 128 floats of scratch, both in shared memory; `r`: thread index in the group.
+__device__ __forceinline__ void idct4_strided(float* p, int stride) {
+  float v[4] = {p[0], p[stride], p[2 * stride], p[3 * stride]};
+  dct4(v, false);
+  p[0] = v[0], p[stride] = v[1], p[2 * stride] = v[2], p[3 * stride] = v[3];
+}
+__device__ __forceinline__ void idct8_contig(float* p) {
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = p[i];
+  RegIdct<8>::run(v);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = v[i];
+}
+
+__device__ void transform_special_coop(float* g, int type, float* s, int r, uint32_t gmask) {
+  auto aux_idct2_coop = [&](int size) {  // aux_idct2
+    const int n = size / 2;
+    for (int it = r; it < n * n; it += 8) {
+      const int y = it / n, x = it % n;
+      const float c00 = g[y * 8 + x], c01 = g[y * 8 + x + n], c10 = g[(y + n) * 8 + x], c11 = g[(y + n) * 8 + x + n];
+      s[(2 * y) * size + 2 * x] = __fadd_rn(__fadd_rn(__fadd_rn(c00, c01), c10), c11);
+      s[(2 * y) * size + 2 * x + 1] = __fsub_rn(__fsub_rn(__fadd_rn(c00, c01), c10), c11);
+      s[(2 * y + 1) * size + 2 * x] = __fsub_rn(__fadd_rn(__fsub_rn(c00, c01), c10), c11);
+      s[(2 * y + 1) * size + 2 * x + 1] = __fadd_rn(__fsub_rn(__fsub_rn(c00, c01), c10), c11);
+    }
+    __syncwarp(gmask);
+    for (int idx = r; idx < size * size; idx += 8) g[(idx / size) * 8 + idx % size] = s[idx];
+    __syncwarp(gmask);
+  };
+  if (type == 2) {  // Dct2
+    aux_idct2_coop(2);
+    aux_idct2_coop(4);
+    aux_idct2_coop(8);
+  } else if (type == 3 || type == 1) {  // Dct4 / Hornuss: four 4x4 sub-blocks of interleaved samples
+    aux_idct2_coop(2);
+    for (int e = r; e < 64; e += 8) {  // s[(y*2+x)*16 + iy*4 + ix] <- (Dct4: transposed) sample (x + 2ix, y + 2iy)
+      const int sub = e >> 4, iy = (e >> 2) & 3, ix = e & 3, y = sub >> 1, x = sub & 1;
+      const float v = g[(y + iy * 2) * 8 + x + ix * 2];
+      if (type == 3) s[sub * 16 + ix * 4 + iy] = v;
+      else s[sub * 16 + iy * 4 + ix] = v;
+    }
+    __syncwarp(gmask);
+    if (type == 3) {
+      for (int it = r; it < 16; it += 8) idct4_strided(s + (it >> 2) * 16 + (it & 3) * 4, 1);  // rows
+      __syncwarp(gmask);
+      for (int it = r; it < 16; it += 8) idct4_strided(s + (it >> 2) * 16 + (it & 3), 4);      // columns
+    } else if (r < 4) {
+      float* q = s + r * 16;
+      float residual_sum = 0.0f;
+      for (int i = 1; i < 16; ++i) residual_sum = __fadd_rn(residual_sum, q[i]);
+      const float avg = __fsub_rn(q[0], __fdiv_rn(residual_sum, 16.0f));
+      q[0] = q[5];
+      q[5] = 0.0f;
+      for (int i = 0; i < 16; ++i) q[i] = __fadd_rn(q[i], avg);
+    }
+    __syncwarp(gmask);
+    for (int e = r; e < 64; e += 8) {
+      const int sub = e >> 4, iy = (e >> 2) & 3, ix = e & 3, y = sub >> 1, x = sub & 1;
+      g[(y * 4 + iy) * 8 + x * 4 + ix] = s[sub * 16 + iy * 4 + ix];
+    }
+    __syncwarp(gmask);
+  } else if (type == 12 || type == 13) {  // Dct4x8 / Dct8x4
+    if (r == 0) {
+      const float coeff0 = g[0], coeff1 = g[8];
+      g[0] = __fadd_rn(coeff0, coeff1);
+      g[8] = __fsub_rn(coeff0, coeff1);
+    }
+    __syncwarp(gmask);
+    for (int e = r; e < 64; e += 8) {  // s[idx*32 + iy*8 + ix] <- sample (ix, 2iy + idx)
+      const int idx = e >> 5, iy = (e >> 3) & 3, ix = e & 7;
+      s[e] = g[(iy * 2 + idx) * 8 + ix];
+    }
+    __syncwarp(gmask);
+    idct8_contig(s + r * 8);  // 2 x 4 rows of 8
+    __syncwarp(gmask);
+    for (int it = r; it < 16; it += 8) idct4_strided(s + (it >> 3) * 32 + (it & 7), 8);  // 2 x 8 columns of 4
+    __syncwarp(gmask);
+    for (int e = r; e < 64; e += 8) {
+      const int y = e >> 3, x = e & 7;
+      if (type == 13) g[x * 8 + y] = s[e];
+      else g[e] = s[e];
+    }
+    __syncwarp(gmask);
+  } else {  // Afv0..3
+    const int n = type - 14;
+    const int flip_x = n % 2, flip_y = n / 2;
+    float* coeff_afv = s;         // 16
+    float* samples_afv = s + 16;  // 16
+    float* s4x4 = s + 32;         // 16
+    float* s4x8 = s + 48;         // 32
+    for (int e = r; e < 64; e += 8) {
+      if (e < 16) {
+        coeff_afv[e] = e == 0 ? __fmul_rn(__fadd_rn(__fadd_rn(g[0], g[1]), g[8]), 4.0f) : g[(2 * (e / 4)) * 8 + 2 * (e % 4)];
+      } else if (e < 32) {
+        const int k = e - 16, iy = k >> 2, ix = k & 3;  // s4x4[ix*4 + iy] <- (2ix+1, 2iy)
+        s4x4[ix * 4 + iy] = (ix | iy) == 0 ? __fadd_rn(__fsub_rn(g[0], g[1]), g[8]) : g[(2 * iy) * 8 + 2 * ix + 1];
+      } else {
+        const int k = e - 32, iy = k >> 3, ix = k & 7;  // s4x8[iy*8 + ix] <- (ix, 2iy+1)
+        s4x8[k] = (ix | iy) == 0 ? __fsub_rn(g[0], g[8]) : g[(2 * iy + 1) * 8 + ix];
+      }
+    }
+    __syncwarp(gmask);
+    for (int j = r; j < 16; j += 8) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc = __fmaf_rn(coeff_afv[i], kAfvBasis[i][j], acc);
+      samples_afv[j] = acc;
+    }
+    if (r < 4) idct4_strided(s4x4 + r * 4, 1);  // 4x4 rows
+    else idct8_contig(s4x8 + (r - 4) * 8);      // 4x8 rows
+    __syncwarp(gmask);
+    idct4_strided(s4x8 + r, 8);                 // 4x8 columns
+    if (r < 4) idct4_strided(s4x4 + r, 4);      // 4x4 columns
+    __syncwarp(gmask);
+    for (int e = r; e < 64; e += 8) {
+      const int y = e >> 3, x = e & 7;
+      const int qx = x >> 2, qy = y >> 2, ix = x & 3, iy = y & 3;
+      float v;
+      if (qy == flip_y) {
+        if (qx == flip_x) v = samples_afv[(flip_y == 0 ? iy : 3 - iy) * 4 + (flip_x == 0 ? ix : 3 - ix)];
+        else v = s4x4[iy * 4 + ix];
+      } else {
+        v = s4x8[iy * 8 + x];
+      }
+      g[e] = v;
+    }
+    __syncwarp(gmask);
+  }
 }
 
 constexpr int kSmallGroups = 32;  // 8-thread groups per CTA
@@ -738,8 +753,7 @@ __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[r * 8 + i] = v[i];
       __syncwarp(gmask);
-      if (r == 0) transform_special(Grid{g, 8, 8, 8}, t, g + 64);
-      __syncwarp(gmask);
+      transform_special_coop(g, t, g + 64, int(r), gmask);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = g[r * 8 + i];
     }
@@ -781,12 +795,12 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
     const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
     const int w = bw * 8, h = bh * 8;
     float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
-    if (lane == 0) compute_llf_serial(f, int(c), bx, by, bw, bh, llf, llf + 16);
     const int logw = 31 - __clz(w);
     for (int idx = int(lane); idx < w * h; idx += 32) {
       const int x = idx & (w - 1), y = idx >> logw;
       tile[y * 33 + x] = block[size_t(y) * f.cw + x];
     }
+    if (lane == 0) compute_llf_small(f, int(c), bx, by, bw, bh, llf);  // overlaps the tile loads in flight
     __syncwarp();
     if (int(lane) < bw * bh) tile[(int(lane) / bw) * 33 + (int(lane) % bw)] = llf[lane];
     __syncwarp();
@@ -852,20 +866,6 @@ __global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, c
 }
 
 }  // namespace
-
-// First (single-thread, global-memory) version; superseded by kernels/blockinfo.cu.
-void launch_build_block_info_v1(DevFrame f, const DevBlockInfoJob* jobs, int num_jobs, float quant_mul_base,
-                                const float* sharp_lut8, int has_epf, int* status, cudaStream_t stream) {
-  if (num_jobs <= 0) return;
-  build_block_info_kernel<<<(num_jobs + 31) / 32, 32, 0, stream>>>(f, jobs, num_jobs, quant_mul_base, sharp_lut8, has_epf, status);
-}
-
-// First (unoptimised, global-memory) version; kept as a debugging reference for entropy.cu.
-void launch_decode_hf_v1(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,
-                         int num_jobs, cudaStream_t stream) {
-  if (num_jobs <= 0) return;
-  decode_hf_kernel<<<num_jobs, 32, 0, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs);
-}
 
 void launch_lf_dequant(DevFrame f, const DevLfDequantJob* jobs, int num_jobs, cudaStream_t stream) {
   if (num_jobs <= 0) return;
