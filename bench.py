@@ -349,8 +349,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="synth8k", help="synth8k | synth4k | mosaic8k | file:PATH")
-    ap.add_argument("--contexts", type=int, default=16, help="decoder contexts (CUDA streams) per GPU")
-    ap.add_argument("--frames-per-step", type=int, default=16, help="independent frames decoded per step per GPU")
+    ap.add_argument("--contexts", type=int, default=32, help="decoder contexts (CUDA streams) per GPU")
+    ap.add_argument("--frames-per-step", type=int, default=32, help="independent frames decoded per step per GPU")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

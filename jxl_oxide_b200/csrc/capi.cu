@@ -159,8 +159,12 @@ int32_t jxlb_frame_channel_to_host(jxlb_decoder* dec, int32_t frame, int32_t cha
     const View& v = f.channels[channel];
     JXLB_CHECK(dst_stride >= v.w, kErrInvalidArg, "dst_stride too small");
     DevView d = dec->be->dev_view(v);
-    cudaError_t e = cudaMemcpy2DAsync(dst, dst_stride * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h,
-                                      cudaMemcpyDeviceToHost, dec->be->stream());
+    cudaError_t e;
+    if (d.stride == v.w && dst_stride == v.w)  // contiguous on both sides: one linear DMA
+      e = cudaMemcpyAsync(dst, d.ptr, size_t(v.w) * v.h * 4, cudaMemcpyDeviceToHost, dec->be->stream());
+    else
+      e = cudaMemcpy2DAsync(dst, dst_stride * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h, cudaMemcpyDeviceToHost,
+                            dec->be->stream());
     JXLB_CHECK(e == cudaSuccess, kErrCuda, cudaGetErrorString(e));
     dec->be->sync();
   });

@@ -260,8 +260,11 @@ DevView CudaBackend::dev_view(const View& v) const {
 void CudaBackend::download_rect(const View& v, void* dst) {
   if (!v.w || !v.h) return;
   DevView d = dev_view(v);
-  CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(v.w) * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h,
-                               cudaMemcpyDeviceToHost, stream_));
+  if (d.stride == v.w)  // contiguous: one linear DMA
+    CUDA_CHECK(cudaMemcpyAsync(dst, d.ptr, size_t(v.w) * v.h * 4, cudaMemcpyDeviceToHost, stream_));
+  else
+    CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(v.w) * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h,
+                                 cudaMemcpyDeviceToHost, stream_));
   sync();
 }
 

@@ -22,79 +22,88 @@ struct BlockRec {
   uint32_t type_mul;  // dct_select | hf_mul << 8 (hf_mul validated to fit)
 };
 
+constexpr uint32_t kStageRecords = 2048;
+
 __global__ void __launch_bounds__(32) place_blocks_kernel(DevFrame f, const DevBlockInfoJob* __restrict__ jobs,
                                                            BlockRec* __restrict__ recs, uint32_t* __restrict__ rec_count,
                                                            uint32_t rec_stride, int* __restrict__ status) {
   __shared__ uint32_t occ[256][8];
-  __shared__ int32_t s_sel[64], s_mul[64];
+  __shared__ int32_t s_sel[kStageRecords], s_mul[kStageRecords];
   const int j = blockIdx.x;
   const uint32_t lane = threadIdx.x;
   const DevBlockInfoJob job = jobs[j];
   const DevLfGroupRect rc = job.rect;
   for (uint32_t i = lane; i < 256 * 8; i += 32) (&occ[0][0])[i] = 0;
   BlockRec* out = recs + size_t(j) * rec_stride;
-  uint32_t data_idx = 0;   // next record to place
-  uint32_t staged_base = 0, staged_n = 0;
+  const uint32_t words = (rc.bw + 31) / 32;
+  const uint32_t last_valid = (rc.bw & 31) ? ((1u << (rc.bw & 31)) - 1) : 0xffffffffu;
+  // scan state (meaningful in lane 0; broadcast after every staged chunk)
+  uint32_t data_idx = 0, y = 0, wi = 0;
   int err = kDevOk;
-  uint32_t placed = 0;
-  __syncwarp();
-  for (uint32_t y = 0; y < rc.bh && err == kDevOk; ++y) {
-    for (uint32_t wi = 0; wi < (rc.bw + 31) / 32 && err == kDevOk; ++wi) {
+  bool full = rc.bw == 0 || rc.bh == 0;
+  while (!full && err == kDevOk) {
+    // all lanes stage the next chunk of (dct_select, hf_mul) records
+    const uint32_t staged_base = data_idx;
+    const uint32_t staged_n = min(kStageRecords, job.nb_blocks > data_idx ? job.nb_blocks - data_idx : 0u);
+    __syncwarp();
+    for (uint32_t i = lane; i < staged_n; i += 32) {
+      s_sel[i] = job.raw[staged_base + i];
+      s_mul[i] = job.raw[job.raw_stride + staged_base + i];
+    }
+    __syncwarp();
+    if (lane == 0) {  // the serial placement scan over this chunk
       for (;;) {
-        // all lanes agree on the control flow through lane 0's decisions (broadcast)
+        // next unoccupied cell in raster order
         uint32_t free_bits = 0;
-        if (lane == 0) {
-          uint32_t valid = (rc.bw - wi * 32 >= 32) ? 0xffffffffu : ((1u << (rc.bw - wi * 32)) - 1);
-          free_bits = ~occ[y][wi] & valid;
-        }
-        free_bits = __shfl_sync(0xffffffffu, free_bits, 0);
-        if (!free_bits) break;
-        if (data_idx >= staged_base + staged_n) {  // stage the next 64 records (all lanes)
-          staged_base = data_idx;
-          staged_n = min(64u, job.nb_blocks > data_idx ? job.nb_blocks - data_idx : 0u);
-          for (uint32_t i = lane; i < staged_n; i += 32) {
-            s_sel[i] = job.raw[staged_base + i];
-            s_mul[i] = job.raw[job.raw_stride + staged_base + i];
-          }
-          __syncwarp();
-        }
-        int e = kDevOk;
-        if (lane == 0) {
-          if (data_idx >= job.nb_blocks) {
-            e = kDevInvalid;
-          } else {
-            const uint32_t x = wi * 32 + uint32_t(__ffs(int(free_bits)) - 1);
-            const int32_t sel = s_sel[data_idx - staged_base];
-            const int32_t hf_mul = s_mul[data_idx - staged_base] + 1;
-            if (sel < 0 || sel >= 27 || hf_mul <= 0 || hf_mul >= (1 << 24)) {
-              e = kDevInvalid;
-            } else {
-              const uint32_t dw = kBlkSize[sel][0], dh = kBlkSize[sel][1];
-              if ((x % 32) + dw > 32 || (y % 32) + dh > 32 || x + dw > rc.bw || y + dh > rc.bh) {
-                e = kDevInvalid;
-              } else {
-                const uint32_t mask = (dw >= 32 ? 0xffffffffu : ((1u << dw) - 1)) << (x & 31);
-                for (uint32_t dy = 0; dy < dh; ++dy) {
-                  if (occ[y + dy][x >> 5] & mask) e = kDevInvalid;  // varblocks overlap
-                  occ[y + dy][x >> 5] |= mask;
-                }
-                out[placed] = {uint16_t(rc.bx0 + x), uint16_t(rc.by0 + y), uint32_t(sel) | (uint32_t(hf_mul) << 8)};
-              }
-            }
+        while (y < rc.bh) {
+          free_bits = ~occ[y][wi] & (wi + 1 == words ? last_valid : 0xffffffffu);
+          if (free_bits) break;
+          if (++wi == words) {
+            wi = 0;
+            ++y;
           }
         }
-        e = __shfl_sync(0xffffffffu, e, 0);
-        if (e != kDevOk) {
-          err = e;
+        if (y >= rc.bh) {
+          full = true;
           break;
         }
+        if (data_idx >= job.nb_blocks) {
+          err = kDevInvalid;  // cells left but no varblock to put there
+          break;
+        }
+        if (data_idx >= staged_base + staged_n) break;  // chunk consumed: stage more
+        const uint32_t x = wi * 32 + uint32_t(__ffs(int(free_bits)) - 1);
+        const int32_t sel = s_sel[data_idx - staged_base];
+        const int32_t hf_mul = s_mul[data_idx - staged_base] + 1;
+        if (sel < 0 || sel >= 27 || hf_mul <= 0 || hf_mul >= (1 << 24)) {
+          err = kDevInvalid;
+          break;
+        }
+        const uint32_t dw = kBlkSize[sel][0], dh = kBlkSize[sel][1];
+        if ((x % 32) + dw > 32 || (y % 32) + dh > 32 || x + dw > rc.bw || y + dh > rc.bh) {
+          err = kDevInvalid;
+          break;
+        }
+        const uint32_t mask = (dw >= 32 ? 0xffffffffu : ((1u << dw) - 1)) << (x & 31);
+        uint32_t clash = 0;
+        for (uint32_t dy = 0; dy < dh; ++dy) {
+          clash |= occ[y + dy][wi] & mask;
+          occ[y + dy][wi] |= mask;
+        }
+        if (clash) {  // varblocks overlap
+          err = kDevInvalid;
+          break;
+        }
+        out[data_idx] = {uint16_t(rc.bx0 + x), uint16_t(rc.by0 + y), uint32_t(sel) | (uint32_t(hf_mul) << 8)};
         ++data_idx;
-        ++placed;
       }
     }
+    data_idx = __shfl_sync(0xffffffffu, data_idx, 0);
+    err = __shfl_sync(0xffffffffu, err, 0);
+    full = __shfl_sync(0xffffffffu, int(full), 0) != 0;
   }
   if (lane == 0) {
-    rec_count[j] = placed;
+    rec_count[j] = data_idx;
     status[j] = err;
   }
 }
