@@ -196,7 +196,11 @@ void FramePlanner::run_inverse_transforms(const ModularStreamSyntax& s, std::vec
         targets.push_back(v);
         added.push_back({v, true});
       }
-      be_.palette_inverse(pal.view, targets, t, s.header.wp, fh_.bit_depth.bits_per_sample);
+      // an empty index channel has nothing to look up (palette.rs: the loops run zero times)
+      if (targets[0].w && targets[0].h && targets[0].plane >= 0) {
+        JXLB_CHECK(pal.view.plane >= 0, kErrUnsupported, "palettes without explicit colours are not supported");
+        be_.palette_inverse(pal.view, targets, t, s.header.wp, fh_.bit_depth.bits_per_sample);
+      }
       bufs.insert(bufs.begin() + t.begin_c + 1, added.begin(), added.end());
       if (pal.owned && pal.view.plane >= 0) drop_plane(pal.view.plane);
     }

@@ -34,4 +34,10 @@ for name, (src, files) in CASES.items():
 os.makedirs(os.path.join(HERE, "benchmark-data"), exist_ok=True)
 for f in BENCH:
     shutil.copyfile(os.path.join(REF, "decode/benchmark-data", f), os.path.join(HERE, "benchmark-data", f))
+# malformed inputs found by the reference's fuzzers (crates/jxl-oxide-tests/tests/fuzz_findings): expectation =
+# no crash, a clean error value (or a successful decode)
+import glob
+os.makedirs(os.path.join(HERE, "fuzz_findings"), exist_ok=True)
+for f in sorted(glob.glob(os.path.join(REF, "tests/fuzz_findings/*.fuzz"))):
+    shutil.copyfile(f, os.path.join(HERE, "fuzz_findings", os.path.basename(f)))
 print("fixtures copied")

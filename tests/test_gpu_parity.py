@@ -148,3 +148,32 @@ def test_fused_filters_other_output_encodings(dec, oracle, output_colour):
     for name in ("opsin_inverse",):
         got, want, _ = _decode_both(dec, oracle, fixture_bytes(name, "input.jxl"), output_colour=output_colour)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_fuzz_findings_are_clean_errors_on_device(dec, oracle):
+    """Malformed inputs: the CUDA path returns the same kind of result as the oracle (decode or an
+    error value of the same class) and the decoder stays usable."""
+    import glob
+    import os
+    import jxl_oxide_b200
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_findings")
+    files = sorted(glob.glob(os.path.join(here, "*.fuzz")))
+    assert len(files) >= 60
+    for f in files:
+        data = open(f, "rb").read()
+        want = None
+        try:
+            oracle.OracleImage(data, threads=2).close()
+        except oracle.OracleError as e:
+            want = e.code
+        got = None
+        try:
+            dec.decode(data)
+            dec.release_frames()
+        except jxl_oxide_b200.JxlError as e:
+            got = e.code
+        # device-side detection reports DEVICE_DECODE (6) where the host oracle says BITSTREAM (1)
+        norm = {6: 1}
+        assert norm.get(got, got) == norm.get(want, want), (os.path.basename(f), got, want)
+    dec.decode(fixture_bytes("grayalpha", "input.jxl"))
+    assert dec.frame_planar(0).shape == (2, 32, 32)

@@ -126,3 +126,23 @@ def test_synthetic_encoder_roundtrips_through_oracle(oracle):
     img = oracle.OracleImage(a, threads=4)
     planes, ncol, is_vardct = img.frame(0)
     assert is_vardct and planes.shape == (3, 392, 520) and np.isfinite(planes).all()
+
+
+def _fuzz_files():
+    import glob
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_findings")
+    return sorted(glob.glob(os.path.join(here, "*.fuzz")))
+
+
+def test_fuzz_findings_are_clean_errors(oracle):
+    """The reference's fuzz corpus (tests/fuzz_findings): every input ends in a decode or an error
+    VALUE with a known code - never a crash, a hang or an unclassified exception."""
+    files = _fuzz_files()
+    assert len(files) >= 60
+    for f in files:
+        data = open(f, "rb").read()
+        try:
+            oracle.OracleImage(data, threads=2).close()
+        except oracle.OracleError as e:
+            assert e.code in (1, 2, 3), (f, str(e))
