@@ -159,8 +159,10 @@ def run_ours(args, rank, world, local_rank):
     def step(e2e):
         errs = []
 
-        def work(d, idxs, out):
+        def work(d, idxs, out, delay):
             try:
+                if delay > 0.0:
+                    time.sleep(delay)  # de-phase the contexts (inside the timed region)
                 for k in idxs:
                     if e2e:
                         d.decode(frames[k])          # host bytes in
@@ -171,7 +173,8 @@ def run_ours(args, rank, world, local_rank):
                     d.release_frames()
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
-        ts = [threading.Thread(target=work, args=(d, idxs, o)) for d, idxs, o in zip(decs, shares, pinned_np)]
+        ts = [threading.Thread(target=work, args=(d, idxs, o, (i % args.stagger_groups) * args.stagger_ms / 1e3))
+              for i, (d, idxs, o) in enumerate(zip(decs, shares, pinned_np))]
         for t in ts:
             t.start()
         for t in ts:
@@ -352,6 +355,8 @@ def main():
     ap.add_argument("--contexts", type=int, default=32, help="decoder contexts (CUDA streams) per GPU")
     ap.add_argument("--frames-per-step", type=int, default=32, help="independent frames decoded per step per GPU")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
+    ap.add_argument("--stagger-ms", type=float, default=0.0, help="start offset between context groups within a step")
+    ap.add_argument("--stagger-groups", type=int, default=4)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

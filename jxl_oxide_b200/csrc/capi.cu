@@ -170,6 +170,34 @@ int32_t jxlb_frame_channel_to_host(jxlb_decoder* dec, int32_t frame, int32_t cha
   });
 }
 
+int32_t jxlb_frame_write_to_buffer(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation, void* dst,
+                                   size_t dst_bytes) {
+  if (!dec || !dst || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    const DecodedFrame& f = dec->res.frames[frame];
+    JXLB_CHECK(sample_type >= 0 && sample_type <= 2, kErrInvalidArg, "sample_type must be 0 (u8), 1 (u16) or 2 (f32)");
+    JXLB_CHECK(!f.channels.empty() && f.channels.size() <= 8, kErrUnsupported, "1..8 channels can be interleaved");
+    const uint32_t orient = orientation == 0 ? dec->res.image_header.orientation : uint32_t(orientation);
+    JXLB_CHECK(orient >= 1 && orient <= 8, kErrInvalidArg, "orientation must be 1..8 (0 = the image's)");
+    DevPackParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.num_channels = uint32_t(f.channels.size());
+    p.width = f.channels[0].w;
+    p.height = f.channels[0].h;
+    for (size_t c = 0; c < f.channels.size(); ++c) {
+      JXLB_CHECK(f.channels[c].w == p.width && f.channels[c].h == p.height, kErrUnsupported, "channels of different sizes");
+      DevView d = dec->be->dev_view(f.channels[c]);
+      p.planes[c] = static_cast<const float*>(d.ptr);
+      p.strides[c] = d.stride;
+    }
+    p.orientation = orient;
+    p.sample_type = uint32_t(sample_type);
+    const size_t bytes = size_t(p.width) * p.height * p.num_channels * (sample_type == 0 ? 1 : (sample_type == 1 ? 2 : 4));
+    JXLB_CHECK(dst_bytes >= bytes, kErrInvalidArg, "destination buffer too small");
+    dec->be->pack_to_host(p, dst, bytes);
+  });
+}
+
 int32_t jxlb_frame_channel_device(jxlb_decoder* dec, int32_t frame, int32_t channel, float** dptr, uint32_t* stride) {
   if (!dec || !dptr || !stride || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return JXLB_ERR_INVALID_ARG;
   return guarded(dec, [&] {

@@ -824,6 +824,10 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   }
   p.block_ctx_map = static_cast<const uint8_t*>(upload_temp(hbc.block_ctx_map.data(), hbc.block_ctx_map.size()));
   p.block_ctx_map_size = uint32_t(hbc.block_ctx_map.size());
+  {
+    const char* lim = std::getenv("JXLB_HF_ANS_SMEM");  // tuning knob (bytes); default: stage up to 128 KB
+    p.ans_smem_limit = lim ? uint32_t(std::atoi(lim)) : 128u * 1024u;
+  }
   std::vector<int32_t> thr;
   for (int c = 0; c < 3; ++c) {
     p.num_lf_thr[c] = uint32_t(hbc.lf_thresholds[c].size());
@@ -1063,6 +1067,16 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
     r.ptr = out_ptr[c];
   }
   return true;
+}
+
+void CudaBackend::pack_to_host(const DevPackParams& p, void* dst, size_t bytes) {
+  void* d = dmalloc(bytes);
+  begin_k("pack_interleaved");
+  launch_pack_interleaved(p, d, stream_);
+  end_k();
+  CUDA_CHECK(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, stream_));
+  sync();
+  dfree(d);
 }
 
 int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) {

@@ -63,6 +63,8 @@ class CudaBackend : public Backend {
   // launch accounting for bench.py ("gpu_launches")
   uint64_t launches = 0;
   // per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline
+  // Interleave + convert on the device, then one linear copy to `dst` (host).
+  void pack_to_host(const DevPackParams& p, void* dst, size_t bytes);
   bool fuse_filters = true;  // single-kernel Gaborish+EPF+colour (off: stage-by-stage, for stage parity tests)
   bool profile = false;
   bool trace_device = false;  // modular streams stamp the device clock; host launch/return times are logged

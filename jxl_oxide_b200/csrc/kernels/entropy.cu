@@ -56,7 +56,7 @@ __host__ __device__ inline HfSmem hf_layout(const DevHfParams& p) {
   L.cmap_stride = (495 * p.num_block_clusters + 15) & ~15u;
   L.cmap = take(L.cmap_stride * kHfWarpsPerCta);
   uint32_t ab = p.code.use_prefix ? 0 : (p.code.num_clusters << p.code.log_alphabet_size) * 8;
-  L.ans = (!p.code.use_prefix && ab <= kHfAnsSmemBytes) ? take(ab) : 0xffffffffu;
+  L.ans = (!p.code.use_prefix && ab <= min(kHfAnsSmemBytes, p.ans_smem_limit)) ? take(ab) : 0xffffffffu;
   L.total = off;
   return L;
 }

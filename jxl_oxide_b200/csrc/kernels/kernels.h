@@ -99,6 +99,7 @@ struct DevHfParams {
   uint32_t order_offset[13 * 3];  // [order_id * 3 + channel] into `orders`
   const uint8_t* block_ctx_map;
   uint32_t block_ctx_map_size;
+  uint32_t ans_smem_limit;  // stage the ANS alias tables in shared memory when they fit in this many bytes
   const int32_t* lf_thresholds;   // concatenated X, Y, B
   uint32_t num_lf_thr[3];
   const uint32_t* qf_thresholds;
@@ -150,6 +151,17 @@ void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaSt
 void launch_copy_rect(DevView src, DevView dst, cudaStream_t stream);
 // One k-times upsampling pass (k = 2, 4, 8); `quarter`: (k/2)^2 kernels of 25 weights (device).
 void launch_upsample(DevView in, DevView out, int k, const float* quarter, cudaStream_t stream);
+// ImageStream::write_to_buffer (crates/jxl-oxide/src/fb.rs:309-410): interleave up to 8 f32 planes into
+// u8 / u16 / f32 samples (channel fastest), applying the image orientation (1..8).
+struct DevPackParams {
+  const float* planes[8];
+  uint32_t strides[8];
+  uint32_t num_channels;
+  uint32_t width, height;  // of the stored (un-oriented) planes
+  uint32_t orientation;    // 1..8
+  uint32_t sample_type;    // 0: u8, 1: u16, 2: f32
+};
+void launch_pack_interleaved(DevPackParams p, void* out, cudaStream_t stream);
 // Gaborish -> EPF -> colour in one kernel (kernels/filters_fused.cu); `in` and `out` must not alias.
 struct DevFusedFilterParams {
   int gab_enabled;

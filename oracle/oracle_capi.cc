@@ -79,6 +79,52 @@ int jxlo_stage(void* hp, const char* name, int idx, uint32_t* w, uint32_t* hgt, 
   return int(it->second.size());
 }
 
+// ImageStream::write_to_buffer::<u8 | u16 | f32> (crates/jxl-oxide/src/fb.rs:309-410, 387-401, 436-520):
+// channel-interleaved samples with the orientation applied. sample_type 0 = u8, 1 = u16, 2 = f32;
+// orientation 0 = the image header's. Returns the number of samples written.
+size_t jxlo_frame_write_to_buffer(void* hp, int frame, int sample_type, int orientation, void* dst) {
+  Handle* h = static_cast<Handle*>(hp);
+  const jxlb::DecodedFrame& f = h->res.frames.at(frame);
+  const uint32_t orient = orientation ? uint32_t(orientation) : h->res.image_header.orientation;
+  const uint32_t width = f.channels.at(0).w, height = f.channels.at(0).h;
+  const uint32_t ow = orient >= 5 ? height : width, oh = orient >= 5 ? width : height;
+  const size_t nc = f.channels.size();
+  std::vector<std::vector<float>> planes(nc);
+  for (size_t c = 0; c < nc; ++c) {
+    planes[c].resize(size_t(width) * height);
+    h->be->download_rect(f.channels[c], planes[c].data());
+  }
+  size_t count = 0;
+  for (uint32_t y = 0; y < oh; ++y)
+    for (uint32_t x = 0; x < ow; ++x) {
+      uint32_t sx, sy;
+      switch (orient) {
+        case 1: sx = x, sy = y; break;
+        case 2: sx = ow - x - 1, sy = y; break;
+        case 3: sx = ow - x - 1, sy = oh - y - 1; break;
+        case 4: sx = x, sy = oh - y - 1; break;
+        case 5: sx = y, sy = x; break;
+        case 6: sx = y, sy = ow - x - 1; break;
+        case 7: sx = oh - y - 1, sy = ow - x - 1; break;
+        default: sx = oh - y - 1, sy = x; break;
+      }
+      for (size_t c = 0; c < nc; ++c, ++count) {
+        const float v = planes[c][size_t(sy) * width + sx];
+        if (sample_type == 2) {
+          static_cast<float*>(dst)[count] = v;
+        } else {
+          const float hi = sample_type == 0 ? 255.0f : 65535.0f;
+          float t = v * hi + 0.5f;
+          t = t < 0.0f ? 0.0f : (t > hi ? hi : t);  // f32::clamp keeps NaN, `as uN` then yields 0
+          const uint32_t q = (t == t) ? uint32_t(t) : 0u;
+          if (sample_type == 0) static_cast<uint8_t*>(dst)[count] = uint8_t(q);
+          else static_cast<uint16_t*>(dst)[count] = uint16_t(q);
+        }
+      }
+    }
+  return count;
+}
+
 void jxlo_free(void* hp) { delete static_cast<Handle*>(hp); }
 
 }  // extern "C"

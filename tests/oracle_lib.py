@@ -27,6 +27,8 @@ def lib():
         L.jxlo_image_info.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 6
         L.jxlo_frame_info.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.POINTER(ctypes.c_uint32)] * 5
         L.jxlo_frame_channel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.jxlo_frame_write_to_buffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.jxlo_frame_write_to_buffer.restype = ctypes.c_size_t
         L.jxlo_stage.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32),
                                  ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
         L.jxlo_free.argtypes = [ctypes.c_void_p]
@@ -62,6 +64,20 @@ class OracleImage:
         for c in range(nch):
             L.jxlo_frame_channel(self._h, idx, c, out[c].ctypes.data)
         return out, ncol, bool(vardct)
+
+    def frame_to_buffer(self, idx=0, dtype=np.uint8, orientation=0):
+        """ImageStream::write_to_buffer: (height, width, channels) interleaved samples, orientation applied."""
+        L = lib()
+        v = [ctypes.c_uint32() for _ in range(5)]
+        L.jxlo_frame_info(self._h, idx, *[ctypes.byref(x) for x in v])
+        w, h, nch, _, _ = [x.value for x in v]
+        if orientation >= 5:
+            w, h = h, w
+        st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
+        out = np.empty((h, w, nch), dtype=dtype)
+        n = L.jxlo_frame_write_to_buffer(self._h, idx, st, orientation, out.ctypes.data)
+        assert n == out.size
+        return out
 
     def stage(self, name, dtype=np.float32):
         L = lib()

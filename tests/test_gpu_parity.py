@@ -177,3 +177,16 @@ def test_fuzz_findings_are_clean_errors_on_device(dec, oracle):
         assert norm.get(got, got) == norm.get(want, want), (os.path.basename(f), got, want)
     dec.decode(fixture_bytes("grayalpha", "input.jxl"))
     assert dec.frame_planar(0).shape == (2, 32, 32)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32])
+@pytest.mark.parametrize("orientation", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_write_to_buffer_matches_reference_packing(dec, oracle, dtype, orientation):
+    """ImageStream::write_to_buffer on the device: interleave + u8/u16 rounding + all 8 orientations."""
+    data = fixture_bytes("alpha_premultiplied", "input.jxl")  # RGBA, non-square
+    dec.decode(data)
+    got = dec.frame_to_buffer(0, dtype, orientation)
+    img = oracle.OracleImage(data, threads=4)
+    want = img.frame_to_buffer(0, dtype, orientation)
+    assert got.shape == want.shape and got.shape[2] == 4
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))

@@ -146,3 +146,17 @@ def test_fuzz_findings_are_clean_errors(oracle):
             oracle.OracleImage(data, threads=2).close()
         except oracle.OracleError as e:
             assert e.code in (1, 2, 3), (f, str(e))
+
+
+def test_write_to_buffer_u8_matches_png(oracle):
+    """ImageStream::write_to_buffer::<u8> (fb.rs:309-410) of a lossless 8-bit image reproduces the PNG bytes."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("lz77_flower", "input.jxl"))
+    buf = img.frame_to_buffer(0, np.uint8, 1)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("lz77_flower", "ref.png"))))
+    assert buf.shape[:2] == ref.shape[:2]
+    assert np.array_equal(buf[:, :, :ref.shape[2]], ref[:, :, :buf.shape[2]])
+    rot = img.frame_to_buffer(0, np.uint8, 6)  # orientation 6: (x, y) <- (y, w - x - 1)
+    assert rot.shape[0] == buf.shape[1] and rot.shape[1] == buf.shape[0]
+    assert np.array_equal(rot, np.rot90(buf, k=-1)) or np.array_equal(rot, np.rot90(buf, k=1))
