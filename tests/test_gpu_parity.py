@@ -190,3 +190,32 @@ def test_write_to_buffer_matches_reference_packing(dec, oracle, dtype, orientati
     want = img.frame_to_buffer(0, dtype, orientation)
     assert got.shape == want.shape and got.shape[2] == 4
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+def test_mutated_streams_end_in_values(dec):
+    """Bit flips / truncations / overwritten runs in valid streams: every decode ends in pixels or a
+    JxlError value, and the decoder keeps working (tools/mutate_check.py runs the same under
+    compute-sanitizer memcheck: 0 errors, profiles/r01_progress.md)."""
+    import random
+    import jxl_oxide_b200
+    rng = random.Random(99)
+    for name in ("opsin_inverse", "grayalpha", "upsampling"):
+        data = fixture_bytes(name, "input.jxl")
+        for i in range(12):
+            m = bytearray(data)
+            if i % 3 == 0:
+                pos = rng.randrange(min(40, len(m) // 4), len(m))
+                m[pos] ^= 1 << rng.randrange(8)
+            elif i % 3 == 1:
+                m = m[: rng.randrange(len(m) // 8, len(m))]
+            else:
+                pos = rng.randrange(len(m) // 3, len(m) - 8)
+                for k in range(8):
+                    m[pos + k] = rng.randrange(256)
+            try:
+                dec.decode(bytes(m))
+                dec.release_frames()
+            except jxl_oxide_b200.JxlError as e:
+                assert e.code in (1, 2, 3, 6)
+        dec.decode(data)
+        dec.release_frames()
