@@ -263,8 +263,15 @@ def run_ours(args, rank, world, local_rank):
         ab = algorithmic_bytes(dom, w, h, stream_bytes)
         avg_ms = prof[dom]["ms"] / prof[dom]["launches"]
         achieved = (ab * per_launch_frames) / (avg_ms / 1e3) / 1e9 if ab else None
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if tj.get("workload") == args.workload:
+                traffic = tj.get(dom)
+        except Exception:
+            pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                     "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s",
                     "avg_launch_ms": avg_ms,
                     "measured": "CUDA events around each launch during one step with all contexts running",
