@@ -835,6 +835,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   }
   thr.push_back(0);
   p.lf_thresholds = static_cast<const int32_t*>(upload_temp(thr.data(), thr.size() * 4));
+  p.has_lf_quant = st.use_lf_frame ? 0 : 1;
   std::vector<uint32_t> qf = hbc.qf_thresholds;
   p.num_qf_thr = uint32_t(qf.size());
   qf.push_back(0);

@@ -61,6 +61,10 @@ struct VarDctState {
   const FrameHeader* fh = nullptr;
   const ImageHeader* ih = nullptr;
   // planes
+  // The frame takes its LF image from an earlier LF frame (FrameHeader flag use_lf_frame): there is no
+  // quantised LF, hence no LF-threshold contexts (hf_coeff.rs:110-127) and no LF dequant / CfL / smoothing
+  // (jxl-render/src/vardct/mod.rs:175-201).
+  bool use_lf_frame = false;
   int lf_quant[3] = {-1, -1, -1};  // i32, X/Y/B, bw x bh
   int x_from_y = -1, b_from_y = -1;  // i32, ceil(w/64) x ceil(h/64)
   int sharpness = -1;                // i32, bw x bh

@@ -51,6 +51,13 @@ struct GroupChannel {
   int32_t hshift, vshift;
 };
 
+// Rendered LF frames by level (RenderContext::lf_frame, jxl-render/src/lib.rs:46, 294-318): slot k holds
+// the frame whose lf_level is k + 1; a frame with use_lf_frame reads slot `lf_level`.
+struct LfFrameStore {
+  bool valid = false;
+  View planes[3];  // X, Y, B (f32)
+};
+
 // A parsed Modular stream whose channel data is about to be (or has been) decoded.
 struct PendingStream {
   std::unique_ptr<ModularStreamSyntax> syntax;
@@ -62,8 +69,9 @@ struct PendingStream {
 
 class FramePlanner {
  public:
-  FramePlanner(Backend& be, const uint8_t* cs, size_t size, const ImageHeader& ih, const DecodeOptions& opt)
-      : be_(be), cs_(cs), size_(size), ih_(ih), opt_(opt) {}
+  FramePlanner(Backend& be, const uint8_t* cs, size_t size, const ImageHeader& ih, const DecodeOptions& opt,
+               LfFrameStore (*lf_store)[4])
+      : be_(be), cs_(cs), size_(size), ih_(ih), opt_(opt), lf_store_(lf_store) {}
 
   DecodedFrame decode_frame(size_t frame_begin_byte, size_t* frame_end_byte);
 
@@ -94,6 +102,7 @@ class FramePlanner {
   size_t size_;
   const ImageHeader& ih_;
   DecodeOptions opt_;
+  LfFrameStore (*lf_store_)[4];
   FrameHeader fh_;
   Toc toc_;
   LfGlobalSyntax lfg_;
@@ -304,12 +313,20 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   JXLB_CHECK(*frame_end_byte <= size_, kErrEof, "frame data beyond end of codestream");
 
   const bool vardct = fh_.encoding == Encoding::kVarDct;
-  JXLB_CHECK(fh_.frame_type == FrameType::kRegular || fh_.frame_type == FrameType::kSkipProgressive, kErrUnsupported,
-             "LF frames / reference-only frames are outside the implemented hot path");
-  JXLB_CHECK(!fh_.use_lf_frame(), kErrUnsupported, "use_lf_frame is outside the implemented hot path");
-  JXLB_CHECK(fh_.is_keyframe(), kErrUnsupported, "non-displayed frames (blending sources) are not supported");
-  JXLB_CHECK(fh_.resets_canvas && fh_.width == ih_.width && fh_.height == ih_.height && fh_.x0 == 0 && fh_.y0 == 0,
-             kErrUnsupported, "cropped / blended frames are outside the implemented hot path");
+  const bool is_lf_frame = fh_.frame_type == FrameType::kLfFrame;
+  JXLB_CHECK(fh_.frame_type == FrameType::kRegular || fh_.frame_type == FrameType::kSkipProgressive || is_lf_frame,
+             kErrUnsupported, "reference-only frames are outside the implemented hot path");
+  if (!is_lf_frame) {
+    JXLB_CHECK(fh_.is_keyframe(), kErrUnsupported, "non-displayed frames (blending sources) are not supported");
+    JXLB_CHECK(fh_.resets_canvas && fh_.width == ih_.width && fh_.height == ih_.height && fh_.x0 == 0 && fh_.y0 == 0,
+               kErrUnsupported, "cropped / blended frames are outside the implemented hot path");
+  } else {
+    JXLB_CHECK(fh_.lf_level >= 1 && fh_.lf_level <= 4 && fh_.upsampling == 1, kErrBitstream, "invalid LF frame header");
+  }
+  if (fh_.use_lf_frame()) {
+    JXLB_CHECK(vardct, kErrBitstream, "use_lf_frame on a Modular frame");
+    JXLB_CHECK(fh_.lf_level < 4 && (*lf_store_)[fh_.lf_level].valid, kErrBitstream, "frame refers to an LF frame that was not decoded");
+  }
   JXLB_CHECK(!fh_.do_ycbcr, kErrUnsupported, "YCbCr (JPEG-transcoded) frames are outside the implemented hot path");
   for (uint32_t u : fh_.ec_upsampling) JXLB_CHECK(u == fh_.upsampling, kErrUnsupported, "extra-channel upsampling differs from colour");
   for (const auto& ec : ih_.ec_info) JXLB_CHECK(ec.dim_shift == 0, kErrUnsupported, "dim_shift extra channels not supported");
@@ -362,6 +379,11 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     st_.hfg = &hfg_;
     st_.fh = &fh_;
     st_.ih = &ih_;
+    st_.use_lf_frame = fh_.use_lf_frame();
+    if (st_.use_lf_frame) {
+      const LfFrameStore& lf = (*lf_store_)[fh_.lf_level];
+      JXLB_CHECK(lf.planes[0].w == st_.bw && lf.planes[0].h == st_.bh, kErrBitstream, "LF frame size does not match the frame");
+    }
     for (int c = 0; c < 3; ++c) {
       st_.lf_quant[c] = new_plane(st_.bw, st_.bh);
       st_.lf[c] = new_plane(st_.bw, st_.bh);
@@ -392,7 +414,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     lf_rect[g] = {gx * (lfd / 8), gy * (lfd / 8), (lw + 7) / 8, (lh + 7) / 8};
   }
   extra_precision_.assign(num_lf_groups, 0);
-  if (vardct) {  // LfCoeff (jxl-vardct/src/lf.rs:138-181)
+  if (vardct && !fh_.use_lf_frame()) {  // LfCoeff (jxl-vardct/src/lf.rs:138-181; absent with an LF frame)
     std::vector<ModularStreamJob> jobs;
     std::vector<PendingStream> pend;
     for (uint32_t g = 0; g < num_lf_groups; ++g) {
@@ -531,7 +553,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   // restoration filters (render.rs:76-131)
   const RestorationFilter& rf = fh_.restoration_filter;
   const bool upsampled = fh_.upsampling > 1;
-  bool colour_done = false;
+  bool colour_done = is_lf_frame;  // an LF frame stays in XYB: it is the next frame's LF image
   if (rf.gab_enabled || rf.epf.iters > 0) {
     JXLB_CHECK(colour.size() == 3, kErrUnsupported, "restoration filters on grayscale frames are not supported");
     View v[3] = {colour[0], colour[1], colour[2]};
@@ -539,7 +561,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     if (vardct) sigma_view = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
     ColorParams cp;
     // colour conversion follows upsampling (render.rs:136-149), so it is fused only without it
-    const bool want_colour = !upsampled && colour_params(ih_.xyb_encoded, colour.size(), &cp);
+    const bool want_colour = !upsampled && !is_lf_frame && colour_params(ih_.xyb_encoded, colour.size(), &cp);
     if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
       colour_done = want_colour;
       if (want_colour) be_.stage_marker("rgb", v, 3);
@@ -570,6 +592,15 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     be_.stage_marker("upsampled", colour.data(), int(colour.size()));
   }
   finish_colour(colour, ih_.xyb_encoded, colour_done, &out);
+  if (is_lf_frame) {
+    JXLB_CHECK(colour.size() == 3, kErrUnsupported, "grayscale LF frames are not supported");
+    LfFrameStore& slot = (*lf_store_)[fh_.lf_level - 1];
+    if (slot.valid)
+      for (const View& v : slot.planes) be_.free_plane(v.plane);
+    for (int c = 0; c < 3; ++c) slot.planes[c] = colour[c];
+    slot.valid = true;
+    out.internal = true;
+  }
   for (size_t c = ec_from; c < gm_image.size() && (c - ec_from) < ih_.ec_info.size(); ++c) {
     View v = gm_image[c].view;
     be_.int_to_float(v, ih_.ec_info[c - ec_from].bit_depth);
@@ -603,9 +634,15 @@ void FramePlanner::render_vardct(DecodedFrame*) {
     for (int c = 0; c < 3; ++c) j.scale[c] = float(double(m[c]) * double(precision_scale) / double(scale_inv));
     jobs.push_back(j);
   }
-  be_.lf_dequant(st_, jobs);
-  be_.lf_chroma_from_luma(st_);
-  if (!fh_.skip_adaptive_lf_smoothing()) be_.lf_adaptive_smoothing(st_);
+  if (st_.use_lf_frame) {
+    // the LF image is the rendered LF frame, used as is (jxl-render/src/vardct/mod.rs:175-180)
+    const LfFrameStore& lf = (*lf_store_)[fh_.lf_level];
+    for (int c = 0; c < 3; ++c) be_.copy_rect(lf.planes[c], View{st_.lf[c], 0, 0, st_.bw, st_.bh});
+  } else {
+    be_.lf_dequant(st_, jobs);
+    be_.lf_chroma_from_luma(st_);
+    if (!fh_.skip_adaptive_lf_smoothing()) be_.lf_adaptive_smoothing(st_);
+  }
   {
     View v[3] = {View{st_.lf[0], 0, 0, st_.bw, st_.bh}, View{st_.lf[1], 0, 0, st_.bw, st_.bh}, View{st_.lf[2], 0, 0, st_.bw, st_.bh}};
     be_.stage_marker("lf", v, 3);
@@ -671,15 +708,31 @@ DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, cons
     (void)pfh;
     fail(kErrUnsupported, "preview frames are not supported");
   }
-  while (pos < size && res.frames.size() < opt.max_frames) {
-    FramePlanner planner(be, cs, size, ih, opt);
-    size_t end = 0;
-    DecodedFrame f = planner.decode_frame(pos, &end);
-    bool last = f.header.is_last;
-    res.frames.push_back(std::move(f));
-    pos = end;
-    if (last) break;
+  LfFrameStore lf_store[4];
+  auto drop_lf_frames = [&] {
+    for (LfFrameStore& s : lf_store)
+      if (s.valid)
+        for (const View& v : s.planes) be.free_plane(v.plane);
+  };
+  try {
+    while (pos < size && res.frames.size() < opt.max_frames) {
+      FramePlanner planner(be, cs, size, ih, opt, &lf_store);
+      size_t end = 0;
+      DecodedFrame f = planner.decode_frame(pos, &end);
+      bool last = f.header.is_last;
+      if (f.internal) {  // an LF frame: its colour planes live on in lf_store, nothing is shown
+        for (size_t c = 3; c < f.channels.size(); ++c) be.free_plane(f.channels[c].plane);
+      } else {
+        res.frames.push_back(std::move(f));
+      }
+      pos = end;
+      if (last) break;
+    }
+  } catch (...) {
+    drop_lf_frames();
+    throw;
   }
+  drop_lf_frames();
   return res;
 }
 

@@ -20,6 +20,7 @@ struct DecodeOptions {
 };
 
 struct DecodedFrame {
+  bool internal = false;  // an LF frame: consumed by later frames, never shown (jxl-render/src/lib.rs:294-318)
   uint32_t width = 0, height = 0;
   uint32_t num_color = 0;
   std::vector<View> channels;  // f32 planes: colour channels then extra channels

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
       const uint32_t num_blocks = w8 * h8;
       const uint32_t num_blocks_log = 31u - uint32_t(__clz(int(num_blocks)));
       uint32_t lf_idx = 0;
-      {
+      if (p.has_lf_quant) {
         const int cs3[3] = {0, 2, 1};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {

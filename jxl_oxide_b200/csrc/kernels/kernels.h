@@ -102,6 +102,7 @@ struct DevHfParams {
   uint32_t ans_smem_limit;  // stage the ANS alias tables in shared memory when they fit in this many bytes
   const int32_t* lf_thresholds;   // concatenated X, Y, B
   uint32_t num_lf_thr[3];
+  uint32_t has_lf_quant;  // 0: the frame uses an LF frame, the LF part of every block context is 0
   const uint32_t* qf_thresholds;
   uint32_t num_qf_thr;
   uint32_t num_block_clusters, num_hf_presets, coeff_shift;

@@ -109,12 +109,14 @@ void OracleBackend::decode_one_hf(VarDctState& st, HfGroupJob& job) {
       uint32_t num_blocks = w8 * h8, num_blocks_log = ceil_log2_nonzero(num_blocks);
       uint32_t order_id = ti.order_id;
       size_t lf_idx = 0;
-      for (int c : {0, 2, 1}) {
-        const auto& thr = hbc.lf_thresholds[c];
-        lf_idx *= thr.size() + 1;
-        int32_t q = lfq[c]->i32()[gi];
-        for (int32_t th : thr)
-          if (q > th) ++lf_idx;
+      if (!st.use_lf_frame) {
+        for (int c : {0, 2, 1}) {
+          const auto& thr = hbc.lf_thresholds[c];
+          lf_idx *= thr.size() + 1;
+          int32_t q = lfq[c]->i32()[gi];
+          for (int32_t th : thr)
+            if (q > th) ++lf_idx;
+        }
       }
       size_t hf_idx = 0;
       for (uint32_t th : hbc.qf_thresholds)

@@ -133,7 +133,8 @@ def test_stage_entry_points_match_pipeline(dec, oracle):
         assert np.array_equal(got.cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("size,seed,extra", [((1000, 600), 5, ()), ((1544, 1032), 6, ("--lf-gradient",))])
+@pytest.mark.parametrize("size,seed,extra", [((1000, 600), 5, ()), ((1544, 1032), 6, ("--lf-gradient",)),
+                                             ((1000, 600), 7, ("--lf-frame",))])
 def test_synthetic_vardct_frames_bit_exact(dec, oracle, size, seed, extra):
     """Frames from tools/synth_enc.cc (the bench workload generator): all 27 transform families,
     WP- or gradient-coded LF, EPF 2 iterations."""

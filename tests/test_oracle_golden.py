@@ -160,3 +160,15 @@ def test_write_to_buffer_u8_matches_png(oracle):
     rot = img.frame_to_buffer(0, np.uint8, 6)  # orientation 6: (x, y) <- (y, w - x - 1)
     assert rot.shape[0] == buf.shape[1] and rot.shape[1] == buf.shape[0]
     assert np.array_equal(rot, np.rot90(buf, k=-1)) or np.array_equal(rot, np.rot90(buf, k=1))
+
+
+def test_lf_frame_streams_decode(oracle):
+    """A frame that takes its LF image from a preceding Modular LF frame (use_lf_frame,
+    jxl-render/src/lib.rs:294-318, vardct/mod.rs:175-180): two frames in the codestream, one shown."""
+    import bench
+    data = bench.synth_frame(1000, 600, 7, extra=("--lf-frame",))
+    img = oracle.OracleImage(data, threads=4, output_colour=2)
+    assert img.num_frames == 1
+    planes, ncol, is_vardct = img.frame(0)
+    assert is_vardct and planes.shape == (3, 600, 1000) and np.isfinite(planes).all()
+    assert 0.2 < float(planes[1].max()) < 1.0  # luma comes from the LF frame's samples

@@ -571,6 +571,7 @@ struct Args {
   double distance = 1.0;
   bool lf_wp = true;
   std::string out = "synth.jxl";
+  bool lf_frame = false;  // put the LF image into a separate Modular LF frame (frame type 1, lf_level 1)
 };
 
 }  // namespace
@@ -585,6 +586,7 @@ int main(int argc, char** argv) {
     else if (s == "--seed") a.seed = uint32_t(atoi(next().c_str()));
     else if (s == "--distance") a.distance = atof(next().c_str());
     else if (s == "--lf-gradient") a.lf_wp = false;
+    else if (s == "--lf-frame") a.lf_frame = true;
     else if (s == "-o") a.out = next();
     else fprintf(stderr, "unknown arg %s\n", s.c_str()), exit(2);
   }
@@ -686,7 +688,7 @@ int main(int argc, char** argv) {
         for (uint32_t x = 0; x < lw; ++x) hm[3].v[size_t(y) * lw + x] = int32_t(((x / 16) * 7 + (y / 16) * 3 + lg) % 8);
     }
     modular_tokens(tree, hm, int32_t(1 + 2 * num_lf + lg), &hfmeta_tokens[lg]);
-    lf_tokens_all.insert(lf_tokens_all.end(), lfcoeff_tokens[lg].begin(), lfcoeff_tokens[lg].end());
+    if (!a.lf_frame) lf_tokens_all.insert(lf_tokens_all.end(), lfcoeff_tokens[lg].begin(), lfcoeff_tokens[lg].end());
     lf_tokens_all.insert(lf_tokens_all.end(), hfmeta_tokens[lg].begin(), hfmeta_tokens[lg].end());
   }
 
@@ -798,9 +800,11 @@ int main(int argc, char** argv) {
     BitWriter& w = sections[1 + lg];
     uint32_t lx0 = (lg % lcols) * 256, ly0 = (lg / lcols) * 256;
     uint32_t lw = std::min(256u, bw - lx0), lh = std::min(256u, bh - ly0);
-    w.write(2, 0);  // extra_precision
-    write_modular_header(w);
-    lf_enc.write_tokens(w, lfcoeff_tokens[lg]);
+    if (!a.lf_frame) {
+      w.write(2, 0);  // extra_precision
+      write_modular_header(w);
+      lf_enc.write_tokens(w, lfcoeff_tokens[lg]);
+    }
     w.write(int(ceil_log2_nonzero(lw * lh)), nb_blocks[lg] - 1);
     write_modular_header(w);
     lf_enc.write_tokens(w, hfmeta_tokens[lg]);
@@ -836,7 +840,81 @@ int main(int argc, char** argv) {
   cs.write(1, 1);  // ImageMetadata all_default
   cs.write(1, 1);  // default_m
   cs.pad();
-  cs.write(1, 1);  // FrameHeader all_default
+  auto write_u64_small = [&](uint32_t v) {  // U64 (jxl-bitstream): 0 | 1 + u(4) | 17 + u(8)
+    if (v == 0) cs.write(2, 0);
+    else if (v <= 16) cs.write(2, 1), cs.write(4, v - 1);
+    else cs.write(2, 2), cs.write(8, v - 17);
+  };
+  auto write_section_size = [&](uint32_t sz) {
+    if (sz < 1024) write_u32(cs, 0, 10, sz);
+    else if (sz < 17408) write_u32(cs, 1, 14, sz - 1024);
+    else if (sz < 4211712) write_u32(cs, 2, 22, sz - 17408);
+    else write_u32(cs, 3, 30, sz - 4211712);
+  };
+  if (a.lf_frame) {
+    // ---- the LF frame: Modular, XYB, ceil(W/8) x ceil(H/8), one group, one TOC entry ----
+    if (bw > 256 || bh > 256) fprintf(stderr, "--lf-frame needs an image of at most 2048x2048\n"), exit(2);
+    // integer XYB samples: Y, X, B - Y with X = x * m_x_lf/128 etc. (defaults 1/32, 1/4, 1/2;
+    // jxl-render/src/image.rs:148-189); the smooth field of the LF quant values, rescaled
+    std::vector<Plane2D> ch(3);
+    for (auto& c : ch) c.w = bw, c.h = bh, c.v.resize(size_t(bw) * bh);
+    for (size_t i = 0; i < size_t(bw) * bh; ++i) {
+      const int32_t iy = lfq[1][i] / 2, ix = lfq[0][i] * 2, ib = lfq[2][i] / 2;
+      ch[0].v[i] = iy;       // Y = iy / 512       (0 .. ~0.45)
+      ch[1].v[i] = ix;       // X = ix / 4096
+      ch[2].v[i] = ib - iy;  // B = (ib) / 256
+    }
+    TreeEval lf_tree(build_tree(1000000, a.lf_wp));
+    std::vector<Token> toks;
+    modular_tokens(lf_tree, ch, 0, &toks);
+    BitWriter sec;
+    sec.write(1, 1);  // LfChannelDequantization all_default
+    sec.write(1, 1);  // global MA tree present
+    write_tree(sec, lf_tree);
+    std::vector<uint8_t> map(size_t(lf_tree.num_leaves()));
+    for (size_t i = 0; i < map.size(); ++i) map[i] = uint8_t(i);
+    EntropyEncoder enc;
+    enc.write_header(sec, toks, uint32_t(map.size()), map);
+    write_modular_header(sec);
+    enc.write_tokens(sec, toks);
+    sec.pad();
+    // frame header (jxl-frame/src/header.rs:9-134)
+    cs.write(1, 0);      // all_default
+    cs.write(2, 1);      // frame_type = LfFrame
+    cs.write(1, 1);      // encoding = Modular
+    write_u64_small(0);  // flags
+    cs.write(2, 0);      // upsampling = 1
+    cs.write(2, 1);      // group_size_shift = 1 (256)
+    cs.write(2, 0);      // num_passes = 1
+    cs.write(2, 0);      // lf_level - 1
+    cs.write(2, 0);      // name: empty
+    cs.write(1, 0);      // restoration filter: not all_default
+    cs.write(1, 0);      //   gab_enabled = 0
+    cs.write(2, 0);      //   epf iters = 0
+    write_u64_small(0);  //   extensions
+    write_u64_small(0);  // frame extensions
+    cs.write(1, 0);      // TOC not permuted
+    cs.pad();
+    write_section_size(uint32_t(sec.bytes.size()));
+    cs.pad();
+    cs.append(sec);
+    // ---- main frame header: VarDCT with use_lf_frame ----
+    cs.write(1, 0);         // all_default
+    cs.write(2, 0);         // Regular
+    cs.write(1, 0);         // VarDCT
+    write_u64_small(0x20);  // flags: use_lf_frame
+    cs.write(3, 3);         // x_qm_scale
+    cs.write(3, 2);         // b_qm_scale
+    cs.write(2, 0);         // num_passes = 1
+    cs.write(1, 0);         // have_crop
+    cs.write(2, 0);         // blend mode Replace
+    cs.write(1, 1);         // is_last
+    cs.write(2, 0);         // name: empty
+    cs.write(1, 1);         // restoration filter all_default
+    write_u64_small(0);     // frame extensions
+  } else {
+    cs.write(1, 1);  // FrameHeader all_default
+  }
   cs.write(1, 0);  // TOC not permuted
   cs.pad();
   for (const BitWriter& s : sections) {
