@@ -359,8 +359,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="synth8k", help="synth8k | synth4k | mosaic8k | file:PATH")
-    ap.add_argument("--contexts", type=int, default=32, help="decoder contexts (CUDA streams) per GPU")
-    ap.add_argument("--frames-per-step", type=int, default=32, help="independent frames decoded per step per GPU")
+    ap.add_argument("--contexts", type=int, default=24, help="decoder contexts (CUDA streams) per GPU")
+    ap.add_argument("--frames-per-step", type=int, default=48, help="independent frames decoded per step per GPU")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--stagger-ms", type=float, default=0.0, help="start offset between context groups within a step")
     ap.add_argument("--stagger-groups", type=int, default=4)
