@@ -1070,6 +1070,29 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
   return true;
 }
 
+void CudaBackend::add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x,
+                            float corr_b) {
+  JXLB_CHECK(v[0].w >= 2 && v[0].h >= 2, kErrUnsupported, "noise on frames narrower than 2 samples is not supported");
+  DevView dv[3];
+  float* field[3];
+  for (int c = 0; c < 3; ++c) {
+    JXLB_CHECK(v[c].w == v[0].w && v[c].h == v[0].h, kErrInvalidArg, "noise needs three equally sized planes");
+    dv[c] = dev_view(v[c]);
+    field[c] = static_cast<float*>(dmalloc(size_t(v[0].w) * v[0].h * 4));
+  }
+  DevNoiseParams p;
+  for (int i = 0; i < 8; ++i) p.lut[i] = lut[i];
+  p.lut[8] = lut[7];
+  p.corr_x = corr_x;
+  p.corr_b = corr_b;
+  p.group_dim = group_dim;
+  p.seed0 = seed0;
+  begin_k("add_noise");
+  launch_add_noise(dv, field, p, stream_);
+  end_k();
+  for (int c = 0; c < 3; ++c) dfree(field[c]);
+}
+
 void CudaBackend::pack_to_host(const DevPackParams& p, void* dst, size_t bytes) {
   void* d = dmalloc(bytes);
   begin_k("pack_interleaved");

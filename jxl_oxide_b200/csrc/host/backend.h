@@ -128,6 +128,11 @@ class Backend {
   virtual void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) = 0;
   // features/upsampling.rs: returns a new plane of (v.w << factor_log2) x (v.h << factor_log2) f32 samples
   virtual int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) = 0;
+  // Noise synthesis (jxl-render/src/features/noise.rs:12-86): pseudo-random field per group_dim x group_dim
+  // group (XorShift128+ seeded by `seed0` and the group origin), 5x5 high-pass, intensity-dependent strength
+  // from `lut`, added to the XYB planes `v` (frame_w x frame_h).
+  virtual void add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x,
+                         float corr_b) = 0;
   virtual void xyb_to_rgb(const View v[3], const ColorParams& p) = 0;
   // Optional single-pass form of gaborish() + epf() + xyb_to_rgb() (`colour` may be null). Returns
   // false when the backend wants the stages issued one by one.

@@ -84,7 +84,10 @@ LfGlobalSyntax parse_lf_global(BitReader& br, const ImageHeader& ih, const Frame
   LfGlobalSyntax g;
   JXLB_CHECK(!fh.patches(), kErrUnsupported, "patches are outside the implemented hot path");
   JXLB_CHECK(!fh.splines(), kErrUnsupported, "splines are outside the implemented hot path");
-  JXLB_CHECK(!fh.noise(), kErrUnsupported, "noise synthesis is outside the implemented hot path");
+  if (fh.noise()) {  // lf_global.rs:96-105
+    g.has_noise = true;
+    for (float& v : g.noise_lut) v = float(br.read(10)) / float(1 << 10);
+  }
   if (!br.read_bool()) {
     g.m_x_lf = br.read_f16();
     g.m_y_lf = br.read_f16();

@@ -39,6 +39,9 @@ struct HfBlockContext {  // lf.rs:52-121
 };
 
 struct LfGlobalSyntax {
+  // NoiseParameters (jxl-frame/src/data/noise.rs:2-17): strength LUT over intensity
+  bool has_noise = false;
+  float noise_lut[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // LfChannelDequantization (lf.rs:8-16)
   float m_x_lf = 1.0f / 32.0f, m_y_lf = 1.0f / 4.0f, m_b_lf = 1.0f / 2.0f;
   // Quantizer (lf.rs:18-23)

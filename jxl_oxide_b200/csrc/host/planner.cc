@@ -70,8 +70,9 @@ struct PendingStream {
 class FramePlanner {
  public:
   FramePlanner(Backend& be, const uint8_t* cs, size_t size, const ImageHeader& ih, const DecodeOptions& opt,
-               LfFrameStore (*lf_store)[4])
-      : be_(be), cs_(cs), size_(size), ih_(ih), opt_(opt), lf_store_(lf_store) {}
+               LfFrameStore (*lf_store)[4], uint64_t visible_before, uint64_t invisible_before)
+      : be_(be), cs_(cs), size_(size), ih_(ih), opt_(opt), lf_store_(lf_store), visible_before_(visible_before),
+        invisible_before_(invisible_before) {}
 
   DecodedFrame decode_frame(size_t frame_begin_byte, size_t* frame_end_byte);
 
@@ -103,6 +104,9 @@ class FramePlanner {
   const ImageHeader& ih_;
   DecodeOptions opt_;
   LfFrameStore (*lf_store_)[4];
+  // frames shown before this one / hidden frames since the last shown one: the noise generator's seed
+  // (jxl-render/src/lib.rs:563-585, features/noise.rs:180-185)
+  uint64_t visible_before_, invisible_before_;
   FrameHeader fh_;
   Toc toc_;
   LfGlobalSyntax lfg_;
@@ -561,7 +565,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     if (vardct) sigma_view = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
     ColorParams cp;
     // colour conversion follows upsampling (render.rs:136-149), so it is fused only without it
-    const bool want_colour = !upsampled && !is_lf_frame && colour_params(ih_.xyb_encoded, colour.size(), &cp);
+    const bool want_colour = !upsampled && !is_lf_frame && !lfg_.has_noise && colour_params(ih_.xyb_encoded, colour.size(), &cp);
     if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
       colour_done = want_colour;
       if (want_colour) be_.stage_marker("rgb", v, 3);
@@ -590,6 +594,16 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     out.width = fh_.width;
     out.height = fh_.height;
     be_.stage_marker("upsampled", colour.data(), int(colour.size()));
+  }
+  if (lfg_.has_noise) {  // render_features (jxl-render/src/render.rs:207-222): after the filters, before colour
+    JXLB_CHECK(colour.size() == 3 && ih_.xyb_encoded, kErrUnsupported, "noise synthesis is implemented for XYB colour frames");
+    JXLB_CHECK(!upsampled, kErrUnsupported, "noise synthesis together with upsampling is not implemented");
+    View v[3] = {colour[0], colour[1], colour[2]};
+    const float corr_x = vardct ? lfg_.base_correlation_x : 0.0f, corr_b = vardct ? lfg_.base_correlation_b : 1.0f;
+    // a shown frame counts itself among the visible ones; a hidden one among the invisible ones
+    const uint64_t seed0 = is_lf_frame ? (visible_before_ << 32) + invisible_before_ + 1 : ((visible_before_ + 1) << 32);
+    be_.add_noise(v, lfg_.noise_lut, fh_.group_dim(), seed0, corr_x, corr_b);
+    be_.stage_marker("noise", v, 3);
   }
   finish_colour(colour, ih_.xyb_encoded, colour_done, &out);
   if (is_lf_frame) {
@@ -709,6 +723,7 @@ DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, cons
     fail(kErrUnsupported, "preview frames are not supported");
   }
   LfFrameStore lf_store[4];
+  uint64_t visible_frames = 0, invisible_frames = 0;
   auto drop_lf_frames = [&] {
     for (LfFrameStore& s : lf_store)
       if (s.valid)
@@ -716,14 +731,17 @@ DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, cons
   };
   try {
     while (pos < size && res.frames.size() < opt.max_frames) {
-      FramePlanner planner(be, cs, size, ih, opt, &lf_store);
+      FramePlanner planner(be, cs, size, ih, opt, &lf_store, visible_frames, invisible_frames);
       size_t end = 0;
       DecodedFrame f = planner.decode_frame(pos, &end);
       bool last = f.header.is_last;
       if (f.internal) {  // an LF frame: its colour planes live on in lf_store, nothing is shown
         for (size_t c = 3; c < f.channels.size(); ++c) be.free_plane(f.channels[c].plane);
+        ++invisible_frames;
       } else {
         res.frames.push_back(std::move(f));
+        ++visible_frames;
+        invisible_frames = 0;
       }
       pos = end;
       if (last) break;

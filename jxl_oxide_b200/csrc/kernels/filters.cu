@@ -261,7 +261,107 @@ __global__ void pack_interleaved_kernel(DevPackParams p, void* out) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Noise synthesis (features/noise.rs)
+__device__ __forceinline__ unsigned long long split_mix_64(unsigned long long z) {  // noise.rs:454-458
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// The reference's generator is eight independent xorshift128+ streams (noise.rs:405-451) whose outputs are
+// interleaved into batches of 16 floats; one thread per (group, stream) walks its stream through the
+// group's three channels and stores the two floats each step contributes.
+__global__ void noise_field_kernel(float* f0, float* f1, float* f2, uint32_t width, uint32_t height, uint32_t group_dim,
+                                   unsigned long long seed0) {
+  const uint32_t gpr = (width + group_dim - 1) / group_dim, gpc = (height + group_dim - 1) / group_dim;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t g = t >> 3, lane = t & 7;
+  if (g >= gpr * gpc) return;
+  const uint32_t x0 = (g % gpr) * group_dim, y0 = (g / gpr) * group_dim;
+  const uint32_t gw = min(group_dim, width - x0), gh = min(group_dim, height - y0);
+  const unsigned long long seed1 = ((unsigned long long)(x0) << 32) + (unsigned long long)(y0);
+  unsigned long long s0 = split_mix_64(seed0 + 0x9E3779B97F4A7C15ull), s1 = split_mix_64(seed1 + 0x9E3779B97F4A7C15ull);
+  for (uint32_t i = 0; i < lane; ++i) {
+    s0 = split_mix_64(s0);
+    s1 = split_mix_64(s1);
+  }
+  const uint32_t width_n2 = (gw + 15) / 16;
+  float* planes[3] = {f0, f1, f2};
+  for (int c = 0; c < 3; ++c) {
+    float* dst = planes[c];
+    for (uint32_t row = 0; row < gh; ++row)
+      for (uint32_t cb = 0; cb < width_n2; ++cb) {
+        unsigned long long a = s0;
+        const unsigned long long b = s1;
+        const unsigned long long ret = a + b;
+        s0 = b;
+        a ^= a << 23;
+        s1 = a ^ (b ^ (a >> 18) ^ (b >> 5));
+        const uint32_t x = cb * 16 + 2 * lane;
+        float* o = dst + size_t(y0 + row) * width + x0 + x;
+        if (x < gw) o[0] = __uint_as_float((uint32_t(ret) >> 9) | 0x3f800000u);
+        if (x + 1 < gw) o[1] = __uint_as_float((uint32_t(ret >> 32) >> 9) | 0x3f800000u);
+      }
+  }
+}
+
+// 5x5 high-pass of the field (rows added in the order of the reference's 5-row ring buffer, which depends
+// on the row's position inside its group: noise.rs:297-320) and application to the XYB planes (noise.rs:45-83).
+__global__ void noise_apply_kernel(DevView vx, DevView vy, DevView vb, const float* __restrict__ f0,
+                                   const float* __restrict__ f1, const float* __restrict__ f2, DevNoiseParams p) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int width = int(vx.w), height = int(vx.h);
+  if (x >= width || y >= height) return;
+  const int ly = y % int(p.group_dim);
+  const float* fields[3] = {f0, f1, f2};
+  float n[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* f = fields[c];
+    float sum = 0.0f;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const int r = ly - 2 + (((s - ly) % 5) + 5) % 5;  // local row held by ring slot s
+      const int sy = mirror(y - ly + r, height);
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) {
+        const int sx = mirror(x + dx - 2, width);
+        sum = fadd(sum, fmul(f[size_t(sy) * width + sx], 0.16f));
+      }
+    }
+    n[c] = fsub(sum, fmul(f[size_t(y) * width + x], 4.0f));
+  }
+  float* px = static_cast<float*>(vx.ptr) + size_t(y) * vx.stride + x;
+  float* py = static_cast<float*>(vy.ptr) + size_t(y) * vy.stride + x;
+  float* pb = static_cast<float*>(vb.ptr) + size_t(y) * vb.stride + x;
+  const float grid_x = *px, grid_y = *py;
+  const float in_x = fadd(grid_x, grid_y), in_y = fsub(grid_y, grid_x);
+  const float in_scaled_x = fmaxf(0.0f, fmul(in_x, 3.0f)), in_scaled_y = fmaxf(0.0f, fmul(in_y, 3.0f));
+  // `as usize` saturates (and maps NaN to 0) before the min with 7
+  const uint32_t in_x_int = min(uint32_t(__float2uint_rz(in_scaled_x)), 7u), in_y_int = min(uint32_t(__float2uint_rz(in_scaled_y)), 7u);
+  const float in_x_frac = fsub(in_scaled_x, float(in_x_int)), in_y_frac = fsub(in_scaled_y, float(in_y_int));
+  const float sx = fadd(fmul(fsub(p.lut[in_x_int + 1], p.lut[in_x_int]), in_x_frac), p.lut[in_x_int]);
+  const float sy = fadd(fmul(fsub(p.lut[in_y_int + 1], p.lut[in_y_int]), in_y_frac), p.lut[in_y_int]);
+  const float nx = fmul(fmul(0.22f, sx), fadd(fmul(0.0078125f, n[0]), fmul(0.9921875f, n[2])));
+  const float ny = fmul(fmul(0.22f, sy), fadd(fmul(0.0078125f, n[1]), fmul(0.9921875f, n[2])));
+  const float nsum = fadd(nx, ny);
+  *px = fadd(*px, fsub(fadd(fmul(p.corr_x, nsum), nx), ny));
+  *py = fadd(*py, nsum);
+  *pb = fadd(*pb, fmul(p.corr_b, nsum));
+}
+
 }  // namespace
+
+void launch_add_noise(const DevView v[3], float* const field[3], DevNoiseParams p, cudaStream_t stream) {
+  const uint32_t width = v[0].w, height = v[0].h;
+  if (!width || !height) return;
+  const uint32_t groups = ((width + p.group_dim - 1) / p.group_dim) * ((height + p.group_dim - 1) / p.group_dim);
+  noise_field_kernel<<<(groups * 8 + 63) / 64, 64, 0, stream>>>(field[0], field[1], field[2], width, height, p.group_dim, p.seed0);
+  dim3 block(32, 8);
+  dim3 grid((width + 31) / 32, (height + 7) / 8);
+  noise_apply_kernel<<<grid, block, 0, stream>>>(v[0], v[1], v[2], field[0], field[1], field[2], p);
+}
 
 void launch_pack_interleaved(DevPackParams p, void* out, cudaStream_t stream) {
   if (!p.width || !p.height || !p.num_channels) return;

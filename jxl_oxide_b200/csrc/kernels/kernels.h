@@ -163,6 +163,14 @@ struct DevPackParams {
   uint32_t sample_type;    // 0: u8, 1: u16, 2: f32
 };
 void launch_pack_interleaved(DevPackParams p, void* out, cudaStream_t stream);
+// Noise synthesis (crates/jxl-render/src/features/noise.rs). `field`: three frame-sized scratch planes.
+struct DevNoiseParams {
+  float lut[9];
+  float corr_x, corr_b;
+  uint32_t group_dim;
+  unsigned long long seed0;
+};
+void launch_add_noise(const DevView v[3], float* const field[3], DevNoiseParams p, cudaStream_t stream);
 // Gaborish -> EPF -> colour in one kernel (kernels/filters_fused.cu); `in` and `out` must not alias.
 struct DevFusedFilterParams {
   int gab_enabled;

@@ -365,6 +365,101 @@ int OracleBackend::upsample(const View& v, uint32_t factor_log2, const ImageHead
 }
 
 // ---------------------------------------------------------------------------------------------
+// Noise synthesis (crates/jxl-render/src/features/noise.rs)
+namespace {
+uint64_t split_mix_64(uint64_t z) {  // noise.rs:454-458
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+}  // namespace
+
+void OracleBackend::add_noise(const View v[3], const float lut8[8], uint32_t group_dim, uint64_t seed0, float corr_x,
+                              float corr_b) {
+  const size_t width = v[0].w, height = v[0].h;
+  JXLB_CHECK(width >= 2 && height >= 2, kErrUnsupported, "noise on frames narrower than 2 samples is not supported");
+  const size_t gpr = (width + group_dim - 1) / group_dim, gpc = (height + group_dim - 1) / group_dim;
+  // 1. the random field, group by group, channel after channel from one generator (noise.rs:199-235)
+  std::vector<float> field[3];
+  for (auto& f : field) f.assign(width * height, 0.0f);
+  for (size_t gy = 0; gy < gpc; ++gy)
+    for (size_t gx = 0; gx < gpr; ++gx) {
+      const size_t x0 = gx * group_dim, y0 = gy * group_dim;
+      const size_t gw = std::min<size_t>(group_dim, width - x0), gh = std::min<size_t>(group_dim, height - y0);
+      const uint64_t seed1 = (uint64_t(x0) << 32) + uint64_t(y0);
+      uint64_t s0[8], s1[8];
+      s0[0] = split_mix_64(seed0 + 0x9E3779B97F4A7C15ull);
+      s1[0] = split_mix_64(seed1 + 0x9E3779B97F4A7C15ull);
+      for (int i = 1; i < 8; ++i) {
+        s0[i] = split_mix_64(s0[i - 1]);
+        s1[i] = split_mix_64(s1[i - 1]);
+      }
+      const size_t width_n2 = (gw + 15) / 16;
+      for (int c = 0; c < 3; ++c)
+        for (size_t it = 0; it < width_n2 * gh; ++it) {
+          const size_t row = it / width_n2, colb = (it % width_n2) * 16;
+          for (int i = 0; i < 8; ++i) {  // XorShift128Plus::fill_batch (noise.rs:439-451)
+            uint64_t a = s0[i];
+            const uint64_t b = s1[i];
+            const uint64_t ret = a + b;
+            s0[i] = b;
+            a ^= a << 23;
+            s1[i] = a ^ (b ^ (a >> 18) ^ (b >> 5));
+            const uint32_t bits[2] = {uint32_t(ret), uint32_t(ret >> 32)};
+            for (int k = 0; k < 2; ++k) {
+              const size_t x = colb + size_t(2 * i + k);
+              if (x >= gw) continue;
+              const uint32_t fb = (bits[k] >> 9) | 0x3f800000u;
+              float fv;
+              std::memcpy(&fv, &fb, 4);
+              field[c][(y0 + row) * width + x0 + x] = fv;
+            }
+          }
+        }
+    }
+  auto mirror = [](ptrdiff_t p, ptrdiff_t n) { return p < 0 ? -p - 1 : (p >= n ? 2 * n - p - 1 : p); };
+  float lut[9];
+  for (int i = 0; i < 8; ++i) lut[i] = lut8[i];
+  lut[8] = lut8[7];
+  Plane* pl[3] = {&plane(v[0].plane), &plane(v[1].plane), &plane(v[2].plane)};
+  // 2 + 3. 5x5 high-pass (rows summed in the order of the reference's 5-row ring buffer, which depends on
+  // the row's position inside its group: noise.rs:297-320) and application (noise.rs:45-83)
+  parallel_for(height, [&](size_t y) {
+    const ptrdiff_t ly = ptrdiff_t(y % group_dim);
+    float* rx = pl[0]->f32() + (v[0].y0 + y) * size_t(pl[0]->w) + v[0].x0;
+    float* ry = pl[1]->f32() + (v[1].y0 + y) * size_t(pl[1]->w) + v[1].x0;
+    float* rb = pl[2]->f32() + (v[2].y0 + y) * size_t(pl[2]->w) + v[2].x0;
+    for (size_t x = 0; x < width; ++x) {
+      float n[3];
+      for (int c = 0; c < 3; ++c) {
+        float sum = 0.0f;
+        for (ptrdiff_t s = 0; s < 5; ++s) {
+          const ptrdiff_t r = ly - 2 + (((s - ly) % 5) + 5) % 5;  // local row held by ring slot s
+          const ptrdiff_t sy = mirror(ptrdiff_t(y) - ly + r, ptrdiff_t(height));
+          for (ptrdiff_t dx = 0; dx < 5; ++dx) {
+            const ptrdiff_t sx = mirror(ptrdiff_t(x) + dx - 2, ptrdiff_t(width));
+            sum = sum + field[c][size_t(sy) * width + size_t(sx)] * 0.16f;
+          }
+        }
+        n[c] = sum - field[c][y * width + x] * 4.0f;
+      }
+      const float grid_x = rx[x], grid_y = ry[x];
+      const float in_x = grid_x + grid_y, in_y = grid_y - grid_x;
+      const float in_scaled_x = std::fmax(0.0f, in_x * 3.0f), in_scaled_y = std::fmax(0.0f, in_y * 3.0f);
+      const size_t in_x_int = std::min<size_t>(size_t(in_scaled_x), 7), in_y_int = std::min<size_t>(size_t(in_scaled_y), 7);
+      const float in_x_frac = in_scaled_x - float(in_x_int), in_y_frac = in_scaled_y - float(in_y_int);
+      const float sx = (lut[in_x_int + 1] - lut[in_x_int]) * in_x_frac + lut[in_x_int];
+      const float sy = (lut[in_y_int + 1] - lut[in_y_int]) * in_y_frac + lut[in_y_int];
+      const float nx = 0.22f * sx * (0.0078125f * n[0] + 0.9921875f * n[2]);
+      const float ny = 0.22f * sy * (0.0078125f * n[1] + 0.9921875f * n[2]);
+      rx[x] = rx[x] + (corr_x * (nx + ny) + nx - ny);
+      ry[x] = ry[x] + (nx + ny);
+      rb[x] = rb[x] + corr_b * (nx + ny);
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
 // XYB -> linear sRGB (-> sRGB), jxl-color/src/{xyb.rs:35-60, ciexyz.rs:81-87, tf/srgb.rs:13-48}
 void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   static const uint8_t kPowUpper[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c, 0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};

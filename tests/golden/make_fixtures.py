@@ -24,6 +24,7 @@ CASES = {
     "bicycles": ("conformance/testcases/bicycles", ["input.jxl"]),
     "lz77_flower": ("conformance/testcases/lz77_flower", ["input.jxl", "ref.png"]),
     "upsampling": ("conformance/testcases/upsampling", ["input.jxl", "ref.png"]),
+    "noise": ("conformance/testcases/noise", ["input.jxl", "ref.png"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 

@@ -56,6 +56,20 @@ def test_vardct_conformance_upsampling(oracle):
     assert math.sqrt(float((diff ** 2).mean())) <= 0.004
 
 
+def test_vardct_conformance_noise(oracle):
+    """Noise synthesis (features/noise.rs): XorShift128+ field per group, 5x5 high-pass, strength LUT. The
+    field is deterministic, so libjxl's rendering pins the generator, its seeds and the placement."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("noise", "input.jxl"), threads=4)
+    planes, ncol, is_vardct = img.frame(0)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("noise", "ref.png")))).astype(np.float32) / 255.0
+    ref = np.moveaxis(ref, 2, 0)
+    diff = np.abs(np.clip(planes, 0.0, 1.0) - ref)
+    assert diff.max() <= 0.004
+    assert math.sqrt(float((diff ** 2).mean())) <= 0.004
+
+
 def test_lz77_modular_vs_png(oracle):
     from PIL import Image
     import io
