@@ -355,6 +355,7 @@ int32_t jxlb_xyb_to_rgb(jxlb_decoder* dec, float* const planes[3], uint32_t widt
     for (int i = 0; i < 9; ++i) p.matrix[i] = inv_matrix[i];
     p.itscale = 255.0f / intensity_target;
     p.apply_srgb_tf = srgb_tf;
+    p.apply_bt709_tf = 0;
     launch_xyb_to_rgb(raw_view(planes[0], width, height, stride), raw_view(planes[1], width, height, stride),
                       raw_view(planes[2], width, height, stride), p, dec->be->stream());
     dec->be->launches++;

@@ -1058,6 +1058,7 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
     p.col.itscale = colour->itscale;
     for (int i = 0; i < 9; ++i) p.col.matrix[i] = colour->matrix[i];
     p.col.apply_srgb_tf = colour->apply_srgb_tf ? 1 : 0;
+    p.col.apply_bt709_tf = colour->apply_bt709_tf ? 1 : 0;
   }
   begin_k("filters_fused");
   launch_filters_fused(in, out, p, stream_);
@@ -1068,6 +1069,40 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
     r.ptr = out_ptr[c];
   }
   return true;
+}
+
+void CudaBackend::blend_patches(const std::vector<PatchJob>& jobs) {
+  // Patches may overlap; samples must then be updated in list order. Jobs are cut into launches such that
+  // no two jobs of one launch touch the same plane rectangle.
+  std::vector<DevPatchJob> batch;
+  std::vector<const PatchJob*> members;
+  auto flush = [&] {
+    if (batch.empty()) return;
+    const DevPatchJob* d = static_cast<const DevPatchJob*>(upload_temp(batch.data(), batch.size() * sizeof(DevPatchJob)));
+    begin_k("blend_patches");
+    launch_blend_patches(d, int(batch.size()), stream_);
+    end_k();
+    batch.clear();
+    members.clear();
+  };
+  auto overlaps = [](const View& a, const View& b) {
+    return a.plane == b.plane && a.x0 < b.x0 + b.w && b.x0 < a.x0 + a.w && a.y0 < b.y0 + b.h && b.y0 < a.y0 + a.h;
+  };
+  for (const PatchJob& j : jobs) {
+    if (!j.dst.w || !j.dst.h) continue;
+    bool clash = false;
+    for (const PatchJob* m : members)
+      if (overlaps(m->dst, j.dst)) {
+        clash = true;
+        break;
+      }
+    if (clash || batch.size() >= 4096) flush();
+    DevView s = dev_view(j.src), d = dev_view(j.dst);
+    batch.push_back({static_cast<const float*>(s.ptr), static_cast<float*>(d.ptr), s.stride, d.stride, j.dst.w, j.dst.h,
+                     j.mode, j.clamp ? 1u : 0u});
+    members.push_back(&j);
+  }
+  flush();
 }
 
 void CudaBackend::add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x,
@@ -1159,6 +1194,7 @@ void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   d.itscale = p.itscale;
   for (int i = 0; i < 9; ++i) d.matrix[i] = p.matrix[i];
   d.apply_srgb_tf = p.apply_srgb_tf ? 1 : 0;
+  d.apply_bt709_tf = p.apply_bt709_tf ? 1 : 0;
   begin_k("xyb_to_rgb");
   launch_xyb_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
   end_k();

@@ -91,6 +91,7 @@ struct ColorParams {  // XYB -> (linear) sRGB, jxl-color/src/{xyb.rs,ciexyz.rs:8
   float itscale;        // 255 / intensity_target
   float matrix[9];      // opsin inverse
   bool apply_srgb_tf;
+  bool apply_bt709_tf = false;  // BT.709 OETF (jxl-color/src/tf/bt709.rs, generic fast_powf)
 };
 
 class Backend {
@@ -128,6 +129,14 @@ class Backend {
   virtual void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) = 0;
   // features/upsampling.rs: returns a new plane of (v.w << factor_log2) x (v.h << factor_log2) f32 samples
   virtual int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) = 0;
+  // Patch blending without alpha (jxl-render/src/blend.rs:550-606): dst (op)= src over equally sized f32
+  // rectangles; mode 1 Replace, 2 Add, 3 Mul (`clamp`: src clamped to [0, 1] first).
+  struct PatchJob {
+    View src, dst;
+    uint32_t mode;
+    bool clamp;
+  };
+  virtual void blend_patches(const std::vector<PatchJob>& jobs) = 0;
   // Noise synthesis (jxl-render/src/features/noise.rs:12-86): pseudo-random field per group_dim x group_dim
   // group (XorShift128+ seeded by `seed0` and the group origin), 5x5 high-pass, intensity-dependent strength
   // from `lut`, added to the XYB planes `v` (frame_w x frame_h).

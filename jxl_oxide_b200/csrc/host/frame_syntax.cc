@@ -2,6 +2,7 @@
 #include "frame_syntax.h"
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 
 namespace jxlb {
@@ -82,7 +83,58 @@ HfBlockContext parse_hf_block_context(BitReader& br) {  // lf.rs:61-121
 
 LfGlobalSyntax parse_lf_global(BitReader& br, const ImageHeader& ih, const FrameHeader& fh) {
   LfGlobalSyntax g;
-  JXLB_CHECK(!fh.patches(), kErrUnsupported, "patches are outside the implemented hot path");
+  if (fh.patches()) {  // Patches::parse (jxl-frame/src/data/patch.rs:83-205)
+    g.has_patches = true;
+    std::vector<uint32_t> alpha_idx;
+    for (size_t i = 0; i < ih.ec_info.size(); ++i)
+      if (ih.ec_info[i].type == ExtraChannelType::kAlpha) alpha_idx.push_back(uint32_t(i));
+    EntropyCode code = parse_entropy_code(br, 10);
+    EntropyReader dec(&code);
+    dec.begin(br);
+    const uint32_t max_refs = uint32_t(std::min<uint64_t>(1u << 24, uint64_t(fh.width) * fh.height / 16));
+    const uint64_t max_patches = uint64_t(max_refs) * 4;
+    const uint32_t num_refs = dec.read_varint(br, 0);
+    JXLB_CHECK(num_refs <= max_refs, kErrBitstream, "too many patches");
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < num_refs; ++r) {
+      PatchRef pr;
+      pr.ref_idx = dec.read_varint(br, 1);
+      JXLB_CHECK(pr.ref_idx < 4, kErrBitstream, "PatchRef index out of bounds");
+      pr.x0 = dec.read_varint(br, 3);
+      pr.y0 = dec.read_varint(br, 3);
+      pr.width = dec.read_varint(br, 2) + 1;
+      pr.height = dec.read_varint(br, 2) + 1;
+      const uint32_t count = dec.read_varint(br, 7) + 1;
+      total += count;
+      JXLB_CHECK(total <= max_patches, kErrBitstream, "too many patches");
+      int32_t px = 0, py = 0;
+      for (uint32_t k = 0; k < count; ++k) {
+        PatchTarget t;
+        if (k) {
+          const int64_t x = int64_t(unpack_signed(dec.read_varint(br, 6))) + px;
+          const int64_t y = int64_t(unpack_signed(dec.read_varint(br, 6))) + py;
+          JXLB_CHECK(x >= INT32_MIN && x <= INT32_MAX && y >= INT32_MIN && y <= INT32_MAX, kErrBitstream, "patch coord overflow");
+          t.x = int32_t(x), t.y = int32_t(y);
+        } else {
+          t.x = int32_t(dec.read_varint(br, 4));
+          t.y = int32_t(dec.read_varint(br, 4));
+        }
+        px = t.x, py = t.y;
+        for (size_t c = 0; c < ih.ec_info.size() + 1; ++c) {
+          PatchBlending b;
+          b.mode = dec.read_varint(br, 5);
+          JXLB_CHECK(b.mode <= 7, kErrBitstream, "invalid patch blend mode");
+          if (b.mode >= 4 && alpha_idx.size() >= 2) b.alpha_channel = dec.read_varint(br, 8);
+          else b.alpha_channel = alpha_idx.empty() ? 0 : alpha_idx[0];
+          if (b.mode >= 3) b.clamp = dec.read_varint(br, 9) != 0;
+          t.blending.push_back(b);
+        }
+        pr.targets.push_back(std::move(t));
+      }
+      g.patches.push_back(std::move(pr));
+    }
+    JXLB_CHECK(dec.finalize_ok(), kErrBitstream, "invalid ANS stream (patches)");
+  }
   JXLB_CHECK(!fh.splines(), kErrUnsupported, "splines are outside the implemented hot path");
   if (fh.noise()) {  // lf_global.rs:96-105
     g.has_noise = true;

@@ -38,7 +38,24 @@ struct HfBlockContext {  // lf.rs:52-121
   uint32_t num_block_clusters = 0;
 };
 
+// Patches (jxl-frame/src/data/patch.rs): rectangles of a reference frame blended onto this frame.
+struct PatchBlending {
+  uint32_t mode = 0;  // 0 None, 1 Replace, 2 Add, 3 Mul, 4 BlendAbove, 5 BlendBelow, 6 MulAddAbove, 7 MulAddBelow
+  uint32_t alpha_channel = 0;
+  bool clamp = false;
+};
+struct PatchTarget {
+  int32_t x = 0, y = 0;
+  std::vector<PatchBlending> blending;  // [0]: colour channels, [1 + i]: extra channel i
+};
+struct PatchRef {
+  uint32_t ref_idx = 0, x0 = 0, y0 = 0, width = 0, height = 0;
+  std::vector<PatchTarget> targets;
+};
+
 struct LfGlobalSyntax {
+  bool has_patches = false;
+  std::vector<PatchRef> patches;
   // NoiseParameters (jxl-frame/src/data/noise.rs:2-17): strength LUT over intensity
   bool has_noise = false;
   float noise_lut[8] = {0, 0, 0, 0, 0, 0, 0, 0};

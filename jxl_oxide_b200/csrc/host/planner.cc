@@ -58,6 +58,14 @@ struct LfFrameStore {
   View planes[3];  // X, Y, B (f32)
 };
 
+// Reference slots (jxl-render/src/state.rs, lib.rs:296-330): a frame saved for later frames' patches. Only
+// reference-only frames saved before the colour transform are kept (what libjxl's patch detector emits).
+struct RefFrameStore {
+  bool valid = false;
+  uint32_t width = 0, height = 0;
+  std::vector<View> channels;  // colour (XYB / as coded, f32) then extra channels (f32)
+};
+
 // A parsed Modular stream whose channel data is about to be (or has been) decoded.
 struct PendingStream {
   std::unique_ptr<ModularStreamSyntax> syntax;
@@ -70,9 +78,10 @@ struct PendingStream {
 class FramePlanner {
  public:
   FramePlanner(Backend& be, const uint8_t* cs, size_t size, const ImageHeader& ih, const DecodeOptions& opt,
-               LfFrameStore (*lf_store)[4], uint64_t visible_before, uint64_t invisible_before)
-      : be_(be), cs_(cs), size_(size), ih_(ih), opt_(opt), lf_store_(lf_store), visible_before_(visible_before),
-        invisible_before_(invisible_before) {}
+               LfFrameStore (*lf_store)[4], RefFrameStore (*ref_store)[4], uint64_t visible_before,
+               uint64_t invisible_before)
+      : be_(be), cs_(cs), size_(size), ih_(ih), opt_(opt), lf_store_(lf_store), ref_store_(ref_store),
+        visible_before_(visible_before), invisible_before_(invisible_before) {}
 
   DecodedFrame decode_frame(size_t frame_begin_byte, size_t* frame_end_byte);
 
@@ -104,6 +113,7 @@ class FramePlanner {
   const ImageHeader& ih_;
   DecodeOptions opt_;
   LfFrameStore (*lf_store_)[4];
+  RefFrameStore (*ref_store_)[4];
   // frames shown before this one / hidden frames since the last shown one: the noise generator's seed
   // (jxl-render/src/lib.rs:563-585, features/noise.rs:180-185)
   uint64_t visible_before_, invisible_before_;
@@ -318,9 +328,11 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
 
   const bool vardct = fh_.encoding == Encoding::kVarDct;
   const bool is_lf_frame = fh_.frame_type == FrameType::kLfFrame;
-  JXLB_CHECK(fh_.frame_type == FrameType::kRegular || fh_.frame_type == FrameType::kSkipProgressive || is_lf_frame,
-             kErrUnsupported, "reference-only frames are outside the implemented hot path");
-  if (!is_lf_frame) {
+  const bool is_ref_frame = fh_.frame_type == FrameType::kReferenceOnly;
+  if (is_ref_frame) {
+    JXLB_CHECK(fh_.save_before_ct, kErrUnsupported, "reference frames saved after the colour transform are not supported");
+    JXLB_CHECK(fh_.upsampling == 1, kErrUnsupported, "upsampled reference frames are not supported");
+  } else if (!is_lf_frame) {
     JXLB_CHECK(fh_.is_keyframe(), kErrUnsupported, "non-displayed frames (blending sources) are not supported");
     JXLB_CHECK(fh_.resets_canvas && fh_.width == ih_.width && fh_.height == ih_.height && fh_.x0 == 0 && fh_.y0 == 0,
                kErrUnsupported, "cropped / blended frames are outside the implemented hot path");
@@ -557,7 +569,9 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   // restoration filters (render.rs:76-131)
   const RestorationFilter& rf = fh_.restoration_filter;
   const bool upsampled = fh_.upsampling > 1;
-  bool colour_done = is_lf_frame;  // an LF frame stays in XYB: it is the next frame's LF image
+  // an LF frame stays in XYB (it is the next frame's LF image), so does a reference frame saved before the
+  // colour transform
+  bool colour_done = is_lf_frame || is_ref_frame;
   if (rf.gab_enabled || rf.epf.iters > 0) {
     JXLB_CHECK(colour.size() == 3, kErrUnsupported, "restoration filters on grayscale frames are not supported");
     View v[3] = {colour[0], colour[1], colour[2]};
@@ -565,7 +579,8 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     if (vardct) sigma_view = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
     ColorParams cp;
     // colour conversion follows upsampling (render.rs:136-149), so it is fused only without it
-    const bool want_colour = !upsampled && !is_lf_frame && !lfg_.has_noise && colour_params(ih_.xyb_encoded, colour.size(), &cp);
+    const bool want_colour = !upsampled && !colour_done && !lfg_.has_noise && !lfg_.has_patches &&
+                             colour_params(ih_.xyb_encoded, colour.size(), &cp);
     if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
       colour_done = want_colour;
       if (want_colour) be_.stage_marker("rgb", v, 3);
@@ -595,17 +610,63 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     out.height = fh_.height;
     be_.stage_marker("upsampled", colour.data(), int(colour.size()));
   }
-  if (lfg_.has_noise) {  // render_features (jxl-render/src/render.rs:207-222): after the filters, before colour
+  // extra channels as floats (they take part in patch blending), upsampled like the colour channels
+  std::vector<View> extra;
+  for (size_t c = ec_from; c < gm_image.size() && (c - ec_from) < ih_.ec_info.size(); ++c) {
+    View v = gm_image[c].view;
+    be_.int_to_float(v, ih_.ec_info[c - ec_from].bit_depth);
+    if (upsampled) upsample_view(v);
+    extra.push_back(v);
+  }
+  // render_features (jxl-render/src/render.rs:159-225): patches, (splines,) noise - after upsampling, before colour
+  if (lfg_.has_patches) {
+    std::vector<View> all = colour;
+    all.insert(all.end(), extra.begin(), extra.end());
+    std::vector<Backend::PatchJob> jobs;
+    for (const PatchRef& pr : lfg_.patches) {
+      const RefFrameStore& ref = (*ref_store_)[pr.ref_idx];
+      JXLB_CHECK(ref.valid, kErrBitstream, "patch refers to a reference frame that was not decoded");
+      JXLB_CHECK(ref.channels.size() == all.size(), kErrBitstream, "patch reference has a different channel count");
+      for (const PatchTarget& t : pr.targets)
+        for (size_t idx = 0; idx < all.size(); ++idx) {  // blend.rs:418-545
+          const PatchBlending& b = idx < colour.size() ? t.blending[0] : t.blending[1 + idx - colour.size()];
+          if (b.mode == 0) continue;
+          JXLB_CHECK(b.mode <= 3, kErrUnsupported, "alpha-weighted patch blend modes are not implemented");
+          // target rectangle clipped to the frame, then the matching reference rectangle clipped to the reference
+          const int64_t fw = all[idx].w, fhh = all[idx].h;
+          const int64_t tl = std::max<int64_t>(t.x, 0), tt = std::max<int64_t>(t.y, 0);
+          const int64_t tr = std::min<int64_t>(int64_t(t.x) + pr.width, fw), tb = std::min<int64_t>(int64_t(t.y) + pr.height, fhh);
+          if (tr <= tl || tb <= tt) continue;
+          const int64_t left = tl - t.x, top = tt - t.y;
+          const int64_t rl = int64_t(pr.x0) + left, rt = int64_t(pr.y0) + top;
+          const int64_t rr = std::min<int64_t>(rl + (tr - tl), ref.width), rb = std::min<int64_t>(rt + (tb - tt), ref.height);
+          if (rr <= rl || rb <= rt) continue;
+          const View& rv = ref.channels[idx];
+          const View& dv = all[idx];
+          Backend::PatchJob j;
+          j.src = View{rv.plane, rv.x0 + uint32_t(rl), rv.y0 + uint32_t(rt), uint32_t(rr - rl), uint32_t(rb - rt)};
+          j.dst = View{dv.plane, dv.x0 + uint32_t(tl), dv.y0 + uint32_t(tt), uint32_t(rr - rl), uint32_t(rb - rt)};
+          j.mode = b.mode;
+          j.clamp = b.clamp;
+          jobs.push_back(j);
+        }
+    }
+    be_.blend_patches(jobs);
+    be_.stage_marker("patches", colour.data(), int(colour.size()));
+  }
+  if (lfg_.has_noise) {
     JXLB_CHECK(colour.size() == 3 && ih_.xyb_encoded, kErrUnsupported, "noise synthesis is implemented for XYB colour frames");
     JXLB_CHECK(!upsampled, kErrUnsupported, "noise synthesis together with upsampling is not implemented");
     View v[3] = {colour[0], colour[1], colour[2]};
     const float corr_x = vardct ? lfg_.base_correlation_x : 0.0f, corr_b = vardct ? lfg_.base_correlation_b : 1.0f;
     // a shown frame counts itself among the visible ones; a hidden one among the invisible ones
-    const uint64_t seed0 = is_lf_frame ? (visible_before_ << 32) + invisible_before_ + 1 : ((visible_before_ + 1) << 32);
+    const bool shown = !is_lf_frame && !is_ref_frame;
+    const uint64_t seed0 = shown ? ((visible_before_ + 1) << 32) : (visible_before_ << 32) + invisible_before_ + 1;
     be_.add_noise(v, lfg_.noise_lut, fh_.group_dim(), seed0, corr_x, corr_b);
     be_.stage_marker("noise", v, 3);
   }
   finish_colour(colour, ih_.xyb_encoded, colour_done, &out);
+  out.channels.insert(out.channels.end(), extra.begin(), extra.end());
   if (is_lf_frame) {
     JXLB_CHECK(colour.size() == 3, kErrUnsupported, "grayscale LF frames are not supported");
     LfFrameStore& slot = (*lf_store_)[fh_.lf_level - 1];
@@ -615,11 +676,15 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     slot.valid = true;
     out.internal = true;
   }
-  for (size_t c = ec_from; c < gm_image.size() && (c - ec_from) < ih_.ec_info.size(); ++c) {
-    View v = gm_image[c].view;
-    be_.int_to_float(v, ih_.ec_info[c - ec_from].bit_depth);
-    if (upsampled) upsample_view(v);
-    out.channels.push_back(v);
+  if (is_ref_frame) {
+    RefFrameStore& slot = (*ref_store_)[fh_.save_as_reference];
+    if (slot.valid)
+      for (const View& v : slot.channels) be_.free_plane(v.plane);
+    slot.channels = out.channels;
+    slot.width = out.width;
+    slot.height = out.height;
+    slot.valid = true;
+    out.internal = true;
   }
   // release everything not exported
   for (int id : frame_planes_) {
@@ -678,7 +743,8 @@ bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p)
   const ColourEncoding& ce = ih_.colour_encoding;
   bool srgb_like = !ce.want_icc && ce.colour_space == ColourSpace::kRgb && ce.white_point == WhitePointKind::kD65 &&
                    ce.primaries == PrimariesKind::kSrgb &&
-                   (ce.tf == TransferFunctionKind::kSrgb || ce.tf == TransferFunctionKind::kLinear);
+                   (ce.tf == TransferFunctionKind::kSrgb || ce.tf == TransferFunctionKind::kLinear ||
+                    ce.tf == TransferFunctionKind::kBt709);
   JXLB_CHECK(srgb_like || opt_.output_colour == 1, kErrUnsupported,
              "only sRGB-gamut (sRGB/linear transfer) output encodings are implemented");
   JXLB_CHECK(ih_.tone_mapping.intensity_target <= 255.0f || opt_.output_colour == 1, kErrUnsupported,
@@ -691,6 +757,7 @@ bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p)
   }
   p->itscale = 255.0f / ih_.tone_mapping.intensity_target;
   p->apply_srgb_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kSrgb;
+  p->apply_bt709_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kBt709;
   return true;
 }
 
@@ -723,20 +790,25 @@ DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, cons
     fail(kErrUnsupported, "preview frames are not supported");
   }
   LfFrameStore lf_store[4];
+  RefFrameStore ref_store[4];
   uint64_t visible_frames = 0, invisible_frames = 0;
   auto drop_lf_frames = [&] {
     for (LfFrameStore& s : lf_store)
       if (s.valid)
         for (const View& v : s.planes) be.free_plane(v.plane);
+    for (RefFrameStore& s : ref_store)
+      if (s.valid)
+        for (const View& v : s.channels) be.free_plane(v.plane);
   };
   try {
     while (pos < size && res.frames.size() < opt.max_frames) {
-      FramePlanner planner(be, cs, size, ih, opt, &lf_store, visible_frames, invisible_frames);
+      FramePlanner planner(be, cs, size, ih, opt, &lf_store, &ref_store, visible_frames, invisible_frames);
       size_t end = 0;
       DecodedFrame f = planner.decode_frame(pos, &end);
       bool last = f.header.is_last;
-      if (f.internal) {  // an LF frame: its colour planes live on in lf_store, nothing is shown
-        for (size_t c = 3; c < f.channels.size(); ++c) be.free_plane(f.channels[c].plane);
+      if (f.internal) {  // an LF / reference frame: its planes live on in lf_store / ref_store, nothing is shown
+        if (f.header.frame_type == FrameType::kLfFrame)
+          for (size_t c = 3; c < f.channels.size(); ++c) be.free_plane(f.channels[c].plane);
         ++invisible_frames;
       } else {
         res.frames.push_back(std::move(f));

@@ -169,6 +169,34 @@ __device__ __forceinline__ float linear_to_srgb(float s) {  // tf/srgb.rs:28-47 
   return copysignf(res, s);
 }
 
+
+// BT.709 OETF exactly as the reference's generic path evaluates it (jxl-color/src/tf/bt709.rs:61-68 with
+// fastmath/powf.rs:7-22, 147-156 and rational_poly.rs:2-6): rational-polynomial log2 / pow2, un-fused
+// except for the final mul_add.
+__device__ __forceinline__ float linear_to_bt709(float a) {
+  if (a <= 0.018f) return fmul(4.5f, a);
+  const int32_t x_bits = __float_as_int(a);
+  const int32_t exp_shifted = (x_bits - 0x3f2aaaab) >> 23;
+  const float mantissa = __int_as_float(x_bits - (exp_shifted << 23));
+  const float exp_val = float(exp_shifted);
+  const float x = fsub(mantissa, 1.0f);
+  const float yp = fadd(fmul(fadd(fmul(7.4245873327820566e-1f, x), 1.4287160470083755f), x), -1.8503833400518310e-6f);
+  const float yq = fadd(fmul(fadd(fmul(1.7409343003366853e-1f, x), 1.0096718572241148f), x), 9.9032814277590719e-1f);
+  const float l2 = fadd(fdiv(yp, yq), exp_val);
+  const float e = fmul(l2, 0.45f);
+  const float x_floor = floorf(e);
+  const float ex = __int_as_float(int32_t(uint32_t(int32_t(x_floor) + 127) << 23));
+  const float frac = fsub(e, x_floor);
+  float num = fadd(frac, 1.01749063e1f);
+  num = fadd(fmul(num, frac), 4.88687798e1f);
+  num = fadd(fmul(num, frac), 9.85506591e1f);
+  num = fmul(num, ex);
+  float den = fadd(fmul(2.10242958e-1f, frac), -2.22328856e-2f);
+  den = fadd(fmul(den, frac), -1.94414990e1f);
+  den = fadd(fmul(den, frac), 9.85506633e1f);
+  return __fmaf_rn(fdiv(num, den), 1.099f, -0.099f);
+}
+
 __global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorParams p) {
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= vx.w) return;
@@ -190,6 +218,10 @@ __global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorPa
     o0 = linear_to_srgb(o0);
     o1 = linear_to_srgb(o1);
     o2 = linear_to_srgb(o2);
+  } else if (p.apply_bt709_tf) {
+    o0 = linear_to_bt709(o0);
+    o1 = linear_to_bt709(o1);
+    o2 = linear_to_bt709(o2);
   }
   *px = o0;
   *py = o1;
@@ -257,6 +289,27 @@ __global__ void pack_interleaved_kernel(DevPackParams p, void* out) {
       const uint32_t q = (t == t) ? uint32_t(t) : 0u;
       if (p.sample_type == 0) static_cast<uint8_t*>(out)[o + c] = uint8_t(q);
       else static_cast<uint16_t*>(out)[o + c] = uint16_t(q);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Patches without alpha (blend.rs:550-606). Jobs of one launch may overlap in `dst` only if the bitstream
+// makes patches overlap; they are then applied in job order by launching overlapping batches separately
+// (the host splits the list), so inside a launch every destination sample has one writer.
+__global__ void blend_patches_kernel(const DevPatchJob* __restrict__ jobs) {
+  const DevPatchJob j = jobs[blockIdx.x];
+  for (uint32_t i = threadIdx.x; i < j.w * j.h; i += blockDim.x) {
+    const uint32_t x = i % j.w, y = i / j.w;
+    float v = j.src[size_t(y) * j.src_stride + x];
+    float* d = j.dst + size_t(y) * j.dst_stride + x;
+    if (j.mode == 1) {
+      *d = v;
+    } else if (j.mode == 2) {
+      *d = fadd(*d, v);
+    } else {
+      if (j.clamp) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+      *d = fmul(*d, v);
     }
   }
 }
@@ -352,6 +405,11 @@ __global__ void noise_apply_kernel(DevView vx, DevView vy, DevView vb, const flo
 }
 
 }  // namespace
+
+void launch_blend_patches(const DevPatchJob* jobs, int num_jobs, cudaStream_t stream) {
+  if (num_jobs <= 0) return;
+  blend_patches_kernel<<<num_jobs, 128, 0, stream>>>(jobs);
+}
 
 void launch_add_noise(const DevView v[3], float* const field[3], DevNoiseParams p, cudaStream_t stream) {
   const uint32_t width = v[0].w, height = v[0].h;

@@ -156,6 +156,34 @@ __device__ __forceinline__ float linear_to_srgb_f(float s) {  // tf/srgb.rs:28-4
   return copysignf(res, s);
 }
 
+
+// BT.709 OETF exactly as the reference's generic path evaluates it (jxl-color/src/tf/bt709.rs:61-68 with
+// fastmath/powf.rs:7-22, 147-156 and rational_poly.rs:2-6): rational-polynomial log2 / pow2, un-fused
+// except for the final mul_add.
+__device__ __forceinline__ float linear_to_bt709_f(float a) {
+  if (a <= 0.018f) return fmul(4.5f, a);
+  const int32_t x_bits = __float_as_int(a);
+  const int32_t exp_shifted = (x_bits - 0x3f2aaaab) >> 23;
+  const float mantissa = __int_as_float(x_bits - (exp_shifted << 23));
+  const float exp_val = float(exp_shifted);
+  const float x = fsub(mantissa, 1.0f);
+  const float yp = fadd(fmul(fadd(fmul(7.4245873327820566e-1f, x), 1.4287160470083755f), x), -1.8503833400518310e-6f);
+  const float yq = fadd(fmul(fadd(fmul(1.7409343003366853e-1f, x), 1.0096718572241148f), x), 9.9032814277590719e-1f);
+  const float l2 = fadd(fdiv(yp, yq), exp_val);
+  const float e = fmul(l2, 0.45f);
+  const float x_floor = floorf(e);
+  const float ex = __int_as_float(int32_t(uint32_t(int32_t(x_floor) + 127) << 23));
+  const float frac = fsub(e, x_floor);
+  float num = fadd(frac, 1.01749063e1f);
+  num = fadd(fmul(num, frac), 4.88687798e1f);
+  num = fadd(fmul(num, frac), 9.85506591e1f);
+  num = fmul(num, ex);
+  float den = fadd(fmul(2.10242958e-1f, frac), -2.22328856e-2f);
+  den = fadd(fmul(den, frac), -1.94414990e1f);
+  den = fadd(fmul(den, frac), 9.85506633e1f);
+  return __fmaf_rn(fdiv(num, den), 1.099f, -0.099f);
+}
+
 __device__ __forceinline__ void xyb_px(float o[3], const DevColorParams& p) {  // xyb.rs:35-60, ciexyz.rs:81-87
   const float xx = o[0], yy = o[1], bb = o[2];
   const float g_l = fsub(fadd(yy, xx), p.cbrt_opsin_bias[0]);
@@ -172,6 +200,10 @@ __device__ __forceinline__ void xyb_px(float o[3], const DevColorParams& p) {  /
     o[0] = linear_to_srgb_f(o[0]);
     o[1] = linear_to_srgb_f(o[1]);
     o[2] = linear_to_srgb_f(o[2]);
+  } else if (p.apply_bt709_tf) {
+    o[0] = linear_to_bt709_f(o[0]);
+    o[1] = linear_to_bt709_f(o[1]);
+    o[2] = linear_to_bt709_f(o[2]);
   }
 }
 

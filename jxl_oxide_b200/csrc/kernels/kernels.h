@@ -147,6 +147,7 @@ void launch_epf_step(const DevView in[3], const DevView out[3], const float* sig
 struct DevColorParams {
   float opsin_bias[3], cbrt_opsin_bias[3], itscale, matrix[9];
   int apply_srgb_tf;
+  int apply_bt709_tf;
 };
 void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream);
 void launch_copy_rect(DevView src, DevView dst, cudaStream_t stream);
@@ -163,6 +164,13 @@ struct DevPackParams {
   uint32_t sample_type;    // 0: u8, 1: u16, 2: f32
 };
 void launch_pack_interleaved(DevPackParams p, void* out, cudaStream_t stream);
+// Patch blending (jxl-render/src/blend.rs:550-606), one CTA per job; modes 1 Replace, 2 Add, 3 Mul.
+struct DevPatchJob {
+  const float* src;
+  float* dst;
+  uint32_t src_stride, dst_stride, w, h, mode, clamp;
+};
+void launch_blend_patches(const DevPatchJob* jobs, int num_jobs, cudaStream_t stream);
 // Noise synthesis (crates/jxl-render/src/features/noise.rs). `field`: three frame-sized scratch planes.
 struct DevNoiseParams {
   float lut[9];

@@ -365,6 +365,28 @@ int OracleBackend::upsample(const View& v, uint32_t factor_log2, const ImageHead
 }
 
 // ---------------------------------------------------------------------------------------------
+// Patches: blend_single for the modes without alpha (crates/jxl-render/src/blend.rs:550-606)
+void OracleBackend::blend_patches(const std::vector<PatchJob>& jobs) {
+  for (const PatchJob& j : jobs) {
+    Plane& sp = plane(j.src.plane);
+    Plane& dp = plane(j.dst.plane);
+    for (uint32_t y = 0; y < j.dst.h; ++y) {
+      const float* s = sp.f32() + size_t(j.src.y0 + y) * sp.w + j.src.x0;
+      float* d = dp.f32() + size_t(j.dst.y0 + y) * dp.w + j.dst.x0;
+      for (uint32_t x = 0; x < j.dst.w; ++x) {
+        float v = s[x];
+        if (j.mode == 1) d[x] = v;
+        else if (j.mode == 2) d[x] = d[x] + v;
+        else {
+          if (j.clamp) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);  // f32::clamp keeps NaN
+          d[x] = d[x] * v;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Noise synthesis (crates/jxl-render/src/features/noise.rs)
 namespace {
 uint64_t split_mix_64(uint64_t z) {  // noise.rs:454-458
@@ -500,6 +522,41 @@ void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
           float acc = pow * mul - 0.055f;
           float res = av <= 0.0031308f ? small : acc;
           s = std::copysign(res, s);
+        }
+      } else if (p.apply_bt709_tf) {
+        // linear_to_bt709 (jxl-color/src/tf/bt709.rs:61-68) with fast_powf_generic
+        // (fastmath/powf.rs:7-22, 147-156, 242-244; rational_poly.rs:2-6)
+        for (float& sref : o) {
+          const float a = sref;
+          if (a <= 0.018f) {
+            sref = 4.5f * a;
+            continue;
+          }
+          int32_t x_bits;
+          std::memcpy(&x_bits, &a, 4);
+          const int32_t exp_shifted = (x_bits - 0x3f2aaaab) >> 23;
+          const int32_t mb = x_bits - (exp_shifted << 23);
+          float mantissa;
+          std::memcpy(&mantissa, &mb, 4);
+          const float exp_val = float(exp_shifted);
+          const float xx = mantissa - 1.0f;
+          const float yp = (7.4245873327820566e-1f * xx + 1.4287160470083755f) * xx + -1.8503833400518310e-6f;
+          const float yq = (1.7409343003366853e-1f * xx + 1.0096718572241148f) * xx + 9.9032814277590719e-1f;
+          const float l2 = yp / yq + exp_val;
+          const float e = l2 * 0.45f;
+          const float x_floor = std::floor(e);
+          const uint32_t eb = uint32_t(int32_t(x_floor) + 127) << 23;
+          float ex;
+          std::memcpy(&ex, &eb, 4);
+          const float frac = e - x_floor;
+          float num = frac + 1.01749063e1f;
+          num = num * frac + 4.88687798e1f;
+          num = num * frac + 9.85506591e1f;
+          num = num * ex;
+          float den = 2.10242958e-1f * frac + -2.22328856e-2f;
+          den = den * frac + -1.94414990e1f;
+          den = den * frac + 9.85506633e1f;
+          sref = std::fmaf(num / den, 1.099f, -0.099f);
         }
       }
       r[0][x] = o[0];

@@ -25,6 +25,8 @@ CASES = {
     "lz77_flower": ("conformance/testcases/lz77_flower", ["input.jxl", "ref.png"]),
     "upsampling": ("conformance/testcases/upsampling", ["input.jxl", "ref.png"]),
     "noise": ("conformance/testcases/noise", ["input.jxl", "ref.png"]),
+    "patches_lossless": ("conformance/testcases/patches_lossless", ["input.jxl", "ref.png"]),
+    "bike": ("conformance/testcases/bike", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 
@@ -35,6 +37,10 @@ for name, (src, files) in CASES.items():
 os.makedirs(os.path.join(HERE, "benchmark-data"), exist_ok=True)
 for f in BENCH:
     shutil.copyfile(os.path.join(REF, "decode/benchmark-data", f), os.path.join(HERE, "benchmark-data", f))
+# bike's reference rendering is 6.7 MB: keep a 640 x 640 crop at (700, 900) (BIKE_CROP in the tests)
+from PIL import Image
+Image.open(os.path.join(REF, "conformance/testcases/bike/ref.png")).crop((700, 900, 1340, 1540)).save(
+    os.path.join(HERE, "bike", "ref_crop_700_900.png"), optimize=True)
 # malformed inputs found by the reference's fuzzers (crates/jxl-oxide-tests/tests/fuzz_findings): expectation =
 # no crash, a clean error value (or a successful decode)
 import glob

@@ -11,11 +11,11 @@ from conftest import fixture_bytes
 
 pytestmark = pytest.mark.gpu
 
-MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower"]
+MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless"]
 MODULAR_BENCH = ["srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
-VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise"]
+VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise", "bike"]
 VARDCT_BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl"]
-STAGES_F32 = ["lf", "hf_dequant", "idct", "pre_filter", "gaborish", "epf", "upsampled", "noise", "rgb"]
+STAGES_F32 = ["lf", "hf_dequant", "idct", "pre_filter", "gaborish", "epf", "upsampled", "patches", "noise", "rgb"]
 
 
 def ulp_diff(a, b):

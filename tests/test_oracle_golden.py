@@ -70,6 +70,34 @@ def test_vardct_conformance_noise(oracle):
     assert math.sqrt(float((diff ** 2).mean())) <= 0.004
 
 
+def test_patches_lossless_exact(oracle):
+    """Reference-only frames + patch dictionary (jxl-frame/src/data/patch.rs, jxl-render/src/blend.rs:418-606)
+    on a lossless image: every 8-bit sample of libjxl's rendering is reproduced."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("patches_lossless", "input.jxl"), threads=4)
+    planes, ncol, _ = img.frame(0)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("patches_lossless", "ref.png"))))
+    ref = np.moveaxis(ref, 2, 0)
+    act = np.rint(np.clip(planes[:ref.shape[0]], 0, 1) * 255.0).astype(np.uint8)
+    assert np.array_equal(act, ref)
+
+
+def test_vardct_conformance_bike(oracle):
+    """The conformance suite's photograph: VarDCT + patches from a reference frame + BT.709 output
+    transfer (jxl-color/src/tf/bt709.rs). Compared on a crop of libjxl's 8-bit rendering (peak limit 0.007)."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("bike", "input.jxl"), threads=8)
+    planes, ncol, is_vardct = img.frame(0)
+    assert is_vardct and planes.shape == (3, 2560, 2048)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("bike", "ref_crop_700_900.png")))).astype(np.float32) / 255.0
+    ref = np.moveaxis(ref, 2, 0)
+    diff = np.abs(np.clip(planes[:, 900:1540, 700:1340], 0.0, 1.0) - ref)
+    assert diff.max() <= 0.007
+    assert math.sqrt(float((diff ** 2).mean())) <= 0.002
+
+
 def test_lz77_modular_vs_png(oracle):
     from PIL import Image
     import io
