@@ -1092,14 +1092,18 @@ void CudaBackend::blend_patches(const std::vector<PatchJob>& jobs) {
     if (!j.dst.w || !j.dst.h) continue;
     bool clash = false;
     for (const PatchJob* m : members)
-      if (overlaps(m->dst, j.dst)) {
+      if (overlaps(m->dst, j.dst) || (j.base_alpha.plane >= 0 && overlaps(m->dst, j.base_alpha)) ||
+          (j.new_alpha.plane >= 0 && overlaps(m->dst, j.new_alpha)) ||
+          (m->base_alpha.plane >= 0 && overlaps(j.dst, m->base_alpha)) ||
+          (m->new_alpha.plane >= 0 && overlaps(j.dst, m->new_alpha))) {
         clash = true;
         break;
       }
     if (clash || batch.size() >= 4096) flush();
-    DevView s = dev_view(j.src), d = dev_view(j.dst);
-    batch.push_back({static_cast<const float*>(s.ptr), static_cast<float*>(d.ptr), s.stride, d.stride, j.dst.w, j.dst.h,
-                     j.mode, j.clamp ? 1u : 0u});
+    DevView s = dev_view(j.src), d = dev_view(j.dst), ba = dev_view(j.base_alpha), na = dev_view(j.new_alpha);
+    batch.push_back({static_cast<const float*>(s.ptr), static_cast<float*>(d.ptr), static_cast<const float*>(ba.ptr),
+                     static_cast<const float*>(na.ptr), s.stride, d.stride, ba.stride, na.stride, j.dst.w, j.dst.h, j.mode,
+                     j.clamp ? 1u : 0u, j.premultiplied ? 1u : 0u});
     members.push_back(&j);
   }
   flush();

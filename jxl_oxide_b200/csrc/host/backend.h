@@ -129,12 +129,16 @@ class Backend {
   virtual void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) = 0;
   // features/upsampling.rs: returns a new plane of (v.w << factor_log2) x (v.h << factor_log2) f32 samples
   virtual int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) = 0;
-  // Patch blending without alpha (jxl-render/src/blend.rs:550-606): dst (op)= src over equally sized f32
-  // rectangles; mode 1 Replace, 2 Add, 3 Mul (`clamp`: src clamped to [0, 1] first).
+  // Blending of equally sized f32 rectangles, in place on `dst` (jxl-render/src/blend.rs:550-727):
+  //   op 1 Replace, 2 Add, 3 Mul (`clamp`: src clamped to [0, 1] first),
+  //   op 4 Blend (alpha over), 5 MulAdd (dst + alpha * src), 6 MixAlpha (dst + src * (1 - dst)).
+  // `base_alpha` / `new_alpha` (plane < 0 = absent -> 0.0) are read, never written, by a job.
   struct PatchJob {
     View src, dst;
     uint32_t mode;
     bool clamp;
+    bool premultiplied = false;
+    View base_alpha, new_alpha;
   };
   virtual void blend_patches(const std::vector<PatchJob>& jobs) = 0;
   // Noise synthesis (jxl-render/src/features/noise.rs:12-86): pseudo-random field per group_dim x group_dim

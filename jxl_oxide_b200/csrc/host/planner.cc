@@ -62,6 +62,7 @@ struct LfFrameStore {
 // reference-only frames saved before the colour transform are kept (what libjxl's patch detector emits).
 struct RefFrameStore {
   bool valid = false;
+  bool ct_done = false;  // saved after the colour transform (regular frames) or before it (reference-only)
   uint32_t width = 0, height = 0;
   std::vector<View> channels;  // colour (XYB / as coded, f32) then extra channels (f32)
 };
@@ -333,9 +334,8 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     JXLB_CHECK(fh_.save_before_ct, kErrUnsupported, "reference frames saved after the colour transform are not supported");
     JXLB_CHECK(fh_.upsampling == 1, kErrUnsupported, "upsampled reference frames are not supported");
   } else if (!is_lf_frame) {
-    JXLB_CHECK(fh_.is_keyframe(), kErrUnsupported, "non-displayed frames (blending sources) are not supported");
-    JXLB_CHECK(fh_.resets_canvas && fh_.width == ih_.width && fh_.height == ih_.height && fh_.x0 == 0 && fh_.y0 == 0,
-               kErrUnsupported, "cropped / blended frames are outside the implemented hot path");
+    // regular frames are composed onto the canvas after the colour transform (jxl-render/src/blend.rs:178-415)
+    JXLB_CHECK(!fh_.save_before_ct || fh_.is_last, kErrUnsupported, "regular frames saved before the colour transform are not supported");
   } else {
     JXLB_CHECK(fh_.lf_level >= 1 && fh_.lf_level <= 4 && fh_.upsampling == 1, kErrBitstream, "invalid LF frame header");
   }
@@ -676,16 +676,87 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     slot.valid = true;
     out.internal = true;
   }
-  if (is_ref_frame) {
+  const bool normal_frame = !is_lf_frame && !is_ref_frame;
+  const bool can_reference = !fh_.is_last && (fh_.duration == 0 || fh_.save_as_reference != 0) && !is_lf_frame;  // header.rs:221-225
+  if (normal_frame && !(fh_.resets_canvas && out.width == ih_.width && out.height == ih_.height)) {
+    // ---- composition onto the image canvas (blend.rs:178-415 as a full-canvas model): every channel starts from
+    // its source slot's canvas (transparent black when the slot is empty) and the frame's rectangle is blended in
+    const size_t ncol = colour.size();
+    const bool has_extra = !fh_.ec_blending_info.empty();
+    std::vector<View> frame_ch = out.channels;
+    std::vector<View> canvas(frame_ch.size());
+    std::vector<Backend::PatchJob> colour_jobs, extra_jobs;
+    // the frame's rectangle clipped to the canvas
+    const int64_t fx0 = std::max<int64_t>(fh_.x0, 0), fy0 = std::max<int64_t>(fh_.y0, 0);
+    const int64_t fx1 = std::min<int64_t>(int64_t(fh_.x0) + out.width, ih_.width), fy1 = std::min<int64_t>(int64_t(fh_.y0) + out.height, ih_.height);
+    for (size_t idx = 0; idx < frame_ch.size(); ++idx) {
+      const BlendingInfo& bi = idx < ncol ? fh_.blending_info : fh_.ec_blending_info[idx - ncol];
+      const RefFrameStore& base = (*ref_store_)[bi.source];
+      int id = new_plane(ih_.width, ih_.height, /*zero=*/true);
+      canvas[idx] = View{id, 0, 0, ih_.width, ih_.height};
+      const bool have_base = base.valid && idx < base.channels.size();
+      if (have_base) {
+        JXLB_CHECK(base.ct_done || !ih_.xyb_encoded, kErrUnsupported, "blending onto a frame saved before the colour transform");
+        const View& bv = base.channels[idx];
+        const uint32_t cw = std::min(bv.w, ih_.width), chh = std::min(bv.h, ih_.height);
+        be_.copy_rect(View{bv.plane, bv.x0, bv.y0, cw, chh}, View{id, 0, 0, cw, chh});
+      }
+      if (fx1 <= fx0 || fy1 <= fy0) continue;
+      Backend::PatchJob j;
+      const uint32_t rw = uint32_t(fx1 - fx0), rh = uint32_t(fy1 - fy0);
+      const uint32_t sx = uint32_t(fx0 - fh_.x0), sy = uint32_t(fy0 - fh_.y0);
+      j.src = View{frame_ch[idx].plane, frame_ch[idx].x0 + sx, frame_ch[idx].y0 + sy, rw, rh};
+      j.dst = View{id, uint32_t(fx0), uint32_t(fy0), rw, rh};
+      j.clamp = bi.clamp;
+      const bool uses_alpha = (bi.mode == BlendMode::kBlend || bi.mode == BlendMode::kMulAdd) && has_extra;
+      const size_t alpha_ch = ncol + bi.alpha_channel;
+      if (uses_alpha) {
+        JXLB_CHECK(alpha_ch < frame_ch.size(), kErrBitstream, "blend alpha channel out of range");
+        j.new_alpha = View{frame_ch[alpha_ch].plane, frame_ch[alpha_ch].x0 + sx, frame_ch[alpha_ch].y0 + sy, rw, rh};
+        if (base.valid && alpha_ch < base.channels.size()) {
+          const View& av = base.channels[alpha_ch];
+          if (uint32_t(fx1) <= av.w && uint32_t(fy1) <= av.h) j.base_alpha = View{av.plane, av.x0 + uint32_t(fx0), av.y0 + uint32_t(fy0), rw, rh};
+          else JXLB_CHECK(false, kErrUnsupported, "blend base smaller than the frame rectangle");
+        }
+        j.premultiplied = ih_.ec_info[bi.alpha_channel].alpha_associated;
+      }
+      switch (bi.mode) {  // BlendParams::from_blending_info (blend.rs:55-103)
+        case BlendMode::kReplace: j.mode = 1; break;
+        case BlendMode::kAdd: j.mode = 2; break;
+        case BlendMode::kMul: j.mode = 3; break;
+        case BlendMode::kBlend: j.mode = !uses_alpha ? 1 : (idx == alpha_ch ? 6 : 4); break;
+        default: j.mode = !uses_alpha ? 2 : (idx == alpha_ch ? 0 : 5); break;  // MulAdd; Skip on its alpha channel
+      }
+      if (j.mode == 6) j.new_alpha = j.base_alpha = View();
+      if (j.mode == 0) continue;
+      (idx < ncol ? colour_jobs : extra_jobs).push_back(j);
+    }
+    be_.blend_patches(colour_jobs);
+    be_.blend_patches(extra_jobs);
+    out.channels = canvas;
+    out.width = ih_.width;
+    out.height = ih_.height;
+  }
+  if (is_ref_frame || (normal_frame && can_reference)) {
     RefFrameStore& slot = (*ref_store_)[fh_.save_as_reference];
     if (slot.valid)
       for (const View& v : slot.channels) be_.free_plane(v.plane);
-    slot.channels = out.channels;
+    slot.channels.clear();
+    if (is_ref_frame) {
+      slot.channels = out.channels;  // never shown: the slot takes the planes over
+    } else {
+      for (const View& v : out.channels) {  // the frame may also be shown: the slot keeps a copy
+        int id = be_.alloc_plane(std::max(v.w, 1u), std::max(v.h, 1u), false);
+        if (v.w && v.h) be_.copy_rect(v, View{id, 0, 0, v.w, v.h});
+        slot.channels.push_back(View{id, 0, 0, v.w, v.h});
+      }
+    }
     slot.width = out.width;
     slot.height = out.height;
+    slot.ct_done = !is_ref_frame;
     slot.valid = true;
-    out.internal = true;
   }
+  if (is_ref_frame || (normal_frame && !fh_.is_keyframe())) out.internal = true;
   // release everything not exported
   for (int id : frame_planes_) {
     bool exported = false;
@@ -806,9 +877,11 @@ DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, cons
       size_t end = 0;
       DecodedFrame f = planner.decode_frame(pos, &end);
       bool last = f.header.is_last;
-      if (f.internal) {  // an LF / reference frame: its planes live on in lf_store / ref_store, nothing is shown
+      if (f.internal) {  // an LF / reference / hidden frame: what later frames need lives in the stores
         if (f.header.frame_type == FrameType::kLfFrame)
           for (size_t c = 3; c < f.channels.size(); ++c) be.free_plane(f.channels[c].plane);
+        else if (f.header.frame_type != FrameType::kReferenceOnly)
+          for (const View& v : f.channels) be.free_plane(v.plane);
         ++invisible_frames;
       } else {
         res.frames.push_back(std::move(f));

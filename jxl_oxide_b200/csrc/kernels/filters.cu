@@ -303,14 +303,36 @@ __global__ void blend_patches_kernel(const DevPatchJob* __restrict__ jobs) {
     const uint32_t x = i % j.w, y = i / j.w;
     float v = j.src[size_t(y) * j.src_stride + x];
     float* d = j.dst + size_t(y) * j.dst_stride + x;
+    const float base = *d;
+    float r;
     if (j.mode == 1) {
-      *d = v;
+      r = v;
     } else if (j.mode == 2) {
-      *d = fadd(*d, v);
+      r = fadd(base, v);
+    } else if (j.mode == 3) {
+      if (j.clamp) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+      r = fmul(base, v);
+    } else if (j.mode == 4) {
+      const float base_alpha = j.base_alpha ? j.base_alpha[size_t(y) * j.base_alpha_stride + x] : 0.0f;
+      float new_alpha = j.new_alpha ? j.new_alpha[size_t(y) * j.new_alpha_stride + x] : 0.0f;
+      if (j.clamp) new_alpha = new_alpha < 0.0f ? 0.0f : (new_alpha > 1.0f ? 1.0f : new_alpha);
+      if (j.premultiplied) {
+        r = fadd(v, fmul(base, fsub(1.0f, new_alpha)));
+      } else {
+        const float base_alpha_rev = fsub(1.0f, base_alpha), new_alpha_rev = fsub(1.0f, new_alpha);
+        const float mixed_alpha = fsub(1.0f, fmul(new_alpha_rev, base_alpha_rev));
+        const float mixed_alpha_recip = mixed_alpha > 0.0f ? fdiv(1.0f, mixed_alpha) : 0.0f;
+        r = fmul(fadd(fmul(new_alpha, v), fmul(fmul(base_alpha, base), new_alpha_rev)), mixed_alpha_recip);
+      }
+    } else if (j.mode == 5) {
+      float new_alpha = j.new_alpha ? j.new_alpha[size_t(y) * j.new_alpha_stride + x] : 0.0f;
+      if (j.clamp) new_alpha = new_alpha < 0.0f ? 0.0f : (new_alpha > 1.0f ? 1.0f : new_alpha);
+      r = fadd(base, fmul(new_alpha, v));
     } else {
       if (j.clamp) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
-      *d = fmul(*d, v);
+      r = fadd(base, fmul(v, fsub(1.0f, base)));
     }
+    *d = r;
   }
 }
 

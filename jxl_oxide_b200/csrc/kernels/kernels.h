@@ -164,11 +164,14 @@ struct DevPackParams {
   uint32_t sample_type;    // 0: u8, 1: u16, 2: f32
 };
 void launch_pack_interleaved(DevPackParams p, void* out, cudaStream_t stream);
-// Patch blending (jxl-render/src/blend.rs:550-606), one CTA per job; modes 1 Replace, 2 Add, 3 Mul.
+// Rectangle blending (jxl-render/src/blend.rs:550-727), one CTA per job; modes 1 Replace, 2 Add, 3 Mul,
+// 4 Blend, 5 MulAdd, 6 MixAlpha.
 struct DevPatchJob {
   const float* src;
   float* dst;
-  uint32_t src_stride, dst_stride, w, h, mode, clamp;
+  const float* base_alpha;  // nullptr: 0.0
+  const float* new_alpha;   // nullptr: 0.0
+  uint32_t src_stride, dst_stride, base_alpha_stride, new_alpha_stride, w, h, mode, clamp, premultiplied;
 };
 void launch_blend_patches(const DevPatchJob* jobs, int num_jobs, cudaStream_t stream);
 // Noise synthesis (crates/jxl-render/src/features/noise.rs). `field`: three frame-sized scratch planes.

@@ -53,6 +53,8 @@ void jxlo_image_info(void* hp, uint32_t* width, uint32_t* height, uint32_t* bits
   *num_extra = uint32_t(ih.ec_info.size()), *xyb = ih.xyb_encoded, *gray = ih.grayscale();
 }
 
+uint32_t jxlo_image_orientation(void* hp) { return static_cast<Handle*>(hp)->res.image_header.orientation; }
+
 void jxlo_frame_info(void* hp, int frame, uint32_t* width, uint32_t* height, uint32_t* num_channels,
                      uint32_t* num_color, uint32_t* is_vardct) {
   const jxlb::DecodedFrame& f = static_cast<Handle*>(hp)->res.frames.at(frame);

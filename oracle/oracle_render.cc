@@ -367,19 +367,51 @@ int OracleBackend::upsample(const View& v, uint32_t factor_log2, const ImageHead
 // ---------------------------------------------------------------------------------------------
 // Patches: blend_single for the modes without alpha (crates/jxl-render/src/blend.rs:550-606)
 void OracleBackend::blend_patches(const std::vector<PatchJob>& jobs) {
+  auto clamp01 = [](float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); };  // f32::clamp keeps NaN
   for (const PatchJob& j : jobs) {
     Plane& sp = plane(j.src.plane);
     Plane& dp = plane(j.dst.plane);
+    Plane* bap = j.base_alpha.plane >= 0 ? &plane(j.base_alpha.plane) : nullptr;
+    Plane* nap = j.new_alpha.plane >= 0 ? &plane(j.new_alpha.plane) : nullptr;
     for (uint32_t y = 0; y < j.dst.h; ++y) {
       const float* s = sp.f32() + size_t(j.src.y0 + y) * sp.w + j.src.x0;
       float* d = dp.f32() + size_t(j.dst.y0 + y) * dp.w + j.dst.x0;
+      const float* ba = bap ? bap->f32() + size_t(j.base_alpha.y0 + y) * bap->w + j.base_alpha.x0 : nullptr;
+      const float* na = nap ? nap->f32() + size_t(j.new_alpha.y0 + y) * nap->w + j.new_alpha.x0 : nullptr;
       for (uint32_t x = 0; x < j.dst.w; ++x) {
         float v = s[x];
-        if (j.mode == 1) d[x] = v;
-        else if (j.mode == 2) d[x] = d[x] + v;
-        else {
-          if (j.clamp) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);  // f32::clamp keeps NaN
-          d[x] = d[x] * v;
+        switch (j.mode) {
+          case 1: d[x] = v; break;
+          case 2: d[x] = d[x] + v; break;
+          case 3:
+            if (j.clamp) v = clamp01(v);
+            d[x] = d[x] * v;
+            break;
+          case 4: {  // blend.rs:607-660
+            const float base_sample = d[x], base_alpha = ba ? ba[x] : 0.0f;
+            float new_alpha = na ? na[x] : 0.0f;
+            if (j.clamp) new_alpha = clamp01(new_alpha);
+            if (j.premultiplied) {
+              d[x] = v + base_sample * (1.0f - new_alpha);
+            } else {
+              const float base_alpha_rev = 1.0f - base_alpha, new_alpha_rev = 1.0f - new_alpha;
+              const float mixed_alpha = 1.0f - new_alpha_rev * base_alpha_rev;
+              const float mixed_alpha_recip = mixed_alpha > 0.0f ? 1.0f / mixed_alpha : 0.0f;
+              d[x] = (new_alpha * v + base_alpha * base_sample * new_alpha_rev) * mixed_alpha_recip;
+            }
+            break;
+          }
+          case 5: {  // blend.rs:662-700
+            float new_alpha = na ? na[x] : 0.0f;
+            if (j.clamp) new_alpha = clamp01(new_alpha);
+            d[x] = d[x] + new_alpha * v;
+            break;
+          }
+          default: {  // 6, MixAlpha: blend.rs:702-723
+            if (j.clamp) v = clamp01(v);
+            d[x] = d[x] + v * (1.0f - d[x]);
+            break;
+          }
         }
       }
     }

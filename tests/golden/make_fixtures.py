@@ -27,6 +27,9 @@ CASES = {
     "noise": ("conformance/testcases/noise", ["input.jxl", "ref.png"]),
     "patches_lossless": ("conformance/testcases/patches_lossless", ["input.jxl", "ref.png"]),
     "bike": ("conformance/testcases/bike", ["input.jxl"]),
+    "sunset_logo": ("conformance/testcases/sunset_logo", ["input.jxl"]),
+    "blendmodes": ("conformance/testcases/blendmodes", ["input.jxl", "ref.png"]),
+    "animation_icos4d": ("conformance/testcases/animation_icos4d", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 
@@ -41,6 +44,14 @@ for f in BENCH:
 from PIL import Image
 Image.open(os.path.join(REF, "conformance/testcases/bike/ref.png")).crop((700, 900, 1340, 1540)).save(
     os.path.join(HERE, "bike", "ref_crop_700_900.png"), optimize=True)
+# sunset_logo's reference is 0.9 MB: a 512 x 512 crop at (200, 400) of the oriented image
+Image.open(os.path.join(REF, "conformance/testcases/sunset_logo/ref.png")).crop((200, 400, 712, 912)).save(
+    os.path.join(HERE, "sunset_logo", "ref_crop_200_400.png"), optimize=True)
+# three frames of the animation's reference APNG
+_ap = Image.open(os.path.join(REF, "conformance/testcases/animation_icos4d/ref.apng"))
+for _k in (0, 17, 47):
+    _ap.seek(_k)
+    _ap.convert("RGBA").save(os.path.join(HERE, "animation_icos4d", "ref_frame_%02d.png" % _k), optimize=True)
 # malformed inputs found by the reference's fuzzers (crates/jxl-oxide-tests/tests/fuzz_findings): expectation =
 # no crash, a clean error value (or a successful decode)
 import glob

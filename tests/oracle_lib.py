@@ -25,6 +25,8 @@ def lib():
                                   ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_size_t]
         L.jxlo_num_frames.argtypes = [ctypes.c_void_p]
         L.jxlo_image_info.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 6
+        L.jxlo_image_orientation.argtypes = [ctypes.c_void_p]
+        L.jxlo_image_orientation.restype = ctypes.c_uint32
         L.jxlo_frame_info.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.POINTER(ctypes.c_uint32)] * 5
         L.jxlo_frame_channel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.jxlo_frame_write_to_buffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
@@ -54,6 +56,7 @@ class OracleImage:
         L.jxlo_image_info(self._h, *[ctypes.byref(x) for x in v])
         self.width, self.height, self.bits, self.num_extra, self.xyb, self.gray = [x.value for x in v]
         self.num_frames = L.jxlo_num_frames(self._h)
+        self.orientation = L.jxlo_image_orientation(self._h)
 
     def frame(self, idx=0):
         L = lib()
@@ -71,7 +74,7 @@ class OracleImage:
         v = [ctypes.c_uint32() for _ in range(5)]
         L.jxlo_frame_info(self._h, idx, *[ctypes.byref(x) for x in v])
         w, h, nch, _, _ = [x.value for x in v]
-        if orientation >= 5:
+        if (orientation or self.orientation) >= 5:
             w, h = h, w
         st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
         out = np.empty((h, w, nch), dtype=dtype)

@@ -11,7 +11,7 @@ from conftest import fixture_bytes
 
 pytestmark = pytest.mark.gpu
 
-MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless"]
+MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless", "sunset_logo", "blendmodes"]
 MODULAR_BENCH = ["srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise", "bike"]
 VARDCT_BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl"]
@@ -220,3 +220,16 @@ def test_mutated_streams_end_in_values(dec):
                 assert e.code in (1, 2, 3, 6)
         dec.decode(data)
         dec.release_frames()
+
+
+def test_animation_all_frames_bit_exact(dec, oracle):
+    """Multi-frame codestream with cropped, blended frames and reference slots: every displayed frame."""
+    data = fixture_bytes("animation_icos4d", "input.jxl")
+    dec.decode(data)
+    img = oracle.OracleImage(data, threads=8)
+    assert dec.num_frames() == img.num_frames == 48
+    for k in range(img.num_frames):
+        got = dec.frame_planar(k)
+        want = img.frame(k)[0]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), k
+    dec.release_frames()

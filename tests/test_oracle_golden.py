@@ -98,6 +98,45 @@ def test_vardct_conformance_bike(oracle):
     assert math.sqrt(float((diff ** 2).mean())) <= 0.002
 
 
+def test_layers_blending_and_orientation_sunset_logo(oracle):
+    """Cropped layers composed onto the canvas (jxl-render/src/blend.rs) and orientation 7 through
+    ImageStream::write_to_buffer (fb.rs:387-401): libjxl's rendering is reproduced at 8 bits."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("sunset_logo", "input.jxl"), threads=4)
+    assert img.orientation == 7
+    buf = img.frame_to_buffer(0, np.uint16, 0).astype(np.float32) / 65535.0
+    assert buf.shape == (1386, 924, 4)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("sunset_logo", "ref_crop_200_400.png")))).astype(np.float32) / 255.0
+    assert np.abs(buf[400:912, 200:712] - ref).max() <= 0.004
+
+
+def test_animation_frames_icos4d(oracle):
+    """48 cropped frames blended over reference slots; three of them against the reference APNG."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("animation_icos4d", "input.jxl"), threads=4)
+    assert img.num_frames == 48
+    for k in (0, 17, 47):
+        ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("animation_icos4d", "ref_frame_%02d.png" % k)))).astype(np.float32) / 255.0
+        got = np.moveaxis(np.clip(img.frame(k)[0], 0.0, 1.0), 0, 2)
+        assert np.abs(got - ref).max() <= 0.004, k
+
+
+def test_blend_modes_alpha_plane(oracle):
+    """Replace / Blend / Add / Mul / MulAdd layers (blend.rs:55-103, 550-727). The alpha plane of libjxl's
+    rendering is reproduced everywhere; the colour planes wherever the last layer's weight stayed in [0, 1]
+    (the reference decoder does not clamp it when the frame's clamp flag is off, the PNG's producer did)."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("blendmodes", "input.jxl"), threads=4)
+    planes, _, _ = img.frame(0)
+    ref = np.moveaxis(np.asarray(Image.open(io.BytesIO(fixture_bytes("blendmodes", "ref.png")))).astype(np.float32) / 255.0, 2, 0)
+    diff = np.abs(np.clip(planes, 0.0, 1.0) - ref)
+    assert diff[3].max() <= 0.004
+    assert float((diff[:3].max(axis=0) <= 0.004).mean()) > 0.25
+
+
 def test_lz77_modular_vs_png(oracle):
     from PIL import Image
     import io
