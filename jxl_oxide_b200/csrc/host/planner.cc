@@ -573,8 +573,18 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   // colour transform
   bool colour_done = is_lf_frame || is_ref_frame;
   if (rf.gab_enabled || rf.epf.iters > 0) {
-    JXLB_CHECK(colour.size() == 3, kErrUnsupported, "restoration filters on grayscale frames are not supported");
-    View v[3] = {colour[0], colour[1], colour[2]};
+    // a grayscale frame is filtered as three identical channels and truncated again (render.rs:74-134)
+    JXLB_CHECK(colour.size() == 3 || colour.size() == 1, kErrUnsupported, "restoration filters need one or three colour channels");
+    View v[3];
+    for (int c = 0; c < 3; ++c) {
+      if (size_t(c) < colour.size()) {
+        v[c] = colour[c];
+      } else {
+        int id = new_plane(colour[0].w, colour[0].h);
+        v[c] = View{id, 0, 0, colour[0].w, colour[0].h};
+        be_.copy_rect(colour[0], v[c]);
+      }
+    }
     View sigma_view;
     if (vardct) sigma_view = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
     ColorParams cp;

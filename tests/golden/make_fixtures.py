@@ -28,6 +28,7 @@ CASES = {
     "patches_lossless": ("conformance/testcases/patches_lossless", ["input.jxl", "ref.png"]),
     "bike": ("conformance/testcases/bike", ["input.jxl"]),
     "sunset_logo": ("conformance/testcases/sunset_logo", ["input.jxl"]),
+    "grayscale_public_university": ("conformance/testcases/grayscale_public_university", ["input.jxl"]),
     "blendmodes": ("conformance/testcases/blendmodes", ["input.jxl", "ref.png"]),
     "animation_icos4d": ("conformance/testcases/animation_icos4d", ["input.jxl"]),
 }
@@ -47,6 +48,8 @@ Image.open(os.path.join(REF, "conformance/testcases/bike/ref.png")).crop((700, 9
 # sunset_logo's reference is 0.9 MB: a 512 x 512 crop at (200, 400) of the oriented image
 Image.open(os.path.join(REF, "conformance/testcases/sunset_logo/ref.png")).crop((200, 400, 712, 912)).save(
     os.path.join(HERE, "sunset_logo", "ref_crop_200_400.png"), optimize=True)
+Image.open(os.path.join(REF, "conformance/testcases/grayscale_public_university/ref.png")).crop((1000, 500, 1512, 1012)).save(
+    os.path.join(HERE, "grayscale_public_university", "ref_crop_1000_500.png"), optimize=True)
 # three frames of the animation's reference APNG
 _ap = Image.open(os.path.join(REF, "conformance/testcases/animation_icos4d/ref.apng"))
 for _k in (0, 17, 47):

@@ -137,6 +137,18 @@ def test_blend_modes_alpha_plane(oracle):
     assert float((diff[:3].max(axis=0) <= 0.004).mean()) > 0.25
 
 
+def test_grayscale_modular_with_filters(oracle):
+    """One-channel Modular frame (Squeeze) whose restoration filters run on a cloned gray triple
+    (jxl-render/src/render.rs:74-134)."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("grayscale_public_university", "input.jxl"), threads=8)
+    planes, ncol, _ = img.frame(0)
+    assert planes.shape == (1, 1620, 2880)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("grayscale_public_university", "ref_crop_1000_500.png")))).astype(np.float32) / 255.0
+    assert np.abs(np.clip(planes[0, 500:1012, 1000:1512], 0.0, 1.0) - ref).max() <= 0.004
+
+
 def test_lz77_modular_vs_png(oracle):
     from PIL import Image
     import io
