@@ -1109,6 +1109,16 @@ void CudaBackend::blend_patches(const std::vector<PatchJob>& jobs) {
   flush();
 }
 
+void CudaBackend::splat_splines(const View v[3], const std::vector<SplineArc>& arcs) {
+  if (arcs.empty()) return;
+  static_assert(sizeof(SplineArc) == sizeof(DevSplineArc), "arc layouts must agree");
+  DevView dv[3] = {dev_view(v[0]), dev_view(v[1]), dev_view(v[2])};
+  const DevSplineArc* d = static_cast<const DevSplineArc*>(upload_temp(arcs.data(), arcs.size() * sizeof(SplineArc)));
+  begin_k("splat_splines");
+  launch_splat_splines(dv, d, int(arcs.size()), stream_);
+  end_k();
+}
+
 void CudaBackend::add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x,
                             float corr_b) {
   JXLB_CHECK(v[0].w >= 2 && v[0].h >= 2, kErrUnsupported, "noise on frames narrower than 2 samples is not supported");

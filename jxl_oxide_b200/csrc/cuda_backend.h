@@ -42,6 +42,7 @@ class CudaBackend : public Backend {
   void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) override;
   int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) override;
   void blend_patches(const std::vector<PatchJob>& jobs) override;
+  void splat_splines(const View v[3], const std::vector<SplineArc>& arcs) override;
   void add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x, float corr_b) override;
   void xyb_to_rgb(const View v[3], const ColorParams& p) override;
   bool filters_colour_fused(const View v[3], const RestorationFilter& rf, const View& sigma, bool sigma_is_constant,

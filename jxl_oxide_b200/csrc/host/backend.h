@@ -141,6 +141,13 @@ class Backend {
     View base_alpha, new_alpha;
   };
   virtual void blend_patches(const std::vector<PatchJob>& jobs) = 0;
+  // Spline rendering (jxl-render/src/features/spline.rs:180-254): every arc sample adds a Gaussian-like blob
+  // 0.25 * value[c] * sigma * factor^2 to the pixels of its bounding box, arcs in list order.
+  struct SplineArc {
+    float x, y, sigma, inv_sigma, value[3];
+    int32_t xbegin, xend, ybegin, yend;
+  };
+  virtual void splat_splines(const View v[3], const std::vector<SplineArc>& arcs) = 0;
   // Noise synthesis (jxl-render/src/features/noise.rs:12-86): pseudo-random field per group_dim x group_dim
   // group (XorShift128+ seeded by `seed0` and the group origin), 5x5 high-pass, intensity-dependent strength
   // from `lut`, added to the XYB planes `v` (frame_w x frame_h).

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cmath>
 
 namespace jxlb {
@@ -135,7 +136,54 @@ LfGlobalSyntax parse_lf_global(BitReader& br, const ImageHeader& ih, const Frame
     }
     JXLB_CHECK(dec.finalize_ok(), kErrBitstream, "invalid ANS stream (patches)");
   }
-  JXLB_CHECK(!fh.splines(), kErrUnsupported, "splines are outside the implemented hot path");
+  if (fh.splines()) {  // Splines::parse + QuantSpline::parse (jxl-frame/src/data/spline.rs:18-66, 155-224)
+    g.has_splines = true;
+    EntropyCode code = parse_entropy_code(br, 6);
+    EntropyReader dec(&code);
+    dec.begin(br);
+    const uint64_t num_pixels = uint64_t(fh.width) * fh.height;
+    size_t num_splines = dec.read_varint(br, 2);
+    JXLB_CHECK(num_splines < std::min<uint64_t>(1u << 24, num_pixels / 4), kErrBitstream, "too many splines");
+    ++num_splines;
+    std::vector<std::pair<int64_t, int64_t>> start(num_splines);
+    std::pair<int64_t, int64_t> prev;
+    prev.first = dec.read_varint(br, 1);
+    prev.second = dec.read_varint(br, 1);
+    start[0] = prev;
+    for (size_t i = 1; i < num_splines; ++i) {
+      const uint32_t x = dec.read_varint(br, 1), y = dec.read_varint(br, 1);
+      prev.first += unpack_signed(x);
+      prev.second += unpack_signed(y);
+      start[i] = prev;
+    }
+    g.spline_quant_adjust = unpack_signed(dec.read_varint(br, 0));
+    size_t acc_points = 0;
+    const size_t max_points = size_t(std::min<uint64_t>(1u << 20, num_pixels / 2));
+    for (size_t i = 0; i < num_splines; ++i) {
+      QuantSpline q;
+      const size_t num_points = dec.read_varint(br, 3);
+      acc_points += num_points;
+      JXLB_CHECK(acc_points <= max_points, kErrBitstream, "too many spline points");
+      std::pair<int64_t, int64_t> cur = start[i], delta{0, 0};
+      q.points.push_back(cur);
+      for (size_t k = 0; k < num_points; ++k) {
+        const std::pair<int64_t, int64_t> before = cur;
+        delta.first += unpack_signed(dec.read_varint(br, 4));
+        delta.second += unpack_signed(dec.read_varint(br, 4));
+        q.manhattan_distance += uint64_t(std::llabs(delta.first)) + uint64_t(std::llabs(delta.second));
+        cur.first += delta.first;
+        cur.second += delta.second;
+        JXLB_CHECK(std::llabs(cur.first) < (int64_t(1) << 40) && std::llabs(cur.second) < (int64_t(1) << 40), kErrBitstream, "control point overflowed");
+        JXLB_CHECK(cur != before, kErrBitstream, "two consecutive control points have the same value");
+        q.points.push_back(cur);
+      }
+      for (auto& ch : q.xyb_dct)
+        for (int32_t& v : ch) v = unpack_signed(dec.read_varint(br, 5));
+      for (int32_t& v : q.sigma_dct) v = unpack_signed(dec.read_varint(br, 5));
+      g.splines.push_back(std::move(q));
+    }
+    JXLB_CHECK(dec.finalize_ok(), kErrBitstream, "invalid ANS stream (splines)");
+  }
   if (fh.noise()) {  // lf_global.rs:96-105
     g.has_noise = true;
     for (float& v : g.noise_lut) v = float(br.read(10)) / float(1 << 10);
@@ -158,6 +206,38 @@ LfGlobalSyntax parse_lf_global(BitReader& br, const ImageHeader& ih, const Frame
       g.x_factor_lf = br.read(8);
       g.b_factor_lf = br.read(8);
     }
+  }
+  if (g.has_splines) {  // Splines::estimate_area and the Level 10 limit (spline.rs:70-118, lf_global.rs:124-147)
+    const bool vardct = fh.encoding == Encoding::kVarDct;
+    const uint64_t corr_x = vardct ? uint64_t(std::ceil(std::fabs(g.base_correlation_x))) : 0;
+    const uint64_t corr_b = vardct ? uint64_t(std::ceil(std::fabs(g.base_correlation_b))) : 1;
+    const int32_t qa = g.spline_quant_adjust;
+    auto div_ceil_qa = [qa](uint32_t v) -> uint64_t {
+      const uint64_t d = v;
+      if (qa >= 0) return (8 * d + 7 + uint64_t(qa)) / (8 + uint64_t(qa));
+      const uint64_t a = uint64_t(-int64_t(qa));
+      return d + (d * a + 7) / 8;
+    };
+    uint64_t total_area = 0;
+    for (const QuantSpline& q : g.splines) {
+      uint64_t colour[3] = {0, 0, 0};
+      for (int c = 0; c < 3; ++c)
+        for (int32_t v : q.xyb_dct[c]) colour[c] += div_ceil_qa(uint32_t(std::llabs(int64_t(v))));
+      colour[0] += corr_x * colour[1];
+      colour[2] += corr_b * colour[1];
+      const uint64_t m = 1 + std::max(colour[0], std::max(colour[1], colour[2]));
+      uint64_t log_colour = 0;
+      while ((uint64_t(1) << log_colour) < m) ++log_colour;
+      uint64_t width_estimate = 0;
+      for (int32_t v : q.sigma_dct) {
+        const uint64_t weight = 1 + div_ceil_qa(uint32_t(std::llabs(int64_t(v))));
+        width_estimate += weight * weight * log_colour;
+      }
+      total_area += width_estimate * q.manhattan_distance;
+    }
+    const uint64_t image_size = uint64_t(fh.width) * fh.height;
+    JXLB_CHECK(total_area <= std::min<uint64_t>(uint64_t(1) << 42, 1024 * image_size + (uint64_t(1) << 32)), kErrBitstream,
+               "too large estimated area for splines");
   }
   br.check();
   // GlobalModular (lf_global.rs:204-313)

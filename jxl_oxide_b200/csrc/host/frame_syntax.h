@@ -53,7 +53,18 @@ struct PatchRef {
   std::vector<PatchTarget> targets;
 };
 
+// Splines (jxl-frame/src/data/spline.rs): quantised control points + DCT32 of colour and thickness.
+struct QuantSpline {
+  std::vector<std::pair<int64_t, int64_t>> points;  // absolute control points
+  int32_t xyb_dct[3][32];
+  int32_t sigma_dct[32];
+  uint64_t manhattan_distance = 0;  // of the control polygon; feeds the area limit
+};
+
 struct LfGlobalSyntax {
+  bool has_splines = false;
+  int32_t spline_quant_adjust = 0;
+  std::vector<QuantSpline> splines;
   bool has_patches = false;
   std::vector<PatchRef> patches;
   // NoiseParameters (jxl-frame/src/data/noise.rs:2-17): strength LUT over intensity

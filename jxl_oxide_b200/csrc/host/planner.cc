@@ -58,6 +58,143 @@ struct LfFrameStore {
   View planes[3];  // X, Y, B (f32)
 };
 
+// Splines: dequantisation, centripetal Catmull-Rom upsampling, unit arc-length resampling and the per-arc colour /
+// thickness (jxl-render/src/features/spline.rs:41-178 and the head of render_spline :180-218). Scalar host work - a
+// few thousand samples per frame - whose output is the arc list both backends splat.
+namespace {
+struct Pt {
+  float x, y;
+};
+inline Pt operator+(Pt a, Pt b) { return {a.x + b.x, a.y + b.y}; }
+inline Pt operator-(Pt a, Pt b) { return {a.x - b.x, a.y - b.y}; }
+inline Pt operator*(Pt a, float k) { return {a.x * k, a.y * k}; }
+inline float norm2(Pt a) { return a.x * a.x + a.y * a.y; }
+inline float norm(Pt a) { return std::sqrt(norm2(a)); }
+inline Pt mirror(Pt p, Pt centre) { return {centre.x + centre.x - p.x, centre.y + centre.y - p.y}; }
+
+// value of a 32-point DCT-II series at the fractional position t (spline.rs:303-310)
+float continuous_idct(const float dct[32], float t) {
+  float res = dct[0];
+  for (int i = 1; i < 32; ++i) {
+    const float theta = float(i) * (3.14159265358979323846f / 32.0f) * (t + 0.5f);
+    res += 1.41421356237309504880f * dct[i] * std::cos(theta);
+  }
+  return res;
+}
+
+// Rust's saturating `as i32` (NaN -> 0)
+int32_t to_i32_sat(float v) {
+  if (v != v) return 0;
+  if (v >= 2147483648.0f) return INT32_MAX;
+  if (v <= -2147483648.0f) return INT32_MIN;
+  return int32_t(v);
+}
+
+std::vector<Pt> catmull_rom_points(const std::vector<Pt>& s) {
+  if (s.size() == 1) return {s[0]};
+  std::vector<Pt> ext;
+  ext.reserve(s.size() + 2);
+  ext.push_back(mirror(s[1], s[0]));
+  ext.insert(ext.end(), s.begin(), s.end());
+  ext.push_back(mirror(s[s.size() - 2], s[s.size() - 1]));
+  std::vector<Pt> up;
+  up.reserve(16 * (ext.size() - 3) + 1);
+  for (size_t i = 0; i + 3 < ext.size(); ++i) {
+    const Pt* p = &ext[i];
+    up.push_back(p[1]);
+    float t[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    for (int k = 1; k < 4; ++k) t[k] = t[k - 1] + std::pow(norm2(p[k] - p[k - 1]), 0.25f);  // knots, alpha = 1/4
+    for (int step = 1; step < 16; ++step) {
+      const float knot = t[1] + (float(step) / 16.0f) * (t[2] - t[1]);
+      Pt a[3], b[2];
+      for (int k = 0; k < 3; ++k) a[k] = p[k] + (p[k + 1] - p[k]) * ((knot - t[k]) / (t[k + 1] - t[k]));
+      for (int k = 0; k < 2; ++k) b[k] = a[k] + (a[k + 1] - a[k]) * ((knot - t[k]) / (t[k + 2] - t[k]));
+      up.push_back(b[0] + (b[1] - b[0]) * ((knot - t[1]) / (t[2] - t[1])));
+    }
+  }
+  up.push_back(s.back());
+  return up;
+}
+
+struct ArcSample {
+  Pt point;
+  float length;
+};
+
+// walk the polyline in unit steps; the last sample carries the remaining length
+std::vector<ArcSample> unit_arc_samples(const std::vector<Pt>& up) {
+  Pt current = up[0];
+  size_t next = 0;
+  std::vector<ArcSample> out{{current, 1.0f}};
+  while (next < up.size()) {
+    Pt prev = current;
+    float arclength = 0.0f;
+    for (;;) {
+      if (next >= up.size()) {
+        out.push_back({prev, arclength});
+        break;
+      }
+      const Pt nx = up[next];
+      const float to_next = norm(nx - prev);
+      if (arclength + to_next >= 1.0f) {
+        current = prev + (nx - prev) * ((1.0f - arclength) / to_next);
+        out.push_back({current, 1.0f});
+        break;
+      }
+      arclength += to_next;
+      prev = nx;
+      ++next;
+    }
+  }
+  return out;
+}
+}  // namespace
+
+std::vector<Backend::SplineArc> build_spline_arcs(const LfGlobalSyntax& g, bool /*vardct*/, float corr_x, float corr_b, uint32_t width,
+                                                  uint32_t height) {
+  std::vector<Backend::SplineArc> arcs;
+  const float qa = float(g.spline_quant_adjust);
+  const float inverted_qa = qa >= 0.0f ? 1.0f / (1.0f + qa / 8.0f) : 1.0f - qa / 8.0f;
+  static const float kChannelWeights[4] = {0.0042f, 0.075f, 0.07f, 0.3333f};
+  for (const QuantSpline& q : g.splines) {
+    std::vector<Pt> pts;
+    for (const auto& xy : q.points) pts.push_back({float(xy.first), float(xy.second)});
+    float xyb[3][32], sigma_dct[32];
+    for (int c = 0; c < 3; ++c)
+      for (int i = 0; i < 32; ++i) xyb[c][i] = float(q.xyb_dct[c][i]) * kChannelWeights[c] * inverted_qa;
+    for (int i = 0; i < 32; ++i) {
+      xyb[0][i] += corr_x * xyb[1][i];
+      xyb[2][i] += corr_b * xyb[1][i];
+    }
+    for (int i = 0; i < 32; ++i) sigma_dct[i] = float(q.sigma_dct[i]) * kChannelWeights[3] * inverted_qa;
+
+    // the area limit does not bound the polygon's length when all colour coefficients are zero; the walk below is
+    // linear in that length, so refuse absurd ones (the reference would allocate a sample per unit of length)
+    JXLB_CHECK(q.manhattan_distance < (uint64_t(1) << 24), kErrUnsupported, "spline control polygon longer than 2^24 samples");
+    const std::vector<ArcSample> samples = unit_arc_samples(catmull_rom_points(pts));
+    const float arclength = float(samples.size()) - 2.0f + samples.back().length;
+    for (size_t i = 0; i < samples.size(); ++i) {
+      const float from_start = std::fmin(1.0f, float(i) / arclength);
+      const float t = 31.0f * from_start;
+      Backend::SplineArc a;
+      a.x = samples[i].point.x;
+      a.y = samples[i].point.y;
+      a.sigma = continuous_idct(sigma_dct, t);
+      a.inv_sigma = 1.0f / a.sigma;
+      for (int c = 0; c < 3; ++c) a.value[c] = continuous_idct(xyb[c], t) * samples[i].length;
+      // f32::max semantics: a NaN operand is ignored
+      const float max_colour = std::fmax(0.01f, std::fmax(std::fmax(a.value[0], a.value[1]), a.value[2]));
+      const float max_distance = std::sqrt(2.0f * (std::log(10.0f) * 3.0f + max_colour)) * std::fabs(a.sigma);
+      a.xbegin = std::max<int32_t>(0, to_i32_sat(std::floor(a.x - max_distance + 0.5f)));
+      a.xend = std::min<int32_t>(int32_t(width), to_i32_sat(std::floor(a.x + max_distance + 1.5f)));
+      a.ybegin = std::max<int32_t>(0, to_i32_sat(std::floor(a.y - max_distance + 0.5f)));
+      a.yend = std::min<int32_t>(int32_t(height), to_i32_sat(std::floor(a.y + max_distance + 1.5f)));
+      if (a.xbegin < a.xend && a.ybegin < a.yend) arcs.push_back(a);
+    }
+  }
+  return arcs;
+}
+
 // Reference slots (jxl-render/src/state.rs, lib.rs:296-330): a frame saved for later frames' patches. Only
 // reference-only frames saved before the colour transform are kept (what libjxl's patch detector emits).
 struct RefFrameStore {
@@ -589,7 +726,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     if (vardct) sigma_view = View{st_.epf_sigma, 0, 0, st_.bw, st_.bh};
     ColorParams cp;
     // colour conversion follows upsampling (render.rs:136-149), so it is fused only without it
-    const bool want_colour = !upsampled && !colour_done && !lfg_.has_noise && !lfg_.has_patches &&
+    const bool want_colour = !upsampled && !colour_done && !lfg_.has_noise && !lfg_.has_patches && !lfg_.has_splines &&
                              colour_params(ih_.xyb_encoded, colour.size(), &cp);
     if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
       colour_done = want_colour;
@@ -663,6 +800,17 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     }
     be_.blend_patches(jobs);
     be_.stage_marker("patches", colour.data(), int(colour.size()));
+  }
+  if (lfg_.has_splines) {
+    JXLB_CHECK(colour.size() == 3, kErrUnsupported, "splines need three colour channels");
+    // the reference draws splines on the grid as it stands after patches (render.rs:182-205); with upsampling and no
+    // patches that is the pre-upsampling grid - not restated here
+    JXLB_CHECK(!upsampled, kErrUnsupported, "splines together with upsampling are not implemented");
+    const std::vector<Backend::SplineArc> arcs =
+        build_spline_arcs(lfg_, vardct, vardct ? lfg_.base_correlation_x : 0.0f, vardct ? lfg_.base_correlation_b : 1.0f, fh_.width, fh_.height);
+    View v[3] = {colour[0], colour[1], colour[2]};
+    be_.splat_splines(v, arcs);
+    be_.stage_marker("splines", v, 3);
   }
   if (lfg_.has_noise) {
     JXLB_CHECK(colour.size() == 3 && ih_.xyb_encoded, kErrUnsupported, "noise synthesis is implemented for XYB colour frames");

@@ -337,6 +337,74 @@ __global__ void blend_patches_kernel(const DevPatchJob* __restrict__ jobs) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Splines (features/spline.rs:218-252, erf :314-331)
+__device__ __forceinline__ float spline_erf(float x) {
+  const float ax = fabsf(x);
+  const float denom1 = fadd(fmul(ax, 7.77394369e-02f), 2.05260015e-04f);
+  const float denom2 = fadd(fmul(denom1, ax), 2.32120216e-01f);
+  const float denom3 = fadd(fmul(denom2, ax), 2.77820801e-01f);
+  const float denom4 = fadd(fmul(denom3, ax), 1.0f);
+  const float denom5 = fmul(denom4, denom4);
+  const float inv_denom5 = fdiv(1.0f, denom5);
+  const float result = fadd(fmul(-inv_denom5, inv_denom5), 1.0f);
+  return x < 0.0f ? -result : result;
+}
+
+// One thread per pixel, 32x8 tiles. The arc list is walked in chunks of 256: every thread tests one arc's bounding box
+// against the tile and the hits are compacted IN LIST ORDER into shared memory (float addition order is part of the
+// result), then every pixel accumulates the surviving arcs.
+__global__ void __launch_bounds__(256) splat_splines_kernel(DevView v0, DevView v1, DevView v2, const DevSplineArc* __restrict__ arcs,
+                                                            int num_arcs) {
+  __shared__ DevSplineArc hit[256];
+  __shared__ int warp_count[8];
+  const int tid = threadIdx.y * 32 + threadIdx.x, lane = threadIdx.x, warp = threadIdx.y;
+  const int tx0 = blockIdx.x * 32, ty0 = blockIdx.y * 8;
+  const int x = tx0 + lane, y = ty0 + warp;
+  const bool inside = x < int(v0.w) && y < int(v0.h);
+  float* p[3] = {static_cast<float*>(v0.ptr) + size_t(y) * v0.stride + x, static_cast<float*>(v1.ptr) + size_t(y) * v1.stride + x,
+                 static_cast<float*>(v2.ptr) + size_t(y) * v2.stride + x};
+  float acc[3] = {0.0f, 0.0f, 0.0f};
+  if (inside) acc[0] = *p[0], acc[1] = *p[1], acc[2] = *p[2];
+  bool touched = false;
+  for (int base = 0; base < num_arcs; base += 256) {
+    DevSplineArc a;
+    bool h = false;
+    if (base + tid < num_arcs) {
+      a = arcs[base + tid];
+      h = a.xbegin < tx0 + 32 && a.xend > tx0 && a.ybegin < ty0 + 8 && a.yend > ty0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, h);
+    if (lane == 0) warp_count[warp] = __popc(m);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) before += warp_count[w];
+      total += warp_count[w];
+    }
+    if (h) hit[before + __popc(m & ((1u << lane) - 1u))] = a;
+    __syncthreads();
+    if (inside)
+      for (int i = 0; i < total; ++i) {
+        const DevSplineArc& q = hit[i];
+        if (x < q.xbegin || x >= q.xend || y < q.ybegin || y >= q.yend) continue;
+        const float dx = fsub(float(x), q.x), dy = fsub(float(y), q.y);
+        const float distance = __fsqrt_rn(fadd(fmul(dx, dx), fmul(dy, dy)));
+        const float factor = fsub(spline_erf(fmul(fadd(fmul(0.5f, distance), 0.35355338f), q.inv_sigma)),
+                                  spline_erf(fmul(fsub(fmul(0.5f, distance), 0.35355338f), q.inv_sigma)));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) acc[c] = fadd(acc[c], fmul(fmul(fmul(fmul(0.25f, q.value[c]), q.sigma), factor), factor));
+        touched = true;
+      }
+    __syncthreads();
+  }
+  if (touched) {
+    *p[0] = acc[0];
+    *p[1] = acc[1];
+    *p[2] = acc[2];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Noise synthesis (features/noise.rs)
 __device__ __forceinline__ unsigned long long split_mix_64(unsigned long long z) {  // noise.rs:454-458
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -431,6 +499,13 @@ __global__ void noise_apply_kernel(DevView vx, DevView vy, DevView vb, const flo
 void launch_blend_patches(const DevPatchJob* jobs, int num_jobs, cudaStream_t stream) {
   if (num_jobs <= 0) return;
   blend_patches_kernel<<<num_jobs, 128, 0, stream>>>(jobs);
+}
+
+void launch_splat_splines(const DevView v[3], const DevSplineArc* arcs, int num_arcs, cudaStream_t stream) {
+  if (num_arcs <= 0 || !v[0].w || !v[0].h) return;
+  dim3 block(32, 8);
+  dim3 grid((v[0].w + 31) / 32, (v[0].h + 7) / 8);
+  splat_splines_kernel<<<grid, block, 0, stream>>>(v[0], v[1], v[2], arcs, num_arcs);
 }
 
 void launch_add_noise(const DevView v[3], float* const field[3], DevNoiseParams p, cudaStream_t stream) {

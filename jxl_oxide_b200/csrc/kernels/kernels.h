@@ -174,6 +174,12 @@ struct DevPatchJob {
   uint32_t src_stride, dst_stride, base_alpha_stride, new_alpha_stride, w, h, mode, clamp, premultiplied;
 };
 void launch_blend_patches(const DevPatchJob* jobs, int num_jobs, cudaStream_t stream);
+// Spline splatting (jxl-render/src/features/spline.rs:218-252): one thread per pixel walks the arc list in order.
+struct DevSplineArc {
+  float x, y, sigma, inv_sigma, value[3];
+  int32_t xbegin, xend, ybegin, yend;
+};
+void launch_splat_splines(const DevView v[3], const DevSplineArc* arcs, int num_arcs, cudaStream_t stream);
 // Noise synthesis (crates/jxl-render/src/features/noise.rs). `field`: three frame-sized scratch planes.
 struct DevNoiseParams {
   float lut[9];

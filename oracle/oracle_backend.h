@@ -61,6 +61,7 @@ class OracleBackend : public Backend {
   void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) override;
   int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) override;
   void blend_patches(const std::vector<PatchJob>& jobs) override;
+  void splat_splines(const View v[3], const std::vector<SplineArc>& arcs) override;
   void add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x, float corr_b) override;
   void xyb_to_rgb(const View v[3], const ColorParams& p) override;
   void stage_marker(const char* name, const View* views, int n) override;

@@ -419,6 +419,42 @@ void OracleBackend::blend_patches(const std::vector<PatchJob>& jobs) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Splines: the splat loop of render_spline and its erf (crates/jxl-render/src/features/spline.rs:218-252, 314-331)
+namespace {
+float spline_erf(float x) {
+  const float ax = std::fabs(x);
+  const float denom1 = ax * 7.77394369e-02f + 2.05260015e-04f;
+  const float denom2 = denom1 * ax + 2.32120216e-01f;
+  const float denom3 = denom2 * ax + 2.77820801e-01f;
+  const float denom4 = denom3 * ax + 1.0f;
+  const float denom5 = denom4 * denom4;
+  const float inv_denom5 = 1.0f / denom5;
+  const float result = -inv_denom5 * inv_denom5 + 1.0f;
+  return x < 0.0f ? -result : result;
+}
+}  // namespace
+
+void OracleBackend::splat_splines(const View v[3], const std::vector<SplineArc>& arcs) {
+  for (const SplineArc& a : arcs)
+    for (int c = 0; c < 3; ++c) {
+      Plane& p = plane(v[c].plane);
+      for (int32_t y = a.ybegin; y < a.yend; ++y) {
+        if (uint32_t(y) >= v[c].h) break;
+        float* row = p.f32() + size_t(v[c].y0 + y) * p.w + v[c].x0;
+        for (int32_t x = a.xbegin; x < a.xend; ++x) {
+          if (uint32_t(x) >= v[c].w) break;
+          const float dx = float(x) - a.x, dy = float(y) - a.y;
+          const float distance = std::sqrt(dx * dx + dy * dy);
+          const float factor = spline_erf((0.5f * distance + 0.35355338f) * a.inv_sigma) -
+                               spline_erf((0.5f * distance - 0.35355338f) * a.inv_sigma);
+          const float extra = 0.25f * a.value[c] * a.sigma * factor * factor;
+          row[x] = row[x] + extra;
+        }
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Noise synthesis (crates/jxl-render/src/features/noise.rs)
 namespace {
 uint64_t split_mix_64(uint64_t z) {  // noise.rs:454-458

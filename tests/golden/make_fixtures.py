@@ -31,6 +31,7 @@ CASES = {
     "grayscale_public_university": ("conformance/testcases/grayscale_public_university", ["input.jxl"]),
     "blendmodes": ("conformance/testcases/blendmodes", ["input.jxl", "ref.png"]),
     "animation_icos4d": ("conformance/testcases/animation_icos4d", ["input.jxl"]),
+    "animation_spline": ("conformance/testcases/animation_spline", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 
@@ -55,6 +56,10 @@ _ap = Image.open(os.path.join(REF, "conformance/testcases/animation_icos4d/ref.a
 for _k in (0, 17, 47):
     _ap.seek(_k)
     _ap.convert("RGBA").save(os.path.join(HERE, "animation_icos4d", "ref_frame_%02d.png" % _k), optimize=True)
+_ap = Image.open(os.path.join(REF, "conformance/testcases/animation_spline/ref.apng"))
+for _k in (0, 23, 59):
+    _ap.seek(_k)
+    _ap.convert("RGB").save(os.path.join(HERE, "animation_spline", "ref_frame_%02d.png" % _k), optimize=True)
 # malformed inputs found by the reference's fuzzers (crates/jxl-oxide-tests/tests/fuzz_findings): expectation =
 # no crash, a clean error value (or a successful decode)
 import glob

@@ -233,3 +233,16 @@ def test_animation_all_frames_bit_exact(dec, oracle):
         want = img.frame(k)[0]
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), k
     dec.release_frames()
+
+
+def test_animation_splines_bit_exact(dec, oracle):
+    """Spline rendering: the host-built arc list splatted by splat_splines_kernel, all 60 frames against the oracle."""
+    data = fixture_bytes("animation_spline", "input.jxl")
+    dec.decode(data)
+    img = oracle.OracleImage(data, threads=8)
+    assert dec.num_frames() == img.num_frames == 60
+    for k in range(img.num_frames):
+        got = dec.frame_planar(k)
+        want = img.frame(k)[0]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), k
+    dec.release_frames()

@@ -123,6 +123,19 @@ def test_animation_frames_icos4d(oracle):
         assert np.abs(got - ref).max() <= 0.004, k
 
 
+def test_animation_splines(oracle):
+    """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
+    points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("animation_spline", "input.jxl"), threads=4)
+    assert img.num_frames == 60
+    for k in (0, 23, 59):
+        ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("animation_spline", "ref_frame_%02d.png" % k)))).astype(np.float32) / 255.0
+        got = np.moveaxis(np.clip(img.frame(k)[0], 0.0, 1.0), 0, 2)
+        assert np.abs(got - ref).max() <= 0.004, k
+
+
 def test_blend_modes_alpha_plane(oracle):
     """Replace / Blend / Add / Mul / MulAdd layers (blend.rs:55-103, 550-727). The alpha plane of libjxl's
     rendering is reproduced everywhere; the colour planes wherever the last layer's weight stayed in [0, 1]
