@@ -1199,6 +1199,13 @@ int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader
   return id;
 }
 
+void CudaBackend::ycbcr_to_rgb(const View v[3], const YcbcrParams& p) {
+  const DevYcbcrParams d{p.y_offset, p.cr_to_r, p.cb_to_g, p.cr_to_g, p.cb_to_b};
+  begin_k("ycbcr_to_rgb");
+  launch_ycbcr_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
+  end_k();
+}
+
 void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   DevColorParams d;
   for (int i = 0; i < 3; ++i) {

@@ -154,6 +154,18 @@ class Backend {
   virtual void add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x,
                          float corr_b) = 0;
   virtual void xyb_to_rgb(const View v[3], const ColorParams& p) = 0;
+  // YCbCr -> RGB of JPEG-transcoded frames, planes in Cb, Y, Cr order (jxl-color/src/ycbcr.rs:40-56)
+  struct YcbcrParams {
+    float y_offset, cr_to_r, cb_to_g, cr_to_g, cb_to_b;
+    YcbcrParams() {
+      y_offset = 128.0f / 255.0f;
+      cr_to_r = 1.402f;
+      cb_to_g = -0.114f * 1.772f / 0.587f;
+      cr_to_g = -0.299f * 1.402f / 0.587f;
+      cb_to_b = 1.772f;
+    }
+  };
+  virtual void ycbcr_to_rgb(const View v[3], const YcbcrParams& p) = 0;
   // Optional single-pass form of gaborish() + epf() + xyb_to_rgb() (`colour` may be null). Returns
   // false when the backend wants the stages issued one by one.
   virtual bool filters_colour_fused(const View /*v*/[3], const RestorationFilter& /*rf*/, const View& /*sigma*/,

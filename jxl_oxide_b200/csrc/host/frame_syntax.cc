@@ -276,7 +276,9 @@ namespace {
 
 // DequantMatrixParamsEncoding (dequant.rs:17-37)
 struct MatrixParams {
-  enum Mode { kHornuss, kDct2, kDct4, kDct4x8, kAfv, kDct } mode = kDct;
+  enum Mode { kHornuss, kDct2, kDct4, kDct4x8, kAfv, kDct, kRaw } mode = kDct;
+  float raw_denominator = 0.0f;        // Raw: weight = sample * denominator, no reciprocal (dequant.rs:367-381)
+  std::vector<int32_t> raw[3];
   float fixed[3][9] = {};              // Hornuss[3], Dct2[6], Dct4[2], Dct4x8[1], Afv[9]
   std::vector<float> dct_params[3];
   std::vector<float> dct4x4_params[3];
@@ -430,6 +432,10 @@ void build_matrix(const MatrixParams& p, uint32_t set, std::vector<float> out[3]
     const float* params = p.fixed[c];
     switch (p.mode) {
       case MatrixParams::kDct: ret = dct_quant_weights(p.dct_params[c], width, height); break;
+      case MatrixParams::kRaw:
+        ret.assign(size_t(width) * height, 0.0f);
+        for (size_t i = 0; i < ret.size() && i < p.raw[c].size(); ++i) ret[i] = float(p.raw[c][i]) * p.raw_denominator;
+        break;
       case MatrixParams::kHornuss:
         ret.assign(64, params[0]);
         ret[0] = 1.0f;
@@ -510,7 +516,8 @@ void build_matrix(const MatrixParams& p, uint32_t set, std::vector<float> out[3]
         break;
       }
     }
-    for (float& w : ret) w = 1.0f / w;
+    if (p.mode != MatrixParams::kRaw)
+      for (float& w : ret) w = 1.0f / w;
     for (float w : ret)
       JXLB_CHECK(!(w >= 1e8f || w <= 0.0f), kErrBitstream, "dequant matrix element out of range");
   }
@@ -532,7 +539,7 @@ void read_dct_params(BitReader& br, std::vector<float> out[3]) {  // dequant.rs:
   for (int c = 0; c < 3; ++c) out[c][0] *= 64.0f;
 }
 
-MatrixParams parse_matrix_params(BitReader& br, uint32_t set) {  // dequant.rs:450-577
+MatrixParams parse_matrix_params(BitReader& br, uint32_t set, uint32_t stream_index, const RawTableDecoder& raw_decoder) {  // dequant.rs:450-577
   uint32_t mode = br.read(3);
   bool small = set == 0 || set == 1 || set == 2 || set == 3 || set == 9 || set == 10;
   JXLB_CHECK(!(mode >= 1 && mode <= 5 && !small), kErrBitstream, "invalid dequant encoding mode for DctSelect");
@@ -567,8 +574,15 @@ MatrixParams parse_matrix_params(BitReader& br, uint32_t set) {  // dequant.rs:4
       p.mode = MatrixParams::kDct;
       read_dct_params(br, p.dct_params);
       break;
-    default:
-      fail(kErrUnsupported, "raw (modular-coded) dequant tables are outside the implemented hot path");
+    default: {  // 7: Raw
+      p.mode = MatrixParams::kRaw;
+      p.raw_denominator = br.read_f16();
+      uint32_t w, h;
+      DequantMatrices::matrix_size(set, &w, &h);
+      JXLB_CHECK(bool(raw_decoder), kErrUnsupported, "raw dequant tables need a Modular decoder");
+      raw_decoder(br, w, h, stream_index, p.raw);
+      break;
+    }
   }
   br.check();
   return p;
@@ -601,8 +615,8 @@ std::vector<uint32_t> natural_order(uint32_t order_id) {  // hf_pass.rs:156-231
   return ret;
 }
 
-HfGlobalSyntax parse_hf_global(BitReader& br, const ImageHeader& ih, const FrameHeader& fh,
-                               const LfGlobalSyntax& lfg) {
+HfGlobalSyntax parse_hf_global(BitReader& br, const ImageHeader& ih, const FrameHeader& fh, const LfGlobalSyntax& lfg,
+                               const RawTableDecoder& raw_decoder) {
   (void)ih;
   HfGlobalSyntax g;
   // DequantMatrixSet (dequant.rs:586-658)
@@ -610,7 +624,7 @@ HfGlobalSyntax parse_hf_global(BitReader& br, const ImageHeader& ih, const Frame
   auto build_all = [&](bool defaults) {
     auto dq = std::make_shared<DequantMatrices>();
     for (uint32_t set = 0; set < 17; ++set) {
-      MatrixParams p = defaults ? default_params(set) : parse_matrix_params(br, set);
+      MatrixParams p = defaults ? default_params(set) : parse_matrix_params(br, set, 1 + 3 * fh.num_lf_groups() + set, raw_decoder);
       build_matrix(p, set, dq->matrices[set]);
       uint32_t w, h;
       DequantMatrices::matrix_size(set, &w, &h);

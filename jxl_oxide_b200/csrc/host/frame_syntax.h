@@ -6,6 +6,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <vector>
 
@@ -110,8 +111,11 @@ struct HfGlobalSyntax {
   uint32_t num_hf_presets = 0;
   std::vector<HfPassSyntax> passes;
 };
-HfGlobalSyntax parse_hf_global(BitReader& br, const ImageHeader& ih, const FrameHeader& fh,
-                               const LfGlobalSyntax& lfg);
+// Decodes the inline three-channel Modular image of a raw dequant table (dequant.rs:537-559): `br` stands at the
+// Modular header on entry and behind the channel data on return.
+using RawTableDecoder = std::function<void(BitReader& br, uint32_t width, uint32_t height, uint32_t stream_index, std::vector<int32_t> out[3])>;
+HfGlobalSyntax parse_hf_global(BitReader& br, const ImageHeader& ih, const FrameHeader& fh, const LfGlobalSyntax& lfg,
+                               const RawTableDecoder& raw_decoder);
 
 // Natural coefficient order for an order id (hf_pass.rs:156-231).
 std::vector<uint32_t> natural_order(uint32_t order_id);

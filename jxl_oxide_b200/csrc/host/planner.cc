@@ -480,7 +480,8 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     JXLB_CHECK(vardct, kErrBitstream, "use_lf_frame on a Modular frame");
     JXLB_CHECK(fh_.lf_level < 4 && (*lf_store_)[fh_.lf_level].valid, kErrBitstream, "frame refers to an LF frame that was not decoded");
   }
-  JXLB_CHECK(!fh_.do_ycbcr, kErrUnsupported, "YCbCr (JPEG-transcoded) frames are outside the implemented hot path");
+  const bool chroma_subsampled = fh_.jpeg_upsampling[0] || fh_.jpeg_upsampling[1] || fh_.jpeg_upsampling[2];
+  JXLB_CHECK(!chroma_subsampled, kErrUnsupported, "chroma-subsampled YCbCr frames are not implemented");
   for (uint32_t u : fh_.ec_upsampling) JXLB_CHECK(u == fh_.upsampling, kErrUnsupported, "extra-channel upsampling differs from colour");
   for (const auto& ec : ih_.ec_info) JXLB_CHECK(ec.dim_shift == 0, kErrUnsupported, "dim_shift extra channels not supported");
 
@@ -637,7 +638,27 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     size_t hpos = pos, hlimit = limit;
     if (!single) section(1 + num_lf_groups, &hpos, &hlimit);
     BitReader r = reader_at(hpos, hlimit);
-    hfg_ = parse_hf_global(r, ih_, fh_, lfg_);
+    // raw dequant tables (JPEG transcodes): an inline Modular image per table, decoded by the backend like any other
+    // stream and read back - the matrices are built on the host
+    RawTableDecoder raw_decoder = [&](BitReader& br, uint32_t w, uint32_t h, uint32_t stream_index, std::vector<int32_t> out[3]) {
+      std::vector<GroupChannel> chans;
+      std::vector<int> planes;
+      for (int c = 0; c < 3; ++c) {
+        planes.push_back(new_plane(w, h));
+        chans.push_back({View{planes[c], 0, 0, w, h}, 0, 0});
+      }
+      std::vector<ModularStreamJob> jobs;
+      PendingStream ps = prepare_stream(br, hlimit, chans, stream_index, &jobs);
+      be_.decode_modular(jobs);
+      finish_stream(ps);
+      for (int c = 0; c < 3; ++c) {
+        out[c].resize(size_t(w) * h);
+        be_.download_rect(chans[c].view, out[c].data());
+        drop_plane(planes[c]);
+      }
+      br = BitReader(cs_, hlimit, jobs[ps.job_index].end_bit);
+    };
+    hfg_ = parse_hf_global(r, ih_, fh_, lfg_, raw_decoder);
     if (single) pos = r.pos();
   }
 
@@ -822,6 +843,13 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     const uint64_t seed0 = shown ? ((visible_before_ + 1) << 32) : (visible_before_ << 32) + invisible_before_ + 1;
     be_.add_noise(v, lfg_.noise_lut, fh_.group_dim(), seed0, corr_x, corr_b);
     be_.stage_marker("noise", v, 3);
+  }
+  if (fh_.do_ycbcr && !colour_done) {  // jxl-render/src/lib.rs:950-954, util.rs:320-329
+    JXLB_CHECK(colour.size() == 3, kErrBitstream, "YCbCr needs three channels");
+    View v[3] = {colour[0], colour[1], colour[2]};
+    be_.ycbcr_to_rgb(v, Backend::YcbcrParams());
+    be_.stage_marker("rgb", v, 3);
+    if (ih_.colour_encoding.colour_space == ColourSpace::kGrey) colour.resize(1);
   }
   finish_colour(colour, ih_.xyb_encoded, colour_done, &out);
   out.channels.insert(out.channels.end(), extra.begin(), extra.end());

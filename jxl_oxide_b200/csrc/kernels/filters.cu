@@ -197,6 +197,18 @@ __device__ __forceinline__ float linear_to_bt709(float a) {
   return __fmaf_rn(fdiv(num, den), 1.099f, -0.099f);
 }
 
+__global__ void ycbcr_to_rgb_kernel(DevView vcb, DevView vy, DevView vcr, DevYcbcrParams p) {
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= vy.w) return;
+  float* pcb = static_cast<float*>(vcb.ptr) + size_t(y) * vcb.stride + x;
+  float* py = static_cast<float*>(vy.ptr) + size_t(y) * vy.stride + x;
+  float* pcr = static_cast<float*>(vcr.ptr) + size_t(y) * vcr.stride + x;
+  const float cb = *pcb, yy = fadd(*py, p.y_offset), cr = *pcr;
+  *pcb = __fmaf_rn(cr, p.cr_to_r, yy);
+  *py = __fmaf_rn(cb, p.cb_to_g, __fmaf_rn(cr, p.cr_to_g, yy));
+  *pcr = __fmaf_rn(cb, p.cb_to_b, yy);
+}
+
 __global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorParams p) {
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= vx.w) return;
@@ -552,6 +564,12 @@ void launch_epf_step(const DevView in[3], const DevView out[3], const float* sig
   if (step == 0) epf_kernel<0><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
   else if (step == 1) epf_kernel<1><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
   else epf_kernel<2><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
+}
+
+void launch_ycbcr_to_rgb(DevView cb, DevView y, DevView cr, DevYcbcrParams p, cudaStream_t stream) {
+  if (!y.w || !y.h) return;
+  dim3 grid((y.w + 127) / 128, y.h);
+  ycbcr_to_rgb_kernel<<<grid, 128, 0, stream>>>(cb, y, cr, p);
 }
 
 void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream) {

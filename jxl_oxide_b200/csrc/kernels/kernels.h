@@ -150,6 +150,11 @@ struct DevColorParams {
   int apply_bt709_tf;
 };
 void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream);
+// YCbCr -> RGB in place, planes Cb, Y, Cr (jxl-color/src/ycbcr.rs:40-56)
+struct DevYcbcrParams {
+  float y_offset, cr_to_r, cb_to_g, cr_to_g, cb_to_b;
+};
+void launch_ycbcr_to_rgb(DevView cb, DevView y, DevView cr, DevYcbcrParams p, cudaStream_t stream);
 void launch_copy_rect(DevView src, DevView dst, cudaStream_t stream);
 // One k-times upsampling pass (k = 2, 4, 8); `quarter`: (k/2)^2 kernels of 25 weights (device).
 void launch_upsample(DevView in, DevView out, int k, const float* quarter, cudaStream_t stream);

@@ -64,6 +64,7 @@ class OracleBackend : public Backend {
   void splat_splines(const View v[3], const std::vector<SplineArc>& arcs) override;
   void add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x, float corr_b) override;
   void xyb_to_rgb(const View v[3], const ColorParams& p) override;
+  void ycbcr_to_rgb(const View v[3], const YcbcrParams& p) override;
   void stage_marker(const char* name, const View* views, int n) override;
 
   Plane& plane(int id) { return planes_.at(id); }

@@ -551,6 +551,21 @@ void OracleBackend::add_noise(const View v[3], const float lut8[8], uint32_t gro
 
 // ---------------------------------------------------------------------------------------------
 // XYB -> linear sRGB (-> sRGB), jxl-color/src/{xyb.rs:35-60, ciexyz.rs:81-87, tf/srgb.rs:13-48}
+// jxl-color/src/ycbcr.rs:40-56 (mul_add = fused)
+void OracleBackend::ycbcr_to_rgb(const View v[3], const YcbcrParams& p) {
+  Plane* pl[3] = {&plane(v[0].plane), &plane(v[1].plane), &plane(v[2].plane)};
+  parallel_for(v[0].h, [&](size_t y) {
+    float* r[3];
+    for (int c = 0; c < 3; ++c) r[c] = pl[c]->f32() + (v[c].y0 + y) * size_t(pl[c]->w) + v[c].x0;
+    for (uint32_t x = 0; x < v[0].w; ++x) {
+      const float cb = r[0][x], yy = r[1][x] + p.y_offset, cr = r[2][x];
+      r[0][x] = std::fmaf(cr, p.cr_to_r, yy);
+      r[1][x] = std::fmaf(cb, p.cb_to_g, std::fmaf(cr, p.cr_to_g, yy));
+      r[2][x] = std::fmaf(cb, p.cb_to_b, yy);
+    }
+  });
+}
+
 void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   static const uint8_t kPowUpper[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c, 0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
   static const uint8_t kPowLower[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68, 0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};

@@ -32,6 +32,8 @@ CASES = {
     "blendmodes": ("conformance/testcases/blendmodes", ["input.jxl", "ref.png"]),
     "animation_icos4d": ("conformance/testcases/animation_icos4d", ["input.jxl"]),
     "animation_spline": ("conformance/testcases/animation_spline", ["input.jxl"]),
+    "bench_oriented_brg": ("conformance/testcases/bench_oriented_brg", ["input.jxl", "ref.png"]),
+    "grayscale_jpeg": ("conformance/testcases/grayscale_jpeg", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 

@@ -123,6 +123,22 @@ def test_animation_frames_icos4d(oracle):
         assert np.abs(got - ref).max() <= 0.004, k
 
 
+def test_jpeg_transcode_ycbcr_444(oracle):
+    """JPEG-transcoded frame: raw (Modular-coded) dequant tables (dequant.rs:367-381, 537-559), YCbCr -> RGB
+    (jxl-color/src/ycbcr.rs) and orientation 5, against libjxl's rendering."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("bench_oriented_brg", "input.jxl"), threads=4)
+    assert img.orientation == 5
+    buf = img.frame_to_buffer(0, np.float32, 0)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("bench_oriented_brg", "ref.png")))).astype(np.float32) / 255.0
+    assert buf.shape == ref.shape == (500, 606, 3)
+    assert np.abs(np.clip(buf, 0.0, 1.0) - ref).max() <= 0.004
+    gray = oracle.OracleImage(fixture_bytes("grayscale_jpeg", "input.jxl"), threads=4)
+    planes, ncol, _ = gray.frame(0)
+    assert planes.shape == (1, 200, 200) and ncol == 1
+
+
 def test_animation_splines(oracle):
     """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
     points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
