@@ -337,6 +337,7 @@ const char* dev_status_message(int s) {
     case kDevBadStream: return "invalid entropy-coded stream (ANS final state / LZ77)";
     case kDevOverrun: return "entropy-coded stream reads past the end of its section";
     case kDevInvalid: return "semantic validation of a decoded stream failed";
+    case kDevUnsupported: return "chroma subsampling with varblocks larger than 8x8 is not supported";
     default: return "unknown device decode error";
   }
 }
@@ -762,6 +763,9 @@ DevFrame CudaBackend::dev_frame(const VarDctState& st) const {
   f.blk_type = static_cast<int32_t*>(plane_ptr(st.blk_type));
   f.blk_mul = static_cast<int32_t*>(plane_ptr(st.blk_mul));
   f.epf_sigma = static_cast<float*>(plane_ptr(st.epf_sigma));
+  f.group_blocks = st.group_dim / 8;
+  for (int c = 0; c < 3; ++c) f.hshift[c] = uint8_t(st.hshift[c]), f.vshift[c] = uint8_t(st.vshift[c]);
+  f.subsampled = st.subsampled ? 1 : 0;
   return f;
 }
 
@@ -864,7 +868,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   release_temps();
   for (size_t i = 0; i < jobs.size(); ++i) {
     if (status[i] != kDevOk)
-      fail(status[i] == kDevOverrun ? kErrEof : kErrDeviceDecode,
+      fail(status[i] == kDevOverrun ? kErrEof : (status[i] == kDevUnsupported ? kErrUnsupported : kErrDeviceDecode),
            std::string("HF group ") + std::to_string(jobs[i].group_idx) + ": " + dev_status_message(status[i]));
     jobs[i].end_bit = size_t(end[i]);
   }
@@ -1196,6 +1200,14 @@ int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader
   r.ptr = cur_owned;
   int id = next_id_++;
   planes_[id] = r;
+  return id;
+}
+
+int CudaBackend::upsample_jpeg(const View& v, bool horizontal, bool vertical, uint32_t out_w, uint32_t out_h) {
+  const int id = alloc_plane(out_w, out_h, false);
+  begin_k("upsample_jpeg");
+  launch_upsample_jpeg(dev_view(v), dev_view(View{id, 0, 0, out_w, out_h}), horizontal ? 1 : 0, vertical ? 1 : 0, stream_);
+  end_k();
   return id;
 }
 

@@ -65,6 +65,12 @@ struct VarDctState {
   // quantised LF, hence no LF-threshold contexts (hf_coeff.rs:110-127) and no LF dequant / CfL / smoothing
   // (jxl-render/src/vardct/mod.rs:175-201).
   bool use_lf_frame = false;
+  // JPEG chroma subsampling (ChannelShift::from_jpeg_upsampling, jxl-modular/src/param.rs:105-140): channel c (Cb, Y,
+  // Cr) keeps one sample per (1 << hshift[c]) x (1 << vshift[c]) luma samples. Every VarDCT plane keeps its full
+  // bw x bh allocation; a subsampled channel lives in the top-left part, block (bx, by) at (bx >> hshift, by >> vshift).
+  // bw / bh are rounded up to even in a subsampled direction (hf_metadata.rs:70-80, vardct/mod.rs:83-95).
+  uint32_t hshift[3] = {0, 0, 0}, vshift[3] = {0, 0, 0};
+  bool subsampled = false;
   int lf_quant[3] = {-1, -1, -1};  // i32, X/Y/B, bw x bh
   int x_from_y = -1, b_from_y = -1;  // i32, ceil(w/64) x ceil(h/64)
   int sharpness = -1;                // i32, bw x bh
@@ -74,6 +80,11 @@ struct VarDctState {
   int lf[3] = {-1, -1, -1};     // f32 dequantised LF, bw x bh
   int coeff[3] = {-1, -1, -1};  // i32 coefficients -> f32 samples in place, (bw*8) x (bh*8)
 };
+
+// The part of an LF-group rectangle channel c covers (shift_size of an even-sized rectangle).
+inline LfGroupRect shifted_rect(const LfGroupRect& r, uint32_t hshift, uint32_t vshift) {
+  return LfGroupRect{r.bx0 >> hshift, r.by0 >> vshift, (r.bw + (1u << hshift) - 1) >> hshift, (r.bh + (1u << vshift) - 1) >> vshift};
+}
 
 struct LfDequantJob {  // copy_lf_dequant (jxl-render/src/vardct/mod.rs:387-412)
   LfGroupRect rect;
@@ -129,6 +140,9 @@ class Backend {
   virtual void epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) = 0;
   // features/upsampling.rs: returns a new plane of (v.w << factor_log2) x (v.h << factor_log2) f32 samples
   virtual int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) = 0;
+  // Chroma upsampling of JPEG-transcoded frames (jxl-render/src/filter/ycbcr.rs:6-78): a 2x triangle filter
+  // (0.75 / 0.25, edges replicated) horizontally and/or vertically; returns a new out_w x out_h f32 plane.
+  virtual int upsample_jpeg(const View& v, bool horizontal, bool vertical, uint32_t out_w, uint32_t out_h) = 0;
   // Blending of equally sized f32 rectangles, in place on `dst` (jxl-render/src/blend.rs:550-727):
   //   op 1 Replace, 2 Add, 3 Mul (`clamp`: src clamped to [0, 1] first),
   //   op 4 Blend (alpha over), 5 MulAdd (dst + alpha * src), 6 MixAlpha (dst + src * (1 - dst)).

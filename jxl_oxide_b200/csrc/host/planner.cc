@@ -241,6 +241,7 @@ class FramePlanner {
   void finish_stream(PendingStream& ps);
   void run_inverse_transforms(const ModularStreamSyntax& s, std::vector<ChanBuf>& bufs);
   void setup_gmodular();
+  std::vector<LfGroupRect> lf_rect_;
   void render_vardct(DecodedFrame* out);
   bool colour_params(bool is_xyb, size_t num_colour, ColorParams* p);
   void finish_colour(std::vector<View>& colour, bool is_xyb, bool already_converted, DecodedFrame* out);
@@ -480,8 +481,24 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     JXLB_CHECK(vardct, kErrBitstream, "use_lf_frame on a Modular frame");
     JXLB_CHECK(fh_.lf_level < 4 && (*lf_store_)[fh_.lf_level].valid, kErrBitstream, "frame refers to an LF frame that was not decoded");
   }
-  const bool chroma_subsampled = fh_.jpeg_upsampling[0] || fh_.jpeg_upsampling[1] || fh_.jpeg_upsampling[2];
-  JXLB_CHECK(!chroma_subsampled, kErrUnsupported, "chroma-subsampled YCbCr frames are not implemented");
+  // JPEG chroma subsampling: per-channel shifts (ChannelShift::from_jpeg_upsampling, jxl-modular/src/param.rs:105-122)
+  bool h_subsampling = false, v_subsampling = false;
+  uint32_t chan_hshift[3] = {0, 0, 0}, chan_vshift[3] = {0, 0, 0};
+  for (uint32_t j : fh_.jpeg_upsampling) {
+    h_subsampling |= j == 1 || j == 2;
+    v_subsampling |= j == 1 || j == 3;
+  }
+  for (int c = 0; c < 3; ++c) {
+    const uint32_t j = fh_.jpeg_upsampling[c];
+    chan_hshift[c] = (j == 0 || j == 3) && h_subsampling;
+    chan_vshift[c] = (j == 0 || j == 2) && v_subsampling;
+  }
+  const bool chroma_subsampled = h_subsampling || v_subsampling;
+  JXLB_CHECK(!chroma_subsampled || vardct, kErrUnsupported, "chroma-subsampled Modular frames are not implemented");
+  JXLB_CHECK(!chroma_subsampled || fh_.skip_adaptive_lf_smoothing(), kErrUnsupported, "adaptive LF smoothing of a chroma-subsampled frame");
+  // block counts are rounded up to even in a subsampled direction (hf_metadata.rs:70-80, vardct/mod.rs:83-95)
+  auto blocks_w = [&](uint32_t px) { return h_subsampling ? ((px + 7) / 8 + 1) / 2 * 2 : (px + 7) / 8; };
+  auto blocks_h = [&](uint32_t px) { return v_subsampling ? ((px + 7) / 8 + 1) / 2 * 2 : (px + 7) / 8; };
   for (uint32_t u : fh_.ec_upsampling) JXLB_CHECK(u == fh_.upsampling, kErrUnsupported, "extra-channel upsampling differs from colour");
   for (const auto& ec : ih_.ec_info) JXLB_CHECK(ec.dim_shift == 0, kErrUnsupported, "dim_shift extra channels not supported");
 
@@ -524,8 +541,10 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     st_ = VarDctState();
     st_.width = cw;
     st_.height = chh;
-    st_.bw = (cw + 7) / 8;
-    st_.bh = (chh + 7) / 8;
+    st_.bw = blocks_w(cw);
+    st_.bh = blocks_h(chh);
+    st_.subsampled = chroma_subsampled;
+    for (int c = 0; c < 3; ++c) st_.hshift[c] = chan_hshift[c], st_.vshift[c] = chan_vshift[c];
     st_.group_dim = fh_.group_dim();
     st_.groups_per_row = fh_.groups_per_row();
     st_.num_groups = num_groups;
@@ -565,8 +584,9 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     uint32_t gx = g % fh_.lf_groups_per_row(), gy = g / fh_.lf_groups_per_row();
     uint32_t lfd = fh_.lf_group_dim();
     uint32_t lw = std::min(lfd, cw - gx * lfd), lh = std::min(lfd, chh - gy * lfd);
-    lf_rect[g] = {gx * (lfd / 8), gy * (lfd / 8), (lw + 7) / 8, (lh + 7) / 8};
+    lf_rect[g] = {gx * (lfd / 8), gy * (lfd / 8), blocks_w(lw), blocks_h(lh)};
   }
+  lf_rect_ = lf_rect;
   extra_precision_.assign(num_lf_groups, 0);
   if (vardct && !fh_.use_lf_frame()) {  // LfCoeff (jxl-vardct/src/lf.rs:138-181; absent with an LF frame)
     std::vector<ModularStreamJob> jobs;
@@ -576,8 +596,10 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
       extra_precision_[g] = r.read(2);
       const LfGroupRect& rc = lf_rect[g];
       std::vector<GroupChannel> chans;
-      for (int mc : {1, 0, 2})  // modular channel order is Y, X, B
-        chans.push_back({View{st_.lf_quant[mc], rc.bx0, rc.by0, rc.bw, rc.bh}, 0, 0});
+      for (int mc : {1, 0, 2}) {  // modular channel order is Y, X, B
+        const LfGroupRect sr = shifted_rect(rc, st_.hshift[mc], st_.vshift[mc]);
+        chans.push_back({View{st_.lf_quant[mc], sr.bx0, sr.by0, sr.bw, sr.bh}, int32_t(st_.hshift[mc]), int32_t(st_.vshift[mc])});
+      }
       pend.push_back(prepare_stream(r, lf_limit[g], chans, 1 + g, &jobs));
     }
     be_.decode_modular(jobs);
@@ -707,7 +729,17 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   size_t ec_from = 0;
   if (vardct) {
     render_vardct(&out);
-    for (int c = 0; c < 3; ++c) colour.push_back(View{st_.coeff[c], 0, 0, cw, chh});
+    for (int c = 0; c < 3; ++c) {
+      if (st_.hshift[c] || st_.vshift[c]) {  // upsample_jpeg (jxl-render/src/image.rs:448-486, filter/ycbcr.rs)
+        const View sub{st_.coeff[c], 0, 0, (cw + st_.hshift[c]) >> st_.hshift[c], (chh + st_.vshift[c]) >> st_.vshift[c]};
+        const int id = be_.upsample_jpeg(sub, st_.hshift[c] != 0, st_.vshift[c] != 0, cw, chh);
+        frame_planes_.push_back(id);
+        colour.push_back(View{id, 0, 0, cw, chh});
+      } else {
+        colour.push_back(View{st_.coeff[c], 0, 0, cw, chh});
+      }
+    }
+    if (st_.subsampled) be_.stage_marker("jpeg_upsampled", colour.data(), 3);
   } else {
     ec_from = fh_.encoded_color_channels;
     JXLB_CHECK(gm_image.size() >= ec_from, kErrBitstream, "missing modular colour channels");
@@ -960,10 +992,8 @@ void FramePlanner::render_vardct(DecodedFrame*) {
   std::vector<LfDequantJob> jobs;
   const uint32_t lfd = fh_.lf_group_dim();
   for (uint32_t g = 0; g < fh_.num_lf_groups(); ++g) {
-    uint32_t gx = g % fh_.lf_groups_per_row(), gy = g / fh_.lf_groups_per_row();
-    uint32_t lw = std::min(lfd, st_.width - gx * lfd), lh = std::min(lfd, st_.height - gy * lfd);
     LfDequantJob j;
-    j.rect = {gx * (lfd / 8), gy * (lfd / 8), (lw + 7) / 8, (lh + 7) / 8};
+    j.rect = lf_rect_[g];
     const float m[3] = {lfg_.m_x_lf, lfg_.m_y_lf, lfg_.m_b_lf};
     int32_t precision_scale = 1 << (9 - extra_precision_[g]);
     uint64_t scale_inv = uint64_t(lfg_.global_scale) * lfg_.quant_lf;
@@ -976,14 +1006,16 @@ void FramePlanner::render_vardct(DecodedFrame*) {
     for (int c = 0; c < 3; ++c) be_.copy_rect(lf.planes[c], View{st_.lf[c], 0, 0, st_.bw, st_.bh});
   } else {
     be_.lf_dequant(st_, jobs);
-    be_.lf_chroma_from_luma(st_);
+    if (!st_.subsampled) be_.lf_chroma_from_luma(st_);  // vardct/mod.rs:184-191
     if (!fh_.skip_adaptive_lf_smoothing()) be_.lf_adaptive_smoothing(st_);
   }
   {
-    View v[3] = {View{st_.lf[0], 0, 0, st_.bw, st_.bh}, View{st_.lf[1], 0, 0, st_.bw, st_.bh}, View{st_.lf[2], 0, 0, st_.bw, st_.bh}};
+    View v[3], cf[3];
+    for (int c = 0; c < 3; ++c) {
+      v[c] = View{st_.lf[c], 0, 0, st_.bw >> st_.hshift[c], st_.bh >> st_.vshift[c]};
+      cf[c] = View{st_.coeff[c], 0, 0, (st_.bw >> st_.hshift[c]) * 8, (st_.bh >> st_.vshift[c]) * 8};
+    }
     be_.stage_marker("lf", v, 3);
-    View cf[3];
-    for (int c = 0; c < 3; ++c) cf[c] = View{st_.coeff[c], 0, 0, st_.bw * 8, st_.bh * 8};
     be_.stage_marker("hf_coeff", cf, 3);
     be_.hf_dequant_cfl(st_);
     be_.stage_marker("hf_dequant", cf, 3);

@@ -12,6 +12,7 @@ enum DevStatus : int {
   kDevBadStream = 1,   // ANS final state mismatch / invalid symbol
   kDevOverrun = 2,     // read past the end of the section
   kDevInvalid = 3,     // semantic validation failed (e.g. non_zeros too large)
+  kDevUnsupported = 4, // valid syntax outside the implemented set
 };
 
 struct DevEntropyCode {

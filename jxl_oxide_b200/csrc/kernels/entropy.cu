@@ -61,6 +61,7 @@ __host__ __device__ inline HfSmem hf_layout(const DevHfParams& p) {
   return L;
 }
 
+template <bool SUB>  // SUB: the frame is chroma-subsampled (JPEG transcodes), channels sit at shifted block positions
 __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(const uint8_t* __restrict__ cs, DevFrame f,
                                                                              DevHfParams p,
                                                                              const DevHfJob* __restrict__ jobs,
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
           const int c = cs3[k];
           lf_idx *= p.num_lf_thr[c] + 1;
           if (p.num_lf_thr[c]) {
-            const int32_t q = f.lf_quant[c][gi];
+            const int32_t q = SUB ? f.lf_quant[c][size_t((by0 + y) >> f.vshift[c]) * f.bw + ((bx0 + x) >> f.hshift[c])] : f.lf_quant[c][gi];
             for (uint32_t i = 0; i < p.num_lf_thr[c]; ++i)
               if (q > thr_base[c][i]) ++lf_idx;
           }
@@ -168,13 +169,26 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
       for (int ci = 0; ci < 3 && err == kDevOk; ++ci) {
         const uint32_t ch_idx = uint32_t(ci) * 13 + order_id;
         const int c = (ci == 0) ? 1 : (ci == 1 ? 0 : 2);
+        uint32_t sx = x, sy = y, sbx0 = bx0, sby0 = by0;
+        if (SUB) {  // hf_coeff.rs:143-155: only blocks aligned to the channel's grid, at the shifted position
+          const uint32_t hs = f.hshift[c], vs = f.vshift[c];
+          sx = x >> hs, sy = y >> vs, sbx0 = bx0 >> hs, sby0 = by0 >> vs;
+          if (hs | vs) {
+            if ((sx << hs) != x || (sy << vs) != y) continue;
+            if (f.blk_type[size_t(by0 + sy) * f.bw + bx0 + sx] < 0) continue;
+            if (num_blocks != 1) {
+              err = kDevUnsupported;
+              break;
+            }
+          }
+        }
         const uint32_t idx = (ch_idx * hf_idx_mul + hf_idx) * lf_idx_mul + lf_idx;
         const uint32_t block_ctx = s_bctx[idx];
         uint32_t predicted;
-        const uint32_t nz_here = nz_row[c][x];
-        const uint32_t nz_left = x ? nz_row[c][x - 1] : 0;
-        if (y == 0) predicted = x == 0 ? 32 : nz_left;
-        else if (x == 0) predicted = nz_here;
+        const uint32_t nz_here = nz_row[c][sx];
+        const uint32_t nz_left = sx ? nz_row[c][sx - 1] : 0;
+        if (sy == 0) predicted = sx == 0 ? 32 : nz_left;
+        else if (sx == 0) predicted = nz_here;
         else predicted = (nz_here + nz_left + 1) >> 1;
         const uint32_t pidx = predicted >= 8 ? 4 + predicted / 2 : predicted;
         const uint32_t nz_ctx = block_ctx + pidx * nbc;
@@ -185,14 +199,14 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
           break;
         }
         const uint32_t nz_val = (non_zeros + num_blocks - 1) >> num_blocks_log;
-        for (uint32_t dx = 0; dx < w8; ++dx) nz_row[c][x + dx] = nz_val;
+        for (uint32_t dx = 0; dx < w8; ++dx) nz_row[c][sx + dx] = nz_val;
         if (non_zeros == 0) continue;
         uint32_t prev_nonzero = (non_zeros <= num_blocks * 4) ? 1 : 0;
         const uint32_t* order = p.orders + p.order_offset[order_id * 3 + c];
         const uint32_t size = num_blocks * 64;
         const uint8_t* cmap = cluster_map + block_ctx * 458 + 37 * nbc;
         uint32_t* plane = f.coeff[c];
-        const size_t base = (size_t(by0 + y) * 8) * f.cw + size_t(bx0 + x) * 8;
+        const size_t base = (size_t(sby0 + sy) * 8) * f.cw + size_t(sbx0 + sx) * 8;
         // context term of the remaining-non-zeros count; changes only after a non-zero coefficient
         uint32_t nzc_ctx = s_ctx[64 + ((non_zeros - 1) >> num_blocks_log)];
         for (uint32_t k = num_blocks, i = 0; k < size; ++k, ++i) {
@@ -239,12 +253,16 @@ void launch_decode_hf(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJ
   if (num_jobs <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(decode_hf_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(decode_hf_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(decode_hf_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   const HfSmem L = hf_layout(p);
   const int ctas = (num_jobs + kHfWarpsPerCta - 1) / kHfWarpsPerCta;
-  decode_hf_fast_kernel<<<ctas, kHfWarpsPerCta * 32, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+  if (f.subsampled)
+    decode_hf_fast_kernel<true><<<ctas, kHfWarpsPerCta * 32, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+  else
+    decode_hf_fast_kernel<false><<<ctas, kHfWarpsPerCta * 32, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
 }
 
 }  // namespace jxlb

@@ -197,6 +197,38 @@ __device__ __forceinline__ float linear_to_bt709(float a) {
   return __fmaf_rn(fdiv(num, den), 1.099f, -0.099f);
 }
 
+// apply_jpeg_upsampling_single (jxl-render/src/filter/ycbcr.rs:6-78): the horizontal pass, then the vertical pass over
+// its output, both computed per output sample (edges replicate).
+__device__ __forceinline__ float jpeg_hsample(const float* row, int x, int in_w, int horizontal) {
+  if (!horizontal) return row[x];
+  const int i = x >> 1;
+  const float cur = row[i];
+  if (x & 1) return fadd(fmul(0.75f, cur), fmul(0.25f, row[min(i + 1, in_w - 1)]));
+  return fadd(fmul(0.25f, row[max(i - 1, 0)]), fmul(0.75f, cur));
+}
+
+__global__ void upsample_jpeg_kernel(DevView in, DevView out, int horizontal, int vertical) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= int(out.w)) return;
+  const float* src = static_cast<const float*>(in.ptr);
+  const int in_w = int(in.w), in_h = int(in.h);
+  float v;
+  if (!vertical) {
+    v = jpeg_hsample(src + size_t(y) * in.stride, x, in_w, horizontal);
+  } else {
+    const int r = y >> 1;
+    const float cur = jpeg_hsample(src + size_t(r) * in.stride, x, in_w, horizontal);
+    if (y & 1) {
+      const float below = jpeg_hsample(src + size_t(min(r + 1, in_h - 1)) * in.stride, x, in_w, horizontal);
+      v = fadd(fmul(0.25f, below), fmul(0.75f, cur));
+    } else {
+      const float above = jpeg_hsample(src + size_t(max(r - 1, 0)) * in.stride, x, in_w, horizontal);
+      v = fadd(fmul(0.75f, cur), fmul(0.25f, above));
+    }
+  }
+  static_cast<float*>(out.ptr)[size_t(y) * out.stride + x] = v;
+}
+
 __global__ void ycbcr_to_rgb_kernel(DevView vcb, DevView vy, DevView vcr, DevYcbcrParams p) {
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= vy.w) return;
@@ -564,6 +596,12 @@ void launch_epf_step(const DevView in[3], const DevView out[3], const float* sig
   if (step == 0) epf_kernel<0><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
   else if (step == 1) epf_kernel<1><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
   else epf_kernel<2><<<grid, block, 0, stream>>>(vi, vo, sigma, sigma_stride, p);
+}
+
+void launch_upsample_jpeg(DevView in, DevView out, int horizontal, int vertical, cudaStream_t stream) {
+  if (!out.w || !out.h) return;
+  dim3 grid((out.w + 127) / 128, out.h);
+  upsample_jpeg_kernel<<<grid, 128, 0, stream>>>(in, out, horizontal, vertical);
 }
 
 void launch_ycbcr_to_rgb(DevView cb, DevView y, DevView cr, DevYcbcrParams p, cudaStream_t stream) {

@@ -87,6 +87,10 @@ struct DevFrame {  // frame-global grids (device pointers), all with stride == t
   float* epf_sigma;
   float* lf[3];
   uint32_t* coeff[3];
+  // JPEG chroma subsampling (VarDctState::hshift / vshift): channel c keeps block (bx, by) at (bx >> hshift[c],
+  // by >> vshift[c]) of its (full-size) planes
+  uint32_t group_blocks;  // group_dim / 8
+  uint8_t hshift[3], vshift[3], subsampled;
 };
 void launch_build_block_info(DevFrame f, const DevBlockInfoJob* jobs, int num_jobs, float quant_mul_base,
                              const float* sharp_lut8 /*device*/, int has_epf, int* status, void* scratch,
@@ -132,6 +136,8 @@ struct DevDequantParams {
   float base_correlation_x, base_correlation_b, colour_factor;
 };
 void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream);
+// chroma upsampling of JPEG-transcoded frames (jxl-render/src/filter/ycbcr.rs:6-78); `in` is the subsampled part
+void launch_upsample_jpeg(DevView in, DevView out, int horizontal, int vertical, cudaStream_t stream);
 // `scratch`: hf_transform_scratch_bytes() of device memory for the per-size-class work lists
 void launch_hf_transform(DevFrame f, void* scratch, cudaStream_t stream);
 size_t hf_transform_scratch_bytes(uint32_t bw, uint32_t bh);

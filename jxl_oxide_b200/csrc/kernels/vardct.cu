@@ -45,9 +45,73 @@ __global__ void lf_dequant_kernel(DevFrame f, const DevLfDequantJob* jobs) {
   const DevLfDequantJob j = jobs[blockIdx.z];
   uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= j.rect.bw || y >= j.rect.bh) return;
-  size_t i = size_t(j.rect.by0 + y) * f.bw + j.rect.bx0 + x;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) f.lf[c][i] = __fmul_rn(float(f.lf_quant[c][i]), j.scale[c]);
+  for (int c = 0; c < 3; ++c) {  // a subsampled channel covers the shifted part of the rectangle
+    const uint32_t hs = f.hshift[c], vs = f.vshift[c];
+    if (x >= ((j.rect.bw + hs) >> hs) || y >= ((j.rect.bh + vs) >> vs)) continue;
+    const size_t i = size_t((j.rect.by0 >> vs) + y) * f.bw + (j.rect.bx0 >> hs) + x;
+    f.lf[c][i] = __fmul_rn(float(f.lf_quant[c][i]), j.scale[c]);
+  }
+}
+
+// for_each_varblocks (vardct/mod.rs:693-730): where channel c keeps the varblock starting at (bx, by); false when a
+// subsampled channel skips it. The second look-up is group-local, like the reference's.
+__device__ __forceinline__ bool channel_block(const DevFrame& f, uint32_t c, uint32_t bx, uint32_t by, uint32_t& dbx, uint32_t& dby) {
+  dbx = bx;
+  dby = by;
+  if (!f.subsampled) return true;
+  const uint32_t hs = f.hshift[c], vs = f.vshift[c];
+  if (!(hs | vs)) return true;
+  const uint32_t gx0 = bx / f.group_blocks * f.group_blocks, gy0 = by / f.group_blocks * f.group_blocks;
+  const uint32_t lx = bx - gx0, ly = by - gy0;
+  if (((lx >> hs) << hs) != lx || ((ly >> vs) << vs) != ly) return false;
+  if (f.blk_type[size_t(gy0 + (ly >> vs)) * f.bw + gx0 + (lx >> hs)] < 0) return false;
+  dbx = (gx0 >> hs) + (lx >> hs);
+  dby = (gy0 >> vs) + (ly >> vs);
+  return true;
+}
+
+// dequant_hf_varblock_grouped for one channel of a chroma-subsampled frame (no chroma from luma, vardct/mod.rs:353):
+// one thread per coefficient of the channel's own (shifted) grid. Subsampled channels hold 8x8 varblocks only.
+__global__ void hf_dequant_channel_kernel(DevFrame f, DevDequantParams p, int c) {
+  const uint32_t hs = f.hshift[c], vs = f.vshift[c];
+  const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= (f.cw >> hs) || y >= (f.ch >> vs)) return;
+  const uint32_t sbx = x >> 3, sby = y >> 3;
+  uint32_t bx = sbx, by = sby, ix, iy;
+  int32_t t;
+  if (hs | vs) {
+    const uint32_t gbx = f.group_blocks >> hs, gby = f.group_blocks >> vs;
+    bx = sbx / gbx * f.group_blocks + ((sbx % gbx) << hs);
+    by = sby / gby * f.group_blocks + ((sby % gby) << vs);
+    if (bx >= f.bw || by >= f.bh) return;
+    t = f.blk_type[size_t(by) * f.bw + bx];
+    uint32_t dbx, dby;
+    if (t < 0 || !channel_block(f, c, bx, by, dbx, dby)) return;
+    if (kDevTransformInfo[t][0] * kDevTransformInfo[t][1] != 1) return;
+    ix = x & 7, iy = y & 7;
+  } else {
+    t = f.blk_type[size_t(by) * f.bw + bx];
+    if (t < 0) {
+      const uint32_t code = uint32_t(-t - 1);
+      bx -= code & 31;
+      by -= code >> 5;
+      t = f.blk_type[size_t(by) * f.bw + bx];
+    }
+    ix = x - bx * 8, iy = y - by * 8;
+  }
+  const uint32_t w = uint32_t(kDevTransformInfo[t][0]) * 8;
+  const uint32_t set = kDevTransformInfo[t][2], tr = kDevTransformInfo[t][4];
+  const float hf_mul = float(f.blk_mul[size_t(by) * f.bw + bx]);
+  const size_t i = size_t(y) * f.cw + x;
+  const float mul = __fmul_rn(__fdiv_rn(65536.0f, __fmul_rn(p.global_scale, hf_mul)), p.qm_scale[c]);
+  const float m = __ldg(p.matrices + p.matrix_offset[(set * 3 + c) * 2 + tr] + iy * w + ix);
+  float q = float(int32_t(f.coeff[c][i]));
+  if (fabsf(q) <= 1.0f) q = __fmul_rn(q, p.quant_bias[c]);
+  else q = __fsub_rn(q, __fdiv_rn(p.quant_bias_numerator, q));
+  q = __fmul_rn(q, m);
+  q = __fmul_rn(q, mul);
+  f.coeff[c][i] = __float_as_uint(q);
 }
 
 __global__ void lf_cfl_kernel(DevFrame f, float kx, float kb) {
@@ -728,8 +792,10 @@ __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f
   float* tile = s_tile[group];
   for (uint32_t work = blockIdx.x * kSmallGroups + group; work < total; work += gridDim.x * kSmallGroups) {
     const uint32_t item = items[work / 3], c = work % 3;
-    const uint32_t bx = item & 0xffff, by = item >> 16;
-    const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
+    const uint32_t sbx = item & 0xffff, sby = item >> 16;
+    const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
+    uint32_t bx, by;  // where channel c keeps this block
+    if (!channel_block(f, c, sbx, sby, bx, by)) continue;
     float* row = reinterpret_cast<float*>(f.coeff[c]) + (size_t(by) * 8 + r) * f.cw + size_t(bx) * 8;
     const float4 lo = *reinterpret_cast<const float4*>(row), hi = *reinterpret_cast<const float4*>(row + 4);
     float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -790,8 +856,10 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
   float* llf = s_llf[warp];
   for (uint32_t work = blockIdx.x * kMediumWarps + warp; work < total; work += gridDim.x * kMediumWarps) {
     const uint32_t item = items[work / 3], c = work % 3;
-    const uint32_t bx = item & 0xffff, by = item >> 16;
-    const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
+    const uint32_t sbx = item & 0xffff, sby = item >> 16;
+    const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
+    uint32_t bx, by;
+    if (!channel_block(f, c, sbx, sby, bx, by)) continue;
     const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
     const int w = bw * 8, h = bh * 8;
     float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
@@ -845,8 +913,10 @@ __global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, c
   const uint32_t total = *count_ptr * 3;
   for (uint32_t work = blockIdx.x; work < total; work += gridDim.x) {
     const uint32_t item = items[work / 3], c = work % 3;
-    const uint32_t bx = item & 0xffff, by = item >> 16;
-    const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
+    const uint32_t sbx = item & 0xffff, sby = item >> 16;
+    const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
+    uint32_t bx, by;
+    if (!channel_block(f, c, sbx, sby, bx, by)) continue;
     const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
     const int w = bw * 8, h = bh * 8;
     float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
@@ -886,6 +956,10 @@ void launch_lf_smooth(DevFrame f, float* tmp[3], float lf_x, float lf_y, float l
 void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream) {
   dim3 block(64, 4);
   dim3 grid((f.cw + 63) / 64, (f.ch + 3) / 4);
+  if (f.subsampled) {
+    for (int c = 0; c < 3; ++c) hf_dequant_channel_kernel<<<grid, block, 0, stream>>>(f, p, c);
+    return;
+  }
   hf_dequant_cfl_kernel<<<grid, block, 0, stream>>>(f, p);
 }
 

@@ -551,6 +551,43 @@ void OracleBackend::add_noise(const View v[3], const float lut8[8], uint32_t gro
 
 // ---------------------------------------------------------------------------------------------
 // XYB -> linear sRGB (-> sRGB), jxl-color/src/{xyb.rs:35-60, ciexyz.rs:81-87, tf/srgb.rs:13-48}
+// apply_jpeg_upsampling_single (jxl-render/src/filter/ycbcr.rs:6-78): horizontal pass into the output rows, then the
+// vertical pass over those rows (the reference runs it in place bottom-to-top; the values read are the horizontal
+// pass's, so a second buffer gives the same result).
+int OracleBackend::upsample_jpeg(const View& v, bool horizontal, bool vertical, uint32_t out_w, uint32_t out_h) {
+  Plane& src = plane(v.plane);
+  std::vector<float> tmp(size_t(out_w) * v.h);
+  for (uint32_t y = 0; y < v.h; ++y) {
+    const float* row = src.f32() + size_t(v.y0 + y) * src.w + v.x0;
+    float* o = tmp.data() + size_t(y) * out_w;
+    if (!horizontal) {
+      for (uint32_t x = 0; x < out_w; ++x) o[x] = row[x];
+      continue;
+    }
+    for (uint32_t i = 0; i < v.w; ++i) {
+      const float prev = row[i ? i - 1 : 0], cur = row[i], next = row[i + 1 < v.w ? i + 1 : v.w - 1];
+      if (2 * i < out_w) o[2 * i] = 0.25f * prev + 0.75f * cur;
+      if (2 * i + 1 < out_w) o[2 * i + 1] = 0.75f * cur + 0.25f * next;
+    }
+  }
+  const int id = alloc_plane(out_w, out_h, false);
+  Plane& dst = plane(id);
+  for (uint32_t y = 0; y < v.h; ++y) {
+    const float* cur = tmp.data() + size_t(y) * out_w;
+    if (!vertical) {
+      if (y < out_h) std::memcpy(dst.f32() + size_t(y) * dst.w, cur, size_t(out_w) * 4);
+      continue;
+    }
+    const float* above = tmp.data() + size_t(y ? y - 1 : 0) * out_w;
+    const float* below = tmp.data() + size_t(y + 1 < v.h ? y + 1 : v.h - 1) * out_w;
+    for (uint32_t x = 0; x < out_w; ++x) {
+      if (2 * y < out_h) dst.f32()[size_t(2 * y) * dst.w + x] = 0.75f * cur[x] + 0.25f * above[x];
+      if (2 * y + 1 < out_h) dst.f32()[size_t(2 * y + 1) * dst.w + x] = 0.25f * below[x] + 0.75f * cur[x];
+    }
+  }
+  return id;
+}
+
 // jxl-color/src/ycbcr.rs:40-56 (mul_add = fused)
 void OracleBackend::ycbcr_to_rgb(const View v[3], const YcbcrParams& p) {
   Plane* pl[3] = {&plane(v[0].plane), &plane(v[1].plane), &plane(v[2].plane)};

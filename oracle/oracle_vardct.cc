@@ -97,6 +97,8 @@ void OracleBackend::decode_one_hf(VarDctState& st, HfGroupJob& job) {
   Plane* coeff[3] = {&plane(st.coeff[0]), &plane(st.coeff[1]), &plane(st.coeff[2])};
   std::vector<uint32_t> nz_row[3];
   for (auto& v : nz_row) v.assign(width, 0);
+  const uint32_t* hs = st.hshift;
+  const uint32_t* vs = st.vshift;
 
   for (uint32_t y = 0; y < height; ++y)
     for (uint32_t x = 0; x < width; ++x) {
@@ -113,7 +115,7 @@ void OracleBackend::decode_one_hf(VarDctState& st, HfGroupJob& job) {
         for (int c : {0, 2, 1}) {
           const auto& thr = hbc.lf_thresholds[c];
           lf_idx *= thr.size() + 1;
-          int32_t q = lfq[c]->i32()[gi];
+          int32_t q = lfq[c]->i32()[size_t((by0 + y) >> vs[c]) * type.w + ((bx0 + x) >> hs[c])];
           for (int32_t th : thr)
             if (q > th) ++lf_idx;
         }
@@ -124,19 +126,26 @@ void OracleBackend::decode_one_hf(VarDctState& st, HfGroupJob& job) {
       for (int ci = 0; ci < 3; ++ci) {
         size_t ch_idx = size_t(ci) * 13 + order_id;
         int c = (ci == 0) ? 1 : (ci == 1 ? 0 : 2);  // y, x, b
+        // a subsampled channel codes only the blocks aligned to its grid, at the shifted position (hf_coeff.rs:143-155)
+        const uint32_t sx = x >> hs[c], sy = y >> vs[c];
+        if (hs[c] || vs[c]) {
+          if ((sx << hs[c]) != x || (sy << vs[c]) != y) continue;
+          if (type.i32()[size_t(by0 + sy) * type.w + bx0 + sx] < 0) continue;
+          JXLB_CHECK(num_blocks == 1, kErrUnsupported, "chroma subsampling with varblocks larger than 8x8 is not supported");
+        }
         size_t idx = (ch_idx * hf_idx_mul + hf_idx) * lf_idx_mul + lf_idx;
         JXLB_CHECK(idx < hbc.block_ctx_map.size(), kErrBitstream, "block context out of range");
         uint32_t block_ctx = hbc.block_ctx_map[idx];
         uint32_t predicted;
-        if (y == 0) predicted = x == 0 ? 32 : nz_row[c][x - 1];
-        else if (x == 0) predicted = nz_row[c][x];
-        else predicted = (nz_row[c][x] + nz_row[c][x - 1] + 1) >> 1;
+        if (sy == 0) predicted = sx == 0 ? 32 : nz_row[c][sx - 1];
+        else if (sx == 0) predicted = nz_row[c][sx];
+        else predicted = (nz_row[c][sx] + nz_row[c][sx - 1] + 1) >> 1;
         uint32_t pidx = predicted >= 8 ? 4 + predicted / 2 : predicted;
         uint32_t nz_ctx = block_ctx + pidx * nbc;
         uint32_t non_zeros = dec.read_varint_clustered(br, cluster_map[nz_ctx], 0);
         JXLB_CHECK(non_zeros <= (63u << num_blocks_log), kErrBitstream, "non_zeros too large");
         uint32_t nz_val = (non_zeros + num_blocks - 1) >> num_blocks_log;
-        for (uint32_t dx = 0; dx < w8; ++dx) nz_row[c][x + dx] = nz_val;
+        for (uint32_t dx = 0; dx < w8; ++dx) nz_row[c][sx + dx] = nz_val;
         if (non_zeros == 0) continue;
         uint32_t prev_nonzero = (non_zeros <= num_blocks * 4) ? 1 : 0;
         const std::vector<uint32_t>& custom = pass.order[order_id][c];
@@ -157,7 +166,7 @@ void OracleBackend::decode_one_hf(VarDctState& st, HfGroupJob& job) {
           int32_t cv = int32_t(uint32_t(unpack_signed(ucoeff)) << coeff_shift);
           uint32_t dx = order[k] & 0xffff, dy = order[k] >> 16;
           if (ti.transpose) std::swap(dx, dy);
-          size_t px = size_t(bx0 + x) * 8 + dx, py = size_t(by0 + y) * 8 + dy;
+          size_t px = size_t((bx0 >> hs[c]) + sx) * 8 + dx, py = size_t((by0 >> vs[c]) + sy) * 8 + dy;
           int32_t& dst = cp.i32()[py * cp.w + px];
           dst = int32_t(uint32_t(dst) + uint32_t(cv));
           prev_nonzero = 1;
@@ -178,9 +187,10 @@ void OracleBackend::lf_dequant(VarDctState& st, const std::vector<LfDequantJob>&
     for (int c = 0; c < 3; ++c) {
       Plane& q = plane(st.lf_quant[c]);
       Plane& o = plane(st.lf[c]);
-      for (uint32_t y = 0; y < j.rect.bh; ++y)
-        for (uint32_t x = 0; x < j.rect.bw; ++x) {
-          size_t i = size_t(j.rect.by0 + y) * q.w + j.rect.bx0 + x;
+      const LfGroupRect rc = shifted_rect(j.rect, st.hshift[c], st.vshift[c]);
+      for (uint32_t y = 0; y < rc.bh; ++y)
+        for (uint32_t x = 0; x < rc.bw; ++x) {
+          size_t i = size_t(rc.by0 + y) * q.w + rc.bx0 + x;
           o.f32()[i] = float(q.i32()[i]) * j.scale[c];
         }
     }
@@ -241,6 +251,23 @@ void OracleBackend::lf_adaptive_smoothing(VarDctState& st) {
 
 // ---------------------------------------------------------------------------------------------
 // dequant_hf_varblock_grouped + chroma_from_luma_hf_grouped (vardct/mod.rs:442-542, 570-603)
+namespace {
+// for_each_varblocks (vardct/mod.rs:693-730): where channel c keeps the varblock that starts at (bx, by), or false
+// when a subsampled channel skips it. The second look-up is group-local, like the reference's.
+bool shifted_block(const VarDctState& st, Plane& type, int c, uint32_t bx, uint32_t by, size_t* sbx, size_t* sby) {
+  const uint32_t hs = st.hshift[c], vs = st.vshift[c];
+  if (!hs && !vs) return true;
+  const uint32_t gb = st.group_dim / 8;
+  const uint32_t gx0 = bx / gb * gb, gy0 = by / gb * gb;
+  const uint32_t lx = bx - gx0, ly = by - gy0;
+  if (((lx >> hs) << hs) != lx || ((ly >> vs) << vs) != ly) return false;
+  if (type.i32()[size_t(gy0 + (ly >> vs)) * type.w + gx0 + (lx >> hs)] < 0) return false;
+  *sbx = (gx0 >> hs) + (lx >> hs);
+  *sby = (gy0 >> vs) + (ly >> vs);
+  return true;
+}
+}  // namespace
+
 void OracleBackend::hf_dequant_cfl(VarDctState& st) {
   const OpsinInverseMatrix& oim = st.ih->opsin_inverse_matrix;
   const LfGlobalSyntax& g = *st.lfg;
@@ -255,13 +282,15 @@ void OracleBackend::hf_dequant_cfl(VarDctState& st) {
         size_t gi = by * type.w + bx;
         int32_t t = type.i32()[gi];
         if (t < 0) continue;
+        size_t sbx = bx, sby = by;
+        if (!shifted_block(st, type, c, bx, uint32_t(by), &sbx, &sby)) continue;
         const TransformTypeInfo& ti = kTransformInfo[t];
         uint32_t w = ti.w8 * 8u, h = ti.h8 * 8u;
         float mul = 65536.0f / (float(g.global_scale) * float(mulp.i32()[gi])) * qm_scale[c];
         const std::vector<float>& m = ti.transpose ? st.hfg->dequant->matrices_tr[ti.param_index][c]
                                                    : st.hfg->dequant->matrices[ti.param_index][c];
         for (uint32_t y = 0; y < h; ++y) {
-          uint32_t* row = cp.data.data() + (size_t(by) * 8 + y) * cp.w + size_t(bx) * 8;
+          uint32_t* row = cp.data.data() + (sby * 8 + y) * cp.w + sbx * 8;
           for (uint32_t x = 0; x < w; ++x) {
             float q = float(int32_t(row[x]));
             if (std::fabs(q) <= 1.0f) q *= quant_bias;
@@ -274,6 +303,7 @@ void OracleBackend::hf_dequant_cfl(VarDctState& st) {
       }
     });
   }
+  if (st.subsampled) return;  // no chroma from luma between planes of different sizes (vardct/mod.rs:353)
   // chroma from luma on coefficients, per 64x64 tile
   Plane& xfy = plane(st.x_from_y);
   Plane& bfy = plane(st.b_from_y);
@@ -607,20 +637,22 @@ void OracleBackend::hf_transform(VarDctState& st) {
       for (uint32_t bx = 0; bx < st.bw; ++bx) {
         int32_t t = type.i32()[by * type.w + bx];
         if (t < 0) continue;
+        size_t sbx = bx, sby = by;
+        if (!shifted_block(st, type, c, bx, uint32_t(by), &sbx, &sby)) continue;
         const TransformTypeInfo& ti = kTransformInfo[t];
         const size_t bw = ti.w8, bh = ti.h8;
-        Grid llf{cp.f32() + (by * 8) * cp.w + size_t(bx) * 8, cp.w, bw, bh};
+        Grid llf{cp.f32() + (sby * 8) * cp.w + sbx * 8, cp.w, bw, bh};
         if (bw * bh == 1) {
-          llf.at(0, 0) = lf.f32()[by * lf.w + bx];
+          llf.at(0, 0) = lf.f32()[sby * lf.w + sbx];
         } else {
           for (size_t y = 0; y < bh; ++y)
-            for (size_t x = 0; x < bw; ++x) llf.at(x, y) = lf.f32()[(by + y) * lf.w + bx + x];
+            for (size_t x = 0; x < bw; ++x) llf.at(x, y) = lf.f32()[(sby + y) * lf.w + sbx + x];
           dct_2d(llf, true);
           size_t logbw = ceil_log2_nonzero(uint32_t(bw)), logbh = ceil_log2_nonzero(uint32_t(bh));
           for (size_t y = 0; y < bh; ++y)
             for (size_t x = 0; x < bw; ++x) llf.at(x, y) /= kScaleF[y << (5 - logbh)] * kScaleF[x << (5 - logbw)];
         }
-        Grid block{cp.f32() + (by * 8) * cp.w + size_t(bx) * 8, cp.w, bw * 8, bh * 8};
+        Grid block{cp.f32() + (sby * 8) * cp.w + sbx * 8, cp.w, bw * 8, bh * 8};
         switch (t) {
           case kDct2: transform_dct2(block); break;
           case kDct4: transform_dct4(block); break;

@@ -34,6 +34,7 @@ CASES = {
     "animation_spline": ("conformance/testcases/animation_spline", ["input.jxl"]),
     "bench_oriented_brg": ("conformance/testcases/bench_oriented_brg", ["input.jxl", "ref.png"]),
     "grayscale_jpeg": ("conformance/testcases/grayscale_jpeg", ["input.jxl"]),
+    "cafe": ("conformance/testcases/cafe", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 
@@ -53,6 +54,11 @@ Image.open(os.path.join(REF, "conformance/testcases/sunset_logo/ref.png")).crop(
     os.path.join(HERE, "sunset_logo", "ref_crop_200_400.png"), optimize=True)
 Image.open(os.path.join(REF, "conformance/testcases/grayscale_public_university/ref.png")).crop((1000, 500, 1512, 1012)).save(
     os.path.join(HERE, "grayscale_public_university", "ref_crop_1000_500.png"), optimize=True)
+# cafe (4:2:0 JPEG transcode): a 512 x 512 crop at (600, 800) and the 256 x 256 bottom-right corner
+Image.open(os.path.join(REF, "conformance/testcases/cafe/ref.png")).crop((600, 800, 1112, 1312)).save(
+    os.path.join(HERE, "cafe", "ref_crop_600_800.png"), optimize=True)
+Image.open(os.path.join(REF, "conformance/testcases/cafe/ref.png")).crop((1024, 1344, 1280, 1600)).save(
+    os.path.join(HERE, "cafe", "ref_crop_corner.png"), optimize=True)
 # three frames of the animation's reference APNG
 _ap = Image.open(os.path.join(REF, "conformance/testcases/animation_icos4d/ref.apng"))
 for _k in (0, 17, 47):

@@ -139,6 +139,22 @@ def test_jpeg_transcode_ycbcr_444(oracle):
     assert planes.shape == (1, 200, 200) and ncol == 1
 
 
+def test_jpeg_transcode_ycbcr_420(oracle):
+    """4:2:0 JPEG transcode: per-channel block grids (ChannelShift::from_jpeg_upsampling), shifted HF decode /
+    dequant / IDCT, the 0.75 / 0.25 chroma upsampling (filter/ycbcr.rs) and YCbCr -> RGB, against libjxl's rendering
+    (an interior crop and the bottom-right corner, where the edge replication shows)."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("cafe", "input.jxl"), threads=8)
+    planes, ncol, _ = img.frame(0)
+    assert planes.shape == (3, 1600, 1280)
+    got = np.moveaxis(np.clip(planes, 0.0, 1.0), 0, 2)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("cafe", "ref_crop_600_800.png")))).astype(np.float32) / 255.0
+    assert np.abs(got[800:1312, 600:1112] - ref).max() <= 0.004
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("cafe", "ref_crop_corner.png")))).astype(np.float32) / 255.0
+    assert np.abs(got[1344:1600, 1024:1280] - ref).max() <= 0.004
+
+
 def test_animation_splines(oracle):
     """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
     points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
