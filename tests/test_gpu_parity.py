@@ -134,10 +134,11 @@ def test_stage_entry_points_match_pipeline(dec, oracle):
 
 
 @pytest.mark.parametrize("size,seed,extra", [((1000, 600), 5, ()), ((1544, 1032), 6, ("--lf-gradient",)),
-                                             ((1000, 600), 7, ("--lf-frame",))])
+                                             ((1000, 600), 7, ("--lf-frame",)), ((1000, 600), 5, ("--passes", "3"))])
 def test_synthetic_vardct_frames_bit_exact(dec, oracle, size, seed, extra):
     """Frames from tools/synth_enc.cc (the bench workload generator): all 27 transform families,
-    WP- or gradient-coded LF, EPF 2 iterations."""
+    WP- or gradient-coded LF, EPF 2 iterations; an LF frame; HF coefficients split over three passes
+    (pass_group.rs:150-170: later passes add `value << shift` to the coefficients of earlier ones)."""
     import bench
     _check_vardct(dec, oracle, bench.synth_frame(size[0], size[1], seed, extra=extra))
 

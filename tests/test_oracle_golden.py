@@ -266,6 +266,17 @@ def test_synthetic_encoder_roundtrips_through_oracle(oracle):
     assert is_vardct and planes.shape == (3, 392, 520) and np.isfinite(planes).all()
 
 
+def test_progressive_passes_sum_to_the_single_pass_image(oracle):
+    """The same coefficients sent in one, two or three passes (shifts 0 / 1,0 / 2,1,0; hf_coeff.rs:246 `<< coeff_shift`,
+    per-pass histograms and non-zero contexts) decode to bit-identical pixels."""
+    import bench
+    one = oracle.OracleImage(bench.synth_frame(600, 500, 5), threads=4).frame(0)[0]
+    for passes in ("2", "3"):
+        data = bench.synth_frame(600, 500, 5, extra=("--passes", passes))
+        got = oracle.OracleImage(data, threads=4).frame(0)[0]
+        assert np.array_equal(got.view(np.uint32), one.view(np.uint32)), passes
+
+
 def _fuzz_files():
     import glob
     import os

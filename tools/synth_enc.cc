@@ -571,6 +571,7 @@ struct Args {
   double distance = 1.0;
   bool lf_wp = true;
   std::string out = "synth.jxl";
+  uint32_t passes = 1;    // HF coefficients split over this many passes (progressive; pass p carries shift passes-1-p)
   bool lf_frame = false;  // put the LF image into a separate Modular LF frame (frame type 1, lf_level 1)
 };
 
@@ -587,6 +588,7 @@ int main(int argc, char** argv) {
     else if (s == "--distance") a.distance = atof(next().c_str());
     else if (s == "--lf-gradient") a.lf_wp = false;
     else if (s == "--lf-frame") a.lf_frame = true;
+    else if (s == "--passes") a.passes = uint32_t(atoi(next().c_str()));
     else if (s == "-o") a.out = next();
     else fprintf(stderr, "unknown arg %s\n", s.c_str()), exit(2);
   }
@@ -596,6 +598,8 @@ int main(int argc, char** argv) {
   const uint32_t bw = (W + 7) / 8, bh = (H + 7) / 8;
   const uint32_t gcols = (W + 255) / 256, grows = (H + 255) / 256, num_groups = gcols * grows;
   const uint32_t lcols = (W + 2047) / 2048, lrows = (H + 2047) / 2048, num_lf = lcols * lrows;
+  if (a.passes < 1 || a.passes > 3 || (a.passes > 1 && a.lf_frame)) fprintf(stderr, "--passes takes 1..3 (not with --lf-frame)\n"), exit(2);
+  const uint32_t P = a.passes;
   if (num_groups == 1) fprintf(stderr, "single-group frames are not produced by this tool\n"), exit(2);
 
   // ---- content ----
@@ -697,15 +701,17 @@ int main(int argc, char** argv) {
   const double kScale = 1.0 / std::max(0.25, a.distance);  // coefficient magnitude scale
   std::vector<std::vector<uint32_t>> orders(13);
   for (uint32_t id = 0; id < 13; ++id) orders[id] = natural_order(id);
-  std::vector<std::vector<Token>> hf_tokens(num_groups);
+  // hf_tokens[pass * num_groups + group]; a coefficient c is sent as sum over passes of (part_p << shift_p), with
+  // part_p = remainder / 2^shift_p truncated toward zero
+  std::vector<std::vector<Token>> hf_tokens(size_t(P) * num_groups);
   std::exponential_distribution<double> expo(1.0);
   for (uint32_t g = 0; g < num_groups; ++g) {
     uint32_t bx0 = (g % gcols) * 32, by0 = (g / gcols) * 32;
     uint32_t gw = std::min(32u, bw - bx0), gh = std::min(32u, bh - by0);
-    std::vector<uint32_t> nz_row[3];
-    for (auto& v : nz_row) v.assign(gw, 0);
-    std::vector<Token>& toks = hf_tokens[g];
-    std::vector<int32_t> coeffs;
+    std::vector<uint32_t> nz_rows[3][3];
+    for (auto& pr : nz_rows)
+      for (auto& v : pr) v.assign(gw, 0);
+    std::vector<int32_t> coeffs, full;
     for (uint32_t y = 0; y < gh; ++y)
       for (uint32_t x = 0; x < gw; ++x) {
         int32_t t = blk_type[size_t(by0 + y) * bw + bx0 + x];
@@ -716,18 +722,25 @@ int main(int argc, char** argv) {
           int c = ci == 0 ? 1 : (ci == 1 ? 0 : 2);
           uint32_t block_ctx = kDefaultBlockCtxMap[ci * 13 + ti.order_id];
           // synthesise coefficients along the scan order: Laplacian with decaying scale
-          coeffs.assign(size, 0);
-          uint32_t non_zeros = 0;
+          full.assign(size, 0);
           double chan_scale = (c == 1 ? 1.0 : (c == 0 ? 0.35 : 0.55)) * kScale * uni(0.4, 1.6);
           for (uint32_t k = num_blocks; k < size; ++k) {
             double pos = double(k) / num_blocks;  // 1..64
             double b = chan_scale * 2.6 / (1.0 + pos * 0.55);
             double mag = expo(rng) * b;
             int32_t q = int32_t(mag + 0.35);
-            if (q) {
-              coeffs[k] = (rng() & 1) ? q : -q;
-              ++non_zeros;
-            }
+            if (q) full[k] = (rng() & 1) ? q : -q;
+          }
+          for (uint32_t pass = 0; pass < P; ++pass) {
+          const uint32_t shift = P - 1 - pass;
+          std::vector<Token>& toks = hf_tokens[size_t(pass) * num_groups + g];
+          std::vector<uint32_t>* nz_row = nz_rows[pass];
+          coeffs.assign(size, 0);
+          uint32_t non_zeros = 0;
+          for (uint32_t k = num_blocks; k < size; ++k) {
+            coeffs[k] = full[k] / (int32_t(1) << shift);
+            full[k] -= coeffs[k] * (int32_t(1) << shift);
+            if (coeffs[k]) ++non_zeros;
           }
           uint32_t predicted;
           if (y == 0) predicted = x == 0 ? 32 : nz_row[c][x - 1];
@@ -753,6 +766,7 @@ int main(int argc, char** argv) {
             prev = 1;
             if (--remaining == 0) break;
           }
+          }
         }
       }
   }
@@ -771,13 +785,18 @@ int main(int argc, char** argv) {
       hf_map[ctx] = uint8_t(4 + chan * 12 + bucket * 2 + prev);
     }
   }
-  std::vector<Token> hf_all;
-  for (auto& t : hf_tokens) hf_all.insert(hf_all.end(), t.begin(), t.end());
+  std::vector<std::vector<Token>> hf_all(P);
+  for (uint32_t pass = 0; pass < P; ++pass)
+    for (uint32_t g = 0; g < num_groups; ++g) {
+      const auto& t = hf_tokens[size_t(pass) * num_groups + g];
+      hf_all[pass].insert(hf_all[pass].end(), t.begin(), t.end());
+    }
 
   // ---- sections ----
   const uint32_t global_scale = uint32_t(std::lround(5111.0 / std::max(0.1, a.distance))), quant_lf = 17;
-  std::vector<BitWriter> sections(1 + num_lf + 1 + num_groups);
-  EntropyEncoder lf_enc, hf_enc;
+  std::vector<BitWriter> sections(1 + num_lf + 1 + size_t(P) * num_groups);
+  EntropyEncoder lf_enc;
+  std::vector<EntropyEncoder> hf_enc(P);
   {  // LfGlobal
     BitWriter& w = sections[0];
     w.write(1, 1);  // LfChannelDequantization all_default
@@ -814,15 +833,18 @@ int main(int argc, char** argv) {
     BitWriter& w = sections[1 + num_lf];
     w.write(1, 1);                                   // default dequant matrices
     w.write(int(ceil_log2_nonzero(num_groups)), 0);  // num_hf_presets - 1
-    write_u32(w, 2, 0, 0);                           // used_orders = 0
-    hf_enc.write_header(w, hf_all, 495 * nbc, hf_map);
+    for (uint32_t pass = 0; pass < P; ++pass) {
+      write_u32(w, 2, 0, 0);  // used_orders = 0
+      hf_enc[pass].write_header(w, hf_all[pass], 495 * nbc, hf_map);
+    }
     w.pad();
   }
-  for (uint32_t g = 0; g < num_groups; ++g) {
-    BitWriter& w = sections[2 + num_lf + g];
-    hf_enc.write_tokens(w, hf_tokens[g]);  // hfp takes 0 bits with a single preset
-    w.pad();
-  }
+  for (uint32_t pass = 0; pass < P; ++pass)
+    for (uint32_t g = 0; g < num_groups; ++g) {
+      BitWriter& w = sections[2 + num_lf + size_t(pass) * num_groups + g];
+      hf_enc[pass].write_tokens(w, hf_tokens[size_t(pass) * num_groups + g]);  // hfp takes 0 bits with a single preset
+      w.pad();
+    }
 
   // ---- codestream ----
   BitWriter cs;
@@ -906,6 +928,23 @@ int main(int argc, char** argv) {
     cs.write(3, 3);         // x_qm_scale
     cs.write(3, 2);         // b_qm_scale
     cs.write(2, 0);         // num_passes = 1
+    cs.write(1, 0);         // have_crop
+    cs.write(2, 0);         // blend mode Replace
+    cs.write(1, 1);         // is_last
+    cs.write(2, 0);         // name: empty
+    cs.write(1, 1);         // restoration filter all_default
+    write_u64_small(0);     // frame extensions
+  } else if (P > 1) {
+    cs.write(1, 0);         // all_default
+    cs.write(2, 0);         // Regular
+    cs.write(1, 0);         // VarDCT
+    write_u64_small(0);     // flags
+    cs.write(2, 0);         // upsampling = 1
+    cs.write(3, 3);         // x_qm_scale
+    cs.write(3, 2);         // b_qm_scale
+    cs.write(2, P - 1);     // num_passes (2 or 3)
+    cs.write(2, 0);         // num_ds = 0
+    for (uint32_t pass = 0; pass + 1 < P; ++pass) cs.write(2, P - 1 - pass);  // shift
     cs.write(1, 0);         // have_crop
     cs.write(2, 0);         // blend mode Replace
     cs.write(1, 1);         // is_last
