@@ -73,10 +73,13 @@ int32_t jxlb_frame_get_info(const jxlb_decoder* dec, int32_t frame, jxlb_frame_i
 /* Render::image_planar equivalent (crates/jxl-oxide/src/lib.rs:1178-1203): copy one channel to
  * host memory, `dst_stride` in floats (>= width). */
 int32_t jxlb_frame_channel_to_host(jxlb_decoder* dec, int32_t frame, int32_t channel, float* dst, size_t dst_stride);
-/* ImageStream::write_to_buffer::<u8 | u16 | f32> (crates/jxl-oxide/src/fb.rs:309-410): all channels of
- * the frame interleaved (channel fastest) with the image orientation applied. sample_type 0 = u8,
- * 1 = u16, 2 = f32; orientation 1..8 or 0 for the image header's. The conversion runs on the device and
- * `dst` (host) receives width*height*channels samples. */
+/* Number of interleaved channels ImageStream::from_render selects (crates/jxl-oxide/src/fb.rs:184-283): the colour
+ * channels plus the first alpha channel; -1 on a bad argument. */
+int32_t jxlb_frame_stream_channels(const jxlb_decoder* dec, int32_t frame);
+/* ImageStream::write_to_buffer::<u8 | u16 | f32> (crates/jxl-oxide/src/fb.rs:309-410): the stream's channels
+ * interleaved (channel fastest) with the image orientation applied and spot-colour channels mixed into RGB
+ * (fb.rs:335-362). sample_type 0 = u8, 1 = u16, 2 = f32; orientation 1..8 or 0 for the image header's. The
+ * conversion runs on the device and `dst` (host) receives width*height*jxlb_frame_stream_channels() samples. */
 int32_t jxlb_frame_write_to_buffer(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation, void* dst,
                                    size_t dst_bytes);
 /* Device-resident access: pointer to the channel's top-left sample and its row stride (floats). */

@@ -27,7 +27,7 @@ OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVI
 EXPORTED_SYMBOLS = [
     "jxlb_decoder_create", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
     "jxlb_image_get_info",
-    "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_write_to_buffer", "jxlb_frame_channel_device",
+    "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
     "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_stage_count", "jxlb_stage_get",
     "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse",
@@ -94,6 +94,8 @@ def load_library():
     L.jxlb_frame_get_info.argtypes = [vp, i32, ctypes.POINTER(_FrameInfo)]
     L.jxlb_frame_channel_to_host.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
     L.jxlb_frame_write_to_buffer.argtypes = [vp, i32, i32, i32, vp, ctypes.c_size_t]
+    L.jxlb_frame_stream_channels.argtypes = [vp, i32]
+    L.jxlb_frame_stream_channels.restype = i32
     L.jxlb_frame_channel_device.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
     L.jxlb_release_frames.argtypes = [vp]
     L.jxlb_sync.argtypes = [vp]
@@ -204,7 +206,7 @@ class Decoder:
         orient = orientation or img.orientation
         w, h = (info.height, info.width) if orient >= 5 else (info.width, info.height)
         st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
-        out = np.empty((h, w, info.num_channels), dtype=dtype)
+        out = np.empty((h, w, self._L.jxlb_frame_stream_channels(self._h, frame)), dtype=dtype)
         self._check(self._L.jxlb_frame_write_to_buffer(self._h, frame, st, orientation, out.ctypes.data, out.nbytes))
         return out
 

@@ -176,19 +176,32 @@ int32_t jxlb_frame_write_to_buffer(jxlb_decoder* dec, int32_t frame, int32_t sam
   return guarded(dec, [&] {
     const DecodedFrame& f = dec->res.frames[frame];
     JXLB_CHECK(sample_type >= 0 && sample_type <= 2, kErrInvalidArg, "sample_type must be 0 (u8), 1 (u16) or 2 (f32)");
-    JXLB_CHECK(!f.channels.empty() && f.channels.size() <= 8, kErrUnsupported, "1..8 channels can be interleaved");
+    JXLB_CHECK(!f.channels.empty(), kErrInvalidArg, "frame without channels");
+    const StreamLayout layout = stream_layout(dec->res.image_header, f);
+    JXLB_CHECK(layout.spots.size() <= 8, kErrUnsupported, "more than 8 spot colour channels");
     const uint32_t orient = orientation == 0 ? dec->res.image_header.orientation : uint32_t(orientation);
     JXLB_CHECK(orient >= 1 && orient <= 8, kErrInvalidArg, "orientation must be 1..8 (0 = the image's)");
     DevPackParams p;
     std::memset(&p, 0, sizeof(p));
-    p.num_channels = uint32_t(f.channels.size());
+    p.num_channels = uint32_t(layout.channels.size());
     p.width = f.channels[0].w;
     p.height = f.channels[0].h;
-    for (size_t c = 0; c < f.channels.size(); ++c) {
-      JXLB_CHECK(f.channels[c].w == p.width && f.channels[c].h == p.height, kErrUnsupported, "channels of different sizes");
-      DevView d = dec->be->dev_view(f.channels[c]);
+    for (size_t c = 0; c < layout.channels.size(); ++c) {
+      const View& v = f.channels[layout.channels[c]];
+      JXLB_CHECK(v.w == p.width && v.h == p.height, kErrUnsupported, "channels of different sizes");
+      DevView d = dec->be->dev_view(v);
       p.planes[c] = static_cast<const float*>(d.ptr);
       p.strides[c] = d.stride;
+    }
+    p.num_spots = uint32_t(layout.spots.size());
+    for (size_t s = 0; s < layout.spots.size(); ++s) {
+      const View& v = f.channels[layout.spots[s].channel];
+      JXLB_CHECK(v.w == p.width && v.h == p.height, kErrUnsupported, "channels of different sizes");
+      DevView d = dec->be->dev_view(v);
+      p.spot_planes[s] = static_cast<const float*>(d.ptr);
+      p.spot_strides[s] = d.stride;
+      for (int k = 0; k < 3; ++k) p.spot_rgb[s][k] = layout.spots[s].rgb[k];
+      p.spot_solidity[s] = layout.spots[s].solidity;
     }
     p.orientation = orient;
     p.sample_type = uint32_t(sample_type);
@@ -196,6 +209,11 @@ int32_t jxlb_frame_write_to_buffer(jxlb_decoder* dec, int32_t frame, int32_t sam
     JXLB_CHECK(dst_bytes >= bytes, kErrInvalidArg, "destination buffer too small");
     dec->be->pack_to_host(p, dst, bytes);
   });
+}
+
+int32_t jxlb_frame_stream_channels(const jxlb_decoder* dec, int32_t frame) {
+  if (!dec || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return -1;
+  return int32_t(stream_layout(dec->res.image_header, dec->res.frames[frame]).channels.size());
 }
 
 int32_t jxlb_frame_channel_device(jxlb_decoder* dec, int32_t frame, int32_t channel, float** dptr, uint32_t* stride) {

@@ -1063,6 +1063,23 @@ void FramePlanner::finish_colour(std::vector<View>& colour, bool is_xyb, bool al
 
 }  // namespace
 
+StreamLayout stream_layout(const ImageHeader& ih, const DecodedFrame& f) {
+  StreamLayout l;
+  for (size_t c = 0; c < f.num_color && c < f.channels.size(); ++c) l.channels.push_back(c);
+  for (size_t e = 0; e < ih.ec_info.size() && f.num_color + e < f.channels.size(); ++e)
+    if (ih.ec_info[e].type == ExtraChannelType::kAlpha) {
+      l.channels.push_back(f.num_color + e);
+      break;
+    }
+  if (f.num_color == 3 && !ih.grayscale())
+    for (size_t e = 0; e < ih.ec_info.size() && f.num_color + e < f.channels.size(); ++e)
+      if (ih.ec_info[e].type == ExtraChannelType::kSpotColour) {
+        const float* s = ih.ec_info[e].spot;
+        l.spots.push_back(StreamSpot{f.num_color + e, {s[0], s[1], s[2]}, s[3]});
+      }
+  return l;
+}
+
 DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, const DecodeOptions& opt) {
   DecodeResult res;
   be.set_codestream(cs, size);

@@ -27,6 +27,21 @@ struct DecodedFrame {
   FrameHeader header;
 };
 
+// What ImageStream::from_render puts into an interleaved buffer (jxl-oxide/src/fb.rs:184-283): the colour channels,
+// then the first alpha channel; spot-colour channels are mixed into a three-channel colour image while it is written
+// (fb.rs:335-362) unless the image is grayscale (lib.rs:416). The black channel of CMYK images would follow the
+// colour channels; CMYK is recognised through the ICC profile, which this library does not interpret.
+struct StreamSpot {
+  size_t channel;  // index into DecodedFrame::channels
+  float rgb[3];
+  float solidity;
+};
+struct StreamLayout {
+  std::vector<size_t> channels;  // indices into DecodedFrame::channels, in output order
+  std::vector<StreamSpot> spots;
+};
+StreamLayout stream_layout(const ImageHeader& ih, const DecodedFrame& f);
+
 struct DecodeResult {
   ImageHeader image_header;
   std::vector<DecodedFrame> frames;

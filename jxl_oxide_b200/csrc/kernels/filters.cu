@@ -323,7 +323,12 @@ __global__ void pack_interleaved_kernel(DevPackParams p, void* out) {
   }
   const size_t o = (size_t(y) * ow + x) * p.num_channels;
   for (uint32_t c = 0; c < p.num_channels; ++c) {
-    const float v = p.planes[c][size_t(sy) * p.strides[c] + sx];
+    float v = p.planes[c][size_t(sy) * p.strides[c] + sx];
+    if (c < 3)
+      for (uint32_t s = 0; s < p.num_spots; ++s) {
+        const float mix = fmul(p.spot_planes[s][size_t(sy) * p.spot_strides[s] + sx], p.spot_solidity[s]);
+        v = fadd(fmul(p.spot_rgb[s][c], mix), fmul(v, fsub(1.0f, mix)));
+      }
     if (p.sample_type == 2) {
       static_cast<float*>(out)[o + c] = v;
     } else {

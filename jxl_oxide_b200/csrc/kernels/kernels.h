@@ -173,6 +173,13 @@ struct DevPackParams {
   uint32_t width, height;  // of the stored (un-oriented) planes
   uint32_t orientation;    // 1..8
   uint32_t sample_type;    // 0: u8, 1: u16, 2: f32
+  // spot colours mixed into channels 0..2 in list order (fb.rs:335-362): v = rgb[c] * mix + v * (1 - mix),
+  // mix = spot sample * solidity
+  uint32_t num_spots;
+  const float* spot_planes[8];
+  uint32_t spot_strides[8];
+  float spot_rgb[8][3];
+  float spot_solidity[8];
 };
 void launch_pack_interleaved(DevPackParams p, void* out, cudaStream_t stream);
 // Rectangle blending (jxl-render/src/blend.rs:550-727), one CTA per job; modes 1 Replace, 2 Add, 3 Mul,

@@ -84,17 +84,27 @@ int jxlo_stage(void* hp, const char* name, int idx, uint32_t* w, uint32_t* hgt, 
 // ImageStream::write_to_buffer::<u8 | u16 | f32> (crates/jxl-oxide/src/fb.rs:309-410, 387-401, 436-520):
 // channel-interleaved samples with the orientation applied. sample_type 0 = u8, 1 = u16, 2 = f32;
 // orientation 0 = the image header's. Returns the number of samples written.
+uint32_t jxlo_frame_stream_channels(void* hp, int frame) {
+  Handle* h = static_cast<Handle*>(hp);
+  return uint32_t(jxlb::stream_layout(h->res.image_header, h->res.frames.at(frame)).channels.size());
+}
+
 size_t jxlo_frame_write_to_buffer(void* hp, int frame, int sample_type, int orientation, void* dst) {
   Handle* h = static_cast<Handle*>(hp);
   const jxlb::DecodedFrame& f = h->res.frames.at(frame);
   const uint32_t orient = orientation ? uint32_t(orientation) : h->res.image_header.orientation;
   const uint32_t width = f.channels.at(0).w, height = f.channels.at(0).h;
   const uint32_t ow = orient >= 5 ? height : width, oh = orient >= 5 ? width : height;
-  const size_t nc = f.channels.size();
-  std::vector<std::vector<float>> planes(nc);
+  const jxlb::StreamLayout layout = jxlb::stream_layout(h->res.image_header, f);
+  const size_t nc = layout.channels.size();
+  std::vector<std::vector<float>> planes(nc), spots(layout.spots.size());
   for (size_t c = 0; c < nc; ++c) {
     planes[c].resize(size_t(width) * height);
-    h->be->download_rect(f.channels[c], planes[c].data());
+    h->be->download_rect(f.channels[layout.channels[c]], planes[c].data());
+  }
+  for (size_t s = 0; s < spots.size(); ++s) {
+    spots[s].resize(size_t(width) * height);
+    h->be->download_rect(f.channels[layout.spots[s].channel], spots[s].data());
   }
   size_t count = 0;
   for (uint32_t y = 0; y < oh; ++y)
@@ -111,7 +121,12 @@ size_t jxlo_frame_write_to_buffer(void* hp, int frame, int sample_type, int orie
         default: sx = oh - y - 1, sy = x; break;
       }
       for (size_t c = 0; c < nc; ++c, ++count) {
-        const float v = planes[c][size_t(sy) * width + sx];
+        float v = planes[c][size_t(sy) * width + sx];
+        if (c < 3)  // spot colours (fb.rs:335-362)
+          for (size_t s = 0; s < spots.size(); ++s) {
+            const float mix = spots[s][size_t(sy) * width + sx] * layout.spots[s].solidity;
+            v = layout.spots[s].rgb[c] * mix + v * (1.0f - mix);
+          }
         if (sample_type == 2) {
           static_cast<float*>(dst)[count] = v;
         } else {

@@ -35,6 +35,7 @@ CASES = {
     "bench_oriented_brg": ("conformance/testcases/bench_oriented_brg", ["input.jxl", "ref.png"]),
     "grayscale_jpeg": ("conformance/testcases/grayscale_jpeg", ["input.jxl"]),
     "cafe": ("conformance/testcases/cafe", ["input.jxl"]),
+    "spot": ("conformance/testcases/spot", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 
@@ -59,6 +60,9 @@ Image.open(os.path.join(REF, "conformance/testcases/cafe/ref.png")).crop((600, 8
     os.path.join(HERE, "cafe", "ref_crop_600_800.png"), optimize=True)
 Image.open(os.path.join(REF, "conformance/testcases/cafe/ref.png")).crop((1024, 1344, 1280, 1600)).save(
     os.path.join(HERE, "cafe", "ref_crop_corner.png"), optimize=True)
+# spot colours: a 300 x 300 crop at (150, 50) of the 8-bit rendering
+Image.open(os.path.join(REF, "conformance/testcases/spot/ref.png")).crop((150, 50, 450, 350)).save(
+    os.path.join(HERE, "spot", "ref_crop_150_50.png"), optimize=True)
 # three frames of the animation's reference APNG
 _ap = Image.open(os.path.join(REF, "conformance/testcases/animation_icos4d/ref.apng"))
 for _k in (0, 17, 47):

@@ -31,6 +31,8 @@ def lib():
         L.jxlo_frame_channel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.jxlo_frame_write_to_buffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.jxlo_frame_write_to_buffer.restype = ctypes.c_size_t
+        L.jxlo_frame_stream_channels.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.jxlo_frame_stream_channels.restype = ctypes.c_uint32
         L.jxlo_stage.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32),
                                  ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
         L.jxlo_free.argtypes = [ctypes.c_void_p]
@@ -77,7 +79,7 @@ class OracleImage:
         if (orientation or self.orientation) >= 5:
             w, h = h, w
         st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
-        out = np.empty((h, w, nch), dtype=dtype)
+        out = np.empty((h, w, L.jxlo_frame_stream_channels(self._h, idx)), dtype=dtype)
         n = L.jxlo_frame_write_to_buffer(self._h, idx, st, orientation, out.ctypes.data)
         assert n == out.size
         return out

@@ -11,7 +11,7 @@ from conftest import fixture_bytes
 
 pytestmark = pytest.mark.gpu
 
-MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless", "sunset_logo", "blendmodes", "grayscale_public_university"]
+MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless", "sunset_logo", "blendmodes", "grayscale_public_university", "spot"]
 MODULAR_BENCH = ["srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise", "bike", "bench_oriented_brg", "grayscale_jpeg", "cafe"]
 VARDCT_BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl"]
@@ -192,6 +192,18 @@ def test_write_to_buffer_matches_reference_packing(dec, oracle, dtype, orientati
     want = img.frame_to_buffer(0, dtype, orientation)
     assert got.shape == want.shape and got.shape[2] == 4
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32])
+def test_write_to_buffer_mixes_spot_colours(dec, oracle, dtype):
+    """Spot-colour channels blended into RGB by the packing kernel, alpha appended (fb.rs:246-283, 335-362)."""
+    data = fixture_bytes("spot", "input.jxl")
+    dec.decode(data)
+    got = dec.frame_to_buffer(0, dtype, 6)
+    want = oracle.OracleImage(data, threads=4).frame_to_buffer(0, dtype, 6)
+    assert got.shape == want.shape == (600, 400, 4)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    dec.release_frames()
 
 
 def test_mutated_streams_end_in_values(dec):

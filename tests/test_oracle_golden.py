@@ -155,6 +155,19 @@ def test_jpeg_transcode_ycbcr_420(oracle):
     assert np.abs(got[1344:1600, 1024:1280] - ref).max() <= 0.004
 
 
+def test_spot_colours_in_the_image_stream(oracle):
+    """16-bit RGB + alpha + two spot-colour channels: ImageStream mixes the spots into RGB while writing
+    (fb.rs:246-283, 335-362) and appends the alpha channel; planar access leaves all six channels untouched."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("spot", "input.jxl"), threads=4)
+    assert img.frame(0)[0].shape == (6, 400, 600)
+    buf = np.clip(img.frame_to_buffer(0, np.float32, 0), 0.0, 1.0)
+    assert buf.shape == (400, 600, 4)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("spot", "ref_crop_150_50.png")))).astype(np.float32) / 255.0
+    assert np.abs(buf[50:350, 150:450] - ref).max() <= 0.004
+
+
 def test_animation_splines(oracle):
     """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
     points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
