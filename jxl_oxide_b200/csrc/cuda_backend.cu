@@ -714,21 +714,42 @@ void CudaBackend::rct_inverse(const View v[3], uint32_t rct_type) {
 }
 
 void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t,
-                                  const WpHeader&, uint32_t bit_depth) {
+                                  const WpHeader& wph, uint32_t bit_depth) {
   JXLB_CHECK(targets.size() <= 4, kErrUnsupported, "palettes with more than 4 channels are not implemented on the device");
   DevView tv[4];
   for (size_t i = 0; i < targets.size(); ++i) tv[i] = dev_view(targets[i]);
+  const uint32_t w = targets[0].w, h = targets[0].h;
   int* d_status = static_cast<int*>(dmalloc(4));
+  uint8_t* d_mask = static_cast<uint8_t*>(dmalloc(size_t(w) * h));
   CUDA_CHECK(cudaMemsetAsync(d_status, 0, 4, stream_));
-  begin_k("palette_inverse_simple");
-  launch_palette_inverse_simple(dev_view(palette), tv, int(targets.size()), int(t.nb_colours), int(bit_depth),
-                                int(t.nb_deltas), d_status, stream_);
+  DevView pal{};
+  if (palette.plane >= 0) pal = dev_view(palette);  // absent when nb_colours == 0
+  begin_k("palette_inverse");
+  launch_palette_inverse(pal, tv, int(targets.size()), int(t.nb_colours), int(bit_depth), int(t.nb_deltas), d_mask, d_status, stream_);
   end_k();
-  int status = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&status, d_status, 4, cudaMemcpyDeviceToHost, stream_));
+  int num_delta = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&num_delta, d_status, 4, cudaMemcpyDeviceToHost, stream_));
   sync();
+  if (num_delta > 0) {  // palette.rs:114-152
+    JXLB_CHECK(t.d_pred <= 13, kErrBitstream, "invalid delta-palette predictor");
+    DevPaletteDeltaParams p;
+    std::memset(&p, 0, sizeof(p));
+    for (size_t i = 0; i < targets.size(); ++i) p.target[i] = tv[i];
+    p.mask = d_mask;
+    p.d_pred = t.d_pred;
+    const uint32_t hdr[11] = {wph.p1, wph.p2, wph.p3a, wph.p3b, wph.p3c, wph.p3d, wph.p3e, wph.w[0], wph.w[1], wph.w[2], wph.w[3]};
+    for (int i = 0; i < 11; ++i) p.wp[i] = hdr[i];
+    int32_t* rows = nullptr;
+    if (t.d_pred == 6) rows = static_cast<int32_t*>(dmalloc(targets.size() * ((5 * size_t(w) + 3) & ~size_t(3)) * 4));
+    p.wp_rows = rows;
+    begin_k("palette_delta");
+    launch_palette_delta(p, int(targets.size()), stream_);
+    end_k();
+    sync();
+    if (rows) dfree(rows);
+  }
   dfree(d_status);
-  JXLB_CHECK(status == 0, kErrUnsupported, "delta-palette entries are not implemented on the device");
+  dfree(d_mask);
 }
 
 void CudaBackend::int_to_float(const View& v, const BitDepth& d) {

@@ -360,7 +360,7 @@ void FramePlanner::run_inverse_transforms(const ModularStreamSyntax& s, std::vec
       }
       // an empty index channel has nothing to look up (palette.rs: the loops run zero times)
       if (targets[0].w && targets[0].h && targets[0].plane >= 0) {
-        JXLB_CHECK(pal.view.plane >= 0, kErrUnsupported, "palettes without explicit colours are not supported");
+        // a palette without explicit colours (nb_colours == 0) has no plane: only implicit and delta entries
         be_.palette_inverse(pal.view, targets, t, s.header.wp, fh_.bit_depth.bits_per_sample);
       }
       bufs.insert(bufs.begin() + t.begin_c + 1, added.begin(), added.end());

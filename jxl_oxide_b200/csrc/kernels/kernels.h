@@ -59,8 +59,18 @@ void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream);
 size_t modular_job_smem_bytes(const DevModularJob& job, uint32_t max_width);
 void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizontal, cudaStream_t stream);
 void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cudaStream_t stream);
-void launch_palette_inverse_simple(DevView palette, const DevView* targets, int num_c, int nb_colours, int bit_depth,
-                                   int nb_deltas, int* status, cudaStream_t stream);
+// Second pass of a delta palette (palette.rs:120-152): every channel is scanned in raster order and the samples marked
+// in `mask` get `d_pred`'s prediction (from already final neighbours) added - a serial recurrence per channel.
+struct DevPaletteDeltaParams {
+  DevView target[4];
+  const uint8_t* mask;  // width x height, 1 = add the prediction
+  uint32_t d_pred;
+  uint32_t wp[11];      // WpHeader p1, p2, p3a..p3e, w0..w3 (d_pred == 6)
+  int32_t* wp_rows;     // num_c * 5 * width ints of scratch (d_pred == 6)
+};
+void launch_palette_delta(DevPaletteDeltaParams p, int num_c, cudaStream_t stream);
+void launch_palette_inverse(DevView palette, const DevView* targets, int num_c, int nb_colours, int bit_depth, int nb_deltas,
+                            uint8_t* mask, int* status, cudaStream_t stream);
 void launch_int_to_float(DevView v, uint32_t bits_per_sample, uint32_t exp_bits, bool float_sample, cudaStream_t stream);
 void launch_modular_xyb(DevView y, DevView x, DevView b, float mx, float my, float mb, cudaStream_t stream);
 void launch_fill_u32(uint32_t* p, size_t n, uint32_t value, cudaStream_t stream);

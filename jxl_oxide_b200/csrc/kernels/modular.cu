@@ -110,20 +110,33 @@ __global__ void rct_kernel(DevView va, DevView vb, DevView vc, uint32_t rct_type
 struct PaletteTargets {
   DevView v[4];
 };
-// Palette without delta entries (palette.rs:26-118 with need_delta empty): pure lookup plus the
-// implicit colour cube for indices >= nb_colours. Indices < nb_deltas flag `status`.
+__constant__ int16_t kDeltaPalette[72][3] = {
+#include "../host/delta_palette.inc"
+};
+
+// First pass of the inverse palette (palette.rs:26-118): explicit colours, the implicit colour cube for indices >=
+// nb_colours, delta entries for negative indices. Samples whose index is < nb_deltas still need the prediction added
+// (second pass, palette_delta_kernel): they are marked in `mask` and counted in `status`.
 __global__ void palette_kernel(DevView pal, PaletteTargets t, int num_c, int nb_colours, int bit_depth, int nb_deltas,
-                               int* status) {
+                               uint8_t* mask, int* status) {
   uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= t.v[0].w) return;
   int32_t index = static_cast<int32_t*>(t.v[0].ptr)[size_t(y) * t.v[0].stride + x];
-  if (index < nb_deltas) {
-    atomicExch(status, kDevInvalid);
-    return;
-  }
+  const bool delta = index < nb_deltas;
+  mask[size_t(y) * t.v[0].w + x] = delta ? 1 : 0;
+  if (delta) atomicAdd(status, 1);
   for (int c = 0; c < num_c; ++c) {
     int32_t sample;
-    if (index < nb_colours) {
+    if (index < 0) {
+      if (c >= 3) {
+        sample = 0;
+      } else {
+        const uint32_t ii = uint32_t((-(index + 1)) % 143);
+        sample = kDeltaPalette[(ii + 1) >> 1][c];
+        if ((ii & 1) == 0) sample = -sample;
+        if (bit_depth > 8) sample <<= min(bit_depth, 24) - 8;
+      }
+    } else if (index < nb_colours) {
       sample = static_cast<const int32_t*>(pal.ptr)[size_t(c) * pal.stride + index];
     } else {
       int32_t idx = index - nb_colours;
@@ -204,12 +217,12 @@ void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cuda
   rct_kernel<<<grid2d(a.w, a.h), 128, 0, stream>>>(a, b, c, rct_type);
 }
 
-void launch_palette_inverse_simple(DevView palette, const DevView* targets, int num_c, int nb_colours, int bit_depth,
-                                   int nb_deltas, int* status, cudaStream_t stream) {
+void launch_palette_inverse(DevView palette, const DevView* targets, int num_c, int nb_colours, int bit_depth, int nb_deltas,
+                            uint8_t* mask, int* status, cudaStream_t stream) {
   PaletteTargets t;
   for (int i = 0; i < num_c && i < 4; ++i) t.v[i] = targets[i];
   if (!t.v[0].w || !t.v[0].h) return;
-  palette_kernel<<<grid2d(t.v[0].w, t.v[0].h), 128, 0, stream>>>(palette, t, num_c, nb_colours, bit_depth, nb_deltas, status);
+  palette_kernel<<<grid2d(t.v[0].w, t.v[0].h), 128, 0, stream>>>(palette, t, num_c, nb_colours, bit_depth, nb_deltas, mask, status);
 }
 
 void launch_int_to_float(DevView v, uint32_t bits, uint32_t exp_bits, bool float_sample, cudaStream_t stream) {

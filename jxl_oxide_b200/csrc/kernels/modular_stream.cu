@@ -619,6 +619,63 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
   }
 }
 
+// Delta-palette prediction pass (palette.rs:120-152): one CTA per channel, thread 0 walks the channel in raster order
+// (every prediction reads the already corrected W / N / NW / NE ... neighbours, a serial recurrence).
+__global__ void __launch_bounds__(32) palette_delta_kernel(DevPaletteDeltaParams p) {
+  __shared__ uint32_t s_div[65];
+  for (uint32_t i = threadIdx.x; i < 65; i += 32) s_div[i] = i ? (1u << 24) / i : 0;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const DevView v = p.target[blockIdx.x];
+  const uint32_t width = v.w, height = v.h;
+  int32_t* base = static_cast<int32_t*>(v.ptr);
+  const bool use_wp = p.d_pred == 6;
+  FastWp wp;
+  if (use_wp) wp.reset(width, p.wp_rows + size_t(blockIdx.x) * ((5 * size_t(width) + 3) & ~size_t(3)), p.wp, s_div);  // 16-byte aligned slices
+  for (uint32_t y = 0; y < height; ++y) {
+    int32_t* row = base + size_t(y) * v.stride;
+    const int32_t* rn = y ? row - v.stride : nullptr;
+    const int32_t* rnn = y >= 2 ? row - 2 * size_t(v.stride) : nullptr;
+    const uint8_t* mrow = p.mask + size_t(y) * width;
+    for (uint32_t x = 0; x < width; ++x) {
+      int32_t wv, n, nw;
+      if (y == 0) {
+        wv = x ? row[x - 1] : 0;
+        n = wv, nw = wv;
+      } else if (x == 0) {
+        n = rn[0];
+        wv = n, nw = n;
+      } else {
+        wv = row[x - 1], n = rn[x], nw = rn[x - 1];
+      }
+      const int32_t ne = (!rn || x + 1 >= width) ? n : rn[x + 1];
+      const int32_t nn = rnn ? rnn[x] : n;
+      if (use_wp) {
+        wp.prefetch();
+        wp.predict(n, nw, ne, wv, nn);
+      }
+      int32_t value = row[x];
+      if (mrow[x]) {
+        int32_t pred;
+        if (p.d_pred == 0) {
+          pred = 0;
+        } else if (p.d_pred == 5) {
+          pred = grad_clamped(n, wv, nw);
+        } else if (p.d_pred == 6) {
+          pred = wp.predicted_sample();
+        } else {
+          const int32_t nee = (!rn || x + 2 >= width) ? ne : rn[x + 2];
+          const int32_t wwv = x >= 2 ? row[x - 2] : wv;
+          pred = rare_predictor(p.d_pred, wv, n, nw, ne, nn, wwv, nee);
+        }
+        value = wadd(value, pred);
+        row[x] = value;
+      }
+      if (use_wp) wp.record(value);
+    }
+  }
+}
+
 __global__ void read_globaltimer_kernel(unsigned long long* out) {
   unsigned long long now;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -626,6 +683,11 @@ __global__ void read_globaltimer_kernel(unsigned long long* out) {
 }
 
 }  // namespace
+
+void launch_palette_delta(DevPaletteDeltaParams p, int num_c, cudaStream_t stream) {
+  if (num_c <= 0 || !p.target[0].w || !p.target[0].h) return;
+  palette_delta_kernel<<<num_c, 32, 0, stream>>>(p);
+}
 
 size_t modular_job_smem_bytes(const DevModularJob& job, uint32_t max_width) {
   return modular_layout(job.num_tree_nodes, job.code, job.lut_total, job.use_wp, max_width).total;

@@ -421,18 +421,7 @@ void OracleBackend::rct_inverse(const View v[3], uint32_t rct_type) {  // rct.rs
 
 namespace {
 const int16_t kDeltaPalette[72][3] = {  // palette.rs:10-24 (normative table)
-    {0, 0, 0}, {4, 4, 4}, {11, 0, 0}, {0, 0, -13}, {0, -12, 0}, {-10, -10, -10},
-    {-18, -18, -18}, {-27, -27, -27}, {-18, -18, 0}, {0, 0, -32}, {-32, 0, 0}, {-37, -37, -37},
-    {0, -32, -32}, {24, 24, 45}, {50, 50, 50}, {-45, -24, -24}, {-24, -45, -45}, {0, -24, -24},
-    {-34, -34, 0}, {-24, 0, -24}, {-45, -45, -24}, {64, 64, 64}, {-32, 0, -32}, {0, -32, 0},
-    {-32, 0, 32}, {-24, -45, -24}, {45, 24, 45}, {24, -24, -45}, {-45, -24, 24}, {80, 80, 80},
-    {64, 0, 0}, {0, 0, -64}, {0, -64, -64}, {-24, -24, 45}, {96, 96, 96}, {64, 64, 0},
-    {45, -24, -24}, {34, -34, 0}, {112, 112, 112}, {24, -45, -45}, {45, 45, -24}, {0, -32, 32},
-    {24, -24, 45}, {0, 96, 96}, {45, -24, 24}, {24, -45, -24}, {-24, -45, 24}, {0, -64, 0},
-    {96, 0, 0}, {128, 128, 128}, {64, 0, 64}, {144, 144, 144}, {96, 96, 0}, {-36, -36, 36},
-    {45, -24, -45}, {45, -45, -24}, {0, 0, -96}, {0, 128, 128}, {0, 96, 0}, {45, 24, -45},
-    {-128, 0, 0}, {24, -45, 24}, {-45, 24, -45}, {64, 0, -64}, {64, -64, -64}, {96, 0, 96},
-    {45, -45, 24}, {24, 45, -45}, {64, 64, -64}, {128, 128, 0}, {0, 0, -128}, {-24, 45, -45},
+#include "../jxl_oxide_b200/csrc/host/delta_palette.inc"
 };
 }
 
@@ -441,8 +430,8 @@ void OracleBackend::palette_inverse(const View& palette, const std::vector<View>
   const int32_t nb_deltas = int32_t(t.nb_deltas), nb_colors = int32_t(t.nb_colours);
   const uint32_t width = targets[0].w, height = targets[0].h;
   const size_t channels = targets.size();
-  Plane& pp = plane(palette.plane);
-  auto pal = [&](int32_t index, size_t c) { return pp.i32()[size_t(palette.y0 + c) * pp.w + palette.x0 + index]; };
+  Plane* pp = palette.plane >= 0 ? &plane(palette.plane) : nullptr;  // absent when nb_colours == 0
+  auto pal = [&](int32_t index, size_t c) { return pp->i32()[size_t(palette.y0 + c) * pp->w + palette.x0 + index]; };
   std::vector<int32_t*> base(channels);
   std::vector<size_t> stride(channels);
   for (size_t c = 0; c < channels; ++c) {

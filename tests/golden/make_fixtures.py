@@ -36,6 +36,7 @@ CASES = {
     "grayscale_jpeg": ("conformance/testcases/grayscale_jpeg", ["input.jxl"]),
     "cafe": ("conformance/testcases/cafe", ["input.jxl"]),
     "spot": ("conformance/testcases/spot", ["input.jxl"]),
+    "delta_palette": ("conformance/testcases/delta_palette", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
 
@@ -63,6 +64,8 @@ Image.open(os.path.join(REF, "conformance/testcases/cafe/ref.png")).crop((1024, 
 # spot colours: a 300 x 300 crop at (150, 50) of the 8-bit rendering
 Image.open(os.path.join(REF, "conformance/testcases/spot/ref.png")).crop((150, 50, 450, 350)).save(
     os.path.join(HERE, "spot", "ref_crop_150_50.png"), optimize=True)
+Image.open(os.path.join(REF, "conformance/testcases/delta_palette/ref.png")).crop((100, 200, 400, 500)).save(
+    os.path.join(HERE, "delta_palette", "ref_crop_100_200.png"), optimize=True)
 # three frames of the animation's reference APNG
 _ap = Image.open(os.path.join(REF, "conformance/testcases/animation_icos4d/ref.apng"))
 for _k in (0, 17, 47):

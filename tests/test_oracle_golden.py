@@ -168,6 +168,19 @@ def test_spot_colours_in_the_image_stream(oracle):
     assert np.abs(buf[50:350, 150:450] - ref).max() <= 0.004
 
 
+def test_delta_palette_exact(oracle):
+    """Lossy palette: a palette without explicit colours, implicit and delta entries, and the serial prediction pass
+    over the samples below nb_deltas (transform/palette.rs:26-152) - libjxl's 8-bit rendering is reproduced exactly."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("delta_palette", "input.jxl"), threads=4)
+    planes, ncol, _ = img.frame(0)
+    assert planes.shape == (3, 751, 555)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("delta_palette", "ref_crop_100_200.png")))).astype(np.int32)
+    got = np.rint(np.clip(np.moveaxis(planes, 0, 2)[200:500, 100:400], 0.0, 1.0) * 255.0).astype(np.int32)
+    assert np.array_equal(got, ref)
+
+
 def test_animation_splines(oracle):
     """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
     points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
