@@ -1084,6 +1084,9 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
     for (int i = 0; i < 9; ++i) p.col.matrix[i] = colour->matrix[i];
     p.col.apply_srgb_tf = colour->apply_srgb_tf ? 1 : 0;
     p.col.apply_bt709_tf = colour->apply_bt709_tf ? 1 : 0;
+    JXLB_CHECK(!colour->second_stage && colour->gamma == 0.0f, kErrInvalidArg, "the fused filter kernel converts to sRGB-gamut targets only");
+    p.col.second_stage = p.col.to_luma = 0;
+    p.col.gamma = 0.0f;
   }
   begin_k("filters_fused");
   launch_filters_fused(in, out, p, stream_);
@@ -1249,6 +1252,11 @@ void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   for (int i = 0; i < 9; ++i) d.matrix[i] = p.matrix[i];
   d.apply_srgb_tf = p.apply_srgb_tf ? 1 : 0;
   d.apply_bt709_tf = p.apply_bt709_tf ? 1 : 0;
+  d.second_stage = p.second_stage ? 1 : 0;
+  d.to_luma = p.to_luma ? 1 : 0;
+  for (int i = 0; i < 3; ++i) d.luminances[i] = p.luminances[i];
+  for (int i = 0; i < 9; ++i) d.matrix2[i] = p.matrix2[i];
+  d.gamma = p.gamma;
   begin_k("xyb_to_rgb");
   launch_xyb_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
   end_k();

@@ -103,6 +103,14 @@ struct ColorParams {  // XYB -> (linear) sRGB, jxl-color/src/{xyb.rs,ciexyz.rs:8
   float matrix[9];      // opsin inverse
   bool apply_srgb_tf;
   bool apply_bt709_tf = false;  // BT.709 OETF (jxl-color/src/tf/bt709.rs, generic fast_powf)
+  // Output encodings other than D65 / sRGB primaries (jxl-color/src/convert.rs:397-466): gamut mapping of the linear
+  // sRGB triple (gamut.rs:4-46; the XYB source is tagged Perceptual), then one matrix (linear sRGB -> XYZ -> adapted
+  // white point -> target primaries, pre-multiplied like ColorTransform::optimize) and, for a Grey target, Y alone.
+  bool second_stage = false;
+  float luminances[3] = {0, 0, 0};  // of the sRGB primaries: the gamut mapper's luma weights
+  float matrix2[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  bool to_luma = false;             // XyzToLuma: channel 0 := Y, one output channel
+  float gamma = 0.0f;               // > 0: v <= 1e-7 ? 0 : fast_powf(v, gamma) (tf.rs:11-70; Gamma and DCI)
 };
 
 class Backend {

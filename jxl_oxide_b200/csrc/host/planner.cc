@@ -2,6 +2,7 @@
 #include "planner.h"
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <deque>
@@ -780,7 +781,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     ColorParams cp;
     // colour conversion follows upsampling (render.rs:136-149), so it is fused only without it
     const bool want_colour = !upsampled && !colour_done && !lfg_.has_noise && !lfg_.has_patches && !lfg_.has_splines &&
-                             colour_params(ih_.xyb_encoded, colour.size(), &cp);
+                             colour_params(ih_.xyb_encoded, colour.size(), &cp) && !cp.second_stage && cp.gamma == 0.0f;
     if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
       colour_done = want_colour;
       if (want_colour) be_.stage_marker("rgb", v, 3);
@@ -1026,16 +1027,99 @@ void FramePlanner::render_vardct(DecodedFrame*) {
 
 // postprocess_keyframe (jxl-render/src/lib.rs:925-998) for the supported colour set: fills the
 // XYB -> (linear) sRGB parameters; false when the planes are left as they are.
+namespace {
+// jxl-color/src/ciexyz.rs:76-179 and consts.rs: every expression evaluated in f32, left to right
+typedef std::array<float, 9> Mat3;
+Mat3 matmul3(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r[i * 3 + j] = a[i * 3] * b[j] + a[i * 3 + 1] * b[3 + j] + a[i * 3 + 2] * b[6 + j];
+  return r;
+}
+std::array<float, 3> matmul3vec(const Mat3& a, const std::array<float, 3>& b) {
+  return {a[0] * b[0] + a[1] * b[1] + a[2] * b[2], a[3] * b[0] + a[4] * b[1] + a[5] * b[2], a[6] * b[0] + a[7] * b[1] + a[8] * b[2]};
+}
+Mat3 matinv(const Mat3& m) {
+  const float det = m[0] * (m[4] * m[8] - m[5] * m[7]) + m[1] * (m[5] * m[6] - m[3] * m[8]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+  return {(m[4] * m[8] - m[5] * m[7]) / det, (m[7] * m[2] - m[8] * m[1]) / det, (m[1] * m[5] - m[2] * m[4]) / det,
+          (m[5] * m[6] - m[3] * m[8]) / det, (m[8] * m[0] - m[6] * m[2]) / det, (m[2] * m[3] - m[0] * m[5]) / det,
+          (m[3] * m[7] - m[4] * m[6]) / det, (m[6] * m[1] - m[7] * m[0]) / det, (m[0] * m[4] - m[1] * m[3]) / det};
+}
+std::array<float, 3> illuminant_to_xyz(const float xy[2]) { return {xy[0] / xy[1], 1.0f, (1.0f - xy[0]) / xy[1] - 1.0f}; }
+Mat3 primaries_grid(const float p[3][2]) {
+  return {p[0][0], p[1][0], p[2][0], p[0][1], p[1][1], p[2][1], (1.0f - p[0][0] - p[0][1]), (1.0f - p[1][0] - p[1][1]),
+          (1.0f - p[2][0] - p[2][1])};
+}
+Mat3 primaries_to_xyz_mat(const float p[3][2], const float wp[2]) {
+  Mat3 m = primaries_grid(p);
+  const std::array<float, 3> mul = matmul3vec(matinv(m), illuminant_to_xyz(wp));
+  for (int i = 0; i < 9; ++i) m[i] *= mul[i % 3];
+  return m;
+}
+Mat3 xyz_to_primaries_mat(const float p[3][2], const float wp[2]) {
+  Mat3 inv = matinv(primaries_grid(p));
+  const std::array<float, 3> mul = matmul3vec(inv, illuminant_to_xyz(wp));
+  for (int i = 0; i < 9; ++i) inv[i] /= mul[i / 3];
+  return inv;
+}
+Mat3 adapt_mat(const float from[2], const float to[2]) {  // Bradford
+  static const Mat3 kBradford = {0.8951f, 0.2664f, -0.1614f, -0.7502f, 1.7135f, 0.0367f, 0.0389f, -0.0685f, 1.0296f};
+  static const Mat3 kBradfordInv = {0.9869929f, -0.1470543f, 0.1599627f, 0.4323053f, 0.5183603f,
+                                    0.0492912f, -0.0085287f, 0.0400428f, 0.9684867f};
+  const std::array<float, 3> from_w = illuminant_to_xyz(from), to_w = illuminant_to_xyz(to);
+  if (from_w == to_w) return {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const std::array<float, 3> from_lms = matmul3vec(kBradford, from_w), to_lms = matmul3vec(kBradford, to_w);
+  const float mul[3] = {to_lms[0] / from_lms[0], to_lms[1] / from_lms[1], to_lms[2] / from_lms[2]};
+  Mat3 multiplied;
+  for (int i = 0; i < 9; ++i) multiplied[i] = kBradford[i] * mul[i / 3];
+  return matmul3(kBradfordInv, multiplied);
+}
+
+const float kIlluminantD65[2] = {0.3127f, 0.329f};
+const float kPrimariesSrgb[3][2] = {{0.639998686f, 0.330010138f}, {0.300003784f, 0.600003357f}, {0.150002046f, 0.059997204f}};
+
+// The tail of ColorTransform::new for a linear-sRGB source (convert.rs:397-466) with its Matrix ops merged as
+// optimize() does (convert.rs:662-690): M = xyz_to_target * (adapt * srgb_to_xyz), or adapt * srgb_to_xyz for Grey.
+void target_matrix(const ColourEncoding& ce, bool grey, ColorParams* p) {
+  float wp[2] = {kIlluminantD65[0], kIlluminantD65[1]};
+  switch (ce.white_point) {
+    case WhitePointKind::kD65: break;
+    case WhitePointKind::kCustom: wp[0] = float(ce.white_xy[0]) / 1e6f, wp[1] = float(ce.white_xy[1]) / 1e6f; break;
+    case WhitePointKind::kE: wp[0] = 1.0f / 3.0f, wp[1] = 1.0f / 3.0f; break;
+    case WhitePointKind::kDci: wp[0] = 0.314f, wp[1] = 0.351f; break;
+  }
+  float prim[3][2];
+  const float (*src)[2] = kPrimariesSrgb;
+  static const float kBt2100[3][2] = {{0.708f, 0.292f}, {0.170f, 0.797f}, {0.131f, 0.046f}};
+  static const float kP3[3][2] = {{0.680f, 0.320f}, {0.265f, 0.690f}, {0.150f, 0.060f}};
+  if (ce.primaries == PrimariesKind::kBt2100) src = kBt2100;
+  if (ce.primaries == PrimariesKind::kP3) src = kP3;
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 2; ++k)
+      prim[i][k] = ce.primaries == PrimariesKind::kCustom ? float(ce.primaries_xy[i][k]) / 1e6f : src[i][k];
+  const Mat3 to_xyz = primaries_to_xyz_mat(kPrimariesSrgb, kIlluminantD65);
+  p->second_stage = true;
+  for (int i = 0; i < 3; ++i) p->luminances[i] = to_xyz[3 + i];
+  Mat3 m = matmul3(adapt_mat(kIlluminantD65, wp), to_xyz);
+  if (!grey) m = matmul3(xyz_to_primaries_mat(prim, wp), m);
+  for (int i = 0; i < 9; ++i) p->matrix2[i] = m[i];
+  p->to_luma = grey;
+}
+}  // namespace
+
 bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p) {
   if (!is_xyb || opt_.output_colour == 2) return false;
   JXLB_CHECK(num_colour == 3, kErrBitstream, "XYB needs three channels");
   const ColourEncoding& ce = ih_.colour_encoding;
-  bool srgb_like = !ce.want_icc && ce.colour_space == ColourSpace::kRgb && ce.white_point == WhitePointKind::kD65 &&
-                   ce.primaries == PrimariesKind::kSrgb &&
-                   (ce.tf == TransferFunctionKind::kSrgb || ce.tf == TransferFunctionKind::kLinear ||
-                    ce.tf == TransferFunctionKind::kBt709);
-  JXLB_CHECK(srgb_like || opt_.output_colour == 1, kErrUnsupported,
-             "only sRGB-gamut (sRGB/linear transfer) output encodings are implemented");
+  // an embedded ICC profile would have to be parsed into an enum encoding (jxl-render/src/lib.rs:104-150)
+  JXLB_CHECK(!ce.want_icc || opt_.output_colour == 1, kErrUnsupported, "XYB images with an embedded ICC profile are not supported");
+  const bool linear_srgb_out = opt_.output_colour == 1;
+  if (!linear_srgb_out) {
+    JXLB_CHECK(ce.colour_space == ColourSpace::kRgb || ce.colour_space == ColourSpace::kGrey, kErrUnsupported,
+               "unsupported output colour space");
+    JXLB_CHECK(ce.tf != TransferFunctionKind::kPq && ce.tf != TransferFunctionKind::kHlg, kErrUnsupported,
+               "PQ / HLG output transfer functions are not implemented");
+  }
   JXLB_CHECK(ih_.tone_mapping.intensity_target <= 255.0f || opt_.output_colour == 1, kErrUnsupported,
              "HDR tone mapping is outside the implemented hot path");
   const OpsinInverseMatrix& oim = ih_.opsin_inverse_matrix;
@@ -1047,6 +1131,12 @@ bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p)
   p->itscale = 255.0f / ih_.tone_mapping.intensity_target;
   p->apply_srgb_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kSrgb;
   p->apply_bt709_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kBt709;
+  if (!linear_srgb_out) {
+    if (ce.tf == TransferFunctionKind::kGamma) p->gamma = float(ce.gamma) / 1e7f;  // Gamma { inverted: true } (color.rs:582-587)
+    if (ce.tf == TransferFunctionKind::kDci) p->gamma = 1.0f / 2.6f;
+    const bool grey = ce.colour_space == ColourSpace::kGrey;
+    if (grey || ce.white_point != WhitePointKind::kD65 || ce.primaries != PrimariesKind::kSrgb) target_matrix(ce, grey, p);
+  }
   return true;
 }
 
@@ -1055,7 +1145,8 @@ void FramePlanner::finish_colour(std::vector<View>& colour, bool is_xyb, bool al
   if (!already_converted && colour_params(is_xyb, colour.size(), &p)) {
     View v[3] = {colour[0], colour[1], colour[2]};
     be_.xyb_to_rgb(v, p);
-    be_.stage_marker("rgb", v, 3);
+    if (p.to_luma) colour.resize(1);  // XyzToLuma leaves Y in the first channel (convert.rs:866-872)
+    be_.stage_marker("rgb", colour.data(), int(colour.size()));
   }
   out->num_color = uint32_t(colour.size());
   out->channels = colour;

@@ -241,6 +241,56 @@ __global__ void ycbcr_to_rgb_kernel(DevView vcb, DevView vy, DevView vcr, DevYcb
   *pcr = __fmaf_rn(cb, p.cb_to_b, yy);
 }
 
+// apply_gamma's scalar tail (jxl-color/src/tf.rs:62-69): v <= 1e-7 ? 0 : fast_powf_generic(v, gamma)
+__device__ __forceinline__ float gamma_tf(float a, float gamma) {
+  if (a <= 1e-7f) return 0.0f;
+  const int32_t x_bits = __float_as_int(a);
+  const int32_t exp_shifted = (x_bits - 0x3f2aaaab) >> 23;
+  const float mantissa = __int_as_float(x_bits - (exp_shifted << 23));
+  const float x = fsub(mantissa, 1.0f);
+  const float yp = fadd(fmul(fadd(fmul(7.4245873327820566e-1f, x), 1.4287160470083755f), x), -1.8503833400518310e-6f);
+  const float yq = fadd(fmul(fadd(fmul(1.7409343003366853e-1f, x), 1.0096718572241148f), x), 9.9032814277590719e-1f);
+  const float e = fmul(fadd(fdiv(yp, yq), float(exp_shifted)), gamma);
+  const float x_floor = floorf(e);
+  const float ex = __int_as_float(int32_t(uint32_t(__float2int_rz(x_floor) + 127) << 23));  // saturating, NaN -> 0
+  const float frac = fsub(e, x_floor);
+  float num = fadd(frac, 1.01749063e1f);
+  num = fadd(fmul(num, frac), 4.88687798e1f);
+  num = fadd(fmul(num, frac), 9.85506591e1f);
+  num = fmul(num, ex);
+  float den = fadd(fmul(2.10242958e-1f, frac), -2.22328856e-2f);
+  den = fadd(fmul(den, frac), -1.94414990e1f);
+  den = fadd(fmul(den, frac), 9.85506633e1f);
+  return fdiv(num, den);
+}
+
+// map_gamut_generic (jxl-color/src/gamut.rs:4-46) followed by the merged target matrix (convert.rs:397-466)
+__device__ __forceinline__ void second_colour_stage(const DevColorParams& p, float& o0, float& o1, float& o2) {
+  float o[3] = {o0, o1, o2};
+  const float yl = fadd(fadd(fmul(o[0], p.luminances[0]), fmul(o[1], p.luminances[1])), fmul(o[2], p.luminances[2]));
+  float gray_saturation = 0.0f, gray_luminance = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float v_sub_y = fsub(o[i], yl);
+    const float inv = fdiv(1.0f, v_sub_y == 0.0f ? 1.0f : v_sub_y);
+    const float v_over = fmul(o[i], inv);
+    if (!(v_sub_y >= 0.0f)) gray_saturation = fmaxf(gray_saturation, v_over);
+    gray_luminance = fmaxf(v_sub_y <= 0.0f ? gray_saturation : fsub(v_over, inv), gray_luminance);
+  }
+  float gray_mix = fadd(fmul(0.3f, fsub(gray_saturation, gray_luminance)), gray_luminance);
+  gray_mix = gray_mix < 0.0f ? 0.0f : (gray_mix > 1.0f ? 1.0f : gray_mix);
+  const float max_colour = fmaxf(o[2], fmaxf(o[1], fmaxf(o[0], 1.0f)));
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o[i] = fdiv(fadd(fmul(gray_mix, fsub(yl, o[i])), o[i]), max_colour);
+  const float* m = p.matrix2;
+  const float t0 = fadd(fadd(fmul(m[0], o[0]), fmul(m[1], o[1])), fmul(m[2], o[2]));
+  const float t1 = fadd(fadd(fmul(m[3], o[0]), fmul(m[4], o[1])), fmul(m[5], o[2]));
+  const float t2 = fadd(fadd(fmul(m[6], o[0]), fmul(m[7], o[1])), fmul(m[8], o[2]));
+  o0 = p.to_luma ? t1 : t0;
+  o1 = t1;
+  o2 = t2;
+}
+
 __global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorParams p) {
   const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= vx.w) return;
@@ -258,7 +308,12 @@ __global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorPa
   float o0 = fadd(fadd(fmul(m[0], a), fmul(m[1], b)), fmul(m[2], c));
   float o1 = fadd(fadd(fmul(m[3], a), fmul(m[4], b)), fmul(m[5], c));
   float o2 = fadd(fadd(fmul(m[6], a), fmul(m[7], b)), fmul(m[8], c));
-  if (p.apply_srgb_tf) {
+  if (p.second_stage) second_colour_stage(p, o0, o1, o2);
+  if (p.gamma > 0.0f) {
+    o0 = gamma_tf(o0, p.gamma);
+    o1 = gamma_tf(o1, p.gamma);
+    o2 = gamma_tf(o2, p.gamma);
+  } else if (p.apply_srgb_tf) {
     o0 = linear_to_srgb(o0);
     o1 = linear_to_srgb(o1);
     o2 = linear_to_srgb(o2);

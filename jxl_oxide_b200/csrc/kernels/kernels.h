@@ -164,6 +164,9 @@ struct DevColorParams {
   float opsin_bias[3], cbrt_opsin_bias[3], itscale, matrix[9];
   int apply_srgb_tf;
   int apply_bt709_tf;
+  // non-sRGB targets (ColorParams::second_stage): gamut map, second matrix, optional XyzToLuma, gamma TF
+  int second_stage, to_luma;
+  float luminances[3], matrix2[9], gamma;
 };
 void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream);
 // YCbCr -> RGB in place, planes Cb, Y, Cr (jxl-color/src/ycbcr.rs:40-56)

@@ -621,7 +621,62 @@ void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
       float c = std::fmaf(g_s * g_s, g_s, p.opsin_bias[2]) * p.itscale;
       const float* m = p.matrix;
       float o[3] = {m[0] * a + m[1] * b + m[2] * c, m[3] * a + m[4] * b + m[5] * c, m[6] * a + m[7] * b + m[8] * c};
-      if (p.apply_srgb_tf) {
+      if (p.second_stage) {
+        {  // map_gamut_generic (jxl-color/src/gamut.rs:4-46), saturation factor 0.3
+          const float yl = o[0] * p.luminances[0] + o[1] * p.luminances[1] + o[2] * p.luminances[2];
+          float gray_saturation = 0.0f, gray_luminance = 0.0f;
+          for (float vv : o) {
+            const float v_sub_y = vv - yl;
+            const float inv = 1.0f / (v_sub_y == 0.0f ? 1.0f : v_sub_y);
+            const float v_over = vv * inv;
+            if (!(v_sub_y >= 0.0f)) gray_saturation = std::fmax(gray_saturation, v_over);
+            gray_luminance = std::fmax(v_sub_y <= 0.0f ? gray_saturation : v_over - inv, gray_luminance);
+          }
+          float gray_mix = 0.3f * (gray_saturation - gray_luminance) + gray_luminance;
+          gray_mix = gray_mix < 0.0f ? 0.0f : (gray_mix > 1.0f ? 1.0f : gray_mix);  // f32::clamp (NaN passes through)
+          float max_colour = 1.0f;
+          for (float vv : o) max_colour = std::fmax(vv, max_colour);
+          for (float& vv : o) vv = (gray_mix * (yl - vv) + vv) / max_colour;
+        }
+        const float* m2 = p.matrix2;
+        const float t0 = m2[0] * o[0] + m2[1] * o[1] + m2[2] * o[2], t1 = m2[3] * o[0] + m2[4] * o[1] + m2[5] * o[2],
+                    t2 = m2[6] * o[0] + m2[7] * o[1] + m2[8] * o[2];
+        o[0] = p.to_luma ? t1 : t0, o[1] = t1, o[2] = t2;
+      }
+      if (p.gamma > 0.0f) {  // apply_gamma (tf.rs:62-69) with fast_powf_generic (fastmath/powf.rs)
+        for (float& sref : o) {
+          const float a0 = sref;
+          if (a0 <= 1e-7f) {
+            sref = 0.0f;
+            continue;
+          }
+          int32_t x_bits;
+          std::memcpy(&x_bits, &a0, 4);
+          const int32_t exp_shifted = (x_bits - 0x3f2aaaab) >> 23;
+          const int32_t mb = x_bits - (exp_shifted << 23);
+          float mantissa;
+          std::memcpy(&mantissa, &mb, 4);
+          const float xx2 = mantissa - 1.0f;
+          const float yp = (7.4245873327820566e-1f * xx2 + 1.4287160470083755f) * xx2 + -1.8503833400518310e-6f;
+          const float yq = (1.7409343003366853e-1f * xx2 + 1.0096718572241148f) * xx2 + 9.9032814277590719e-1f;
+          const float e = (yp / yq + float(exp_shifted)) * p.gamma;
+          const float x_floor = std::floor(e);
+          // `x_floor as i32` saturates (NaN -> 0); the sum wraps like release-mode Rust
+          const int32_t xi = x_floor != x_floor ? 0 : (x_floor >= 2147483648.0f ? INT32_MAX : (x_floor <= -2147483648.0f ? INT32_MIN : int32_t(x_floor)));
+          const uint32_t eb = (uint32_t(xi) + 127u) << 23;
+          float ex;
+          std::memcpy(&ex, &eb, 4);
+          const float frac = e - x_floor;
+          float num = frac + 1.01749063e1f;
+          num = num * frac + 4.88687798e1f;
+          num = num * frac + 9.85506591e1f;
+          num = num * ex;
+          float den = 2.10242958e-1f * frac + -2.22328856e-2f;
+          den = den * frac + -1.94414990e1f;
+          den = den * frac + 9.85506633e1f;
+          sref = num / den;
+        }
+      } else if (p.apply_srgb_tf) {
         for (float& s : o) {
           uint32_t bits;
           std::memcpy(&bits, &s, 4);

@@ -143,6 +143,14 @@ def test_synthetic_vardct_frames_bit_exact(dec, oracle, size, seed, extra):
     _check_vardct(dec, oracle, bench.synth_frame(size[0], size[1], seed, extra=extra))
 
 
+@pytest.mark.parametrize("colour", ["p3", "rec2020-gamma", "gray", "dci", "custom"])
+def test_enum_colour_targets_bit_exact(dec, oracle, colour):
+    """Non-sRGB enum output encodings: gamut mapping, the merged target matrix, XyzToLuma and the gamma transfer
+    function of xyb_to_rgb_kernel (convert.rs:397-466) against the oracle, stage by stage."""
+    import bench
+    _check_vardct(dec, oracle, bench.synth_frame(712, 520, 9, extra=("--colour", colour)))
+
+
 @pytest.mark.parametrize("output_colour", [1, 2])
 def test_fused_filters_other_output_encodings(dec, oracle, output_colour):
     """Linear-sRGB and XYB outputs go through the fused Gaborish+EPF(+colour) kernel as well."""

@@ -303,6 +303,64 @@ def test_progressive_passes_sum_to_the_single_pass_image(oracle):
         assert np.array_equal(got.view(np.uint32), one.view(np.uint32)), passes
 
 
+def test_enum_colour_targets_against_float64_colour_math(oracle):
+    """XYB -> P3 / BT.2100 / custom primaries, DCI / custom white points, Grey, gamma and DCI transfer functions
+    (jxl-color/src/convert.rs:397-466, ciexyz.rs, gamut.rs, tf.rs). No reference rendering with such an enum encoding
+    exists offline, so the check is numerical: the decoder's linear-sRGB output pushed through textbook float64
+    colour math (chromaticity matrices, Bradford adaptation, analytic transfer curves) must agree."""
+    import bench
+    D65 = (0.3127, 0.329)
+    SRGB = ((0.639998686, 0.330010138), (0.300003784, 0.600003357), (0.150002046, 0.059997204))
+    P3 = ((0.680, 0.320), (0.265, 0.690), (0.150, 0.060))
+    BT2100 = ((0.708, 0.292), (0.170, 0.797), (0.131, 0.046))
+
+    def wxyz(w):
+        return np.array([w[0] / w[1], 1.0, (1 - w[0] - w[1]) / w[1]])
+
+    def rgb2xyz(prim, wp):
+        m = np.array([[q[0] for q in prim], [q[1] for q in prim], [1 - q[0] - q[1] for q in prim]])
+        return m * np.linalg.solve(m, wxyz(wp))[None, :]
+
+    br = np.array([[0.8951, 0.2664, -0.1614], [-0.7502, 1.7135, 0.0367], [0.0389, -0.0685, 1.0296]])
+
+    def adapt(f, t):
+        return np.linalg.inv(br) @ np.diag((br @ wxyz(t)) / (br @ wxyz(f))) @ br
+
+    def gamut(rgb, lum, sat=0.3):  # gamut.rs:4-46
+        y = (rgb * lum[:, None, None]).sum(0)
+        gs, gl = np.zeros_like(y), np.zeros_like(y)
+        for v in rgb:
+            d = v - y
+            inv = 1.0 / np.where(d == 0, 1.0, d)
+            vo = v * inv
+            gs = np.where(d >= 0, gs, np.maximum(gs, vo))
+            gl = np.maximum(np.where(d <= 0, gs, vo - inv), gl)
+        mix = np.clip(sat * (gs - gl) + gl, 0, 1)
+        return (mix * (y - rgb) + rgb) / np.maximum(1.0, rgb.max(0))
+
+    def srgb_oetf(v):
+        a = np.abs(v)
+        return np.sign(v) * np.where(a <= 0.0031308, 12.92 * a, 1.055 * np.power(a, 1 / 2.4) - 0.055)
+
+    def gam(v, g):
+        return np.where(v <= 1e-7, 0.0, np.power(np.maximum(v, 1e-30), g))
+
+    lin = oracle.OracleImage(bench.synth_frame(600, 500, 5), output_colour=1, threads=4).frame(0)[0].astype(np.float64)
+    to_xyz = rgb2xyz(SRGB, D65)
+    g = gamut(lin, to_xyz[1])
+    cases = {"p3": (P3, D65, srgb_oetf, 2e-4), "rec2020-gamma": (BT2100, D65, lambda v: gam(v, 0.4166667), 5e-6),
+             "dci": (P3, (0.314, 0.351), lambda v: gam(v, 1 / 2.6), 5e-6),
+             "custom": (((0.64, 0.33), (0.21, 0.71), (0.15, 0.06)), (0.3457, 0.3585), lambda v: gam(v, 0.4545455), 5e-6)}
+    for name, (prim, wp, tf, tol) in cases.items():
+        m = np.linalg.inv(rgb2xyz(prim, wp)) @ adapt(D65, wp) @ to_xyz
+        want = tf(np.einsum("ij,jhw->ihw", m, g))
+        got = oracle.OracleImage(bench.synth_frame(600, 500, 5, extra=("--colour", name)), threads=4).frame(0)[0]
+        assert got.shape == want.shape and np.abs(got - want).max() <= tol, name
+    got = oracle.OracleImage(bench.synth_frame(600, 500, 5, extra=("--colour", "gray")), threads=4).frame(0)[0]
+    assert got.shape == (1, 500, 600)
+    assert np.abs(got[0] - srgb_oetf(np.einsum("ij,jhw->ihw", to_xyz, g))[1]).max() <= 2e-4
+
+
 def _fuzz_files():
     import glob
     import os

@@ -572,6 +572,7 @@ struct Args {
   bool lf_wp = true;
   std::string out = "synth.jxl";
   uint32_t passes = 1;    // HF coefficients split over this many passes (progressive; pass p carries shift passes-1-p)
+  std::string colour;     // "" = all-default metadata (sRGB); p3 | rec2020-gamma | gray | dci | custom: an enum colour encoding
   bool lf_frame = false;  // put the LF image into a separate Modular LF frame (frame type 1, lf_level 1)
 };
 
@@ -589,6 +590,7 @@ int main(int argc, char** argv) {
     else if (s == "--lf-gradient") a.lf_wp = false;
     else if (s == "--lf-frame") a.lf_frame = true;
     else if (s == "--passes") a.passes = uint32_t(atoi(next().c_str()));
+    else if (s == "--colour") a.colour = next();
     else if (s == "-o") a.out = next();
     else fprintf(stderr, "unknown arg %s\n", s.c_str()), exit(2);
   }
@@ -859,7 +861,54 @@ int main(int argc, char** argv) {
   write_dim(H);
   cs.write(3, 0);  // ratio
   write_dim(W);
-  cs.write(1, 1);  // ImageMetadata all_default
+  if (a.colour.empty()) {
+    cs.write(1, 1);  // ImageMetadata all_default
+  } else {  // ImageMetadata with an enum ColourEncoding (jxl-image/src/lib.rs:229-287, color.rs:21-58)
+    auto write_enum = [&](uint32_t v) {
+      if (v == 0) write_u32(cs, 0, 0, 0);
+      else if (v == 1) write_u32(cs, 1, 0, 0);
+      else if (v < 18) write_u32(cs, 2, 4, v - 2);
+      else write_u32(cs, 3, 6, v - 18);
+    };
+    auto write_xy = [&](double x, double y) {
+      for (double c : {x, y}) {
+        const uint32_t u = pack_signed(int32_t(std::lround(c * 1e6)));
+        if (u < 524288) write_u32(cs, 0, 19, u);
+        else if (u < 1048576) write_u32(cs, 1, 19, u - 524288);
+        else if (u < 2097152) write_u32(cs, 2, 20, u - 1048576);
+        else write_u32(cs, 3, 21, u - 2097152);
+      }
+    };
+    cs.write(1, 0);  // all_default
+    cs.write(1, 0);  // extra_fields
+    cs.write(1, 0);  // integer samples
+    cs.write(2, 0);  // 8 bits
+    cs.write(1, 1);  // modular_16bit_buffers
+    cs.write(2, 0);  // no extra channels
+    cs.write(1, 1);  // xyb_encoded
+    cs.write(1, 0);  // ColourEncoding all_default
+    cs.write(1, 0);  // want_icc
+    const bool grey = a.colour == "gray";
+    write_enum(grey ? 1 : 0);  // colour space: RGB / Grey
+    if (a.colour == "dci") write_enum(11);  // white point: DCI
+    else if (a.colour == "custom") write_enum(2), write_xy(0.3457, 0.3585);  // custom (D50-like)
+    else write_enum(1);  // D65
+    if (!grey) {
+      if (a.colour == "p3" || a.colour == "dci") write_enum(11);
+      else if (a.colour == "rec2020-gamma") write_enum(9);
+      else if (a.colour == "custom") write_enum(2), write_xy(0.64, 0.33), write_xy(0.21, 0.71), write_xy(0.15, 0.06);  // Adobe RGB-like
+      else fprintf(stderr, "unknown --colour %s\n", a.colour.c_str()), exit(2);
+    }
+    if (a.colour == "rec2020-gamma" || a.colour == "custom") {
+      cs.write(1, 1);  // has_gamma
+      cs.write(24, a.colour == "custom" ? 4545455 : 4166667);  // 1/2.2, 1/2.4
+    } else {
+      cs.write(1, 0);
+      write_enum(a.colour == "dci" ? 17 : 13);  // DCI / sRGB
+    }
+    write_enum(1);   // rendering intent: relative
+    cs.write(2, 0);  // extensions
+  }
   cs.write(1, 1);  // default_m
   cs.pad();
   auto write_u64_small = [&](uint32_t v) {  // U64 (jxl-bitstream): 0 | 1 + u(4) | 17 + u(8)
