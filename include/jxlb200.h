@@ -68,6 +68,10 @@ int32_t jxlb_decode(jxlb_decoder* dec, const uint8_t* data, size_t size, const j
 int32_t jxlb_preload(jxlb_decoder* dec, int32_t slot, const uint8_t* data, size_t size);
 int32_t jxlb_decode_slot(jxlb_decoder* dec, int32_t slot, const jxlb_options* opt);
 int32_t jxlb_image_get_info(const jxlb_decoder* dec, jxlb_image_info* info);
+/* JxlImage::original_icc (crates/jxl-oxide/src/lib.rs:536-540): the embedded ICC profile, reconstructed from the
+ * codestream (crates/jxl-color/src/icc/decode.rs). Returns its size in bytes (0 = none, -1 = bad argument) and copies
+ * it when `dst` holds at least that many bytes. */
+int64_t jxlb_image_original_icc(const jxlb_decoder* dec, uint8_t* dst, size_t dst_bytes);
 int32_t jxlb_num_frames(const jxlb_decoder* dec);
 int32_t jxlb_frame_get_info(const jxlb_decoder* dec, int32_t frame, jxlb_frame_info* info);
 /* Render::image_planar equivalent (crates/jxl-oxide/src/lib.rs:1178-1203): copy one channel to

@@ -26,7 +26,7 @@ OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVI
 # every symbol include/jxlb200.h declares
 EXPORTED_SYMBOLS = [
     "jxlb_decoder_create", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
-    "jxlb_image_get_info",
+    "jxlb_image_get_info", "jxlb_image_original_icc",
     "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
     "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_stage_count", "jxlb_stage_get",
@@ -94,6 +94,8 @@ def load_library():
     L.jxlb_frame_get_info.argtypes = [vp, i32, ctypes.POINTER(_FrameInfo)]
     L.jxlb_frame_channel_to_host.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
     L.jxlb_frame_write_to_buffer.argtypes = [vp, i32, i32, i32, vp, ctypes.c_size_t]
+    L.jxlb_image_original_icc.argtypes = [vp, vp, ctypes.c_size_t]
+    L.jxlb_image_original_icc.restype = ctypes.c_int64
     L.jxlb_frame_stream_channels.argtypes = [vp, i32]
     L.jxlb_frame_stream_channels.restype = i32
     L.jxlb_frame_channel_device.argtypes = [vp, i32, i32, ctypes.POINTER(vp), ctypes.POINTER(u32)]
@@ -197,6 +199,15 @@ class Decoder:
         """Copies all channels of a frame into a preallocated (channels, h, w) float32 array."""
         for c in range(out.shape[0]):
             self._check(self._L.jxlb_frame_channel_to_host(self._h, frame, c, out[c].ctypes.data, out.shape[2]))
+
+    def original_icc(self):
+        """JxlImage::original_icc: the embedded ICC profile's bytes (b"" when the image has none)."""
+        n = self._L.jxlb_image_original_icc(self._h, None, 0)
+        if n <= 0:
+            return b""
+        buf = ctypes.create_string_buffer(n)
+        self._L.jxlb_image_original_icc(self._h, buf, n)
+        return buf.raw
 
     def frame_to_buffer(self, frame, dtype=np.uint8, orientation=0):
         """ImageStream::write_to_buffer: (height, width, channels) interleaved u8 / u16 / f32 samples with the

@@ -10,7 +10,7 @@ OUT = os.path.join(HERE, "libjxlb200.so")
 SOURCES = [
     "capi.cu", "cuda_backend.cu",
     "kernels/modular.cu", "kernels/modular_stream.cu", "kernels/entropy.cu", "kernels/blockinfo.cu", "kernels/vardct.cu", "kernels/filters.cu", "kernels/filters_fused.cu",
-    "host/entropy.cc", "host/headers.cc", "host/modular_syntax.cc", "host/frame_syntax.cc", "host/planner.cc",
+    "host/entropy.cc", "host/headers.cc", "host/modular_syntax.cc", "host/frame_syntax.cc", "host/planner.cc", "host/icc.cc",
 ]
 
 # -fmad=false: the reference's generic float path never contracts a*b+c (SimdVector::muladd is

@@ -137,6 +137,13 @@ int32_t jxlb_image_get_info(const jxlb_decoder* dec, jxlb_image_info* info) {
   return JXLB_OK;
 }
 
+int64_t jxlb_image_original_icc(const jxlb_decoder* dec, uint8_t* dst, size_t dst_bytes) {
+  if (!dec || !dec->have_result) return -1;
+  const std::vector<uint8_t>& icc = dec->res.image_header.icc_profile;
+  if (dst && dst_bytes >= icc.size() && !icc.empty()) std::memcpy(dst, icc.data(), icc.size());
+  return int64_t(icc.size());
+}
+
 int32_t jxlb_num_frames(const jxlb_decoder* dec) { return (dec && dec->have_result) ? int32_t(dec->res.frames.size()) : 0; }
 
 int32_t jxlb_frame_get_info(const jxlb_decoder* dec, int32_t frame, jxlb_frame_info* info) {

@@ -269,9 +269,14 @@ ImageHeader parse_image_header(BitReader& br) {
 
 // jxl-color/src/icc/decode.rs:9-105 — the encoded ICC stream is entropy-decoded only to find
 // where it ends; ICC colour management is outside the hot path.
-void skip_icc_profile(BitReader& br) {
+void skip_icc_profile(BitReader& br) { read_icc_stream(br); }
+
+std::vector<uint8_t> read_icc_stream(BitReader& br) {
   uint64_t enc_size = br.read_u64();
   JXLB_CHECK(enc_size <= (1u << 28), kErrBitstream, "encoded ICC profile too large");
+  JXLB_CHECK(enc_size <= br.size_bits(), kErrEof, "encoded ICC profile larger than the codestream");
+  std::vector<uint8_t> encoded;
+  encoded.reserve(size_t(enc_size));
   EntropyCode code = parse_entropy_code(br, 41);
   EntropyReader dec(&code);
   dec.begin(br);
@@ -300,9 +305,11 @@ void skip_icc_profile(BitReader& br) {
     JXLB_CHECK(sym < 256, kErrBitstream, "invalid ICC stream");
     b2 = b1;
     b1 = uint8_t(sym);
+    encoded.push_back(b1);
     br.check();
   }
   JXLB_CHECK(dec.finalize_ok(), kErrBitstream, "invalid ANS stream (ICC)");
+  return encoded;
 }
 
 uint32_t FrameHeader::sample_width(uint32_t ups) const {  // header.rs:227-245

@@ -47,6 +47,7 @@ struct ColourEncoding {  // jxl-image/src/color.rs:9-58
   int32_t primaries_xy[3][2] = {};
   TransferFunctionKind tf = TransferFunctionKind::kSrgb;
   uint32_t gamma = 0;
+  bool gamma_inverted = true;  // Gamma { g, inverted }: the bitstream codes 1/gamma (color.rs:582-587), an ICC 'para' curve gamma
   uint32_t rendering_intent = 1;
 };
 
@@ -79,6 +80,12 @@ struct ImageHeader {  // jxl-image/src/lib.rs:17-60, 130-170
   OpsinInverseMatrix opsin_inverse_matrix;
   std::vector<float> up2_weight, up4_weight, up8_weight;  // 15 / 55 / 210
   bool grayscale() const { return colour_encoding.colour_space == ColourSpace::kGrey; }
+  // Embedded ICC profile (want_icc): the decoded bytes, and the encoding an XYB image is rendered into - the enum
+  // encoding equivalent to the profile when there is one, else sRGB / gray sRGB (jxl-render/src/lib.rs:104-150).
+  std::vector<uint8_t> icc_profile;
+  bool icc_is_enum = false;
+  bool icc_is_cmyk = false;  // the profile's data colour space is CMYK: the black channel joins the image stream
+  ColourEncoding icc_encoding;
 };
 
 enum class FrameType : uint32_t { kRegular = 0, kLfFrame = 1, kReferenceOnly = 2, kSkipProgressive = 3 };
@@ -181,6 +188,8 @@ struct Toc {
 ImageHeader parse_image_header(BitReader& br);
 // Parses an ICC profile's *presence* only: the encoded ICC stream is skipped (not decoded).
 void skip_icc_profile(BitReader& br);
+// The entropy-decoded (still command-coded) ICC stream (jxl-color/src/icc/decode.rs:9-81)
+std::vector<uint8_t> read_icc_stream(BitReader& br);
 FrameHeader parse_frame_header(BitReader& br, const ImageHeader& ih);
 Toc parse_toc(BitReader& br, const FrameHeader& fh);
 

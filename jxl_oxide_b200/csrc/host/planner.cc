@@ -1,6 +1,8 @@
 // See planner.h.
 #include "planner.h"
 
+#include "icc.h"
+
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -1110,9 +1112,8 @@ void target_matrix(const ColourEncoding& ce, bool grey, ColorParams* p) {
 bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p) {
   if (!is_xyb || opt_.output_colour == 2) return false;
   JXLB_CHECK(num_colour == 3, kErrBitstream, "XYB needs three channels");
-  const ColourEncoding& ce = ih_.colour_encoding;
-  // an embedded ICC profile would have to be parsed into an enum encoding (jxl-render/src/lib.rs:104-150)
-  JXLB_CHECK(!ce.want_icc || opt_.output_colour == 1, kErrUnsupported, "XYB images with an embedded ICC profile are not supported");
+  // with an embedded ICC profile the target is the equivalent enum encoding, or sRGB (jxl-render/src/lib.rs:104-150)
+  const ColourEncoding& ce = ih_.colour_encoding.want_icc ? ih_.icc_encoding : ih_.colour_encoding;
   const bool linear_srgb_out = opt_.output_colour == 1;
   if (!linear_srgb_out) {
     JXLB_CHECK(ce.colour_space == ColourSpace::kRgb || ce.colour_space == ColourSpace::kGrey, kErrUnsupported,
@@ -1132,7 +1133,8 @@ bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p)
   p->apply_srgb_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kSrgb;
   p->apply_bt709_tf = (opt_.output_colour == 0) && ce.tf == TransferFunctionKind::kBt709;
   if (!linear_srgb_out) {
-    if (ce.tf == TransferFunctionKind::kGamma) p->gamma = float(ce.gamma) / 1e7f;  // Gamma { inverted: true } (color.rs:582-587)
+    if (ce.tf == TransferFunctionKind::kGamma)  // convert.rs:972-989
+      p->gamma = ce.gamma_inverted ? float(ce.gamma) / 1e7f : 1e7f / float(ce.gamma);
     if (ce.tf == TransferFunctionKind::kDci) p->gamma = 1.0f / 2.6f;
     const bool grey = ce.colour_space == ColourSpace::kGrey;
     if (grey || ce.white_point != WhitePointKind::kD65 || ce.primaries != PrimariesKind::kSrgb) target_matrix(ce, grey, p);
@@ -1157,6 +1159,12 @@ void FramePlanner::finish_colour(std::vector<View>& colour, bool is_xyb, bool al
 StreamLayout stream_layout(const ImageHeader& ih, const DecodedFrame& f) {
   StreamLayout l;
   for (size_t c = 0; c < f.num_color && c < f.channels.size(); ++c) l.channels.push_back(c);
+  if (ih.icc_is_cmyk)  // fb.rs:211-226
+    for (size_t e = 0; e < ih.ec_info.size() && f.num_color + e < f.channels.size(); ++e)
+      if (ih.ec_info[e].type == ExtraChannelType::kBlack) {
+        l.channels.push_back(f.num_color + e);
+        break;
+      }
   for (size_t e = 0; e < ih.ec_info.size() && f.num_color + e < f.channels.size(); ++e)
     if (ih.ec_info[e].type == ExtraChannelType::kAlpha) {
       l.channels.push_back(f.num_color + e);
@@ -1177,7 +1185,23 @@ DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, cons
   BitReader br(cs, size);
   res.image_header = parse_image_header(br);
   const ImageHeader& ih = res.image_header;
-  if (ih.colour_encoding.want_icc) skip_icc_profile(br);
+  if (ih.colour_encoding.want_icc) {  // jxl-oxide/src/lib.rs:365-372, jxl-render/src/lib.rs:100-150
+    ImageHeader& mih = res.image_header;
+    mih.icc_profile = decode_icc_stream(read_icc_stream(br));
+    IccInfo info;
+    const IccStatus st = icc_to_enum(mih.icc_profile, &info);
+    const bool header_gray = mih.colour_encoding.colour_space == ColourSpace::kGrey;
+    if (st != IccStatus::kMalformed)
+      JXLB_CHECK(header_gray == info.is_gray, kErrBitstream, "colour channel mismatch between header and ICC profile");
+    mih.icc_is_enum = st == IccStatus::kEnum;
+    mih.icc_is_cmyk = st != IccStatus::kMalformed && info.is_cmyk;
+    if (mih.icc_is_enum) {
+      mih.icc_encoding = info.encoding;
+    } else {  // EnumColourEncoding::{gray_srgb, srgb}
+      mih.icc_encoding = ColourEncoding();
+      if (header_gray) mih.icc_encoding.colour_space = ColourSpace::kGrey;
+    }
+  }
   br.zero_pad_to_byte();
   size_t pos = br.pos() / 8;
   if (ih.have_preview) {  // skipped, like jxl-oxide/src/lib.rs:384-411

@@ -29,8 +29,8 @@ struct DecodedFrame {
 
 // What ImageStream::from_render puts into an interleaved buffer (jxl-oxide/src/fb.rs:184-283): the colour channels,
 // then the first alpha channel; spot-colour channels are mixed into a three-channel colour image while it is written
-// (fb.rs:335-362) unless the image is grayscale (lib.rs:416). The black channel of CMYK images would follow the
-// colour channels; CMYK is recognised through the ICC profile, which this library does not interpret.
+// (fb.rs:335-362) unless the image is grayscale (lib.rs:416). The black channel of a CMYK image (recognised by its
+// ICC profile's data colour space) follows the colour channels; the samples stay CMYK - no CMS here.
 struct StreamSpot {
   size_t channel;  // index into DecodedFrame::channels
   float rgb[3];

@@ -53,6 +53,12 @@ void jxlo_image_info(void* hp, uint32_t* width, uint32_t* height, uint32_t* bits
   *num_extra = uint32_t(ih.ec_info.size()), *xyb = ih.xyb_encoded, *gray = ih.grayscale();
 }
 
+size_t jxlo_image_original_icc(void* hp, uint8_t* dst, size_t cap) {
+  const std::vector<uint8_t>& icc = static_cast<Handle*>(hp)->res.image_header.icc_profile;
+  if (dst && cap >= icc.size() && !icc.empty()) std::memcpy(dst, icc.data(), icc.size());
+  return icc.size();
+}
+
 uint32_t jxlo_image_orientation(void* hp) { return static_cast<Handle*>(hp)->res.image_header.orientation; }
 
 void jxlo_frame_info(void* hp, int frame, uint32_t* width, uint32_t* height, uint32_t* num_channels,

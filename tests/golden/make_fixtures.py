@@ -36,6 +36,7 @@ CASES = {
     "grayscale_jpeg": ("conformance/testcases/grayscale_jpeg", ["input.jxl"]),
     "cafe": ("conformance/testcases/cafe", ["input.jxl"]),
     "spot": ("conformance/testcases/spot", ["input.jxl"]),
+    "grayscale": ("conformance/testcases/grayscale", ["input.jxl", "ref.png"]),
     "delta_palette": ("conformance/testcases/delta_palette", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]

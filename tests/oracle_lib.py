@@ -31,6 +31,8 @@ def lib():
         L.jxlo_frame_channel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.jxlo_frame_write_to_buffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.jxlo_frame_write_to_buffer.restype = ctypes.c_size_t
+        L.jxlo_image_original_icc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.jxlo_image_original_icc.restype = ctypes.c_size_t
         L.jxlo_frame_stream_channels.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.jxlo_frame_stream_channels.restype = ctypes.c_uint32
         L.jxlo_stage.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32),
@@ -69,6 +71,13 @@ class OracleImage:
         for c in range(nch):
             L.jxlo_frame_channel(self._h, idx, c, out[c].ctypes.data)
         return out, ncol, bool(vardct)
+
+    def original_icc(self):
+        L = lib()
+        n = L.jxlo_image_original_icc(self._h, None, 0)
+        buf = ctypes.create_string_buffer(max(n, 1))
+        L.jxlo_image_original_icc(self._h, buf, n)
+        return buf.raw[:n]
 
     def frame_to_buffer(self, idx=0, dtype=np.uint8, orientation=0):
         """ImageStream::write_to_buffer: (height, width, channels) interleaved samples, orientation applied."""

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless", "sunset_logo", "blendmodes", "grayscale_public_university", "spot", "delta_palette"]
 MODULAR_BENCH = ["srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
-VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise", "bike", "bench_oriented_brg", "grayscale_jpeg", "cafe"]
+VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise", "bike", "bench_oriented_brg", "grayscale_jpeg", "cafe", "grayscale"]
 VARDCT_BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl"]
 STAGES_F32 = ["lf", "hf_dequant", "idct", "jpeg_upsampled", "pre_filter", "gaborish", "epf", "upsampled", "patches", "splines", "noise", "rgb"]
 
@@ -211,6 +211,14 @@ def test_write_to_buffer_mixes_spot_colours(dec, oracle, dtype):
     want = oracle.OracleImage(data, threads=4).frame_to_buffer(0, dtype, 6)
     assert got.shape == want.shape == (600, 400, 4)
     assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    dec.release_frames()
+
+
+def test_original_icc_matches_oracle(dec, oracle):
+    """The product's host side reconstructs the embedded ICC profile (shared code path with the oracle)."""
+    data = fixture_bytes("spot", "input.jxl")
+    dec.decode(data)
+    assert dec.original_icc() == oracle.OracleImage(data, threads=2).original_icc() != b""
     dec.release_frames()
 
 

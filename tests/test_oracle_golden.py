@@ -181,6 +181,39 @@ def test_delta_palette_exact(oracle):
     assert np.array_equal(got, ref)
 
 
+# sha256 of the embedded profile ("original.icc" in the conformance suite's test.json files)
+ICC_SHA256 = {
+    "bench_oriented_brg": "6603ae12a4ac",
+    "cafe": "bef95ce5cdb1",
+    "grayscale": "3f62598dfd40",
+    "grayscale_jpeg": "78001f4bf342",
+    "patches_lossless": "3a10bcd8e4c3",
+    "spot": "ce0caee95061",
+}
+
+
+@pytest.mark.parametrize("name", sorted(ICC_SHA256))
+def test_embedded_icc_profiles_are_reconstructed_exactly(oracle, name):
+    """ICC stream decode (jxl-color/src/icc/decode.rs): header prediction, tag-list commands, shuffles and Nth-order
+    predictors - the reconstructed profiles hash to the conformance suite's `original.icc` digests."""
+    import hashlib
+    icc = oracle.OracleImage(fixture_bytes(name, "input.jxl"), threads=2).original_icc()
+    assert len(icc) >= 128 and icc[36:40] == b"acsp"
+    assert hashlib.sha256(icc).hexdigest().startswith(ICC_SHA256[name])
+
+
+def test_xyb_grayscale_with_icc_profile(oracle):
+    """XYB image tagged with a gray ICC profile whose curve is tabulated: no enum encoding describes it, so the
+    render target is gray sRGB (jxl-render/src/lib.rs:104-150) - gamut map, D65 luma row, sRGB curve, one channel."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("grayscale", "input.jxl"), threads=4)
+    planes, ncol, _ = img.frame(0)
+    assert planes.shape == (1, 200, 200) and ncol == 1
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("grayscale", "ref.png")))).astype(np.float32) / 255.0
+    assert np.abs(np.clip(planes[0], 0.0, 1.0) - ref).max() <= 0.004
+
+
 def test_animation_splines(oracle):
     """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
     points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
