@@ -1087,6 +1087,7 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
     JXLB_CHECK(!colour->second_stage && colour->gamma == 0.0f, kErrInvalidArg, "the fused filter kernel converts to sRGB-gamut targets only");
     p.col.second_stage = p.col.to_luma = 0;
     p.col.gamma = 0.0f;
+    p.col.pq_intensity_target = 0.0f;
   }
   begin_k("filters_fused");
   launch_filters_fused(in, out, p, stream_);
@@ -1257,6 +1258,7 @@ void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   for (int i = 0; i < 3; ++i) d.luminances[i] = p.luminances[i];
   for (int i = 0; i < 9; ++i) d.matrix2[i] = p.matrix2[i];
   d.gamma = p.gamma;
+  d.pq_intensity_target = p.pq_intensity_target;
   begin_k("xyb_to_rgb");
   launch_xyb_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
   end_k();

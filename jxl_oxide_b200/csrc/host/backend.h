@@ -111,6 +111,8 @@ struct ColorParams {  // XYB -> (linear) sRGB, jxl-color/src/{xyb.rs,ciexyz.rs:8
   float matrix2[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   bool to_luma = false;             // XyzToLuma: channel 0 := Y, one output channel
   float gamma = 0.0f;               // > 0: v <= 1e-7 ? 0 : fast_powf(v, gamma) (tf.rs:11-70; Gamma and DCI)
+  // PQ inverse EOTF (tf/pq.rs:126-142): linear 1.0 = `pq_intensity_target` nits; 0 = off
+  float pq_intensity_target = 0.0f;
 };
 
 class Backend {

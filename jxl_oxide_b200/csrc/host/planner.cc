@@ -783,7 +783,8 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     ColorParams cp;
     // colour conversion follows upsampling (render.rs:136-149), so it is fused only without it
     const bool want_colour = !upsampled && !colour_done && !lfg_.has_noise && !lfg_.has_patches && !lfg_.has_splines &&
-                             colour_params(ih_.xyb_encoded, colour.size(), &cp) && !cp.second_stage && cp.gamma == 0.0f;
+                             colour_params(ih_.xyb_encoded, colour.size(), &cp) && !cp.second_stage && cp.gamma == 0.0f &&
+                             cp.pq_intensity_target == 0.0f;
     if (be_.filters_colour_fused(v, rf, sigma_view, !vardct, want_colour ? &cp : nullptr)) {
       colour_done = want_colour;
       if (want_colour) be_.stage_marker("rgb", v, 3);
@@ -1118,10 +1119,12 @@ bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p)
   if (!linear_srgb_out) {
     JXLB_CHECK(ce.colour_space == ColourSpace::kRgb || ce.colour_space == ColourSpace::kGrey, kErrUnsupported,
                "unsupported output colour space");
-    JXLB_CHECK(ce.tf != TransferFunctionKind::kPq && ce.tf != TransferFunctionKind::kHlg, kErrUnsupported,
-               "PQ / HLG output transfer functions are not implemented");
+    // HLG needs libm's powf / ln on the device; its results would not be reproducible bit for bit
+    JXLB_CHECK(ce.tf != TransferFunctionKind::kHlg, kErrUnsupported, "the HLG output transfer function is not implemented");
   }
-  JXLB_CHECK(ih_.tone_mapping.intensity_target <= 255.0f || opt_.output_colour == 1, kErrUnsupported,
+  // an HDR target keeps the image's range (convert.rs:478-499: tone mapping only towards non-HDR targets)
+  const bool hdr_target = !linear_srgb_out && ce.tf == TransferFunctionKind::kPq;
+  JXLB_CHECK(ih_.tone_mapping.intensity_target <= 255.0f || opt_.output_colour == 1 || hdr_target, kErrUnsupported,
              "HDR tone mapping is outside the implemented hot path");
   const OpsinInverseMatrix& oim = ih_.opsin_inverse_matrix;
   for (int i = 0; i < 3; ++i) {
@@ -1136,6 +1139,7 @@ bool FramePlanner::colour_params(bool is_xyb, size_t num_colour, ColorParams* p)
     if (ce.tf == TransferFunctionKind::kGamma)  // convert.rs:972-989
       p->gamma = ce.gamma_inverted ? float(ce.gamma) / 1e7f : 1e7f / float(ce.gamma);
     if (ce.tf == TransferFunctionKind::kDci) p->gamma = 1.0f / 2.6f;
+    if (ce.tf == TransferFunctionKind::kPq) p->pq_intensity_target = ih_.tone_mapping.intensity_target;
     const bool grey = ce.colour_space == ColourSpace::kGrey;
     if (grey || ce.white_point != WhitePointKind::kD65 || ce.primaries != PrimariesKind::kSrgb) target_matrix(ce, grey, p);
   }

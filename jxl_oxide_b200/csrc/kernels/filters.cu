@@ -241,6 +241,21 @@ __global__ void ycbcr_to_rgb_kernel(DevView vcb, DevView vy, DevView vcr, DevYcb
   *pcr = __fmaf_rn(cb, p.cb_to_b, yy);
 }
 
+// linear_to_pq_generic (jxl-color/src/tf/pq.rs:126-142): fourth root, then a 4/4 rational polynomial (Horner, un-fused)
+__device__ __forceinline__ float pq_tf(float s, float y_mult) {
+  const float a = fabsf(s);
+  const float a_1_4 = __fsqrt_rn(__fsqrt_rn(fmul(a, y_mult)));
+  float yp, yq;
+  if (a < 1e-4f) {
+    yp = fadd(fmul(fadd(fmul(fadd(fmul(fadd(fmul(-2.864824e5f, a_1_4), 6.889862e4f), a_1_4), 1.352821e2f), a_1_4), 3.881234e-1f), a_1_4), 9.863406e-6f);
+    yq = fadd(fmul(fadd(fmul(fadd(fmul(fadd(fmul(-2.072546e5f, a_1_4), -4.389884e4f), a_1_4), 1.608477e4f), a_1_4), 1.477719e3f), a_1_4), 3.371868e1f);
+  } else {
+    yp = fadd(fmul(fadd(fmul(fadd(fmul(fadd(fmul(4.838434e1f, a_1_4), 1.492516e2f), a_1_4), 5.522776e1f), a_1_4), -1.095778f), a_1_4), 1.351392e-2f);
+    yq = fadd(fmul(fadd(fmul(fadd(fmul(fadd(fmul(2.590418e1f, a_1_4), 1.120607e2f), a_1_4), 9.26371e1f), a_1_4), 2.016708e1f), a_1_4), 1.012416f);
+  }
+  return copysignf(fdiv(yp, yq), s);
+}
+
 // apply_gamma's scalar tail (jxl-color/src/tf.rs:62-69): v <= 1e-7 ? 0 : fast_powf_generic(v, gamma)
 __device__ __forceinline__ float gamma_tf(float a, float gamma) {
   if (a <= 1e-7f) return 0.0f;
@@ -309,7 +324,12 @@ __global__ void xyb_to_rgb_kernel(DevView vx, DevView vy, DevView vb, DevColorPa
   float o1 = fadd(fadd(fmul(m[3], a), fmul(m[4], b)), fmul(m[5], c));
   float o2 = fadd(fadd(fmul(m[6], a), fmul(m[7], b)), fmul(m[8], c));
   if (p.second_stage) second_colour_stage(p, o0, o1, o2);
-  if (p.gamma > 0.0f) {
+  if (p.pq_intensity_target > 0.0f) {
+    const float y_mult = fdiv(p.pq_intensity_target, 10000.0f);
+    o0 = pq_tf(o0, y_mult);
+    o1 = pq_tf(o1, y_mult);
+    o2 = pq_tf(o2, y_mult);
+  } else if (p.gamma > 0.0f) {
     o0 = gamma_tf(o0, p.gamma);
     o1 = gamma_tf(o1, p.gamma);
     o2 = gamma_tf(o2, p.gamma);

@@ -167,6 +167,7 @@ struct DevColorParams {
   // non-sRGB targets (ColorParams::second_stage): gamut map, second matrix, optional XyzToLuma, gamma TF
   int second_stage, to_luma;
   float luminances[3], matrix2[9], gamma;
+  float pq_intensity_target;  // > 0: PQ inverse EOTF (tf/pq.rs:126-142)
 };
 void launch_xyb_to_rgb(DevView x, DevView y, DevView b, DevColorParams p, cudaStream_t stream);
 // YCbCr -> RGB in place, planes Cb, Y, Cr (jxl-color/src/ycbcr.rs:40-56)

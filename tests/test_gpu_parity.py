@@ -143,7 +143,7 @@ def test_synthetic_vardct_frames_bit_exact(dec, oracle, size, seed, extra):
     _check_vardct(dec, oracle, bench.synth_frame(size[0], size[1], seed, extra=extra))
 
 
-@pytest.mark.parametrize("colour", ["p3", "rec2020-gamma", "gray", "dci", "custom"])
+@pytest.mark.parametrize("colour", ["p3", "rec2020-gamma", "gray", "dci", "custom", "pq"])
 def test_enum_colour_targets_bit_exact(dec, oracle, colour):
     """Non-sRGB enum output encodings: gamut mapping, the merged target matrix, XyzToLuma and the gamma transfer
     function of xyb_to_rgb_kernel (convert.rs:397-466) against the oracle, stage by stage."""

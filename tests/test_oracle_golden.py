@@ -389,6 +389,14 @@ def test_enum_colour_targets_against_float64_colour_math(oracle):
         want = tf(np.einsum("ij,jhw->ihw", m, g))
         got = oracle.OracleImage(bench.synth_frame(600, 500, 5, extra=("--colour", name)), threads=4).frame(0)[0]
         assert got.shape == want.shape and np.abs(got - want).max() <= tol, name
+    # PQ (SMPTE ST 2084 inverse EOTF) on BT.2100 primaries, 1000-nit intensity target: an HDR target, no tone mapping
+    data = bench.synth_frame(600, 500, 5, extra=("--colour", "pq"))
+    hdr = oracle.OracleImage(data, output_colour=1, threads=4).frame(0)[0].astype(np.float64)
+    v = np.einsum("ij,jhw->ihw", np.linalg.inv(rgb2xyz(BT2100, D65)) @ to_xyz, gamut(hdr, to_xyz[1]))
+    y = np.abs(v) * 1000.0 / 10000.0
+    m1, m2, c1, c2, c3 = 2610 / 16384, 2523 / 4096 * 128, 3424 / 4096, 2413 / 4096 * 32, 2392 / 4096 * 32
+    want = np.sign(v) * ((c1 + c2 * y ** m1) / (1 + c3 * y ** m1)) ** m2
+    assert np.abs(oracle.OracleImage(data, threads=4).frame(0)[0] - want).max() <= 2e-6
     got = oracle.OracleImage(bench.synth_frame(600, 500, 5, extra=("--colour", "gray")), threads=4).frame(0)[0]
     assert got.shape == (1, 500, 600)
     assert np.abs(got[0] - srgb_oetf(np.einsum("ij,jhw->ihw", to_xyz, g))[1]).max() <= 2e-4

@@ -879,8 +879,15 @@ int main(int argc, char** argv) {
         else write_u32(cs, 3, 21, u - 2097152);
       }
     };
+    const bool pq = a.colour == "pq";
     cs.write(1, 0);  // all_default
-    cs.write(1, 0);  // extra_fields
+    cs.write(1, pq ? 1 : 0);  // extra_fields
+    if (pq) {
+      cs.write(3, 0);  // orientation 1
+      cs.write(1, 0);  // have_intrinsic_size
+      cs.write(1, 0);  // have_preview
+      cs.write(1, 0);  // have_animation
+    }
     cs.write(1, 0);  // integer samples
     cs.write(2, 0);  // 8 bits
     cs.write(1, 1);  // modular_16bit_buffers
@@ -895,7 +902,7 @@ int main(int argc, char** argv) {
     else write_enum(1);  // D65
     if (!grey) {
       if (a.colour == "p3" || a.colour == "dci") write_enum(11);
-      else if (a.colour == "rec2020-gamma") write_enum(9);
+      else if (a.colour == "rec2020-gamma" || pq) write_enum(9);
       else if (a.colour == "custom") write_enum(2), write_xy(0.64, 0.33), write_xy(0.21, 0.71), write_xy(0.15, 0.06);  // Adobe RGB-like
       else fprintf(stderr, "unknown --colour %s\n", a.colour.c_str()), exit(2);
     }
@@ -904,9 +911,16 @@ int main(int argc, char** argv) {
       cs.write(24, a.colour == "custom" ? 4545455 : 4166667);  // 1/2.2, 1/2.4
     } else {
       cs.write(1, 0);
-      write_enum(a.colour == "dci" ? 17 : 13);  // DCI / sRGB
+      write_enum(a.colour == "dci" ? 17 : (pq ? 16 : 13));  // DCI / PQ / sRGB
     }
     write_enum(1);   // rendering intent: relative
+    if (pq) {  // ToneMapping (color.rs:312-319): 1000 nits
+      cs.write(1, 0);        // all_default
+      cs.write(16, 0x63d0);  // intensity_target = 1000.0 (f16)
+      cs.write(16, 0);       // min_nits
+      cs.write(1, 0);        // relative_to_max_display
+      cs.write(16, 0);       // linear_below
+    }
     cs.write(2, 0);  // extensions
   }
   cs.write(1, 1);  // default_m
