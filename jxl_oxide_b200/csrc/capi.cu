@@ -372,7 +372,7 @@ int32_t jxlb_xyb_to_rgb(jxlb_decoder* dec, float* const planes[3], uint32_t widt
                         const float opsin_bias[3], const float inv_matrix[9], float intensity_target, int32_t srgb_tf) {
   if (!dec || !planes || !opsin_bias || !inv_matrix) return JXLB_ERR_INVALID_ARG;
   return guarded(dec, [&] {
-    DevColorParams p;
+    DevColorParams p{};  // sRGB-gamut target: no second stage, no gamma / PQ curve
     for (int i = 0; i < 3; ++i) {
       p.opsin_bias[i] = opsin_bias[i];
       p.cbrt_opsin_bias[i] = cbrtf(opsin_bias[i]);

@@ -1244,7 +1244,7 @@ void CudaBackend::ycbcr_to_rgb(const View v[3], const YcbcrParams& p) {
 }
 
 void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
-  DevColorParams d;
+  DevColorParams d{};
   for (int i = 0; i < 3; ++i) {
     d.opsin_bias[i] = p.opsin_bias[i];
     d.cbrt_opsin_bias[i] = p.cbrt_opsin_bias[i];
