@@ -20,7 +20,7 @@ CASES = {
     "minecraft_vardct_e7": ("decode/minecraft_vardct_e7", ["input.jxl"]),
     "opsin_inverse": ("conformance/testcases/opsin_inverse", ["input.jxl", "ref.png"]),
     "alpha_premultiplied": ("conformance/testcases/alpha_premultiplied", ["input.jxl"]),
-    "alpha_triangles": ("conformance/testcases/alpha_triangles", ["input.jxl"]),
+    "alpha_triangles": ("conformance/testcases/alpha_triangles", ["input.jxl", "ref.png"]),
     "bicycles": ("conformance/testcases/bicycles", ["input.jxl"]),
     "lz77_flower": ("conformance/testcases/lz77_flower", ["input.jxl", "ref.png"]),
     "upsampling": ("conformance/testcases/upsampling", ["input.jxl", "ref.png"]),
@@ -37,6 +37,9 @@ CASES = {
     "cafe": ("conformance/testcases/cafe", ["input.jxl"]),
     "spot": ("conformance/testcases/spot", ["input.jxl"]),
     "grayscale": ("conformance/testcases/grayscale", ["input.jxl", "ref.png"]),
+    "lossless_pfm": ("conformance/testcases/lossless_pfm", ["input.jxl"]),
+    "alpha_nonpremultiplied": ("conformance/testcases/alpha_nonpremultiplied", ["input.jxl", "ref.png"]),
+    "animation_newtons_cradle": ("conformance/testcases/animation_newtons_cradle", ["input.jxl"]),
     "delta_palette": ("conformance/testcases/delta_palette", ["input.jxl"]),
 }
 BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl", "srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
@@ -67,6 +70,22 @@ Image.open(os.path.join(REF, "conformance/testcases/spot/ref.png")).crop((150, 5
     os.path.join(HERE, "spot", "ref_crop_150_50.png"), optimize=True)
 Image.open(os.path.join(REF, "conformance/testcases/delta_palette/ref.png")).crop((100, 200, 400, 500)).save(
     os.path.join(HERE, "delta_palette", "ref_crop_100_200.png"), optimize=True)
+# lossless_pfm: the float reference (3 MB) is kept as the digest of its top-down interleaved little-endian f32 samples
+import hashlib
+import numpy as np
+_raw = open(os.path.join(REF, "conformance/testcases/lossless_pfm/ref.pfm"), "rb").read().split(b"\n", 3)
+_w, _h = map(int, _raw[1].split())
+_pix = np.frombuffer(_raw[3], dtype="<f4" if float(_raw[2]) < 0 else ">f4").reshape(_h, _w, 3)[::-1]
+with open(os.path.join(HERE, "lossless_pfm", "ref_f32_sha256.txt"), "w") as _f:
+    _f.write(hashlib.sha256(np.ascontiguousarray(_pix, dtype="<f4").tobytes()).hexdigest() + "\n")
+Image.open(os.path.join(REF, "conformance/testcases/bicycles/ref.png")).crop((300, 100, 812, 612)).save(
+    os.path.join(HERE, "bicycles", "ref_crop_300_100.png"), optimize=True)
+Image.open(os.path.join(REF, "conformance/testcases/alpha_premultiplied/ref.png")).crop((256, 256, 768, 768)).save(
+    os.path.join(HERE, "alpha_premultiplied", "ref_crop_256_256.png"), optimize=True)
+_g = Image.open(os.path.join(REF, "conformance/testcases/animation_newtons_cradle/ref.gif"))
+for _k in (0, 10):
+    _g.seek(_k)
+    _g.convert("RGBA").save(os.path.join(HERE, "animation_newtons_cradle", "ref_frame_%02d.png" % _k), optimize=True)
 # three frames of the animation's reference APNG
 _ap = Image.open(os.path.join(REF, "conformance/testcases/animation_icos4d/ref.apng"))
 for _k in (0, 17, 47):

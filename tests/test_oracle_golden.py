@@ -214,6 +214,52 @@ def test_xyb_grayscale_with_icc_profile(oracle):
     assert np.abs(np.clip(planes[0], 0.0, 1.0) - ref).max() <= 0.004
 
 
+def test_lossless_float_samples_exact(oracle):
+    """32-bit float Modular image (jxl-image/src/lib.rs:464-488 sample reinterpretation): every sample equals the
+    conformance suite's ref.pfm bit for bit (values span -2 .. 1.99)."""
+    import hashlib
+    planes = oracle.OracleImage(fixture_bytes("lossless_pfm", "input.jxl"), threads=4).frame(0)[0]
+    assert planes.shape == (3, 500, 500)
+    digest = hashlib.sha256(np.ascontiguousarray(np.moveaxis(planes, 0, 2), dtype="<f4").tobytes()).hexdigest()
+    assert digest == fixture_bytes("lossless_pfm", "ref_f32_sha256.txt").decode().strip()
+
+
+def test_alpha_images_against_libjxl_renderings(oracle):
+    """Straight and premultiplied alpha (ExtraChannelInfo::alpha_associated), 8 and 16 bit, Modular and VarDCT."""
+    from PIL import Image
+    import io
+
+    def png(*parts):
+        return np.asarray(Image.open(io.BytesIO(fixture_bytes(*parts)))).astype(np.float32) / 255.0
+
+    for name in ("alpha_triangles", "alpha_nonpremultiplied"):
+        buf = np.clip(oracle.OracleImage(fixture_bytes(name, "input.jxl"), threads=4).frame_to_buffer(0, np.float32, 0), 0, 1)
+        assert np.abs(buf - png(name, "ref.png")).max() <= 0.004, name
+    # the PNG holds straight alpha, the decoder (like jxl-oxide) leaves the colours premultiplied
+    buf = oracle.OracleImage(fixture_bytes("alpha_premultiplied", "input.jxl"), threads=4).frame_to_buffer(0, np.float32, 0)[256:768, 256:768]
+    ref = png("alpha_premultiplied", "ref_crop_256_256.png")
+    assert np.abs(buf[..., 3] - ref[..., 3]).max() <= 0.004
+    opaque = buf[..., 3] > 0.05
+    straight = np.clip(buf[..., :3] / np.maximum(buf[..., 3:4], 1e-6), 0, 1)
+    assert np.abs(straight - ref[..., :3])[opaque].max() <= 0.004
+    buf = np.clip(oracle.OracleImage(fixture_bytes("bicycles", "input.jxl"), threads=4).frame_to_buffer(0, np.float32, 0), 0, 1)
+    assert np.abs(buf[100:612, 300:812] - png("bicycles", "ref_crop_300_100.png")).max() <= 0.004
+
+
+def test_palette_animation_newtons_cradle(oracle):
+    """36-frame Modular animation transcoded from a GIF (palette + blending over the previous canvas): the first frame
+    equals the GIF's exactly; a later one everywhere except the handful of pixels where PIL composes transparent GIF
+    pixels differently."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("animation_newtons_cradle", "input.jxl"), threads=4)
+    assert img.num_frames == 36
+    for k, tol in ((0, 0.0), (10, 0.01)):
+        ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("animation_newtons_cradle", "ref_frame_%02d.png" % k)))).astype(np.float32) / 255.0
+        got = np.moveaxis(np.clip(img.frame(k)[0], 0, 1), 0, 2)
+        assert (np.abs(got - ref).max(axis=2) > 0.004).mean() <= tol, k
+
+
 def test_animation_splines(oracle):
     """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
     points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
