@@ -35,6 +35,7 @@ CASES = {
     "bench_oriented_brg": ("conformance/testcases/bench_oriented_brg", ["input.jxl", "ref.png"]),
     "grayscale_jpeg": ("conformance/testcases/grayscale_jpeg", ["input.jxl"]),
     "cafe": ("conformance/testcases/cafe", ["input.jxl"]),
+    "issue_425": ("decode/issue_425", ["input.jxl", "ref.jpg"]),
     "spot": ("conformance/testcases/spot", ["input.jxl"]),
     "grayscale": ("conformance/testcases/grayscale", ["input.jxl", "ref.png"]),
     "lossless_pfm": ("conformance/testcases/lossless_pfm", ["input.jxl"]),

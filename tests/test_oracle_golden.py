@@ -260,6 +260,19 @@ def test_palette_animation_newtons_cradle(oracle):
         assert (np.abs(got - ref).max(axis=2) > 0.004).mean() <= tol, k
 
 
+def test_jpeg_transcode_odd_block_count(oracle):
+    """228 x 256 4:2:0 transcode (the reference's issue_425): 28.5 luma blocks per row, so the block grid is rounded
+    up to an even count (hf_metadata.rs:70-80) and the chroma edge sample is replicated. The source JPEG decoded by
+    libjpeg agrees to within the two decoders' IDCT / upsampling differences."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("issue_425", "input.jxl"), threads=4)
+    buf = np.clip(img.frame_to_buffer(0, np.float32, 0), 0, 1)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("issue_425", "ref.jpg"))).convert("RGB")).astype(np.float32) / 255.0
+    assert buf.shape == ref.shape == (256, 228, 3)
+    assert np.abs(buf - ref).max() <= 0.02 and np.sqrt(((buf - ref) ** 2).mean()) <= 0.004
+
+
 def test_animation_splines(oracle):
     """60 frames whose only content is splines drawn over a flat background (features/spline.rs): quantised control
     points, Catmull-Rom upsampling, unit arc sampling and the erf splat, against three frames of the reference APNG."""
