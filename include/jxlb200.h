@@ -141,6 +141,12 @@ int32_t jxlb_xyb_to_rgb(jxlb_decoder* dec, float* const planes[3], uint32_t widt
 int32_t jxlb_squeeze_inverse(jxlb_decoder* dec, const int32_t* avg, uint32_t avg_w, uint32_t avg_h, uint32_t avg_stride,
                              const int32_t* res, uint32_t res_w, uint32_t res_h, uint32_t res_stride, int32_t* out,
                              uint32_t out_stride, int32_t horizontal);
+/* blend_single (crates/jxl-render/src/blend.rs:550-727) on one rectangle, in place on `base`: mode 1 Replace, 2 Add,
+ * 3 Mul, 4 Blend, 5 MulAdd, 6 MixAlpha; `swapped` gives the patch the base role (the *Below patch modes). The alpha
+ * planes (device pointers, same stride) may be null (read as 0). */
+int32_t jxlb_blend(jxlb_decoder* dec, float* base, const float* patch, const float* base_alpha, const float* new_alpha,
+                   uint32_t width, uint32_t height, uint32_t stride, int32_t mode, int32_t clamp, int32_t premultiplied,
+                   int32_t swapped);
 /* rct::inverse_rct (crates/jxl-modular/src/transform/rct.rs:15). In place on three planes. */
 int32_t jxlb_rct_inverse(jxlb_decoder* dec, int32_t* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
                          uint32_t rct_type);

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
     "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_stage_count", "jxlb_stage_get",
-    "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse",
+    "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse", "jxlb_blend",
 ]
 
 
@@ -111,6 +111,7 @@ def load_library():
     L.jxlb_timeline_get.argtypes = [vp, i32, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     L.jxlb_stage_count.argtypes = [vp, ctypes.c_char_p]
     L.jxlb_stage_get.argtypes = [vp, ctypes.c_char_p, i32, ctypes.POINTER(u32), ctypes.POINTER(u32), vp]
+    L.jxlb_blend.argtypes = [vp, vp, vp, vp, vp, u32, u32, u32, i32, i32, i32, i32]
     L.jxlb_gaborish.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, ctypes.POINTER(ctypes.c_float)]
     L.jxlb_epf.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, vp, u32, ctypes.POINTER(EpfParams)]
     L.jxlb_xyb_to_rgb.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, ctypes.POINTER(ctypes.c_float),
@@ -276,6 +277,13 @@ class Decoder:
         self._check(self._L.jxlb_squeeze_inverse(self._h, int(avg.data_ptr()), avg.shape[1], avg.shape[0], avg.stride(0),
                                                  int(res.data_ptr()), res.shape[1], res.shape[0], max(res.stride(0), 1),
                                                  int(out.data_ptr()), out.stride(0), int(horizontal)))
+
+    def blend(self, base, patch, base_alpha, new_alpha, mode, clamp=False, premultiplied=False, swapped=False):
+        """blend_single on equally shaped device tensors, in place on `base` (alpha tensors may be None)."""
+        h, w = base.shape
+        ptr = lambda t: int(t.data_ptr()) if t is not None else None
+        self._check(self._L.jxlb_blend(self._h, ptr(base), ptr(patch), ptr(base_alpha), ptr(new_alpha), w, h, base.stride(0),
+                                       int(mode), int(clamp), int(premultiplied), int(swapped)))
 
     def rct_inverse(self, planes, rct_type):
         h, w = planes[0].shape

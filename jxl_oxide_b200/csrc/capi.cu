@@ -410,4 +410,15 @@ int32_t jxlb_rct_inverse(jxlb_decoder* dec, int32_t* const planes[3], uint32_t w
   });
 }
 
+int32_t jxlb_blend(jxlb_decoder* dec, float* base, const float* patch, const float* base_alpha, const float* new_alpha,
+                   uint32_t width, uint32_t height, uint32_t stride, int32_t mode, int32_t clamp, int32_t premultiplied,
+                   int32_t swapped) {
+  if (!dec || !base || !patch || mode < 1 || mode > 6) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    const DevPatchJob j{patch, base, base_alpha, new_alpha, stride, stride, stride, stride, width, height, uint32_t(mode),
+                        clamp ? 1u : 0u, premultiplied ? 1u : 0u, swapped ? 1u : 0u};
+    dec->be->blend_raw(j);
+  });
+}
+
 }  // extern "C"

@@ -715,8 +715,8 @@ void CudaBackend::rct_inverse(const View v[3], uint32_t rct_type) {
 
 void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t,
                                   const WpHeader& wph, uint32_t bit_depth) {
-  JXLB_CHECK(targets.size() <= 4, kErrUnsupported, "palettes with more than 4 channels are not implemented on the device");
-  DevView tv[4];
+  JXLB_CHECK(targets.size() <= size_t(kMaxPaletteChannels), kErrUnsupported, "palettes with more than 16 channels are not implemented on the device");
+  DevView tv[kMaxPaletteChannels];
   for (size_t i = 0; i < targets.size(); ++i) tv[i] = dev_view(targets[i]);
   const uint32_t w = targets[0].w, h = targets[0].h;
   int* d_status = static_cast<int*>(dmalloc(4));
@@ -1132,10 +1132,19 @@ void CudaBackend::blend_patches(const std::vector<PatchJob>& jobs) {
     DevView s = dev_view(j.src), d = dev_view(j.dst), ba = dev_view(j.base_alpha), na = dev_view(j.new_alpha);
     batch.push_back({static_cast<const float*>(s.ptr), static_cast<float*>(d.ptr), static_cast<const float*>(ba.ptr),
                      static_cast<const float*>(na.ptr), s.stride, d.stride, ba.stride, na.stride, j.dst.w, j.dst.h, j.mode,
-                     j.clamp ? 1u : 0u, j.premultiplied ? 1u : 0u});
+                     j.clamp ? 1u : 0u, j.premultiplied ? 1u : 0u, j.swapped ? 1u : 0u});
     members.push_back(&j);
   }
   flush();
+}
+
+void CudaBackend::blend_raw(const DevPatchJob& job) {
+  const DevPatchJob* d = static_cast<const DevPatchJob*>(upload_temp(&job, sizeof(job)));
+  begin_k("blend_patches");
+  launch_blend_patches(d, 1, stream_);
+  end_k();
+  sync();
+  release_temps();
 }
 
 void CudaBackend::splat_splines(const View v[3], const std::vector<SplineArc>& arcs) {

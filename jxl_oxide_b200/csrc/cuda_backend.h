@@ -43,6 +43,7 @@ class CudaBackend : public Backend {
   int upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) override;
   int upsample_jpeg(const View& v, bool horizontal, bool vertical, uint32_t out_w, uint32_t out_h) override;
   void blend_patches(const std::vector<PatchJob>& jobs) override;
+  void blend_raw(const DevPatchJob& job);  // one rectangle on caller-owned device memory (jxlb_blend)
   void splat_splines(const View v[3], const std::vector<SplineArc>& arcs) override;
   void add_noise(const View v[3], const float lut[8], uint32_t group_dim, uint64_t seed0, float corr_x, float corr_b) override;
   void xyb_to_rgb(const View v[3], const ColorParams& p) override;

@@ -162,6 +162,7 @@ class Backend {
     uint32_t mode;
     bool clamp;
     bool premultiplied = false;
+    bool swapped = false;  // patch modes BlendBelow / MulAddBelow: the patch goes under the frame (blend.rs:119-152)
     View base_alpha, new_alpha;
   };
   virtual void blend_patches(const std::vector<PatchJob>& jobs) = 0;

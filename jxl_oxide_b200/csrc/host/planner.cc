@@ -835,7 +835,22 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
         for (size_t idx = 0; idx < all.size(); ++idx) {  // blend.rs:418-545
           const PatchBlending& b = idx < colour.size() ? t.blending[0] : t.blending[1 + idx - colour.size()];
           if (b.mode == 0) continue;
-          JXLB_CHECK(b.mode <= 3, kErrUnsupported, "alpha-weighted patch blend modes are not implemented");
+          // BlendParams::from_patch_blending_info (blend.rs:104-163)
+          uint32_t job_mode = b.mode;
+          bool with_alpha = false, swapped = false;
+          const size_t alpha_view = colour.size() + b.alpha_channel;
+          if (b.mode >= 4) {
+            JXLB_CHECK(alpha_view < all.size(), kErrBitstream, "patch blending refers to a missing alpha channel");
+            swapped = b.mode == 5 || b.mode == 7;
+            const bool is_alpha = idx == alpha_view;
+            if (b.mode <= 5) {  // BlendAbove / BlendBelow
+              job_mode = is_alpha ? 6 : 4;
+            } else {  // MulAddAbove / MulAddBelow: the alpha channel itself is replaced (below) or kept (above)
+              if (is_alpha && !swapped) continue;
+              job_mode = is_alpha ? 1 : 5;
+            }
+            with_alpha = !is_alpha;
+          }
           // target rectangle clipped to the frame, then the matching reference rectangle clipped to the reference
           const int64_t fw = all[idx].w, fhh = all[idx].h;
           const int64_t tl = std::max<int64_t>(t.x, 0), tt = std::max<int64_t>(t.y, 0);
@@ -850,8 +865,16 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
           Backend::PatchJob j;
           j.src = View{rv.plane, rv.x0 + uint32_t(rl), rv.y0 + uint32_t(rt), uint32_t(rr - rl), uint32_t(rb - rt)};
           j.dst = View{dv.plane, dv.x0 + uint32_t(tl), dv.y0 + uint32_t(tt), uint32_t(rr - rl), uint32_t(rb - rt)};
-          j.mode = b.mode;
+          j.mode = job_mode;
           j.clamp = b.clamp;
+          j.swapped = swapped && job_mode != 1;
+          if (with_alpha) {  // the frame's and the reference's alpha over the same rectangles (blend.rs:470-505)
+            const View& fa = all[alpha_view];
+            const View& ra = ref.channels[alpha_view];
+            j.base_alpha = View{fa.plane, fa.x0 + uint32_t(tl), fa.y0 + uint32_t(tt), j.dst.w, j.dst.h};
+            j.new_alpha = View{ra.plane, ra.x0 + uint32_t(rl), ra.y0 + uint32_t(rt), j.dst.w, j.dst.h};
+            j.premultiplied = ih_.ec_info[b.alpha_channel].alpha_associated;
+          }
           jobs.push_back(j);
         }
     }

@@ -437,24 +437,32 @@ __global__ void blend_patches_kernel(const DevPatchJob* __restrict__ jobs) {
       if (j.clamp) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
       r = fmul(base, v);
     } else if (j.mode == 4) {
-      const float base_alpha = j.base_alpha ? j.base_alpha[size_t(y) * j.base_alpha_stride + x] : 0.0f;
-      float new_alpha = j.new_alpha ? j.new_alpha[size_t(y) * j.new_alpha_stride + x] : 0.0f;
+      const float frame_alpha = j.base_alpha ? j.base_alpha[size_t(y) * j.base_alpha_stride + x] : 0.0f;
+      const float patch_alpha = j.new_alpha ? j.new_alpha[size_t(y) * j.new_alpha_stride + x] : 0.0f;
+      const float base_sample = j.swapped ? v : base, new_sample = j.swapped ? base : v;
+      const float base_alpha = j.swapped ? patch_alpha : frame_alpha;
+      float new_alpha = j.swapped ? frame_alpha : patch_alpha;
       if (j.clamp) new_alpha = new_alpha < 0.0f ? 0.0f : (new_alpha > 1.0f ? 1.0f : new_alpha);
       if (j.premultiplied) {
-        r = fadd(v, fmul(base, fsub(1.0f, new_alpha)));
+        r = fadd(new_sample, fmul(base_sample, fsub(1.0f, new_alpha)));
       } else {
         const float base_alpha_rev = fsub(1.0f, base_alpha), new_alpha_rev = fsub(1.0f, new_alpha);
         const float mixed_alpha = fsub(1.0f, fmul(new_alpha_rev, base_alpha_rev));
         const float mixed_alpha_recip = mixed_alpha > 0.0f ? fdiv(1.0f, mixed_alpha) : 0.0f;
-        r = fmul(fadd(fmul(new_alpha, v), fmul(fmul(base_alpha, base), new_alpha_rev)), mixed_alpha_recip);
+        r = fmul(fadd(fmul(new_alpha, new_sample), fmul(fmul(base_alpha, base_sample), new_alpha_rev)), mixed_alpha_recip);
       }
     } else if (j.mode == 5) {
-      float new_alpha = j.new_alpha ? j.new_alpha[size_t(y) * j.new_alpha_stride + x] : 0.0f;
+      const float base_sample = j.swapped ? v : base, new_sample = j.swapped ? base : v;
+      float new_alpha;
+      if (j.swapped) new_alpha = j.base_alpha ? j.base_alpha[size_t(y) * j.base_alpha_stride + x] : 0.0f;
+      else new_alpha = j.new_alpha ? j.new_alpha[size_t(y) * j.new_alpha_stride + x] : 0.0f;
       if (j.clamp) new_alpha = new_alpha < 0.0f ? 0.0f : (new_alpha > 1.0f ? 1.0f : new_alpha);
-      r = fadd(base, fmul(new_alpha, v));
+      r = fadd(base_sample, fmul(new_alpha, new_sample));
     } else {
-      if (j.clamp) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
-      r = fadd(base, fmul(v, fsub(1.0f, base)));
+      const float b0 = j.swapped ? v : base;
+      float n0 = j.swapped ? base : v;
+      if (j.clamp) n0 = n0 < 0.0f ? 0.0f : (n0 > 1.0f ? 1.0f : n0);
+      r = fadd(b0, fmul(n0, fsub(1.0f, b0)));
     }
     *d = r;
   }

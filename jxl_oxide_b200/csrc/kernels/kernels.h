@@ -61,8 +61,9 @@ void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizont
 void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cudaStream_t stream);
 // Second pass of a delta palette (palette.rs:120-152): every channel is scanned in raster order and the samples marked
 // in `mask` get `d_pred`'s prediction (from already final neighbours) added - a serial recurrence per channel.
+constexpr int kMaxPaletteChannels = 16;  // colour + extra channels one palette transform may cover on the device
 struct DevPaletteDeltaParams {
-  DevView target[4];
+  DevView target[kMaxPaletteChannels];
   const uint8_t* mask;  // width x height, 1 = add the prediction
   uint32_t d_pred;
   uint32_t wp[11];      // WpHeader p1, p2, p3a..p3e, w0..w3 (d_pred == 6)
@@ -204,6 +205,7 @@ struct DevPatchJob {
   const float* base_alpha;  // nullptr: 0.0
   const float* new_alpha;   // nullptr: 0.0
   uint32_t src_stride, dst_stride, base_alpha_stride, new_alpha_stride, w, h, mode, clamp, premultiplied;
+  uint32_t swapped;  // the patch sample takes the base role (BlendBelow / MulAddBelow, blend.rs:119-152)
 };
 void launch_blend_patches(const DevPatchJob* jobs, int num_jobs, cudaStream_t stream);
 // Spline splatting (jxl-render/src/features/spline.rs:218-252): one thread per pixel walks the arc list in order.

@@ -108,7 +108,7 @@ __global__ void rct_kernel(DevView va, DevView vb, DevView vc, uint32_t rct_type
 }
 
 struct PaletteTargets {
-  DevView v[4];
+  DevView v[kMaxPaletteChannels];
 };
 __constant__ int16_t kDeltaPalette[72][3] = {
 #include "../host/delta_palette.inc"
@@ -220,7 +220,7 @@ void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cuda
 void launch_palette_inverse(DevView palette, const DevView* targets, int num_c, int nb_colours, int bit_depth, int nb_deltas,
                             uint8_t* mask, int* status, cudaStream_t stream) {
   PaletteTargets t;
-  for (int i = 0; i < num_c && i < 4; ++i) t.v[i] = targets[i];
+  for (int i = 0; i < num_c && i < kMaxPaletteChannels; ++i) t.v[i] = targets[i];
   if (!t.v[0].w || !t.v[0].h) return;
   palette_kernel<<<grid2d(t.v[0].w, t.v[0].h), 128, 0, stream>>>(palette, t, num_c, nb_colours, bit_depth, nb_deltas, mask, status);
 }

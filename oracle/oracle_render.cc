@@ -388,28 +388,32 @@ void OracleBackend::blend_patches(const std::vector<PatchJob>& jobs) {
             d[x] = d[x] * v;
             break;
           case 4: {  // blend.rs:607-660
-            const float base_sample = d[x], base_alpha = ba ? ba[x] : 0.0f;
-            float new_alpha = na ? na[x] : 0.0f;
+            const float frame_alpha = ba ? ba[x] : 0.0f, patch_alpha = na ? na[x] : 0.0f;
+            const float base_sample = j.swapped ? v : d[x], new_sample = j.swapped ? d[x] : v;
+            const float base_alpha = j.swapped ? patch_alpha : frame_alpha;
+            float new_alpha = j.swapped ? frame_alpha : patch_alpha;
             if (j.clamp) new_alpha = clamp01(new_alpha);
             if (j.premultiplied) {
-              d[x] = v + base_sample * (1.0f - new_alpha);
+              d[x] = new_sample + base_sample * (1.0f - new_alpha);
             } else {
               const float base_alpha_rev = 1.0f - base_alpha, new_alpha_rev = 1.0f - new_alpha;
               const float mixed_alpha = 1.0f - new_alpha_rev * base_alpha_rev;
               const float mixed_alpha_recip = mixed_alpha > 0.0f ? 1.0f / mixed_alpha : 0.0f;
-              d[x] = (new_alpha * v + base_alpha * base_sample * new_alpha_rev) * mixed_alpha_recip;
+              d[x] = (new_alpha * new_sample + base_alpha * base_sample * new_alpha_rev) * mixed_alpha_recip;
             }
             break;
           }
           case 5: {  // blend.rs:662-700
-            float new_alpha = na ? na[x] : 0.0f;
+            const float base_sample = j.swapped ? v : d[x], new_sample = j.swapped ? d[x] : v;
+            float new_alpha = j.swapped ? (ba ? ba[x] : 0.0f) : (na ? na[x] : 0.0f);
             if (j.clamp) new_alpha = clamp01(new_alpha);
-            d[x] = d[x] + new_alpha * v;
+            d[x] = base_sample + new_alpha * new_sample;
             break;
           }
           default: {  // 6, MixAlpha: blend.rs:702-723
-            if (j.clamp) v = clamp01(v);
-            d[x] = d[x] + v * (1.0f - d[x]);
+            float base = j.swapped ? v : d[x], nw = j.swapped ? d[x] : v;
+            if (j.clamp) nw = clamp01(nw);
+            d[x] = base + nw * (1.0f - base);
             break;
           }
         }

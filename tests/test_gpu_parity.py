@@ -222,6 +222,40 @@ def test_original_icc_matches_oracle(dec, oracle):
     dec.release_frames()
 
 
+def test_blend_modes_and_swapped_patch_roles(dec):
+    """blend_single (blend.rs:550-727) incl. the *Below patch modes: the kernel against the formulas in f32 numpy
+    (each expression is a chain of single IEEE operations, so numpy reproduces it bit for bit)."""
+    import itertools
+    import torch
+    rng = np.random.default_rng(3)
+    shape = (33, 47)
+    f32 = np.float32
+    base0, patch, ba, na = [rng.uniform(-0.2, 1.2, size=shape).astype(f32) for _ in range(4)]
+    one = f32(1.0)
+    for mode, clamp, premultiplied, swapped in itertools.product((4, 5, 6), (False, True), (False, True), (False, True)):
+        t = [torch.from_numpy(x.copy()).cuda() for x in (base0, patch, ba, na)]
+        dec.blend(t[0], t[1], t[2], t[3], mode, clamp, premultiplied, swapped)
+        dec.sync()
+        got = t[0].cpu().numpy()
+        b, n = (patch, base0) if swapped else (base0, patch)
+        if mode == 6:
+            nn = np.clip(n, 0, 1).astype(f32) if clamp else n
+            want = b + nn * (one - b)
+        else:
+            b_a, n_a = (na, ba) if swapped else (ba, na)
+            n_a = np.clip(n_a, 0, 1).astype(f32) if clamp else n_a
+            if mode == 5:
+                want = b + n_a * n
+            elif premultiplied:
+                want = n + b * (one - n_a)
+            else:
+                mixed = one - (one - n_a) * (one - b_a)
+                with np.errstate(divide="ignore"):
+                    recip = np.where(mixed > 0, one / mixed, f32(0)).astype(f32)
+                want = (n_a * n + b_a * b * (one - n_a)) * recip
+        assert np.array_equal(got.view(np.uint32), want.astype(f32).view(np.uint32)), (mode, clamp, premultiplied, swapped)
+
+
 def test_mutated_streams_end_in_values(dec):
     """Bit flips / truncations / overwritten runs in valid streams: every decode ends in pixels or a
     JxlError value, and the decoder keeps working (tools/mutate_check.py runs the same under
