@@ -1223,7 +1223,6 @@ int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader
     w *= k;
     h *= k;
   };
-  JXLB_CHECK(v.w >= 2 && v.h >= 2, kErrUnsupported, "upsampling of images narrower than 2 samples is not implemented");
   for (uint32_t i = 0; i < factor_log2 / 3; ++i) pass(8, ih.up8_weight);
   if (factor_log2 % 3 == 1) pass(2, ih.up2_weight);
   if (factor_log2 % 3 == 2) pass(4, ih.up4_weight);

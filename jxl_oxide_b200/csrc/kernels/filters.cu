@@ -362,12 +362,16 @@ __global__ void upsample_kernel(DevView in, DevView out, int k, const float* __r
 #pragma unroll
   for (int iy = 0; iy < 5; ++iy) {
     const int ky = flip_v ? 4 - iy : iy;
-    const int sy = mirror(ref_y + iy - 2, gh);
+    // One-sample-wide / -high images: the reference fills its padding in place (util.rs:423-454), which leaves
+    // zeros two samples to the left and right of a single column and two rows above a single row.
+    const int sy = gh == 1 ? 0 : mirror(ref_y + iy - 2, gh);
+    const bool zero_row = gh == 1 && iy == 0;
 #pragma unroll
     for (int ix = 0; ix < 5; ++ix) {
       const int kx = flip_h ? 4 - ix : ix;
-      const int sx = mirror(ref_x + ix - 2, gw);
-      const float sample = src[size_t(sy) * in.stride + sx];
+      const int sx = gw == 1 ? 0 : mirror(ref_x + ix - 2, gw);
+      const bool zero = zero_row || (gw == 1 && (ix == 0 || ix == 4));
+      const float sample = zero ? 0.0f : src[size_t(sy) * in.stride + sx];
       sum = fadd(sum, fmul(__ldg(kernel + ky * 5 + kx), sample));
       mn = fminf(mn, sample);
       mx = fmaxf(mx, sample);

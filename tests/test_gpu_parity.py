@@ -171,17 +171,25 @@ def test_fuzz_findings_are_clean_errors_on_device(dec, oracle):
     assert len(files) >= 60
     for f in files:
         data = open(f, "rb").read()
-        want = None
+        want = want_px = got_px = None
         try:
-            oracle.OracleImage(data, threads=2).close()
+            img = oracle.OracleImage(data, threads=2)
+            if img.num_frames:
+                want_px = img.frame(0)[0]
+            img.close()
         except oracle.OracleError as e:
             want = e.code
         got = None
         try:
             dec.decode(data)
+            if dec.num_frames():
+                got_px = dec.frame_planar(0)
             dec.release_frames()
         except jxl_oxide_b200.JxlError as e:
             got = e.code
+        if want_px is not None and got_px is not None:  # both decode: the same pixels, bit for bit
+            assert got_px.shape == want_px.shape, os.path.basename(f)
+            assert np.array_equal(got_px.view(np.uint32), want_px.view(np.uint32)), os.path.basename(f)
         # device-side detection reports DEVICE_DECODE (6) where the host oracle says BITSTREAM (1)
         norm = {6: 1}
         assert norm.get(got, got) == norm.get(want, want), (os.path.basename(f), got, want)
