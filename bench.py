@@ -156,21 +156,25 @@ def run_ours(args, rank, world, local_rank):
     pinned = [torch.empty((3, h, w), dtype=torch.float32).pin_memory() for _ in range(nthreads)]
     pinned_np = [p.numpy() for p in pinned]
 
-    def step(e2e):
+    def step(e2e, nsteps=1):
+        """`nsteps` passes over the batch. Every context walks its share of the batch `nsteps` times; contexts are
+        joined only at the end, so consecutive steps pipeline (no barrier between steps, one on each side of the
+        timed region) when --pipeline-steps asks for it; by default one step per call."""
         errs = []
 
         def work(d, idxs, out, delay):
             try:
                 if delay > 0.0:
                     time.sleep(delay)  # de-phase the contexts (inside the timed region)
-                for k in idxs:
-                    if e2e:
-                        d.decode(frames[k])          # host bytes in
-                        d.frame_to_host(0, out)      # planar f32 out (pinned host)
-                    else:
-                        d.decode_slot(k)
-                        d.sync()
-                    d.release_frames()
+                for _ in range(nsteps):
+                    for k in idxs:
+                        if e2e:
+                            d.decode(frames[k])          # host bytes in
+                            d.frame_to_host(0, out)      # planar f32 out (pinned host)
+                        else:
+                            d.decode_slot(k)
+                            d.sync()
+                        d.release_frames()
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
         ts = [threading.Thread(target=work, args=(d, idxs, o, (i % args.stagger_groups) * args.stagger_ms / 1e3))
@@ -197,8 +201,11 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            step(e2e)
+        if args.pipeline_steps:
+            step(e2e, steps)
+        else:
+            for _ in range(steps):
+                step(e2e)
         torch.cuda.synchronize()
         e1.record()
         e1.synchronize()
@@ -298,7 +305,10 @@ def run_ours(args, rank, world, local_rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if "synth" in args.workload else "real-file mosaic",
         "config": {"workload": desc, "frames_per_step_per_gpu": len(frames), "decoder_contexts_per_gpu": nthreads,
-                   "cache": "inputs+planes per step (>= 33 MP x 24 B) exceed L2 (126 MB); no explicit L2 flush"},
+                   "cache": "inputs+planes per step (>= 33 MP x 24 B) exceed L2 (126 MB); no explicit L2 flush",
+                   "step_barrier": "before and after the K timed steps (steps pipeline across decoder contexts)"
+                                   if args.pipeline_steps else "after every step",
+                   "stagger_ms": args.stagger_ms},
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
                 "d2h_bytes_per_step": int(px_per_frame * 12 * len(frames)), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "pipeline_roofline": pipeline,
@@ -364,6 +374,9 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--stagger-ms", type=float, default=0.0, help="start offset between context groups within a step")
     ap.add_argument("--stagger-groups", type=int, default=4)
+    ap.add_argument("--pipeline-steps", action="store_true",
+                    help="run the K timed steps back to back, contexts joined only at the end (default: joined after every "
+                         "step - measured faster, profiles/r01_progress.md)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
