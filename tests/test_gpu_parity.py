@@ -271,7 +271,7 @@ def test_mutated_streams_end_in_values(dec):
     import random
     import jxl_oxide_b200
     rng = random.Random(99)
-    for name in ("opsin_inverse", "grayalpha", "upsampling"):
+    for name in ("opsin_inverse", "grayalpha", "upsampling", "cafe", "delta_palette", "spot", "animation_spline", "grayscale"):
         data = fixture_bytes(name, "input.jxl")
         for i in range(12):
             m = bytearray(data)
