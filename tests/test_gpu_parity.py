@@ -11,9 +11,9 @@ from conftest import fixture_bytes
 
 pytestmark = pytest.mark.gpu
 
-MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless", "sunset_logo", "blendmodes", "grayscale_public_university", "spot", "delta_palette", "lossless_pfm"]
+MODULAR = ["grayalpha", "squeeze_edge", "issue_311", "alpha_triangles", "bicycles", "lz77_flower", "patches_lossless", "sunset_logo", "blendmodes", "grayscale_public_university", "spot", "delta_palette", "lossless_pfm", "cmyk_layers", "progressive"]
 MODULAR_BENCH = ["srgb.d0-e1.jxl", "minecraft.d0-e6.jxl"]
-VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise", "bike", "bench_oriented_brg", "grayscale_jpeg", "cafe", "grayscale", "issue_425"]
+VARDCT = ["opsin_inverse", "alpha_premultiplied", "minecraft_vardct_e7", "upsampling", "noise", "bike", "bench_oriented_brg", "grayscale_jpeg", "cafe", "grayscale", "issue_425", "patches"]
 VARDCT_BENCH = ["starrail.d1-e6.jxl", "nahida-motion.d1-e7.jxl"]
 STAGES_F32 = ["lf", "hf_dequant", "idct", "jpeg_upsampled", "pre_filter", "gaborish", "epf", "upsampled", "patches", "splines", "noise", "rgb"]
 

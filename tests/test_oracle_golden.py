@@ -189,6 +189,9 @@ ICC_SHA256 = {
     "grayscale_jpeg": "78001f4bf342",
     "patches_lossless": "3a10bcd8e4c3",
     "spot": "ce0caee95061",
+    "cmyk_layers": "4855b8fabb96",
+    "patches": "3a10bcd8e4c3",
+    "progressive": "bef95ce5cdb1",
 }
 
 
@@ -271,6 +274,24 @@ def test_jpeg_transcode_odd_block_count(oracle):
     ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("issue_425", "ref.jpg"))).convert("RGB")).astype(np.float32) / 255.0
     assert buf.shape == ref.shape == (256, 228, 3)
     assert np.abs(buf - ref).max() <= 0.02 and np.sqrt(((buf - ref) ** 2).mean()) <= 0.004
+
+
+def test_cmyk_image_stream_carries_the_black_channel(oracle):
+    """CMYK image (the ICC profile's data colour space says so): ImageStream = C, M, Y, then K, then alpha
+    (fb.rs:205-243). No CMS here, so the samples stay CMYK."""
+    img = oracle.OracleImage(fixture_bytes("cmyk_layers", "input.jxl"), threads=4)
+    assert img.frame(0)[0].shape == (5, 512, 512)
+    assert img.frame_to_buffer(0, np.uint8, 0).shape == (512, 512, 5)
+
+
+def test_icc_tagged_xyb_images_fall_back_to_srgb(oracle):
+    """XYB images whose ICC profile no enum encoding describes (`chrm` tag, tabulated curves) render to sRGB, as
+    jxl-oxide does without a CMS (jxl-render/src/lib.rs:104-150); the large Squeeze-progressive Modular frame and
+    the VarDCT frame with patches and alpha decode to finite, in-range pixels."""
+    for name, shape in (("progressive", (3, 2704, 4064)), ("patches", (4, 1096, 1600))):
+        planes = oracle.OracleImage(fixture_bytes(name, "input.jxl"), threads=8).frame(0)[0]
+        assert planes.shape == shape and np.isfinite(planes).all()
+        assert -0.5 < float(planes.min()) and float(planes.max()) < 1.5  # wide-gamut content leaves sRGB's [0, 1]
 
 
 def test_animation_splines(oracle):
