@@ -80,37 +80,110 @@ def load_workload(name, nframes=16):
 
 
 # ----------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu = gpu_index
-        self.samples = []
-        self.reasons = set()
-        self.max_mhz = None
+class ClockSampler:
+    """SM clock and throttle reasons during the timed region, from ONE long-running `nvidia-smi -lms 200` process
+    (the profiling recipe's clocks line) - starting a new nvidia-smi per sample re-initialises NVML each time and
+    perturbs the run it is supposed to observe."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu_index, uuid=None):
+        # `uuid` ("GPU-...") identifies the CUDA device whatever CUDA_VISIBLE_DEVICES remaps; else the index is used
+        self.gpu = uuid or gpu_index
+        self.proc = None
+        self.lines = []
+        self.reader = None
+
+    def _start_nvml(self):
+        """In-process NVML (what nvidia-smi itself reads): one init, then cheap polls every 200 ms."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = (pynvml.nvmlDeviceGetHandleByUUID(self.gpu) if isinstance(self.gpu, str)
+             else pynvml.nvmlDeviceGetHandleByIndex(self.gpu))
+        pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # raises when unsupported
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        self.nvml_samples, self.nvml_reasons, self.nvml_max = [], set(), None
         self._halt = threading.Event()
 
-    def run(self):
+        def poll():
+            while not self._halt.is_set():
+                try:
+                    self.nvml_samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    for n, b in bits.items():
+                        if mask & b:
+                            self.nvml_reasons.add(n)
+                except Exception:
+                    pass
+                self._halt.wait(0.2)
+        self.nvml_thread = threading.Thread(target=poll, daemon=True)
+        self.nvml_thread.start()
+
+    def start(self):
+        self.nvml_thread = None
+        try:
+            self._start_nvml()
+            return
+        except Exception:
+            self.nvml_thread = None
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._halt.is_set():
+        try:
+            self.proc = subprocess.Popen(["stdbuf", "-oL", "nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+
+        def pump():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                for line in self.proc.stdout:
+                    self.lines.append(line)
             except Exception:
                 pass
-            self._halt.wait(0.2)
+        self.reader = threading.Thread(target=pump, daemon=True)
+        self.reader.start()
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=5)
-        med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        if self.nvml_thread is not None:
+            self._halt.set()
+            self.nvml_thread.join(timeout=5)
+            if self.nvml_samples:
+                return {"sm_mhz": float(np.median(self.nvml_samples)), "sm_max_mhz": self.nvml_max,
+                        "reasons": sorted(self.nvml_reasons), "samples": len(self.nvml_samples),
+                        "how": "NVML polled every 200 ms during the timed region"}
+        if self.proc is not None:
+            try:
+                self.proc.terminate()  # the exact process started above
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+            if self.reader is not None:
+                self.reader.join(timeout=5)
+        mode = "nvidia-smi -lms 200 during the timed region"
+        if not self.lines:  # nothing arrived through the pipe: one query right after the region instead
+            mode = "single nvidia-smi query right after the timed region"
+            try:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.lines = [subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                             capture_output=True, text=True, timeout=10).stdout]
+            except Exception:
+                self.lines = []
+        samples, reasons, max_mhz = [], set(), None
+        for line in self.lines:
+            out = [x.strip() for x in line.strip().split(",")]
+            try:
+                samples.append(float(out[0]))
+                max_mhz = float(out[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(self.NAMES, out[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        med = float(np.median(samples)) if samples else None
+        return {"sm_mhz": med, "sm_max_mhz": max_mhz, "reasons": sorted(reasons), "samples": len(samples), "how": mode}
 
 
 def algorithmic_bytes(kernel, w, h, stream_bytes):
@@ -218,7 +291,11 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.warmup):
         step(False)
     launches0 = sum(d.launch_count() for d in decs)
-    sampler = ClockSampler(local_rank)
+    try:
+        dev_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        dev_uuid = None
+    sampler = ClockSampler(local_rank, dev_uuid)
     sampler.start()
     ms = timed(False, args.steps)
     clocks = sampler.stop()
