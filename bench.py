@@ -90,6 +90,7 @@ class ClockSampler:
     def __init__(self, gpu_index, uuid=None):
         # `uuid` ("GPU-...") identifies the CUDA device whatever CUDA_VISIBLE_DEVICES remaps; else the index is used
         self.gpu = uuid or gpu_index
+        self.index = gpu_index
         self.proc = None
         self.lines = []
         self.reader = None
@@ -98,8 +99,14 @@ class ClockSampler:
         """In-process NVML (what nvidia-smi itself reads): one init, then cheap polls every 200 ms."""
         import pynvml
         pynvml.nvmlInit()
-        h = (pynvml.nvmlDeviceGetHandleByUUID(self.gpu) if isinstance(self.gpu, str)
-             else pynvml.nvmlDeviceGetHandleByIndex(self.gpu))
+        try:
+            h = (pynvml.nvmlDeviceGetHandleByUUID(self.gpu) if isinstance(self.gpu, str)
+                 else pynvml.nvmlDeviceGetHandleByIndex(self.gpu))
+        except Exception:
+            if not isinstance(self.gpu, str):
+                raise
+            self.gpu = self.index  # the UUID did not resolve: fall back to the CUDA ordinal
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
         pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # raises when unsupported
         bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
         self.nvml_samples, self.nvml_reasons, self.nvml_max = [], set(), None
