@@ -11,14 +11,6 @@ namespace {
 __device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return int32_t(uint32_t(a) + uint32_t(b)); }
 __device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return int32_t(uint32_t(a) - uint32_t(b)); }
 __device__ __forceinline__ int32_t wmul(int32_t a, int32_t b) { return int32_t(uint32_t(a) * uint32_t(b)); }
-__device__ __forceinline__ uint32_t abs_diff(int32_t a, int32_t b) {
-  return a > b ? uint32_t(a) - uint32_t(b) : uint32_t(b) - uint32_t(a);
-}
-__device__ __forceinline__ int32_t grad_clamped(int32_t n, int32_t w, int32_t nw) {
-  int64_t hi = n > w ? n : w, lo = n > w ? w : n;
-  int64_t v = lo + hi - int64_t(nw);
-  return int32_t(v < lo ? lo : (v > hi ? hi : v));
-}
 
 __device__ __forceinline__ int32_t tendency(int32_t a, int32_t b, int32_t c) {  // squeeze.rs:1104-1137
   if (a >= b && b >= c) {
