@@ -5,6 +5,7 @@
 
 #include "../jxl_oxide_b200/csrc/host/planner.h"
 #include "oracle_backend.h"
+#include "../jxl_oxide_b200/csrc/host/icc.h"
 
 namespace {
 struct Handle {
@@ -51,6 +52,18 @@ void jxlo_image_info(void* hp, uint32_t* width, uint32_t* height, uint32_t* bits
   const jxlb::ImageHeader& ih = static_cast<Handle*>(hp)->res.image_header;
   *width = ih.width, *height = ih.height, *bits = ih.bit_depth.bits_per_sample;
   *num_extra = uint32_t(ih.ec_info.size()), *xyb = ih.xyb_encoded, *gray = ih.grayscale();
+}
+
+// Known-answer hook for the ICC recognition rules (host/icc.cc, shared with the product): status 0 enum / 1
+// unsupported / 2 malformed; out = colour space, white point, primaries, transfer function, gamma, gamma_inverted,
+// rendering intent.
+int jxlo_icc_to_enum(const uint8_t* icc, size_t size, uint32_t out[7]) {
+  jxlb::IccInfo info;
+  const jxlb::IccStatus st = jxlb::icc_to_enum(std::vector<uint8_t>(icc, icc + size), &info);
+  const jxlb::ColourEncoding& e = info.encoding;
+  out[0] = uint32_t(e.colour_space), out[1] = uint32_t(e.white_point), out[2] = uint32_t(e.primaries), out[3] = uint32_t(e.tf);
+  out[4] = e.gamma, out[5] = e.gamma_inverted ? 1 : 0, out[6] = e.rendering_intent;
+  return int(st);
 }
 
 size_t jxlo_image_original_icc(void* hp, uint8_t* dst, size_t cap) {

@@ -101,6 +101,11 @@ _ap = Image.open(os.path.join(REF, "conformance/testcases/animation_spline/ref.a
 for _k in (0, 23, 59):
     _ap.seek(_k)
     _ap.convert("RGB").save(os.path.join(HERE, "animation_spline", "ref_frame_%02d.png" % _k), optimize=True)
+# the reference's own ICC test profiles (crates/jxl-color/src/icc/test-profiles, expectations in icc/parse.rs:566-671)
+import glob
+os.makedirs(os.path.join(HERE, "icc"), exist_ok=True)
+for f in sorted(glob.glob("/root/reference/crates/jxl-color/src/icc/test-profiles/*.icc")):
+    shutil.copyfile(f, os.path.join(HERE, "icc", os.path.basename(f)))
 # malformed inputs found by the reference's fuzzers (crates/jxl-oxide-tests/tests/fuzz_findings): expectation =
 # no crash, a clean error value (or a successful decode)
 import glob

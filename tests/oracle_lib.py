@@ -33,6 +33,7 @@ def lib():
         L.jxlo_frame_write_to_buffer.restype = ctypes.c_size_t
         L.jxlo_image_original_icc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.jxlo_image_original_icc.restype = ctypes.c_size_t
+        L.jxlo_icc_to_enum.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
         L.jxlo_frame_stream_channels.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.jxlo_frame_stream_channels.restype = ctypes.c_uint32
         L.jxlo_stage.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32),
@@ -40,6 +41,14 @@ def lib():
         L.jxlo_free.argtypes = [ctypes.c_void_p]
         _LIB = L
     return _LIB
+
+
+def icc_to_enum(icc: bytes):
+    """(status, dict) of the ICC recognition rules: status 0 = an enum encoding describes the profile."""
+    out = (ctypes.c_uint32 * 7)()
+    st = lib().jxlo_icc_to_enum(icc, len(icc), out)
+    keys = ("colour_space", "white_point", "primaries", "tf", "gamma", "gamma_inverted", "rendering_intent")
+    return st, dict(zip(keys, [int(x) for x in out]))
 
 
 class OracleError(RuntimeError):

@@ -205,6 +205,37 @@ def test_embedded_icc_profiles_are_reconstructed_exactly(oracle, name):
     assert hashlib.sha256(icc).hexdigest().startswith(ICC_SHA256[name])
 
 
+def test_icc_recognition_known_answers(oracle):
+    """The reference's own unit tests for parse_icc (crates/jxl-color/src/icc/parse.rs:566-671) on its test profiles:
+    colour space, white point, primaries, transfer function and rendering intent of each."""
+    RGB, GREY, D65, SRGB_PRIM, CUSTOM = 0, 1, 1, 1, 2
+    TF_GAMMA, TF_709, TF_LINEAR, TF_SRGB = 0, 1, 8, 13
+    PERCEPTUAL, RELATIVE = 0, 1
+    cases = {
+        "srgb-rel.icc": (RGB, D65, SRGB_PRIM, TF_SRGB, RELATIVE),
+        "srgb-bt709-per.icc": (RGB, D65, SRGB_PRIM, TF_709, PERCEPTUAL),
+        "srgb-gamma22-rel.icc": (RGB, D65, SRGB_PRIM, TF_GAMMA, RELATIVE),
+        "srgb-linear-rel.icc": (RGB, D65, SRGB_PRIM, TF_LINEAR, RELATIVE),
+        "gray-d65-srgb-rel.icc": (GREY, D65, None, TF_SRGB, RELATIVE),
+        "gray-d65-linear-rel.icc": (GREY, D65, None, TF_LINEAR, RELATIVE),
+    }
+    for name, (cs, wp, prim, tf, intent) in cases.items():
+        st, e = oracle.icc_to_enum(fixture_bytes("icc", name))
+        assert st == 0, name
+        assert (e["colour_space"], e["white_point"], e["tf"], e["rendering_intent"]) == (cs, wp, tf, intent), (name, e)
+        if prim is not None:
+            assert e["primaries"] == prim, (name, e)
+        if tf == TF_GAMMA:  # 0x23332 / 65536 = 2.19998...: Gamma { g in 21999000..=22001000, inverted: false }
+            assert 21999000 <= e["gamma"] <= 22001000 and e["gamma_inverted"] == 0
+    # ProPhoto (ROMM) primaries, D50 white, gamma 1.8: custom xy values, still an enum encoding
+    st, e = oracle.icc_to_enum(fixture_bytes("icc", "prophoto-gamma18-rel.icc"))
+    assert st == 0 and e["colour_space"] == RGB and e["primaries"] == CUSTOM and e["white_point"] == CUSTOM
+    assert e["tf"] == TF_GAMMA and 17990000 <= e["gamma"] <= 18010000
+    # truncated / foreign data is malformed, not a crash
+    assert oracle.icc_to_enum(b"\0" * 64)[0] == 2
+    assert oracle.icc_to_enum(fixture_bytes("icc", "srgb-rel.icc")[:200])[0] == 2
+
+
 def test_xyb_grayscale_with_icc_profile(oracle):
     """XYB image tagged with a gray ICC profile whose curve is tabulated: no enum encoding describes it, so the
     render target is gray sRGB (jxl-render/src/lib.rs:104-150) - gamut map, D65 luma row, sRGB curve, one channel."""
