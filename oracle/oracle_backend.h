@@ -111,4 +111,6 @@ class OracleBackend : public Backend {
   int threads_;
 };
 
+float linear_to_pq(float s, float intensity_target);  // oracle_render.cc
+
 }  // namespace jxlo

@@ -66,6 +66,11 @@ int jxlo_icc_to_enum(const uint8_t* icc, size_t size, uint32_t out[7]) {
   return int(st);
 }
 
+// Known-answer hook: the PQ inverse EOTF as the colour stage applies it (replays tf/pq.rs:460-478)
+void jxlo_linear_to_pq(float* samples, size_t n, float intensity_target) {
+  for (size_t i = 0; i < n; ++i) samples[i] = jxlo::linear_to_pq(samples[i], intensity_target);
+}
+
 size_t jxlo_image_original_icc(void* hp, uint8_t* dst, size_t cap) {
   const std::vector<uint8_t>& icc = static_cast<Handle*>(hp)->res.image_header.icc_profile;
   if (dst && cap >= icc.size() && !icc.empty()) std::memcpy(dst, icc.data(), icc.size());

@@ -607,6 +607,22 @@ void OracleBackend::ycbcr_to_rgb(const View v[3], const YcbcrParams& p) {
   });
 }
 
+// linear_to_pq_generic (tf/pq.rs:126-142) with rational_poly::eval_generic (Horner from the last coefficient)
+float linear_to_pq(float s, float intensity_target) {
+  static const float kP[5] = {1.351392e-2f, -1.095778f, 5.522776e1f, 1.492516e2f, 4.838434e1f};
+  static const float kQ[5] = {1.012416f, 2.016708e1f, 9.26371e1f, 1.120607e2f, 2.590418e1f};
+  static const float kPSmall[5] = {9.863406e-6f, 3.881234e-1f, 1.352821e2f, 6.889862e4f, -2.864824e5f};
+  static const float kQSmall[5] = {3.371868e1f, 1.477719e3f, 1.608477e4f, -4.389884e4f, -2.072546e5f};
+  const float y_mult = intensity_target / 10000.0f;
+  const float a0 = std::fabs(s);
+  const float a_1_4 = std::sqrt(std::sqrt(a0 * y_mult));
+  const float* pp = a0 < 1e-4f ? kPSmall : kP;
+  const float* qq = a0 < 1e-4f ? kQSmall : kQ;
+  float yp = pp[4], yq = qq[4];
+  for (int k = 3; k >= 0; --k) yp = yp * a_1_4 + pp[k], yq = yq * a_1_4 + qq[k];
+  return std::copysign(yp / yq, s);
+}
+
 void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   static const uint8_t kPowUpper[16] = {0x00, 0x0a, 0x19, 0x26, 0x32, 0x41, 0x4d, 0x5c, 0x68, 0x75, 0x83, 0x8f, 0xa0, 0xaa, 0xb9, 0xc6};
   static const uint8_t kPowLower[16] = {0x00, 0xb7, 0x04, 0x0d, 0xcb, 0xe7, 0x41, 0x68, 0x51, 0xd1, 0xeb, 0xf2, 0x00, 0xb7, 0x04, 0x0d};
@@ -647,21 +663,8 @@ void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
                     t2 = m2[6] * o[0] + m2[7] * o[1] + m2[8] * o[2];
         o[0] = p.to_luma ? t1 : t0, o[1] = t1, o[2] = t2;
       }
-      if (p.pq_intensity_target > 0.0f) {  // linear_to_pq_generic (tf/pq.rs:126-142), rational_poly::eval_generic
-        static const float kP[5] = {1.351392e-2f, -1.095778f, 5.522776e1f, 1.492516e2f, 4.838434e1f};
-        static const float kQ[5] = {1.012416f, 2.016708e1f, 9.26371e1f, 1.120607e2f, 2.590418e1f};
-        static const float kPSmall[5] = {9.863406e-6f, 3.881234e-1f, 1.352821e2f, 6.889862e4f, -2.864824e5f};
-        static const float kQSmall[5] = {3.371868e1f, 1.477719e3f, 1.608477e4f, -4.389884e4f, -2.072546e5f};
-        const float y_mult = p.pq_intensity_target / 10000.0f;
-        for (float& sref : o) {
-          const float a0 = std::fabs(sref);
-          const float a_1_4 = std::sqrt(std::sqrt(a0 * y_mult));
-          const float* pp = a0 < 1e-4f ? kPSmall : kP;
-          const float* qq = a0 < 1e-4f ? kQSmall : kQ;
-          float yp = pp[4], yq = qq[4];
-          for (int k = 3; k >= 0; --k) yp = yp * a_1_4 + pp[k], yq = yq * a_1_4 + qq[k];
-          sref = std::copysign(yp / yq, sref);
-        }
+      if (p.pq_intensity_target > 0.0f) {
+        for (float& sref : o) sref = linear_to_pq(sref, p.pq_intensity_target);
       } else if (p.gamma > 0.0f) {  // apply_gamma (tf.rs:62-69) with fast_powf_generic (fastmath/powf.rs)
         for (float& sref : o) {
           const float a0 = sref;
