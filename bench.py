@@ -392,7 +392,8 @@ def run_ours(args, rank, world, local_rank):
                    "cache": "inputs+planes per step (>= 33 MP x 24 B) exceed L2 (126 MB); no explicit L2 flush",
                    "step_barrier": "before and after the K timed steps (steps pipeline across decoder contexts)"
                                    if args.pipeline_steps else "after every step",
-                   "stagger_ms": args.stagger_ms},
+                   "stagger_ms": args.stagger_ms,
+                   "hf_streams_per_cta": int(os.environ.get("JXLB_HF_LANES", "0") or 0)},
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
                 "d2h_bytes_per_step": int(px_per_frame * 12 * len(frames)), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "pipeline_roofline": pipeline,

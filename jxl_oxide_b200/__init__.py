@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "jxlb_image_get_info", "jxlb_image_original_icc",
     "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
-    "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_stage_count", "jxlb_stage_get",
+    "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_set_hf_streams_per_cta", "jxlb_stage_count", "jxlb_stage_get",
     "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse", "jxlb_blend",
 ]
 
@@ -105,6 +105,7 @@ def load_library():
     L.jxlb_launch_count.restype = ctypes.c_uint64
     L.jxlb_set_capture.argtypes = [vp, i32]
     L.jxlb_set_fuse_filters.argtypes = [vp, i32]
+    L.jxlb_set_hf_streams_per_cta.argtypes = [vp, i32]
     L.jxlb_set_profile.argtypes = [vp, i32]
     L.jxlb_profile_get.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double)]
     L.jxlb_profile_reset.argtypes = [vp]
@@ -238,6 +239,11 @@ class Decoder:
 
     def set_fuse_filters(self, on=True):
         self._L.jxlb_set_fuse_filters(self._h, int(on))
+
+    def set_hf_streams_per_cta(self, streams):
+        """0: one warp per HF stream (default); 32 / 64 / 128: one thread per stream, that many streams per CTA."""
+        if self._L.jxlb_set_hf_streams_per_cta(self._h, int(streams)) != 0:
+            raise ValueError("streams per CTA must be 0, 32, 64 or 128")
 
     def stage(self, name, dtype=np.float32):
         n = self._L.jxlb_stage_count(self._h, name.encode())

@@ -49,6 +49,10 @@ CudaBackend::CudaBackend(int device) : device_(device) {
   // changes its split when idle, so kernels with different splits cannot share an SM, and the
   // long-running one-warp entropy CTAs would otherwise fence other streams' kernels off their SMs.
   if (!std::getenv("JXLB_NO_CARVEOUT")) CUDA_CHECK(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
+  if (const char* lanes = std::getenv("JXLB_HF_LANES")) {
+    const int n = std::atoi(lanes);
+    hf_streams_per_cta = n <= 0 ? 0 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128));
+  }
 }
 
 CudaBackend::~CudaBackend() {
@@ -870,15 +874,27 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   p.coeff_shift = pass < st.fh->passes.shift.size() ? st.fh->passes.shift[pass] : 0;
   p.group_dim_blocks = st.group_dim / 8;
   p.groups_per_row = st.groups_per_row;
+  // Thread-per-stream kernel: streams of similar length share a warp (longest first), so that a warp's lanes
+  // finish together; `perm` maps the launch order back to `jobs`.
+  std::vector<uint32_t> perm(jobs.size());
+  for (size_t i = 0; i < jobs.size(); ++i) perm[i] = uint32_t(i);
+  if (hf_streams_per_cta > 0)
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
+      return jobs[a].bit_limit - jobs[a].bit_pos > jobs[b].bit_limit - jobs[b].bit_pos;
+    });
   std::vector<DevHfJob> dj;
-  for (const HfGroupJob& j : jobs) dj.push_back({j.bit_pos, j.bit_limit, j.group_idx});
+  for (uint32_t i : perm) dj.push_back({jobs[i].bit_pos, jobs[i].bit_limit, jobs[i].group_idx});
   const DevHfJob* d_jobs = static_cast<const DevHfJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevHfJob)));
   uint64_t* d_end = static_cast<uint64_t*>(dmalloc(jobs.size() * 8));
   int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
   temps_.push_back(d_end);
   temps_.push_back(d_status);
   begin_k("decode_hf");
-  launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0, stream_);
+  if (hf_streams_per_cta > 0)
+    launch_decode_hf_lanes(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
+                           hf_streams_per_cta, stream_);
+  else
+    launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0, stream_);
   end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());
@@ -888,10 +904,11 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   CUDA_CHECK(cudaGetLastError());
   release_temps();
   for (size_t i = 0; i < jobs.size(); ++i) {
+    HfGroupJob& job = jobs[perm[i]];
     if (status[i] != kDevOk)
       fail(status[i] == kDevOverrun ? kErrEof : (status[i] == kDevUnsupported ? kErrUnsupported : kErrDeviceDecode),
-           std::string("HF group ") + std::to_string(jobs[i].group_idx) + ": " + dev_status_message(status[i]));
-    jobs[i].end_bit = size_t(end[i]);
+           std::string("HF group ") + std::to_string(job.group_idx) + ": " + dev_status_message(status[i]));
+    job.end_bit = size_t(end[i]);
   }
 }
 

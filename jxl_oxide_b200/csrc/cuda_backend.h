@@ -72,6 +72,9 @@ class CudaBackend : public Backend {
   // Interleave + convert on the device, then one linear copy to `dst` (host).
   void pack_to_host(const DevPackParams& p, void* dst, size_t bytes);
   bool fuse_filters = true;  // single-kernel Gaborish+EPF+colour (off: stage-by-stage, for stage parity tests)
+  // HF coefficient streams: 0 = one warp per stream (decode_hf_fast_kernel), 32 / 64 / 128 = one thread per stream
+  // with that many streams per CTA (decode_hf_lanes_kernel). Initialised from JXLB_HF_LANES.
+  int hf_streams_per_cta = 0;
   bool profile = false;
   bool trace_device = false;  // modular streams stamp the device clock; host launch/return times are logged
   double phase_t0_ = -1.0;  // wall clock (ms) of the previous phase_mark

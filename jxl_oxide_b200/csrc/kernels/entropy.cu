@@ -12,27 +12,14 @@
 // crates/jxl-vardct/src/hf_coeff.rs (bit-exact, wrapping i32).
 #include "kernels.h"
 #include "stream_common.cuh"
+#include "hf_lanes.cuh"
 
 namespace jxlb {
 
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// HF coefficients (jxl-vardct/src/hf_coeff.rs:21-252)
-#define JXLB_TABLE_QUAL __device__ __constant__ const
-namespace hftab {
-#include "../host/jxl_tables.inc"
-}
-#undef JXLB_TABLE_QUAL
-
-__device__ __constant__ const uint8_t kTInfo[27][5] = {
-    {1, 1, 0, 0, 1},  {1, 1, 1, 1, 0},  {1, 1, 2, 1, 0},   {1, 1, 3, 1, 0},    {2, 2, 4, 2, 1},   {4, 4, 5, 3, 1},
-    {1, 2, 6, 4, 1},  {2, 1, 6, 4, 0},  {1, 4, 7, 5, 1},   {4, 1, 7, 5, 0},    {2, 4, 8, 6, 1},   {4, 2, 8, 6, 0},
-    {1, 1, 9, 1, 0},  {1, 1, 9, 1, 0},  {1, 1, 10, 1, 0},  {1, 1, 10, 1, 0},   {1, 1, 10, 1, 0},  {1, 1, 10, 1, 0},
-    {8, 8, 11, 7, 1}, {4, 8, 12, 8, 1}, {8, 4, 12, 8, 0},  {16, 16, 13, 9, 1}, {8, 16, 14, 10, 1}, {16, 8, 14, 10, 0},
-    {32, 32, 15, 11, 1}, {16, 32, 16, 12, 1}, {32, 16, 16, 12, 0},
-};
-
+// HF coefficients (jxl-vardct/src/hf_coeff.rs:21-252); hftab / kTInfo live in hf_lanes.cuh
 constexpr int kHfWarpsPerCta = 4;
 constexpr uint32_t kHfAnsSmemBytes = 128 * 1024;
 
@@ -246,7 +233,105 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
   status[job_idx] = err;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// One thread per stream (hf_lanes.cuh). A CTA of `blockDim.x` threads carries blockDim.x streams and
+// stages, once: context LUTs, hybrid-uint configs, block-context map, the cluster maps of every HF preset
+// (global memory when they exceed kLaneCmapSmemBytes), the ANS alias tables (same rule as above) and 96
+// bytes of non-zero-count row per stream.
+constexpr uint32_t kLaneCmapSmemBytes = 32 * 1024;
+struct HfLaneSmem {
+  uint32_t ctxlut, configs, bctx, cmap, cmap_stride, nz, ans, total;
+};
+__host__ __device__ inline HfLaneSmem hf_lane_layout(const DevHfParams& p, uint32_t nthreads) {
+  HfLaneSmem L;
+  uint32_t off = 0;
+  auto take = [&](uint32_t bytes) {
+    uint32_t o = off;
+    off += (bytes + 15) & ~15u;
+    return o;
+  };
+  L.ctxlut = take(128);
+  L.configs = take(p.code.num_clusters * 4);
+  L.bctx = take(p.block_ctx_map_size);
+  L.cmap_stride = 495 * p.num_block_clusters;
+  const uint32_t cmap_bytes = L.cmap_stride * p.num_hf_presets;
+  L.cmap = cmap_bytes <= kLaneCmapSmemBytes ? take(cmap_bytes) : 0xffffffffu;
+  L.nz = take(96 * nthreads);
+  uint32_t ab = p.code.use_prefix ? 0 : (p.code.num_clusters << p.code.log_alphabet_size) * 8;
+  L.ans = (!p.code.use_prefix && ab <= min(kHfAnsSmemBytes, p.ans_smem_limit)) ? take(ab) : 0xffffffffu;
+  L.total = off;
+  return L;
+}
+
+template <bool SUB>
+__global__ void __launch_bounds__(128) decode_hf_lanes_kernel(const uint8_t* __restrict__ cs, DevFrame f, DevHfParams p,
+                                                              const DevHfJob* __restrict__ jobs,
+                                                              uint64_t* __restrict__ end_bits, int* __restrict__ status,
+                                                              int num_jobs, int first_pass) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
+  const HfLaneSmem L = hf_lane_layout(p, nthreads);
+  uint8_t* s_ctx = smem + L.ctxlut;
+  for (uint32_t i = tid; i < 63; i += nthreads) {
+    s_ctx[i] = hftab::kCoeffFreqContext[i];
+    s_ctx[64 + i] = hftab::kCoeffNumNonzeroContext[i];
+  }
+  uint32_t* s_cfg = reinterpret_cast<uint32_t*>(smem + L.configs);
+  for (uint32_t i = tid; i < p.code.num_clusters; i += nthreads) s_cfg[i] = __ldg(p.code.configs + i);
+  uint8_t* s_bctx = smem + L.bctx;
+  for (uint32_t i = tid; i < p.block_ctx_map_size; i += nthreads) s_bctx[i] = __ldg(p.block_ctx_map + i);
+  HfLaneTables T;
+  T.ctx = s_ctx;
+  T.cfg = s_cfg;
+  T.bctx = s_bctx;
+  T.cmap = p.code.cluster_map;
+  T.cmap_stride = L.cmap_stride;
+  if (L.cmap != 0xffffffffu) {
+    uint8_t* s_cmap = smem + L.cmap;
+    const uint32_t n = L.cmap_stride * p.num_hf_presets;
+    for (uint32_t i = tid; i < n; i += nthreads) s_cmap[i] = __ldg(p.code.cluster_map + i);
+    T.cmap = s_cmap;
+  }
+  T.cv.log_alphabet_size = p.code.log_alphabet_size;
+  T.cv.use_prefix = p.code.use_prefix;
+  T.cv.configs = s_cfg;
+  T.cv.ans = p.code.ans;
+  T.cv.prefix = p.code.prefix;
+  T.cv.prefix_meta = p.code.prefix_meta;
+  if (L.ans != 0xffffffffu) {
+    uint4* s_ans = reinterpret_cast<uint4*>(smem + L.ans);
+    const uint32_t quads = (p.code.num_clusters << p.code.log_alphabet_size) / 2;  // 2 buckets per 16 bytes
+    const uint4* src = reinterpret_cast<const uint4*>(p.code.ans);
+    for (uint32_t i = tid; i < quads; i += nthreads) s_ans[i] = __ldg(src + i);
+    T.cv.ans = reinterpret_cast<const uint64_t*>(s_ans);
+  }
+  __syncthreads();
+  const int job_idx = blockIdx.x * int(nthreads) + int(tid);
+  if (job_idx >= num_jobs) return;
+  const DevHfJob job = jobs[job_idx];
+  hf_lane_decode<SUB>(cs, f, p, T, job, smem + L.nz + tid, nthreads, first_pass, end_bits + job_idx, status + job_idx);
+}
+
 }  // namespace
+
+void launch_decode_hf_lanes(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
+                            int* status, int num_jobs, int first_pass, int streams_per_cta, cudaStream_t stream) {
+  if (num_jobs <= 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(decode_hf_lanes_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(decode_hf_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  const int nthreads = streams_per_cta <= 32 ? 32 : (streams_per_cta <= 64 ? 64 : 128);
+  const HfLaneSmem L = hf_lane_layout(p, uint32_t(nthreads));
+  const int ctas = (num_jobs + nthreads - 1) / nthreads;
+  if (f.subsampled)
+    decode_hf_lanes_kernel<true><<<ctas, nthreads, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+  else
+    decode_hf_lanes_kernel<false><<<ctas, nthreads, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+}
 
 void launch_decode_hf(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,
                       int num_jobs, int first_pass, cudaStream_t stream) {

@@ -129,6 +129,9 @@ struct DevHfJob {
 };
 void launch_decode_hf(const uint8_t* codestream, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
                       int* status, int num_jobs, int first_pass, cudaStream_t stream);
+// Same contract, one thread per stream (kernels/hf_lanes.cuh); `streams_per_cta` in {32, 64, 128}.
+void launch_decode_hf_lanes(const uint8_t* codestream, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
+                            int* status, int num_jobs, int first_pass, int streams_per_cta, cudaStream_t stream);
 
 struct DevLfDequantJob {
   DevLfGroupRect rect;

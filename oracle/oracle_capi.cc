@@ -7,6 +7,16 @@
 #include "oracle_backend.h"
 #include "../jxl_oxide_b200/csrc/host/icc.h"
 
+// tests/emu/ builds this file a second time with a backend whose entropy stages run the host-compiled device code
+#ifdef JXLO_BACKEND_FACTORY
+namespace jxlo {
+OracleBackend* JXLO_BACKEND_FACTORY(int threads);
+}
+#define JXLO_NEW_BACKEND(threads) jxlo::JXLO_BACKEND_FACTORY(threads)
+#else
+#define JXLO_NEW_BACKEND(threads) new jxlo::OracleBackend(threads)
+#endif
+
 namespace {
 struct Handle {
   std::unique_ptr<jxlo::OracleBackend> be;
@@ -28,7 +38,7 @@ void* jxlo_decode(const uint8_t* data, size_t size, int output_colour, int threa
   auto h = std::make_unique<Handle>();
   try {
     h->codestream = jxlb::extract_codestream(data, size);
-    h->be.reset(new jxlo::OracleBackend(threads));
+    h->be.reset(JXLO_NEW_BACKEND(threads));
     h->be->capture = capture != 0;
     jxlb::DecodeOptions opt;
     opt.output_colour = output_colour;

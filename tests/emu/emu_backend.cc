@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE — NOT PART OF THE PRODUCT.
+//
+// Host emulation of the thread-per-stream HF coefficient kernel (kernels/hf_lanes.cuh). The oracle backend
+// is reused for everything else; decode_hf() builds the same DevFrame / DevHfParams / job list the CUDA
+// backend uploads (cuda_backend.cu: dev_frame, upload_code, decode_hf) but over host memory, and then runs
+// hf_lane_decode() -- the very function every device thread runs -- once per stream, with the interleaved
+// non-zero-row layout of a 32-thread CTA. tests/test_emu_lanes.py compares the resulting coefficient planes,
+// end positions and final pixels with the plain oracle.
+#include <algorithm>
+#include <cstring>
+
+#include "cuda_shim.h"
+#include "../../jxl_oxide_b200/csrc/kernels/hf_lanes.cuh"
+#include "../../oracle/oracle_backend.h"
+#include "../../jxl_oxide_b200/csrc/host/planner.h"
+
+namespace {
+std::atomic<uint64_t> g_hf_streams{0};
+}
+
+// how many HF streams went through hf_lane_decode() so far (the test checks that the emulated path really ran)
+extern "C" uint64_t jxle_hf_streams() { return g_hf_streams.load(); }
+
+namespace jxlo {
+
+class EmuBackend : public OracleBackend {
+ public:
+  explicit EmuBackend(int threads) : OracleBackend(threads) {}
+  void set_codestream(const uint8_t* data, size_t size) override {
+    OracleBackend::set_codestream(data, size);
+    // the device copy is zero padded (the word-ahead bit reader touches up to 3 words past the last bit)
+    storage_.assign((size + 64 + 7) / 8 + 1, 0);
+    std::memcpy(storage_.data(), data, size);
+  }
+  void decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) override;
+
+ private:
+  std::vector<uint64_t> storage_;  // 8-byte aligned
+};
+
+namespace {
+template <typename T>
+T* pl(OracleBackend& be, int id) {
+  return id < 0 ? nullptr : reinterpret_cast<T*>(be.plane(id).data.data());
+}
+}  // namespace
+
+void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
+  if (jobs.empty()) return;
+  const uint8_t* cs = reinterpret_cast<const uint8_t*>(storage_.data());
+  DevFrame f;
+  std::memset(&f, 0, sizeof(f));
+  f.width = st.width, f.height = st.height, f.bw = st.bw, f.bh = st.bh;
+  f.cw = st.bw * 8, f.ch = st.bh * 8;
+  f.w64 = (st.width + 63) / 64;
+  for (int c = 0; c < 3; ++c) {
+    f.lf_quant[c] = pl<int32_t>(*this, st.lf_quant[c]);
+    f.coeff[c] = pl<uint32_t>(*this, st.coeff[c]);
+    f.hshift[c] = uint8_t(st.hshift[c]), f.vshift[c] = uint8_t(st.vshift[c]);
+  }
+  f.blk_type = pl<int32_t>(*this, st.blk_type);
+  f.blk_mul = pl<int32_t>(*this, st.blk_mul);
+  f.group_blocks = st.group_dim / 8;
+  f.subsampled = st.subsampled ? 1 : 0;
+
+  const HfBlockContext& hbc = st.lfg->hf_block_ctx;
+  const uint32_t pass = jobs[0].pass_idx;
+  const HfPassSyntax& hp = st.hfg->passes[pass];
+  const EntropyCode& code = hp.code;
+  DevHfParams p;
+  std::memset(&p, 0, sizeof(p));
+  std::vector<uint32_t> cfg;
+  for (const HybridUintConfig& h : code.configs) cfg.push_back(h.packed());
+  std::vector<uint32_t> meta;
+  for (const PrefixMeta& m : code.prefix_meta) {
+    meta.push_back(m.table_offset);
+    meta.push_back(m.root_bits);
+  }
+  p.code.cluster_map = code.cluster_map.data();
+  p.code.configs = cfg.data();
+  p.code.log_alphabet_size = code.log_alphabet_size;
+  p.code.use_prefix = code.use_prefix ? 1 : 0;
+  p.code.num_clusters = code.num_clusters;
+  p.code.cluster_map_size = uint32_t(code.cluster_map.size());
+  p.code.prefix = code.prefix_table.data();
+  p.code.prefix_meta = meta.data();
+  p.code.ans = code.ans_table.data();
+  std::vector<uint32_t> orders;
+  for (int id = 0; id < 13; ++id)
+    for (int c = 0; c < 3; ++c) {
+      p.order_offset[id * 3 + c] = uint32_t(orders.size());
+      std::vector<uint32_t> o = hp.order[id][c].empty() ? natural_order(uint32_t(id)) : hp.order[id][c];
+      orders.insert(orders.end(), o.begin(), o.end());
+    }
+  p.orders = orders.data();
+  p.block_ctx_map = hbc.block_ctx_map.data();
+  p.block_ctx_map_size = uint32_t(hbc.block_ctx_map.size());
+  std::vector<int32_t> thr;
+  for (int c = 0; c < 3; ++c) {
+    p.num_lf_thr[c] = uint32_t(hbc.lf_thresholds[c].size());
+    thr.insert(thr.end(), hbc.lf_thresholds[c].begin(), hbc.lf_thresholds[c].end());
+  }
+  thr.push_back(0);
+  p.lf_thresholds = thr.data();
+  p.has_lf_quant = st.use_lf_frame ? 0 : 1;
+  std::vector<uint32_t> qf = hbc.qf_thresholds;
+  p.num_qf_thr = uint32_t(qf.size());
+  qf.push_back(0);
+  p.qf_thresholds = qf.data();
+  p.num_block_clusters = hbc.num_block_clusters;
+  p.num_hf_presets = st.hfg->num_hf_presets;
+  p.coeff_shift = pass < st.fh->passes.shift.size() ? st.fh->passes.shift[pass] : 0;
+  p.group_dim_blocks = st.group_dim / 8;
+  p.groups_per_row = st.groups_per_row;
+
+  // "shared memory" tables of one CTA
+  uint8_t ctx[128] = {0};
+  for (int i = 0; i < 63; ++i) {
+    ctx[i] = hftab::kCoeffFreqContext[i];
+    ctx[64 + i] = hftab::kCoeffNumNonzeroContext[i];
+  }
+  HfLaneTables T;
+  T.ctx = ctx;
+  T.cfg = cfg.data();
+  T.bctx = p.block_ctx_map;
+  T.cmap = p.code.cluster_map;
+  T.cmap_stride = 495 * p.num_block_clusters;
+  T.cv.configs = cfg.data();
+  T.cv.ans = p.code.ans;
+  T.cv.prefix = p.code.prefix;
+  T.cv.prefix_meta = p.code.prefix_meta;
+  T.cv.log_alphabet_size = p.code.log_alphabet_size;
+  T.cv.use_prefix = p.code.use_prefix;
+
+  // launch order of the CUDA backend: longest section first
+  std::vector<uint32_t> perm(jobs.size());
+  for (size_t i = 0; i < jobs.size(); ++i) perm[i] = uint32_t(i);
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
+    return jobs[a].bit_limit - jobs[a].bit_pos > jobs[b].bit_limit - jobs[b].bit_pos;
+  });
+  constexpr uint32_t kThreads = 32;
+  std::vector<uint8_t> nz(96 * kThreads, 0xee);
+  for (size_t i = 0; i < perm.size(); ++i) {
+    HfGroupJob& job = jobs[perm[i]];
+    DevHfJob dj{job.bit_pos, job.bit_limit, job.group_idx};
+    uint64_t end = 0;
+    int status = 0;
+    const uint32_t tid = uint32_t(i % kThreads);
+    if (f.subsampled) hf_lane_decode<true>(cs, f, p, T, dj, nz.data() + tid, kThreads, pass == 0 ? 1 : 0, &end, &status);
+    else hf_lane_decode<false>(cs, f, p, T, dj, nz.data() + tid, kThreads, pass == 0 ? 1 : 0, &end, &status);
+    if (status != kDevOk)
+      throw Error(status == kDevOverrun ? kErrEof : (status == kDevUnsupported ? kErrUnsupported : kErrDeviceDecode),
+                  "emulated HF lane: status " + std::to_string(status) + " in group " + std::to_string(job.group_idx));
+    job.end_bit = size_t(end);
+    ++g_hf_streams;
+  }
+}
+
+OracleBackend* make_emu_backend(int threads) { return new EmuBackend(threads); }
+
+}  // namespace jxlo

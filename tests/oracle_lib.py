@@ -16,31 +16,47 @@ def build():
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(ROOT, "oracle", "_build", "libjxloracle.so")
-        if not os.path.exists(path):
-            build()
-        L = ctypes.CDLL(path)
-        L.jxlo_decode.restype = ctypes.c_void_p
-        L.jxlo_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                  ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_size_t]
-        L.jxlo_num_frames.argtypes = [ctypes.c_void_p]
-        L.jxlo_image_info.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 6
-        L.jxlo_image_orientation.argtypes = [ctypes.c_void_p]
-        L.jxlo_image_orientation.restype = ctypes.c_uint32
-        L.jxlo_frame_info.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.POINTER(ctypes.c_uint32)] * 5
-        L.jxlo_frame_channel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
-        L.jxlo_frame_write_to_buffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
-        L.jxlo_frame_write_to_buffer.restype = ctypes.c_size_t
-        L.jxlo_image_original_icc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
-        L.jxlo_image_original_icc.restype = ctypes.c_size_t
-        L.jxlo_icc_to_enum.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
-        L.jxlo_frame_stream_channels.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        L.jxlo_frame_stream_channels.restype = ctypes.c_uint32
-        L.jxlo_stage.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32),
-                                 ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
-        L.jxlo_free.argtypes = [ctypes.c_void_p]
+        L = _load(os.path.join(ROOT, "oracle", "_build", "libjxloracle.so"), os.path.join(ROOT, "oracle"))
         _LIB = L
     return _LIB
+
+
+_EMU_LIB = None
+
+
+def emu_lib():
+    """The oracle rebuilt around tests/emu/emu_backend.cc (always rebuilt through make: it tracks the kernel headers)."""
+    global _EMU_LIB
+    if _EMU_LIB is None:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+        _EMU_LIB = _load(os.path.join(ROOT, "tests", "emu", "_build", "libjxlemu.so"), None)
+    return _EMU_LIB
+
+
+def _load(path, make_dir):
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-s", "-C", make_dir])
+    L = ctypes.CDLL(path)
+    L.jxlo_decode.restype = ctypes.c_void_p
+    L.jxlo_decode.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                              ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_size_t]
+    L.jxlo_num_frames.argtypes = [ctypes.c_void_p]
+    L.jxlo_image_info.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_uint32)] * 6
+    L.jxlo_image_orientation.argtypes = [ctypes.c_void_p]
+    L.jxlo_image_orientation.restype = ctypes.c_uint32
+    L.jxlo_frame_info.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.POINTER(ctypes.c_uint32)] * 5
+    L.jxlo_frame_channel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.jxlo_frame_write_to_buffer.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    L.jxlo_frame_write_to_buffer.restype = ctypes.c_size_t
+    L.jxlo_image_original_icc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    L.jxlo_image_original_icc.restype = ctypes.c_size_t
+    L.jxlo_icc_to_enum.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
+    L.jxlo_frame_stream_channels.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.jxlo_frame_stream_channels.restype = ctypes.c_uint32
+    L.jxlo_stage.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32),
+                             ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p]
+    L.jxlo_free.argtypes = [ctypes.c_void_p]
+    return L
 
 
 def icc_to_enum(icc: bytes):
@@ -58,8 +74,8 @@ class OracleError(RuntimeError):
 
 
 class OracleImage:
-    def __init__(self, data: bytes, output_colour=0, threads=1, capture=False):
-        L = lib()
+    def __init__(self, data: bytes, output_colour=0, threads=1, capture=False, emu=False):
+        L = self._L = emu_lib() if emu else lib()
         status = ctypes.c_int(0)
         err = ctypes.create_string_buffer(512)
         self._h = L.jxlo_decode(data, len(data), output_colour, threads, int(capture), ctypes.byref(status), err, 512)
@@ -72,7 +88,7 @@ class OracleImage:
         self.orientation = L.jxlo_image_orientation(self._h)
 
     def frame(self, idx=0):
-        L = lib()
+        L = self._L
         v = [ctypes.c_uint32() for _ in range(5)]
         L.jxlo_frame_info(self._h, idx, *[ctypes.byref(x) for x in v])
         w, h, nch, ncol, vardct = [x.value for x in v]
@@ -82,7 +98,7 @@ class OracleImage:
         return out, ncol, bool(vardct)
 
     def original_icc(self):
-        L = lib()
+        L = self._L
         n = L.jxlo_image_original_icc(self._h, None, 0)
         buf = ctypes.create_string_buffer(max(n, 1))
         L.jxlo_image_original_icc(self._h, buf, n)
@@ -90,7 +106,7 @@ class OracleImage:
 
     def frame_to_buffer(self, idx=0, dtype=np.uint8, orientation=0):
         """ImageStream::write_to_buffer: (height, width, channels) interleaved samples, orientation applied."""
-        L = lib()
+        L = self._L
         v = [ctypes.c_uint32() for _ in range(5)]
         L.jxlo_frame_info(self._h, idx, *[ctypes.byref(x) for x in v])
         w, h, nch, _, _ = [x.value for x in v]
@@ -103,7 +119,7 @@ class OracleImage:
         return out
 
     def stage(self, name, dtype=np.float32):
-        L = lib()
+        L = self._L
         w, h = ctypes.c_uint32(), ctypes.c_uint32()
         n = L.jxlo_stage(self._h, name.encode(), -1, ctypes.byref(w), ctypes.byref(h), None)
         planes = []
@@ -116,7 +132,7 @@ class OracleImage:
 
     def close(self):
         if self._h:
-            lib().jxlo_free(self._h)
+            self._L.jxlo_free(self._h)
             self._h = None
 
     def __del__(self):

@@ -1,0 +1,77 @@
+"""GPU parity of the thread-per-stream HF coefficient kernel (decode_hf_lanes_kernel, kernels/hf_lanes.cuh).
+
+The kernel is an opt-in schedule (jxlb_set_hf_streams_per_cta / JXLB_HF_LANES) of the same streams the default
+one-warp-per-stream kernel decodes; its per-stream logic is pinned on the CPU by tests/test_emu_lanes.py. Here the
+device launch is compared with the oracle (coefficients bit-identical, final pixels 0 ULP) and with the default
+kernel's error behaviour. The file sorts last on purpose: it exercises an alternative schedule, after the product
+defaults have been checked.
+"""
+import numpy as np
+import pytest
+
+import bench
+from conftest import fixture_bytes
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["opsin_inverse", "bike", "cafe", "issue_425", "bench_oriented_brg", "minecraft_vardct_e7", "upsampling"]
+
+
+@pytest.fixture(scope="module")
+def dec():
+    import jxl_oxide_b200
+    d = jxl_oxide_b200.Decoder(0)
+    yield d
+    d.close()
+
+
+def _check(dec, oracle, data, streams):
+    dec.set_hf_streams_per_cta(streams)
+    try:
+        dec.set_capture(True)
+        dec.decode(data)
+        got = dec.frame_planar(0)
+        img = oracle.OracleImage(data, threads=8, capture=True)
+        want = img.frame(0)[0]
+        for g, w in zip(dec.stage("hf_coeff", np.int32), img.stage("hf_coeff", np.int32)):
+            assert np.array_equal(g, w), "HF coefficient decode differs"
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    finally:
+        dec.set_capture(False)
+        dec.set_hf_streams_per_cta(0)
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_hf_lanes_fixture(dec, oracle, name):
+    _check(dec, oracle, fixture_bytes(name, "input.jxl"), 32)
+
+
+@pytest.mark.parametrize("streams", [32, 64, 128])
+@pytest.mark.parametrize("extra", [(), ("--passes", "3")])
+def test_hf_lanes_synthetic(dec, oracle, streams, extra):
+    # 2000x1500: 8x6 groups (ragged right / bottom), more streams than one CTA carries at 32 per CTA
+    _check(dec, oracle, bench.synth_frame(2000, 1500, 3, extra=extra), streams)
+
+
+def test_hf_lanes_bench_file(dec, oracle):
+    _check(dec, oracle, fixture_bytes("benchmark-data", "starrail.d1-e6.jxl"), 32)
+
+
+def test_hf_lanes_errors_are_values(dec):
+    import jxl_oxide_b200
+    data = bytearray(bench.synth_frame(1000, 600, 7))
+    rng = np.random.default_rng(5)
+    dec.set_hf_streams_per_cta(32)
+    try:
+        for _ in range(12):
+            m = bytearray(data)
+            for pos in rng.integers(len(m) // 2, len(m), size=3):
+                m[pos] ^= 1 << int(rng.integers(0, 8))
+            try:
+                dec.decode(bytes(m))
+            except jxl_oxide_b200.JxlError:
+                pass
+        dec.decode(bytes(data))  # the decoder keeps working
+    finally:
+        dec.set_hf_streams_per_cta(0)
