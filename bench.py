@@ -333,6 +333,53 @@ def run_ours(args, rank, world, local_rank):
         d.set_profile(False)
 
     total_px = px_per_frame * len(frames) * world
+    gather = None
+    if args.gather != "none":
+        # BASELINE config #5's delivery: every frame packed on its GPU (interleaved u8 / u16, 3-6 B/px instead of 12 B/px
+        # of f32 planes) and gathered to rank 0 over NCCL (jxl_oxide_b200.sharding.gather_frames); timed like `value`.
+        from jxl_oxide_b200 import sharding
+        gdt = np.uint8 if args.gather == "u8" else np.uint16
+        packed = [None] * len(frames)
+
+        def gather_step():
+            errs = []
+
+            def work(d, idxs):
+                try:
+                    for k in idxs:
+                        d.decode_slot(k)
+                        packed[k] = d.frame_to_torch(0, gdt, out=packed[k])
+                        d.release_frames()
+                except Exception as e:  # noqa: BLE001
+                    errs.append(e)
+            ts = [threading.Thread(target=work, args=(d, idxs)) for d, idxs in zip(decs, shares)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errs:
+                raise errs[0]
+            return sharding.gather_frames(packed, len(frames) * world, dst=0)
+
+        gather_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            got = gather_step()
+        torch.cuda.synchronize()
+        g1.record()
+        g1.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1)], device="cuda")
+        if dist is not None:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        ms_g = float(tg.item())
+        nbytes = int(packed[0].numel() * packed[0].element_size())
+        gather = {"value": total_px / (ms_g / args.steps / 1e3) / 1e6, "unit": "MP/s", "ms_per_step": ms_g / args.steps,
+                  "format": f"{args.gather} interleaved RGB, packed on the device",
+                  "bytes_to_rank0_per_step": nbytes * len(frames) * (world - 1),
+                  "collective": "torch.distributed gather (nccl), one per round of world_size frames" if world > 1 else "none (1 rank)",
+                  "frames_at_rank0": (len([g for g in got if g is not None]) if got is not None else 0) if rank == 0 else None}
     value = total_px / (ms / args.steps / 1e3) / 1e6
     e2e_value = total_px / (ms_e2e / args.steps / 1e3) / 1e6
     if dist is not None:
@@ -400,6 +447,8 @@ def run_ours(args, rank, world, local_rank):
         "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "kernel_ms_per_frame_solo": {k: round(v, 3) for k, v in solo.items()}, "cpu_baseline": cpu,
     }
+    if gather is not None:
+        line["gather"] = gather
     print(json.dumps(line))
 
 
@@ -479,6 +528,8 @@ def main():
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--stagger-ms", type=float, default=0.0, help="start offset between context groups within a step")
     ap.add_argument("--stagger-groups", type=int, default=4)
+    ap.add_argument("--gather", default="none", choices=["none", "u8", "u16"],
+                    help="also time decode + device-side packing + NCCL gather of every frame to rank 0 (BASELINE config #5)")
     ap.add_argument("--pipeline-steps", action="store_true",
                     help="run the K timed steps back to back, contexts joined only at the end (default: joined after every "
                          "step - measured faster, profiles/r01_progress.md)")

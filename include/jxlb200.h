@@ -86,6 +86,11 @@ int32_t jxlb_frame_stream_channels(const jxlb_decoder* dec, int32_t frame);
  * conversion runs on the device and `dst` (host) receives width*height*jxlb_frame_stream_channels() samples. */
 int32_t jxlb_frame_write_to_buffer(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation, void* dst,
                                    size_t dst_bytes);
+/* Same conversion with a DEVICE destination (memory of this decoder's GPU, e.g. a torch tensor): the packed frame
+ * never touches the host, which is how BASELINE config #5 hands decoded frames to an NCCL gather over NVLink. The call
+ * returns after the packing kernel has finished, so the buffer may be used on any stream. */
+int32_t jxlb_frame_write_to_device(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation,
+                                   void* device_dst, size_t dst_bytes);
 /* Device-resident access: pointer to the channel's top-left sample and its row stride (floats). */
 int32_t jxlb_frame_channel_device(jxlb_decoder* dec, int32_t frame, int32_t channel, float** dptr, uint32_t* stride);
 int32_t jxlb_release_frames(jxlb_decoder* dec);

@@ -27,7 +27,7 @@ OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVI
 EXPORTED_SYMBOLS = [
     "jxlb_decoder_create", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
     "jxlb_image_get_info", "jxlb_image_original_icc",
-    "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_channel_device",
+    "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_write_to_device", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
     "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_set_hf_streams_per_cta", "jxlb_stage_count", "jxlb_stage_get",
     "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse", "jxlb_blend",
@@ -94,6 +94,7 @@ def load_library():
     L.jxlb_frame_get_info.argtypes = [vp, i32, ctypes.POINTER(_FrameInfo)]
     L.jxlb_frame_channel_to_host.argtypes = [vp, i32, i32, vp, ctypes.c_size_t]
     L.jxlb_frame_write_to_buffer.argtypes = [vp, i32, i32, i32, vp, ctypes.c_size_t]
+    L.jxlb_frame_write_to_device.argtypes = [vp, i32, i32, i32, vp, ctypes.c_size_t]
     L.jxlb_image_original_icc.argtypes = [vp, vp, ctypes.c_size_t]
     L.jxlb_image_original_icc.restype = ctypes.c_int64
     L.jxlb_frame_stream_channels.argtypes = [vp, i32]
@@ -134,6 +135,7 @@ class Decoder:
             raise JxlError(rc, "cannot create CUDA decoder (no CUDA device? this path has no CPU fallback)")
         self._h = h
         self._L = L
+        self.device = int(device)
 
     def _check(self, rc):
         if rc != OK:
@@ -221,6 +223,23 @@ class Decoder:
         st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
         out = np.empty((h, w, self._L.jxlb_frame_stream_channels(self._h, frame)), dtype=dtype)
         self._check(self._L.jxlb_frame_write_to_buffer(self._h, frame, st, orientation, out.ctypes.data, out.nbytes))
+        return out
+
+    def frame_to_torch(self, frame, dtype=np.uint8, orientation=0, out=None):
+        """frame_to_buffer() with the packed (height, width, channels) samples left in HBM as a torch tensor on this
+        decoder's GPU (jxlb_frame_write_to_device); torch only owns the memory."""
+        import torch
+        info = self.frame_info(frame)
+        orient = orientation or self.image_info().orientation
+        w, h = (info.height, info.width) if orient >= 5 else (info.width, info.height)
+        st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
+        tdt = {0: torch.uint8, 1: torch.uint16, 2: torch.float32}[st]
+        shape = (h, w, self._L.jxlb_frame_stream_channels(self._h, frame))
+        if out is None:
+            out = torch.empty(shape, dtype=tdt, device=f"cuda:{self.device}")
+        if tuple(out.shape) != shape or out.dtype != tdt or not out.is_contiguous() or not out.is_cuda:
+            raise ValueError(f"out must be a contiguous CUDA {tdt} tensor of shape {shape}")
+        self._check(self._L.jxlb_frame_write_to_device(self._h, frame, st, orientation, out.data_ptr(), out.numel() * out.element_size()))
         return out
 
     def set_capture(self, on=True):

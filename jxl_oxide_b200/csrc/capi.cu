@@ -177,8 +177,24 @@ int32_t jxlb_frame_channel_to_host(jxlb_decoder* dec, int32_t frame, int32_t cha
   });
 }
 
+namespace {
+int32_t write_frame(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation, void* dst, size_t dst_bytes,
+                    bool dst_on_device);
+}
+
 int32_t jxlb_frame_write_to_buffer(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation, void* dst,
                                    size_t dst_bytes) {
+  return write_frame(dec, frame, sample_type, orientation, dst, dst_bytes, false);
+}
+
+int32_t jxlb_frame_write_to_device(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation, void* device_dst,
+                                   size_t dst_bytes) {
+  return write_frame(dec, frame, sample_type, orientation, device_dst, dst_bytes, true);
+}
+
+namespace {
+int32_t write_frame(jxlb_decoder* dec, int32_t frame, int32_t sample_type, int32_t orientation, void* dst, size_t dst_bytes,
+                    bool dst_on_device) {
   if (!dec || !dst || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return JXLB_ERR_INVALID_ARG;
   return guarded(dec, [&] {
     const DecodedFrame& f = dec->res.frames[frame];
@@ -214,9 +230,11 @@ int32_t jxlb_frame_write_to_buffer(jxlb_decoder* dec, int32_t frame, int32_t sam
     p.sample_type = uint32_t(sample_type);
     const size_t bytes = size_t(p.width) * p.height * p.num_channels * (sample_type == 0 ? 1 : (sample_type == 1 ? 2 : 4));
     JXLB_CHECK(dst_bytes >= bytes, kErrInvalidArg, "destination buffer too small");
-    dec->be->pack_to_host(p, dst, bytes);
+    if (dst_on_device) dec->be->pack_to_device(p, dst);
+    else dec->be->pack_to_host(p, dst, bytes);
   });
 }
+}  // namespace
 
 int32_t jxlb_frame_stream_channels(const jxlb_decoder* dec, int32_t frame) {
   if (!dec || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return -1;

@@ -1207,6 +1207,18 @@ void CudaBackend::pack_to_host(const DevPackParams& p, void* dst, size_t bytes) 
   dfree(d);
 }
 
+void CudaBackend::pack_to_device(const DevPackParams& p, void* d_dst) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, d_dst) != cudaSuccess || attr.type != cudaMemoryTypeDevice || attr.device != device_) {
+    cudaGetLastError();
+    fail(kErrInvalidArg, "destination is not device memory of this decoder's GPU");
+  }
+  begin_k("pack_interleaved");
+  launch_pack_interleaved(p, d_dst, stream_);
+  end_k();
+  sync();  // the caller may hand the buffer to any stream (NCCL's, torch's) afterwards
+}
+
 int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader& ih) {
   DevView cur = dev_view(v);
   void* cur_owned = nullptr;

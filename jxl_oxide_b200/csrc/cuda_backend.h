@@ -71,6 +71,8 @@ class CudaBackend : public Backend {
   // per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline
   // Interleave + convert on the device, then one linear copy to `dst` (host).
   void pack_to_host(const DevPackParams& p, void* dst, size_t bytes);
+  // Same, straight into the caller's device buffer (no host copy): the packed frame stays in HBM for an NCCL gather.
+  void pack_to_device(const DevPackParams& p, void* d_dst);
   bool fuse_filters = true;  // single-kernel Gaborish+EPF+colour (off: stage-by-stage, for stage parity tests)
   // HF coefficient streams: 0 = one warp per stream (decode_hf_fast_kernel), 32 / 64 / 128 = one thread per stream
   // with that many streams per CTA (decode_hf_lanes_kernel). Initialised from JXLB_HF_LANES.

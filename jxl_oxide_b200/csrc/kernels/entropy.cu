@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
 // bytes of non-zero-count row per stream.
 constexpr uint32_t kLaneCmapSmemBytes = 32 * 1024;
 struct HfLaneSmem {
-  uint32_t ctxlut, configs, bctx, cmap, cmap_stride, nz, ans, total;
+  uint32_t ctxlut, small, configs, bctx, cmap, cmap_stride, nz, ans, total;
 };
 __host__ __device__ inline HfLaneSmem hf_lane_layout(const DevHfParams& p, uint32_t nthreads) {
   HfLaneSmem L;
@@ -252,6 +252,7 @@ __host__ __device__ inline HfLaneSmem hf_lane_layout(const DevHfParams& p, uint3
     return o;
   };
   L.ctxlut = take(128);
+  L.small = take((27 + 39) * 4);
   L.configs = take(p.code.num_clusters * 4);
   L.bctx = take(p.block_ctx_map_size);
   L.cmap_stride = 495 * p.num_block_clusters;
@@ -281,7 +282,12 @@ __global__ void __launch_bounds__(128) decode_hf_lanes_kernel(const uint8_t* __r
   for (uint32_t i = tid; i < p.code.num_clusters; i += nthreads) s_cfg[i] = __ldg(p.code.configs + i);
   uint8_t* s_bctx = smem + L.bctx;
   for (uint32_t i = tid; i < p.block_ctx_map_size; i += nthreads) s_bctx[i] = __ldg(p.block_ctx_map + i);
+  uint32_t* s_small = reinterpret_cast<uint32_t*>(smem + L.small);
+  for (uint32_t i = tid; i < 27; i += nthreads) s_small[i] = hf_pack_tinfo(i);
+  for (uint32_t i = tid; i < 39; i += nthreads) s_small[27 + i] = p.order_offset[i];
   HfLaneTables T;
+  T.tinfo = s_small;
+  T.order_offset = s_small + 27;
   T.ctx = s_ctx;
   T.cfg = s_cfg;
   T.bctx = s_bctx;

@@ -34,6 +34,10 @@ __device__ __constant__ const uint8_t kTInfo[27][5] = {
 
 // Tables one CTA shares (shared memory on the device, plain host memory under emulation).
 struct HfLaneTables {
+  // Lanes index these with their own block's transform type / channel: from constant memory (kTInfo, the kernel
+  // parameter bank) such a lookup costs one replay per distinct address, from shared memory it is one access.
+  const uint32_t* tinfo;         // [27] hf_pack_tinfo(): width | blocks << 8 | order id << 16 | transposed << 24
+  const uint32_t* order_offset;  // [13 * 3] copy of DevHfParams::order_offset
   const uint8_t* ctx;        // [0..63): coefficient frequency context, [64..127): non-zero-count context
   const uint32_t* cfg;       // packed HybridUintConfig per cluster
   const uint8_t* bctx;       // block context map
@@ -46,6 +50,10 @@ struct HfLaneTables {
 // each (a count is at most 63). `nz[(c * 32 + x) * nz_stride]`: on the device the lanes of a CTA interleave
 // (nz_stride = blockDim.x) so that a warp's accesses to one (c, x) fall into consecutive bytes.
 __device__ __forceinline__ uint32_t hf_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+__device__ __forceinline__ uint32_t hf_pack_tinfo(uint32_t t) {
+  return uint32_t(kTInfo[t][0]) | (uint32_t(kTInfo[t][0]) * kTInfo[t][1]) << 8 | uint32_t(kTInfo[t][3]) << 16 |
+         uint32_t(kTInfo[t][4]) << 24;
+}
 
 template <bool SUB>
 __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, const DevFrame& f, const DevHfParams& p,
@@ -116,10 +124,11 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
           if (done) break;
           const size_t gi = size_t(by0 + y) * f.bw + bx0 + x;
           const int32_t qf = f.blk_mul[gi];
-          w8 = kTInfo[t][0];
-          num_blocks = w8 * kTInfo[t][1];
-          order_id = kTInfo[t][3];
-          transpose = kTInfo[t][4];
+          const uint32_t ti = T.tinfo[t];
+          w8 = ti & 0xff;
+          num_blocks = (ti >> 8) & 0xff;
+          order_id = (ti >> 16) & 0xff;
+          transpose = ti >> 24;
           num_blocks_log = 31u - uint32_t(__clz(int(num_blocks)));
           uint32_t lf_idx = 0;
           if (p.has_lf_quant) {
@@ -129,12 +138,14 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
               if (p.num_lf_thr[cc]) {
                 const int32_t q = SUB ? f.lf_quant[cc][size_t((by0 + y) >> f.vshift[cc]) * f.bw + ((bx0 + x) >> f.hshift[cc])]
                                       : f.lf_quant[cc][gi];
+#pragma unroll 1
                 for (uint32_t i = 0; i < p.num_lf_thr[cc]; ++i)
                   if (q > thr_base[cc][i]) ++lf_idx;
               }
             }
           }
           uint32_t hf_idx = 0;
+#pragma unroll 1
           for (uint32_t i = 0; i < p.num_qf_thr; ++i)
             if (qf > int32_t(p.qf_thresholds[i])) ++hf_idx;
           blk_ctx_idx = hf_idx * lf_idx_mul + lf_idx;
@@ -193,7 +204,7 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
       if (value == 0) continue;
       non_zeros = value;
       prev_nonzero = (non_zeros <= num_blocks * 4) ? 1 : 0;
-      order = p.orders + p.order_offset[order_id * 3 + c];
+      order = p.orders + T.order_offset[order_id * 3 + c];
       size = num_blocks * 64;
       cmap = cluster_map + block_ctx * 458 + 37 * nbc;
       nzc_ctx = T.ctx[64 + ((non_zeros - 1) >> num_blocks_log)];

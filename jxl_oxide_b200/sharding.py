@@ -21,3 +21,40 @@ def max_over_ranks_ms(local_ms, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def gather_frames(local_frames, num_frames, dst=0, group=None):
+    """BASELINE config #5's delivery step: every rank holds the packed frames `frames_for_rank()` gave it (equally
+    shaped tensors, on the GPU with the nccl backend); rank `dst` receives all `num_frames` of them in frame order, the
+    other ranks get None. One `gather` per round of `world_size` frames (frame k of round r lives on rank k): with
+    nccl the copies go GPU to GPU over NVLink / NVSwitch, nothing is staged through the host. Frames are
+    independent, so this is the path's only exchange and it carries finished pixels, never intermediate data."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = frames_for_rank(num_frames, rank, world)
+    if len(local_frames) != len(mine):
+        raise ValueError(f"rank {rank} holds {len(local_frames)} frames, its share of {num_frames} is {len(mine)}")
+    if world == 1:
+        return list(local_frames)
+    rounds = (num_frames + world - 1) // world
+    # a rank without a frame in the last (ragged) round still takes part in the collective with a dummy
+    proto = local_frames[0] if local_frames else None
+    out = [None] * num_frames
+    for r in range(rounds):
+        have = r < len(local_frames)
+        if have:
+            send = local_frames[r].contiguous()
+        else:
+            if proto is None:
+                raise ValueError("a rank without any frame cannot size its placeholder; pass at least world_size frames")
+            send = torch.empty_like(proto)
+        recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+        dist.gather(send, recv, dst=dst, group=group)
+        if rank == dst:
+            for src in range(world):
+                k = r * world + src
+                if k < num_frames:
+                    out[k] = recv[src]
+    return out if rank == dst else None

@@ -119,7 +119,11 @@ void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     ctx[i] = hftab::kCoeffFreqContext[i];
     ctx[64 + i] = hftab::kCoeffNumNonzeroContext[i];
   }
+  uint32_t tinfo[27];
+  for (uint32_t t = 0; t < 27; ++t) tinfo[t] = hf_pack_tinfo(t);
   HfLaneTables T;
+  T.tinfo = tinfo;
+  T.order_offset = p.order_offset;
   T.ctx = ctx;
   T.cfg = cfg.data();
   T.bctx = p.block_ctx_map;

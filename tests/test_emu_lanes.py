@@ -4,7 +4,7 @@ The per-stream function every device thread runs is plain integer C++ without cr
 tests/emu/ compiles it for the host and plugs it into the oracle's planner in place of the oracle's own
 HF decoder. These tests pin its LOGIC (state machine, contexts, stores, end positions) against the oracle on
 every VarDCT shape the fixtures hold; the device launch itself (shared-memory staging, lane interleave) is
-covered by tests/test_gpu_parity.py::test_hf_lanes_* on a GPU.
+covered by tests/test_zz_gpu_schedules.py::test_hf_lanes_* on a GPU.
 """
 import ctypes
 import os

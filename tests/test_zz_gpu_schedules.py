@@ -1,4 +1,5 @@
-"""GPU parity of the thread-per-stream HF coefficient kernel (decode_hf_lanes_kernel, kernels/hf_lanes.cuh).
+"""GPU parity of the opt-in schedules and delivery paths: the thread-per-stream HF coefficient kernel
+(decode_hf_lanes_kernel, kernels/hf_lanes.cuh) and packing into a device buffer (jxlb_frame_write_to_device).
 
 The kernel is an opt-in schedule (jxlb_set_hf_streams_per_cta / JXLB_HF_LANES) of the same streams the default
 one-warp-per-stream kernel decodes; its per-stream logic is pinned on the CPU by tests/test_emu_lanes.py. Here the
@@ -75,3 +76,21 @@ def test_hf_lanes_errors_are_values(dec):
         dec.decode(bytes(data))  # the decoder keeps working
     finally:
         dec.set_hf_streams_per_cta(0)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32])
+def test_write_to_device_matches_write_to_buffer(dec, dtype):
+    """jxlb_frame_write_to_device: the packed frame stays in HBM (input of the NCCL gather, BASELINE config #5)."""
+    import jxl_oxide_b200
+    import torch
+    dec.decode(fixture_bytes("sunset_logo", "input.jxl"))  # orientation 7, alpha
+    for orientation in (0, 1, 6):
+        host = dec.frame_to_buffer(0, dtype, orientation)
+        dev = dec.frame_to_torch(0, dtype, orientation)
+        assert dev.is_cuda and tuple(dev.shape) == host.shape
+        got = dev.cpu().view(torch.uint8).numpy().view(dtype).reshape(host.shape)
+        assert np.array_equal(got.view(np.uint8), host.view(np.uint8))
+    # a host pointer is refused with an error value, not dereferenced on the device
+    pinned = np.empty(host.shape, dtype=dtype)
+    rc = dec._L.jxlb_frame_write_to_device(dec._h, 0, {1: 0, 2: 1, 4: 2}[np.dtype(dtype).itemsize], 0, pinned.ctypes.data, pinned.nbytes)
+    assert rc != jxl_oxide_b200.OK
