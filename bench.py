@@ -201,6 +201,7 @@ def algorithmic_bytes(kernel, w, h, stream_bytes):
         "modular_decode": stream_bytes * 0.12 + lf * 3 * 4 + lf * 4 + (px / 4096) * 8,  # LF + HfMetadata streams
         "decode_hf": stream_bytes * 0.88 + px * 12,       # HF sections read, 3 x i32 coefficients written
         "build_block_info": lf * 4 * 4,
+        "hf_block_ctx": lf * 6 * 4,                        # type, multiplier, 3 quantised LF read, 1 word written
         "hf_dequant_cfl": px * 24,
         "hf_transform": px * 24 + lf * 12,
         "filters_fused": px * 24,                          # Gaborish + EPF + colour in one pass
@@ -212,7 +213,7 @@ def algorithmic_bytes(kernel, w, h, stream_bytes):
     return table.get(kernel)
 
 
-KERNELS = ["modular_decode", "build_block_info", "decode_hf", "lf_dequant", "lf_cfl", "lf_smooth", "hf_dequant_cfl",
+KERNELS = ["modular_decode", "build_block_info", "hf_block_ctx", "decode_hf", "lf_dequant", "lf_cfl", "lf_smooth", "hf_dequant_cfl",
            "hf_transform", "filters_fused", "gaborish", "epf_step", "xyb_to_rgb", "copy_rect", "squeeze_inverse", "rct_inverse",
            "int_to_float", "modular_xyb", "palette_inverse_simple"]
 

@@ -889,9 +889,17 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
   temps_.push_back(d_end);
   temps_.push_back(d_status);
+  uint32_t* d_blk_ctx = nullptr;
+  if (hf_streams_per_cta > 0) {
+    d_blk_ctx = static_cast<uint32_t*>(dmalloc(size_t(st.bw) * st.bh * 4));
+    temps_.push_back(d_blk_ctx);
+    begin_k("hf_block_ctx");
+    launch_hf_block_ctx(dev_frame(st), p, d_blk_ctx, stream_);
+    end_k();
+  }
   begin_k("decode_hf");
   if (hf_streams_per_cta > 0)
-    launch_decode_hf_lanes(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
+    launch_decode_hf_lanes(active_cs_, dev_frame(st), p, d_blk_ctx, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
                            hf_streams_per_cta, stream_);
   else
     launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0, stream_);

@@ -266,7 +266,14 @@ __host__ __device__ inline HfLaneSmem hf_lane_layout(const DevHfParams& p, uint3
 }
 
 template <bool SUB>
+__global__ void __launch_bounds__(256) hf_block_ctx_kernel(DevFrame f, DevHfParams p, uint32_t* __restrict__ out) {
+  const uint32_t bx = blockIdx.x * 32 + (threadIdx.x & 31), by = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (bx < f.bw && by < f.bh) out[size_t(by) * f.bw + bx] = hf_block_ctx_cell<SUB>(f, p, bx, by);
+}
+
+template <bool SUB>
 __global__ void __launch_bounds__(128) decode_hf_lanes_kernel(const uint8_t* __restrict__ cs, DevFrame f, DevHfParams p,
+                                                              const uint32_t* __restrict__ blk_ctx,
                                                               const DevHfJob* __restrict__ jobs,
                                                               uint64_t* __restrict__ end_bits, int* __restrict__ status,
                                                               int num_jobs, int first_pass) {
@@ -316,13 +323,21 @@ __global__ void __launch_bounds__(128) decode_hf_lanes_kernel(const uint8_t* __r
   const int job_idx = blockIdx.x * int(nthreads) + int(tid);
   if (job_idx >= num_jobs) return;
   const DevHfJob job = jobs[job_idx];
-  hf_lane_decode<SUB>(cs, f, p, T, job, smem + L.nz + tid, nthreads, first_pass, end_bits + job_idx, status + job_idx);
+  hf_lane_decode<SUB>(cs, f, p, T, blk_ctx, job, smem + L.nz + tid, nthreads, first_pass, end_bits + job_idx,
+                      status + job_idx);
 }
 
 }  // namespace
 
-void launch_decode_hf_lanes(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
-                            int* status, int num_jobs, int first_pass, int streams_per_cta, cudaStream_t stream) {
+void launch_hf_block_ctx(DevFrame f, DevHfParams p, uint32_t* out, cudaStream_t stream) {
+  const dim3 grid((f.bw + 31) / 32, (f.bh + 7) / 8);
+  if (f.subsampled) hf_block_ctx_kernel<true><<<grid, 256, 0, stream>>>(f, p, out);
+  else hf_block_ctx_kernel<false><<<grid, 256, 0, stream>>>(f, p, out);
+}
+
+void launch_decode_hf_lanes(const uint8_t* cs, DevFrame f, DevHfParams p, const uint32_t* blk_ctx, const DevHfJob* jobs,
+                            uint64_t* end_bits, int* status, int num_jobs, int first_pass, int streams_per_cta,
+                            cudaStream_t stream) {
   if (num_jobs <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
@@ -334,9 +349,9 @@ void launch_decode_hf_lanes(const uint8_t* cs, DevFrame f, DevHfParams p, const 
   const HfLaneSmem L = hf_lane_layout(p, uint32_t(nthreads));
   const int ctas = (num_jobs + nthreads - 1) / nthreads;
   if (f.subsampled)
-    decode_hf_lanes_kernel<true><<<ctas, nthreads, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+    decode_hf_lanes_kernel<true><<<ctas, nthreads, L.total, stream>>>(cs, f, p, blk_ctx, jobs, end_bits, status, num_jobs, first_pass);
   else
-    decode_hf_lanes_kernel<false><<<ctas, nthreads, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+    decode_hf_lanes_kernel<false><<<ctas, nthreads, L.total, stream>>>(cs, f, p, blk_ctx, jobs, end_bits, status, num_jobs, first_pass);
 }
 
 void launch_decode_hf(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,

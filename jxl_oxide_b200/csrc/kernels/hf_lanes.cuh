@@ -55,10 +55,45 @@ __device__ __forceinline__ uint32_t hf_pack_tinfo(uint32_t t) {
          uint32_t(kTInfo[t][4]) << 24;
 }
 
+// Pre-pass, one thread per 8x8 cell (hf_coeff.rs:100-127): everything a stream needs to know about a varblock before
+// its first symbol -- transform type and the block's context offset `hf_idx * lf_idx_mul + lf_idx` from the quantised
+// LF values and the HF multiplier -- packed as `type | offset << 8`; 0xffffffff for cells that are not a varblock's
+// top-left corner. Keeps the threshold loops and five dependent loads out of the streams' serial walk.
+constexpr uint32_t kHfNoBlock = 0xffffffffu;
+template <bool SUB>
+__device__ __forceinline__ uint32_t hf_block_ctx_cell(const DevFrame& f, const DevHfParams& p, uint32_t bx, uint32_t by) {
+  const size_t gi = size_t(by) * f.bw + bx;
+  const int32_t t = f.blk_type[gi];
+  if (t < 0) return kHfNoBlock;
+  const int32_t qf = f.blk_mul[gi];
+  const int32_t* thr = p.lf_thresholds;
+  uint32_t lf_idx = 0;
+  if (p.has_lf_quant) {
+    const int32_t* thr_base[3] = {thr, thr + p.num_lf_thr[0], thr + p.num_lf_thr[0] + p.num_lf_thr[1]};
+    for (int kk = 0; kk < 3; ++kk) {
+      const int cc = kk == 0 ? 0 : (kk == 1 ? 2 : 1);
+      lf_idx *= p.num_lf_thr[cc] + 1;
+      if (p.num_lf_thr[cc]) {
+        const int32_t q = SUB ? f.lf_quant[cc][size_t(by >> f.vshift[cc]) * f.bw + (bx >> f.hshift[cc])] : f.lf_quant[cc][gi];
+#pragma unroll 1
+        for (uint32_t i = 0; i < p.num_lf_thr[cc]; ++i)
+          if (q > thr_base[cc][i]) ++lf_idx;
+      }
+    }
+  }
+  uint32_t hf_idx = 0;
+#pragma unroll 1
+  for (uint32_t i = 0; i < p.num_qf_thr; ++i)
+    if (qf > int32_t(p.qf_thresholds[i])) ++hf_idx;
+  const uint32_t lf_idx_mul = (p.num_lf_thr[0] + 1) * (p.num_lf_thr[1] + 1) * (p.num_lf_thr[2] + 1);
+  return uint32_t(t) | (hf_idx * lf_idx_mul + lf_idx) << 8;
+}
+
 template <bool SUB>
 __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, const DevFrame& f, const DevHfParams& p,
-                                               const HfLaneTables& T, const DevHfJob& job, uint8_t* nz, uint32_t nz_stride,
-                                               int first_pass, uint64_t* end_bit, int* status) {
+                                               const HfLaneTables& T, const uint32_t* __restrict__ blk_ctx,
+                                               const DevHfJob& job, uint8_t* nz, uint32_t nz_stride, int first_pass,
+                                               uint64_t* end_bit, int* status) {
   DevBitReader br;
   int err = kDevOk;
   br.init(cs, job.bit_pos);
@@ -80,8 +115,6 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
   const uint32_t bx0 = gx * gb, by0 = gy * gb;
   const uint32_t width = hf_umin(gb, f.bw - bx0), height = hf_umin(gb, f.bh - by0);
   for (uint32_t i = 0; i < 96; ++i) nz[i * nz_stride] = 0;
-  const int32_t* thr_base[3] = {p.lf_thresholds, p.lf_thresholds + p.num_lf_thr[0],
-                                p.lf_thresholds + p.num_lf_thr[0] + p.num_lf_thr[1]};
 
   // ---- block cursor ----
   uint32_t x = 0, y = 0;     // the varblock being decoded (its top-left cell)
@@ -107,7 +140,7 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
           // next varblock origin in raster order
           if (first_block) first_block = false;
           else ++x;
-          int32_t t = -1;
+          uint32_t info = kHfNoBlock;
           for (;;) {
             if (x >= width) {
               x = 0;
@@ -117,38 +150,18 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
               done = true;
               break;
             }
-            t = f.blk_type[size_t(by0 + y) * f.bw + bx0 + x];
-            if (t >= 0) break;
+            info = __ldg(blk_ctx + size_t(by0 + y) * f.bw + bx0 + x);
+            if (info != kHfNoBlock) break;
             ++x;
           }
           if (done) break;
-          const size_t gi = size_t(by0 + y) * f.bw + bx0 + x;
-          const int32_t qf = f.blk_mul[gi];
-          const uint32_t ti = T.tinfo[t];
+          const uint32_t ti = T.tinfo[info & 0xff];
           w8 = ti & 0xff;
           num_blocks = (ti >> 8) & 0xff;
           order_id = (ti >> 16) & 0xff;
           transpose = ti >> 24;
           num_blocks_log = 31u - uint32_t(__clz(int(num_blocks)));
-          uint32_t lf_idx = 0;
-          if (p.has_lf_quant) {
-            for (int kk = 0; kk < 3; ++kk) {
-              const int cc = kk == 0 ? 0 : (kk == 1 ? 2 : 1);
-              lf_idx *= p.num_lf_thr[cc] + 1;
-              if (p.num_lf_thr[cc]) {
-                const int32_t q = SUB ? f.lf_quant[cc][size_t((by0 + y) >> f.vshift[cc]) * f.bw + ((bx0 + x) >> f.hshift[cc])]
-                                      : f.lf_quant[cc][gi];
-#pragma unroll 1
-                for (uint32_t i = 0; i < p.num_lf_thr[cc]; ++i)
-                  if (q > thr_base[cc][i]) ++lf_idx;
-              }
-            }
-          }
-          uint32_t hf_idx = 0;
-#pragma unroll 1
-          for (uint32_t i = 0; i < p.num_qf_thr; ++i)
-            if (qf > int32_t(p.qf_thresholds[i])) ++hf_idx;
-          blk_ctx_idx = hf_idx * lf_idx_mul + lf_idx;
+          blk_ctx_idx = info >> 8;
           ci = 0;
         }
         // channel slot ci of the current block

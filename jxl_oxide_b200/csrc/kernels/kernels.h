@@ -130,8 +130,11 @@ struct DevHfJob {
 void launch_decode_hf(const uint8_t* codestream, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
                       int* status, int num_jobs, int first_pass, cudaStream_t stream);
 // Same contract, one thread per stream (kernels/hf_lanes.cuh); `streams_per_cta` in {32, 64, 128}.
-void launch_decode_hf_lanes(const uint8_t* codestream, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
-                            int* status, int num_jobs, int first_pass, int streams_per_cta, cudaStream_t stream);
+// `blk_ctx` (bw x bh words) comes from launch_hf_block_ctx: transform type and context offset of every varblock origin.
+void launch_hf_block_ctx(DevFrame f, DevHfParams p, uint32_t* out, cudaStream_t stream);
+void launch_decode_hf_lanes(const uint8_t* codestream, DevFrame f, DevHfParams p, const uint32_t* blk_ctx, const DevHfJob* jobs,
+                            uint64_t* end_bits, int* status, int num_jobs, int first_pass, int streams_per_cta,
+                            cudaStream_t stream);
 
 struct DevLfDequantJob {
   DevLfGroupRect rect;

@@ -142,6 +142,11 @@ void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
     return jobs[a].bit_limit - jobs[a].bit_pos > jobs[b].bit_limit - jobs[b].bit_pos;
   });
+  // the pre-pass kernel: one "thread" per 8x8 cell
+  std::vector<uint32_t> blk_ctx(size_t(f.bw) * f.bh);
+  for (uint32_t by = 0; by < f.bh; ++by)
+    for (uint32_t bx = 0; bx < f.bw; ++bx)
+      blk_ctx[size_t(by) * f.bw + bx] = f.subsampled ? hf_block_ctx_cell<true>(f, p, bx, by) : hf_block_ctx_cell<false>(f, p, bx, by);
   constexpr uint32_t kThreads = 32;
   std::vector<uint8_t> nz(96 * kThreads, 0xee);
   for (size_t i = 0; i < perm.size(); ++i) {
@@ -150,8 +155,8 @@ void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     uint64_t end = 0;
     int status = 0;
     const uint32_t tid = uint32_t(i % kThreads);
-    if (f.subsampled) hf_lane_decode<true>(cs, f, p, T, dj, nz.data() + tid, kThreads, pass == 0 ? 1 : 0, &end, &status);
-    else hf_lane_decode<false>(cs, f, p, T, dj, nz.data() + tid, kThreads, pass == 0 ? 1 : 0, &end, &status);
+    if (f.subsampled) hf_lane_decode<true>(cs, f, p, T, blk_ctx.data(), dj, nz.data() + tid, kThreads, pass == 0 ? 1 : 0, &end, &status);
+    else hf_lane_decode<false>(cs, f, p, T, blk_ctx.data(), dj, nz.data() + tid, kThreads, pass == 0 ? 1 : 0, &end, &status);
     if (status != kDevOk)
       throw Error(status == kDevOverrun ? kErrEof : (status == kDevUnsupported ? kErrUnsupported : kErrDeviceDecode),
                   "emulated HF lane: status " + std::to_string(status) + " in group " + std::to_string(job.group_idx));
