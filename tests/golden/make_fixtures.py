@@ -17,6 +17,7 @@ CASES = {
     "grayalpha": ("decode/grayalpha", ["input.jxl", "output.buf.zst"]),
     "squeeze_edge": ("decode/squeeze_edge", ["input.jxl", "output.buf.zst"]),
     "issue_311": ("decode/issue_311", ["input.jxl", "output.buf.zst"]),
+    "issue_24": ("decode/issue_24", ["input.jxl", "output.buf.zst"]),  # 1x1 VarDCT animation, 9 keyframes
     "minecraft_vardct_e7": ("decode/minecraft_vardct_e7", ["input.jxl"]),
     "opsin_inverse": ("conformance/testcases/opsin_inverse", ["input.jxl", "ref.png"]),
     "alpha_premultiplied": ("conformance/testcases/alpha_premultiplied", ["input.jxl"]),

@@ -27,6 +27,27 @@ def test_modular_golden_bit_exact(oracle, name):
     assert np.array_equal(act, exp)
 
 
+def test_vardct_golden_issue_24_all_keyframes(oracle):
+    """The reference's only VarDCT fixture whose golden buffer is in the tree: a 1 x 1 grayscale
+    VarDCT animation, nine keyframes, replayed like tests/decode/mod.rs:29-86 (per keyframe: marker 0, then the planes
+    as u16 = (v * 65535 + 0.5)). The reference allows 0.004 * 65535 = 262 for VarDCT; the oracle reproduces every
+    sample exactly."""
+    gold = oracle.zstd_decompress(fixture_bytes("issue_24", "output.buf.zst"))
+    w, h, ch = struct.unpack("<III", gold[:12])
+    img = oracle.OracleImage(fixture_bytes("issue_24", "input.jxl"))
+    assert (w, h, ch) == (1, 1, 1) and img.num_frames == 9
+    off = 12
+    for i in range(img.num_frames):
+        assert gold[off] == 0
+        planes, _, is_vardct = img.frame(i)
+        assert is_vardct and planes.shape == (ch, h, w)
+        exp = np.frombuffer(gold, dtype="<u2", count=w * h * ch, offset=off + 1).reshape(ch, h, w)
+        act = (planes * np.float32(65535.0) + np.float32(0.5)).astype(np.uint16)
+        assert np.array_equal(act, exp), f"keyframe {i}"
+        off += 1 + w * h * ch * 2
+    assert gold[off] == 0xFF and off + 1 == len(gold)
+
+
 def test_vardct_conformance_opsin_inverse(oracle):
     """ISO 18181-3 level of agreement with libjxl's reference rendering (8-bit ref.png):
     crates/jxl-oxide-tests/tests/conformance/mod.rs:139-368 uses peak 0.004 for VarDCT."""

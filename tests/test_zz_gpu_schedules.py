@@ -94,3 +94,15 @@ def test_write_to_device_matches_write_to_buffer(dec, dtype):
     pinned = np.empty(host.shape, dtype=dtype)
     rc = dec._L.jxlb_frame_write_to_device(dec._h, 0, {1: 0, 2: 1, 4: 2}[np.dtype(dtype).itemsize], 0, pinned.ctypes.data, pinned.nbytes)
     assert rc != jxl_oxide_b200.OK
+
+
+def test_issue_24_one_pixel_vardct_animation(dec, oracle):
+    """The reference's 1 x 1 VarDCT animation (its golden buffer pins the oracle in test_oracle_golden.py): every
+    keyframe identical to the oracle on the device."""
+    data = fixture_bytes("issue_24", "input.jxl")
+    dec.decode(data)
+    img = oracle.OracleImage(data)
+    assert dec.num_frames() == img.num_frames == 9
+    for i in range(9):
+        got, want = dec.frame_planar(i), img.frame(i)[0]
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
