@@ -21,6 +21,73 @@ std::atomic<uint64_t> g_hf_streams{0};
 // how many HF streams went through hf_lane_decode() so far (the test checks that the emulated path really ran)
 extern "C" uint64_t jxle_hf_streams() { return g_hf_streams.load(); }
 
+// Known-answer check of the device bit reader (common.cuh: word-ahead, 64-bit buffer) against the host reader
+// (host/bitreader.h) that the planner and the oracle use: random start offsets, random read widths 0..32, peeks,
+// and pos() after every step. Returns 0 when every step agreed, otherwise 1 + the index of the first mismatch.
+extern "C" uint64_t jxle_bitreader_selftest(uint64_t seed, uint32_t steps) {
+  std::vector<uint64_t> store(4096 + 8, 0);
+  uint64_t x = seed * 0x9e3779b97f4a7c15ull + 1;
+  auto rnd = [&]() {
+    x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+    return x;
+  };
+  for (size_t i = 0; i < 4096; ++i) store[i] = rnd();
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(store.data());
+  const uint64_t start = rnd() % 4096;
+  jxlb::BitReader host(bytes, 4096 * 8, start);
+  jxlb::DevBitReader dev;
+  dev.init(bytes, start);
+  for (uint32_t i = 0; i < steps; ++i) {
+    if (host.pos() + 64 > 4096ull * 8 * 8) break;
+    if (dev.pos() != host.pos()) return 1 + i;
+    const uint32_t n = uint32_t(rnd() % 33);
+    if (rnd() & 1) {
+      if (dev.peek(n) != host.peek(n)) return 1 + i;
+    }
+    if (dev.read(n) != host.read(n)) return 1 + i;
+  }
+  return 0;
+}
+
+// cv_read_uint (stream_common.cuh) against the closed form of the hybrid integer coding (jxl-coding/src/lib.rs:572-605):
+// token < split -> token; otherwise n extra bits follow, value = (((1 << msb | mid) << n | extra) << lsb) | low.
+extern "C" uint64_t jxle_hybrid_uint_selftest(uint64_t seed, uint32_t steps) {
+  std::vector<uint64_t> store(1024 + 8, 0);
+  uint64_t x = seed * 0x9e3779b97f4a7c15ull + 7;
+  auto rnd = [&]() {
+    x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+    return x;
+  };
+  for (size_t i = 0; i < 1024; ++i) store[i] = rnd();
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(store.data());
+  for (uint32_t i = 0; i < steps; ++i) {
+    const uint32_t split_exponent = uint32_t(rnd() % 9);           // log_alphabet_size <= 8
+    const uint32_t msb = split_exponent ? uint32_t(rnd() % (split_exponent + 1)) : 0;
+    const uint32_t lsb = uint32_t(rnd() % (split_exponent - msb + 1));
+    const uint32_t cfg = split_exponent | msb << 8 | lsb << 16;
+    const uint32_t token = uint32_t(rnd() % 256);
+    const uint64_t pos = rnd() % (1024 * 64 - 128);
+    jxlb::BitReader host(bytes, 1024 * 8, pos);
+    jxlb::DevBitReader dev;
+    dev.init(bytes, pos);
+    const uint32_t got = jxlb::cv_read_uint(dev, cfg, token);
+    uint32_t want;
+    const uint32_t split = 1u << split_exponent;
+    if (token < split) {
+      want = token;
+    } else {
+      const uint32_t in_token = msb + lsb;
+      const uint32_t n = (split_exponent - in_token + ((token - split) >> in_token)) & 31;
+      const uint32_t low = token & ((1u << lsb) - 1);
+      const uint32_t mid = (token >> lsb) & ((1u << msb) - 1);
+      const uint64_t extra = host.read(n);
+      want = uint32_t(((((uint64_t(1) << msb | mid) << n) | extra) << lsb) | low);
+    }
+    if (got != want || dev.pos() != host.pos()) return 1 + i;
+  }
+  return 0;
+}
+
 namespace jxlo {
 
 class EmuBackend : public OracleBackend {

@@ -80,3 +80,21 @@ def test_emulated_lanes_reject_truncated_streams():
         with pytest.raises(oracle_lib.OracleError) as e2:
             oracle_lib.OracleImage(data[:cut], threads=2, emu=True)
         assert e1.value.code == e2.value.code
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_device_bit_reader_matches_host_reader(seed):
+    """DevBitReader (kernels/common.cuh) is shared by all three entropy kernels: random offsets / widths / peeks against
+    host/bitreader.h, position included."""
+    L = oracle_lib.emu_lib()
+    L.jxle_bitreader_selftest.restype = ctypes.c_uint64
+    L.jxle_bitreader_selftest.argtypes = [ctypes.c_uint64, ctypes.c_uint32]
+    assert L.jxle_bitreader_selftest(seed, 12000) == 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_device_hybrid_uint_matches_closed_form(seed):
+    L = oracle_lib.emu_lib()
+    L.jxle_hybrid_uint_selftest.restype = ctypes.c_uint64
+    L.jxle_hybrid_uint_selftest.argtypes = [ctypes.c_uint64, ctypes.c_uint32]
+    assert L.jxle_hybrid_uint_selftest(seed, 20000) == 0
