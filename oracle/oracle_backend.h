@@ -12,6 +12,9 @@
 // only at 8/16-bit by conformance ref.png — see DESIGN.md "Oracle".
 #pragma once
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <exception>
 #include <map>
@@ -67,6 +70,14 @@ class OracleBackend : public Backend {
   void xyb_to_rgb(const View v[3], const ColorParams& p) override;
   void ycbcr_to_rgb(const View v[3], const YcbcrParams& p) override;
   void stage_marker(const char* name, const View* views, int n) override;
+  // JXLO_TRACE=1: wall time of every host phase of the planner on stderr (where the CPU time of a frame goes)
+  void phase_mark(const char* name) override {
+    static const bool on = std::getenv("JXLO_TRACE") != nullptr;
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    if (name) std::fprintf(stderr, "[oracle] %-20s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(now - phase_t0_).count());
+    phase_t0_ = now;
+  }
 
   Plane& plane(int id) { return planes_.at(id); }
   // Stage snapshots (tightly packed rects), filled when capture is on.
@@ -109,6 +120,7 @@ class OracleBackend : public Backend {
   std::map<int, Plane> planes_;
   int next_id_ = 0;
   int threads_;
+  std::chrono::steady_clock::time_point phase_t0_ = std::chrono::steady_clock::now();
 };
 
 float linear_to_pq(float s, float intensity_target);  // oracle_render.cc

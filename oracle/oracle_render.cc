@@ -210,6 +210,8 @@ const int8_t kDist2[1][2] = {{0, 0}};
 
 void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, bool sigma_is_constant) {
   const size_t width = v[0].w, height = v[0].h;
+  auto T0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* n) { auto t = std::chrono::steady_clock::now(); if (std::getenv("JXLO_TRACE")) std::fprintf(stderr, "  epf %-10s %.1f ms\n", n, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t; };
   std::vector<float> bufs[2][3];
   for (int c = 0; c < 3; ++c) {
     bufs[0][c].resize(width * height);
@@ -225,6 +227,7 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
     sig = sp.f32();
     sig_stride = sp.w;
   }
+  lap("copy_in");
   int cur = 0;
   auto run_step = [&](int step) {
     const int8_t(*kernel)[2] = step == 0 ? kKernel2 : kKernel1;
@@ -234,6 +237,13 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
     const float step_multiplier = step == 0 ? p.pass0_sigma_scale : (step == 2 ? p.pass2_sigma_scale : 1.0f);
     const float* in[3] = {bufs[cur][0].data(), bufs[cur][1].data(), bufs[cur][2].data()};
     float* out[3] = {bufs[cur ^ 1][0].data(), bufs[cur ^ 1][1].data(), bufs[cur ^ 1][2].data()};
+    // Pixels whose whole stencil (kernel reach + distance-pattern reach) lies inside the image index the planes
+    // directly; the mirrored coordinates of the general path are only needed in a border of `reach` pixels. Same
+    // operations in the same order either way (this only keeps the CPU baseline from paying for mirror() per tap).
+    const ptrdiff_t reach = step == 0 ? 3 : (step == 1 ? 2 : 1);
+    ptrdiff_t koff[12], doff[5];
+    for (int k = 0; k < nk; ++k) koff[k] = ptrdiff_t(kernel[k][1]) * ptrdiff_t(width) + kernel[k][0];
+    for (int i = 0; i < nd; ++i) doff[i] = ptrdiff_t(dist[i][1]) * ptrdiff_t(width) + dist[i][0];
     parallel_for(height, [&](size_t y) {
       const bool is_y_border = ((y + 1) & 6) == 0;
       float sm[8];
@@ -242,6 +252,7 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
         sm[0] *= p.border_sad_mul;
         sm[7] *= p.border_sad_mul;
       }
+      const bool row_inside = ptrdiff_t(y) >= reach && ptrdiff_t(y) + reach < ptrdiff_t(height);
       for (size_t dx = 0; dx < width; ++dx) {
         float sigma_val = sigma_is_constant ? p.sigma_for_modular : sig[(y / 8) * sig_stride + dx / 8];
         if (sigma_val < 0.3f) {
@@ -250,29 +261,46 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
         }
         float sum_weights = 1.0f;
         float sum_channels[3] = {in[0][y * width + dx], in[1][y * width + dx], in[2][y * width + dx]};
-        for (int k = 0; k < nk; ++k) {
-          ptrdiff_t kx = ptrdiff_t(dx) + kernel[k][0], ky = ptrdiff_t(y) + kernel[k][1];
-          float d = 0.0f;
-          for (int c = 0; c < 3; ++c) {
-            float acc = 0.0f;
-            for (int i = 0; i < nd; ++i) {
-              size_t ay = mirror(ky + dist[i][1], height), ax = mirror(kx + dist[i][0], width);
-              size_t by = mirror(ptrdiff_t(y) + dist[i][1], height), bx = mirror(ptrdiff_t(dx) + dist[i][0], width);
-              acc += std::fabs(in[c][ay * width + ax] - in[c][by * width + bx]);
+        // weight() (impls/generic/epf.rs:205-210)
+        const float neg_inv_sigma = 6.6f * (0.70710678118654752440f - 1.0f) / sigma_val * sm[dx & 7];
+        if (row_inside && ptrdiff_t(dx) >= reach && ptrdiff_t(dx) + reach < ptrdiff_t(width)) {
+          const size_t at = y * width + dx;
+          for (int k = 0; k < nk; ++k) {
+            float d = 0.0f;
+            for (int c = 0; c < 3; ++c) {
+              const float* pc = in[c] + at;
+              float acc = 0.0f;
+              for (int i = 0; i < nd; ++i) acc += std::fabs(pc[koff[k] + doff[i]] - pc[doff[i]]);
+              d += p.channel_scale[c] * acc;
             }
-            d += p.channel_scale[c] * acc;
+            float weight = std::max(1.0f + d * neg_inv_sigma, 0.0f);
+            sum_weights += weight;
+            for (int c = 0; c < 3; ++c) sum_channels[c] += weight * in[c][at + koff[k]];
           }
-          // weight() (impls/generic/epf.rs:205-210)
-          float neg_inv_sigma = 6.6f * (0.70710678118654752440f - 1.0f) / sigma_val * sm[dx & 7];
-          float weight = std::max(1.0f + d * neg_inv_sigma, 0.0f);
-          sum_weights += weight;
-          size_t my = mirror(ky, height), mx = mirror(kx, width);
-          for (int c = 0; c < 3; ++c) sum_channels[c] += weight * in[c][my * width + mx];
+        } else {
+          for (int k = 0; k < nk; ++k) {
+            ptrdiff_t kx = ptrdiff_t(dx) + kernel[k][0], ky = ptrdiff_t(y) + kernel[k][1];
+            float d = 0.0f;
+            for (int c = 0; c < 3; ++c) {
+              float acc = 0.0f;
+              for (int i = 0; i < nd; ++i) {
+                size_t ay = mirror(ky + dist[i][1], height), ax = mirror(kx + dist[i][0], width);
+                size_t by = mirror(ptrdiff_t(y) + dist[i][1], height), bx = mirror(ptrdiff_t(dx) + dist[i][0], width);
+                acc += std::fabs(in[c][ay * width + ax] - in[c][by * width + bx]);
+              }
+              d += p.channel_scale[c] * acc;
+            }
+            float weight = std::max(1.0f + d * neg_inv_sigma, 0.0f);
+            sum_weights += weight;
+            size_t my = mirror(ky, height), mx = mirror(kx, width);
+            for (int c = 0; c < 3; ++c) sum_channels[c] += weight * in[c][my * width + mx];
+          }
         }
         for (int c = 0; c < 3; ++c) out[c][y * width + dx] = sum_channels[c] / sum_weights;
       }
     });
     cur ^= 1;
+    lap("step");
   };
   if (p.iters == 3) run_step(0);
   run_step(1);

@@ -592,3 +592,19 @@ def test_lf_frame_streams_decode(oracle):
     planes, ncol, is_vardct = img.frame(0)
     assert is_vardct and planes.shape == (3, 600, 1000) and np.isfinite(planes).all()
     assert 0.2 < float(planes[1].max()) < 1.0  # luma comes from the LF frame's samples
+
+
+def test_epf_iteration_counts_change_the_image(oracle):
+    """tools/synth_enc.cc --epf-iters 0 / 1 / 3 (explicit restoration filter) next to the all-default filter (2): each
+    count decodes to a different image, ordered by how much smoothing it applies."""
+    import bench
+    imgs = {}
+    for it in (0, 1, 2, 3):
+        extra = () if it == 2 else ("--epf-iters", str(it))
+        imgs[it] = oracle.OracleImage(bench.synth_frame(520, 392, 11, extra=extra), threads=4).frame(0)[0]
+    for a in range(4):
+        for b in range(a + 1, 4):
+            assert not np.array_equal(imgs[a], imgs[b])
+    # more smoothing iterations move the image further from the unfiltered one
+    d = [float(np.abs(imgs[it] - imgs[0]).mean()) for it in (1, 2, 3)]
+    assert 0 < d[0] < d[1] < d[2]

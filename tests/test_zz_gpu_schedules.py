@@ -106,3 +106,21 @@ def test_issue_24_one_pixel_vardct_animation(dec, oracle):
     for i in range(9):
         got, want = dec.frame_planar(i), img.frame(i)[0]
         assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("iters", [0, 1, 3])
+def test_epf_iteration_counts(dec, oracle, iters):
+    """Restoration filter with 0 / 1 / 3 EPF iterations (the all-default filter of the other synthetic frames has 2):
+    3 iterations add the 12-neighbour step 0; fused production kernel and the stage-by-stage path against the oracle."""
+    data = bench.synth_frame(1000, 600, 7, extra=("--epf-iters", str(iters)))
+    img = oracle.OracleImage(data, threads=8)
+    want = img.frame(0)[0]
+    for fused in (True, False):
+        dec.set_fuse_filters(fused)
+        try:
+            dec.decode(data)
+            got = dec.frame_planar(0)
+        finally:
+            dec.set_fuse_filters(True)
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"fused={fused}"

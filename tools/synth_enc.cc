@@ -574,6 +574,7 @@ struct Args {
   uint32_t passes = 1;    // HF coefficients split over this many passes (progressive; pass p carries shift passes-1-p)
   std::string colour;     // "" = all-default metadata (sRGB); p3 | rec2020-gamma | gray | dci | custom: an enum colour encoding
   bool lf_frame = false;  // put the LF image into a separate Modular LF frame (frame type 1, lf_level 1)
+  uint32_t epf_iters = 2; // edge-preserving filter iterations (0..3); 2 = the all-default restoration filter
 };
 
 }  // namespace
@@ -591,6 +592,7 @@ int main(int argc, char** argv) {
     else if (s == "--lf-frame") a.lf_frame = true;
     else if (s == "--passes") a.passes = uint32_t(atoi(next().c_str()));
     else if (s == "--colour") a.colour = next();
+    else if (s == "--epf-iters") a.epf_iters = uint32_t(atoi(next().c_str()));
     else if (s == "-o") a.out = next();
     else fprintf(stderr, "unknown arg %s\n", s.c_str()), exit(2);
   }
@@ -997,7 +999,7 @@ int main(int argc, char** argv) {
     cs.write(2, 0);         // name: empty
     cs.write(1, 1);         // restoration filter all_default
     write_u64_small(0);     // frame extensions
-  } else if (P > 1) {
+  } else if (P > 1 || a.epf_iters != 2) {
     cs.write(1, 0);         // all_default
     cs.write(2, 0);         // Regular
     cs.write(1, 0);         // VarDCT
@@ -1005,14 +1007,29 @@ int main(int argc, char** argv) {
     cs.write(2, 0);         // upsampling = 1
     cs.write(3, 3);         // x_qm_scale
     cs.write(3, 2);         // b_qm_scale
-    cs.write(2, P - 1);     // num_passes (2 or 3)
-    cs.write(2, 0);         // num_ds = 0
-    for (uint32_t pass = 0; pass + 1 < P; ++pass) cs.write(2, P - 1 - pass);  // shift
+    cs.write(2, P - 1);     // num_passes (1, 2 or 3)
+    if (P > 1) {
+      cs.write(2, 0);       // num_ds = 0
+      for (uint32_t pass = 0; pass + 1 < P; ++pass) cs.write(2, P - 1 - pass);  // shift
+    }
     cs.write(1, 0);         // have_crop
     cs.write(2, 0);         // blend mode Replace
     cs.write(1, 1);         // is_last
     cs.write(2, 0);         // name: empty
-    cs.write(1, 1);         // restoration filter all_default
+    if (a.epf_iters == 2) {
+      cs.write(1, 1);       // restoration filter all_default
+    } else {                // filter.rs: Gaborish on with default weights, `epf_iters` EPF iterations, default parameters
+      cs.write(1, 0);
+      cs.write(1, 1);       //   gab_enabled
+      cs.write(1, 0);       //   gab_custom
+      cs.write(2, a.epf_iters & 3);
+      if (a.epf_iters & 3) {
+        cs.write(1, 0);     //   epf_sharp_custom
+        cs.write(1, 0);     //   epf_weight_custom
+        cs.write(1, 0);     //   epf_sigma_custom
+      }
+      write_u64_small(0);   //   extensions
+    }
     write_u64_small(0);     // frame extensions
   } else {
     cs.write(1, 1);  // FrameHeader all_default
