@@ -14,6 +14,11 @@
 #include "kernels.h"
 #include "stream_common.cuh"
 
+// Hook for the host emulation's SIMT model (tests/emu: which kind of symbol each loop trip decodes); nothing on the device.
+#ifndef JXLB_LANE_TRIP
+#define JXLB_LANE_TRIP(is_coefficient)
+#endif
+
 namespace jxlb {
 namespace {
 
@@ -205,6 +210,7 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
     }
 
     // ---- the part every lane executes together: one entropy-coded integer ----
+    JXLB_LANE_TRIP(in_coeffs);
     const uint32_t value = cv_read_uint(br, T.cfg[cl], cv_read_symbol(T.cv, ans_state, br, cl));
 
     if (!in_coeffs) {

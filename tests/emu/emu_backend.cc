@@ -10,12 +10,33 @@
 #include <cstring>
 
 #include "cuda_shim.h"
+
+#include <vector>
+// SIMT model: every loop trip of hf_lane_decode() reports whether it decodes a coefficient (1) or a block's non-zero
+// count (0); decode_hf() below lines the trips of 32 consecutive streams up the way a warp would execute them.
+namespace {
+thread_local std::vector<unsigned char>* g_trip_log = nullptr;
+inline void emu_trip(bool is_coefficient) {
+  if (g_trip_log) g_trip_log->push_back(is_coefficient ? 1 : 0);
+}
+}  // namespace
+#define JXLB_LANE_TRIP(c) emu_trip(c)
 #include "../../jxl_oxide_b200/csrc/kernels/hf_lanes.cuh"
 #include "../../oracle/oracle_backend.h"
 #include "../../jxl_oxide_b200/csrc/host/planner.h"
 
 namespace {
 std::atomic<uint64_t> g_hf_streams{0};
+// accumulated over all decode_hf() calls since the last reset:
+//   [0] streams, [1] symbols (= lane trips), [2] warp trips (sum over warps of the longest lane), [3] warp trips with
+//   at least one lane on a non-zero count (the divergent block walk runs), [4] warp trips with at least one lane on a
+//   coefficient, [5] warps
+uint64_t g_lane_stats[6] = {0, 0, 0, 0, 0, 0};
+}
+extern "C" void jxle_lane_stats(uint64_t out[6], int reset) {
+  for (int i = 0; i < 6; ++i) out[i] = g_lane_stats[i];
+  if (reset)
+    for (int i = 0; i < 6; ++i) g_lane_stats[i] = 0;
 }
 
 // how many HF streams went through hf_lane_decode() so far (the test checks that the emulated path really ran)
@@ -216,7 +237,9 @@ void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
       blk_ctx[size_t(by) * f.bw + bx] = f.subsampled ? hf_block_ctx_cell<true>(f, p, bx, by) : hf_block_ctx_cell<false>(f, p, bx, by);
   constexpr uint32_t kThreads = 32;
   std::vector<uint8_t> nz(96 * kThreads, 0xee);
+  std::vector<std::vector<unsigned char>> trips(perm.size());
   for (size_t i = 0; i < perm.size(); ++i) {
+    g_trip_log = &trips[i];
     HfGroupJob& job = jobs[perm[i]];
     DevHfJob dj{job.bit_pos, job.bit_limit, job.group_idx};
     uint64_t end = 0;
@@ -230,6 +253,20 @@ void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     job.end_bit = size_t(end);
     ++g_hf_streams;
   }
+  g_trip_log = nullptr;
+  for (size_t w0 = 0; w0 < trips.size(); w0 += 32) {  // one warp = 32 consecutive streams of the launch order
+    const size_t w1 = std::min(trips.size(), w0 + 32);
+    size_t longest = 0;
+    for (size_t i = w0; i < w1; ++i) longest = std::max(longest, trips[i].size()), g_lane_stats[1] += trips[i].size();
+    for (size_t t = 0; t < longest; ++t) {
+      bool any_header = false, any_coeff = false;
+      for (size_t i = w0; i < w1; ++i)
+        if (t < trips[i].size()) (trips[i][t] ? any_coeff : any_header) = true;
+      g_lane_stats[3] += any_header, g_lane_stats[4] += any_coeff;
+    }
+    g_lane_stats[2] += longest, ++g_lane_stats[5];
+  }
+  g_lane_stats[0] += trips.size();
 }
 
 OracleBackend* make_emu_backend(int threads) { return new EmuBackend(threads); }
