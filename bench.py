@@ -236,6 +236,11 @@ def run_ours(args, rank, world, local_rank):
             d.preload(k, frames[k])
     pinned = [torch.empty((3, h, w), dtype=torch.float32).pin_memory() for _ in range(nthreads)]
     pinned_np = [p.numpy() for p in pinned]
+    decs[0].decode_slot(shares[0][0])  # shape of the packed 8-bit image (orientation and alpha are the stream's)
+    u8_shape = decs[0].frame_to_buffer(0, np.uint8).shape
+    decs[0].release_frames()
+    pinned_u8 = [torch.empty(u8_shape, dtype=torch.uint8).pin_memory() for _ in range(nthreads)]
+    pinned_u8_np = [p.numpy() for p in pinned_u8]
 
     def step(e2e, nsteps=1):
         """`nsteps` passes over the batch. Every context walks its share of the batch `nsteps` times; contexts are
@@ -243,13 +248,16 @@ def run_ours(args, rank, world, local_rank):
         timed region) when --pipeline-steps asks for it; by default one step per call."""
         errs = []
 
-        def work(d, idxs, out, delay):
+        def work(d, idxs, out, out_u8, delay):
             try:
                 if delay > 0.0:
                     time.sleep(delay)  # de-phase the contexts (inside the timed region)
                 for _ in range(nsteps):
                     for k in idxs:
-                        if e2e:
+                        if e2e == "u8":
+                            d.decode(frames[k])                          # host bytes in
+                            d.frame_to_buffer(0, np.uint8, out=out_u8)   # interleaved 8-bit RGB out, packed on the device
+                        elif e2e:
                             d.decode(frames[k])          # host bytes in
                             d.frame_to_host(0, out)      # planar f32 out (pinned host)
                         else:
@@ -258,8 +266,8 @@ def run_ours(args, rank, world, local_rank):
                         d.release_frames()
             except Exception as e:  # noqa: BLE001
                 errs.append(e)
-        ts = [threading.Thread(target=work, args=(d, idxs, o, (i % args.stagger_groups) * args.stagger_ms / 1e3))
-              for i, (d, idxs, o) in enumerate(zip(decs, shares, pinned_np))]
+        ts = [threading.Thread(target=work, args=(d, idxs, o, o8, (i % args.stagger_groups) * args.stagger_ms / 1e3))
+              for i, (d, idxs, o, o8) in enumerate(zip(decs, shares, pinned_np, pinned_u8_np))]
         for t in ts:
             t.start()
         for t in ts:
@@ -310,6 +318,10 @@ def run_ours(args, rank, world, local_rank):
     launches = sum(d.launch_count() for d in decs) - launches0
     step(True)
     ms_e2e = timed(True, args.steps)
+    # the same end-to-end call with the output an 8-bit image (ImageStream::write_to_buffer::<u8>): 3 B/px cross the
+    # host link instead of the 12 B/px of f32 planes that bound `e2e`
+    step("u8")
+    ms_e2e_u8 = timed("u8", args.steps)
 
     # per-kernel device time (CUDA events on the launching stream), one extra profiled step
     for d in decs:
@@ -383,6 +395,7 @@ def run_ours(args, rank, world, local_rank):
                   "frames_at_rank0": (len([g for g in got if g is not None]) if got is not None else 0) if rank == 0 else None}
     value = total_px / (ms / args.steps / 1e3) / 1e6
     e2e_value = total_px / (ms_e2e / args.steps / 1e3) / 1e6
+    e2e_u8_value = total_px / (ms_e2e_u8 / args.steps / 1e3) / 1e6
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -444,6 +457,10 @@ def run_ours(args, rank, world, local_rank):
                    "hf_streams_per_cta": int(os.environ.get("JXLB_HF_LANES", "0") or 0)},
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
                 "d2h_bytes_per_step": int(px_per_frame * 12 * len(frames)), "ms_per_step": ms_e2e / args.steps},
+        "e2e_u8": {"value": e2e_u8_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
+                   "d2h_bytes_per_step": int(np.prod(u8_shape)) * len(frames), "ms_per_step": ms_e2e_u8 / args.steps,
+                   "note": "same call path as e2e, output = interleaved 8-bit RGB packed on the device "
+                           "(jxlb_frame_write_to_buffer); reported beside e2e, not instead of it"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "pipeline_roofline": pipeline,
         "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
         "kernel_ms_per_frame_solo": {k: round(v, 3) for k, v in solo.items()}, "cpu_baseline": cpu,

@@ -213,15 +213,19 @@ class Decoder:
         self._L.jxlb_image_original_icc(self._h, buf, n)
         return buf.raw
 
-    def frame_to_buffer(self, frame, dtype=np.uint8, orientation=0):
+    def frame_to_buffer(self, frame, dtype=np.uint8, orientation=0, out=None):
         """ImageStream::write_to_buffer: (height, width, channels) interleaved u8 / u16 / f32 samples with the
-        orientation applied (0 = the image header's)."""
+        orientation applied (0 = the image header's). `out`: a C-contiguous array of that shape to fill (e.g. pinned)."""
         info = self.frame_info(frame)
         img = self.image_info()
         orient = orientation or img.orientation
         w, h = (info.height, info.width) if orient >= 5 else (info.width, info.height)
         st = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
-        out = np.empty((h, w, self._L.jxlb_frame_stream_channels(self._h, frame)), dtype=dtype)
+        shape = (h, w, self._L.jxlb_frame_stream_channels(self._h, frame))
+        if out is None:
+            out = np.empty(shape, dtype=dtype)
+        elif out.shape != shape or out.dtype != np.dtype(dtype) or not out.flags.c_contiguous:
+            raise ValueError(f"out must be a C-contiguous {np.dtype(dtype)} array of shape {shape}")
         self._check(self._L.jxlb_frame_write_to_buffer(self._h, frame, st, orientation, out.ctypes.data, out.nbytes))
         return out
 
