@@ -218,6 +218,105 @@ KERNELS = ["modular_decode", "build_block_info", "hf_block_ctx", "decode_hf", "l
            "int_to_float", "modular_xyb", "palette_inverse_simple"]
 
 
+def run_probe(args):
+    """Child process of choose_hf_schedule(): one JSON line on stdout. Runs in its own process so that a fault in the
+    candidate kernel cannot poison the CUDA context of the measuring process."""
+    import torch
+    import jxl_oxide_b200 as J
+    dev = args.probe_device
+    torch.cuda.set_device(dev)
+    nctx = max(1, args.contexts)
+    _, frames, (w, h) = load_workload(args.workload, nctx)
+    if args.probe == "parity":
+        d = J.Decoder(dev)
+        d.decode(frames[0])
+        want = d.frame_planar(0).view(np.uint32).copy()
+        d.release_frames()
+        same = {}
+        for n in (32, 64, 128):
+            d.set_hf_streams_per_cta(n)
+            d.decode(frames[0])
+            same[str(n)] = bool(np.array_equal(want, d.frame_planar(0).view(np.uint32)))
+            d.release_frames()
+        print(json.dumps({"probe": "parity", "identical_to_default_kernel": same}))
+        return
+    decs = [J.Decoder(dev) for _ in range(nctx)]
+    for i, d in enumerate(decs):
+        d.set_hf_streams_per_cta(args.probe_lanes)
+        d.preload(0, frames[i % len(frames)])
+
+    def one_step():
+        errs = []
+
+        def work(d):
+            try:
+                d.decode_slot(0)
+                d.sync()
+                d.release_frames()
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=work, args=(d,)) for d in decs]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+    for _ in range(2):
+        one_step()
+    torch.cuda.synchronize()
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    print(json.dumps({"probe": "speed", "lanes": args.probe_lanes, "value": w * h * nctx / dt / 1e6, "ms_per_step": dt * 1e3}))
+
+
+def choose_hf_schedule(args, device):
+    """HF coefficient schedule for the timed run: (streams per CTA, report). An explicit --hf-lanes / JXLB_HF_LANES wins.
+    Otherwise child processes (a) decode a frame of the workload with the default kernel and with every candidate and
+    compare the f32 planes bit for bit, (b) time a short lock-step run (all contexts, one frame each) per surviving
+    candidate; a candidate is kept only if it is identical and at least 3 % faster than the default. Any failure,
+    timeout or disagreement falls back to the default kernel."""
+    env_knob = os.environ.get("JXLB_HF_LANES")
+    if env_knob is not None or args.hf_lanes != "auto":
+        n = int(env_knob if env_knob is not None else args.hf_lanes)
+        return (0 if n <= 0 else (32 if n <= 32 else (64 if n <= 64 else 128))), {"mode": "explicit"}
+    report = {"mode": "auto", "rule": "bit-identical to the default kernel and >= 3 % faster in a lock-step probe"}
+
+    def child(extra, timeout):
+        env = dict(os.environ)
+        env.pop("JXLB_HF_LANES", None)
+        fake = os.environ.get("JXLB_BENCH_FAKE_PROBE")  # host-logic test hook: canned child outputs, no GPU
+        if fake:
+            key = extra[1] + (":" + extra[3] if len(extra) > 3 else "")
+            return json.loads(fake)[key]
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--contexts",
+                            str(args.contexts), "--probe-device", str(device)] + extra,
+                           capture_output=True, text=True, timeout=timeout, env=env)
+        if p.returncode != 0:
+            raise RuntimeError(f"probe {extra} exited with {p.returncode}: {p.stderr[-300:]}")
+        return json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+    try:
+        par = child(["--probe", "parity"], 240)["identical_to_default_kernel"]
+        report["identical_to_default_kernel"] = par
+        cands = [n for n in (64, 128) if par.get(str(n))]
+        speeds = {}
+        if cands:
+            for n in [0] + cands:
+                speeds[str(n)] = child(["--probe", "speed", "--probe-lanes", str(n)], 240)["value"]
+        report["probe_mp_s"] = speeds
+        best = max(cands, key=lambda n: speeds[str(n)]) if cands else 0
+        chosen = best if best and speeds[str(best)] >= 1.03 * speeds["0"] else 0
+    except Exception as e:  # noqa: BLE001
+        report["fallback"] = f"{type(e).__name__}: {e}"[:300]
+        chosen = 0
+    report["chosen"] = chosen
+    return chosen, report
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import jxl_oxide_b200 as J
@@ -225,6 +324,8 @@ def run_ours(args, rank, world, local_rank):
     if not os.path.exists(J.LIB_PATH):
         jb.build()
     torch.cuda.set_device(local_rank)
+    # rank 0 picks the HF schedule before it touches its GPU; the other ranks adopt it after the process group is up
+    hf_lanes, hf_report = choose_hf_schedule(args, local_rank) if rank == 0 else (0, None)
     desc, frames, (w, h) = load_workload(args.workload, args.frames_per_step)
     px_per_frame = w * h
     nthreads = max(1, min(args.contexts, len(frames)))
@@ -280,6 +381,11 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        knob = torch.tensor([hf_lanes], dtype=torch.int32, device="cuda")
+        dist.broadcast(knob, src=0)
+        hf_lanes = int(knob.item())
+    for d in decs:
+        d.set_hf_streams_per_cta(hf_lanes)
 
     def barrier():
         if dist is not None:
@@ -454,7 +560,7 @@ def run_ours(args, rank, world, local_rank):
                    "step_barrier": "before and after the K timed steps (steps pipeline across decoder contexts)"
                                    if args.pipeline_steps else "after every step",
                    "stagger_ms": args.stagger_ms,
-                   "hf_streams_per_cta": int(os.environ.get("JXLB_HF_LANES", "0") or 0)},
+                   "hf_streams_per_cta": hf_lanes, "hf_schedule": hf_report},
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
                 "d2h_bytes_per_step": int(px_per_frame * 12 * len(frames)), "ms_per_step": ms_e2e / args.steps},
         "e2e_u8": {"value": e2e_u8_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
@@ -548,6 +654,13 @@ def main():
     ap.add_argument("--stagger-groups", type=int, default=4)
     ap.add_argument("--gather", default="none", choices=["none", "u8", "u16"],
                     help="also time decode + device-side packing + NCCL gather of every frame to rank 0 (BASELINE config #5)")
+    ap.add_argument("--hf-lanes", default="auto", choices=["auto", "0", "32", "64", "128"],
+                    help="HF coefficient schedule: streams per CTA of the thread-per-stream kernel, 0 = one warp per stream; "
+                         "auto = probe in child processes (parity against the default kernel, then a short A/B) and keep the "
+                         "faster one. JXLB_HF_LANES in the environment overrides.")
+    ap.add_argument("--probe", default=None, choices=["parity", "speed"], help=argparse.SUPPRESS)
+    ap.add_argument("--probe-lanes", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--probe-device", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--pipeline-steps", action="store_true",
                     help="run the K timed steps back to back, contexts joined only at the end (default: joined after every "
                          "step - measured faster, profiles/r01_progress.md)")
@@ -555,7 +668,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
+    if args.probe:
+        run_probe(args)
+    elif args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)
