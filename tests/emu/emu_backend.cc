@@ -168,6 +168,7 @@ void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   p.code.configs = cfg.data();
   p.code.log_alphabet_size = code.log_alphabet_size;
   p.code.use_prefix = code.use_prefix ? 1 : 0;
+  if (std::getenv("JXLE_TRACE")) std::fprintf(stderr, "[emu] decode_hf pass %u: %zu streams, %s, %u clusters, %u presets, subsampled %d\n", pass, jobs.size(), code.use_prefix ? "prefix" : "ANS", code.num_clusters, st.hfg->num_hf_presets, int(st.subsampled));
   p.code.num_clusters = code.num_clusters;
   p.code.cluster_map_size = uint32_t(code.cluster_map.size());
   p.code.prefix = code.prefix_table.data();

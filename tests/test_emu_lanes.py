@@ -66,7 +66,8 @@ def test_emulated_lanes_match_oracle_on_fixture(name):
     _same(_input(name))
 
 
-@pytest.mark.parametrize("extra", [(), ("--passes", "2"), ("--passes", "3"), ("--lf-frame",)])
+@pytest.mark.parametrize("extra", [(), ("--passes", "2"), ("--passes", "3"), ("--lf-frame",), ("--hf-presets", "3"),
+                                   ("--hf-presets", "5", "--passes", "2")])
 def test_emulated_lanes_match_oracle_on_synthetic_frames(extra):
     # ragged right / bottom groups, all 27 transform types, several groups per warp
     _same(bench.synth_frame(1000, 600, 7, extra=extra))

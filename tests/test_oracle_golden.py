@@ -608,3 +608,14 @@ def test_epf_iteration_counts_change_the_image(oracle):
     # more smoothing iterations move the image further from the unfiltered one
     d = [float(np.abs(imgs[it] - imgs[0]).mean()) for it in (1, 2, 3)]
     assert 0 < d[0] < d[1] < d[2]
+
+
+@pytest.mark.parametrize("presets", [2, 5])
+def test_hf_presets_select_their_own_cluster_maps(oracle, presets):
+    """No fixture of the reference uses more than one HF preset (hf_pass.rs / hf_coeff.rs:60-75), so tools/synth_enc.cc
+    --hf-presets N codes group g with preset g % N, every preset owning a differently clustered slice of the pass code:
+    the coefficients are the same, so the image must equal the single-preset stream's bit for bit."""
+    import bench
+    one = oracle.OracleImage(bench.synth_frame(1000, 600, 7), threads=4).frame(0)[0]
+    many = oracle.OracleImage(bench.synth_frame(1000, 600, 7, extra=("--hf-presets", str(presets))), threads=4).frame(0)[0]
+    assert np.array_equal(one.view(np.uint32), many.view(np.uint32))

@@ -124,3 +124,16 @@ def test_epf_iteration_counts(dec, oracle, iters):
             dec.set_fuse_filters(True)
         assert got.shape == want.shape
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"fused={fused}"
+
+
+@pytest.mark.parametrize("streams", [0, 32, 128])
+def test_hf_presets_on_the_device(dec, oracle, streams):
+    """Several HF presets (synthetic: no reference fixture has more than one): the default kernel stages one preset's
+    cluster-map slice per warp, the thread-per-stream kernel all of them per CTA."""
+    data = bench.synth_frame(1000, 600, 7, extra=("--hf-presets", "5", "--passes", "2"))
+    if streams:
+        _check(dec, oracle, data, streams)
+    else:
+        dec.decode(data)
+        got, want = dec.frame_planar(0), oracle.OracleImage(data, threads=8).frame(0)[0]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))

@@ -575,6 +575,7 @@ struct Args {
   std::string colour;     // "" = all-default metadata (sRGB); p3 | rec2020-gamma | gray | dci | custom: an enum colour encoding
   bool lf_frame = false;  // put the LF image into a separate Modular LF frame (frame type 1, lf_level 1)
   uint32_t epf_iters = 2; // edge-preserving filter iterations (0..3); 2 = the all-default restoration filter
+  uint32_t hf_presets = 1; // HF presets (hf_pass.rs): group g uses preset g % N, each preset has its own (rotated) cluster map
 };
 
 }  // namespace
@@ -593,6 +594,7 @@ int main(int argc, char** argv) {
     else if (s == "--passes") a.passes = uint32_t(atoi(next().c_str()));
     else if (s == "--colour") a.colour = next();
     else if (s == "--epf-iters") a.epf_iters = uint32_t(atoi(next().c_str()));
+    else if (s == "--hf-presets") a.hf_presets = std::max(1, atoi(next().c_str()));
     else if (s == "-o") a.out = next();
     else fprintf(stderr, "unknown arg %s\n", s.c_str()), exit(2);
   }
@@ -789,6 +791,20 @@ int main(int argc, char** argv) {
       hf_map[ctx] = uint8_t(4 + chan * 12 + bucket * 2 + prev);
     }
   }
+  // HF presets: preset p owns contexts [p * 495 * nbc, (p + 1) * 495 * nbc) of the pass code; its cluster map is the
+  // base map rotated by p clusters, so a decoder that picks the wrong preset's slice reads the stream with other
+  // distributions. Group g selects preset g % NP (written at the start of its stream).
+  const uint32_t NP = std::min<uint32_t>(a.hf_presets, num_groups);
+  if (NP > 1) {
+    const uint32_t ncl = 28, per = 495 * nbc;
+    std::vector<uint8_t> all(size_t(per) * NP);
+    for (uint32_t pr = 0; pr < NP; ++pr)
+      for (uint32_t ctx = 0; ctx < per; ++ctx) all[size_t(pr) * per + ctx] = uint8_t((hf_map[ctx] + pr) % ncl);
+    hf_map.swap(all);
+    for (uint32_t pass = 0; pass < P; ++pass)
+      for (uint32_t g = 0; g < num_groups; ++g)
+        for (Token& t : hf_tokens[size_t(pass) * num_groups + g]) t.ctx += (g % NP) * per;
+  }
   std::vector<std::vector<Token>> hf_all(P);
   for (uint32_t pass = 0; pass < P; ++pass)
     for (uint32_t g = 0; g < num_groups; ++g) {
@@ -836,17 +852,18 @@ int main(int argc, char** argv) {
   {  // HfGlobal
     BitWriter& w = sections[1 + num_lf];
     w.write(1, 1);                                   // default dequant matrices
-    w.write(int(ceil_log2_nonzero(num_groups)), 0);  // num_hf_presets - 1
+    w.write(int(ceil_log2_nonzero(num_groups)), NP - 1);  // num_hf_presets - 1
     for (uint32_t pass = 0; pass < P; ++pass) {
       write_u32(w, 2, 0, 0);  // used_orders = 0
-      hf_enc[pass].write_header(w, hf_all[pass], 495 * nbc, hf_map);
+      hf_enc[pass].write_header(w, hf_all[pass], 495 * nbc * NP, hf_map);
     }
     w.pad();
   }
   for (uint32_t pass = 0; pass < P; ++pass)
     for (uint32_t g = 0; g < num_groups; ++g) {
       BitWriter& w = sections[2 + num_lf + size_t(pass) * num_groups + g];
-      hf_enc[pass].write_tokens(w, hf_tokens[size_t(pass) * num_groups + g]);  // hfp takes 0 bits with a single preset
+      w.write(int(ceil_log2_nonzero(NP)), g % NP);  // hfp: 0 bits with a single preset
+      hf_enc[pass].write_tokens(w, hf_tokens[size_t(pass) * num_groups + g]);
       w.pad();
     }
 
