@@ -218,6 +218,10 @@ KERNELS = ["modular_decode", "build_block_info", "hf_block_ctx", "decode_hf", "l
            "int_to_float", "modular_xyb", "palette_inverse_simple"]
 
 
+# streams per CTA tried against the default (4, one warp each): 16 one-warp streams; 64 / 128 one-thread streams
+HF_CANDIDATES = (16, 64, 128)
+
+
 def run_probe(args):
     """Child process of choose_hf_schedule(): one JSON line on stdout. Runs in its own process so that a fault in the
     candidate kernel cannot poison the CUDA context of the measuring process."""
@@ -233,7 +237,7 @@ def run_probe(args):
         want = d.frame_planar(0).view(np.uint32).copy()
         d.release_frames()
         same = {}
-        for n in (32, 64, 128):
+        for n in HF_CANDIDATES:
             d.set_hf_streams_per_cta(n)
             d.decode(frames[0])
             same[str(n)] = bool(np.array_equal(want, d.frame_planar(0).view(np.uint32)))
@@ -283,7 +287,7 @@ def choose_hf_schedule(args, device):
     env_knob = os.environ.get("JXLB_HF_LANES")
     if env_knob is not None or args.hf_lanes != "auto":
         n = int(env_knob if env_knob is not None else args.hf_lanes)
-        return (0 if n <= 0 else (32 if n <= 32 else (64 if n <= 64 else 128))), {"mode": "explicit"}
+        return (0 if n <= 0 else (8 if n <= 8 else (16 if n <= 16 else (32 if n <= 32 else (64 if n <= 64 else 128))))), {"mode": "explicit"}
     report = {"mode": "auto", "rule": "bit-identical to the default kernel and >= 3 % faster in a lock-step probe"}
 
     def child(extra, timeout):
@@ -302,7 +306,7 @@ def choose_hf_schedule(args, device):
     try:
         par = child(["--probe", "parity"], 240)["identical_to_default_kernel"]
         report["identical_to_default_kernel"] = par
-        cands = [n for n in (64, 128) if par.get(str(n))]
+        cands = [n for n in HF_CANDIDATES if par.get(str(n))]
         speeds = {}
         if cands:
             for n in [0] + cands:
@@ -654,8 +658,9 @@ def main():
     ap.add_argument("--stagger-groups", type=int, default=4)
     ap.add_argument("--gather", default="none", choices=["none", "u8", "u16"],
                     help="also time decode + device-side packing + NCCL gather of every frame to rank 0 (BASELINE config #5)")
-    ap.add_argument("--hf-lanes", default="auto", choices=["auto", "0", "32", "64", "128"],
-                    help="HF coefficient schedule: streams per CTA of the thread-per-stream kernel, 0 = one warp per stream; "
+    ap.add_argument("--hf-lanes", default="auto", choices=["auto", "0", "8", "16", "32", "64", "128"],
+                    help="HF coefficient schedule = streams per CTA: 0 (= 4) / 8 / 16 one warp per stream, 32 / 64 / 128 one "
+                         "thread per stream; "
                          "auto = probe in child processes (parity against the default kernel, then a short A/B) and keep the "
                          "faster one. JXLB_HF_LANES in the environment overrides.")
     ap.add_argument("--probe", default=None, choices=["parity", "speed"], help=argparse.SUPPRESS)

@@ -118,9 +118,9 @@ int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on);
 /* Restoration filters + colour as one fused kernel (default, on) or stage by stage (off): the
  * stage-by-stage form also emits the "gaborish" / "epf" snapshots for stage-level parity tests. */
 int32_t jxlb_set_fuse_filters(jxlb_decoder* dec, int32_t on);
-/* Scheduling of the HF coefficient streams (one per 256x256 group and pass, jxl-frame/src/data/pass_group.rs:31):
- * 0 = one warp per stream (default), 32 / 64 / 128 = one thread per stream, that many streams per CTA. Results are
- * identical; the process-wide default comes from the environment variable JXLB_HF_LANES. */
+/* Scheduling of the HF coefficient streams (one per 256x256 group and pass, jxl-frame/src/data/pass_group.rs:31): how
+ * many streams share one CTA and its staged tables. 0 (default, = 4), 8, 16: one warp per stream; 32 / 64 / 128: one
+ * thread per stream. Results are identical; the process-wide default comes from the environment variable JXLB_HF_LANES. */
 int32_t jxlb_set_hf_streams_per_cta(jxlb_decoder* dec, int32_t streams);
 int32_t jxlb_stage_count(const jxlb_decoder* dec, const char* name);
 int32_t jxlb_stage_get(const jxlb_decoder* dec, const char* name, int32_t idx, uint32_t* width, uint32_t* height,

@@ -264,9 +264,9 @@ class Decoder:
         self._L.jxlb_set_fuse_filters(self._h, int(on))
 
     def set_hf_streams_per_cta(self, streams):
-        """0: one warp per HF stream (default); 32 / 64 / 128: one thread per stream, that many streams per CTA."""
+        """HF streams per CTA: 0 (default, = 4), 8, 16: one warp per stream; 32 / 64 / 128: one thread per stream."""
         if self._L.jxlb_set_hf_streams_per_cta(self._h, int(streams)) != 0:
-            raise ValueError("streams per CTA must be 0, 32, 64 or 128")
+            raise ValueError("streams per CTA must be 0, 8, 16, 32, 64 or 128")
 
     def stage(self, name, dtype=np.float32):
         n = self._L.jxlb_stage_count(self._h, name.encode())

@@ -319,7 +319,8 @@ int32_t jxlb_set_fuse_filters(jxlb_decoder* dec, int32_t on) {
 }
 
 int32_t jxlb_set_hf_streams_per_cta(jxlb_decoder* dec, int32_t streams) {
-  if (!dec || (streams != 0 && streams != 32 && streams != 64 && streams != 128)) return JXLB_ERR_INVALID_ARG;
+  if (!dec || (streams != 0 && streams != 8 && streams != 16 && streams != 32 && streams != 64 && streams != 128))
+    return JXLB_ERR_INVALID_ARG;
   dec->be->hf_streams_per_cta = streams;
   return JXLB_OK;
 }

@@ -51,7 +51,7 @@ CudaBackend::CudaBackend(int device) : device_(device) {
   if (!std::getenv("JXLB_NO_CARVEOUT")) CUDA_CHECK(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
   if (const char* lanes = std::getenv("JXLB_HF_LANES")) {
     const int n = std::atoi(lanes);
-    hf_streams_per_cta = n <= 0 ? 0 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128));
+    hf_streams_per_cta = n <= 0 ? 0 : (n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128))));
   }
 }
 
@@ -878,7 +878,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   // finish together; `perm` maps the launch order back to `jobs`.
   std::vector<uint32_t> perm(jobs.size());
   for (size_t i = 0; i < jobs.size(); ++i) perm[i] = uint32_t(i);
-  if (hf_streams_per_cta > 0)
+  if (hf_streams_per_cta >= 32)
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
       return jobs[a].bit_limit - jobs[a].bit_pos > jobs[b].bit_limit - jobs[b].bit_pos;
     });
@@ -890,7 +890,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   temps_.push_back(d_end);
   temps_.push_back(d_status);
   uint32_t* d_blk_ctx = nullptr;
-  if (hf_streams_per_cta > 0) {
+  if (hf_streams_per_cta >= 32) {
     d_blk_ctx = static_cast<uint32_t*>(dmalloc(size_t(st.bw) * st.bh * 4));
     temps_.push_back(d_blk_ctx);
     begin_k("hf_block_ctx");
@@ -898,11 +898,12 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     end_k();
   }
   begin_k("decode_hf");
-  if (hf_streams_per_cta > 0)
+  if (hf_streams_per_cta >= 32)
     launch_decode_hf_lanes(active_cs_, dev_frame(st), p, d_blk_ctx, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
                            hf_streams_per_cta, stream_);
   else
-    launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0, stream_);
+    launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
+                     hf_streams_per_cta > 0 ? hf_streams_per_cta : 4, stream_);
   end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());

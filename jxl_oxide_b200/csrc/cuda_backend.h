@@ -74,8 +74,8 @@ class CudaBackend : public Backend {
   // Same, straight into the caller's device buffer (no host copy): the packed frame stays in HBM for an NCCL gather.
   void pack_to_device(const DevPackParams& p, void* d_dst);
   bool fuse_filters = true;  // single-kernel Gaborish+EPF+colour (off: stage-by-stage, for stage parity tests)
-  // HF coefficient streams: 0 = one warp per stream (decode_hf_fast_kernel), 32 / 64 / 128 = one thread per stream
-  // with that many streams per CTA (decode_hf_lanes_kernel). Initialised from JXLB_HF_LANES.
+  // HF coefficient streams per CTA: 0 (= 4), 8, 16 = one warp per stream (decode_hf_fast_kernel); 32 / 64 / 128 = one
+  // thread per stream (decode_hf_lanes_kernel). Initialised from JXLB_HF_LANES.
   int hf_streams_per_cta = 0;
   bool profile = false;
   bool trace_device = false;  // modular streams stamp the device clock; host launch/return times are logged

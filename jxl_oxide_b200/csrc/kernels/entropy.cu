@@ -22,14 +22,16 @@ namespace {
 // HF coefficients (jxl-vardct/src/hf_coeff.rs:21-252); hftab / kTInfo live in hf_lanes.cuh
 constexpr int kHfWarpsPerCta = 4;
 constexpr uint32_t kHfAnsSmemBytes = 128 * 1024;
+constexpr uint32_t kLaneCmapSmemBytes = 32 * 1024;  // all presets' cluster maps are staged once per CTA up to this size
 
-// Shared-memory layout of one CTA (4 streams): everything a coefficient symbol touches is staged --
-// the two context LUTs, hybrid-uint configs, the block-context map, each warp's own preset slice of
-// the cluster map, and the ANS alias tables (up to 128 KB; real libjxl d1 frames need ~86 KB).
+// Shared-memory layout of one CTA (W streams, one warp each): everything a coefficient symbol touches is staged --
+// the two context LUTs, hybrid-uint configs, the block-context map, the cluster map (SHARED_CMAP: every preset's, once
+// per CTA; otherwise each warp's own preset slice), and the ANS alias tables (up to 128 KB; real libjxl d1 frames
+// need ~86 KB). The tables dominate: a CTA that carries more streams holds more streams per SM for the same bytes.
 struct HfSmem {
   uint32_t ctxlut, configs, bctx, cmap, cmap_stride, ans, total;
 };
-__host__ __device__ inline HfSmem hf_layout(const DevHfParams& p) {
+__host__ __device__ inline HfSmem hf_layout(const DevHfParams& p, uint32_t warps = kHfWarpsPerCta, bool shared_cmap = false) {
   HfSmem L;
   uint32_t off = 0;
   auto take = [&](uint32_t bytes) {
@@ -40,24 +42,24 @@ __host__ __device__ inline HfSmem hf_layout(const DevHfParams& p) {
   L.ctxlut = take(128);
   L.configs = take(p.code.num_clusters * 4);
   L.bctx = take(p.block_ctx_map_size);
-  L.cmap_stride = (495 * p.num_block_clusters + 15) & ~15u;
-  L.cmap = take(L.cmap_stride * kHfWarpsPerCta);
+  L.cmap_stride = shared_cmap ? 495 * p.num_block_clusters : (495 * p.num_block_clusters + 15) & ~15u;
+  L.cmap = take(L.cmap_stride * (shared_cmap ? p.num_hf_presets : warps));
   uint32_t ab = p.code.use_prefix ? 0 : (p.code.num_clusters << p.code.log_alphabet_size) * 8;
   L.ans = (!p.code.use_prefix && ab <= min(kHfAnsSmemBytes, p.ans_smem_limit)) ? take(ab) : 0xffffffffu;
   L.total = off;
   return L;
 }
 
-template <bool SUB>  // SUB: the frame is chroma-subsampled (JPEG transcodes), channels sit at shifted block positions
-__global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(const uint8_t* __restrict__ cs, DevFrame f,
-                                                                             DevHfParams p,
-                                                                             const DevHfJob* __restrict__ jobs,
-                                                                             uint64_t* __restrict__ end_bits,
-                                                                             int* __restrict__ status, int num_jobs,
-                                                                             int first_pass) {
+// SUB: the frame is chroma-subsampled (JPEG transcodes), channels sit at shifted block positions. W: streams (warps)
+// per CTA. SHARED_CMAP: see HfSmem.
+template <bool SUB, int W = kHfWarpsPerCta, bool SHARED_CMAP = false>
+__global__ void __launch_bounds__(W * 32) decode_hf_fast_kernel(const uint8_t* __restrict__ cs, DevFrame f, DevHfParams p,
+                                                                const DevHfJob* __restrict__ jobs,
+                                                                uint64_t* __restrict__ end_bits, int* __restrict__ status,
+                                                                int num_jobs, int first_pass) {
   extern __shared__ __align__(16) uint8_t smem[];
-  __shared__ uint32_t s_nz[kHfWarpsPerCta][3][32];
-  const HfSmem L = hf_layout(p);
+  __shared__ uint32_t s_nz[W][3][32];
+  const HfSmem L = hf_layout(p, W, SHARED_CMAP);
   const uint32_t tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
   // ---- stage tables (whole CTA) ----
   uint8_t* s_ctx = smem + L.ctxlut;  // [0..63): freq ctx, [64..127): nonzero ctx
@@ -84,8 +86,13 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
     cv.ans = reinterpret_cast<const uint64_t*>(s_ans);
   }
   // ---- per-warp: stream header (HF preset) and that preset's cluster-map slice ----
-  const int job_idx = blockIdx.x * kHfWarpsPerCta + int(warp);
+  const int job_idx = blockIdx.x * W + int(warp);
   const bool active = job_idx < num_jobs;
+  if (SHARED_CMAP) {
+    uint8_t* dst = smem + L.cmap;
+    const uint32_t n = L.cmap_stride * p.num_hf_presets;
+    for (uint32_t i = tid; i < n; i += nthreads) dst[i] = __ldg(p.code.cluster_map + i);
+  }
   const uint32_t nbc = p.num_block_clusters;
   DevBitReader br;
   int err = kDevOk;
@@ -102,14 +109,16 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
       err = kDevInvalid;
       hfp = 0;
     }
-    uint8_t* dst = smem + L.cmap + warp * L.cmap_stride;
-    const uint8_t* src = p.code.cluster_map + size_t(495) * nbc * hfp;
-    for (uint32_t i = lane; i < 495 * nbc; i += 32) dst[i] = __ldg(src + i);
+    if (!SHARED_CMAP) {
+      uint8_t* dst = smem + L.cmap + warp * L.cmap_stride;
+      const uint8_t* src = p.code.cluster_map + size_t(495) * nbc * hfp;
+      for (uint32_t i = lane; i < 495 * nbc; i += 32) dst[i] = __ldg(src + i);
+    }
   }
   __syncthreads();
   if (!active || lane != 0) return;
 
-  const uint8_t* cluster_map = smem + L.cmap + warp * L.cmap_stride;
+  const uint8_t* cluster_map = smem + L.cmap + (SHARED_CMAP ? hfp : warp) * L.cmap_stride;
   const uint32_t lf_idx_mul = (p.num_lf_thr[0] + 1) * (p.num_lf_thr[1] + 1) * (p.num_lf_thr[2] + 1);
   const uint32_t hf_idx_mul = p.num_qf_thr + 1;
   uint32_t ans_state = p.code.use_prefix ? 0x130000u : br.read(32);
@@ -239,7 +248,6 @@ __global__ void __launch_bounds__(kHfWarpsPerCta * 32) decode_hf_fast_kernel(con
 // stages, once: context LUTs, hybrid-uint configs, block-context map, the cluster maps of every HF preset
 // (global memory when they exceed kLaneCmapSmemBytes), the ANS alias tables (same rule as above) and 96
 // bytes of non-zero-count row per stream.
-constexpr uint32_t kLaneCmapSmemBytes = 32 * 1024;
 struct HfLaneSmem {
   uint32_t ctxlut, small, configs, bctx, cmap, cmap_stride, nz, ans, total;
 };
@@ -354,21 +362,34 @@ void launch_decode_hf_lanes(const uint8_t* cs, DevFrame f, DevHfParams p, const 
     decode_hf_lanes_kernel<false><<<ctas, nthreads, L.total, stream>>>(cs, f, p, blk_ctx, jobs, end_bits, status, num_jobs, first_pass);
 }
 
-void launch_decode_hf(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,
-                      int num_jobs, int first_pass, cudaStream_t stream) {
-  if (num_jobs <= 0) return;
+namespace {
+template <int W, bool SHARED_CMAP>
+void launch_hf_warps(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,
+                     int num_jobs, int first_pass, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(decode_hf_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(decode_hf_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(decode_hf_fast_kernel<false, W, SHARED_CMAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(decode_hf_fast_kernel<true, W, SHARED_CMAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  const HfSmem L = hf_layout(p);
-  const int ctas = (num_jobs + kHfWarpsPerCta - 1) / kHfWarpsPerCta;
+  const HfSmem L = hf_layout(p, W, SHARED_CMAP);
+  const int ctas = (num_jobs + W - 1) / W;
   if (f.subsampled)
-    decode_hf_fast_kernel<true><<<ctas, kHfWarpsPerCta * 32, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+    decode_hf_fast_kernel<true, W, SHARED_CMAP><<<ctas, W * 32, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
   else
-    decode_hf_fast_kernel<false><<<ctas, kHfWarpsPerCta * 32, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+    decode_hf_fast_kernel<false, W, SHARED_CMAP><<<ctas, W * 32, L.total, stream>>>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass);
+}
+}  // namespace
+
+// `warps_per_cta`: 4 (default layout: a preset slice per warp), or 8 / 16 with every preset's cluster map staged once per
+// CTA (falls back to 4 when those maps exceed kLaneCmapSmemBytes).
+void launch_decode_hf(const uint8_t* cs, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits, int* status,
+                      int num_jobs, int first_pass, int warps_per_cta, cudaStream_t stream) {
+  if (num_jobs <= 0) return;
+  const bool fits = 495u * p.num_block_clusters * p.num_hf_presets <= kLaneCmapSmemBytes;
+  if (warps_per_cta >= 16 && fits) launch_hf_warps<16, true>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass, stream);
+  else if (warps_per_cta >= 8 && fits) launch_hf_warps<8, true>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass, stream);
+  else launch_hf_warps<kHfWarpsPerCta, false>(cs, f, p, jobs, end_bits, status, num_jobs, first_pass, stream);
 }
 
 }  // namespace jxlb

@@ -127,8 +127,9 @@ struct DevHfJob {
   uint64_t bit_pos, bit_limit;
   uint32_t group_idx;
 };
+// One warp per stream, `warps_per_cta` (4, 8 or 16) streams per CTA sharing the staged tables.
 void launch_decode_hf(const uint8_t* codestream, DevFrame f, DevHfParams p, const DevHfJob* jobs, uint64_t* end_bits,
-                      int* status, int num_jobs, int first_pass, cudaStream_t stream);
+                      int* status, int num_jobs, int first_pass, int warps_per_cta, cudaStream_t stream);
 // Same contract, one thread per stream (kernels/hf_lanes.cuh); `streams_per_cta` in {32, 64, 128}.
 // `blk_ctx` (bw x bh words) comes from launch_hf_block_ctx: transform type and context offset of every varblock origin.
 void launch_hf_block_ctx(DevFrame f, DevHfParams p, uint32_t* out, cudaStream_t stream);

@@ -20,14 +20,14 @@ def _fake(monkeypatch, parity, speeds):
 
 
 def test_candidate_must_be_identical_and_faster(monkeypatch):
-    _fake(monkeypatch, {"32": True, "64": True, "128": True}, {"0": 3000.0, "64": 3600.0, "128": 3900.0})
+    _fake(monkeypatch, {"16": True, "64": True, "128": True}, {"0": 3000.0, "16": 3300.0, "64": 3600.0, "128": 3900.0})
     n, rep = bench.choose_hf_schedule(_args(), 0)
     assert n == 128 and rep["chosen"] == 128 and rep["probe_mp_s"]["0"] == 3000.0
-    _fake(monkeypatch, {"32": True, "64": True, "128": False}, {"0": 3000.0, "64": 3600.0})
-    assert bench.choose_hf_schedule(_args(), 0)[0] == 64          # 128 differs from the default kernel: never timed
-    _fake(monkeypatch, {"32": True, "64": True, "128": True}, {"0": 3000.0, "64": 3050.0, "128": 2900.0})
+    _fake(monkeypatch, {"16": True, "64": True, "128": False}, {"0": 3000.0, "16": 3700.0, "64": 3600.0})
+    assert bench.choose_hf_schedule(_args(), 0)[0] == 16          # 128 differs from the default kernel: never timed
+    _fake(monkeypatch, {"16": True, "64": True, "128": True}, {"0": 3000.0, "16": 3010.0, "64": 3050.0, "128": 2900.0})
     assert bench.choose_hf_schedule(_args(), 0)[0] == 0           # within 3 %: keep the default
-    _fake(monkeypatch, {"32": False, "64": False, "128": False}, {})
+    _fake(monkeypatch, {"16": False, "64": False, "128": False}, {})
     n, rep = bench.choose_hf_schedule(_args(), 0)
     assert n == 0 and rep["probe_mp_s"] == {}
 
@@ -39,7 +39,7 @@ def test_probe_failure_falls_back_to_the_default(monkeypatch):
     assert n == 0 and "fallback" in rep
 
 
-@pytest.mark.parametrize("flag,env,want", [("64", None, 64), ("auto", "128", 128), ("0", None, 0), ("auto", "50", 64)])
+@pytest.mark.parametrize("flag,env,want", [("64", None, 64), ("auto", "128", 128), ("0", None, 0), ("auto", "50", 64), ("16", None, 16)])
 def test_explicit_choice_wins(monkeypatch, flag, env, want):
     monkeypatch.delenv("JXLB_BENCH_FAKE_PROBE", raising=False)
     if env is None:

@@ -16,6 +16,8 @@ from conftest import fixture_bytes
 pytestmark = pytest.mark.gpu
 
 FIXTURES = ["opsin_inverse", "bike", "cafe", "issue_425", "bench_oriented_brg", "minecraft_vardct_e7", "upsampling"]
+# streams per CTA: 16 = one warp per stream with every preset's cluster map staged once; 32 = one thread per stream
+SCHEDULES = [16, 32]
 
 
 @pytest.fixture(scope="module")
@@ -43,12 +45,13 @@ def _check(dec, oracle, data, streams):
         dec.set_hf_streams_per_cta(0)
 
 
+@pytest.mark.parametrize("streams", SCHEDULES)
 @pytest.mark.parametrize("name", FIXTURES)
-def test_hf_lanes_fixture(dec, oracle, name):
-    _check(dec, oracle, fixture_bytes(name, "input.jxl"), 32)
+def test_hf_lanes_fixture(dec, oracle, name, streams):
+    _check(dec, oracle, fixture_bytes(name, "input.jxl"), streams)
 
 
-@pytest.mark.parametrize("streams", [32, 64, 128])
+@pytest.mark.parametrize("streams", [8, 16, 32, 64, 128])
 @pytest.mark.parametrize("extra", [(), ("--passes", "3")])
 def test_hf_lanes_synthetic(dec, oracle, streams, extra):
     # 2000x1500: 8x6 groups (ragged right / bottom), more streams than one CTA carries at 32 per CTA
@@ -126,7 +129,7 @@ def test_epf_iteration_counts(dec, oracle, iters):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"fused={fused}"
 
 
-@pytest.mark.parametrize("streams", [0, 32, 128])
+@pytest.mark.parametrize("streams", [0, 16, 32, 128])
 def test_hf_presets_on_the_device(dec, oracle, streams):
     """Several HF presets (synthetic: no reference fixture has more than one): the default kernel stages one preset's
     cluster-map slice per warp, the thread-per-stream kernel all of them per CTA."""

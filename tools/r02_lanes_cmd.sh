@@ -10,13 +10,15 @@ run A_default $B --hf-lanes 0
 run B_lanes32 JXLB_HF_LANES=32 $B
 run C_lanes64 JXLB_HF_LANES=64 $B
 run D_lanes128 JXLB_HF_LANES=128 $B
+run D2_warps16 JXLB_HF_LANES=16 $B
+run D3_warps8 JXLB_HF_LANES=8 $B
 run E_lanes64_pipe JXLB_HF_LANES=64 $B --pipeline-steps
 run F_lanes64_c48 JXLB_HF_LANES=64 $B --contexts 48 --frames-per-step 48
 run G_default_c48 $B --hf-lanes 0 --contexts 48 --frames-per-step 48
 run H_auto $B
 python - <<PY
 import json
-for n in ("A_default","B_lanes32","C_lanes64","D_lanes128","E_lanes64_pipe","F_lanes64_c48","G_default_c48","H_auto"):
+for n in ("A_default","B_lanes32","C_lanes64","D_lanes128","D2_warps16","D3_warps8","E_lanes64_pipe","F_lanes64_c48","G_default_c48","H_auto"):
     try:
         d=json.load(open("gpurun_out/r02_%s.json"%n))
         k=d["kernel_ms_per_step"]; s=d["kernel_ms_per_frame_solo"]
