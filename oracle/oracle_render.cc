@@ -7,6 +7,7 @@
 #include <array>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 #include "oracle_backend.h"
 
@@ -229,11 +230,12 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
   }
   lap("copy_in");
   int cur = 0;
-  auto run_step = [&](int step) {
+  auto run_step = [&](auto step_tag) {  // the step is a compile-time constant: fixed trip counts for the tap loops
+    constexpr int step = decltype(step_tag)::value;
     const int8_t(*kernel)[2] = step == 0 ? kKernel2 : kKernel1;
-    const int nk = step == 0 ? 12 : 4;
+    constexpr int nk = step == 0 ? 12 : 4;
     const int8_t(*dist)[2] = step == 0 ? kDist0 : (step == 1 ? kDist1 : kDist2);
-    const int nd = step == 2 ? 1 : 5;
+    constexpr int nd = step == 2 ? 1 : 5;
     const float step_multiplier = step == 0 ? p.pass0_sigma_scale : (step == 2 ? p.pass2_sigma_scale : 1.0f);
     const float* in[3] = {bufs[cur][0].data(), bufs[cur][1].data(), bufs[cur][2].data()};
     float* out[3] = {bufs[cur ^ 1][0].data(), bufs[cur ^ 1][1].data(), bufs[cur ^ 1][2].data()};
@@ -253,7 +255,52 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
         sm[7] *= p.border_sad_mul;
       }
       const bool row_inside = ptrdiff_t(y) >= reach && ptrdiff_t(y) + reach < ptrdiff_t(height);
+      // Interior of the row, array form: the same per-pixel operations in the same order, laid out so that the compiler
+      // can run several pixels per instruction (what the reference's SIMD EPF does); pixels with sigma < 0.3 are
+      // overwritten with the input afterwards, exactly as the scalar path would have left them.
+      size_t xa = width, xb = width;  // [xa, xb): pixels done here
+      if (row_inside && ptrdiff_t(width) > 2 * reach) {
+        xa = size_t(reach), xb = width - size_t(reach);
+        const size_t n = xb - xa, row = y * width + xa;
+        std::vector<float> tmp(n * 8);
+        float *nis = tmp.data(), *wsum = nis + n, *s0 = wsum + n, *s1 = s0 + n, *s2 = s1 + n, *dd = s2 + n, *acc = dd + n, *sg = acc + n;
+        for (size_t i = 0; i < n; ++i) sg[i] = sigma_is_constant ? p.sigma_for_modular : sig[(y / 8) * sig_stride + (xa + i) / 8];
+        for (size_t i = 0; i < n; ++i) nis[i] = 6.6f * (0.70710678118654752440f - 1.0f) / sg[i] * sm[(xa + i) & 7];
+        for (size_t i = 0; i < n; ++i) wsum[i] = 1.0f, s0[i] = in[0][row + i], s1[i] = in[1][row + i], s2[i] = in[2][row + i];
+        for (int k = 0; k < nk; ++k) {
+          for (size_t i = 0; i < n; ++i) dd[i] = 0.0f;
+          for (int c = 0; c < 3; ++c) {
+            const float* pc = in[c] + row;
+            const float scale = p.channel_scale[c];
+            for (size_t i = 0; i < n; ++i) acc[i] = 0.0f;
+            for (int t = 0; t < nd; ++t) {
+              const float* pa = pc + koff[k] + doff[t];
+              const float* pb = pc + doff[t];
+              for (size_t i = 0; i < n; ++i) acc[i] += std::fabs(pa[i] - pb[i]);
+            }
+            for (size_t i = 0; i < n; ++i) dd[i] += scale * acc[i];
+          }
+          const float *q0 = in[0] + row + koff[k], *q1 = in[1] + row + koff[k], *q2 = in[2] + row + koff[k];
+          for (size_t i = 0; i < n; ++i) {
+            const float weight = std::max(1.0f + dd[i] * nis[i], 0.0f);
+            wsum[i] += weight;
+            s0[i] += weight * q0[i];
+            s1[i] += weight * q1[i];
+            s2[i] += weight * q2[i];
+          }
+        }
+        for (size_t i = 0; i < n; ++i) {
+          const bool keep = sg[i] < 0.3f;
+          out[0][row + i] = keep ? in[0][row + i] : s0[i] / wsum[i];
+          out[1][row + i] = keep ? in[1][row + i] : s1[i] / wsum[i];
+          out[2][row + i] = keep ? in[2][row + i] : s2[i] / wsum[i];
+        }
+      }
       for (size_t dx = 0; dx < width; ++dx) {
+        if (dx >= xa && dx < xb) {
+          dx = xb - 1;
+          continue;
+        }
         float sigma_val = sigma_is_constant ? p.sigma_for_modular : sig[(y / 8) * sig_stride + dx / 8];
         if (sigma_val < 0.3f) {
           for (int c = 0; c < 3; ++c) out[c][y * width + dx] = in[c][y * width + dx];
@@ -302,9 +349,9 @@ void OracleBackend::epf(const View v[3], const View& sigma, const EpfParams& p, 
     cur ^= 1;
     lap("step");
   };
-  if (p.iters == 3) run_step(0);
-  run_step(1);
-  if (p.iters >= 2) run_step(2);
+  if (p.iters == 3) run_step(std::integral_constant<int, 0>{});
+  run_step(std::integral_constant<int, 1>{});
+  if (p.iters >= 2) run_step(std::integral_constant<int, 2>{});
   for (int c = 0; c < 3; ++c) {
     Plane& pl = plane(v[c].plane);
     for (size_t y = 0; y < height; ++y)
