@@ -120,6 +120,11 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
   const uint32_t bx0 = gx * gb, by0 = gy * gb;
   const uint32_t width = hf_umin(gb, f.bw - bx0), height = hf_umin(gb, f.bh - by0);
   for (uint32_t i = 0; i < 96; ++i) nz[i * nz_stride] = 0;
+  // Hard stop for corrupt streams: the reader's look-ahead pointer is never more than 3 words past the consumed
+  // position, so once it is more than 4 words past the section's last word the stream has certainly consumed bits
+  // beyond `bit_limit` (no false positives), and no load ever lands more than 32 bytes behind the section -- inside
+  // the zero padding of the device copy. (The per-channel pos() check below reports the same error, only later.)
+  const uint32_t* const stop_word = br.origin + ((job.bit_limit + 31) >> 5) + 4;
 
   // ---- block cursor ----
   uint32_t x = 0, y = 0;     // the varblock being decoded (its top-left cell)
@@ -212,6 +217,10 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
     // ---- the part every lane executes together: one entropy-coded integer ----
     JXLB_LANE_TRIP(in_coeffs);
     const uint32_t value = cv_read_uint(br, T.cfg[cl], cv_read_symbol(T.cv, ans_state, br, cl));
+    if (br.next_word > stop_word) {
+      err = kDevOverrun;
+      break;
+    }
 
     if (!in_coeffs) {
       if (value > (63u << num_blocks_log)) {
