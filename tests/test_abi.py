@@ -48,3 +48,14 @@ def test_product_does_not_reference_oracle():
                 text = open(os.path.join(root, f)).read()
                 assert "oracle/" not in text.replace("oracle/) ", "") or "test oracle implements" in text or f == "backend.h", \
                     f"{f} references oracle/"
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_device():
+    """Argument validation needs no GPU: a NULL decoder is an error value, never a crash."""
+    import jxl_oxide_b200
+    L = ctypes.CDLL(_built_lib())
+    L.jxlb_set_hf_streams_per_cta.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+    L.jxlb_frame_write_to_device.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_size_t]
+    assert L.jxlb_set_hf_streams_per_cta(None, 64) == jxl_oxide_b200.ERR_INVALID_ARG
+    buf = ctypes.create_string_buffer(16)
+    assert L.jxlb_frame_write_to_device(None, 0, 0, 0, buf, 16) == jxl_oxide_b200.ERR_INVALID_ARG
