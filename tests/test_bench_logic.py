@@ -11,10 +11,11 @@ def _args(hf_lanes="auto"):
     return argparse.Namespace(hf_lanes=hf_lanes, workload="synth8k", contexts=24)
 
 
-def _fake(monkeypatch, parity, speeds):
-    canned = {"parity": {"identical_to_default_kernel": parity}}
+def _fake(monkeypatch, identical, speeds):
+    """Canned child outputs keyed by the schedule: value + digest ("ref" when identical to the default kernel's)."""
+    canned = {}
     for n, v in speeds.items():
-        canned[f"speed:{n}"] = {"value": v}
+        canned[n] = {"value": v, "sha256": "ref" if n == "0" or identical.get(n) else "other"}
     monkeypatch.setenv("JXLB_BENCH_FAKE_PROBE", json.dumps(canned))
     monkeypatch.delenv("JXLB_HF_LANES", raising=False)
 
@@ -23,13 +24,14 @@ def test_candidate_must_be_identical_and_faster(monkeypatch):
     _fake(monkeypatch, {"16": True, "64": True, "128": True}, {"0": 3000.0, "16": 3300.0, "64": 3600.0, "128": 3900.0})
     n, rep = bench.choose_hf_schedule(_args(), 0)
     assert n == 128 and rep["chosen"] == 128 and rep["probe_mp_s"]["0"] == 3000.0
-    _fake(monkeypatch, {"16": True, "64": True, "128": False}, {"0": 3000.0, "16": 3700.0, "64": 3600.0})
-    assert bench.choose_hf_schedule(_args(), 0)[0] == 16          # 128 differs from the default kernel: never timed
+    _fake(monkeypatch, {"16": True, "64": True, "128": False}, {"0": 3000.0, "16": 3700.0, "64": 3600.0, "128": 9999.0})
+    n, rep = bench.choose_hf_schedule(_args(), 0)
+    assert n == 16 and rep["identical_to_default_kernel"]["128"] is False   # differs from the default kernel: never used
     _fake(monkeypatch, {"16": True, "64": True, "128": True}, {"0": 3000.0, "16": 3010.0, "64": 3050.0, "128": 2900.0})
     assert bench.choose_hf_schedule(_args(), 0)[0] == 0           # within 3 %: keep the default
-    _fake(monkeypatch, {"16": False, "64": False, "128": False}, {})
+    _fake(monkeypatch, {"16": True}, {"0": 3000.0, "16": 3500.0})  # the 64 / 128 children "crash": only they are dropped
     n, rep = bench.choose_hf_schedule(_args(), 0)
-    assert n == 0 and rep["probe_mp_s"] == {}
+    assert n == 16 and str(rep["identical_to_default_kernel"]["64"]).startswith("failed")
 
 
 def test_probe_failure_falls_back_to_the_default(monkeypatch):
