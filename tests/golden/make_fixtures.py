@@ -37,6 +37,7 @@ CASES = {
     "grayscale_jpeg": ("conformance/testcases/grayscale_jpeg", ["input.jxl"]),
     "cafe": ("conformance/testcases/cafe", ["input.jxl"]),
     "issue_425": ("decode/issue_425", ["input.jxl", "ref.jpg"]),
+    "genshin_ycbcr_420": ("decode/genshin_ycbcr_420", ["input.jxl"]),  # 2560x1440 4:2:0 transcode, 60 groups
     "spot": ("conformance/testcases/spot", ["input.jxl"]),
     "grayscale": ("conformance/testcases/grayscale", ["input.jxl", "ref.png"]),
     # these three need a CMS to match their ref.png (tabulated-curve / chrm / CMYK ICC profiles): kept for the ICC
@@ -72,6 +73,9 @@ Image.open(os.path.join(REF, "conformance/testcases/cafe/ref.png")).crop((600, 8
     os.path.join(HERE, "cafe", "ref_crop_600_800.png"), optimize=True)
 Image.open(os.path.join(REF, "conformance/testcases/cafe/ref.png")).crop((1024, 1344, 1280, 1600)).save(
     os.path.join(HERE, "cafe", "ref_crop_corner.png"), optimize=True)
+# genshin_ycbcr_420: a 256 x 256 crop at (1000, 600) of the source JPEG as libjpeg decodes it (ref.jpg is 0.7 MB)
+Image.open(os.path.join(REF, "decode/genshin_ycbcr_420/ref.jpg")).convert("RGB").crop((1000, 600, 1256, 856)).save(
+    os.path.join(HERE, "genshin_ycbcr_420", "refjpg_crop_1000_600.png"), optimize=True)
 # spot colours: a 300 x 300 crop at (150, 50) of the 8-bit rendering
 Image.open(os.path.join(REF, "conformance/testcases/spot/ref.png")).crop((150, 50, 450, 350)).save(
     os.path.join(HERE, "spot", "ref_crop_150_50.png"), optimize=True)

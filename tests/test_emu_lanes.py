@@ -24,6 +24,7 @@ VARDCT_FIXTURES = [
     "upsampling",
     "cafe",                 # JPEG transcode 4:2:0: shifted channel grids (SUB path)
     "issue_425",            # 4:2:0 with an odd block count
+    "genshin_ycbcr_420",    # 4:2:0 at 2560 x 1440: 60 groups, two warps of streams
     "bench_oriented_brg",   # JPEG transcode 4:4:4
     "grayscale_jpeg",
     "minecraft_vardct_e7",

@@ -619,3 +619,17 @@ def test_hf_presets_select_their_own_cluster_maps(oracle, presets):
     one = oracle.OracleImage(bench.synth_frame(1000, 600, 7), threads=4).frame(0)[0]
     many = oracle.OracleImage(bench.synth_frame(1000, 600, 7, extra=("--hf-presets", str(presets))), threads=4).frame(0)[0]
     assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+
+
+def test_jpeg_transcode_420_full_size(oracle):
+    """The reference's genshin_ycbcr_420 (2560 x 1440, 60 groups, chroma at half resolution both ways; its golden buffer
+    is not in the tree): a 256 x 256 crop of the source JPEG as libjpeg decodes it agrees to within the two decoders'
+    IDCT / upsampling differences, as for issue_425."""
+    from PIL import Image
+    import io
+    img = oracle.OracleImage(fixture_bytes("genshin_ycbcr_420", "input.jxl"), threads=4)
+    buf = np.clip(img.frame_to_buffer(0, np.float32, 0), 0, 1)
+    assert buf.shape == (1440, 2560, 3)
+    ref = np.asarray(Image.open(io.BytesIO(fixture_bytes("genshin_ycbcr_420", "refjpg_crop_1000_600.png")))).astype(np.float32) / 255.0
+    crop = buf[600:856, 1000:1256]
+    assert np.abs(crop - ref).max() <= 0.03 and np.sqrt(((crop - ref) ** 2).mean()) <= 0.004

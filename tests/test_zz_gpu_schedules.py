@@ -15,7 +15,7 @@ from conftest import fixture_bytes
 
 pytestmark = pytest.mark.gpu
 
-FIXTURES = ["opsin_inverse", "bike", "cafe", "issue_425", "bench_oriented_brg", "minecraft_vardct_e7", "upsampling"]
+FIXTURES = ["opsin_inverse", "bike", "cafe", "issue_425", "genshin_ycbcr_420", "bench_oriented_brg", "minecraft_vardct_e7", "upsampling"]
 # streams per CTA: 16 = one warp per stream with every preset's cluster map staged once; 32 = one thread per stream
 SCHEDULES = [16, 32]
 
@@ -140,3 +140,11 @@ def test_hf_presets_on_the_device(dec, oracle, streams):
         dec.decode(data)
         got, want = dec.frame_planar(0), oracle.OracleImage(data, threads=8).frame(0)[0]
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_genshin_ycbcr_420_default_schedule(dec, oracle):
+    """Full-size 4:2:0 JPEG transcode on the default kernels (the schedule variants are covered by test_hf_lanes_fixture)."""
+    data = fixture_bytes("genshin_ycbcr_420", "input.jxl")
+    dec.decode(data)
+    got, want = dec.frame_planar(0), oracle.OracleImage(data, threads=8).frame(0)[0]
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
