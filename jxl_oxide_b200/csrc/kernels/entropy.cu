@@ -127,6 +127,8 @@ __global__ void __launch_bounds__(W * 32) decode_hf_fast_kernel(const uint8_t* _
   const uint32_t gb = p.group_dim_blocks;
   const uint32_t bx0 = gx * gb, by0 = gy * gb;
   const uint32_t width = min(gb, f.bw - bx0), height = min(gb, f.bh - by0);
+  // (variants only, so that the measured default keeps its code) hard stop for corrupt streams, see hf_lanes.cuh
+  const uint32_t* const stop_word = br.origin + ((job.bit_limit + 31) >> 5) + 4;
   uint32_t(*nz_row)[32] = s_nz[warp];
   for (int c = 0; c < 3; ++c)
     for (int i = 0; i < 32; ++i) nz_row[c][i] = 0;
@@ -190,6 +192,10 @@ __global__ void __launch_bounds__(W * 32) decode_hf_fast_kernel(const uint8_t* _
         const uint32_t nz_ctx = block_ctx + pidx * nbc;
         uint32_t cl = cluster_map[nz_ctx];
         uint32_t non_zeros = cv_read_uint(br, s_cfg[cl], cv_read_symbol(cv, ans_state, br, cl));
+        if (SHARED_CMAP && br.next_word > stop_word) {
+          err = kDevOverrun;
+          break;
+        }
         if (non_zeros > (63u << num_blocks_log)) {
           err = kDevInvalid;
           break;
@@ -213,6 +219,10 @@ __global__ void __launch_bounds__(W * 32) decode_hf_fast_kernel(const uint8_t* _
           }
           cl = cmap[cctx];
           const uint32_t ucoeff = cv_read_uint(br, s_cfg[cl], cv_read_symbol(cv, ans_state, br, cl));
+          if (SHARED_CMAP && br.next_word > stop_word) {
+            err = kDevOverrun;
+            break;
+          }
           if (ucoeff == 0) {
             prev_nonzero = 0;
             continue;
