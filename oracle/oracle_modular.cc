@@ -59,8 +59,8 @@ struct WpState {
   }
   void predict(int32_t n, int32_t nw, int32_t ne, int32_t w, int32_t nn) {  // predictor.rs:312-394
     int64_t tew = true_err_w, tenw = true_err_nw, ten = true_err_n, tene = true_err_ne;
-    int64_t n3 = int64_t(n) << 3, nw3 = int64_t(nw) << 3, ne3 = int64_t(ne) << 3, w3 = int64_t(w) << 3,
-            nn3 = int64_t(nn) << 3;
+    // (x * 8: the reference's `x << 3` on i64, written without shifting a negative value)
+    int64_t n3 = int64_t(n) * 8, nw3 = int64_t(nw) * 8, ne3 = int64_t(ne) * 8, w3 = int64_t(w) * 8, nn3 = int64_t(nn) * 8;
     subpred[0] = w3 + ne3 - n3;
     subpred[1] = n3 - (((tew + ten + tene) * int64_t(wp.p1)) >> 5);
     subpred[2] = w3 - (((tew + ten + tenw) * int64_t(wp.p2)) >> 5);
@@ -93,10 +93,10 @@ struct WpState {
   }
   void record(int32_t sample_) {  // predictor.rs:396-441
     int64_t sample = sample_;
-    int64_t true_err = prediction - (sample << 3);
+    int64_t true_err = prediction - sample * 8;
     uint32_t sub_err[4];
     for (int i = 0; i < 4; ++i) {
-      int64_t d = subpred[i] - (sample << 3);
+      int64_t d = subpred[i] - sample * 8;
       uint64_t ad = d < 0 ? uint64_t(-d) : uint64_t(d);
       sub_err[i] = uint32_t((ad + 3) >> 3);
     }

@@ -750,7 +750,7 @@ void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
           int32_t x_bits;
           std::memcpy(&x_bits, &a0, 4);
           const int32_t exp_shifted = (x_bits - 0x3f2aaaab) >> 23;
-          const int32_t mb = x_bits - (exp_shifted << 23);
+          const int32_t mb = x_bits - exp_shifted * (1 << 23);
           float mantissa;
           std::memcpy(&mantissa, &mb, 4);
           const float xx2 = mantissa - 1.0f;
@@ -807,7 +807,7 @@ void OracleBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
           int32_t x_bits;
           std::memcpy(&x_bits, &a, 4);
           const int32_t exp_shifted = (x_bits - 0x3f2aaaab) >> 23;
-          const int32_t mb = x_bits - (exp_shifted << 23);
+          const int32_t mb = x_bits - exp_shifted * (1 << 23);
           float mantissa;
           std::memcpy(&mantissa, &mb, 4);
           const float exp_val = float(exp_shifted);
