@@ -100,10 +100,13 @@ int32_t jxlb_decode(jxlb_decoder* dec, const uint8_t* data, size_t size, const j
 int32_t jxlb_preload(jxlb_decoder* dec, int32_t slot, const uint8_t* data, size_t size) {
   if (!dec || !data) return JXLB_ERR_INVALID_ARG;
   return guarded(dec, [&] {
+    // build the new copy first: a failure (malformed container, out of memory) leaves the slot as it was
+    std::vector<uint8_t> cs = extract_codestream(data, size);
+    uint8_t* dptr = dec->be->upload_resident(cs.data(), cs.size());
     jxlb_decoder::Slot& s = dec->slots[slot];
     if (s.dptr) cudaFree(s.dptr);
-    s.codestream = extract_codestream(data, size);
-    s.dptr = dec->be->upload_resident(s.codestream.data(), s.codestream.size());
+    s.codestream = std::move(cs);
+    s.dptr = dptr;
   });
 }
 

@@ -826,6 +826,9 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   const HfBlockContext& hbc = st.lfg->hf_block_ctx;
   const uint32_t pass = jobs[0].pass_idx;
   const HfPassSyntax& hp = st.hfg->passes[pass];
+  // The coefficient kernels read plain hybrid-uint tokens; an LZ77-enabled HF code (legal, hf_coeff.rs:181-222 goes
+  // through read_varint_with_multiplier_clustered, but no known encoder emits it) would decode silently wrong.
+  JXLB_CHECK(!hp.code.lz77_enabled, kErrUnsupported, "LZ77 in the HF coefficient streams is not supported on the device");
   DevHfParams p;
   std::memset(&p, 0, sizeof(p));
   p.code = upload_code(hp.code);

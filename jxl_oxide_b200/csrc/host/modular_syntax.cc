@@ -25,7 +25,9 @@ MaTree parse_ma_tree(BitReader& br, size_t node_limit, size_t depth_limit) {  //
     uint32_t property = dec.read_varint(br, 1);
     MaNode node;
     if (property > 0) {
-      node.property = int32_t(property - 1);
+      // Properties beyond the last previous channel a stream can have (16 + 4 * 16) evaluate to 0 whatever their
+      // number (predictor.rs:495-528), so they share one value: a huge property must never look like a leaf (< 0).
+      node.property = int32_t(std::min<uint32_t>(property - 1, 16 + 4 * 16));
       node.value = unpack_signed(dec.read_varint(br, 0));
       node.a = next_child;
       node.b = next_child + 1;

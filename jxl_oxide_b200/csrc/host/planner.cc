@@ -225,6 +225,11 @@ class FramePlanner {
         visible_before_(visible_before), invisible_before_(invisible_before) {}
 
   DecodedFrame decode_frame(size_t frame_begin_byte, size_t* frame_end_byte);
+  // A frame that fails half way (malformed or unsupported stream) must not keep its planes: they are
+  // cleared from the list once exported or freed at the end of decode_frame().
+  ~FramePlanner() {
+    for (int id : frame_planes_) be_.free_plane(id);
+  }
 
  private:
   BitReader reader_at(size_t bit_pos, size_t limit_byte) const { return BitReader(cs_, limit_byte, bit_pos); }
@@ -1270,6 +1275,8 @@ DecodeResult decode_codestream(Backend& be, const uint8_t* cs, size_t size, cons
     }
   } catch (...) {
     drop_lf_frames();
+    for (DecodedFrame& f : res.frames)  // frames finished before the failing one
+      for (const View& v : f.channels) be.free_plane(v.plane);
     throw;
   }
   drop_lf_frames();

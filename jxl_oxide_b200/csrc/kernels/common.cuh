@@ -33,12 +33,18 @@ struct DevEntropyCode {
 struct DevBitReader {
   const uint32_t* next_word;  // word after `ahead`
   const uint32_t* origin;     // first word of the codestream
+  const uint32_t* stop;       // last word a refill may load; beyond it the stream reads as zeros (like the
+                              // reference's reader past the end of its slice, bitstream.rs:133-141)
   uint64_t buf;
   uint32_t ahead;
   int nbits;
 
-  __device__ __forceinline__ void init(const uint8_t* d, uint64_t bit_pos) {
+  // `bit_limit`: absolute end of the enclosing section. A corrupt stream can ask for up to ~47 bits per symbol for
+  // as many symbols as its geometry holds (65536 in a DCT256 block); the loads stop two words after the section, so
+  // nothing outside the zero-padded codestream copy is ever touched and the overrun is reported from pos().
+  __device__ __forceinline__ void init(const uint8_t* d, uint64_t bit_pos, uint64_t bit_limit = ~uint64_t(0)) {
     origin = reinterpret_cast<const uint32_t*>(d);
+    stop = bit_limit == ~uint64_t(0) ? reinterpret_cast<const uint32_t*>(~uintptr_t(0)) : origin + ((bit_limit + 31) >> 5) + 2;
     const uint32_t* w = origin + (bit_pos >> 5);
     const uint32_t skip = uint32_t(bit_pos & 31);
     buf = uint64_t(__ldg(w)) >> skip;
@@ -51,7 +57,7 @@ struct DevBitReader {
   __device__ __forceinline__ void refill() {  // requires nbits <= 32; afterwards nbits > 32
     buf |= uint64_t(ahead) << nbits;
     nbits += 32;
-    ahead = __ldg(next_word);
+    ahead = next_word <= stop ? __ldg(next_word) : 0u;
     ++next_word;
   }
   __device__ __forceinline__ uint32_t peek(uint32_t n) {  // n <= 32

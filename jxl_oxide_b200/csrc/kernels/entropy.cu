@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(W * 32) decode_hf_fast_kernel(const uint8_t* _
   job.bit_pos = 0, job.bit_limit = 0, job.group_idx = 0;
   if (active) {
     job = jobs[job_idx];
-    br.init(cs, job.bit_pos);
+    br.init(cs, job.bit_pos, job.bit_limit);
     uint32_t hfp_bits = 0;
     while ((1u << hfp_bits) < p.num_hf_presets) ++hfp_bits;
     hfp = br.read(hfp_bits);  // every lane reads the same bits

@@ -101,7 +101,7 @@ __device__ __forceinline__ void hf_lane_decode(const uint8_t* __restrict__ cs, c
                                                uint64_t* end_bit, int* status) {
   DevBitReader br;
   int err = kDevOk;
-  br.init(cs, job.bit_pos);
+  br.init(cs, job.bit_pos, job.bit_limit);
   uint32_t hfp_bits = 0;
   while ((1u << hfp_bits) < p.num_hf_presets) ++hfp_bits;
   uint32_t hfp = br.read(hfp_bits);

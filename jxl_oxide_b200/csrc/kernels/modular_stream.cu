@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
 
   // ---- serial decode (lane 0) ----
   StreamState s;
-  s.br.init(cs, job.bit_pos);
+  s.br.init(cs, job.bit_pos, job.bit_limit);
   s.ans_state = code.use_prefix ? 0x130000u : s.br.read(32);
   s.window = job.lz_window;
   s.lz_to_copy = s.lz_copy_pos = s.lz_decoded = 0;
