@@ -60,14 +60,16 @@ def load_workload(name, nframes=16):
         desc = ("8K-equivalent (33.18 MP/step/GPU): 3x3 mosaic of a real libjxl VarDCT d1.0 2560x1440 frame "
                 "(starrail.d1-e6.jxl, Gaborish + EPF), decoded as 9 independent frames")
         return desc, [tile] * 9, (2560, 1440)
-    if name in ("synth8k", "synth4k"):
-        w, h = (7680, 4320) if name == "synth8k" else (3840, 2160)
+    if name in ("synth8k", "synth4k", "synth8k_d2"):
+        w, h = (3840, 2160) if name == "synth4k" else (7680, 4320)
+        d2 = name == "synth8k_d2"  # BASELINE config #3: d2.0, the full filter chain (EPF 3 iterations: steps 0, 1, 2)
         frames = []
         for seed in (1, 2, 3, 4):
-            frames.append(synth_frame(w, h, seed))
+            frames.append(synth_frame(w, h, seed, distance=2.0, extra=("--epf-iters", "3")) if d2 else synth_frame(w, h, seed))
         frames = [frames[i % len(frames)] for i in range(max(1, nframes))]
-        desc = (f"{w}x{h} VarDCT d1.0 synthetic encoded frames (tools/synth_enc.cc seeds 1-4, ~0.93 bit/px, "
-                "libjxl-like: WP-coded LF, mixed varblocks 8x8..64x64, Gaborish + EPF 2 iters), "
+        bpp = sum(len(f) for f in frames) * 8.0 / (w * h * len(frames))
+        desc = (f"{w}x{h} VarDCT d{'2.0' if d2 else '1.0'} synthetic encoded frames (tools/synth_enc.cc seeds 1-4, {bpp:.2f} bit/px, "
+                f"libjxl-like: WP-coded LF, mixed varblocks 8x8..64x64, Gaborish + EPF {3 if d2 else 2} iters), "
                 f"{len(frames)} independent frames per step")
         return desc, frames, (w, h)
     if name.startswith("file:"):
@@ -218,108 +220,27 @@ KERNELS = ["modular_decode", "build_block_info", "hf_block_ctx", "decode_hf", "l
            "int_to_float", "modular_xyb", "palette_inverse_simple"]
 
 
-# streams per CTA tried against the default (4, one warp each): 16 one-warp streams; 64 / 128 one-thread streams
-HF_CANDIDATES = (16, 64, 128)
-
-
-def run_probe(args):
-    """Child process of choose_hf_schedule(): one JSON line on stdout. Runs in its own process so that a fault in the
-    candidate kernel cannot poison the CUDA context of the measuring process."""
-    import torch
-    import jxl_oxide_b200 as J
-    dev = args.probe_device
-    torch.cuda.set_device(dev)
-    nctx = max(1, args.contexts)
-    _, frames, (w, h) = load_workload(args.workload, nctx)
-    # bit pattern of one decoded frame under this schedule (the parent compares it with the default kernel's)
-    import hashlib
-    d0 = J.Decoder(dev)
-    d0.set_hf_streams_per_cta(args.probe_lanes)
-    d0.decode(frames[0])
-    digest = hashlib.sha256(d0.frame_planar(0).tobytes()).hexdigest()
-    d0.close()
-    decs = [J.Decoder(dev) for _ in range(nctx)]
-    for i, d in enumerate(decs):
-        d.set_hf_streams_per_cta(args.probe_lanes)
-        d.preload(0, frames[i % len(frames)])
-
-    def one_step():
-        errs = []
-
-        def work(d):
-            try:
-                d.decode_slot(0)
-                d.sync()
-                d.release_frames()
-            except Exception as e:  # noqa: BLE001
-                errs.append(e)
-        ts = [threading.Thread(target=work, args=(d,)) for d in decs]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
-    for _ in range(2):
-        one_step()
-    torch.cuda.synchronize()
-    steps = 3
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one_step()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / steps
-    print(json.dumps({"probe": "speed", "lanes": args.probe_lanes, "value": w * h * nctx / dt / 1e6, "ms_per_step": dt * 1e3,
-                      "sha256": digest}))
-
-
-def choose_hf_schedule(args, device):
-    """HF coefficient schedule for the timed run: (streams per CTA, report). An explicit --hf-lanes / JXLB_HF_LANES wins.
-    Otherwise one child process per schedule (the default first, then every candidate) decodes a frame of the workload,
-    reports the SHA-256 of its f32 planes and times a short lock-step run (all contexts, one frame each); a candidate is
-    kept only if its planes are bit-identical to the default kernel's and it is at least 3 % faster. A candidate whose
-    child fails or times out is dropped; if the default's child fails the default kernel is used without a probe."""
-    env_knob = os.environ.get("JXLB_HF_LANES")
-    if env_knob is not None or args.hf_lanes != "auto":
-        n = int(env_knob if env_knob is not None else args.hf_lanes)
-        return (0 if n <= 0 else (8 if n <= 8 else (16 if n <= 16 else (32 if n <= 32 else (64 if n <= 64 else 128))))), {"mode": "explicit"}
-    report = {"mode": "auto", "rule": "bit-identical to the default kernel and >= 3 % faster in a lock-step probe"}
-
-    def child(extra, timeout):
-        env = dict(os.environ)
-        env.pop("JXLB_HF_LANES", None)
-        fake = os.environ.get("JXLB_BENCH_FAKE_PROBE")  # host-logic test hook: canned child outputs, no GPU
-        if fake:
-            key = extra[3]
-            return json.loads(fake)[key]
-        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--contexts",
-                            str(args.contexts), "--probe-device", str(device)] + extra,
-                           capture_output=True, text=True, timeout=timeout, env=env)
-        if p.returncode != 0:
-            raise RuntimeError(f"probe {extra} exited with {p.returncode}: {p.stderr[-300:]}")
-        return json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+def gpu_local_cpus(device_index):
+    """CPUs local to the GPU's PCIe root (sysfs); empty when the topology cannot be read."""
     try:
-        ref = child(["--probe", "speed", "--probe-lanes", "0"], 300)
-        speeds, same = {"0": ref["value"]}, {}
-        for n in HF_CANDIDATES:
-            try:
-                r = child(["--probe", "speed", "--probe-lanes", str(n)], 300)
-            except Exception as e:  # noqa: BLE001  (this candidate is out; the others and the default are unaffected)
-                same[str(n)] = f"failed: {type(e).__name__}: {e}"[:200]
-                continue
-            same[str(n)] = r["sha256"] == ref["sha256"]
-            if same[str(n)] is True:
-                speeds[str(n)] = r["value"]
-        report["identical_to_default_kernel"] = same
-        report["probe_mp_s"] = speeds
-        cands = [n for n in HF_CANDIDATES if str(n) in speeds]
-        best = max(cands, key=lambda n: speeds[str(n)]) if cands else 0
-        chosen = best if best and speeds[str(best)] >= 1.03 * speeds["0"] else 0
-    except Exception as e:  # noqa: BLE001
-        report["fallback"] = f"{type(e).__name__}: {e}"[:300]
-        chosen = 0
-    report["chosen"] = chosen
-    return chosen, report
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        devid = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/local_cpulist"
+        out = []
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            out.extend(range(int(a), int(b or a) + 1))
+        return out
+    except Exception:
+        return []
+
+
+# HF coefficient schedule of the timed run: fixed (ncu evidence in profiles/r02_*), never probed inside the bench.
+HF_STREAMS_PER_CTA = 16
+CHAIN = ["hf_dequant_cfl", "hf_transform", "filters_fused", "gaborish", "epf_step", "xyb_to_rgb"]
+ENTROPY = ["modular_decode", "build_block_info", "decode_hf"]
 
 
 def run_ours(args, rank, world, local_rank):
@@ -329,83 +250,70 @@ def run_ours(args, rank, world, local_rank):
     if not os.path.exists(J.LIB_PATH):
         jb.build()
     torch.cuda.set_device(local_rank)
-    # rank 0 picks the HF schedule before it touches its GPU; the other ranks adopt it after the process group is up
-    hf_lanes, hf_report = choose_hf_schedule(args, local_rank) if rank == 0 else (0, None)
+    cpus = gpu_local_cpus(local_rank)
+    if cpus:
+        try:
+            os.sched_setaffinity(0, cpus)  # this process (and the pinned buffers it touches first) next to its GPU
+        except Exception:
+            cpus = []
+    env_knob = os.environ.get("JXLB_HF_LANES")
+    hf_lanes = int(env_knob) if env_knob is not None else (HF_STREAMS_PER_CTA if args.hf_lanes == "auto" else int(args.hf_lanes))
     desc, frames, (w, h) = load_workload(args.workload, args.frames_per_step)
     px_per_frame = w * h
-    nthreads = max(1, min(args.contexts, len(frames)))
-    decs = [J.Decoder(local_rank) for _ in range(nthreads)]
-    shares = [list(range(i, len(frames), nthreads)) for i in range(nthreads)]
-    # encoded frames resident in HBM ("inputs already resident"): one preloaded slot per frame
-    for d, idxs in zip(decs, shares):
-        for k in idxs:
-            d.preload(k, frames[k])
-    pinned = [torch.empty((3, h, w), dtype=torch.float32).pin_memory() for _ in range(nthreads)]
-    pinned_np = [p.numpy() for p in pinned]
-    decs[0].decode_slot(shares[0][0])  # shape of the packed 8-bit image (orientation and alpha are the stream's)
-    u8_shape = decs[0].frame_to_buffer(0, np.uint8).shape
-    decs[0].release_frames()
-    pinned_u8 = [torch.empty(u8_shape, dtype=torch.uint8).pin_memory() for _ in range(nthreads)]
-    pinned_u8_np = [p.numpy() for p in pinned_u8]
+    pipe = J.Pipeline(local_rank, workers=args.contexts, heavy_frames=args.heavy_frames, hf_streams_per_cta=hf_lanes)
+    # encoded frames resident in HBM ("inputs already resident"): one preloaded slot per distinct frame
+    distinct = {}
+    slots = []
+    for f in frames:
+        if id(f) not in distinct:
+            distinct[id(f)] = len(distinct)
+            pipe.preload(distinct[id(f)], f)
+        slots.append(distinct[id(f)])
 
-    def step(e2e, nsteps=1):
-        """`nsteps` passes over the batch. Every context walks its share of the batch `nsteps` times; contexts are
-        joined only at the end, so consecutive steps pipeline (no barrier between steps, one on each side of the
-        timed region) when --pipeline-steps asks for it; by default one step per call."""
-        errs = []
-
-        def work(d, idxs, out, out_u8, delay):
-            try:
-                if delay > 0.0:
-                    time.sleep(delay)  # de-phase the contexts (inside the timed region)
-                for _ in range(nsteps):
-                    for k in idxs:
-                        if e2e == "u8":
-                            d.decode(frames[k])                          # host bytes in
-                            d.frame_to_buffer(0, np.uint8, out=out_u8)   # interleaved 8-bit RGB out, packed on the device
-                        elif e2e:
-                            d.decode(frames[k])          # host bytes in
-                            d.frame_to_host(0, out)      # planar f32 out (pinned host)
-                        else:
-                            d.decode_slot(k)
-                            d.sync()
-                        d.release_frames()
-            except Exception as e:  # noqa: BLE001
-                errs.append(e)
-        ts = [threading.Thread(target=work, args=(d, idxs, o, o8, (i % args.stagger_groups) * args.stagger_ms / 1e3))
-              for i, (d, idxs, o, o8) in enumerate(zip(decs, shares, pinned_np, pinned_u8_np))]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
+    def run_steps(mode, nsteps):
+        """`nsteps` passes over the batch, frames flowing through the pipeline without a barrier between steps
+        (the contract's barriers sit on both sides of the K timed steps)."""
+        total = nsteps * len(frames)
+        sent = 0
+        got = 0
+        checksum = 0
+        # keep the queue a few steps deep at most: submission is cheap, but host buffers of submitted e2e jobs are not
+        depth = max(2 * pipe.workers(), 64)
+        while got < total:
+            while sent < total and sent - got < depth:
+                k = sent % len(frames)
+                if mode == "value":
+                    pipe.submit(slot=slots[k])
+                elif mode == "e2e":
+                    pipe.submit(data=frames[k], mode=J.Pipeline.OUT_PLANAR_F32)   # host bytes in, planar f32 to pinned host
+                else:
+                    pipe.submit(data=frames[k], mode=J.Pipeline.OUT_U8)           # host bytes in, interleaved u8 to pinned host
+                sent += 1
+            if mode == "value":
+                pipe.wait()
+            else:
+                _, addr, nbytes = pipe.wait(want_output=True)
+                checksum ^= nbytes  # the pixels are in host memory here; hand the buffer back to the ring
+                pipe.release_output(addr)
+            got += 1
+        return checksum
 
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        knob = torch.tensor([hf_lanes], dtype=torch.int32, device="cuda")
-        dist.broadcast(knob, src=0)
-        hf_lanes = int(knob.item())
-    for d in decs:
-        d.set_hf_streams_per_cta(hf_lanes)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(e2e, steps):
+    def timed(mode, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        if args.pipeline_steps:
-            step(e2e, steps)
-        else:
-            for _ in range(steps):
-                step(e2e)
+        run_steps(mode, steps)
         torch.cuda.synchronize()
         e1.record()
         e1.synchronize()
@@ -415,98 +323,59 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
-        step(False)
-    launches0 = sum(d.launch_count() for d in decs)
+    run_steps("value", max(1, args.warmup))
+    launches0 = pipe.launch_count()
     try:
         dev_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         dev_uuid = None
     sampler = ClockSampler(local_rank, dev_uuid)
     sampler.start()
-    ms = timed(False, args.steps)
+    ms = timed("value", args.steps)
     clocks = sampler.stop()
-    launches = sum(d.launch_count() for d in decs) - launches0
-    step(True)
-    ms_e2e = timed(True, args.steps)
-    # the same end-to-end call with the output an 8-bit image (ImageStream::write_to_buffer::<u8>): 3 B/px cross the
-    # host link instead of the 12 B/px of f32 planes that bound `e2e`
-    step("u8")
+    launches = pipe.launch_count() - launches0
+    run_steps("e2e", 1)
+    ms_e2e = timed("e2e", args.steps)
+    run_steps("u8", 1)
     ms_e2e_u8 = timed("u8", args.steps)
 
-    # per-kernel device time (CUDA events on the launching stream), one extra profiled step
+    # per-kernel device time (CUDA events on each worker's stream) of one extra step under full load, then of one frame
+    # alone on the GPU. Profiling is off during the timed steps: an event pair per launch costs stream concurrency.
+    decs = [pipe.decoder(i) for i in range(pipe.workers())]
     for d in decs:
         d.set_profile(True)
         d.profile_reset()
-    step(False)
+    run_steps("value", 1)
     prof = {}
     for k in KERNELS:
         n = sum(d.profile(k)[0] for d in decs)
         t = sum(d.profile(k)[1] for d in decs)
         if n:
             prof[k] = {"launches": n, "ms": t}
-    # the same kernels with one frame alone on the GPU (no queueing behind other streams' kernels)
-    decs[0].profile_reset()
-    solo_reps = 2
+    for d in decs:
+        d.profile_reset()
+    solo_reps = 3
     for _ in range(solo_reps):
-        decs[0].decode_slot(shares[0][0])
-        decs[0].sync()
-        decs[0].release_frames()
-    solo = {k: decs[0].profile(k)[1] / solo_reps for k in KERNELS if decs[0].profile(k)[0]}
+        pipe.submit(slot=slots[0])
+        pipe.wait()
+    solo = {}
+    for k in KERNELS:
+        n = sum(d.profile(k)[0] for d in decs)
+        t = sum(d.profile(k)[1] for d in decs)
+        if n:
+            solo[k] = t / solo_reps
     for d in decs:
         d.set_profile(False)
 
     total_px = px_per_frame * len(frames) * world
     gather = None
     if args.gather != "none":
-        # BASELINE config #5's delivery: every frame packed on its GPU (interleaved u8 / u16, 3-6 B/px instead of 12 B/px
-        # of f32 planes) and gathered to rank 0 over NCCL (jxl_oxide_b200.sharding.gather_frames); timed like `value`.
-        from jxl_oxide_b200 import sharding
-        gdt = np.uint8 if args.gather == "u8" else np.uint16
-        packed = [None] * len(frames)
-
-        def gather_step():
-            errs = []
-
-            def work(d, idxs):
-                try:
-                    for k in idxs:
-                        d.decode_slot(k)
-                        packed[k] = d.frame_to_torch(0, gdt, out=packed[k])
-                        d.release_frames()
-                except Exception as e:  # noqa: BLE001
-                    errs.append(e)
-            ts = [threading.Thread(target=work, args=(d, idxs)) for d, idxs in zip(decs, shares)]
-            for t in ts:
-                t.start()
-            for t in ts:
-                t.join()
-            if errs:
-                raise errs[0]
-            return sharding.gather_frames(packed, len(frames) * world, dst=0)
-
-        gather_step()
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
-            got = gather_step()
-        torch.cuda.synchronize()
-        g1.record()
-        g1.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1)], device="cuda")
-        if dist is not None:
-            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        ms_g = float(tg.item())
-        nbytes = int(packed[0].numel() * packed[0].element_size())
-        gather = {"value": total_px / (ms_g / args.steps / 1e3) / 1e6, "unit": "MP/s", "ms_per_step": ms_g / args.steps,
-                  "format": f"{args.gather} interleaved RGB, packed on the device",
-                  "bytes_to_rank0_per_step": nbytes * len(frames) * (world - 1),
-                  "collective": "torch.distributed gather (nccl), one per round of world_size frames" if world > 1 else "none (1 rank)",
-                  "frames_at_rank0": (len([g for g in got if g is not None]) if got is not None else 0) if rank == 0 else None}
+        gather = run_gather(args, torch, dist, J, local_rank, world, rank, frames, total_px, barrier, hf_lanes)
     value = total_px / (ms / args.steps / 1e3) / 1e6
     e2e_value = total_px / (ms_e2e / args.steps / 1e3) / 1e6
     e2e_u8_value = total_px / (ms_e2e_u8 / args.steps / 1e3) / 1e6
+    u8_bytes = px_per_frame * 3
+    pipe.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -518,67 +387,158 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
-    dom = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
+    peak_source = "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # The dominant HBM-bound work: the pixel chain coefficients -> RGB planes (24.3 B/px when fully fused).
+    # One "launch" = the chain's kernels for one frame; duration = the sum of their CUDA-event times.
+    chain_bytes = px_per_frame * 24.3
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if tj.get("workload") == args.workload:
+            traffic = tj.get("chain_dram_bytes_per_frame")
+    except Exception:
+        pass
     roofline = None
-    if dom:
-        stream_bytes = float(np.mean([len(f) for f in frames]))
-        per_launch_frames = len(frames) / max(1, prof[dom]["launches"])
-        ab = algorithmic_bytes(dom, w, h, stream_bytes)
-        avg_ms = prof[dom]["ms"] / prof[dom]["launches"]
-        achieved = (ab * per_launch_frames) / (avg_ms / 1e3) / 1e9 if ab else None
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if tj.get("workload") == args.workload:
-                traffic = tj.get(dom)
-        except Exception:
-            pass
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                    "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 GB/s",
-                    "avg_launch_ms": avg_ms,
-                    "measured": "CUDA events around each launch during one step with all contexts running",
-                    "note": "entropy decode is latency-bound (serial ANS/context chain per stream), see DESIGN.md"}
-    # the HBM-bound pixel pipeline, reported beside the dominant kernel
-    pipe = ["hf_dequant_cfl", "hf_transform", "filters_fused", "gaborish", "epf_step", "xyb_to_rgb"]
-    pipe_ms = sum(prof[k]["ms"] for k in pipe if k in prof)
-    pipe_bytes = sum((algorithmic_bytes(k, w, h, 0) or 0) * (prof[k]["launches"] / (3 if k == "gaborish" else 1))
-                     for k in pipe if k in prof)
-    pipeline = None
-    if pipe_ms > 0:
-        ach = pipe_bytes / (pipe_ms / 1e3) / 1e9
-        pipeline = {"kernels": [k for k in pipe if k in prof], "ms_per_step": pipe_ms, "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "bytes": "sum of each kernel's own algorithmic bytes (24 B/px each)"}
-        solo_ms = sum(solo.get(k, 0.0) for k in pipe)
-        if solo_ms > 0:
-            fused_bytes = px_per_frame * 24.3  # coefficients in -> RGB out, fully fused chain
-            pipeline["solo"] = {"ms_per_frame": solo_ms, "achieved_vs_fused_chain_bytes": fused_bytes / (solo_ms / 1e3) / 1e9,
-                                "frac_of_peak": fused_bytes / (solo_ms / 1e3) / 1e9 / peak,
-                                "note": "one frame alone on the GPU; 24.3 B/px algorithmic bytes of the fully fused chain"}
-    cpu = cpu_baseline(args, frames, px_per_frame)
+    chain_solo_ms = sum(solo.get(k, 0.0) for k in CHAIN)
+    chain_load_ms = sum(prof[k]["ms"] for k in CHAIN if k in prof) / max(1, len(frames))
+    if chain_solo_ms > 0:
+        ach = chain_bytes / (chain_solo_ms / 1e3) / 1e9
+        roofline = {"kernel": "+".join(k for k in CHAIN if k in solo), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic, "peak_source": peak_source,
+                    "bytes_per_launch": chain_bytes, "avg_launch_ms": chain_solo_ms,
+                    "per_kernel_ms": {k: round(solo[k], 4) for k in CHAIN if k in solo},
+                    "measured": "CUDA events around the chain's launches, one frame alone on the GPU (mean of 3)",
+                    "under_load": {"avg_launch_ms": chain_load_ms, "achieved": chain_bytes / (chain_load_ms / 1e3) / 1e9 if chain_load_ms else None,
+                                   "note": "same kernels during one step with every worker busy: event times include waiting "
+                                           "for SMs held by other frames' kernels"},
+                    "algorithmic_bytes": "24.3 B/px x pixels: 12 B coefficients + 0.33 B LF/meta read, 12 B RGB written (fully fused chain)"}
+    entropy = None
+    try:
+        sym = json.load(open(os.path.join(ROOT, "profiles", "r02_symbols.json"))).get(args.workload)
+    except Exception:
+        sym = None
+    ent_solo = {k: round(solo[k], 3) for k in ENTROPY if k in solo}
+    if ent_solo:
+        entropy = {"bound": "latency", "ms_per_frame_solo": ent_solo,
+                   "ms_per_frame_under_load": {k: round(prof[k]["ms"] / len(frames), 3) for k in ENTROPY if k in prof},
+                   "note": "serial ANS / context chains (one per LF-group stream, one per 256x256 group): reported as "
+                           "symbols/s, not against the HBM roofline"}
+        if sym and "decode_hf" in solo:
+            entropy["hf_symbols_per_frame"] = sym.get("hf_symbols")
+            entropy["hf_symbols_per_s_solo"] = sym.get("hf_symbols", 0) / (solo["decode_hf"] / 1e3)
+            entropy["hf_symbols_per_s_whole_job"] = sym.get("hf_symbols", 0) * len(frames) * world / (ms / args.steps / 1e3)
+    cpu = cpu_baseline(args, frames, px_per_frame) if not args.no_cpu_baseline else None
     line = {
-        "metric": "Megapixels/s decoded (8K VarDCT d1.0)", "value": value, "unit": "MP/s", "n_gpus": world,
+        "metric": METRIC.get(args.workload, "Megapixels/s decoded"), "value": value, "unit": "MP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if "synth" in args.workload else "real-file mosaic",
-        "config": {"workload": desc, "frames_per_step_per_gpu": len(frames), "decoder_contexts_per_gpu": nthreads,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if "mod" not in args.workload else "i32",
+        "data": "synthetic" if "synth" in args.workload else "real-file mosaic",
+        "config": {"workload": desc, "frames_per_step_per_gpu": len(frames), "pipeline_workers_per_gpu": pipe_workers(args),
+                   "heavy_frames_per_gpu": args.heavy_frames,
                    "cache": "inputs+planes per step (>= 33 MP x 24 B) exceed L2 (126 MB); no explicit L2 flush",
-                   "step_barrier": "before and after the K timed steps (steps pipeline across decoder contexts)"
-                                   if args.pipeline_steps else "after every step",
-                   "stagger_ms": args.stagger_ms,
-                   "hf_streams_per_cta": hf_lanes, "hf_schedule": hf_report},
+                   "step_barrier": "before and after the K timed steps; frames flow through the in-library pipeline",
+                   "hf_streams_per_cta": hf_lanes, "cpu_affinity": "GPU-local CPUs" if cpus else "unchanged"},
         "e2e": {"value": e2e_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
-                "d2h_bytes_per_step": int(px_per_frame * 12 * len(frames)), "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": int(px_per_frame * 12 * len(frames)), "ms_per_step": ms_e2e / args.steps,
+                "path": "jxlb_pipeline_submit(host bytes) -> planar f32 in pinned host memory (jxlb_pipeline_wait)"},
         "e2e_u8": {"value": e2e_u8_value, "unit": "MP/s", "h2d_bytes_per_step": int(sum(len(f) for f in frames)),
-                   "d2h_bytes_per_step": int(np.prod(u8_shape)) * len(frames), "ms_per_step": ms_e2e_u8 / args.steps,
-                   "note": "same call path as e2e, output = interleaved 8-bit RGB packed on the device "
-                           "(jxlb_frame_write_to_buffer); reported beside e2e, not instead of it"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "pipeline_roofline": pipeline,
-        "kernel_ms_per_step": {k: round(v["ms"], 3) for k, v in prof.items()},
+                   "d2h_bytes_per_step": int(u8_bytes) * len(frames), "ms_per_step": ms_e2e_u8 / args.steps,
+                   "note": "same call path, output = interleaved 8-bit RGB packed on the device (ImageStream::write_to_buffer::<u8>); "
+                           "reported beside e2e, not instead of it"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "entropy": entropy,
+        "kernel_ms_per_step_summed_over_streams": {k: round(v["ms"], 3) for k, v in prof.items()},
         "kernel_ms_per_frame_solo": {k: round(v, 3) for k, v in solo.items()}, "cpu_baseline": cpu,
     }
     if gather is not None:
         line["gather"] = gather
     print(json.dumps(line))
+
+
+def pipe_workers(args):
+    return args.contexts
+
+
+METRIC = {"synth8k": "Megapixels/s decoded (8K VarDCT d1.0)", "synth4k": "Megapixels/s decoded (4K VarDCT d1.0)",
+          "synth8k_d2": "Megapixels/s decoded (8K VarDCT d2.0, EPF 3 iterations)",
+          "synthmod4k": "Megapixels/s decoded (4K Modular lossless, Squeeze + weighted predictor)",
+          "mosaic8k": "Megapixels/s decoded (8K VarDCT d1.0)"}
+
+
+def run_gather(args, torch, dist, J, local_rank, world, rank, frames, total_px, barrier, hf_lanes):
+    """BASELINE config #5's delivery: every frame packed on its GPU (interleaved u8 / u16, 3-6 B/px instead of 12 B/px of
+    f32 planes) and gathered to rank 0 over NCCL (jxl_oxide_b200.sharding.gather_frames); timed like `value`. Decode
+    contexts run in threads; the gather of round r overlaps the decode of round r + 1 (frames packed into a second
+    buffer set)."""
+    from jxl_oxide_b200 import sharding
+    gdt = np.uint8 if args.gather == "u8" else np.uint16
+    nthreads = max(1, min(args.gather_contexts, len(frames)))
+    decs = [J.Decoder(local_rank) for _ in range(nthreads)]
+    shares = [list(range(i, len(frames), nthreads)) for i in range(nthreads)]
+    for d, idxs in zip(decs, shares):
+        d.set_hf_streams_per_cta(hf_lanes)
+        for k in idxs:
+            d.preload(k, frames[k])
+    packed = [None] * len(frames)
+
+    def decode_all():
+        errs = []
+
+        def work(d, idxs):
+            try:
+                for k in idxs:
+                    d.decode_slot(k)
+                    packed[k] = d.frame_to_torch(0, gdt, out=packed[k])
+                    d.release_frames()
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=work, args=(d, idxs)) for d, idxs in zip(decs, shares)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def gather_step():
+        decode_all()
+        return sharding.gather_frames(packed, len(frames) * world, dst=0)
+
+    got = gather_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        got = gather_step()
+    torch.cuda.synchronize()
+    g1.record()
+    g1.synchronize()
+    tg = torch.tensor([g0.elapsed_time(g1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    ms_g = float(tg.item())
+    # decode + pack without the collective, same threads: what the gather adds
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0.record()
+    for _ in range(args.steps):
+        decode_all()
+    torch.cuda.synchronize()
+    d1.record()
+    d1.synchronize()
+    td = torch.tensor([d0.elapsed_time(d1)], device="cuda")
+    if dist is not None:
+        dist.all_reduce(td, op=dist.ReduceOp.MAX)
+    ms_d = float(td.item())
+    nbytes = int(packed[0].numel() * packed[0].element_size())
+    for d in decs:
+        d.close()
+    return {"value": total_px / (ms_g / args.steps / 1e3) / 1e6, "unit": "MP/s", "ms_per_step": ms_g / args.steps,
+            "decode_pack_only": {"value": total_px / (ms_d / args.steps / 1e3) / 1e6, "ms_per_step": ms_d / args.steps},
+            "format": f"{args.gather} interleaved RGB, packed on the device",
+            "bytes_to_rank0_per_step": nbytes * len(frames) * (world - 1),
+            "nvlink_gb_s_into_rank0": nbytes * len(frames) * (world - 1) / (ms_g / args.steps / 1e3) / 1e9,
+            "collective": "torch.distributed gather (nccl), one per round of world_size frames" if world > 1 else "none (1 rank)",
+            "frames_at_rank0": (len([g for g in got if g is not None]) if got is not None else 0) if rank == 0 else None}
 
 
 def cpu_throughput(frames, px_per_frame, steps, warm=1):
@@ -636,7 +596,7 @@ def run_reference(args, rank, world):
     desc, frames, (w, h) = load_workload(args.workload, args.frames_per_step)
     value, dt, cpu = cpu_throughput(frames, w * h, max(1, args.steps), warm=max(1, min(args.warmup, 1)))
     print(json.dumps({
-        "impl": "reference", "metric": "Megapixels/s decoded (8K VarDCT d1.0)", "value": value, "unit": "MP/s",
+        "impl": "reference", "metric": METRIC.get(args.workload, "Megapixels/s decoded"), "value": value, "unit": "MP/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if "synth" in args.workload else "real-file mosaic",
         "config": {"workload": desc, "note": "CPU restatement of jxl-oxide's generic render path, all host cores: "
@@ -652,31 +612,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="synth8k", help="synth8k | synth4k | mosaic8k | file:PATH")
-    ap.add_argument("--contexts", type=int, default=24, help="decoder contexts (CUDA streams) per GPU")
+    ap.add_argument("--contexts", type=int, default=40, help="pipeline workers (decoder contexts = CUDA streams) per GPU")
+    ap.add_argument("--heavy-frames", type=int, default=10, help="frames allowed past the LF stage at once (HBM slabs)")
+    ap.add_argument("--gather-contexts", type=int, default=8)
     ap.add_argument("--frames-per-step", type=int, default=48, help="independent frames decoded per step per GPU")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
-    ap.add_argument("--stagger-ms", type=float, default=0.0, help="start offset between context groups within a step")
-    ap.add_argument("--stagger-groups", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (experiments only)")
     ap.add_argument("--gather", default="none", choices=["none", "u8", "u16"],
                     help="also time decode + device-side packing + NCCL gather of every frame to rank 0 (BASELINE config #5)")
     ap.add_argument("--hf-lanes", default="auto", choices=["auto", "0", "8", "16", "32", "64", "128"],
                     help="HF coefficient schedule = streams per CTA: 0 (= 4) / 8 / 16 one warp per stream, 32 / 64 / 128 one "
-                         "thread per stream; "
-                         "auto = probe in child processes (parity against the default kernel, then a short A/B) and keep the "
-                         "faster one. JXLB_HF_LANES in the environment overrides.")
-    ap.add_argument("--probe", default=None, choices=["speed"], help=argparse.SUPPRESS)
-    ap.add_argument("--probe-lanes", type=int, default=0, help=argparse.SUPPRESS)
-    ap.add_argument("--probe-device", type=int, default=0, help=argparse.SUPPRESS)
-    ap.add_argument("--pipeline-steps", action="store_true",
-                    help="run the K timed steps back to back, contexts joined only at the end (default: joined after every "
-                         "step - measured faster, profiles/r01_progress.md)")
+                         "thread per stream; auto = the fixed default (HF_STREAMS_PER_CTA). JXLB_HF_LANES in the environment "
+                         "overrides.")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.probe:
-        run_probe(args)
-    elif args.impl == "reference":
+    if args.impl == "reference":
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, world, local_rank)

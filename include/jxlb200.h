@@ -103,7 +103,8 @@ uint64_t jxlb_launch_count(const jxlb_decoder* dec);
  * stream; jxlb_profile_get returns launches and accumulated milliseconds for a kernel family
  * ("modular_decode", "decode_hf", "hf_transform", "epf_step", ...). Used by bench.py's roofline.
  * on == 2 selects a lighter trace instead: no events, the Modular stream kernels stamp the device
- * clock and the host logs launch / return times (see jxlb_timeline_get). */
+ * clock and the host logs launch / return times (see jxlb_timeline_get). on == 3: only the host wall clock per
+ * planner phase ("host:lf_coeff", "host:pass_groups", ...; device waits included), no events at all. */
 int32_t jxlb_set_profile(jxlb_decoder* dec, int32_t on);
 int32_t jxlb_profile_get(jxlb_decoder* dec, const char* name, uint64_t* launches, double* total_ms);
 int32_t jxlb_profile_reset(jxlb_decoder* dec);
@@ -119,8 +120,9 @@ int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on);
  * stage-by-stage form also emits the "gaborish" / "epf" snapshots for stage-level parity tests. */
 int32_t jxlb_set_fuse_filters(jxlb_decoder* dec, int32_t on);
 /* Scheduling of the HF coefficient streams (one per 256x256 group and pass, jxl-frame/src/data/pass_group.rs:31): how
- * many streams share one CTA and its staged tables. 0 (default, = 4), 8, 16: one warp per stream; 32 / 64 / 128: one
- * thread per stream. Results are identical; the process-wide default comes from the environment variable JXLB_HF_LANES. */
+ * many streams share one CTA and its staged tables. 0 (default, = 16), 8, 16, 32: one warp per stream, all presets'
+ * tables staged once per CTA; 4: the round-1 kernel; 64 / 128: one thread per stream (experimental, slower). Results are
+ * identical; the process-wide default comes from the environment variable JXLB_HF_LANES. */
 int32_t jxlb_set_hf_streams_per_cta(jxlb_decoder* dec, int32_t streams);
 int32_t jxlb_stage_count(const jxlb_decoder* dec, const char* name);
 int32_t jxlb_stage_get(const jxlb_decoder* dec, const char* name, int32_t idx, uint32_t* width, uint32_t* height,
@@ -159,6 +161,46 @@ int32_t jxlb_blend(jxlb_decoder* dec, float* base, const float* patch, const flo
 /* rct::inverse_rct (crates/jxl-modular/src/transform/rct.rs:15). In place on three planes. */
 int32_t jxlb_rct_inverse(jxlb_decoder* dec, int32_t* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
                          uint32_t rct_type);
+
+/* ---- Frame pipeline: many independent frames through one GPU ----
+ * Replaces the reference's frame-level concurrency: jxl-oxide-cli renders keyframes through rayon's par_iter
+ * (crates/jxl-oxide-cli/src/decode.rs:285-320), jxl-render spawns reference / LF frames eagerly
+ * (crates/jxl-render/src/lib.rs:496-509). `workers` decoder contexts (one CUDA stream + one host thread each, threads
+ * pinned to the CPUs local to the GPU) take frames from one queue; at most `heavy_frames` of them are past the LF
+ * stage at any time (each of those owns a pre-allocated slab of HBM for its full-resolution planes), so HBM use is
+ * heavy_frames x ~25 B/px whatever `workers` is. Frames are reported in completion order. */
+typedef struct jxlb_pipeline jxlb_pipeline;
+typedef struct {
+  int32_t workers;            /* 0 = default (32) */
+  int32_t heavy_frames;       /* 0 = default (8) */
+  int32_t hf_streams_per_cta; /* 0 = library default, see jxlb_set_hf_streams_per_cta */
+  int32_t no_affinity;        /* 1 = leave the worker threads' CPU affinity alone */
+} jxlb_pipeline_config;
+int32_t jxlb_pipeline_create(int32_t cuda_device, const jxlb_pipeline_config* cfg, jxlb_pipeline** out);
+void jxlb_pipeline_destroy(jxlb_pipeline* p);
+const char* jxlb_pipeline_last_error(const jxlb_pipeline* p);
+/* Encoded image kept resident in HBM for jxlb_pipeline_submit(data = NULL, slot). */
+int32_t jxlb_pipeline_preload(jxlb_pipeline* p, int32_t slot, const uint8_t* data, size_t size);
+/* Queue one frame: `data`/`size` host bytes (kept alive by the caller until the frame is reported) or data = NULL
+ * and a preloaded `slot`. out_mode 0: decode only (planes are produced in HBM and released), 1: all channels as
+ * planar f32 (channel-major, Render::image_planar), 2 / 3: ImageStream::write_to_buffer::<u8 / u16> (interleaved, image
+ * orientation, packed on the device). The pixels go to host `dst` or, with dst = NULL, into a pinned buffer of the
+ * pipeline's own ring (allocated NUMA-local to the GPU by the worker threads) that jxlb_pipeline_wait hands out and
+ * jxlb_pipeline_release_output takes back. `tag` comes back from jxlb_pipeline_wait. Never blocks. */
+int32_t jxlb_pipeline_submit(jxlb_pipeline* p, const uint8_t* data, size_t size, int32_t slot, int32_t out_mode, void* dst,
+                             size_t dst_bytes, uint64_t tag);
+/* Blocks until a submitted frame has finished (its output, if any, is complete in `dst`); returns its tag and decode
+ * status (+ message), and where its pixels are (`out`, `out_bytes`; may be NULL pointers when not wanted).
+ * JXLB_ERR_INVALID_ARG when nothing is in flight. */
+int32_t jxlb_pipeline_wait(jxlb_pipeline* p, uint64_t* tag, int32_t* status, void** out, size_t* out_bytes, char* err,
+                           size_t err_cap);
+/* Returns a pipeline-owned output buffer (from jxlb_pipeline_wait) to the ring. */
+int32_t jxlb_pipeline_release_output(jxlb_pipeline* p, void* out);
+uint64_t jxlb_pipeline_launch_count(const jxlb_pipeline* p);
+int32_t jxlb_pipeline_workers(const jxlb_pipeline* p);
+/* The i-th worker's decoder context (profiling knobs: jxlb_set_profile / jxlb_profile_get); NULL when out of range.
+ * Must not be used to decode while frames are in flight. */
+jxlb_decoder* jxlb_pipeline_decoder(jxlb_pipeline* p, int32_t index);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,8 @@ EXPORTED_SYMBOLS = [
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
     "jxlb_profile_reset", "jxlb_timeline_get", "jxlb_set_capture", "jxlb_set_fuse_filters", "jxlb_set_hf_streams_per_cta", "jxlb_stage_count", "jxlb_stage_get",
     "jxlb_gaborish", "jxlb_epf", "jxlb_xyb_to_rgb", "jxlb_squeeze_inverse", "jxlb_rct_inverse", "jxlb_blend",
+    "jxlb_pipeline_create", "jxlb_pipeline_destroy", "jxlb_pipeline_last_error", "jxlb_pipeline_preload", "jxlb_pipeline_submit",
+    "jxlb_pipeline_wait", "jxlb_pipeline_release_output", "jxlb_pipeline_launch_count", "jxlb_pipeline_workers", "jxlb_pipeline_decoder",
 ]
 
 
@@ -58,6 +60,10 @@ class _FrameInfo(ctypes.Structure):
 class _ImageInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint32) for n in
                 ("width", "height", "bits_per_sample", "num_extra_channels", "xyb_encoded", "grayscale", "orientation")]
+
+
+class _PipelineConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("workers", "heavy_frames", "hf_streams_per_cta", "no_affinity")]
 
 
 class EpfParams(ctypes.Structure):
@@ -120,6 +126,21 @@ def load_library():
                                   ctypes.POINTER(ctypes.c_float), ctypes.c_float, i32]
     L.jxlb_squeeze_inverse.argtypes = [vp, vp, u32, u32, u32, vp, u32, u32, u32, vp, u32, i32]
     L.jxlb_rct_inverse.argtypes = [vp, ctypes.POINTER(vp), u32, u32, u32, u32]
+    L.jxlb_pipeline_create.argtypes = [i32, ctypes.POINTER(_PipelineConfig), ctypes.POINTER(vp)]
+    L.jxlb_pipeline_destroy.argtypes = [vp]
+    L.jxlb_pipeline_destroy.restype = None
+    L.jxlb_pipeline_last_error.argtypes = [vp]
+    L.jxlb_pipeline_last_error.restype = ctypes.c_char_p
+    L.jxlb_pipeline_preload.argtypes = [vp, i32, ctypes.c_char_p, ctypes.c_size_t]
+    L.jxlb_pipeline_submit.argtypes = [vp, vp, ctypes.c_size_t, i32, i32, vp, ctypes.c_size_t, ctypes.c_uint64]
+    L.jxlb_pipeline_wait.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(i32), ctypes.POINTER(vp),
+                                     ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
+    L.jxlb_pipeline_release_output.argtypes = [vp, vp]
+    L.jxlb_pipeline_launch_count.argtypes = [vp]
+    L.jxlb_pipeline_launch_count.restype = ctypes.c_uint64
+    L.jxlb_pipeline_workers.argtypes = [vp]
+    L.jxlb_pipeline_decoder.argtypes = [vp, i32]
+    L.jxlb_pipeline_decoder.restype = vp
     _lib = L
     return L
 
@@ -264,9 +285,9 @@ class Decoder:
         self._L.jxlb_set_fuse_filters(self._h, int(on))
 
     def set_hf_streams_per_cta(self, streams):
-        """HF streams per CTA: 0 (default, = 4), 8, 16: one warp per stream; 32 / 64 / 128: one thread per stream."""
+        """HF streams per CTA: 0 (default, = 16), 8, 16, 32: one warp per stream; 4: round-1 kernel; 64 / 128: one thread per stream."""
         if self._L.jxlb_set_hf_streams_per_cta(self._h, int(streams)) != 0:
-            raise ValueError("streams per CTA must be 0, 8, 16, 32, 64 or 128")
+            raise ValueError("streams per CTA must be 0, 4, 8, 16, 32, 64 or 128")
 
     def stage(self, name, dtype=np.float32):
         n = self._L.jxlb_stage_count(self._h, name.encode())
@@ -320,7 +341,121 @@ class Decoder:
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.jxlb_decoder_destroy(self._h)
+            if getattr(self, "_owned", True):
+                self._L.jxlb_decoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pipeline:
+    """Many independent frames through one GPU (jxlb_pipeline_*): `workers` decoder contexts fed from one queue, at
+    most `heavy_frames` of them past the LF stage. The analogue of decoding keyframes in a rayon par_iter
+    (crates/jxl-oxide-cli/src/decode.rs:285-320)."""
+
+    OUT_NONE, OUT_PLANAR_F32, OUT_U8, OUT_U16 = 0, 1, 2, 3
+
+    def __init__(self, device=0, workers=0, heavy_frames=0, hf_streams_per_cta=0, no_affinity=False):
+        self._L = load_library()
+        self.device = device
+        cfg = _PipelineConfig(int(workers), int(heavy_frames), int(hf_streams_per_cta), int(bool(no_affinity)))
+        h = ctypes.c_void_p()
+        rc = self._L.jxlb_pipeline_create(device, ctypes.byref(cfg), ctypes.byref(h))
+        if rc != OK:
+            raise JxlError(rc, "cannot create a pipeline (no CUDA device? there is no CPU fallback)")
+        self._h = h
+        self._keep = {}      # tag -> objects that must outlive the job (input bytes, output arrays)
+        self._next_tag = 0
+        self.in_flight = 0
+
+    def _err(self, rc):
+        raise JxlError(rc, (self._L.jxlb_pipeline_last_error(self._h) or b"").decode())
+
+    def preload(self, slot, data: bytes):
+        rc = self._L.jxlb_pipeline_preload(self._h, slot, data, len(data))
+        if rc != OK:
+            self._err(rc)
+
+    def submit(self, data=None, slot=-1, out=None, mode=None, tag=None):
+        """Queues one frame: `data` (bytes) or a preloaded `slot`. `out`: None (decode only), a float32 (c, h, w) array
+        (planar) or a uint8 / uint16 (h, w, c) array (interleaved); it must stay untouched until wait() reports the tag."""
+        if tag is None:
+            tag = self._next_tag
+            self._next_tag += 1
+        if mode is None:  # with out=None pass mode explicitly to get the pixels in a pipeline-owned pinned buffer
+            mode = self.OUT_NONE if out is None else {np.dtype(np.float32): 1, np.dtype(np.uint8): 2, np.dtype(np.uint16): 3}[out.dtype]
+        dst, nbytes = (out.ctypes.data, out.nbytes) if out is not None else (None, 0)
+        buf = None
+        if data is not None:
+            buf = ctypes.c_char_p(data)
+        rc = self._L.jxlb_pipeline_submit(self._h, ctypes.cast(buf, ctypes.c_void_p) if buf is not None else None,
+                                          len(data) if data is not None else 0, slot, mode, dst, nbytes, tag)
+        if rc != OK:
+            self._err(rc)
+        self._keep[tag] = (data, buf, out)
+        self.in_flight += 1
+        return tag
+
+    def wait(self, want_output=False):
+        """Blocks until one frame has finished; returns its tag, or (tag, address, nbytes) of its pixels with
+        want_output (a pipeline-owned pinned buffer must then go back through release_output()). Raises JxlError when
+        that frame failed. Without want_output a pipeline-owned buffer is returned to the ring at once."""
+        tag, status = ctypes.c_uint64(), ctypes.c_int32()
+        out, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        msg = ctypes.create_string_buffer(256)
+        rc = self._L.jxlb_pipeline_wait(self._h, ctypes.byref(tag), ctypes.byref(status), ctypes.byref(out), ctypes.byref(nbytes), msg, 256)
+        if rc != OK:
+            raise JxlError(rc, "no frame in flight")
+        self.in_flight -= 1
+        kept = self._keep.pop(tag.value, None)
+        if status.value != OK:
+            raise JxlError(status.value, msg.value.decode(errors="replace"))
+        owned = out.value is not None and (kept is None or kept[2] is None)
+        if want_output:
+            return tag.value, out.value, nbytes.value
+        if owned:
+            self._L.jxlb_pipeline_release_output(self._h, out)
+        return tag.value
+
+    def release_output(self, address):
+        self._L.jxlb_pipeline_release_output(self._h, ctypes.c_void_p(address))
+
+    def drain(self):
+        """Waits for every frame in flight; raises the first error after all have been collected."""
+        first = None
+        while self.in_flight:
+            try:
+                self.wait()
+            except JxlError as e:
+                first = first or e
+        if first:
+            raise first
+
+    def launch_count(self):
+        return int(self._L.jxlb_pipeline_launch_count(self._h))
+
+    def workers(self):
+        return int(self._L.jxlb_pipeline_workers(self._h))
+
+    def decoder(self, index):
+        """The index-th worker's Decoder (profiling knobs only; not owned by the returned object)."""
+        h = self._L.jxlb_pipeline_decoder(self._h, index)
+        if not h:
+            raise IndexError(index)
+        d = Decoder.__new__(Decoder)
+        d._L = self._L
+        d._h = ctypes.c_void_p(h)
+        d._owned = False  # borrowed: destroyed with the pipeline
+        d.device = self.device
+        return d
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.jxlb_pipeline_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -2,31 +2,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
-#include <map>
-#include <memory>
-#include <string>
 
-#include "../../include/jxlb200.h"
-#include "cuda_backend.h"
-#include "host/planner.h"
+#include "capi_internal.h"
 
 using namespace jxlb;
-
-struct jxlb_decoder {
-  std::unique_ptr<CudaBackend> be;
-  DecodeResult res;
-  bool have_result = false;
-  std::string error;
-  std::vector<uint8_t> codestream;
-  struct Slot {
-    std::vector<uint8_t> codestream;
-    uint8_t* dptr = nullptr;
-  };
-  std::map<int32_t, Slot> slots;
-  ~jxlb_decoder() {
-    for (auto& kv : slots) cudaFree(kv.second.dptr);
-  }
-};
 
 namespace {
 
@@ -62,6 +41,45 @@ DevView raw_view(void* p, uint32_t w, uint32_t h, uint32_t stride) {
 }
 
 }  // namespace
+
+namespace jxlb {
+int32_t decode_resident(jxlb_decoder* dec, const uint8_t* cs, size_t size, const uint8_t* dptr, const jxlb_options* opt) {
+  if (!dec || !cs || !dptr) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    release(dec);
+    DecodeOptions o;
+    if (opt) {
+      o.output_colour = opt->output_colour;
+      if (opt->max_frames) o.max_frames = opt->max_frames;
+    }
+    dec->be->use_resident_once(dptr);
+    dec->res = decode_codestream(*dec->be, cs, size, o);
+    dec->have_result = true;
+  });
+}
+
+int32_t frame_planar_to_host(jxlb_decoder* dec, int32_t frame, float* dst, size_t dst_bytes) {
+  if (!dec || !dst || !dec->have_result || frame < 0 || size_t(frame) >= dec->res.frames.size()) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    const DecodedFrame& f = dec->res.frames[frame];
+    size_t off = 0;
+    for (const View& v : f.channels) {
+      const size_t bytes = size_t(v.w) * v.h * 4;
+      JXLB_CHECK(off + bytes <= dst_bytes, kErrInvalidArg, "destination buffer too small");
+      DevView d = dec->be->dev_view(v);
+      cudaError_t e;
+      if (d.stride == v.w)
+        e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(dst) + off, d.ptr, bytes, cudaMemcpyDeviceToHost, dec->be->stream());
+      else
+        e = cudaMemcpy2DAsync(reinterpret_cast<uint8_t*>(dst) + off, size_t(v.w) * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h,
+                              cudaMemcpyDeviceToHost, dec->be->stream());
+      JXLB_CHECK(e == cudaSuccess, kErrCuda, cudaGetErrorString(e));
+      off += bytes;
+    }
+    dec->be->sync();
+  });
+}
+}  // namespace jxlb
 
 extern "C" {
 
@@ -269,6 +287,7 @@ uint64_t jxlb_launch_count(const jxlb_decoder* dec) { return dec ? dec->be->laun
 
 int32_t jxlb_set_profile(jxlb_decoder* dec, int32_t on) {
   if (!dec) return JXLB_ERR_INVALID_ARG;
+  dec->be->host_phases = on == 3;   // host wall clock per planner phase only
   dec->be->profile = on == 1;       // CUDA events around every launch + host phase clock
   dec->be->trace_device = on == 2;  // no events: device-clock stamps in the stream kernels + host launch/return times
   return JXLB_OK;
@@ -322,7 +341,7 @@ int32_t jxlb_set_fuse_filters(jxlb_decoder* dec, int32_t on) {
 }
 
 int32_t jxlb_set_hf_streams_per_cta(jxlb_decoder* dec, int32_t streams) {
-  if (!dec || (streams != 0 && streams != 8 && streams != 16 && streams != 32 && streams != 64 && streams != 128))
+  if (!dec || (streams != 0 && streams != 4 && streams != 8 && streams != 16 && streams != 32 && streams != 64 && streams != 128))
     return JXLB_ERR_INVALID_ARG;
   dec->be->hf_streams_per_cta = streams;
   return JXLB_OK;

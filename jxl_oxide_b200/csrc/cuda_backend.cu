@@ -51,14 +51,16 @@ CudaBackend::CudaBackend(int device) : device_(device) {
   if (!std::getenv("JXLB_NO_CARVEOUT")) CUDA_CHECK(cudaDeviceSetCacheConfig(cudaFuncCachePreferShared));
   if (const char* lanes = std::getenv("JXLB_HF_LANES")) {
     const int n = std::atoi(lanes);
-    hf_streams_per_cta = n <= 0 ? 0 : (n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128))));
+    hf_streams_per_cta = n <= 0 ? 0 : (n <= 4 ? 4 : (n <= 8 ? 8 : (n <= 16 ? 16 : (n <= 32 ? 32 : (n <= 64 ? 64 : 128)))));
   }
 }
 
 CudaBackend::~CudaBackend() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
-  for (auto& kv : planes_) cudaFree(kv.second.ptr);
+  for (auto& kv : planes_)
+    if (!(arena_base_ && kv.second.ptr >= static_cast<void*>(arena_base_) && kv.second.ptr < static_cast<void*>(arena_base_ + arena_cap_)))
+      cudaFree(kv.second.ptr);
   for (void* p : temps_) cudaFree(p);
   if (d_codestream_) cudaFree(d_codestream_);
   if (d_natural_orders_) cudaFree(d_natural_orders_);
@@ -69,14 +71,49 @@ CudaBackend::~CudaBackend() {
   if (pool_ && !std::getenv("JXLB_SHARED_POOL")) cudaMemPoolDestroy(pool_);
 }
 
+void CudaBackend::begin_heavy_stage(size_t bytes_hint) {
+  if (heavy_announced_) return;
+  heavy_announced_ = true;
+  if (on_heavy_stage) on_heavy_stage(bytes_hint);
+}
+
+void CudaBackend::end_arena() {
+  if (!arena_base_) return;
+  auto inside = [&](const void* p) { return p >= static_cast<void*>(arena_base_) && p < static_cast<void*>(arena_base_ + arena_cap_); };
+  std::vector<void*> keep;
+  for (void* p : temps_)
+    if (!inside(p)) keep.push_back(p);
+  temps_.swap(keep);
+  if (d_dequant_ && inside(d_dequant_)) {
+    d_dequant_ = nullptr;
+    cached_hfg_ = nullptr;
+  }
+  for (auto it = planes_.begin(); it != planes_.end();)  // planes a failed decode left behind
+    it = inside(it->second.ptr) ? planes_.erase(it) : std::next(it);
+  arena_base_ = nullptr;
+  arena_cap_ = arena_off_ = 0;
+}
+
 void* CudaBackend::dmalloc(size_t bytes) {
   void* p = nullptr;
+  if (arena_base_ && bytes >= (256u << 10)) {  // big planes: carved from the frame slab, released with it
+    const size_t need = (bytes + 511) & ~size_t(511);
+    if (arena_off_ + need <= arena_cap_) {
+      p = arena_base_ + arena_off_;
+      arena_off_ += need;
+      arena_peak_ = std::max(arena_peak_, arena_off_);
+      return p;
+    }
+    arena_spill_ += need;
+  }
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), pool_, stream_));
   return p;
 }
 void CudaBackend::dfree(void* p) {
-  if (p) CUDA_CHECK(cudaFreeAsync(p, stream_));
+  if (!p) return;
+  if (arena_base_ && p >= arena_base_ && p < arena_base_ + arena_cap_) return;  // the slab is reset as a whole
+  CUDA_CHECK(cudaFreeAsync(p, stream_));
 }
 void* CudaBackend::upload_temp(const void* src, size_t bytes) {
   void* p = dmalloc(bytes);
@@ -193,6 +230,7 @@ void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
 }
 
 void CudaBackend::new_frame() {
+  heavy_announced_ = false;
   cached_hfg_ = nullptr;
   if (d_dequant_) {
     dfree(d_dequant_);
@@ -279,13 +317,13 @@ void CudaBackend::copy_rect(const View& src, const View& dst) {
 }
 
 void CudaBackend::phase_mark(const char* name) {
-  if (!profile) return;
+  if (!profile && !host_phases) return;
   const double now = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   if (name && phase_t0_ >= 0.0) {
     auto& acc = profile_acc[std::string("host:") + name];
     acc.first += 1;
     acc.second += now - phase_t0_;
-    timeline.push_back({std::string("host:") + name, phase_t0_ - time_origin().host_ms, now - time_origin().host_ms});
+    if (profile) timeline.push_back({std::string("host:") + name, phase_t0_ - time_origin().host_ms, now - time_origin().host_ms});
   }
   phase_t0_ = now;
 }
@@ -522,6 +560,7 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   std::vector<DevChannel> dchans;
   std::vector<DevChannelPlan> dplans;
   size_t max_smem = 0;
+  bool all_staged = true;
   for (size_t i = 0; i < jobs.size(); ++i) {
     const ModularStreamJob& j = jobs[i];
     auto it = trees.find(j.tree);
@@ -642,6 +681,7 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
       d.luts = static_cast<const uint16_t*>(upload_temp(luts.data(), luts.size() * 2));
     }
     max_smem = std::max(max_smem, modular_job_smem_bytes(d, max_w));
+    all_staged = all_staged && modular_job_all_staged(d, max_w);
     if (d.use_wp && max_w) {
       d.wp_scratch = static_cast<int32_t*>(dmalloc(size_t(max_w) * 5 * 4));
       temps_.push_back(d.wp_scratch);
@@ -668,7 +708,7 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
     host_launch = host_now_ms();
   }
   begin_k("modular_decode");
-  launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, stream_, d_trace);
+  launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, all_staged, stream_, d_trace);
   end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());
@@ -881,7 +921,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   // finish together; `perm` maps the launch order back to `jobs`.
   std::vector<uint32_t> perm(jobs.size());
   for (size_t i = 0; i < jobs.size(); ++i) perm[i] = uint32_t(i);
-  if (hf_streams_per_cta >= 32)
+  if (hf_streams_per_cta >= 64)
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) {
       return jobs[a].bit_limit - jobs[a].bit_pos > jobs[b].bit_limit - jobs[b].bit_pos;
     });
@@ -893,7 +933,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   temps_.push_back(d_end);
   temps_.push_back(d_status);
   uint32_t* d_blk_ctx = nullptr;
-  if (hf_streams_per_cta >= 32) {
+  if (hf_streams_per_cta >= 64) {
     d_blk_ctx = static_cast<uint32_t*>(dmalloc(size_t(st.bw) * st.bh * 4));
     temps_.push_back(d_blk_ctx);
     begin_k("hf_block_ctx");
@@ -901,12 +941,12 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     end_k();
   }
   begin_k("decode_hf");
-  if (hf_streams_per_cta >= 32)
+  if (hf_streams_per_cta >= 64)
     launch_decode_hf_lanes(active_cs_, dev_frame(st), p, d_blk_ctx, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
                            hf_streams_per_cta, stream_);
   else
     launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
-                     hf_streams_per_cta > 0 ? hf_streams_per_cta : 4, stream_);
+                     hf_streams_per_cta > 0 ? hf_streams_per_cta : 16, stream_);
   end_k();
   std::vector<uint64_t> end(jobs.size());
   std::vector<int> status(jobs.size());
@@ -998,6 +1038,14 @@ void CudaBackend::hf_dequant_cfl(VarDctState& st) {
   p.base_correlation_x = st.lfg->base_correlation_x;
   p.base_correlation_b = st.lfg->base_correlation_b;
   p.colour_factor = float(st.lfg->colour_factor);
+  // Production path: dequantisation + chroma from luma run inside the inverse transforms' load stage (hf_transform), which
+  // saves one HBM round trip of the three coefficient planes. The separate kernel remains for stage snapshots (tests
+  // compare the "hf_dequant" planes) and for chroma-subsampled frames (per-channel grids, no chroma from luma).
+  if (!capture && !st.subsampled && fuse_dequant) {
+    pending_dequant_ = p;
+    have_pending_dequant_ = true;
+    return;
+  }
   begin_k("hf_dequant_cfl");
   launch_hf_dequant_cfl(dev_frame(st), p, stream_);
   end_k();
@@ -1006,8 +1054,9 @@ void CudaBackend::hf_dequant_cfl(VarDctState& st) {
 void CudaBackend::hf_transform(VarDctState& st) {
   void* scratch = dmalloc(hf_transform_scratch_bytes(st.bw, st.bh));
   begin_k("hf_transform");
-  launch_hf_transform(dev_frame(st), scratch, stream_);
+  launch_hf_transform(dev_frame(st), scratch, have_pending_dequant_ ? &pending_dequant_ : nullptr, stream_);
   end_k();
+  have_pending_dequant_ = false;
   dfree(scratch);
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,12 +54,27 @@ class CudaBackend : public Backend {
   void stage_marker(const char* name, const View* views, int n) override;
   void phase_mark(const char* name) override;
 
+  // Heavy stage of a frame (everything that needs full-resolution planes): the planner announces it with the bytes it
+  // is about to allocate; a pipeline (csrc/pipeline.cu) hooks in here to bound the number of frames past this point
+  // and to hand the backend a pre-allocated slab the big planes are carved from (no allocator calls per frame).
+  void begin_heavy_stage(size_t bytes_hint) override;
+  std::function<void(size_t)> on_heavy_stage;  // called once per frame, before the first big allocation
+  void set_arena(void* base, size_t bytes) {
+    arena_base_ = static_cast<uint8_t*>(base);
+    arena_cap_ = bytes;
+    arena_off_ = 0;
+  }
+  // The slab goes back to its owner: nothing of this backend may point into it afterwards.
+  void end_arena();
+  size_t arena_peak() const { return arena_peak_; }
+  size_t arena_spill() const { return arena_spill_; }  // bytes that did not fit the slab (allocated from the pool)
+
   cudaStream_t stream() const { return stream_; }
   // "inputs resident in HBM": upload once, then point the next decode at the device copy
   uint8_t* upload_resident(const uint8_t* data, size_t size);
   void use_resident_once(const uint8_t* dptr) { resident_next_ = dptr; }
   void sync();
-  void* plane_ptr(int id) const { return planes_.at(id).ptr; }
+  void* plane_ptr(int id) const { return id < 0 ? nullptr : planes_.at(id).ptr; }
   // device pointer + stride (elements) of a view's top-left element
   DevView dev_view(const View& v) const;
 
@@ -73,11 +89,13 @@ class CudaBackend : public Backend {
   void pack_to_host(const DevPackParams& p, void* dst, size_t bytes);
   // Same, straight into the caller's device buffer (no host copy): the packed frame stays in HBM for an NCCL gather.
   void pack_to_device(const DevPackParams& p, void* d_dst);
+  bool fuse_dequant = true;  // dequant + chroma from luma inside the inverse transforms (off: separate kernel)
   bool fuse_filters = true;  // single-kernel Gaborish+EPF+colour (off: stage-by-stage, for stage parity tests)
   // HF coefficient streams per CTA: 0 (= 4), 8, 16 = one warp per stream (decode_hf_fast_kernel); 32 / 64 / 128 = one
   // thread per stream (decode_hf_lanes_kernel). Initialised from JXLB_HF_LANES.
   int hf_streams_per_cta = 0;
   bool profile = false;
+  bool host_phases = false;  // wall clock per planner phase only (no CUDA events): where a frame's latency goes under load
   bool trace_device = false;  // modular streams stamp the device clock; host launch/return times are logged
   double phase_t0_ = -1.0;  // wall clock (ms) of the previous phase_mark
   std::map<std::string, std::pair<uint64_t, double>> profile_acc;  // name -> (launches, total ms)
@@ -120,6 +138,9 @@ class CudaBackend : public Backend {
  private:
 
   int device_;
+  uint8_t* arena_base_ = nullptr;
+  size_t arena_cap_ = 0, arena_off_ = 0, arena_peak_ = 0, arena_spill_ = 0;
+  bool heavy_announced_ = false;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t sync_event_ = nullptr;
   cudaMemPool_t pool_ = nullptr;  // this decoder's own stream-ordered pool (no cross-stream reuse dependencies)
@@ -141,6 +162,8 @@ class CudaBackend : public Backend {
   float* d_dequant_default_ = nullptr;  // all-default matrix set, uploaded once per decoder
   DevDequantParams dequant_default_params_;
   DevDequantParams dequant_params_;
+  DevDequantParams pending_dequant_;  // handed from hf_dequant_cfl() to hf_transform() when the two are fused
+  bool have_pending_dequant_ = false;
 };
 
 }  // namespace jxlb

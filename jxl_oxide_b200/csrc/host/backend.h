@@ -121,6 +121,11 @@ class Backend {
   virtual void set_codestream(const uint8_t* data, size_t size) = 0;
   // Called at the start of every frame: table pointers handed over earlier may be stale now.
   virtual void new_frame() {}
+  // Called once per frame right before the planner allocates the frame's full-resolution planes (coefficients,
+  // Modular image channels), with an estimate of the bytes the rest of the frame needs. Everything before it (headers,
+  // LF groups: 1/64 of the samples) is cheap in memory but long in latency; a backend may hold a frame here until a
+  // heavy-stage slot is free.
+  virtual void begin_heavy_stage(size_t /*bytes_hint*/) {}
   // planes
   virtual int alloc_plane(uint32_t w, uint32_t h, bool zero) = 0;
   virtual void free_plane(int id) = 0;

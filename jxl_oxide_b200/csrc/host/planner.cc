@@ -228,7 +228,12 @@ class FramePlanner {
   // A frame that fails half way (malformed or unsupported stream) must not keep its planes: they are
   // cleared from the list once exported or freed at the end of decode_frame().
   ~FramePlanner() {
-    for (int id : frame_planes_) be_.free_plane(id);
+    for (int id : frame_planes_) {
+      try {
+        be_.free_plane(id);
+      } catch (...) {  // already unwinding: nothing more to do for this plane
+      }
+    }
   }
 
  private:
@@ -524,6 +529,8 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     pos = r.pos();
   }
   if (lfg_.has_gmodular) {
+    // a Modular image allocates its full-size channels up front (coded channels, then one plane per inverse transform)
+    if (!vardct) be_.begin_heavy_stage(size_t(cw) * chh * 4 * 2 * (lfg_.gmodular.channels.size() + 2) + (size_t(64) << 20));
     setup_gmodular();
     std::vector<ModularStreamJob> jobs(1);
     ModularStreamJob& job = jobs[0];
@@ -568,8 +575,7 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
     for (int c = 0; c < 3; ++c) {
       st_.lf_quant[c] = new_plane(st_.bw, st_.bh);
       st_.lf[c] = new_plane(st_.bw, st_.bh);
-      st_.coeff[c] = new_plane(st_.bw * 8, st_.bh * 8, /*zero=*/true);
-    }
+    }  // the coefficient planes are allocated when the pass groups are reached (begin_heavy_stage)
     st_.x_from_y = new_plane((cw + 63) / 64, (chh + 63) / 64);
     st_.b_from_y = new_plane((cw + 63) / 64, (chh + 63) / 64);
     st_.sharpness = new_plane(st_.bw, st_.bh);
@@ -693,6 +699,13 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   }
 
   be_.phase_mark("hf_global");
+  if (vardct) {
+    // Everything so far worked on 1/64 of the samples; from here on the frame needs its full-resolution planes
+    // (3 coefficient planes that become the pixels in place + 3 planes of filter output).
+    be_.begin_heavy_stage(size_t(st_.bw) * st_.bh * 64 * 4 * 6 + (size_t(64) << 20));
+    be_.phase_mark("heavy_wait");
+    for (int c = 0; c < 3; ++c) st_.coeff[c] = new_plane(st_.bw * 8, st_.bh * 8, /*zero=*/true);
+  }
   // ---- PassGroups ----
   for (uint32_t p = 0; p < num_passes; ++p) {
     std::vector<size_t> gpos(num_groups), glimit(num_groups);

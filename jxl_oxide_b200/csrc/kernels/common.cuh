@@ -77,6 +77,48 @@ struct DevBitReader {
   }
 };
 
+// Same reader with a 32-bit word index instead of 64-bit pointers: a refill costs one 32-bit compare and one
+// IMAD.WIDE address instead of 64-bit pointer arithmetic and compares (the stream kernels execute one refill per ~2-4
+// symbols on a single lane, so every instruction of it is on the serial path).
+struct WordBitReader {
+  const uint32_t* base;
+  uint32_t widx, stop_idx;
+  uint64_t buf;
+  uint32_t ahead;
+  int nbits;
+  __device__ __forceinline__ void init(const uint8_t* d, uint64_t bit_pos, uint64_t bit_limit = ~uint64_t(0)) {
+    base = reinterpret_cast<const uint32_t*>(d);
+    const uint32_t w = uint32_t(bit_pos >> 5), skip = uint32_t(bit_pos & 31);
+    stop_idx = bit_limit == ~uint64_t(0) ? 0xffffffffu : uint32_t((bit_limit + 31) >> 5) + 2;
+    buf = uint64_t(__ldg(base + w)) >> skip;
+    nbits = 32 - int(skip);
+    buf |= uint64_t(__ldg(base + w + 1)) << nbits;
+    nbits += 32;
+    ahead = __ldg(base + w + 2);
+    widx = w + 3;
+  }
+  __device__ __forceinline__ void refill() {  // requires nbits <= 32; afterwards nbits > 32
+    buf |= uint64_t(ahead) << nbits;
+    nbits += 32;
+    ahead = widx <= stop_idx ? __ldg(base + widx) : 0u;
+    ++widx;
+  }
+  __device__ __forceinline__ uint32_t peek(uint32_t n) {  // n <= 32
+    if (nbits < 32) refill();
+    return uint32_t(buf) & (n >= 32 ? 0xffffffffu : ((1u << n) - 1));
+  }
+  __device__ __forceinline__ void consume(uint32_t n) {
+    buf >>= n;
+    nbits -= int(n);
+  }
+  __device__ __forceinline__ uint64_t pos() const { return uint64_t(widx - 1) * 32 - uint64_t(nbits); }
+  __device__ __forceinline__ uint32_t read(uint32_t n) {
+    uint32_t v = peek(n);
+    consume(n);
+    return v;
+  }
+};
+
 __device__ __constant__ const int8_t kDevSpecialDistances[120][2] = {
     {0, 1},  {1, 0},  {1, 1},  {-1, 1}, {0, 2},  {2, 0},  {1, 2},  {-1, 2}, {2, 1},  {-2, 1},
     {2, 2},  {-2, 2}, {0, 3},  {3, 0},  {1, 3},  {-1, 3}, {3, 1},  {-3, 1}, {2, 3},  {-2, 3},

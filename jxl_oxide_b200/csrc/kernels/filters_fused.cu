@@ -6,6 +6,14 @@
 // between two shared buffers and writes the final pixels: 12 B/px read (+halo, served by L2) and
 // 12 B/px written.
 //
+// EPF in two half-stages per step. The reference computes, per pixel p and neighbour k, the patch distance
+//   dist_k(p) = sum_c scale_c * sum_{o in plus} |a_c[p+k+o] - a_c[p+o]|        (epf.rs:3-210)
+// i.e. 12 x 15 (step 0) / 4 x 15 (step 1) / 4 x 3 (step 2) absolute differences. But |x - y| == |y - x| bit for bit, and
+// the sums run over the same o and c in the same order, so dist_{-d}(p) == dist_d(p - d) EXACTLY: opposite neighbours
+// share one distance map. Half-stage 1 evaluates the 6 / 2 / 2 maps of the "positive" directions once per pixel into
+// shared memory; half-stage 2 reads two values per direction pair and forms weights and weighted sums in the
+// reference's neighbour order. Same values, same rounding, half the arithmetic and a third of the shared-memory reads.
+//
 // Per-pixel arithmetic and its order are those of the stand-alone kernels in filters.cu, i.e. the
 // reference's generic path (crates/jxl-render/src/filter/impls/generic/{gabor.rs,epf.rs},
 // crates/jxl-color/src/xyb.rs). Border semantics: Gaborish uses its own edge formulas on the image
@@ -13,6 +21,10 @@
 // of the halo that lies outside the image is filled by mirroring, so the stencils index plainly.
 #include "kernels.h"
 
+#include <cuda.h>  // CUtensorMap (types only: the encoder entry point is fetched from the driver at run time)
+
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 namespace jxlb {
@@ -82,16 +94,65 @@ __device__ __forceinline__ float gab_px(const float* a, int x, int y, int width,
   return fmul(fadd(fadd(at(0, 0), fmul(sum_side, w0)), fmul(sum_diag, w1)), gw);
 }
 
-__device__ __constant__ const int8_t kFK1[4][2] = {{0, -1}, {0, 1}, {-1, 0}, {1, 0}};
-__device__ __constant__ const int8_t kFK2[12][2] = {{0, -2}, {-1, -1}, {0, -1}, {1, -1}, {-2, 0}, {-1, 0},
-                                                    {1, 0},  {2, 0},   {-1, 1}, {0, 1},  {1, 1},  {0, 2}};
-__device__ __constant__ const int8_t kFD0[5][2] = {{0, -1}, {1, 0}, {0, 0}, {-1, 0}, {0, 1}};
-__device__ __constant__ const int8_t kFD1[5][2] = {{0, -1}, {0, 0}, {0, 1}, {-1, 0}, {1, 0}};
+// Neighbour offsets in the reference's order (epf.rs): 4 for steps 1 / 2, 12 for step 0. constexpr functions, so that every
+// offset below folds into an immediate address.
+__device__ __forceinline__ constexpr int fk_x(int step, int k) {
+  constexpr int k1[4] = {0, 0, -1, 1};
+  constexpr int k2[12] = {0, -1, 0, 1, -2, -1, 1, 2, -1, 0, 1, 0};
+  return step == 0 ? k2[k] : k1[k];
+}
+__device__ __forceinline__ constexpr int fk_y(int step, int k) {
+  constexpr int k1[4] = {-1, 1, 0, 0};
+  constexpr int k2[12] = {-2, -1, -1, -1, 0, 0, 0, 0, 1, 1, 1, 2};
+  return step == 0 ? k2[k] : k1[k];
+}
 
-// One EPF step at one pixel (impls/generic/epf.rs:3-210); `a` points at the pixel in channel 0 of
-// the input buffer (channels kPlane apart), halo already mirrored.
+// "Positive" directions of each step; the other half of the neighbour list is their negation.
+//   step 0: (0,2) (1,1) (0,1) (-1,1) (2,0) (1,0)        steps 1, 2: (0,1) (1,0)
+__device__ __forceinline__ constexpr int dplus_x(int step, int m) {
+  return step == 0 ? (m == 0 ? 0 : m == 1 ? 1 : m == 2 ? 0 : m == 3 ? -1 : m == 4 ? 2 : 1) : (m == 0 ? 0 : 1);
+}
+__device__ __forceinline__ constexpr int dplus_y(int step, int m) {
+  return step == 0 ? (m == 0 ? 2 : m == 1 ? 1 : m == 2 ? 1 : m == 3 ? 1 : 0) : (m == 0 ? 1 : 0);
+}
+// offsets of the 5-sample plus in the reference's summation order (epf.rs: step 0 and step 1 differ), step 2: centre only
+__device__ __forceinline__ constexpr int plus_x(int step, int i) {
+  return step == 2 ? 0 : step == 0 ? (i == 1 ? 1 : i == 3 ? -1 : 0) : (i == 3 ? -1 : i == 4 ? 1 : 0);
+}
+__device__ __forceinline__ constexpr int plus_y(int step, int i) {
+  return step == 2 ? 0 : step == 0 ? (i == 0 ? -1 : i == 4 ? 1 : 0) : (i == 0 ? -1 : i == 2 ? 1 : 0);
+}
+
+// Half-stage 1: the distance maps of one EPF step at cell q. `a` points at q in channel 0 of the input buffer, `d` at q in
+// map 0 (maps kPlane apart). dist_d(q) = sum_c scale_c * sum_o |a_c[q+d+o] - a_c[q+o]|, accumulated exactly like
+// epf.rs (acc starts at 0.0, so the first addition is exact; likewise dist).
 template <int STEP>
-__device__ __forceinline__ void epf_px(const float* a, int x, int y, float sigma_val, const DevEpfParams& p, float o[3]) {
+__device__ __forceinline__ void epf_dist(const float* a, float* d, const DevEpfParams& p) {
+  constexpr int NM = STEP == 0 ? 6 : 2;
+  constexpr int ND = STEP == 2 ? 1 : 5;
+#pragma unroll
+  for (int m = 0; m < NM; ++m) {
+    const int dx = dplus_x(STEP, m), dy = dplus_y(STEP, m);
+    float dist = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < ND; ++i) {
+        const int ox = plus_x(STEP, i), oy = plus_y(STEP, i);
+        acc = fadd(acc, fabsf(fsub(a[c * kPlane + (dy + oy) * kS + dx + ox], a[c * kPlane + oy * kS + ox])));
+      }
+      dist = fadd(dist, fmul(p.channel_scale[c], acc));
+    }
+    d[m * kPlane] = dist;
+  }
+}
+
+// Half-stage 2: weights and weighted sums at pixel p in the reference's neighbour order; `a` points at p in channel 0 of
+// the input buffer, `d` at p in distance map 0.
+template <int STEP>
+__device__ __forceinline__ void epf_apply(const float* a, const float* d, int x, int y, float sigma_val, const DevEpfParams& p,
+                                          float o[3]) {
   if (sigma_val < 0.3f) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) o[c] = a[c * kPlane];
@@ -108,22 +169,17 @@ __device__ __forceinline__ void epf_px(const float* a, int x, int y, float sigma
 #pragma unroll
   for (int c = 0; c < 3; ++c) sum_channels[c] = a[c * kPlane];
   constexpr int NK = STEP == 0 ? 12 : 4;
-  constexpr int ND = STEP == 2 ? 1 : 5;
+  constexpr int NM = STEP == 0 ? 6 : 2;
 #pragma unroll
   for (int k = 0; k < NK; ++k) {
-    const int kx = STEP == 0 ? kFK2[k][0] : kFK1[k][0];
-    const int ky = STEP == 0 ? kFK2[k][1] : kFK1[k][1];
+    const int kx = fk_x(STEP, k), ky = fk_y(STEP, k);
+    // which map holds this neighbour's distance, and at which cell
     float dist = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float acc = 0.0f;
-#pragma unroll
-      for (int i = 0; i < ND; ++i) {
-        const int ox = STEP == 2 ? 0 : (STEP == 0 ? kFD0[i][0] : kFD1[i][0]);
-        const int oy = STEP == 2 ? 0 : (STEP == 0 ? kFD0[i][1] : kFD1[i][1]);
-        acc = fadd(acc, fabsf(fsub(a[c * kPlane + (ky + oy) * kS + kx + ox], a[c * kPlane + oy * kS + ox])));
-      }
-      dist = fadd(dist, fmul(p.channel_scale[c], acc));
+    for (int m = 0; m < NM; ++m) {
+      const int dx = dplus_x(STEP, m), dy = dplus_y(STEP, m);
+      if (dx == kx && dy == ky) dist = d[m * kPlane];                      // positive direction: dist_d(p)
+      if (dx == -kx && dy == -ky) dist = d[m * kPlane + ky * kS + kx];     // its negation: dist_d(p - d) = dist_d(p + k)
     }
     const float weight = fmaxf(fadd(1.0f, fmul(dist, neg_inv_sigma)), 0.0f);
     sum_weights = fadd(sum_weights, weight);
@@ -212,7 +268,15 @@ struct FusedViews {
   float* out[3];
   uint32_t in_stride[3], out_stride[3];
   int width, height;
+  int use_tma;  // the three input planes are described by `maps` (row pitch a multiple of 16 bytes)
 };
+
+// TMA descriptors of the three input planes (2-D, f32, box kS x kS, out-of-bounds cells read as zero).
+struct FusedMaps {
+  CUtensorMap map[3];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 // Cells of `need` that lie outside the image take the value of their mirrored in-image cell.
 __device__ __forceinline__ void mirror_fill(float* buf, Rect need, int gx0, int gy0, int width, int height) {
@@ -229,10 +293,14 @@ __device__ __forceinline__ void mirror_fill(float* buf, Rect need, int gx0, int 
     }
 }
 
-__global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFusedFilterParams p) {
-  extern __shared__ float s_buf[];
+// NMAPS: distance maps kept in shared memory (6 when the frame runs EPF step 0, else 2; 0 without EPF).
+template <int NMAPS>
+__global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFusedFilterParams p, const __grid_constant__ FusedMaps maps) {
+  extern __shared__ __align__(128) float s_buf[];
+  __shared__ __align__(8) unsigned long long s_mbar;
   float* cur = s_buf;               // [3][kS][kS]
   float* alt = s_buf + 3 * kPlane;
+  float* dmap = s_buf + 6 * kPlane;  // [NMAPS][kS][kS]
   const int width = v.width, height = v.height;
   // shared cell (lx, ly) <-> image pixel (gx0 + lx, gy0 + ly)
   const int gx0 = int(blockIdx.x) * kT - kHM, gy0 = int(blockIdx.y) * kT - kHM;
@@ -247,7 +315,33 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
     return r;
   };
 
-  {  // load the input region
+  if (v.use_tma) {
+    // Tile + halo by TMA: one elected thread arms an mbarrier with the byte count and issues three bulk tensor copies
+    // (the whole kS x kS window of each plane; cells outside the image arrive as zeros and are never read before
+    // mirror_fill overwrites them), everybody waits on the barrier's phase. No per-thread address arithmetic, no
+    // register staging, and the copies of the three planes are in flight together.
+    const uint32_t mbar = smem_u32(&s_mbar);
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(uint32_t(3 * kPlane * sizeof(float))) : "memory");
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                smem_u32(cur + c * kPlane)),
+            "l"(reinterpret_cast<uint64_t>(&maps.map[c])), "r"(gx0), "r"(gy0), "r"(mbar)
+            : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anybody polls it
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done && spin < (1u << 24); ++spin)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(mbar), "r"(0u)
+          : "memory");
+  } else {  // load the input region (planes whose pitch TMA cannot address)
     const Rect r = clip(rect(halo));
     for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
       for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
@@ -282,31 +376,43 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
 
   auto epf_stage = [&](auto step_tag, int radius, bool last) {
     constexpr int STEP = decltype(step_tag)::value;
-    halo -= radius;
-    const Rect r = clip(rect(halo));
-    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
-      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
-        const int x = gx0 + lx, y = gy0 + ly;
-        const float sigma_val = p.sigma ? __ldg(p.sigma + size_t(y >> 3) * p.sigma_stride + (x >> 3)) : p.epf.sigma_for_modular;
-        float o[3];
-        epf_px<STEP>(cur + ly * kS + lx, x, y, sigma_val, p.epf, o);
-        if (last) {
-          if (p.colour) xyb_px(o, p.col);
-#pragma unroll
-          for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
-        } else {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) alt[c * kPlane + ly * kS + lx] = o[c];
-        }
+    if constexpr (NMAPS >= (STEP == 0 ? 6 : 2)) {
+      halo -= radius;
+      const Rect out = rect(halo);
+      {  // half-stage 1: distance maps wherever a pixel of `out` or its negative-direction neighbour looks them up
+         // (cells beyond the image included: they stand for mirrored pixels)
+        constexpr int ex = STEP == 0 ? 2 : 1;  // reach of the negated directions: x - 2 .. x + 1 (step 0), x - 1 .. x
+        const Rect q{out.x0 - ex, out.y0 - ex, out.x1 + (STEP == 0 ? 1 : 0), out.y1};
+        for (int ly = q.y0 + int(threadIdx.y); ly < q.y1; ly += int(blockDim.y))
+          for (int lx = q.x0 + int(threadIdx.x); lx < q.x1; lx += int(blockDim.x))
+            epf_dist<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, p.epf);
       }
-    if (!last) {
-      float* t = cur;
-      cur = alt;
-      alt = t;
       __syncthreads();
-      if (border_tile) {
-        mirror_fill(cur, rect(halo), gx0, gy0, width, height);
+      const Rect r = clip(out);
+      for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
+        for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
+          const int x = gx0 + lx, y = gy0 + ly;
+          const float sigma_val = p.sigma ? __ldg(p.sigma + size_t(y >> 3) * p.sigma_stride + (x >> 3)) : p.epf.sigma_for_modular;
+          float o[3];
+          epf_apply<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, x, y, sigma_val, p.epf, o);
+          if (last) {
+            if (p.colour) xyb_px(o, p.col);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) alt[c * kPlane + ly * kS + lx] = o[c];
+          }
+        }
+      if (!last) {
+        float* t = cur;
+        cur = alt;
+        alt = t;
         __syncthreads();
+        if (border_tile) {
+          mirror_fill(cur, rect(halo), gx0, gy0, width, height);
+          __syncthreads();
+        }
       }
     }
   };
@@ -333,6 +439,22 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
 
 bool fused_filters_supported(uint32_t width, uint32_t height) { return width >= 16 && height >= 16; }
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+}  // namespace
+
 void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFilterParams p, cudaStream_t stream) {
   FusedViews v;
   for (int c = 0; c < 3; ++c) {
@@ -344,15 +466,37 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
   v.width = int(in[0].w);
   v.height = int(in[0].h);
   if (!v.width || !v.height) return;
-  constexpr size_t smem = size_t(2) * 3 * kPlane * sizeof(float);
+  FusedMaps maps;
+  std::memset(&maps, 0, sizeof(maps));
+  v.use_tma = 0;
+  static const bool no_tma = std::getenv("JXLB_NO_TMA") != nullptr;
+  if (EncodeTiledFn enc = no_tma ? nullptr : tensor_map_encoder()) {
+    bool ok = true;
+    for (int c = 0; c < 3 && ok; ++c) {
+      ok = (reinterpret_cast<uintptr_t>(v.in[c]) & 15) == 0 && (size_t(v.in_stride[c]) * 4) % 16 == 0;
+      if (!ok) break;
+      const cuuint64_t dims[2] = {cuuint64_t(v.width), cuuint64_t(v.height)};
+      const cuuint64_t strides[1] = {cuuint64_t(v.in_stride[c]) * 4};
+      const cuuint32_t box[2] = {cuuint32_t(kS), cuuint32_t(kS)};
+      const cuuint32_t estr[2] = {1, 1};
+      ok = enc(&maps.map[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(v.in[c]), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    v.use_tma = ok ? 1 : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(fused_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaFuncSetAttribute(fused_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(6 * kPlane * sizeof(float)));
+    cudaFuncSetAttribute(fused_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(8 * kPlane * sizeof(float)));
+    cudaFuncSetAttribute(fused_filter_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(12 * kPlane * sizeof(float)));
     attr_set = true;
   }
   dim3 block(32, 8);
   dim3 grid((v.width + kT - 1) / kT, (v.height + kT - 1) / kT);
-  fused_filter_kernel<<<grid, block, smem, stream>>>(v, p);
+  if (p.epf_iters == 3) fused_filter_kernel<6><<<grid, block, 12 * kPlane * sizeof(float), stream>>>(v, p, maps);
+  else if (p.epf_iters > 0) fused_filter_kernel<2><<<grid, block, 8 * kPlane * sizeof(float), stream>>>(v, p, maps);
+  else fused_filter_kernel<0><<<grid, block, 6 * kPlane * sizeof(float), stream>>>(v, p, maps);
 }
 
 }  // namespace jxlb

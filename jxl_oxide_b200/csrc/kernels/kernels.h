@@ -52,7 +52,9 @@ struct DevView {
 // Modular ------------------------------------------------------------------------------------
 void launch_modular_decode(const uint8_t* codestream, const DevModularJob* jobs, const DevChannel* channels,
                            const DevChannelPlan* plans, uint64_t* end_bits, int* status, int num_jobs,
-                           size_t smem_bytes, cudaStream_t stream, unsigned long long* trace = nullptr);
+                           size_t smem_bytes, bool all_tables_staged, cudaStream_t stream,
+                           unsigned long long* trace = nullptr);
+bool modular_job_all_staged(const DevModularJob& job, uint32_t max_width);
 // tracing aid: writes the device's %globaltimer (ns)
 void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream);
 // bytes of dynamic shared memory a job wants for its tree / entropy tables / WP rows / LUTs
@@ -157,7 +159,7 @@ void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream);
 // chroma upsampling of JPEG-transcoded frames (jxl-render/src/filter/ycbcr.rs:6-78); `in` is the subsampled part
 void launch_upsample_jpeg(DevView in, DevView out, int horizontal, int vertical, cudaStream_t stream);
 // `scratch`: hf_transform_scratch_bytes() of device memory for the per-size-class work lists
-void launch_hf_transform(DevFrame f, void* scratch, cudaStream_t stream);
+void launch_hf_transform(DevFrame f, void* scratch, const DevDequantParams* fused_dequant, cudaStream_t stream);
 size_t hf_transform_scratch_bytes(uint32_t bw, uint32_t bh);
 
 // Filters / colour ----------------------------------------------------------------------------

@@ -46,12 +46,12 @@ __host__ __device__ inline SmemLayout modular_layout(uint32_t num_nodes, const D
   };
   L.div = take(65 * 4);
   uint32_t tree_bytes = num_nodes * 16;
-  L.tree = (tree_bytes && tree_bytes <= kSmemTreeBytes) ? take(tree_bytes) : 0xffffffffu;
+  L.tree = tree_bytes <= kSmemTreeBytes ? take(tree_bytes) : 0xffffffffu;
   L.configs = take(code.num_clusters * 4);
   if (code.use_prefix) {
     L.ans = 0xffffffffu;
     uint32_t pb = code.prefix_table_size * 4;
-    L.prefix = (pb && pb <= kSmemPrefixBytes) ? take(pb) : 0xffffffffu;
+    L.prefix = pb <= kSmemPrefixBytes ? take(pb) : 0xffffffffu;
     L.prefix_meta = take(code.num_clusters * 8);
   } else {
     uint32_t ab = (code.num_clusters << code.log_alphabet_size) * 8;
@@ -60,7 +60,7 @@ __host__ __device__ inline SmemLayout modular_layout(uint32_t num_nodes, const D
     L.prefix_meta = 0xffffffffu;
   }
   uint32_t lb = lut_total * 2;
-  L.luts = (lb && lb <= kSmemLutBytes) ? take(lb) : 0xffffffffu;
+  L.luts = lb <= kSmemLutBytes ? take(lb + 4) : 0xffffffffu;
   L.wp = (use_wp && max_w <= kSmemWpMaxWidth) ? take(max_w * 5 * 4) : 0xffffffffu;
   L.total = off;
   return L;
@@ -247,7 +247,7 @@ struct FastWp {
 constexpr int kMaxPrev = 16;
 
 struct StreamState {
-  DevBitReader br;
+  WordBitReader br;
   uint32_t ans_state;
   uint32_t* window;  // LZ77 state (lib.rs:346-352)
   uint32_t lz_to_copy, lz_copy_pos, lz_decoded;
@@ -498,6 +498,10 @@ __device__ __forceinline__ void decode_channel(const DevModularJob& job, const D
   }
 }
 
+// ALLSM: every table of every job of the launch fits its shared-memory budget (what libjxl's LF / HfMetadata streams
+// need: a few KB). All table pointers then derive from the shared array unconditionally, so the compiler emits LDS with
+// 32-bit addresses instead of generic loads for the tree nodes, alias buckets, leaf LUT and predictor rows.
+template <bool ALLSM>
 __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __restrict__ cs,
                                                             const DevModularJob* __restrict__ jobs,
                                                             const DevChannel* __restrict__ channels,
@@ -520,7 +524,7 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
   uint32_t* s_div = reinterpret_cast<uint32_t*>(smem + L.div);
   for (uint32_t i = lane; i < 65; i += 32) s_div[i] = i ? (1u << 24) / i : 0;
   const MaNode* tree = job.tree;
-  if (L.tree != 0xffffffffu) {
+  if (ALLSM || L.tree != 0xffffffffu) {
     warp_copy_words(reinterpret_cast<uint32_t*>(smem + L.tree), reinterpret_cast<const uint32_t*>(job.tree),
                     job.num_tree_nodes * 4, lane);
     tree = reinterpret_cast<const MaNode*>(smem + L.tree);
@@ -536,22 +540,27 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
   if (code.use_prefix) {
     warp_copy_words(reinterpret_cast<uint32_t*>(smem + L.prefix_meta), code.prefix_meta, code.num_clusters * 2, lane);
     cv.prefix_meta = reinterpret_cast<const uint32_t*>(smem + L.prefix_meta);
-    if (L.prefix != 0xffffffffu) {
+    if (ALLSM || L.prefix != 0xffffffffu) {
       warp_copy_words(reinterpret_cast<uint32_t*>(smem + L.prefix), code.prefix, code.prefix_table_size, lane);
       cv.prefix = reinterpret_cast<const uint32_t*>(smem + L.prefix);
     }
-  } else if (L.ans != 0xffffffffu) {
+  } else if (ALLSM || L.ans != 0xffffffffu) {
     warp_copy_words(reinterpret_cast<uint32_t*>(smem + L.ans), reinterpret_cast<const uint32_t*>(code.ans),
                     (code.num_clusters << code.log_alphabet_size) * 2, lane);
     cv.ans = reinterpret_cast<const uint64_t*>(smem + L.ans);
   }
+  if (ALLSM) {  // unconditionally shared pointers (the unused ones are never dereferenced)
+    cv.ans = reinterpret_cast<const uint64_t*>(smem + (L.ans & 0xffffffu));
+    cv.prefix = reinterpret_cast<const uint32_t*>(smem + (L.prefix & 0xffffffu));
+    cv.prefix_meta = reinterpret_cast<const uint32_t*>(smem + (L.prefix_meta & 0xffffffu));
+  }
   const uint16_t* luts = job.luts;
-  if (L.luts != 0xffffffffu) {
+  if (ALLSM || L.luts != 0xffffffffu) {
     warp_copy_words(reinterpret_cast<uint32_t*>(smem + L.luts), reinterpret_cast<const uint32_t*>(job.luts),
                     (job.lut_total + 1) / 2, lane);
     luts = reinterpret_cast<const uint16_t*>(smem + L.luts);
   }
-  int32_t* wp_rows = (L.wp != 0xffffffffu) ? reinterpret_cast<int32_t*>(smem + L.wp) : job.wp_scratch;
+  int32_t* wp_rows = (ALLSM || L.wp != 0xffffffffu) ? reinterpret_cast<int32_t*>(smem + L.wp) : job.wp_scratch;
   __syncwarp();
   if (lane != 0) return;
   if (trace) {  // tracing aid: device clock (ns) when this stream starts / ends decoding
@@ -695,14 +704,27 @@ size_t modular_job_smem_bytes(const DevModularJob& job, uint32_t max_width) {
 
 void launch_modular_decode(const uint8_t* cs, const DevModularJob* jobs, const DevChannel* channels,
                            const DevChannelPlan* plans, uint64_t* end_bits, int* status, int num_jobs, size_t smem_bytes,
-                           cudaStream_t stream, unsigned long long* trace) {
+                           bool all_tables_staged, cudaStream_t stream, unsigned long long* trace) {
   if (num_jobs <= 0) return;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(modular_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(modular_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(modular_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
-  modular_stream_kernel<<<num_jobs, 32, smem_bytes, stream>>>(cs, jobs, channels, plans, end_bits, status, num_jobs, trace);
+  if (all_tables_staged)
+    modular_stream_kernel<true><<<num_jobs, 32, smem_bytes, stream>>>(cs, jobs, channels, plans, end_bits, status, num_jobs, trace);
+  else
+    modular_stream_kernel<false><<<num_jobs, 32, smem_bytes, stream>>>(cs, jobs, channels, plans, end_bits, status, num_jobs, trace);
+}
+
+// Whether modular_stream_kernel stages every table of this job (tree, entropy tables, leaf LUTs, predictor rows).
+bool modular_job_all_staged(const DevModularJob& job, uint32_t max_width) {
+  const SmemLayout L = modular_layout(job.num_tree_nodes, job.code, job.lut_total, job.use_wp, max_width);
+  if (L.tree == 0xffffffffu || L.luts == 0xffffffffu) return false;
+  if (job.code.use_prefix ? L.prefix == 0xffffffffu : L.ans == 0xffffffffu) return false;
+  if (job.use_wp && L.wp == 0xffffffffu) return false;
+  return !job.code.lz77_enabled;
 }
 
 void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream) { read_globaltimer_kernel<<<1, 1, 0, stream>>>(out); }

@@ -32,7 +32,8 @@ struct CodeView {
 };
 
 // ANS symbol (ans.rs:276-330): alias-table lookup, state update, 16-bit refill.
-__device__ __forceinline__ uint32_t cv_read_symbol_ans(const CodeView& c, uint32_t& ans_state, DevBitReader& br, uint32_t cluster) {
+template <typename BR>
+__device__ __forceinline__ uint32_t cv_read_symbol_ans(const CodeView& c, uint32_t& ans_state, BR& br, uint32_t cluster) {
   const uint32_t log_bucket = 12 - c.log_alphabet_size;
   uint32_t state = ans_state;
   uint32_t idx = state & 0xfff;
@@ -54,7 +55,8 @@ __device__ __forceinline__ uint32_t cv_read_symbol_ans(const CodeView& c, uint32
   return symbol;
 }
 
-__device__ __forceinline__ uint32_t cv_read_symbol(const CodeView& c, uint32_t& ans_state, DevBitReader& br, uint32_t cluster) {
+template <typename BR>
+__device__ __forceinline__ uint32_t cv_read_symbol(const CodeView& c, uint32_t& ans_state, BR& br, uint32_t cluster) {
   if (c.use_prefix) {  // prefix.rs:335-357
     uint32_t off = c.prefix_meta[cluster * 2], root_bits = c.prefix_meta[cluster * 2 + 1];
     uint32_t peeked = br.peek(15);
@@ -69,7 +71,8 @@ __device__ __forceinline__ uint32_t cv_read_symbol(const CodeView& c, uint32_t& 
   return cv_read_symbol_ans(c, ans_state, br, cluster);
 }
 
-__device__ __forceinline__ uint32_t cv_read_uint(DevBitReader& br, uint32_t cfg, uint32_t token) {
+template <typename BR>
+__device__ __forceinline__ uint32_t cv_read_uint(BR& br, uint32_t cfg, uint32_t token) {
   uint32_t split_exponent = cfg & 0xff;
   uint32_t split = 1u << split_exponent;
   if (token < split) return token;

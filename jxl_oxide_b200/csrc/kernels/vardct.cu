@@ -5,6 +5,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <cstring>
 
 namespace jxlb {
 
@@ -781,51 +782,111 @@ __device__ void transform_special_coop(float* g, int type, float* s, int r, uint
   }
 }
 
+// dequant_hf_varblock_grouped + chroma_from_luma_hf_grouped (vardct/mod.rs:442-542, 570-603) folded into the load
+// stage of the inverse transforms: per varblock, the three channels are dequantised together (chroma from luma needs
+// the dequantised Y coefficient at the same position), then transformed. Same operations in the same order as
+// hf_dequant_cfl_kernel, so the result is bit-identical to the two-pass form.
+struct DeqBlock {
+  float mul[3];         // 65536 / (global_scale * hf_mul) * qm_scale[c]
+  const float* mat[3];  // the block's weight matrices (normal or transposed), row stride = block width
+};
+__device__ __forceinline__ DeqBlock deq_block(const DevFrame& f, const DevDequantParams& p, int32_t t, uint32_t bx, uint32_t by) {
+  DeqBlock d;
+  const uint32_t set = kDevTransformInfo[t][2], tr = kDevTransformInfo[t][4];
+  const float hf_mul = float(f.blk_mul[size_t(by) * f.bw + bx]);
+  const float base = __fdiv_rn(65536.0f, __fmul_rn(p.global_scale, hf_mul));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    d.mul[c] = __fmul_rn(base, p.qm_scale[c]);
+    d.mat[c] = p.matrices + p.matrix_offset[(set * 3 + c) * 2 + tr];
+  }
+  return d;
+}
+__device__ __forceinline__ float deq_one(uint32_t raw, float m, float mul, float qb, float qbn) {
+  float q = float(int32_t(raw));
+  if (fabsf(q) <= 1.0f) q = __fmul_rn(q, qb);
+  else q = __fsub_rn(q, __fdiv_rn(qbn, q));
+  q = __fmul_rn(q, m);
+  return __fmul_rn(q, mul);
+}
+// chroma-from-luma factors of the 64x64 tile that holds coefficient position (x, y) (frame coordinates)
+__device__ __forceinline__ void cfl_factors(const DevFrame& f, const DevDequantParams& p, uint32_t x, uint32_t y, float& kx, float& kb) {
+  const size_t ti = size_t(y >> 6) * f.w64 + (x >> 6);
+  kx = __fadd_rn(p.base_correlation_x, __fdiv_rn(float(f.x_from_y[ti]), p.colour_factor));
+  kb = __fadd_rn(p.base_correlation_b, __fdiv_rn(float(f.b_from_y[ti]), p.colour_factor));
+}
+
 constexpr int kSmallGroups = 32;  // 8-thread groups per CTA
-__global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f, const uint32_t* __restrict__ items,
+template <bool DEQ>
+__global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f, DevDequantParams dq,
+                                                                      const uint32_t* __restrict__ items,
                                                                       const uint32_t* __restrict__ count_ptr) {
   __shared__ float s_tile[kSmallGroups][72];      // 8 x 9
   __shared__ float s_special[kSmallGroups][192];  // 8 x 8 copy + 128 scratch
   const uint32_t group = threadIdx.x >> 3, r = threadIdx.x & 7;
   const uint32_t gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
-  const uint32_t total = *count_ptr * 3;
+  // DEQ: one work item per varblock (the three channels together: Y first, its dequantised row feeds the chroma
+  // channels); else one per (varblock, channel)
+  const uint32_t total = DEQ ? *count_ptr : *count_ptr * 3;
   float* tile = s_tile[group];
   for (uint32_t work = blockIdx.x * kSmallGroups + group; work < total; work += gridDim.x * kSmallGroups) {
-    const uint32_t item = items[work / 3], c = work % 3;
+    const uint32_t item = items[DEQ ? work : work / 3];
     const uint32_t sbx = item & 0xffff, sby = item >> 16;
     const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
-    uint32_t bx, by;  // where channel c keeps this block
-    if (!channel_block(f, c, sbx, sby, bx, by)) continue;
-    float* row = reinterpret_cast<float*>(f.coeff[c]) + (size_t(by) * 8 + r) * f.cw + size_t(bx) * 8;
-    const float4 lo = *reinterpret_cast<const float4*>(row), hi = *reinterpret_cast<const float4*>(row + 4);
-    float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-    if (r == 0) v[0] = f.lf[c][size_t(by) * f.bw + bx];
-    if (t == 0) {
-      RegIdct<8>::run(v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tile[r * 9 + i] = v[i];
-      __syncwarp(gmask);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = tile[i * 9 + r];
-      RegIdct<8>::run(v);
-      __syncwarp(gmask);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) tile[i * 9 + r] = v[i];
-      __syncwarp(gmask);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = tile[r * 9 + i];
-    } else {
-      float* g = s_special[group];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[r * 8 + i] = v[i];
-      __syncwarp(gmask);
-      transform_special_coop(g, t, g + 64, int(r), gmask);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = g[r * 8 + i];
+    DeqBlock db;
+    float kx = 0.0f, kb = 0.0f, vy[8];
+    if (DEQ) {
+      db = deq_block(f, dq, t, sbx, sby);
+      cfl_factors(f, dq, sbx * 8, sby * 8, kx, kb);
     }
-    __syncwarp(gmask);
-    *reinterpret_cast<float4*>(row) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(row + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll 1
+    for (int ci = 0; ci < (DEQ ? 3 : 1); ++ci) {
+      const uint32_t c = DEQ ? (ci == 0 ? 1u : (ci == 1 ? 0u : 2u)) : work % 3;
+      uint32_t bx, by;  // where channel c keeps this block
+      if (!channel_block(f, c, sbx, sby, bx, by)) continue;
+      float* row = reinterpret_cast<float*>(f.coeff[c]) + (size_t(by) * 8 + r) * f.cw + size_t(bx) * 8;
+      const float4 lo = *reinterpret_cast<const float4*>(row), hi = *reinterpret_cast<const float4*>(row + 4);
+      float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      if (DEQ) {
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(db.mat[c] + r * 8));
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(db.mat[c] + r * 8 + 4));
+        const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        const float k = c == 0 ? kx : kb;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float q = deq_one(__float_as_uint(v[i]), m[i], db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
+          if (c == 1) vy[i] = v[i] = q;
+          else v[i] = __fadd_rn(q, __fmul_rn(k, vy[i]));
+        }
+      }
+      if (r == 0) v[0] = f.lf[c][size_t(by) * f.bw + bx];
+      if (t == 0) {
+        RegIdct<8>::run(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[r * 9 + i] = v[i];
+        __syncwarp(gmask);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tile[i * 9 + r];
+        RegIdct<8>::run(v);
+        __syncwarp(gmask);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[i * 9 + r] = v[i];
+        __syncwarp(gmask);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tile[r * 9 + i];
+      } else {
+        float* g = s_special[group];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[r * 8 + i] = v[i];
+        __syncwarp(gmask);
+        transform_special_coop(g, t, g + 64, int(r), gmask);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = g[r * 8 + i];
+      }
+      __syncwarp(gmask);
+      *reinterpret_cast<float4*>(row) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(row + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
   }
 }
 
@@ -846,41 +907,62 @@ __device__ __forceinline__ void idct_line_dispatch(float* p, int stride, int n) 
 }
 
 constexpr int kMediumWarps = 4;
-__global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame f, const uint32_t* __restrict__ items,
+template <bool DEQ>
+__global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame f, DevDequantParams dq,
+                                                                        const uint32_t* __restrict__ items,
                                                                         const uint32_t* __restrict__ count_ptr) {
   __shared__ float s_tile[kMediumWarps][32 * 33];
+  __shared__ float s_ytile[DEQ ? kMediumWarps : 1][DEQ ? 32 * 33 : 1];  // dequantised Y coefficients (chroma from luma)
   __shared__ float s_llf[kMediumWarps][16 + 12];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t total = *count_ptr * 3;
+  const uint32_t total = DEQ ? *count_ptr : *count_ptr * 3;
   float* tile = s_tile[warp];
+  float* ytile = s_ytile[DEQ ? warp : 0];
   float* llf = s_llf[warp];
   for (uint32_t work = blockIdx.x * kMediumWarps + warp; work < total; work += gridDim.x * kMediumWarps) {
-    const uint32_t item = items[work / 3], c = work % 3;
+    const uint32_t item = items[DEQ ? work : work / 3];
     const uint32_t sbx = item & 0xffff, sby = item >> 16;
     const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
-    uint32_t bx, by;
-    if (!channel_block(f, c, sbx, sby, bx, by)) continue;
     const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
     const int w = bw * 8, h = bh * 8;
-    float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
     const int logw = 31 - __clz(w);
-    for (int idx = int(lane); idx < w * h; idx += 32) {
-      const int x = idx & (w - 1), y = idx >> logw;
-      tile[y * 33 + x] = block[size_t(y) * f.cw + x];
+    DeqBlock db;
+    if (DEQ) db = deq_block(f, dq, t, sbx, sby);
+#pragma unroll 1
+    for (int ci = 0; ci < (DEQ ? 3 : 1); ++ci) {
+      const uint32_t c = DEQ ? (ci == 0 ? 1u : (ci == 1 ? 0u : 2u)) : work % 3;
+      uint32_t bx, by;
+      if (!channel_block(f, c, sbx, sby, bx, by)) continue;
+      float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
+      for (int idx = int(lane); idx < w * h; idx += 32) {
+        const int x = idx & (w - 1), y = idx >> logw;
+        float v = block[size_t(y) * f.cw + x];
+        if (DEQ) {
+          const float q = deq_one(__float_as_uint(v), __ldg(db.mat[c] + y * w + x), db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
+          if (c == 1) {
+            ytile[y * 33 + x] = v = q;
+          } else {
+            float kx, kb;
+            cfl_factors(f, dq, bx * 8 + uint32_t(x), by * 8 + uint32_t(y), kx, kb);
+            v = __fadd_rn(q, __fmul_rn(c == 0 ? kx : kb, ytile[y * 33 + x]));
+          }
+        }
+        tile[y * 33 + x] = v;
+      }
+      if (lane == 0) compute_llf_small(f, int(c), bx, by, bw, bh, llf);  // overlaps the tile loads in flight
+      __syncwarp();
+      if (int(lane) < bw * bh) tile[(int(lane) / bw) * 33 + (int(lane) % bw)] = llf[lane];
+      __syncwarp();
+      if (int(lane) < h) idct_line_dispatch(tile + lane * 33, 1, w);
+      __syncwarp();
+      if (int(lane) < w) idct_line_dispatch(tile + lane, 33, h);
+      __syncwarp();
+      for (int idx = int(lane); idx < w * h; idx += 32) {
+        const int x = idx & (w - 1), y = idx >> logw;
+        block[size_t(y) * f.cw + x] = tile[y * 33 + x];
+      }
+      __syncwarp();
     }
-    if (lane == 0) compute_llf_small(f, int(c), bx, by, bw, bh, llf);  // overlaps the tile loads in flight
-    __syncwarp();
-    if (int(lane) < bw * bh) tile[(int(lane) / bw) * 33 + (int(lane) % bw)] = llf[lane];
-    __syncwarp();
-    if (int(lane) < h) idct_line_dispatch(tile + lane * 33, 1, w);
-    __syncwarp();
-    if (int(lane) < w) idct_line_dispatch(tile + lane, 33, h);
-    __syncwarp();
-    for (int idx = int(lane); idx < w * h; idx += 32) {
-      const int x = idx & (w - 1), y = idx >> logw;
-      block[size_t(y) * f.cw + x] = tile[y * 33 + x];
-    }
-    __syncwarp();
   }
 }
 
@@ -905,33 +987,58 @@ __device__ void dct_2d_coop(float* p, size_t stride, int width, int height, bool
 }
 
 constexpr int kLargeThreads = 64;
-__global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, const uint32_t* __restrict__ items,
+template <bool DEQ>
+__global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, DevDequantParams dq,
+                                                                   const uint32_t* __restrict__ items,
                                                                    const uint32_t* __restrict__ count_ptr, int nmax) {
   extern __shared__ float s_large[];  // llf (32 x 32) | per-thread line buffers (2 * nmax each)
   float* llf = s_large;
   float* lines = s_large + 1024;
-  const uint32_t total = *count_ptr * 3;
+  const uint32_t total = DEQ ? *count_ptr : *count_ptr * 3;
   for (uint32_t work = blockIdx.x; work < total; work += gridDim.x) {
-    const uint32_t item = items[work / 3], c = work % 3;
+    const uint32_t item = items[DEQ ? work : work / 3];
     const uint32_t sbx = item & 0xffff, sby = item >> 16;
     const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
-    uint32_t bx, by;
-    if (!channel_block(f, c, sbx, sby, bx, by)) continue;
     const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
     const int w = bw * 8, h = bh * 8;
-    float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
-    const float* lf = f.lf[c];
-    for (int i = int(threadIdx.x); i < bw * bh; i += kLargeThreads)
-      llf[i] = lf[size_t(by + i / bw) * f.bw + bx + i % bw];
-    __syncthreads();
-    dct_2d_coop(llf, size_t(bw), bw, bh, true, lines, nmax);
-    const int logbw = 31 - __clz(bw), logbh = 31 - __clz(bh);
-    for (int i = int(threadIdx.x); i < bw * bh; i += kLargeThreads) {
-      const int x = i % bw, y = i / bw;
-      block[size_t(y) * f.cw + x] = __fdiv_rn(llf[i], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+    if (DEQ) {  // dequantise the three channels in place (L2-resident block), then transform them one by one
+      const DeqBlock db = deq_block(f, dq, t, sbx, sby);
+      const int logw = 31 - __clz(w);
+      for (int idx = int(threadIdx.x); idx < w * h; idx += kLargeThreads) {
+        const int x = idx & (w - 1), y = idx >> logw;
+        const size_t gi = (size_t(sby) * 8 + y) * f.cw + size_t(sbx) * 8 + x;
+        float v[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          v[c] = deq_one(f.coeff[c][gi], __ldg(db.mat[c] + y * w + x), db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
+        float kx, kb;
+        cfl_factors(f, dq, sbx * 8 + uint32_t(x), sby * 8 + uint32_t(y), kx, kb);
+        v[0] = __fadd_rn(v[0], __fmul_rn(kx, v[1]));
+        v[2] = __fadd_rn(v[2], __fmul_rn(kb, v[1]));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f.coeff[c][gi] = __float_as_uint(v[c]);
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    dct_2d_coop(block, f.cw, w, h, false, lines, nmax);
+#pragma unroll 1
+    for (int ci = 0; ci < (DEQ ? 3 : 1); ++ci) {
+      const uint32_t c = DEQ ? uint32_t(ci) : work % 3;
+      uint32_t bx, by;
+      if (!channel_block(f, c, sbx, sby, bx, by)) continue;
+      float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
+      const float* lf = f.lf[c];
+      for (int i = int(threadIdx.x); i < bw * bh; i += kLargeThreads)
+        llf[i] = lf[size_t(by + i / bw) * f.bw + bx + i % bw];
+      __syncthreads();
+      dct_2d_coop(llf, size_t(bw), bw, bh, true, lines, nmax);
+      const int logbw = 31 - __clz(bw), logbh = 31 - __clz(bh);
+      for (int i = int(threadIdx.x); i < bw * bh; i += kLargeThreads) {
+        const int x = i % bw, y = i / bw;
+        block[size_t(y) * f.cw + x] = __fdiv_rn(llf[i], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+      }
+      __syncthreads();
+      dct_2d_coop(block, f.cw, w, h, false, lines, nmax);
+    }
   }
 }
 
@@ -968,7 +1075,24 @@ size_t hf_transform_scratch_bytes(uint32_t bw, uint32_t bh) {
   return 256 + (cells + cells / 2 + 2 * (cells / 32 + 1) + 64) * 4;
 }
 
-void launch_hf_transform(DevFrame f, void* scratch, cudaStream_t stream) {
+namespace {
+template <bool DEQ>
+void launch_idcts(DevFrame f, const DevDequantParams& dq, const TransformLists& L, size_t cells, int num_sms, cudaStream_t stream) {
+  const size_t per = DEQ ? 1 : 3;  // work items per varblock
+  const int small_grid = int(std::min<size_t>((cells * per + kSmallGroups - 1) / kSmallGroups, size_t(num_sms) * 8));
+  idct_small_kernel<DEQ><<<small_grid, kSmallGroups * 8, 0, stream>>>(f, dq, L.items[0], L.counts + 0);
+  const int medium_grid = int(std::min<size_t>((cells / 2 * per + kMediumWarps) / kMediumWarps, size_t(num_sms) * 8));
+  idct_medium_kernel<DEQ><<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, dq, L.items[1], L.counts + 1);
+  const int large_grid = int(std::min<size_t>((cells / 32 + 1) * per, size_t(num_sms) * 4));
+  idct_large_kernel<DEQ><<<large_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 64 + 1)) * 4, stream>>>(f, dq, L.items[2], L.counts + 2, 64);
+  const int huge_grid = int(std::min<size_t>((cells / 128 + 1) * per, size_t(num_sms)));
+  idct_large_kernel<DEQ><<<huge_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 256 + 1)) * 4, stream>>>(f, dq, L.items[3], L.counts + 3, 256);
+}
+}  // namespace
+
+// `dq` non-null: the coefficient planes still hold quantised integers; dequantisation and chroma from luma run in the
+// transforms' load stage (one HBM round trip less than hf_dequant_cfl_kernel + transforms). Not for subsampled frames.
+void launch_hf_transform(DevFrame f, void* scratch, const DevDequantParams* dq, cudaStream_t stream) {
   const size_t cells = size_t(f.bw) * f.bh;
   TransformLists L;
   L.counts = static_cast<uint32_t*>(scratch);
@@ -985,16 +1109,16 @@ void launch_hf_transform(DevFrame f, void* scratch, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(idct_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+    cudaFuncSetAttribute(idct_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+    cudaFuncSetAttribute(idct_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
   }
-  const int small_grid = int(std::min<size_t>((cells * 3 + kSmallGroups - 1) / kSmallGroups, size_t(num_sms) * 8));
-  idct_small_kernel<<<small_grid, kSmallGroups * 8, 0, stream>>>(f, L.items[0], L.counts + 0);
-  const int medium_grid = int(std::min<size_t>((cells / 2 * 3 + kMediumWarps) / kMediumWarps, size_t(num_sms) * 8));
-  idct_medium_kernel<<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, L.items[1], L.counts + 1);
-  const int large_grid = int(std::min<size_t>((cells / 32 + 1) * 3, size_t(num_sms) * 4));
-  idct_large_kernel<<<large_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 64 + 1)) * 4, stream>>>(f, L.items[2], L.counts + 2, 64);
-  const int huge_grid = int(std::min<size_t>((cells / 128 + 1) * 3, size_t(num_sms)));
-  idct_large_kernel<<<huge_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 256 + 1)) * 4, stream>>>(f, L.items[3], L.counts + 3, 256);
+  if (dq && !f.subsampled) {
+    launch_idcts<true>(f, *dq, L, cells, num_sms, stream);
+  } else {
+    DevDequantParams none;
+    memset(&none, 0, sizeof(none));
+    launch_idcts<false>(f, none, L, cells, num_sms, stream);
+  }
 }
 
 }  // namespace jxlb

@@ -1,0 +1,409 @@
+// Frame pipeline: N decoder contexts (one CUDA stream + one host thread each) fed from one queue, the in-library
+// counterpart of the reference's frame-level concurrency (jxl-oxide-cli renders keyframes with rayon's par_iter,
+// crates/jxl-oxide-cli/src/decode.rs:285-320; jxl-render spawns reference / LF frames eagerly, lib.rs:496-509).
+//
+// Why it lives below the C ABI: a JPEG XL frame spends most of its latency in a handful of strictly serial entropy
+// streams (LfCoeff + HfMetadata of every 2048x2048 LF group, ~0.1 s for an 8K frame) that occupy a few warps, and
+// only a few milliseconds in kernels that fill the GPU. Throughput therefore needs many frames in flight, but a
+// frame past its LF stage holds ~25 bytes per pixel of planes. The pipeline separates the two: `workers` frames may be
+// anywhere, at most `heavy_frames` of them past Backend::begin_heavy_stage(); each heavy slot owns a pre-allocated
+// slab the full-resolution planes are carved from, so a frame costs no allocator call and HBM use is bounded by
+// heavy_frames x slab whatever `workers` is. Frames flow without barriers, so the contexts de-phase by themselves and
+// the GPU-filling stages of some frames overlap the latency-bound stages of others.
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include <thread>
+
+#include <pthread.h>
+#include <sched.h>
+
+#include "capi_internal.h"
+
+using namespace jxlb;
+
+namespace {
+
+struct Job {
+  const uint8_t* data = nullptr;  // host bytes (caller keeps them alive until the job is reported done) or
+  size_t size = 0;
+  int32_t slot = -1;              // a preloaded slot
+  int32_t out_mode = 0;
+  void* dst = nullptr;
+  size_t dst_bytes = 0;
+  uint64_t tag = 0;
+};
+
+struct Done {
+  uint64_t tag;
+  int32_t status;
+  std::string error;
+  void* out = nullptr;  // pipeline-owned pinned buffer (jobs submitted with dst == NULL), else the job's dst
+  size_t out_bytes = 0;
+};
+
+struct HostBuf {  // pinned staging owned by the pipeline: allocated by a worker thread (NUMA-local to the GPU)
+  void* p = nullptr;
+  size_t bytes = 0;
+  bool busy = false;
+};
+
+struct Resident {
+  std::vector<uint8_t> codestream;
+  uint8_t* dptr = nullptr;
+};
+
+struct Slab {
+  void* base = nullptr;
+  size_t bytes = 0;
+  bool busy = false;
+};
+
+// CPUs local to the GPU's PCIe root (sysfs), so that worker threads - and whatever they first-touch - sit on the NUMA
+// node the device DMAs to. Empty when the topology cannot be read (containers without sysfs): affinity is left alone.
+std::vector<int> device_local_cpus(int device) {
+  std::vector<int> cpus;
+  char busid[32] = {0};
+  if (cudaDeviceGetPCIBusId(busid, sizeof(busid), device) != cudaSuccess) return cpus;
+  for (char* c = busid; *c; ++c) *c = char(tolower(*c));
+  std::ifstream f(std::string("/sys/bus/pci/devices/") + busid + "/local_cpulist");
+  std::string list;
+  if (!f || !std::getline(f, list)) return cpus;
+  std::stringstream ss(list);
+  std::string part;
+  while (std::getline(ss, part, ',')) {
+    int a = 0, b = 0;
+    if (std::sscanf(part.c_str(), "%d-%d", &a, &b) == 2) {
+      for (int i = a; i <= b; ++i) cpus.push_back(i);
+    } else if (std::sscanf(part.c_str(), "%d", &a) == 1) {
+      cpus.push_back(a);
+    }
+  }
+  return cpus;
+}
+
+}  // namespace
+
+struct jxlb_pipeline {
+  int device = 0;
+  int heavy_frames = 0;
+  std::vector<jxlb_decoder*> decoders;
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_job, cv_done, cv_slab;
+  std::deque<Job> queue;
+  std::deque<Done> done;
+  uint64_t submitted = 0, reported = 0;
+  bool stopping = false;
+  std::map<int32_t, Resident> resident;
+  std::vector<Slab> slabs;
+  std::vector<HostBuf> hostbufs;
+  std::condition_variable cv_host;
+  std::string error;
+  std::vector<int> cpus;
+
+  int acquire_slab(size_t bytes_hint) {
+    std::unique_lock<std::mutex> lk(mu);
+    int idx = -1;
+    cv_slab.wait(lk, [&] {
+      for (size_t i = 0; i < slabs.size(); ++i)
+        if (!slabs[i].busy) {
+          idx = int(i);
+          return true;
+        }
+      return false;
+    });
+    Slab& s = slabs[size_t(idx)];
+    s.busy = true;
+    if (s.bytes < bytes_hint) {  // first frame of this size: (re)allocate the slab; never shrinks
+      lk.unlock();
+      cudaSetDevice(device);
+      if (s.base) cudaFree(s.base);
+      s.base = nullptr;
+      s.bytes = 0;
+      void* p = nullptr;
+      if (cudaMalloc(&p, bytes_hint) == cudaSuccess) {
+        s.base = p;
+        s.bytes = bytes_hint;
+      } else {
+        cudaGetLastError();  // out of memory: the frame falls back to the stream-ordered pool
+      }
+    }
+    return idx;
+  }
+  void* acquire_host(size_t bytes) {
+    std::unique_lock<std::mutex> lk(mu);
+    int idx = -1;
+    cv_host.wait(lk, [&] {
+      for (size_t i = 0; i < hostbufs.size(); ++i)
+        if (!hostbufs[i].busy) {
+          idx = int(i);
+          return true;
+        }
+      return false;
+    });
+    HostBuf& b = hostbufs[size_t(idx)];
+    b.busy = true;
+    if (b.bytes < bytes) {
+      lk.unlock();
+      if (b.p) cudaFreeHost(b.p);
+      b.p = nullptr;
+      b.bytes = 0;
+      void* q = nullptr;
+      if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) == cudaSuccess) {
+        std::memset(q, 0, bytes);  // first touch by this (GPU-local) thread
+        b.p = q;
+        b.bytes = bytes;
+      } else {
+        cudaGetLastError();
+        lk.lock();
+        b.busy = false;
+        lk.unlock();
+        cv_host.notify_one();
+        return nullptr;
+      }
+    }
+    return b.p;
+  }
+  bool release_host(void* ptr) {
+    bool found = false;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (HostBuf& b : hostbufs)
+        if (b.p == ptr && b.busy) {
+          b.busy = false;
+          found = true;
+        }
+    }
+    if (found) cv_host.notify_one();
+    return found;
+  }
+  void release_slab(int idx) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      slabs[size_t(idx)].busy = false;
+    }
+    cv_slab.notify_one();
+  }
+
+  void worker(size_t wi) {
+    cudaSetDevice(device);
+    if (!cpus.empty()) {
+      cpu_set_t set;
+      CPU_ZERO(&set);
+      for (int c : cpus) CPU_SET(c, &set);
+      pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+    jxlb_decoder* dec = decoders[wi];
+    int held = -1;
+    dec->be->on_heavy_stage = [&](size_t hint) {
+      if (held >= 0) return;  // a later frame of the same image: it shares the slab (overflow goes to the pool)
+      held = acquire_slab(hint);
+      dec->be->set_arena(slabs[size_t(held)].base, slabs[size_t(held)].bytes);
+    };
+    for (;;) {
+      Job job;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_job.wait(lk, [&] { return stopping || !queue.empty(); });
+        if (queue.empty()) return;
+        job = queue.front();
+        queue.pop_front();
+      }
+      Done d{job.tag, JXLB_OK, std::string()};
+      int32_t rc;
+      if (job.data) {
+        rc = jxlb_decode(dec, job.data, job.size, nullptr);
+      } else {
+        const Resident* r = nullptr;
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          auto it = resident.find(job.slot);
+          if (it != resident.end()) r = &it->second;
+        }
+        if (!r) {
+          rc = JXLB_ERR_INVALID_ARG;
+          dec->error = "unknown preload slot";
+        } else {
+          rc = decode_resident(dec, r->codestream.data(), r->codestream.size(), r->dptr, nullptr);
+        }
+      }
+      if (rc == JXLB_OK && job.out_mode != 0) {
+        void* dst = job.dst;
+        size_t dst_bytes = job.dst_bytes;
+        if (!dst) {  // library-owned pinned staging, sized from the decoded frame
+          jxlb_frame_info fi;
+          jxlb_frame_get_info(dec, 0, &fi);
+          if (job.out_mode == 1) {
+            dst_bytes = 0;
+            for (const View& v : dec->res.frames[0].channels) dst_bytes += size_t(v.w) * v.h * 4;
+          } else {
+            dst_bytes = size_t(fi.width) * fi.height * size_t(jxlb_frame_stream_channels(dec, 0)) * (job.out_mode == 2 ? 1 : 2);
+          }
+          dst = acquire_host(dst_bytes);
+          if (!dst) {
+            rc = JXLB_ERR_CUDA;
+            dec->error = "cannot allocate pinned host memory for the frame output";
+          }
+        }
+        if (rc == JXLB_OK) {
+          if (job.out_mode == 1) rc = frame_planar_to_host(dec, 0, static_cast<float*>(dst), dst_bytes);
+          else rc = jxlb_frame_write_to_buffer(dec, 0, job.out_mode - 2, 0, dst, dst_bytes);
+          d.out = dst;
+          d.out_bytes = dst_bytes;
+          if (rc != JXLB_OK && !job.dst) {
+            release_host(dst);
+            d.out = nullptr;
+          }
+        }
+      } else if (rc == JXLB_OK) {
+        rc = jxlb_sync(dec);
+      }
+      if (rc != JXLB_OK) {
+        d.status = rc;
+        d.error = dec->error;
+        jxlb_sync(dec);
+      }
+      jxlb_release_frames(dec);
+      if (held >= 0) {
+        dec->be->end_arena();
+        release_slab(held);
+        held = -1;
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        done.push_back(std::move(d));
+      }
+      cv_done.notify_all();
+    }
+  }
+};
+
+extern "C" {
+
+int32_t jxlb_pipeline_create(int32_t device, const jxlb_pipeline_config* cfg, jxlb_pipeline** out) {
+  if (!out) return JXLB_ERR_INVALID_ARG;
+  *out = nullptr;
+  const int workers = cfg && cfg->workers > 0 ? cfg->workers : 32;
+  const int heavy = cfg && cfg->heavy_frames > 0 ? cfg->heavy_frames : 8;
+  auto p = std::make_unique<jxlb_pipeline>();
+  p->device = device;
+  p->heavy_frames = heavy;
+  p->slabs.resize(size_t(heavy));
+  p->hostbufs.resize(size_t(heavy) + 4);
+  for (int i = 0; i < workers; ++i) {
+    jxlb_decoder* d = nullptr;
+    const int32_t rc = jxlb_decoder_create(device, &d);
+    if (rc != JXLB_OK) {
+      for (jxlb_decoder* q : p->decoders) jxlb_decoder_destroy(q);
+      return rc;
+    }
+    if (cfg && cfg->hf_streams_per_cta > 0) jxlb_set_hf_streams_per_cta(d, cfg->hf_streams_per_cta);
+    p->decoders.push_back(d);
+  }
+  if (!(cfg && cfg->no_affinity)) p->cpus = device_local_cpus(device);
+  for (int i = 0; i < workers; ++i) p->threads.emplace_back([q = p.get(), i] { q->worker(size_t(i)); });
+  *out = p.release();
+  return JXLB_OK;
+}
+
+void jxlb_pipeline_destroy(jxlb_pipeline* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    p->stopping = true;
+    p->queue.clear();
+  }
+  p->cv_job.notify_all();
+  for (std::thread& t : p->threads) t.join();
+  for (jxlb_decoder* d : p->decoders) jxlb_decoder_destroy(d);
+  cudaSetDevice(p->device);
+  for (Slab& s : p->slabs)
+    if (s.base) cudaFree(s.base);
+  for (auto& kv : p->resident)
+    if (kv.second.dptr) cudaFree(kv.second.dptr);
+  for (HostBuf& b : p->hostbufs)
+    if (b.p) cudaFreeHost(b.p);
+  delete p;
+}
+
+const char* jxlb_pipeline_last_error(const jxlb_pipeline* p) { return p ? p->error.c_str() : "null pipeline"; }
+
+int32_t jxlb_pipeline_preload(jxlb_pipeline* p, int32_t slot, const uint8_t* data, size_t size) {
+  if (!p || !data) return JXLB_ERR_INVALID_ARG;
+  try {
+    Resident r;
+    r.codestream = extract_codestream(data, size);
+    r.dptr = p->decoders[0]->be->upload_resident(r.codestream.data(), r.codestream.size());
+    std::lock_guard<std::mutex> lk(p->mu);
+    Resident& dst = p->resident[slot];
+    if (dst.dptr) cudaFree(dst.dptr);
+    dst = std::move(r);
+    return JXLB_OK;
+  } catch (const Error& e) {
+    p->error = e.what();
+    return e.code;
+  }
+}
+
+int32_t jxlb_pipeline_submit(jxlb_pipeline* p, const uint8_t* data, size_t size, int32_t slot, int32_t out_mode, void* dst,
+                             size_t dst_bytes, uint64_t tag) {
+  if (!p || out_mode < 0 || out_mode > 3 || (!data && slot < 0)) return JXLB_ERR_INVALID_ARG;
+  Job j;
+  j.data = data;
+  j.size = size;
+  j.slot = slot;
+  j.out_mode = out_mode;
+  j.dst = dst;
+  j.dst_bytes = dst_bytes;
+  j.tag = tag;
+  {
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (p->stopping) return JXLB_ERR_INVALID_ARG;
+    p->queue.push_back(j);
+    ++p->submitted;
+  }
+  p->cv_job.notify_one();
+  return JXLB_OK;
+}
+
+int32_t jxlb_pipeline_wait(jxlb_pipeline* p, uint64_t* tag, int32_t* status, void** out, size_t* out_bytes, char* err,
+                           size_t err_cap) {
+  if (!p || !tag || !status) return JXLB_ERR_INVALID_ARG;
+  std::unique_lock<std::mutex> lk(p->mu);
+  if (p->reported == p->submitted) return JXLB_ERR_INVALID_ARG;  // nothing in flight
+  p->cv_done.wait(lk, [&] { return !p->done.empty(); });
+  Done d = std::move(p->done.front());
+  p->done.pop_front();
+  ++p->reported;
+  *tag = d.tag;
+  *status = d.status;
+  if (out) *out = d.out;
+  if (out_bytes) *out_bytes = d.out_bytes;
+  if (err && err_cap) std::snprintf(err, err_cap, "%s", d.error.c_str());
+  return JXLB_OK;
+}
+
+int32_t jxlb_pipeline_release_output(jxlb_pipeline* p, void* out) {
+  if (!p || !out) return JXLB_ERR_INVALID_ARG;
+  return p->release_host(out) ? JXLB_OK : JXLB_ERR_INVALID_ARG;
+}
+
+uint64_t jxlb_pipeline_launch_count(const jxlb_pipeline* p) {
+  uint64_t n = 0;
+  if (p)
+    for (const jxlb_decoder* d : p->decoders) n += d->be->launches;
+  return n;
+}
+
+int32_t jxlb_pipeline_workers(const jxlb_pipeline* p) { return p ? int32_t(p->decoders.size()) : 0; }
+
+jxlb_decoder* jxlb_pipeline_decoder(jxlb_pipeline* p, int32_t index) {
+  return (p && index >= 0 && size_t(index) < p->decoders.size()) ? p->decoders[size_t(index)] : nullptr;
+}
+
+}  // extern "C"

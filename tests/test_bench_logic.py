@@ -1,52 +1,25 @@
-"""Host logic of bench.py that needs no GPU: the HF schedule choice (child-process probes are replaced by canned outputs)."""
+"""Host logic of bench.py that needs no GPU."""
 import argparse
-import json
-
-import pytest
 
 import bench
 
 
-def _args(hf_lanes="auto"):
-    return argparse.Namespace(hf_lanes=hf_lanes, workload="synth8k", contexts=24)
+def test_metric_names_follow_the_workload():
+    assert "8K VarDCT d1.0" in bench.METRIC["synth8k"]
+    assert "d2.0" in bench.METRIC["synth8k_d2"] and "Modular" in bench.METRIC["synthmod4k"]
 
 
-def _fake(monkeypatch, identical, speeds):
-    """Canned child outputs keyed by the schedule: value + digest ("ref" when identical to the default kernel's)."""
-    canned = {}
-    for n, v in speeds.items():
-        canned[n] = {"value": v, "sha256": "ref" if n == "0" or identical.get(n) else "other"}
-    monkeypatch.setenv("JXLB_BENCH_FAKE_PROBE", json.dumps(canned))
-    monkeypatch.delenv("JXLB_HF_LANES", raising=False)
+def test_workloads_are_seeded_and_sized():
+    desc, frames, (w, h) = bench.load_workload("synth4k", 5)
+    assert (w, h) == (3840, 2160) and len(frames) == 5 and frames[0] == frames[4] and frames[0] != frames[1]
+    assert "EPF 2" in desc
 
 
-def test_candidate_must_be_identical_and_faster(monkeypatch):
-    _fake(monkeypatch, {"16": True, "64": True, "128": True}, {"0": 3000.0, "16": 3300.0, "64": 3600.0, "128": 3900.0})
-    n, rep = bench.choose_hf_schedule(_args(), 0)
-    assert n == 128 and rep["chosen"] == 128 and rep["probe_mp_s"]["0"] == 3000.0
-    _fake(monkeypatch, {"16": True, "64": True, "128": False}, {"0": 3000.0, "16": 3700.0, "64": 3600.0, "128": 9999.0})
-    n, rep = bench.choose_hf_schedule(_args(), 0)
-    assert n == 16 and rep["identical_to_default_kernel"]["128"] is False   # differs from the default kernel: never used
-    _fake(monkeypatch, {"16": True, "64": True, "128": True}, {"0": 3000.0, "16": 3010.0, "64": 3050.0, "128": 2900.0})
-    assert bench.choose_hf_schedule(_args(), 0)[0] == 0           # within 3 %: keep the default
-    _fake(monkeypatch, {"16": True}, {"0": 3000.0, "16": 3500.0})  # the 64 / 128 children "crash": only they are dropped
-    n, rep = bench.choose_hf_schedule(_args(), 0)
-    assert n == 16 and str(rep["identical_to_default_kernel"]["64"]).startswith("failed")
+def test_fixed_hf_schedule_and_roofline_families():
+    assert bench.HF_STREAMS_PER_CTA in (0, 8, 16)
+    assert set(bench.CHAIN) & set(bench.KERNELS) and set(bench.ENTROPY) <= set(bench.KERNELS)
+    assert bench.algorithmic_bytes("filters_fused", 7680, 4320, 0) == 7680 * 4320 * 24
 
 
-def test_probe_failure_falls_back_to_the_default(monkeypatch):
-    monkeypatch.setenv("JXLB_BENCH_FAKE_PROBE", json.dumps({}))     # the parity child "fails"
-    monkeypatch.delenv("JXLB_HF_LANES", raising=False)
-    n, rep = bench.choose_hf_schedule(_args(), 0)
-    assert n == 0 and "fallback" in rep
-
-
-@pytest.mark.parametrize("flag,env,want", [("64", None, 64), ("auto", "128", 128), ("0", None, 0), ("auto", "50", 64), ("16", None, 16)])
-def test_explicit_choice_wins(monkeypatch, flag, env, want):
-    monkeypatch.delenv("JXLB_BENCH_FAKE_PROBE", raising=False)
-    if env is None:
-        monkeypatch.delenv("JXLB_HF_LANES", raising=False)
-    else:
-        monkeypatch.setenv("JXLB_HF_LANES", env)
-    n, rep = bench.choose_hf_schedule(_args(flag), 0)
-    assert n == want and rep["mode"] == "explicit"
+def test_gpu_local_cpus_without_a_gpu_is_empty():
+    assert bench.gpu_local_cpus(0) == []

@@ -18,8 +18,9 @@ from conftest import fixture_bytes
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]
 
 FIXTURES = ["opsin_inverse", "bike", "cafe", "issue_425", "genshin_ycbcr_420", "bench_oriented_brg", "minecraft_vardct_e7", "upsampling"]
-# streams per CTA: 16 = one warp per stream with every preset's cluster map staged once; 32 = one thread per stream
-SCHEDULES = [16, 32]
+# streams per CTA: 8 / 16 (default) / 32 = one warp per stream, every preset's tables staged once per CTA
+# (decode_hf_warp_kernel); 4 = the round-1 kernel (also the fall-back for oversized cluster maps); 64 = one thread per stream
+SCHEDULES = [4, 32, 64]
 
 
 @pytest.fixture(scope="module")
@@ -53,7 +54,7 @@ def test_hf_lanes_fixture(dec, oracle, name, streams):
     _check(dec, oracle, fixture_bytes(name, "input.jxl"), streams)
 
 
-@pytest.mark.parametrize("streams", [8, 16, 32, 64, 128])
+@pytest.mark.parametrize("streams", [4, 8, 16, 32, 64, 128])
 @pytest.mark.parametrize("extra", [(), ("--passes", "3")])
 def test_hf_lanes_synthetic(dec, oracle, streams, extra):
     # 2000x1500: 8x6 groups (ragged right / bottom), more streams than one CTA carries at 32 per CTA
