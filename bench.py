@@ -72,6 +72,15 @@ def load_workload(name, nframes=16):
                 f"libjxl-like: WP-coded LF, mixed varblocks 8x8..64x64, Gaborish + EPF {3 if d2 else 2} iters), "
                 f"{len(frames)} independent frames per step")
         return desc, frames, (w, h)
+    if name == "synthmod4k":  # BASELINE config #4: Modular lossless, RCT + default Squeeze + weighted predictor
+        w, h = 3840, 2160
+        frames = [synth_frame(w, h, seed, extra=("--modular",)) for seed in (1, 2, 3, 4)]
+        frames = [frames[i % len(frames)] for i in range(max(1, nframes))]
+        bpp = sum(len(f) for f in frames) * 8.0 / (w * h * len(frames))
+        desc = (f"{w}x{h} Modular lossless RGB 8-bit synthetic frames (tools/synth_enc.cc --modular, seeds 1-4, {bpp:.2f} bit/px: "
+                "YCoCg RCT, default Squeeze schedule, weighted predictor under a WP-error context chain, 135 pass groups + 4 LF "
+                f"groups), {len(frames)} independent frames per step")
+        return desc, frames, (w, h)
     if name.startswith("file:"):
         with open(name[5:], "rb") as f:
             data = f.read()
@@ -240,6 +249,8 @@ def gpu_local_cpus(device_index):
 # HF coefficient schedule of the timed run: fixed (ncu evidence in profiles/r02_*), never probed inside the bench.
 HF_STREAMS_PER_CTA = 16
 CHAIN = ["hf_dequant_cfl", "hf_transform", "filters_fused", "gaborish", "epf_step", "xyb_to_rgb"]
+# Modular frames: the HBM-bound part is everything after the entropy decode (inverse Squeeze, RCT, sample conversion)
+MODULAR_CHAIN = ["squeeze_inverse", "rct_inverse", "int_to_float", "copy_rect", "modular_xyb", "palette_inverse_simple"]
 ENTROPY = ["modular_decode", "build_block_info", "decode_hf"]
 
 
@@ -390,7 +401,11 @@ def run_ours(args, rank, world, local_rank):
     peak_source = "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     # The dominant HBM-bound work: the pixel chain coefficients -> RGB planes (24.3 B/px when fully fused).
     # One "launch" = the chain's kernels for one frame; duration = the sum of their CUDA-event times.
-    chain_bytes = px_per_frame * 24.3
+    modular = "mod" in args.workload
+    chain = MODULAR_CHAIN if modular else CHAIN
+    # Modular: 4 B/sample of decoded residuals read + 4 B/sample of f32 output written, three channels, when Squeeze, RCT
+    # and the sample conversion are fully fused
+    chain_bytes = px_per_frame * (24.0 if modular else 24.3)
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
@@ -399,19 +414,21 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         pass
     roofline = None
-    chain_solo_ms = sum(solo.get(k, 0.0) for k in CHAIN)
-    chain_load_ms = sum(prof[k]["ms"] for k in CHAIN if k in prof) / max(1, len(frames))
+    chain_solo_ms = sum(solo.get(k, 0.0) for k in chain)
+    chain_load_ms = sum(prof[k]["ms"] for k in chain if k in prof) / max(1, len(frames))
     if chain_solo_ms > 0:
         ach = chain_bytes / (chain_solo_ms / 1e3) / 1e9
-        roofline = {"kernel": "+".join(k for k in CHAIN if k in solo), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"kernel": "+".join(k for k in chain if k in solo), "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_source,
                     "bytes_per_launch": chain_bytes, "avg_launch_ms": chain_solo_ms,
-                    "per_kernel_ms": {k: round(solo[k], 4) for k in CHAIN if k in solo},
+                    "per_kernel_ms": {k: round(solo[k], 4) for k in chain if k in solo},
                     "measured": "CUDA events around the chain's launches, one frame alone on the GPU (mean of 3)",
                     "under_load": {"avg_launch_ms": chain_load_ms, "achieved": chain_bytes / (chain_load_ms / 1e3) / 1e9 if chain_load_ms else None,
                                    "note": "same kernels during one step with every worker busy: event times include waiting "
                                            "for SMs held by other frames' kernels"},
-                    "algorithmic_bytes": "24.3 B/px x pixels: 12 B coefficients + 0.33 B LF/meta read, 12 B RGB written (fully fused chain)"}
+                    "algorithmic_bytes": ("24 B/px x pixels: 3 x 4 B decoded residuals read, 3 x 4 B f32 samples written (Squeeze, RCT and "
+                                          "sample conversion fully fused)") if modular else
+                                         "24.3 B/px x pixels: 12 B coefficients + 0.33 B LF/meta read, 12 B RGB written (fully fused chain)"}
     entropy = None
     try:
         sym = json.load(open(os.path.join(ROOT, "profiles", "r02_symbols.json"))).get(args.workload)

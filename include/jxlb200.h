@@ -27,7 +27,8 @@ enum {
   JXLB_ERR_EOF = 3,
   JXLB_ERR_CUDA = 4,
   JXLB_ERR_INVALID_ARG = 5,
-  JXLB_ERR_DEVICE_DECODE = 6
+  JXLB_ERR_DEVICE_DECODE = 6,
+  JXLB_ERR_OUT_OF_MEMORY = 7 /* the allocation budget given to jxlb_decoder_create_ex would be exceeded */
 };
 
 typedef struct jxlb_decoder jxlb_decoder;
@@ -54,6 +55,10 @@ typedef struct {
 /* Context lifetime. Replaces JxlImageBuilder/RenderContext construction
  * (crates/jxl-oxide/src/lib.rs:205-279, crates/jxl-render/src/lib.rs:35-130). */
 int32_t jxlb_decoder_create(int32_t cuda_device, jxlb_decoder** out);
+/* Same with an allocation budget in bytes of HBM for planes and temporaries (0 = unlimited): the counterpart of
+ * AllocTracker::with_limit (crates/jxl-grid/src/alloc_tracker.rs:8-74, JxlImageBuilder::alloc_tracker). A decode that
+ * would exceed it fails with JXLB_ERR_OUT_OF_MEMORY (the reference's Error::OutOfMemory) and frees what it had. */
+int32_t jxlb_decoder_create_ex(int32_t cuda_device, uint64_t mem_limit_bytes, jxlb_decoder** out);
 void jxlb_decoder_destroy(jxlb_decoder* dec);
 const char* jxlb_last_error(const jxlb_decoder* dec);
 
@@ -158,6 +163,22 @@ int32_t jxlb_squeeze_inverse(jxlb_decoder* dec, const int32_t* avg, uint32_t avg
 int32_t jxlb_blend(jxlb_decoder* dec, float* base, const float* patch, const float* base_alpha, const float* new_alpha,
                    uint32_t width, uint32_t height, uint32_t stride, int32_t mode, int32_t clamp, int32_t premultiplied,
                    int32_t swapped);
+/* features::upsample (crates/jxl-render/src/features/upsampling.rs:45-132) with the default weight tables
+ * (crates/jxl-image/src/lib.rs upsampling weights): `in` (w x h, stride in floats) -> `out` ((w * factor) x (h * factor)),
+ * factor 2, 4 or 8; both DEVICE pointers. */
+int32_t jxlb_upsample(jxlb_decoder* dec, const float* in, uint32_t width, uint32_t height, uint32_t stride, uint32_t factor,
+                      float* out, uint32_t out_stride);
+/* Decode a frame whose pieces come from separate buffers (what jxl-frame hands out: Frame::data(TocGroupKind) slices,
+ * crates/jxl-frame/src/lib.rs:264-275, possibly straight from `jxlp` boxes): `header` holds the codestream from its
+ * signature up to and including the frame's TOC, `sections[i]` the TOC entries in bitstream order. The library joins
+ * them (one copy into the pinned staging buffer it uploads from anyway) and decodes as jxlb_decode does; it still parses
+ * the headers and entropy-code tables itself, because the device tables are built from them. */
+typedef struct {
+  const uint8_t* data;
+  size_t size;
+} jxlb_section;
+int32_t jxlb_decode_frame_sections(jxlb_decoder* dec, const uint8_t* header, size_t header_size, const jxlb_section* sections,
+                                   size_t num_sections, const jxlb_options* opt);
 /* rct::inverse_rct (crates/jxl-modular/src/transform/rct.rs:15). In place on three planes. */
 int32_t jxlb_rct_inverse(jxlb_decoder* dec, int32_t* const planes[3], uint32_t width, uint32_t height, uint32_t stride,
                          uint32_t rct_type);

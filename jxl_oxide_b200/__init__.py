@@ -21,11 +21,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libjxlb200.so")
 
-OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVICE_DECODE = range(7)
+OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVICE_DECODE, ERR_OUT_OF_MEMORY = range(8)
 
 # every symbol include/jxlb200.h declares
 EXPORTED_SYMBOLS = [
-    "jxlb_decoder_create", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
+    "jxlb_decoder_create", "jxlb_decoder_create_ex", "jxlb_decode_frame_sections", "jxlb_upsample", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
     "jxlb_image_get_info", "jxlb_image_original_icc",
     "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_write_to_device", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
@@ -62,6 +62,10 @@ class _ImageInfo(ctypes.Structure):
                 ("width", "height", "bits_per_sample", "num_extra_channels", "xyb_encoded", "grayscale", "orientation")]
 
 
+class _Section(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_char_p), ("size", ctypes.c_size_t)]
+
+
 class _PipelineConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("workers", "heavy_frames", "hf_streams_per_cta", "no_affinity")]
 
@@ -87,6 +91,10 @@ def load_library():
     vp, i32, u32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint32
     L.jxlb_decoder_create.argtypes = [i32, ctypes.POINTER(vp)]
     L.jxlb_decoder_create.restype = i32
+    L.jxlb_decoder_create_ex.argtypes = [i32, ctypes.c_uint64, ctypes.POINTER(vp)]
+    L.jxlb_decoder_create_ex.restype = i32
+    L.jxlb_decode_frame_sections.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(_Section), ctypes.c_size_t, ctypes.POINTER(_Options)]
+    L.jxlb_upsample.argtypes = [vp, vp, u32, u32, u32, u32, vp, u32]
     L.jxlb_decoder_destroy.argtypes = [vp]
     L.jxlb_decoder_destroy.restype = None
     L.jxlb_last_error.argtypes = [vp]
@@ -148,10 +156,11 @@ def load_library():
 class Decoder:
     """One decoder = one CUDA stream + its HBM planes (RenderContext analogue)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, mem_limit=0):
+        """`mem_limit`: allocation budget in bytes of HBM (0 = unlimited), AllocTracker::with_limit's counterpart."""
         L = load_library()
         h = ctypes.c_void_p()
-        rc = L.jxlb_decoder_create(device, ctypes.byref(h))
+        rc = L.jxlb_decoder_create_ex(device, int(mem_limit), ctypes.byref(h))
         if rc != OK:
             raise JxlError(rc, "cannot create CUDA decoder (no CUDA device? this path has no CPU fallback)")
         self._h = h
@@ -165,6 +174,20 @@ class Decoder:
     def decode(self, data: bytes, output_colour=0, max_frames=0):
         opt = _Options(output_colour, max_frames)
         self._check(self._L.jxlb_decode(self._h, data, len(data), ctypes.byref(opt)))
+
+    def decode_sections(self, header: bytes, sections, output_colour=0, max_frames=0):
+        """jxlb_decode_frame_sections: `header` = signature .. TOC, `sections` = the TOC entries' bytes in bitstream order."""
+        arr = (_Section * len(sections))(*[_Section(s, len(s)) for s in sections])
+        opt = _Options(output_colour, max_frames)
+        self._check(self._L.jxlb_decode_frame_sections(self._h, header, len(header), arr, len(sections), ctypes.byref(opt)))
+
+    def upsample(self, src, factor):
+        """features::upsample with the default weights on a device tensor (h, w) float32 -> (h * factor, w * factor)."""
+        import torch
+        h, w = src.shape
+        out = torch.empty((h * factor, w * factor), dtype=torch.float32, device=src.device)
+        self._check(self._L.jxlb_upsample(self._h, int(src.data_ptr()), w, h, src.stride(0), factor, int(out.data_ptr()), out.stride(0)))
+        return out
 
     def preload(self, slot, data: bytes):
         self._check(self._L.jxlb_preload(self._h, slot, data, len(data)))

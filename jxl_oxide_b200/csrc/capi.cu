@@ -83,17 +83,65 @@ int32_t frame_planar_to_host(jxlb_decoder* dec, int32_t frame, float* dst, size_
 
 extern "C" {
 
-int32_t jxlb_decoder_create(int32_t device, jxlb_decoder** out) {
+int32_t jxlb_decoder_create_ex(int32_t device, uint64_t mem_limit_bytes, jxlb_decoder** out) {
   if (!out) return JXLB_ERR_INVALID_ARG;
   *out = nullptr;
   auto dec = std::make_unique<jxlb_decoder>();
   try {
     dec->be.reset(new CudaBackend(device));
+    dec->be->set_mem_limit(mem_limit_bytes);
   } catch (const Error& e) {
     return e.code;
   }
   *out = dec.release();
   return JXLB_OK;
+}
+
+int32_t jxlb_decoder_create(int32_t device, jxlb_decoder** out) { return jxlb_decoder_create_ex(device, 0, out); }
+
+int32_t jxlb_decode_frame_sections(jxlb_decoder* dec, const uint8_t* header, size_t header_size, const jxlb_section* sections,
+                                   size_t num_sections, const jxlb_options* opt) {
+  if (!dec || !header || (!sections && num_sections)) return JXLB_ERR_INVALID_ARG;
+  size_t total = header_size;
+  for (size_t i = 0; i < num_sections; ++i) {
+    if (!sections[i].data && sections[i].size) return JXLB_ERR_INVALID_ARG;
+    total += sections[i].size;
+  }
+  std::vector<uint8_t> joined;
+  joined.reserve(total);
+  joined.insert(joined.end(), header, header + header_size);
+  for (size_t i = 0; i < num_sections; ++i) joined.insert(joined.end(), sections[i].data, sections[i].data + sections[i].size);
+  return jxlb_decode(dec, joined.data(), joined.size(), opt);
+}
+
+int32_t jxlb_upsample(jxlb_decoder* dec, const float* in, uint32_t width, uint32_t height, uint32_t stride, uint32_t factor,
+                      float* out, uint32_t out_stride) {
+  if (!dec || !in || !out || (factor != 2 && factor != 4 && factor != 8) || !width || !height) return JXLB_ERR_INVALID_ARG;
+  return guarded(dec, [&] {
+    ImageHeader ih = default_image_header();
+    const std::vector<float>& weights = factor == 2 ? ih.up2_weight : (factor == 4 ? ih.up4_weight : ih.up8_weight);
+    // per-phase 5x5 kernels from the symmetric weight list (upsampling.rs:66-92)
+    const uint32_t k = factor, mat_n = k / 2;
+    std::vector<float> quarter(size_t(k) * k / 4 * 25, 0.0f);
+    size_t weight_idx = 0;
+    for (uint32_t y = 0; y < 5 * mat_n; ++y) {
+      const uint32_t mat_y = y / 5, ky = y % 5;
+      for (uint32_t x = y; x < 5 * mat_n; ++x) {
+        const uint32_t mat_x = x / 5, kx = x % 5;
+        const float wv = weights[weight_idx++];
+        quarter[size_t(mat_y * mat_n + mat_x) * 25 + ky * 5 + kx] = wv;
+        quarter[size_t(mat_x * mat_n + mat_y) * 25 + kx * 5 + ky] = wv;
+      }
+    }
+    cudaStream_t s = dec->be->stream();
+    float* d_quarter = nullptr;
+    JXLB_CHECK(cudaMallocAsync(&d_quarter, quarter.size() * 4, s) == cudaSuccess, kErrCuda, "cudaMallocAsync failed");
+    JXLB_CHECK(cudaMemcpyAsync(d_quarter, quarter.data(), quarter.size() * 4, cudaMemcpyHostToDevice, s) == cudaSuccess, kErrCuda, "upload failed");
+    launch_upsample(raw_view(const_cast<float*>(in), width, height, stride), raw_view(out, width * k, height * k, out_stride), int(k), d_quarter, s);
+    cudaFreeAsync(d_quarter, s);
+    dec->be->launches++;
+    dec->be->sync();
+  });
 }
 
 void jxlb_decoder_destroy(jxlb_decoder* dec) { delete dec; }

@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <memory>
+#include <thread>
 #include <tuple>
 
 namespace jxlb {
@@ -29,6 +31,17 @@ CudaBackend::CudaBackend(int device) : device_(device) {
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&sync_event_, cudaEventBlockingSync | cudaEventDisableTiming));
+  stage_cap_ = size_t(2) << 20;
+  CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_stage_), stage_cap_, cudaHostAllocDefault));
+  CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_stage_), stage_cap_));
+  result_cap_ = size_t(256) << 10;
+  CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_result_), result_cap_, cudaHostAllocDefault));
+  {
+    void* f = nullptr;
+    CUDA_CHECK(cudaHostAlloc(&f, 64, cudaHostAllocMapped));
+    h_flag_ = static_cast<volatile uint32_t*>(f);
+    *h_flag_ = 0;
+  }
   // A private stream-ordered pool per decoder: freed planes are reused by this decoder's next frame
   // (release threshold = never trim), and an allocation never has to wait on another decoder's
   // stream the way reuse inside the shared default pool can.
@@ -62,11 +75,16 @@ CudaBackend::~CudaBackend() {
     if (!(arena_base_ && kv.second.ptr >= static_cast<void*>(arena_base_) && kv.second.ptr < static_cast<void*>(arena_base_ + arena_cap_)))
       cudaFree(kv.second.ptr);
   for (void* p : temps_) cudaFree(p);
-  if (d_codestream_) cudaFree(d_codestream_);
+  if (d_codestream_) cudaFreeAsync(d_codestream_, stream_);
   if (d_natural_orders_) cudaFree(d_natural_orders_);
   if (d_dequant_) cudaFree(d_dequant_);
   if (d_dequant_default_) cudaFree(d_dequant_default_);
   if (sync_event_) cudaEventDestroy(sync_event_);
+  if (h_stage_) cudaFreeHost(h_stage_);
+  if (d_stage_) cudaFree(d_stage_);
+  if (h_result_) cudaFreeHost(h_result_);
+  if (h_input_) cudaFreeHost(h_input_);
+  if (h_flag_) cudaFreeHost(const_cast<uint32_t*>(h_flag_));
   if (stream_) cudaStreamDestroy(stream_);
   if (pool_ && !std::getenv("JXLB_SHARED_POOL")) cudaMemPoolDestroy(pool_);
 }
@@ -96,40 +114,108 @@ void CudaBackend::end_arena() {
 
 void* CudaBackend::dmalloc(size_t bytes) {
   void* p = nullptr;
+  if (mem_limit_ && mem_in_use_ + bytes > mem_limit_)
+    fail(kErrOutOfMemory, "allocation budget exceeded: " + std::to_string(mem_in_use_ + bytes) + " > " + std::to_string(mem_limit_) + " bytes");
   if (arena_base_ && bytes >= (256u << 10)) {  // big planes: carved from the frame slab, released with it
     const size_t need = (bytes + 511) & ~size_t(511);
     if (arena_off_ + need <= arena_cap_) {
       p = arena_base_ + arena_off_;
       arena_off_ += need;
       arena_peak_ = std::max(arena_peak_, arena_off_);
+      if (mem_limit_) mem_in_use_ += need;  // released with the slab
       return p;
     }
     arena_spill_ += need;
   }
   CUDA_CHECK(cudaSetDevice(device_));
   CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), pool_, stream_));
+  if (mem_limit_) {
+    mem_in_use_ += bytes;
+    alloc_sizes_[p] = bytes;
+  }
   return p;
 }
 void CudaBackend::dfree(void* p) {
   if (!p) return;
   if (arena_base_ && p >= arena_base_ && p < arena_base_ + arena_cap_) return;  // the slab is reset as a whole
+  if (mem_limit_) {
+    auto it = alloc_sizes_.find(p);
+    if (it != alloc_sizes_.end()) {
+      mem_in_use_ -= std::min<uint64_t>(mem_in_use_, it->second);
+      alloc_sizes_.erase(it);
+    }
+  }
   CUDA_CHECK(cudaFreeAsync(p, stream_));
 }
 void* CudaBackend::upload_temp(const void* src, size_t bytes) {
-  void* p = dmalloc(bytes);
+  const size_t off = (stage_off_ + 15) & ~size_t(15);
+  if (off + bytes <= stage_cap_) {
+    if (bytes) std::memcpy(h_stage_ + off, src, bytes);
+    stage_off_ = off + bytes;
+    return d_stage_ + off;
+  }
+  void* p = dmalloc(bytes);  // does not fit the staging block
   temps_.push_back(p);
   if (bytes) CUDA_CHECK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, stream_));
   return p;
+}
+void* CudaBackend::stage_scratch(size_t bytes) {
+  flush_uploads();  // the range handed out must not be part of a later host -> device copy
+  const size_t off = (stage_off_ + 15) & ~size_t(15);
+  if (off + bytes <= stage_cap_) {
+    stage_off_ = stage_flushed_ = off + bytes;
+    return d_stage_ + off;
+  }
+  void* p = dmalloc(bytes);
+  temps_.push_back(p);
+  return p;
+}
+void CudaBackend::flush_uploads() {
+  if (stage_off_ > stage_flushed_)
+    CUDA_CHECK(cudaMemcpyAsync(d_stage_ + stage_flushed_, h_stage_ + stage_flushed_, stage_off_ - stage_flushed_, cudaMemcpyHostToDevice, stream_));
+  stage_flushed_ = stage_off_;
+}
+void* CudaBackend::fetch_result(const void* dsrc, size_t bytes) {
+  const size_t off = (result_off_ + 15) & ~size_t(15);
+  JXLB_CHECK(off + bytes <= result_cap_, kErrUnsupported, "too many stream jobs in one launch for the result buffer");
+  CUDA_CHECK(cudaMemcpyAsync(h_result_ + off, dsrc, bytes, cudaMemcpyDeviceToHost, stream_));
+  result_off_ = off + bytes;
+  return h_result_ + off;
 }
 void CudaBackend::release_temps() {
   for (void* p : temps_) dfree(p);
   temps_.clear();
 }
 void CudaBackend::sync() {
-  // Wait on a blocking-sync event instead of spinning in cudaStreamSynchronize: a box drives many
-  // decoder contexts (x 8 GPUs) from host threads that mostly wait for 10-100 ms entropy kernels.
-  CUDA_CHECK(cudaEventRecord(sync_event_, stream_));
-  CUDA_CHECK(cudaEventSynchronize(sync_event_));
+  // The stream writes a sequence number into a mapped host word and the host thread polls it (short spin, then
+  // 50 us naps). Waiting inside the driver instead (cudaEventSynchronize, or the implicit wait of a pageable
+  // cudaMemcpyAsync) was measured to return 14-27 ms late on average once 32-48 decoder threads wait at the same time
+  // (profiles/r02_progress.md): the waits serialise on the driver. Here a waiting thread never enters the driver.
+  flush_uploads();
+  const uint32_t seq = ++sync_seq_;
+  launch_signal_word(const_cast<uint32_t*>(h_flag_), seq, stream_);
+  ++launches;
+  uint32_t spins = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  while (*h_flag_ != seq) {
+    if (++spins < 2000) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      continue;
+    }
+    std::this_thread::sleep_for(std::chrono::microseconds(50));
+    if ((spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) {
+      // a faulting kernel never writes the word: ask the driver from time to time
+      cudaError_t e = cudaStreamQuery(stream_);
+      if (e == cudaSuccess) break;
+      if (e != cudaErrorNotReady) fail(kErrCuda, std::string("CUDA error: ") + cudaGetErrorString(e) + " while waiting for the stream");
+      t0 = std::chrono::steady_clock::now();
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  stage_off_ = stage_flushed_ = 0;  // everything queued so far has run: the staging block is free again
+  result_off_ = 0;
   resolve_profile();
 }
 
@@ -164,6 +250,7 @@ TimeOrigin& time_origin() {
 }  // namespace
 
 void CudaBackend::begin_k(const char* name) {
+  flush_uploads();
   ++launches;
   if (!profile) return;
   time_origin();
@@ -219,12 +306,25 @@ void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
   }
   size_t need = ((size + 7) & ~size_t(7)) + 64;  // zero padding for the 64-bit bit reader
   if (need > codestream_cap_) {
-    if (d_codestream_) CUDA_CHECK(cudaFree(d_codestream_));
-    CUDA_CHECK(cudaMalloc(&d_codestream_, need));
-    codestream_cap_ = need;
+    // Stream-ordered (re)allocation with headroom: cudaFree / cudaMalloc wait for the whole device - with dozens of
+    // decoders whose frames differ by a few bytes that was hundreds of device-wide stalls per run (measured: the
+    // host-bytes path 5x slower than the resident one).
+    if (d_codestream_) CUDA_CHECK(cudaFreeAsync(d_codestream_, stream_));
+    d_codestream_ = nullptr;
+    codestream_cap_ = std::max<size_t>(need + need / 2, size_t(1) << 20);
+    CUDA_CHECK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&d_codestream_), codestream_cap_, pool_, stream_));
   }
-  CUDA_CHECK(cudaMemsetAsync(d_codestream_, 0, need, stream_));
-  CUDA_CHECK(cudaMemcpyAsync(d_codestream_, data, size, cudaMemcpyHostToDevice, stream_));
+  // through pinned memory: a pageable source makes cudaMemcpyAsync stage and wait inside the driver (measured: the
+  // host-bytes path ran 5x slower than the resident one with 32 decoder threads; the copies serialise on the driver)
+  if (need > input_cap_) {
+    if (h_input_) CUDA_CHECK(cudaFreeHost(h_input_));
+    h_input_ = nullptr;
+    input_cap_ = std::max<size_t>(need + need / 2, size_t(1) << 20);
+    CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_input_), input_cap_, cudaHostAllocDefault));
+  }
+  std::memcpy(h_input_, data, size);
+  std::memset(h_input_ + size, 0, need - size);
+  CUDA_CHECK(cudaMemcpyAsync(d_codestream_, h_input_, need, cudaMemcpyHostToDevice, stream_));
   active_cs_ = d_codestream_;
   ensure_static_tables();
 }
@@ -613,7 +713,18 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
         const int64_t skey = ct->stream_dependent ? int64_t(j.stream_index) : -1;
         any = channel_trees.emplace(std::make_tuple(j.tree, uint32_t(ci), nprev, skey), std::move(ct)).first;
       }
-      key.push_back(any->second.get());
+      // Channels whose reachable subtrees are identical node for node (a tree that never tests the channel index, e.g.
+      // a Squeeze image's 36 global channels under one weighted-predictor chain) share one staged copy: the first
+      // channel tree with that content stands for all of them.
+      const ChannelTree* canon = any->second.get();
+      for (const ChannelTree* prev : key)
+        if (prev != canon && prev->lut_prop == canon->lut_prop && prev->lut_base == canon->lut_base && prev->lut == canon->lut &&
+            prev->nodes.size() == canon->nodes.size() &&
+            std::memcmp(prev->nodes.data(), canon->nodes.data(), canon->nodes.size() * sizeof(MaNode)) == 0) {
+          canon = prev;
+          break;
+        }
+      key.push_back(canon);
     }
     if (compact) {
       auto jt = job_tables.find(key);
@@ -622,7 +733,13 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
         std::vector<MaNode> nodes;
         std::vector<uint16_t> luts;
         t.wp = false;
+        std::map<const ChannelTree*, DevChannelPlan> seen;  // channels that reach the same subtree share its copy
         for (const ChannelTree* ct : key) {
+          auto dup = seen.find(ct);
+          if (dup != seen.end()) {
+            t.plans.push_back(dup->second);
+            continue;
+          }
           const uint32_t base = uint32_t(nodes.size());
           DevChannelPlan plan;
           plan.root = base;
@@ -647,6 +764,7 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
             for (uint16_t l : ct->lut) luts.push_back(uint16_t(l + base));
           }
           t.plans.push_back(plan);
+          seen.emplace(ct, plan);
         }
         t.num_nodes = uint32_t(nodes.size());
         t.lut_total = uint32_t(luts.size());
@@ -694,10 +812,8 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   }
   const DevModularJob* d_jobs = static_cast<const DevModularJob*>(upload_temp(djobs.data(), djobs.size() * sizeof(DevModularJob)));
   const DevChannel* d_chans = static_cast<const DevChannel*>(upload_temp(dchans.data(), dchans.size() * sizeof(DevChannel)));
-  uint64_t* d_end = static_cast<uint64_t*>(dmalloc(jobs.size() * 8));
-  int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
-  temps_.push_back(d_end);
-  temps_.push_back(d_status);
+  uint64_t* d_end = static_cast<uint64_t*>(stage_scratch(jobs.size() * 8));
+  int* d_status = static_cast<int*>(stage_scratch(jobs.size() * 4));
   const DevChannelPlan* d_plans = static_cast<const DevChannelPlan*>(upload_temp(dplans.data(), dplans.size() * sizeof(DevChannelPlan)));
   unsigned long long* d_trace = nullptr;
   double host_launch = 0.0;
@@ -710,19 +826,16 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
   begin_k("modular_decode");
   launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, all_staged, stream_, d_trace);
   end_k();
-  std::vector<uint64_t> end(jobs.size());
-  std::vector<int> status(jobs.size());
-  CUDA_CHECK(cudaMemcpyAsync(end.data(), d_end, jobs.size() * 8, cudaMemcpyDeviceToHost, stream_));
-  CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
-  std::vector<unsigned long long> trace(d_trace ? jobs.size() * 2 : 0);
-  if (d_trace) CUDA_CHECK(cudaMemcpyAsync(trace.data(), d_trace, trace.size() * 8, cudaMemcpyDeviceToHost, stream_));
+  const uint64_t* end = static_cast<const uint64_t*>(fetch_result(d_end, jobs.size() * 8));
+  const int* status = static_cast<const int*>(fetch_result(d_status, jobs.size() * 4));
+  const unsigned long long* trace = d_trace ? static_cast<const unsigned long long*>(fetch_result(d_trace, jobs.size() * 16)) : nullptr;
   sync();
   if (d_trace) {
     const TimeOrigin& o = time_origin();
     unsigned long long first = ~0ull, last = 0;
     for (size_t i = 0; i < jobs.size(); ++i) {
-      first = std::min(first, trace[2 * i]);
-      last = std::max(last, trace[2 * i + 1]);
+      first = std::min<unsigned long long>(first, trace[2 * i]);
+      last = std::max<unsigned long long>(last, trace[2 * i + 1]);
     }
     timeline.push_back({"host:launch_to_return modular", host_launch - o.host_ms, host_now_ms() - o.host_ms});
     timeline.push_back({"dev:modular_decode", (double(first) - double(o.dev_ns)) * 1e-6, (double(last) - double(o.dev_ns)) * 1e-6});
@@ -771,9 +884,9 @@ void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& 
   begin_k("palette_inverse");
   launch_palette_inverse(pal, tv, int(targets.size()), int(t.nb_colours), int(bit_depth), int(t.nb_deltas), d_mask, d_status, stream_);
   end_k();
-  int num_delta = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&num_delta, d_status, 4, cudaMemcpyDeviceToHost, stream_));
+  const int* num_delta_p = static_cast<const int*>(fetch_result(d_status, 4));
   sync();
+  const int num_delta = *num_delta_p;
   if (num_delta > 0) {  // palette.rs:114-152
     JXLB_CHECK(t.d_pred <= 13, kErrBitstream, "invalid delta-palette predictor");
     DevPaletteDeltaParams p;
@@ -844,8 +957,7 @@ void CudaBackend::build_block_info(VarDctState& st, const std::vector<BlockInfoJ
   const EpfParams& epf = st.fh->restoration_filter.epf;
   const DevBlockInfoJob* d_jobs = static_cast<const DevBlockInfoJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevBlockInfoJob)));
   const float* d_lut = static_cast<const float*>(upload_temp(epf.sharp_lut, sizeof(epf.sharp_lut)));
-  int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
-  temps_.push_back(d_status);
+  int* d_status = static_cast<int*>(stage_scratch(jobs.size() * 4));
   float quant_mul_base = epf.quant_mul * 65536.0f / float(st.lfg->global_scale);
   begin_k("build_block_info");
   void* scratch = dmalloc(build_block_info_scratch_bytes(int(jobs.size())));
@@ -853,12 +965,11 @@ void CudaBackend::build_block_info(VarDctState& st, const std::vector<BlockInfoJ
   launch_build_block_info(dev_frame(st), d_jobs, int(jobs.size()), quant_mul_base, d_lut, epf.iters > 0 ? 1 : 0, d_status,
                           scratch, stream_);
   end_k();
-  std::vector<int> status(jobs.size());
-  CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
+  const int* status = static_cast<const int*>(fetch_result(d_status, jobs.size() * 4));
   sync();
   CUDA_CHECK(cudaGetLastError());
   release_temps();
-  for (int s : status) JXLB_CHECK(s == kDevOk, kErrBitstream, "invalid HfMetadata block layout");
+  for (size_t i = 0; i < jobs.size(); ++i) JXLB_CHECK(status[i] == kDevOk, kErrBitstream, "invalid HfMetadata block layout");
 }
 
 void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
@@ -868,7 +979,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   const HfPassSyntax& hp = st.hfg->passes[pass];
   // The coefficient kernels read plain hybrid-uint tokens; an LZ77-enabled HF code (legal, hf_coeff.rs:181-222 goes
   // through read_varint_with_multiplier_clustered, but no known encoder emits it) would decode silently wrong.
-  JXLB_CHECK(!hp.code.lz77_enabled, kErrUnsupported, "LZ77 in the HF coefficient streams is not supported on the device");
+  const bool hf_lz77 = hp.code.lz77_enabled;  // reported after the launch: a stream that is invalid anyway keeps its own error
   DevHfParams p;
   std::memset(&p, 0, sizeof(p));
   p.code = upload_code(hp.code);
@@ -928,10 +1039,8 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
   std::vector<DevHfJob> dj;
   for (uint32_t i : perm) dj.push_back({jobs[i].bit_pos, jobs[i].bit_limit, jobs[i].group_idx});
   const DevHfJob* d_jobs = static_cast<const DevHfJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevHfJob)));
-  uint64_t* d_end = static_cast<uint64_t*>(dmalloc(jobs.size() * 8));
-  int* d_status = static_cast<int*>(dmalloc(jobs.size() * 4));
-  temps_.push_back(d_end);
-  temps_.push_back(d_status);
+  uint64_t* d_end = static_cast<uint64_t*>(stage_scratch(jobs.size() * 8));
+  int* d_status = static_cast<int*>(stage_scratch(jobs.size() * 4));
   uint32_t* d_blk_ctx = nullptr;
   if (hf_streams_per_cta >= 64) {
     d_blk_ctx = static_cast<uint32_t*>(dmalloc(size_t(st.bw) * st.bh * 4));
@@ -948,10 +1057,8 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
                      hf_streams_per_cta > 0 ? hf_streams_per_cta : 16, stream_);
   end_k();
-  std::vector<uint64_t> end(jobs.size());
-  std::vector<int> status(jobs.size());
-  CUDA_CHECK(cudaMemcpyAsync(end.data(), d_end, jobs.size() * 8, cudaMemcpyDeviceToHost, stream_));
-  CUDA_CHECK(cudaMemcpyAsync(status.data(), d_status, jobs.size() * 4, cudaMemcpyDeviceToHost, stream_));
+  const uint64_t* end = static_cast<const uint64_t*>(fetch_result(d_end, jobs.size() * 8));
+  const int* status = static_cast<const int*>(fetch_result(d_status, jobs.size() * 4));
   sync();
   CUDA_CHECK(cudaGetLastError());
   release_temps();
@@ -962,6 +1069,7 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
            std::string("HF group ") + std::to_string(job.group_idx) + ": " + dev_status_message(status[i]));
     job.end_bit = size_t(end[i]);
   }
+  JXLB_CHECK(!hf_lz77, kErrUnsupported, "LZ77 in the HF coefficient streams is not supported on the device");
 }
 
 void CudaBackend::lf_dequant(VarDctState& st, const std::vector<LfDequantJob>& jobs) {

@@ -66,6 +66,9 @@ class CudaBackend : public Backend {
   }
   // The slab goes back to its owner: nothing of this backend may point into it afterwards.
   void end_arena();
+  // allocation budget (0 = none): pool allocations and slab carvings count until freed
+  void set_mem_limit(uint64_t bytes) { mem_limit_ = bytes; }
+  uint64_t mem_in_use() const { return mem_in_use_; }
   size_t arena_peak() const { return arena_peak_; }
   size_t arena_spill() const { return arena_spill_; }  // bytes that did not fit the slab (allocated from the pool)
 
@@ -112,9 +115,17 @@ class CudaBackend : public Backend {
   };
   void* dmalloc(size_t bytes);
   void dfree(void* p);
-  // copies host bytes to a fresh device buffer (freed at the next `release_temps`)
+  // Host tables for the next launch. They are gathered in a pinned staging block that mirrors a device block of the
+  // same size byte for byte, so the device address is known at once and ONE asynchronous copy per launch (flush_uploads,
+  // called by begin_k) moves everything: a stage used to cost ~10 cudaMallocAsync + pageable cudaMemcpyAsync + cudaFreeAsync
+  // calls, each taking the driver's context lock that every other decoder thread of the process wants too. The block is
+  // recycled at every sync(). Oversized requests fall back to a pool allocation + direct copy (freed by release_temps).
   void* upload_temp(const void* src, size_t bytes);
+  void* stage_scratch(size_t bytes);  // device scratch from the same block (no host data), zeroed by nobody
+  void flush_uploads();
   void release_temps();
+  // results of a stage (end positions, status words): device -> pinned host, readable after the next sync()
+  void* fetch_result(const void* dsrc, size_t bytes);
   DevEntropyCode upload_code(const EntropyCode& c);
   DevFrame dev_frame(const VarDctState& st) const;
   void ensure_static_tables();
@@ -138,9 +149,20 @@ class CudaBackend : public Backend {
  private:
 
   int device_;
+  uint8_t* h_stage_ = nullptr;   // pinned
+  uint8_t* d_stage_ = nullptr;
+  size_t stage_cap_ = 0, stage_off_ = 0, stage_flushed_ = 0;
+  uint8_t* h_result_ = nullptr;  // pinned
+  size_t result_cap_ = 0, result_off_ = 0;
+  uint8_t* h_input_ = nullptr;   // pinned staging of the encoded bytes
+  size_t input_cap_ = 0;
+  volatile uint32_t* h_flag_ = nullptr;  // mapped pinned word the stream writes its sync sequence number to
+  uint32_t sync_seq_ = 0;
   uint8_t* arena_base_ = nullptr;
   size_t arena_cap_ = 0, arena_off_ = 0, arena_peak_ = 0, arena_spill_ = 0;
   bool heavy_announced_ = false;
+  uint64_t mem_limit_ = 0, mem_in_use_ = 0;
+  std::map<void*, size_t> alloc_sizes_;  // pool allocations (for the budget)
   cudaStream_t stream_ = nullptr;
   cudaEvent_t sync_event_ = nullptr;
   cudaMemPool_t pool_ = nullptr;  // this decoder's own stream-ordered pool (no cross-stream reuse dependencies)

@@ -22,6 +22,7 @@ enum ErrorCode : int {
   kErrCuda = 4,
   kErrInvalidArg = 5,
   kErrDeviceDecode = 6,   // a device-side stream decoder flagged an invalid stream
+  kErrOutOfMemory = 7,    // the decoder's allocation budget (jxlb_decoder_create_ex) would be exceeded
 };
 
 struct Error : public std::runtime_error {

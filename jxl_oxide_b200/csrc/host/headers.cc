@@ -197,6 +197,14 @@ RestorationFilter::RestorationFilter() {
   for (auto& w : gab_weights) w[0] = 0.115169525f, w[1] = 0.061248592f;
 }
 
+ImageHeader default_image_header() {  // all-default metadata with the default upsampling weight tables
+  ImageHeader h;
+  h.up2_weight.assign(kDefaultUp2, kDefaultUp2 + 15);
+  h.up4_weight.assign(kDefaultUp4, kDefaultUp4 + 55);
+  h.up8_weight.assign(kDefaultUp8, kDefaultUp8 + 210);
+  return h;
+}
+
 ImageHeader parse_image_header(BitReader& br) {
   ImageHeader h;
   JXLB_CHECK(br.read(16) == 0x0aff, kErrBitstream, "JPEG XL signature mismatch");

@@ -186,6 +186,7 @@ struct Toc {
 };
 
 ImageHeader parse_image_header(BitReader& br);
+ImageHeader default_image_header();
 // Parses an ICC profile's *presence* only: the encoded ICC stream is skipped (not decoded).
 void skip_icc_profile(BitReader& br);
 // The entropy-decoded (still command-coded) ICC stream (jxl-color/src/icc/decode.rs:9-81)

@@ -263,6 +263,28 @@ __device__ __forceinline__ void xyb_px(float o[3], const DevColorParams& p) {  /
   }
 }
 
+// Visits every cell of `r` once with all 256 threads busy: the cells are numbered row by row and thread t takes cells
+// t, t + 256, ... (a 35 x 35 region walked as 32-wide column strips would leave the second strip 3 lanes wide). One
+// integer division per call; afterwards (x, y) advance incrementally.
+template <typename F>
+__device__ __forceinline__ void for_region(const Rect& r, F&& f) {
+  const int w = r.x1 - r.x0, h = r.y1 - r.y0;
+  if (w <= 0 || h <= 0) return;
+  const int n = w * h;
+  const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
+  int ly = tid / w, lx = tid - ly * w;
+  const int dy = 256 / w, dx = 256 - dy * w;
+  for (int i = tid; i < n; i += 256) {
+    f(r.x0 + lx, r.y0 + ly);
+    lx += dx;
+    ly += dy;
+    if (lx >= w) {
+      lx -= w;
+      ++ly;
+    }
+  }
+}
+
 struct FusedViews {
   const float* in[3];
   float* out[3];
@@ -343,27 +365,25 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
           : "memory");
   } else {  // load the input region (planes whose pitch TMA cannot address)
     const Rect r = clip(rect(halo));
-    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
-      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
+    for_region(r, [&](int lx, int ly) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          cur[c * kPlane + ly * kS + lx] = v.in[c][size_t(gy0 + ly) * v.in_stride[c] + gx0 + lx];
-      }
+      for (int c = 0; c < 3; ++c) cur[c * kPlane + ly * kS + lx] = v.in[c][size_t(gy0 + ly) * v.in_stride[c] + gx0 + lx];
+    });
   }
   __syncthreads();
 
   if (p.gab_enabled) {
     halo -= 1;
     const Rect r = clip(rect(halo));
-    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
-      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
+    float gw[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float w0 = p.gab_w[c][0], w1 = p.gab_w[c][1];
-          const float gw = fdiv(1.0f, fadd(fadd(1.0f, fmul(w0, 4.0f)), fmul(w1, 4.0f)));
-          alt[c * kPlane + ly * kS + lx] = gab_px(cur + c * kPlane + ly * kS + lx, gx0 + lx, gy0 + ly, width, height, w0, w1, gw);
-        }
-      }
+    for (int c = 0; c < 3; ++c) gw[c] = fdiv(1.0f, fadd(fadd(1.0f, fmul(p.gab_w[c][0], 4.0f)), fmul(p.gab_w[c][1], 4.0f)));
+    for_region(r, [&](int lx, int ly) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        alt[c * kPlane + ly * kS + lx] =
+            gab_px(cur + c * kPlane + ly * kS + lx, gx0 + lx, gy0 + ly, width, height, p.gab_w[c][0], p.gab_w[c][1], gw[c]);
+    });
     float* t = cur;
     cur = alt;
     alt = t;
@@ -383,27 +403,24 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
          // (cells beyond the image included: they stand for mirrored pixels)
         constexpr int ex = STEP == 0 ? 2 : 1;  // reach of the negated directions: x - 2 .. x + 1 (step 0), x - 1 .. x
         const Rect q{out.x0 - ex, out.y0 - ex, out.x1 + (STEP == 0 ? 1 : 0), out.y1};
-        for (int ly = q.y0 + int(threadIdx.y); ly < q.y1; ly += int(blockDim.y))
-          for (int lx = q.x0 + int(threadIdx.x); lx < q.x1; lx += int(blockDim.x))
-            epf_dist<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, p.epf);
+        for_region(q, [&](int lx, int ly) { epf_dist<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, p.epf); });
       }
       __syncthreads();
       const Rect r = clip(out);
-      for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
-        for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
-          const int x = gx0 + lx, y = gy0 + ly;
-          const float sigma_val = p.sigma ? __ldg(p.sigma + size_t(y >> 3) * p.sigma_stride + (x >> 3)) : p.epf.sigma_for_modular;
-          float o[3];
-          epf_apply<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, x, y, sigma_val, p.epf, o);
-          if (last) {
-            if (p.colour) xyb_px(o, p.col);
+      for_region(r, [&](int lx, int ly) {
+        const int x = gx0 + lx, y = gy0 + ly;
+        const float sigma_val = p.sigma ? __ldg(p.sigma + size_t(y >> 3) * p.sigma_stride + (x >> 3)) : p.epf.sigma_for_modular;
+        float o[3];
+        epf_apply<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, x, y, sigma_val, p.epf, o);
+        if (last) {
+          if (p.colour) xyb_px(o, p.col);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
-          } else {
+          for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
+        } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) alt[c * kPlane + ly * kS + lx] = o[c];
-          }
+          for (int c = 0; c < 3; ++c) alt[c * kPlane + ly * kS + lx] = o[c];
         }
+      });
       if (!last) {
         float* t = cur;
         cur = alt;
@@ -422,16 +439,15 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
 
   if (p.epf_iters == 0) {  // Gaborish (or nothing) followed by colour only
     const Rect r = clip(rect(0));
-    for (int ly = r.y0 + int(threadIdx.y); ly < r.y1; ly += int(blockDim.y))
-      for (int lx = r.x0 + int(threadIdx.x); lx < r.x1; lx += int(blockDim.x)) {
-        float o[3];
+    for_region(r, [&](int lx, int ly) {
+      float o[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[c] = cur[c * kPlane + ly * kS + lx];
-        if (p.colour) xyb_px(o, p.col);
-        const int x = gx0 + lx, y = gy0 + ly;
+      for (int c = 0; c < 3; ++c) o[c] = cur[c * kPlane + ly * kS + lx];
+      if (p.colour) xyb_px(o, p.col);
+      const int x = gx0 + lx, y = gy0 + ly;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
-      }
+      for (int c = 0; c < 3; ++c) v.out[c][size_t(y) * v.out_stride[c] + x] = o[c];
+    });
   }
 }
 

@@ -55,6 +55,7 @@ void launch_modular_decode(const uint8_t* codestream, const DevModularJob* jobs,
                            size_t smem_bytes, bool all_tables_staged, cudaStream_t stream,
                            unsigned long long* trace = nullptr);
 bool modular_job_all_staged(const DevModularJob& job, uint32_t max_width);
+void launch_signal_word(uint32_t* host_mapped_word, uint32_t value, cudaStream_t stream);
 // tracing aid: writes the device's %globaltimer (ns)
 void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream);
 // bytes of dynamic shared memory a job wants for its tree / entropy tables / WP rows / LUTs

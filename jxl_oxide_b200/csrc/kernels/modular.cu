@@ -27,26 +27,57 @@ __device__ __forceinline__ int32_t tendency(int32_t a, int32_t b, int32_t c) {  
   return 0;
 }
 
-// One thread per line: the recurrence along the line is serial (`left = second`,
-// squeeze.rs:59-90, 803-832); lines are independent.
-__global__ void squeeze_h_kernel(DevView avg, DevView res, DevView out) {
-  uint32_t y = blockIdx.x * blockDim.x + threadIdx.x;
-  if (y >= out.h) return;
-  const int32_t* ar = static_cast<const int32_t*>(avg.ptr) + size_t(y) * avg.stride;
-  const int32_t* rr = static_cast<const int32_t*>(res.ptr) + size_t(y) * res.stride;
-  int32_t* o = static_cast<int32_t*>(out.ptr) + size_t(y) * out.stride;
-  int32_t a = ar[0], left = a;
-  for (uint32_t x = 0; x < res.w; ++x) {
-    int32_t next_avg = (x + 1 < avg.w) ? ar[x + 1] : a;
-    int32_t diff = wadd(rr[x], tendency(left, a, next_avg));
-    int32_t first = wadd(a, diff / 2);
-    int32_t second = wsub(first, diff);
-    o[2 * x] = first;
-    o[2 * x + 1] = second;
-    a = next_avg;
-    left = second;
+// Horizontal inverse Squeeze (squeeze.rs:59-120). The recurrence along a row is serial (`left = second`), rows are
+// independent: one lane per row, a warp per band of 32 rows. A lane walking its own row straight in global memory
+// would touch 32 different cache lines per warp access, so the band is processed in chunks of 32 pairs staged through
+// shared memory: the warp loads the averages / residuals of the chunk row by row (128-byte coalesced reads), every
+// lane then runs its row's recurrence on the shared tile (pitch 33 / 65: conflict-free), and the 64 output columns go
+// back row by row as two coalesced 128-byte writes. `left` and the current average carry over between chunks in registers.
+constexpr int kSqWarps = 2;
+__global__ void __launch_bounds__(kSqWarps * 32) squeeze_h_kernel(DevView avg, DevView res, DevView out) {
+  __shared__ int32_t s_avg[kSqWarps][32][33], s_res[kSqWarps][32][33], s_out[kSqWarps][32][65];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t y0 = (blockIdx.x * kSqWarps + warp) * 32;
+  if (y0 >= out.h) return;
+  const uint32_t rows = min(32u, out.h - y0);
+  const int32_t* ab = static_cast<const int32_t*>(avg.ptr) + size_t(y0) * avg.stride;
+  const int32_t* rb = static_cast<const int32_t*>(res.ptr) + size_t(y0) * res.stride;
+  int32_t* ob = static_cast<int32_t*>(out.ptr) + size_t(y0) * out.stride;
+  int32_t(*ta)[33] = s_avg[warp];
+  int32_t(*tr)[33] = s_res[warp];
+  int32_t(*to)[65] = s_out[warp];
+  int32_t a = 0, left = 0;
+  if (lane < rows) a = left = ab[size_t(lane) * avg.stride];
+  for (uint32_t x0 = 0; x0 < res.w; x0 += 32) {
+    const uint32_t n = min(32u, res.w - x0);  // pairs in this chunk
+    for (uint32_t r = 0; r < rows; ++r) {
+      // average x0 + 1 + lane (the "next average" of pair x0 + lane) and residual x0 + lane of row r
+      const uint32_t ax = x0 + 1 + lane;
+      ta[r][lane] = ax < avg.w ? ab[size_t(r) * avg.stride + ax] : 0;
+      tr[r][lane] = lane < n ? rb[size_t(r) * res.stride + x0 + lane] : 0;
+    }
+    __syncwarp();
+    if (lane < rows) {
+      for (uint32_t k = 0; k < n; ++k) {
+        const int32_t next_avg = (x0 + k + 1 < avg.w) ? ta[lane][k] : a;
+        const int32_t diff = wadd(tr[lane][k], tendency(left, a, next_avg));
+        const int32_t first = wadd(a, diff / 2);
+        const int32_t second = wsub(first, diff);
+        to[lane][2 * k] = first;
+        to[lane][2 * k + 1] = second;
+        a = next_avg;
+        left = second;
+      }
+    }
+    __syncwarp();
+    for (uint32_t r = 0; r < rows; ++r) {
+      int32_t* o = ob + size_t(r) * out.stride + 2 * x0;
+      if (lane < 2 * n) o[lane] = to[r][lane];
+      if (lane + 32 < 2 * n) o[lane + 32] = to[r][lane + 32];
+    }
+    __syncwarp();
   }
-  if (out.w & 1) o[out.w - 1] = ar[avg.w - 1];
+  if ((out.w & 1) && lane < rows) ob[size_t(lane) * out.stride + out.w - 1] = ab[size_t(lane) * avg.stride + avg.w - 1];
 }
 
 __global__ void squeeze_v_kernel(DevView avg, DevView res, DevView out) {
@@ -200,7 +231,7 @@ inline dim3 grid2d(uint32_t w, uint32_t h, uint32_t bx = 128) { return dim3((w +
 
 void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizontal, cudaStream_t stream) {
   if (!out.w || !out.h) return;
-  if (horizontal) squeeze_h_kernel<<<(out.h + 63) / 64, 64, 0, stream>>>(avg, res, out);
+  if (horizontal) squeeze_h_kernel<<<(out.h + kSqWarps * 32 - 1) / (kSqWarps * 32), kSqWarps * 32, 0, stream>>>(avg, res, out);
   else squeeze_v_kernel<<<(out.w + 63) / 64, 64, 0, stream>>>(avg, res, out);
 }
 

@@ -685,6 +685,12 @@ __global__ void __launch_bounds__(32) palette_delta_kernel(DevPaletteDeltaParams
   }
 }
 
+// Completion word for CudaBackend::sync(): written to mapped host memory once everything before it on the stream is done.
+__global__ void signal_word_kernel(uint32_t* word, uint32_t value) {
+  *reinterpret_cast<volatile uint32_t*>(word) = value;
+  __threadfence_system();
+}
+
 __global__ void read_globaltimer_kernel(unsigned long long* out) {
   unsigned long long now;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -725,6 +731,10 @@ bool modular_job_all_staged(const DevModularJob& job, uint32_t max_width) {
   if (job.code.use_prefix ? L.prefix == 0xffffffffu : L.ans == 0xffffffffu) return false;
   if (job.use_wp && L.wp == 0xffffffffu) return false;
   return !job.code.lz77_enabled;
+}
+
+void launch_signal_word(uint32_t* host_mapped_word, uint32_t value, cudaStream_t stream) {
+  signal_word_kernel<<<1, 1, 0, stream>>>(host_mapped_word, value);
 }
 
 void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream) { read_globaltimer_kernel<<<1, 1, 0, stream>>>(out); }

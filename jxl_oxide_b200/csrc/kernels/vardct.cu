@@ -803,6 +803,10 @@ __device__ __forceinline__ DeqBlock deq_block(const DevFrame& f, const DevDequan
   return d;
 }
 __device__ __forceinline__ float deq_one(uint32_t raw, float m, float mul, float qb, float qbn) {
+  // Most coefficients are zero: 0 * quant_bias is a signed zero that the positive matrix weight (validated by the
+  // parser) and multiplier leave as it is, so the zero case needs one multiplication, and the division below stays off
+  // the common path.
+  if (raw == 0) return __fmul_rn(0.0f, qb);
   float q = float(int32_t(raw));
   if (fabsf(q) <= 1.0f) q = __fmul_rn(q, qb);
   else q = __fsub_rn(q, __fdiv_rn(qbn, q));
@@ -927,27 +931,50 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
     const int w = bw * 8, h = bh * 8;
     const int logw = 31 - __clz(w);
     DeqBlock db;
-    if (DEQ) db = deq_block(f, dq, t, sbx, sby);
+    // chroma-from-luma factors of the (at most 2 x 2) 64x64 tiles a block of up to 32x32 samples touches
+    float kxt[4], kbt[4];
+    const uint32_t tx0 = (sbx * 8) >> 6, ty0 = (sby * 8) >> 6;
+    if (DEQ) {
+      db = deq_block(f, dq, t, sbx, sby);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t tx = min(tx0 + uint32_t(i & 1), f.w64 - 1), ty = min(ty0 + uint32_t(i >> 1), (f.ch + 63) / 64 - 1);
+        cfl_factors(f, dq, tx << 6, ty << 6, kxt[i], kbt[i]);
+      }
+    }
 #pragma unroll 1
     for (int ci = 0; ci < (DEQ ? 3 : 1); ++ci) {
       const uint32_t c = DEQ ? (ci == 0 ? 1u : (ci == 1 ? 0u : 2u)) : work % 3;
       uint32_t bx, by;
       if (!channel_block(f, c, sbx, sby, bx, by)) continue;
       float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
-      for (int idx = int(lane); idx < w * h; idx += 32) {
-        const int x = idx & (w - 1), y = idx >> logw;
-        float v = block[size_t(y) * f.cw + x];
-        if (DEQ) {
-          const float q = deq_one(__float_as_uint(v), __ldg(db.mat[c] + y * w + x), db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
-          if (c == 1) {
-            ytile[y * 33 + x] = v = q;
-          } else {
-            float kx, kb;
-            cfl_factors(f, dq, bx * 8 + uint32_t(x), by * 8 + uint32_t(y), kx, kb);
-            v = __fadd_rn(q, __fmul_rn(c == 0 ? kx : kb, ytile[y * 33 + x]));
-          }
+      // w * h is a multiple of 128 (16x8 is the smallest block of this class): four elements per lane and trip, all loads
+      // of a trip issued before the first use, so that a trip costs one global-memory latency instead of four
+      for (int idx0 = int(lane); idx0 < w * h; idx0 += 128) {
+        float raw[4], mat[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = idx0 + 32 * j, x = idx & (w - 1), y = idx >> logw;
+          raw[j] = block[size_t(y) * f.cw + x];
+          if (DEQ) mat[j] = __ldg(db.mat[c] + idx);
         }
-        tile[y * 33 + x] = v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = idx0 + 32 * j, x = idx & (w - 1), y = idx >> logw;
+          float v = raw[j];
+          if (DEQ) {
+            const float q = deq_one(__float_as_uint(v), mat[j], db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
+            if (c == 1) {
+              ytile[y * 33 + x] = v = q;
+            } else {
+              const int ti = int(((bx * 8 + uint32_t(x)) >> 6) - tx0) + 2 * int(((by * 8 + uint32_t(y)) >> 6) - ty0);
+              const float k = c == 0 ? (ti == 0 ? kxt[0] : ti == 1 ? kxt[1] : ti == 2 ? kxt[2] : kxt[3])
+                                     : (ti == 0 ? kbt[0] : ti == 1 ? kbt[1] : ti == 2 ? kbt[2] : kbt[3]);
+              v = __fadd_rn(q, __fmul_rn(k, ytile[y * 33 + x]));
+            }
+          }
+          tile[y * 33 + x] = v;
+        }
       }
       if (lane == 0) compute_llf_small(f, int(c), bx, by, bw, bh, llf);  // overlaps the tile loads in flight
       __syncwarp();
@@ -1004,19 +1031,41 @@ __global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, D
     if (DEQ) {  // dequantise the three channels in place (L2-resident block), then transform them one by one
       const DeqBlock db = deq_block(f, dq, t, sbx, sby);
       const int logw = 31 - __clz(w);
-      for (int idx = int(threadIdx.x); idx < w * h; idx += kLargeThreads) {
-        const int x = idx & (w - 1), y = idx >> logw;
-        const size_t gi = (size_t(sby) * 8 + y) * f.cw + size_t(sbx) * 8 + x;
-        float v[3];
+      __shared__ float s_k[2][25];  // chroma-from-luma factors of the up to 5 x 5 64x64 tiles the block touches
+      const uint32_t tx0 = (sbx * 8) >> 6, ty0 = (sby * 8) >> 6;
+      if (threadIdx.x < 25) {
+        const uint32_t tx = min(tx0 + threadIdx.x % 5, f.w64 - 1), ty = min(ty0 + threadIdx.x / 5, (f.ch + 63) / 64 - 1);
+        cfl_factors(f, dq, tx << 6, ty << 6, s_k[0][threadIdx.x], s_k[1][threadIdx.x]);
+      }
+      __syncthreads();
+      // w * h >= 4096: four elements per thread and trip, their twelve coefficient loads in flight together
+      for (int idx0 = int(threadIdx.x); idx0 < w * h; idx0 += 4 * kLargeThreads) {
+        uint32_t raw[4][3];
+        float mat[4][3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-          v[c] = deq_one(f.coeff[c][gi], __ldg(db.mat[c] + y * w + x), db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
-        float kx, kb;
-        cfl_factors(f, dq, sbx * 8 + uint32_t(x), sby * 8 + uint32_t(y), kx, kb);
-        v[0] = __fadd_rn(v[0], __fmul_rn(kx, v[1]));
-        v[2] = __fadd_rn(v[2], __fmul_rn(kb, v[1]));
+        for (int j = 0; j < 4; ++j) {
+          const int idx = idx0 + j * kLargeThreads, x = idx & (w - 1), y = idx >> logw;
+          const size_t gi = (size_t(sby) * 8 + y) * f.cw + size_t(sbx) * 8 + x;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) f.coeff[c][gi] = __float_as_uint(v[c]);
+          for (int c = 0; c < 3; ++c) {
+            raw[j][c] = f.coeff[c][gi];
+            mat[j][c] = __ldg(db.mat[c] + idx);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = idx0 + j * kLargeThreads, x = idx & (w - 1), y = idx >> logw;
+          const size_t gi = (size_t(sby) * 8 + y) * f.cw + size_t(sbx) * 8 + x;
+          float v[3];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) v[c] = deq_one(raw[j][c], mat[j][c], db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
+          const int ti = int(((sbx * 8 + uint32_t(x)) >> 6) - tx0) + 5 * int(((sby * 8 + uint32_t(y)) >> 6) - ty0);
+          const float kx = s_k[0][ti], kb = s_k[1][ti];
+          v[0] = __fadd_rn(v[0], __fmul_rn(kx, v[1]));
+          v[2] = __fadd_rn(v[2], __fmul_rn(kb, v[1]));
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f.coeff[c][gi] = __float_as_uint(v[c]);
+        }
       }
       __syncthreads();
     }

@@ -103,6 +103,7 @@ struct jxlb_pipeline {
   std::vector<Slab> slabs;
   std::vector<HostBuf> hostbufs;
   std::condition_variable cv_host;
+  std::mutex copy_mu;  // one frame's output crosses the host link at a time
   std::string error;
   std::vector<int> cpus;
 
@@ -251,7 +252,13 @@ struct jxlb_pipeline {
           }
         }
         if (rc == JXLB_OK) {
-          if (job.out_mode == 1) rc = frame_planar_to_host(dec, 0, static_cast<float*>(dst), dst_bytes);
+          // Device -> host copies of different streams share the copy engines chunk by chunk; a dozen 400 MB copies
+          // in flight together were measured at 29 GB/s in total against 55 GB/s for one at a time. The decode work of the
+          // other frames goes on meanwhile; only the copies queue up.
+          rc = jxlb_sync(dec);
+          std::lock_guard<std::mutex> copy_lock(copy_mu);
+          if (rc != JXLB_OK) {
+          } else if (job.out_mode == 1) rc = frame_planar_to_host(dec, 0, static_cast<float*>(dst), dst_bytes);
           else rc = jxlb_frame_write_to_buffer(dec, 0, job.out_mode - 2, 0, dst, dst_bytes);
           d.out = dst;
           d.out_bytes = dst_bytes;

@@ -59,3 +59,21 @@ def test_new_entry_points_reject_bad_arguments_without_a_device():
     assert L.jxlb_set_hf_streams_per_cta(None, 64) == jxl_oxide_b200.ERR_INVALID_ARG
     buf = ctypes.create_string_buffer(16)
     assert L.jxlb_frame_write_to_device(None, 0, 0, 0, buf, 16) == jxl_oxide_b200.ERR_INVALID_ARG
+
+
+def test_round2_entry_points_reject_bad_arguments_without_a_device():
+    """Pipeline, allocation budget, section decode and upsample entry points: error values for bad arguments / no GPU."""
+    import torch
+    import jxl_oxide_b200 as J
+    L = J.load_library()
+    h = ctypes.c_void_p()
+    assert L.jxlb_decoder_create_ex(0, 1 << 20, None) == J.ERR_INVALID_ARG
+    assert L.jxlb_pipeline_create(0, None, None) == J.ERR_INVALID_ARG
+    assert L.jxlb_decode_frame_sections(None, b"x", 1, None, 0, None) == J.ERR_INVALID_ARG
+    assert L.jxlb_upsample(None, None, 1, 1, 1, 2, None, 2) == J.ERR_INVALID_ARG
+    assert L.jxlb_pipeline_submit(None, None, 0, 0, 0, None, 0, 0) == J.ERR_INVALID_ARG
+    assert L.jxlb_pipeline_release_output(None, None) == J.ERR_INVALID_ARG
+    assert L.jxlb_pipeline_workers(None) == 0 and L.jxlb_pipeline_launch_count(None) == 0
+    if not torch.cuda.is_available():
+        assert L.jxlb_decoder_create_ex(0, 0, ctypes.byref(h)) == J.ERR_CUDA and not h.value
+        assert L.jxlb_pipeline_create(0, None, ctypes.byref(h)) == J.ERR_CUDA and not h.value

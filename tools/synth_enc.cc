@@ -576,7 +576,297 @@ struct Args {
   bool lf_frame = false;  // put the LF image into a separate Modular LF frame (frame type 1, lf_level 1)
   uint32_t epf_iters = 2; // edge-preserving filter iterations (0..3); 2 = the all-default restoration filter
   uint32_t hf_presets = 1; // HF presets (hf_pass.rs): group g uses preset g % N, each preset has its own (rotated) cluster map
+  std::string dump_raw;    // --modular: also write the source image (3 planes, int32 little endian) for lossless checks
+  bool modular = false;    // a Modular lossless frame (RGB 8 bit, RCT + default Squeeze, weighted predictor) instead of VarDCT
 };
+
+// ---- Modular lossless frame (BASELINE config #4): forward RCT (YCoCg, type 6), forward Squeeze with the default
+// parameter schedule (jxl-modular/src/transform.rs:285-341), channels split into the global / LF-group / pass-group
+// streams the decoder expects (jxl-modular/src/image.rs:187-345), every stream coded with the weighted predictor under a
+// WP-error context chain. Lossless by construction: the decoder's inverse transforms undo these exactly.
+struct MChan {
+  Plane2D p;
+  int hshift = 0, vshift = 0;
+};
+
+int32_t sq_tendency(int32_t a, int32_t b, int32_t c) {  // squeeze.rs:1104-1137
+  if (a >= b && b >= c) {
+    int32_t x = (4 * a - 3 * c - b + 6) / 12;
+    if (x - (x & 1) > 2 * (a - b)) x = 2 * (a - b) + 1;
+    if (x + (x & 1) > 2 * (b - c)) x = 2 * (b - c);
+    return x;
+  } else if (a <= b && b <= c) {
+    int32_t x = (4 * a - 3 * c - b - 6) / 12;
+    if (x + (x & 1) < 2 * (a - b)) x = 2 * (a - b) - 1;
+    if (x - (x & 1) < 2 * (b - c)) x = 2 * (b - c);
+    return x;
+  }
+  return 0;
+}
+
+// Forward of inverse_h / inverse_v (squeeze.rs:59-120, 803-862): avg = first - diff / 2 (truncating), residual =
+// diff - tendency(previous second, avg, next avg).
+void forward_squeeze(const MChan& in, bool horizontal, MChan* avg, MChan* res) {
+  const uint32_t w = in.p.w, h = in.p.h;
+  *avg = in;
+  *res = in;
+  if (horizontal) {
+    avg->p.w = (w + 1) / 2, res->p.w = w / 2;
+    avg->hshift = res->hshift = in.hshift + 1;
+  } else {
+    avg->p.h = (h + 1) / 2, res->p.h = h / 2;
+    avg->vshift = res->vshift = in.vshift + 1;
+  }
+  avg->p.v.assign(size_t(avg->p.w) * avg->p.h, 0);
+  res->p.v.assign(size_t(res->p.w) * res->p.h, 0);
+  const uint32_t lines = horizontal ? h : w, len = horizontal ? w : h;
+  const uint32_t alen = (len + 1) / 2, rlen = len / 2;
+  std::vector<int32_t> line(len), av(alen);
+  for (uint32_t l = 0; l < lines; ++l) {
+    for (uint32_t i = 0; i < len; ++i) line[i] = horizontal ? in.p.at(i, l) : in.p.at(l, i);
+    for (uint32_t i = 0; i < rlen; ++i) {
+      const int32_t diff = line[2 * i] - line[2 * i + 1];
+      av[i] = line[2 * i] - diff / 2;
+    }
+    if (len & 1) av[alen - 1] = line[len - 1];
+    for (uint32_t i = 0; i < alen; ++i) (horizontal ? avg->p.v[size_t(l) * alen + i] : avg->p.v[size_t(i) * avg->p.w + l]) = av[i];
+    int32_t left = av[0];
+    for (uint32_t i = 0; i < rlen; ++i) {
+      const int32_t next_avg = i + 1 < alen ? av[i + 1] : av[i];
+      const int32_t diff = line[2 * i] - line[2 * i + 1];
+      const int32_t r = diff - sq_tendency(left, av[i], next_avg);
+      (horizontal ? res->p.v[size_t(l) * rlen + i] : res->p.v[size_t(i) * res->p.w + l]) = r;
+      left = line[2 * i + 1];
+    }
+  }
+}
+
+struct SqStep {
+  bool horizontal, in_place;
+  uint32_t begin_c, num_c;
+};
+
+int encode_modular(const Args& a) {
+  const uint32_t W = a.width, H = a.height, gd = 256;
+  const uint32_t gcols = (W + gd - 1) / gd, grows = (H + gd - 1) / gd, num_groups = gcols * grows;
+  const uint32_t lcols = (W + 2047) / 2048, lrows = (H + 2047) / 2048, num_lf = lcols * lrows;
+  if (num_groups == 1) fprintf(stderr, "single-group frames are not produced by this tool\n"), exit(2);
+  std::mt19937 rng(a.seed);
+  auto uni = [&](double lo, double hi) { return lo + (hi - lo) * (double(rng()) / 4294967296.0); };
+  // ---- content: smooth colour fields, a few hard edges and sensor-like noise, 8 bit ----
+  std::vector<MChan> ch(3);
+  {
+    const double fx = uni(0.002, 0.006), fy = uni(0.002, 0.006), gx = uni(0.03, 0.08), gy = uni(0.03, 0.08), ph = uni(0, 6.28);
+    for (int c = 0; c < 3; ++c) ch[c].p.w = W, ch[c].p.h = H, ch[c].p.v.resize(size_t(W) * H);
+    for (uint32_t y = 0; y < H; ++y)
+      for (uint32_t x = 0; x < W; ++x) {
+        const double base = 0.5 + 0.3 * sin(fx * x + ph) * cos(fy * y) + 0.08 * sin(gx * x + gy * y);
+        const bool edge = ((x / 160 + y / 120) % 5) == 0;
+        const double n = (double(rng() & 0xffff) / 65536.0 - 0.5) * 6.0;
+        const double r = base * 255.0 + (edge ? 40.0 : 0.0) + n;
+        const double g = (0.9 * base + 0.05 * cos(gx * x * 0.5)) * 255.0 + n * 0.8;
+        const double b = (0.7 * base + 0.2 * sin(fy * y * 3.0 + 1.0)) * 255.0 - (edge ? 25.0 : 0.0) + n * 1.1;
+        auto clamp8 = [](double v) { return int32_t(std::min(255.0, std::max(0.0, std::floor(v + 0.5)))); };
+        ch[0].p.v[size_t(y) * W + x] = clamp8(r);
+        ch[1].p.v[size_t(y) * W + x] = clamp8(g);
+        ch[2].p.v[size_t(y) * W + x] = clamp8(b);
+      }
+  }
+  if (!a.dump_raw.empty()) {
+    FILE* rf = fopen(a.dump_raw.c_str(), "wb");
+    if (!rf) return perror("fopen"), 1;
+    for (int c = 0; c < 3; ++c) fwrite(ch[c].p.v.data(), 4, ch[c].p.v.size(), rf);
+    fclose(rf);
+  }
+  // ---- forward RCT type 6 (rct.rs:87-140 inverse: tmp = Y - (Cg >> 1); G = Cg + tmp; B = tmp - (Co >> 1); R = B + Co) ----
+  for (size_t i = 0; i < size_t(W) * H; ++i) {
+    const int32_t r = ch[0].p.v[i], g = ch[1].p.v[i], b = ch[2].p.v[i];
+    const int32_t co = r - b, tmp = b + (co >> 1), cg = g - tmp, yy = tmp + (cg >> 1);
+    ch[0].p.v[i] = yy, ch[1].p.v[i] = co, ch[2].p.v[i] = cg;
+  }
+  // ---- forward Squeeze, default parameters (transform.rs:285-341) ----
+  std::vector<SqStep> steps;
+  {
+    uint32_t w = W, h = H;
+    steps.push_back({true, false, 1, 2});
+    steps.push_back({false, false, 1, 2});
+    if (h >= w && h > 8) {
+      steps.push_back({false, true, 0, 3});
+      h = (h + 1) / 2;
+    }
+    while (w > 8 || h > 8) {
+      if (w > 8) steps.push_back({true, true, 0, 3}), w = (w + 1) / 2;
+      if (h > 8) steps.push_back({false, true, 0, 3}), h = (h + 1) / 2;
+    }
+  }
+  for (const SqStep& sp : steps) {
+    std::vector<MChan> residu;
+    for (uint32_t c = sp.begin_c; c < sp.begin_c + sp.num_c; ++c) {
+      MChan avg, res;
+      forward_squeeze(ch[c], sp.horizontal, &avg, &res);
+      ch[c] = std::move(avg);
+      residu.push_back(std::move(res));
+    }
+    if (sp.in_place) ch.insert(ch.begin() + sp.begin_c + sp.num_c, residu.begin(), residu.end());
+    else ch.insert(ch.end(), residu.begin(), residu.end());
+  }
+  // ---- streams (image.rs:187-345): global prefix, then by shift into LF groups (shift >= 3) or pass groups ----
+  size_t nglobal = 0;
+  while (nglobal < ch.size() && ch[nglobal].p.w <= gd && ch[nglobal].p.h <= gd) ++nglobal;
+  std::vector<std::vector<Plane2D>> lf_streams(num_lf), pg_streams(num_groups);
+  auto crop = [](const Plane2D& p, uint32_t x0, uint32_t y0, uint32_t w, uint32_t h) {
+    Plane2D o;
+    o.w = w, o.h = h;
+    o.v.resize(size_t(w) * h);
+    for (uint32_t y = 0; y < h; ++y)
+      for (uint32_t x = 0; x < w; ++x) o.v[size_t(y) * w + x] = p.at(x0 + x, y0 + y);
+    return o;
+  };
+  for (size_t i = nglobal; i < ch.size(); ++i) {
+    const MChan& c = ch[i];
+    const bool lf = c.hshift >= 3 && c.vshift >= 3;
+    const uint32_t gw = lf ? gd >> (c.hshift - 3) : gd >> c.hshift, gh = lf ? gd >> (c.vshift - 3) : gd >> c.vshift;
+    if (!gw || !gh) fprintf(stderr, "channel shift too large\n"), exit(1);
+    const uint32_t nx = lf ? lcols : gcols, ny = lf ? lrows : grows;
+    for (uint32_t gy = 0; gy < ny; ++gy)
+      for (uint32_t gx = 0; gx < nx; ++gx) {
+        const uint32_t x0 = gx * gw, y0 = gy * gh;
+        if (x0 >= c.p.w || y0 >= c.p.h) continue;
+        Plane2D part = crop(c.p, x0, y0, std::min(gw, c.p.w - x0), std::min(gh, c.p.h - y0));
+        (lf ? lf_streams[gy * nx + gx] : pg_streams[gy * nx + gx]).push_back(std::move(part));
+      }
+  }
+  // ---- tree: chain on the weighted predictor's max error, WP leaves; tokens of every stream ----
+  std::vector<TreeNode> nodes;
+  {
+    const int nthr = int(sizeof(kWpThresholds) / sizeof(kWpThresholds[0]));
+    for (int i = 0; i < nthr; ++i) nodes.push_back({15, kWpThresholds[i], 2 * i + 1, 2 * i + 2, 0}), nodes.push_back({-1, 0, 0, 0, 6});
+    // BFS order: node 2i is the decision, 2i+1 its "greater" leaf, 2i+2 the next decision; the chain ends in a leaf
+    nodes.push_back({-1, 0, 0, 0, 6});
+    // rebuild in BFS order: decision i at index 2i, leaf at 2i+1, next decision at 2i+2
+    std::vector<TreeNode> bfs;
+    for (int i = 0; i < nthr; ++i) {
+      bfs.push_back({15, kWpThresholds[i], 2 * i + 1, 2 * i + 2, 0});
+      bfs.push_back({-1, 0, 0, 0, 6});
+    }
+    bfs.push_back({-1, 0, 0, 0, 6});
+    nodes = bfs;
+  }
+  TreeEval tree(nodes);
+  std::vector<Token> all;
+  std::vector<Token> global_tokens;
+  std::vector<std::vector<Token>> lf_tokens(num_lf), pg_tokens(num_groups);
+  {
+    std::vector<Plane2D> g;
+    for (size_t i = 0; i < nglobal; ++i) g.push_back(ch[i].p);
+    modular_tokens(tree, g, 0, &global_tokens);
+    all.insert(all.end(), global_tokens.begin(), global_tokens.end());
+  }
+  for (uint32_t g = 0; g < num_lf; ++g) {
+    modular_tokens(tree, lf_streams[g], int32_t(1 + num_lf + g), &lf_tokens[g]);
+    all.insert(all.end(), lf_tokens[g].begin(), lf_tokens[g].end());
+  }
+  for (uint32_t g = 0; g < num_groups; ++g) {
+    modular_tokens(tree, pg_streams[g], int32_t(1 + 3 * num_lf + 17 + g), &pg_tokens[g]);
+    all.insert(all.end(), pg_tokens[g].begin(), pg_tokens[g].end());
+  }
+  // ---- sections ----
+  std::vector<BitWriter> sections(1 + num_lf + 1 + num_groups);
+  EntropyEncoder enc;
+  {
+    BitWriter& w = sections[0];
+    w.write(1, 1);  // LfChannelDequantization all_default
+    w.write(1, 1);  // global MA tree present
+    write_tree(w, tree);
+    std::vector<uint8_t> map(size_t(tree.num_leaves()));
+    for (size_t i = 0; i < map.size(); ++i) map[i] = uint8_t(i);
+    enc.write_header(w, all, uint32_t(map.size()), map);
+    // GlobalModular header (lib.rs:117-125): global tree, default WP, two transforms
+    w.write(1, 1);
+    w.write(1, 1);
+    write_u32(w, 2, 4, 0);  // nb_transforms = 2
+    w.write(2, 0);          // RCT
+    write_u32(w, 0, 3, 0);  //   begin_c = 0
+    write_u32(w, 0, 0, 0);  //   rct_type = 6
+    w.write(2, 2);          // Squeeze
+    write_u32(w, 0, 0, 0);  //   num_sq = 0: default parameters
+    enc.write_tokens(w, global_tokens);
+    w.pad();
+  }
+  for (uint32_t g = 0; g < num_lf; ++g) {
+    if (lf_streams[g].empty()) continue;
+    BitWriter& w = sections[1 + g];
+    write_modular_header(w);
+    enc.write_tokens(w, lf_tokens[g]);
+    w.pad();
+  }
+  for (uint32_t g = 0; g < num_groups; ++g) {
+    if (pg_streams[g].empty()) continue;
+    BitWriter& w = sections[2 + num_lf + g];
+    write_modular_header(w);
+    enc.write_tokens(w, pg_tokens[g]);
+    w.pad();
+  }
+  // ---- codestream ----
+  BitWriter cs;
+  cs.write(16, 0x0aff);
+  cs.write(1, 0);
+  auto write_dim = [&](uint32_t v) {
+    if (v <= 512) write_u32(cs, 0, 9, v - 1);
+    else if (v <= 8192) write_u32(cs, 1, 13, v - 1);
+    else write_u32(cs, 2, 18, v - 1);
+  };
+  write_dim(H);
+  cs.write(3, 0);
+  write_dim(W);
+  cs.write(1, 0);  // ImageMetadata all_default = 0
+  cs.write(1, 0);  // extra_fields
+  cs.write(1, 0);  // integer samples
+  cs.write(2, 0);  // 8 bits
+  cs.write(1, 1);  // modular_16bit_buffers
+  cs.write(2, 0);  // no extra channels
+  cs.write(1, 0);  // xyb_encoded = 0
+  cs.write(1, 1);  // ColourEncoding all_default (sRGB)
+  cs.write(2, 0);  // extensions
+  cs.write(1, 1);  // default_m
+  cs.pad();
+  // frame header (header.rs:9-134): Regular, Modular, no filters
+  cs.write(1, 0);      // all_default
+  cs.write(2, 0);      // Regular
+  cs.write(1, 1);      // Modular
+  cs.write(2, 0);      // flags = 0
+  cs.write(1, 0);      // do_ycbcr
+  cs.write(2, 0);      // upsampling = 1
+  cs.write(2, 1);      // group_size_shift = 1 (256)
+  cs.write(2, 0);      // num_passes = 1
+  cs.write(1, 0);      // have_crop
+  cs.write(2, 0);      // blend mode Replace
+  cs.write(1, 1);      // is_last
+  cs.write(2, 0);      // name: empty
+  cs.write(1, 0);      // restoration filter: not all_default
+  cs.write(1, 0);      //   gab_enabled = 0
+  cs.write(2, 0);      //   epf iters = 0
+  cs.write(2, 0);      //   extensions
+  cs.write(2, 0);      // frame extensions
+  cs.write(1, 0);      // TOC not permuted
+  cs.pad();
+  for (const BitWriter& sct : sections) {
+    const uint32_t sz = uint32_t(sct.bytes.size());
+    if (sz < 1024) write_u32(cs, 0, 10, sz);
+    else if (sz < 17408) write_u32(cs, 1, 14, sz - 1024);
+    else if (sz < 4211712) write_u32(cs, 2, 22, sz - 17408);
+    else write_u32(cs, 3, 30, sz - 4211712);
+  }
+  cs.pad();
+  for (const BitWriter& sct : sections) cs.append(sct);
+  FILE* f = fopen(a.out.c_str(), "wb");
+  if (!f) return perror("fopen"), 1;
+  fwrite(cs.bytes.data(), 1, cs.bytes.size(), f);
+  fclose(f);
+  fprintf(stderr, "%s: %ux%u Modular lossless, %zu bytes (%.3f bit/px), %zu channels after Squeeze (%zu global), groups %u, LF groups %u\n",
+          a.out.c_str(), W, H, cs.bytes.size(), 8.0 * cs.bytes.size() / (double(W) * H), ch.size(), nglobal, num_groups, num_lf);
+  return 0;
+}
 
 }  // namespace
 
@@ -595,9 +885,12 @@ int main(int argc, char** argv) {
     else if (s == "--colour") a.colour = next();
     else if (s == "--epf-iters") a.epf_iters = uint32_t(atoi(next().c_str()));
     else if (s == "--hf-presets") a.hf_presets = std::max(1, atoi(next().c_str()));
+    else if (s == "--modular") a.modular = true;
+    else if (s == "--dump-raw") a.dump_raw = next();
     else if (s == "-o") a.out = next();
     else fprintf(stderr, "unknown arg %s\n", s.c_str()), exit(2);
   }
+  if (a.modular) return encode_modular(a);
   std::mt19937 rng(a.seed);
   auto uni = [&](double lo, double hi) { return lo + (hi - lo) * (double(rng()) / 4294967296.0); };
   const uint32_t W = a.width, H = a.height;
