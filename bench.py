@@ -271,7 +271,10 @@ def run_ours(args, rank, world, local_rank):
     hf_lanes = int(env_knob) if env_knob is not None else (HF_STREAMS_PER_CTA if args.hf_lanes == "auto" else int(args.hf_lanes))
     desc, frames, (w, h) = load_workload(args.workload, args.frames_per_step)
     px_per_frame = w * h
-    pipe = J.Pipeline(local_rank, workers=args.contexts, heavy_frames=args.heavy_frames, hf_streams_per_cta=hf_lanes)
+    workers = args.contexts or (64 if "mod" in args.workload else 96)
+    heavy = args.heavy_frames or (26 if "mod" in args.workload else 20)
+    args.contexts, args.heavy_frames = workers, heavy
+    pipe = J.Pipeline(local_rank, workers=workers, heavy_frames=heavy, hf_streams_per_cta=hf_lanes, batch_streams=args.batch_streams)
     # encoded frames resident in HBM ("inputs already resident"): one preloaded slot per distinct frame
     distinct = {}
     slots = []
@@ -451,7 +454,7 @@ def run_ours(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if "mod" not in args.workload else "i32",
         "data": "synthetic" if "synth" in args.workload else "real-file mosaic",
         "config": {"workload": desc, "frames_per_step_per_gpu": len(frames), "pipeline_workers_per_gpu": pipe_workers(args),
-                   "heavy_frames_per_gpu": args.heavy_frames,
+                   "heavy_frames_per_gpu": args.heavy_frames, "lf_batch_streams": args.batch_streams,
                    "cache": "inputs+planes per step (>= 33 MP x 24 B) exceed L2 (126 MB); no explicit L2 flush",
                    "step_barrier": "before and after the K timed steps; frames flow through the in-library pipeline",
                    "hf_streams_per_cta": hf_lanes, "cpu_affinity": "GPU-local CPUs" if cpus else "unchanged"},
@@ -629,8 +632,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="synth8k", help="synth8k | synth4k | mosaic8k | file:PATH")
-    ap.add_argument("--contexts", type=int, default=40, help="pipeline workers (decoder contexts = CUDA streams) per GPU")
-    ap.add_argument("--heavy-frames", type=int, default=10, help="frames allowed past the LF stage at once (HBM slabs)")
+    ap.add_argument("--contexts", type=int, default=0, help="pipeline workers = frames in flight per GPU (0: 96, Modular workloads 64)")
+    ap.add_argument("--heavy-frames", type=int, default=0,
+                    help="heavy slots (HBM slab + CUDA stream) per GPU (0: 20, Modular workloads 26)")
+    ap.add_argument("--batch-streams", type=int, default=6, help="CUDA streams of the LF batch service")
     ap.add_argument("--gather-contexts", type=int, default=8)
     ap.add_argument("--frames-per-step", type=int, default=48, help="independent frames decoded per step per GPU")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)

@@ -186,16 +186,19 @@ int32_t jxlb_rct_inverse(jxlb_decoder* dec, int32_t* const planes[3], uint32_t w
 /* ---- Frame pipeline: many independent frames through one GPU ----
  * Replaces the reference's frame-level concurrency: jxl-oxide-cli renders keyframes through rayon's par_iter
  * (crates/jxl-oxide-cli/src/decode.rs:285-320), jxl-render spawns reference / LF frames eagerly
- * (crates/jxl-render/src/lib.rs:496-509). `workers` decoder contexts (one CUDA stream + one host thread each, threads
- * pinned to the CPUs local to the GPU) take frames from one queue; at most `heavy_frames` of them are past the LF
- * stage at any time (each of those owns a pre-allocated slab of HBM for its full-resolution planes), so HBM use is
- * heavy_frames x ~25 B/px whatever `workers` is. Frames are reported in completion order. */
+ * (crates/jxl-render/src/lib.rs:496-509). `workers` frames are in flight (one host thread each, pinned to the CPUs
+ * local to the GPU). A frame's LF stage - two long, narrow entropy kernels - holds no CUDA stream: it rides in the
+ * kernels of a batch service that merges the LF streams of all frames that are ready. Past the LF stage a frame holds
+ * one of `heavy_frames` slots (a pre-allocated slab of HBM for its full-resolution planes + a CUDA stream), so HBM use
+ * is heavy_frames x ~25 B/px whatever `workers` is. Frames are reported in completion order. */
 typedef struct jxlb_pipeline jxlb_pipeline;
 typedef struct {
-  int32_t workers;            /* 0 = default (32) */
-  int32_t heavy_frames;       /* 0 = default (8) */
+  int32_t workers;            /* frames in flight (host threads); 0 = default (64) */
+  int32_t heavy_frames;       /* heavy slots = slabs = CUDA streams for everything but the LF stage; 0 = default (16) */
   int32_t hf_streams_per_cta; /* 0 = library default, see jxlb_set_hf_streams_per_cta */
   int32_t no_affinity;        /* 1 = leave the worker threads' CPU affinity alone */
+  int32_t batch_streams;      /* CUDA streams of the LF batch service; 0 = default (6). heavy_frames + batch_streams
+                                 should stay below 32, the number of hardware queues a process can use concurrently */
 } jxlb_pipeline_config;
 int32_t jxlb_pipeline_create(int32_t cuda_device, const jxlb_pipeline_config* cfg, jxlb_pipeline** out);
 void jxlb_pipeline_destroy(jxlb_pipeline* p);

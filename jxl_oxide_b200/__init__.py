@@ -67,7 +67,7 @@ class _Section(ctypes.Structure):
 
 
 class _PipelineConfig(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_int32) for n in ("workers", "heavy_frames", "hf_streams_per_cta", "no_affinity")]
+    _fields_ = [(n, ctypes.c_int32) for n in ("workers", "heavy_frames", "hf_streams_per_cta", "no_affinity", "batch_streams")]
 
 
 class EpfParams(ctypes.Structure):
@@ -382,10 +382,10 @@ class Pipeline:
 
     OUT_NONE, OUT_PLANAR_F32, OUT_U8, OUT_U16 = 0, 1, 2, 3
 
-    def __init__(self, device=0, workers=0, heavy_frames=0, hf_streams_per_cta=0, no_affinity=False):
+    def __init__(self, device=0, workers=0, heavy_frames=0, hf_streams_per_cta=0, no_affinity=False, batch_streams=0):
         self._L = load_library()
         self.device = device
-        cfg = _PipelineConfig(int(workers), int(heavy_frames), int(hf_streams_per_cta), int(bool(no_affinity)))
+        cfg = _PipelineConfig(int(workers), int(heavy_frames), int(hf_streams_per_cta), int(bool(no_affinity)), int(batch_streams))
         h = ctypes.c_void_p()
         rc = self._L.jxlb_pipeline_create(device, ctypes.byref(cfg), ctypes.byref(h))
         if rc != OK:

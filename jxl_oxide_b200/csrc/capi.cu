@@ -43,6 +43,19 @@ DevView raw_view(void* p, uint32_t w, uint32_t h, uint32_t stride) {
 }  // namespace
 
 namespace jxlb {
+jxlb_decoder* create_decoder_internal(int32_t device, uint64_t mem_limit, bool own_stream, int32_t* code) {
+  auto dec = std::make_unique<jxlb_decoder>();
+  try {
+    dec->be.reset(new CudaBackend(device, own_stream));
+    dec->be->set_mem_limit(mem_limit);
+  } catch (const Error& e) {
+    if (code) *code = e.code;
+    return nullptr;
+  }
+  if (code) *code = JXLB_OK;
+  return dec.release();
+}
+
 int32_t decode_resident(jxlb_decoder* dec, const uint8_t* cs, size_t size, const uint8_t* dptr, const jxlb_options* opt) {
   if (!dec || !cs || !dptr) return JXLB_ERR_INVALID_ARG;
   return guarded(dec, [&] {
@@ -85,16 +98,9 @@ extern "C" {
 
 int32_t jxlb_decoder_create_ex(int32_t device, uint64_t mem_limit_bytes, jxlb_decoder** out) {
   if (!out) return JXLB_ERR_INVALID_ARG;
-  *out = nullptr;
-  auto dec = std::make_unique<jxlb_decoder>();
-  try {
-    dec->be.reset(new CudaBackend(device));
-    dec->be->set_mem_limit(mem_limit_bytes);
-  } catch (const Error& e) {
-    return e.code;
-  }
-  *out = dec.release();
-  return JXLB_OK;
+  int32_t code = JXLB_OK;
+  *out = create_decoder_internal(device, mem_limit_bytes, true, &code);
+  return code;
 }
 
 int32_t jxlb_decoder_create(int32_t device, jxlb_decoder** out) { return jxlb_decoder_create_ex(device, 0, out); }

@@ -26,6 +26,8 @@ struct jxlb_decoder {
 };
 
 namespace jxlb {
+// A decoder without a CUDA stream of its own (pipeline workers: CudaBackend(own_stream = false)); nullptr + code on failure.
+jxlb_decoder* create_decoder_internal(int32_t device, uint64_t mem_limit, bool own_stream, int32_t* code);
 // Decodes a codestream whose bytes already live in HBM at `dptr` (zero-padded like upload_resident() does) and on the
 // host at `cs` (the planner parses headers, TOC and entropy-code tables from the host copy).
 int32_t decode_resident(jxlb_decoder* dec, const uint8_t* cs, size_t size, const uint8_t* dptr, const jxlb_options* opt);

@@ -23,13 +23,13 @@ void upload_sec_large(const float* host224);  // kernels/vardct.cu
       fail(kErrCuda, std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " #expr);        \
   } while (0)
 
-CudaBackend::CudaBackend(int device) : device_(device) {
+CudaBackend::CudaBackend(int device, bool own_stream) : device_(device), own_stream_(own_stream) {
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0)
     fail(kErrCuda, "no CUDA device available: the jxl_oxide_b200 hot path has no CPU fallback");
   CUDA_CHECK(cudaSetDevice(device_));
-  CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  if (own_stream_) CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&sync_event_, cudaEventBlockingSync | cudaEventDisableTiming));
   stage_cap_ = size_t(2) << 20;
   CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_stage_), stage_cap_, cudaHostAllocDefault));
@@ -42,6 +42,7 @@ CudaBackend::CudaBackend(int device) : device_(device) {
     h_flag_ = static_cast<volatile uint32_t*>(f);
     *h_flag_ = 0;
   }
+  ensure_static_tables();
   // A private stream-ordered pool per decoder: freed planes are reused by this decoder's next frame
   // (release threshold = never trim), and an allocation never has to wait on another decoder's
   // stream the way reuse inside the shared default pool can.
@@ -72,10 +73,13 @@ CudaBackend::~CudaBackend() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (auto& kv : planes_)
-    if (!(arena_base_ && kv.second.ptr >= static_cast<void*>(arena_base_) && kv.second.ptr < static_cast<void*>(arena_base_ + arena_cap_)))
+    if (!(arena_base_ && kv.second.ptr >= static_cast<void*>(arena_base_) && kv.second.ptr < static_cast<void*>(arena_base_ + arena_cap_)) &&
+        !in_lf_arena(kv.second.ptr))
       cudaFree(kv.second.ptr);
-  for (void* p : temps_) cudaFree(p);
-  if (d_codestream_) cudaFreeAsync(d_codestream_, stream_);
+  for (void* p : temps_)
+    if (!in_lf_arena(p)) cudaFree(p);
+  for (void* p : deferred_free_) cudaFree(p);
+  if (d_codestream_ && !in_lf_arena(d_codestream_) && stream_) cudaFreeAsync(d_codestream_, stream_);
   if (d_natural_orders_) cudaFree(d_natural_orders_);
   if (d_dequant_) cudaFree(d_dequant_);
   if (d_dequant_default_) cudaFree(d_dequant_default_);
@@ -85,8 +89,56 @@ CudaBackend::~CudaBackend() {
   if (h_result_) cudaFreeHost(h_result_);
   if (h_input_) cudaFreeHost(h_input_);
   if (h_flag_) cudaFreeHost(const_cast<uint32_t*>(h_flag_));
-  if (stream_) cudaStreamDestroy(stream_);
+  if (stream_ && own_stream_) cudaStreamDestroy(stream_);
+  if (lf_arena_) cudaFree(lf_arena_);
   if (pool_ && !std::getenv("JXLB_SHARED_POOL")) cudaMemPoolDestroy(pool_);
+}
+
+cudaStream_t CudaBackend::S() {
+  if (!stream_) {
+    // A pipeline decoder has no stream of its own: the LF stage runs through the batch service, everything else on the
+    // stream of a heavy slot. Whatever needs a stream before the planner announces the heavy stage takes the slot now.
+    JXLB_CHECK(bool(on_need_stream), kErrCuda, "decoder has no CUDA stream");
+    on_need_stream();
+    JXLB_CHECK(stream_ != nullptr, kErrCuda, "no CUDA stream was leased to the decoder");
+    if (pending_cs_bytes_) {  // encoded bytes staged for a batch that never came
+      CUDA_CHECK(cudaMemcpyAsync(d_codestream_, h_input_, pending_cs_bytes_, cudaMemcpyHostToDevice, stream_));
+      pending_cs_bytes_ = 0;
+    }
+    for (void* p : deferred_free_) CUDA_CHECK(cudaFreeAsync(p, stream_));
+    deferred_free_.clear();
+  }
+  return stream_;
+}
+
+void CudaBackend::end_lease() {
+  if (!stream_ || own_stream_) return;
+  release_temps();
+  if (d_dequant_) {
+    dfree(d_dequant_);
+    d_dequant_ = nullptr;
+    cached_hfg_ = nullptr;
+  }
+  if (d_codestream_ && !in_lf_arena(d_codestream_)) {
+    CUDA_CHECK(cudaFreeAsync(d_codestream_, stream_));
+    d_codestream_ = nullptr;
+    codestream_cap_ = 0;
+  }
+  stream_ = nullptr;
+}
+
+void* CudaBackend::lf_arena_alloc(size_t bytes) {
+  if (!lf_arena_) {
+    const char* e = std::getenv("JXLB_LF_ARENA_MB");
+    lf_arena_cap_ = size_t(e ? std::atoi(e) : 64) << 20;
+    CUDA_CHECK(cudaSetDevice(device_));
+    CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&lf_arena_), lf_arena_cap_));
+  }
+  const size_t need = (bytes + 255) & ~size_t(255);
+  if (lf_arena_off_ + need > lf_arena_cap_) return nullptr;
+  void* p = lf_arena_ + lf_arena_off_;
+  lf_arena_off_ += need;
+  return p;
 }
 
 void CudaBackend::begin_heavy_stage(size_t bytes_hint) {
@@ -127,8 +179,11 @@ void* CudaBackend::dmalloc(size_t bytes) {
     }
     arena_spill_ += need;
   }
+  if (!stream_ && lf_service) {  // a pipeline decoder without a stream yet: LF-stage planes come from its own LF arena
+    if (void* q = lf_arena_alloc(std::max<size_t>(bytes, 16))) return q;
+  }
   CUDA_CHECK(cudaSetDevice(device_));
-  CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), pool_, stream_));
+  CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 16), pool_, S()));
   if (mem_limit_) {
     mem_in_use_ += bytes;
     alloc_sizes_[p] = bytes;
@@ -137,6 +192,11 @@ void* CudaBackend::dmalloc(size_t bytes) {
 }
 void CudaBackend::dfree(void* p) {
   if (!p) return;
+  if (in_lf_arena(p)) return;  // recycled as a whole at the next decode call
+  if (!stream_ && lf_service) {  // a pool allocation of the previous frame released before this frame has a stream
+    deferred_free_.push_back(p);
+    return;
+  }
   if (arena_base_ && p >= arena_base_ && p < arena_base_ + arena_cap_) return;  // the slab is reset as a whole
   if (mem_limit_) {
     auto it = alloc_sizes_.find(p);
@@ -145,7 +205,7 @@ void CudaBackend::dfree(void* p) {
       alloc_sizes_.erase(it);
     }
   }
-  CUDA_CHECK(cudaFreeAsync(p, stream_));
+  CUDA_CHECK(cudaFreeAsync(p, S()));
 }
 void* CudaBackend::upload_temp(const void* src, size_t bytes) {
   const size_t off = (stage_off_ + 15) & ~size_t(15);
@@ -156,14 +216,15 @@ void* CudaBackend::upload_temp(const void* src, size_t bytes) {
   }
   void* p = dmalloc(bytes);  // does not fit the staging block
   temps_.push_back(p);
-  if (bytes) CUDA_CHECK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, stream_));
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, S()));
   return p;
 }
 void* CudaBackend::stage_scratch(size_t bytes) {
-  flush_uploads();  // the range handed out must not be part of a later host -> device copy
+  if (stream_) flush_uploads();  // the range handed out must not be part of a later host -> device copy
   const size_t off = (stage_off_ + 15) & ~size_t(15);
   if (off + bytes <= stage_cap_) {
-    stage_off_ = stage_flushed_ = off + bytes;
+    stage_off_ = off + bytes;
+    if (stream_) stage_flushed_ = stage_off_;  // stream-less: the batch copies the whole block before its kernel
     return d_stage_ + off;
   }
   void* p = dmalloc(bytes);
@@ -171,14 +232,15 @@ void* CudaBackend::stage_scratch(size_t bytes) {
   return p;
 }
 void CudaBackend::flush_uploads() {
+  if (!stream_ && lf_service) return;  // stream-less LF stage: the batch service copies the block
   if (stage_off_ > stage_flushed_)
-    CUDA_CHECK(cudaMemcpyAsync(d_stage_ + stage_flushed_, h_stage_ + stage_flushed_, stage_off_ - stage_flushed_, cudaMemcpyHostToDevice, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(d_stage_ + stage_flushed_, h_stage_ + stage_flushed_, stage_off_ - stage_flushed_, cudaMemcpyHostToDevice, S()));
   stage_flushed_ = stage_off_;
 }
 void* CudaBackend::fetch_result(const void* dsrc, size_t bytes) {
   const size_t off = (result_off_ + 15) & ~size_t(15);
   JXLB_CHECK(off + bytes <= result_cap_, kErrUnsupported, "too many stream jobs in one launch for the result buffer");
-  CUDA_CHECK(cudaMemcpyAsync(h_result_ + off, dsrc, bytes, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(h_result_ + off, dsrc, bytes, cudaMemcpyDeviceToHost, S()));
   result_off_ = off + bytes;
   return h_result_ + off;
 }
@@ -187,13 +249,14 @@ void CudaBackend::release_temps() {
   temps_.clear();
 }
 void CudaBackend::sync() {
+  if (!stream_) return;  // a pipeline decoder between leases: nothing of it is queued anywhere
   // The stream writes a sequence number into a mapped host word and the host thread polls it (short spin, then
   // 50 us naps). Waiting inside the driver instead (cudaEventSynchronize, or the implicit wait of a pageable
   // cudaMemcpyAsync) was measured to return 14-27 ms late on average once 32-48 decoder threads wait at the same time
   // (profiles/r02_progress.md): the waits serialise on the driver. Here a waiting thread never enters the driver.
   flush_uploads();
   const uint32_t seq = ++sync_seq_;
-  launch_signal_word(const_cast<uint32_t*>(h_flag_), seq, stream_);
+  launch_signal_word(const_cast<uint32_t*>(h_flag_), seq, S());
   ++launches;
   uint32_t spins = 0;
   auto t0 = std::chrono::steady_clock::now();
@@ -207,7 +270,7 @@ void CudaBackend::sync() {
     std::this_thread::sleep_for(std::chrono::microseconds(50));
     if ((spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) {
       // a faulting kernel never writes the word: ask the driver from time to time
-      cudaError_t e = cudaStreamQuery(stream_);
+      cudaError_t e = cudaStreamQuery(S());
       if (e == cudaSuccess) break;
       if (e != cudaErrorNotReady) fail(kErrCuda, std::string("CUDA error: ") + cudaGetErrorString(e) + " while waiting for the stream");
       t0 = std::chrono::steady_clock::now();
@@ -250,6 +313,7 @@ TimeOrigin& time_origin() {
 }  // namespace
 
 void CudaBackend::begin_k(const char* name) {
+  S();  // a pipeline decoder takes its stream here at the latest
   flush_uploads();
   ++launches;
   if (!profile) return;
@@ -258,13 +322,13 @@ void CudaBackend::begin_k(const char* name) {
   t.name = name;
   CUDA_CHECK(cudaEventCreate(&t.e0));
   CUDA_CHECK(cudaEventCreate(&t.e1));
-  CUDA_CHECK(cudaEventRecord(t.e0, stream_));
+  CUDA_CHECK(cudaEventRecord(t.e0, S()));
   pending_.push_back(t);
 }
 
 void CudaBackend::end_k() {
   if (!profile || pending_.empty()) return;
-  CUDA_CHECK(cudaEventRecord(pending_.back().e1, stream_));
+  CUDA_CHECK(cudaEventRecord(pending_.back().e1, S()));
 }
 
 void CudaBackend::resolve_profile() {
@@ -298,6 +362,11 @@ void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
   CUDA_CHECK(cudaSetDevice(device_));
   stages.clear();  // stage snapshots belong to one decode call
   stage_dims.clear();
+  if (!stream_) {  // a new decode call of a pipeline decoder: its LF arena starts empty again
+    lf_arena_off_ = 0;
+    if (in_lf_arena(d_codestream_)) d_codestream_ = nullptr, codestream_cap_ = 0;
+    pending_cs_bytes_ = 0;
+  }
   if (resident_next_) {  // encoded bytes already live in HBM (jxlb_preload)
     active_cs_ = resident_next_;
     resident_next_ = nullptr;
@@ -305,15 +374,6 @@ void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
     return;
   }
   size_t need = ((size + 7) & ~size_t(7)) + 64;  // zero padding for the 64-bit bit reader
-  if (need > codestream_cap_) {
-    // Stream-ordered (re)allocation with headroom: cudaFree / cudaMalloc wait for the whole device - with dozens of
-    // decoders whose frames differ by a few bytes that was hundreds of device-wide stalls per run (measured: the
-    // host-bytes path 5x slower than the resident one).
-    if (d_codestream_) CUDA_CHECK(cudaFreeAsync(d_codestream_, stream_));
-    d_codestream_ = nullptr;
-    codestream_cap_ = std::max<size_t>(need + need / 2, size_t(1) << 20);
-    CUDA_CHECK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&d_codestream_), codestream_cap_, pool_, stream_));
-  }
   // through pinned memory: a pageable source makes cudaMemcpyAsync stage and wait inside the driver (measured: the
   // host-bytes path ran 5x slower than the resident one with 32 decoder threads; the copies serialise on the driver)
   if (need > input_cap_) {
@@ -324,7 +384,28 @@ void CudaBackend::set_codestream(const uint8_t* data, size_t size) {
   }
   std::memcpy(h_input_, data, size);
   std::memset(h_input_ + size, 0, need - size);
-  CUDA_CHECK(cudaMemcpyAsync(d_codestream_, h_input_, need, cudaMemcpyHostToDevice, stream_));
+  if (!stream_ && lf_service) {
+    // pipeline decoder: the device copy lives in the LF arena and is made by the first LF batch of the frame (or when
+    // the decoder gets its stream, whichever comes first)
+    if (void* q = lf_arena_alloc(need)) {
+      d_codestream_ = static_cast<uint8_t*>(q);
+      codestream_cap_ = need;
+      pending_cs_bytes_ = need;
+      active_cs_ = d_codestream_;
+      ensure_static_tables();
+      return;
+    }
+  }
+  if (need > codestream_cap_ || in_lf_arena(d_codestream_)) {
+    // Stream-ordered (re)allocation with headroom: cudaFree / cudaMalloc wait for the whole device - with dozens of
+    // decoders whose frames differ by a few bytes that was hundreds of device-wide stalls per run (measured: the
+    // host-bytes path 5x slower than the resident one).
+    if (d_codestream_ && !in_lf_arena(d_codestream_)) CUDA_CHECK(cudaFreeAsync(d_codestream_, S()));
+    d_codestream_ = nullptr;
+    codestream_cap_ = std::max<size_t>(need + need / 2, size_t(1) << 20);
+    CUDA_CHECK(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&d_codestream_), codestream_cap_, pool_, S()));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(d_codestream_, h_input_, need, cudaMemcpyHostToDevice, S()));
   active_cs_ = d_codestream_;
   ensure_static_tables();
 }
@@ -372,7 +453,7 @@ int CudaBackend::alloc_plane(uint32_t w, uint32_t h, bool zero) {
   r.h = h;
   size_t bytes = size_t(w) * h * 4;
   r.ptr = dmalloc(bytes);
-  if (zero) CUDA_CHECK(cudaMemsetAsync(r.ptr, 0, bytes, stream_));
+  if (zero) CUDA_CHECK(cudaMemsetAsync(r.ptr, 0, bytes, S()));
   int id = next_id_++;
   planes_[id] = r;
   return id;
@@ -403,16 +484,16 @@ void CudaBackend::download_rect(const View& v, void* dst) {
   if (!v.w || !v.h) return;
   DevView d = dev_view(v);
   if (d.stride == v.w)  // contiguous: one linear DMA
-    CUDA_CHECK(cudaMemcpyAsync(dst, d.ptr, size_t(v.w) * v.h * 4, cudaMemcpyDeviceToHost, stream_));
+    CUDA_CHECK(cudaMemcpyAsync(dst, d.ptr, size_t(v.w) * v.h * 4, cudaMemcpyDeviceToHost, S()));
   else
     CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(v.w) * 4, d.ptr, size_t(d.stride) * 4, size_t(v.w) * 4, v.h,
-                                 cudaMemcpyDeviceToHost, stream_));
+                                 cudaMemcpyDeviceToHost, S()));
   sync();
 }
 
 void CudaBackend::copy_rect(const View& src, const View& dst) {
   begin_k("copy_rect");
-  launch_copy_rect(dev_view(src), dev_view(dst), stream_);
+  launch_copy_rect(dev_view(src), dev_view(dst), S());
   end_k();
 }
 
@@ -823,24 +904,63 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
     temps_.push_back(d_trace);
     host_launch = host_now_ms();
   }
-  begin_k("modular_decode");
-  launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, all_staged, stream_, d_trace);
-  end_k();
-  const uint64_t* end = static_cast<const uint64_t*>(fetch_result(d_end, jobs.size() * 8));
-  const int* status = static_cast<const int*>(fetch_result(d_status, jobs.size() * 4));
-  const unsigned long long* trace = d_trace ? static_cast<const unsigned long long*>(fetch_result(d_trace, jobs.size() * 16)) : nullptr;
-  sync();
-  if (d_trace) {
-    const TimeOrigin& o = time_origin();
-    unsigned long long first = ~0ull, last = 0;
-    for (size_t i = 0; i < jobs.size(); ++i) {
-      first = std::min<unsigned long long>(first, trace[2 * i]);
-      last = std::max<unsigned long long>(last, trace[2 * i + 1]);
+  const uint64_t* end;
+  const int* status;
+  if (!stream_ && lf_service && !d_trace && jobs.size() <= 2048) {
+    // LF stage of a pipeline decoder: the launch joins the batch service's next kernel (several frames' streams in one
+    // launch on one of a few batch streams); this thread sleeps until that batch has run. No CUDA stream is held.
+    LfBatchItem item;
+    if (pending_cs_bytes_) {
+      item.up[item.num_up++] = {d_codestream_, h_input_, pending_cs_bytes_};
+      pending_cs_bytes_ = 0;
     }
-    timeline.push_back({"host:launch_to_return modular", host_launch - o.host_ms, host_now_ms() - o.host_ms});
-    timeline.push_back({"dev:modular_decode", (double(first) - double(o.dev_ns)) * 1e-6, (double(last) - double(o.dev_ns)) * 1e-6});
+    item.up[item.num_up++] = {d_stage_, h_stage_, stage_off_};
+    item.ref.cs = active_cs_;
+    item.ref.jobs = d_jobs;
+    item.ref.channels = d_chans;
+    item.ref.plans = d_plans;
+    item.ref.end_bits = d_end;
+    item.ref.status = d_status;
+    item.num_jobs = int(jobs.size());
+    item.smem_bytes = max_smem;
+    item.all_staged = all_staged;
+    uint8_t* h_end = h_result_;
+    uint8_t* h_status = h_result_ + ((jobs.size() * 8 + 15) & ~size_t(15));
+    JXLB_CHECK(size_t(h_status - h_result_) + jobs.size() * 4 <= result_cap_, kErrUnsupported, "too many stream jobs in one launch for the result buffer");
+    item.down[item.num_down++] = {h_end, d_end, jobs.size() * 8};
+    item.down[item.num_down++] = {h_status, d_status, jobs.size() * 4};
+    item.want_timing = profile;
+    lf_service->run(item);
+    ++launches;
+    if (profile) {
+      auto& acc = profile_acc["modular_decode"];
+      acc.first += 1;
+      acc.second += double(item.elapsed_ms);
+    }
+    stage_off_ = stage_flushed_ = 0;
+    result_off_ = 0;
+    end = reinterpret_cast<const uint64_t*>(h_end);
+    status = reinterpret_cast<const int*>(h_status);
+  } else {
+    begin_k("modular_decode");
+    launch_modular_decode(active_cs_, d_jobs, d_chans, d_plans, d_end, d_status, int(jobs.size()), max_smem, all_staged, S(), d_trace);
+    end_k();
+    end = static_cast<const uint64_t*>(fetch_result(d_end, jobs.size() * 8));
+    status = static_cast<const int*>(fetch_result(d_status, jobs.size() * 4));
+    const unsigned long long* trace = d_trace ? static_cast<const unsigned long long*>(fetch_result(d_trace, jobs.size() * 16)) : nullptr;
+    sync();
+    if (d_trace) {
+      const TimeOrigin& o = time_origin();
+      unsigned long long first = ~0ull, last = 0;
+      for (size_t i = 0; i < jobs.size(); ++i) {
+        first = std::min<unsigned long long>(first, trace[2 * i]);
+        last = std::max<unsigned long long>(last, trace[2 * i + 1]);
+      }
+      timeline.push_back({"host:launch_to_return modular", host_launch - o.host_ms, host_now_ms() - o.host_ms});
+      timeline.push_back({"dev:modular_decode", (double(first) - double(o.dev_ns)) * 1e-6, (double(last) - double(o.dev_ns)) * 1e-6});
+    }
+    CUDA_CHECK(cudaGetLastError());
   }
-  CUDA_CHECK(cudaGetLastError());
   release_temps();
   for (size_t i = 0; i < jobs.size(); ++i) {
     if (status[i] != kDevOk)
@@ -859,14 +979,38 @@ int CudaBackend::squeeze_inverse(const View& avg, const View& res, bool horizont
   if (!ow || !oh) return id;
   View ov{id, 0, 0, ow, oh};
   begin_k("squeeze_inverse");
-  launch_squeeze_inverse(dev_view(avg), dev_view(res), dev_view(ov), horizontal, stream_);
+  launch_squeeze_inverse(dev_view(avg), dev_view(res), dev_view(ov), horizontal, S());
   end_k();
   return id;
 }
 
+std::vector<int> CudaBackend::squeeze_inverse_many(const std::vector<std::pair<View, View>>& avg_res, bool horizontal) {
+  std::vector<int> ids;
+  std::vector<DevView> a, r, o;
+  for (const auto& p : avg_res) {
+    const View& avg = p.first;
+    const View& res = p.second;
+    const uint32_t ow = horizontal ? avg.w + res.w : avg.w, oh = horizontal ? avg.h : avg.h + res.h;
+    JXLB_CHECK(horizontal ? (res.h == avg.h || res.w == 0) : (res.w == avg.w || res.h == 0), kErrBitstream,
+               "squeeze residual size mismatch");
+    const int id = alloc_plane(std::max(ow, 1u), std::max(oh, 1u), false);
+    ids.push_back(id);
+    if (!ow || !oh) continue;
+    a.push_back(dev_view(avg));
+    r.push_back(dev_view(res));
+    o.push_back(dev_view(View{id, 0, 0, ow, oh}));
+  }
+  if (!o.empty()) {
+    begin_k("squeeze_inverse");
+    launch_squeeze_inverse_batch(a.data(), r.data(), o.data(), int(o.size()), horizontal, S());
+    end_k();
+  }
+  return ids;
+}
+
 void CudaBackend::rct_inverse(const View v[3], uint32_t rct_type) {
   begin_k("rct_inverse");
-  launch_rct_inverse(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), rct_type, stream_);
+  launch_rct_inverse(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), rct_type, S());
   end_k();
 }
 
@@ -878,11 +1022,11 @@ void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& 
   const uint32_t w = targets[0].w, h = targets[0].h;
   int* d_status = static_cast<int*>(dmalloc(4));
   uint8_t* d_mask = static_cast<uint8_t*>(dmalloc(size_t(w) * h));
-  CUDA_CHECK(cudaMemsetAsync(d_status, 0, 4, stream_));
+  CUDA_CHECK(cudaMemsetAsync(d_status, 0, 4, S()));
   DevView pal{};
   if (palette.plane >= 0) pal = dev_view(palette);  // absent when nb_colours == 0
   begin_k("palette_inverse");
-  launch_palette_inverse(pal, tv, int(targets.size()), int(t.nb_colours), int(bit_depth), int(t.nb_deltas), d_mask, d_status, stream_);
+  launch_palette_inverse(pal, tv, int(targets.size()), int(t.nb_colours), int(bit_depth), int(t.nb_deltas), d_mask, d_status, S());
   end_k();
   const int* num_delta_p = static_cast<const int*>(fetch_result(d_status, 4));
   sync();
@@ -900,7 +1044,7 @@ void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& 
     if (t.d_pred == 6) rows = static_cast<int32_t*>(dmalloc(targets.size() * ((5 * size_t(w) + 3) & ~size_t(3)) * 4));
     p.wp_rows = rows;
     begin_k("palette_delta");
-    launch_palette_delta(p, int(targets.size()), stream_);
+    launch_palette_delta(p, int(targets.size()), S());
     end_k();
     sync();
     if (rows) dfree(rows);
@@ -911,13 +1055,13 @@ void CudaBackend::palette_inverse(const View& palette, const std::vector<View>& 
 
 void CudaBackend::int_to_float(const View& v, const BitDepth& d) {
   begin_k("int_to_float");
-  launch_int_to_float(dev_view(v), d.bits_per_sample, d.exp_bits, d.float_sample, stream_);
+  launch_int_to_float(dev_view(v), d.bits_per_sample, d.exp_bits, d.float_sample, S());
   end_k();
 }
 
 void CudaBackend::modular_xyb_to_float(const View yxb[3], const float m[3]) {
   begin_k("modular_xyb");
-  launch_modular_xyb(dev_view(yxb[0]), dev_view(yxb[1]), dev_view(yxb[2]), m[0], m[1], m[2], stream_);
+  launch_modular_xyb(dev_view(yxb[0]), dev_view(yxb[1]), dev_view(yxb[2]), m[0], m[1], m[2], S());
   end_k();
 }
 
@@ -963,7 +1107,7 @@ void CudaBackend::build_block_info(VarDctState& st, const std::vector<BlockInfoJ
   void* scratch = dmalloc(build_block_info_scratch_bytes(int(jobs.size())));
   temps_.push_back(scratch);
   launch_build_block_info(dev_frame(st), d_jobs, int(jobs.size()), quant_mul_base, d_lut, epf.iters > 0 ? 1 : 0, d_status,
-                          scratch, stream_);
+                          scratch, S());
   end_k();
   const int* status = static_cast<const int*>(fetch_result(d_status, jobs.size() * 4));
   sync();
@@ -1046,16 +1190,16 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     d_blk_ctx = static_cast<uint32_t*>(dmalloc(size_t(st.bw) * st.bh * 4));
     temps_.push_back(d_blk_ctx);
     begin_k("hf_block_ctx");
-    launch_hf_block_ctx(dev_frame(st), p, d_blk_ctx, stream_);
+    launch_hf_block_ctx(dev_frame(st), p, d_blk_ctx, S());
     end_k();
   }
   begin_k("decode_hf");
   if (hf_streams_per_cta >= 64)
     launch_decode_hf_lanes(active_cs_, dev_frame(st), p, d_blk_ctx, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
-                           hf_streams_per_cta, stream_);
+                           hf_streams_per_cta, S());
   else
     launch_decode_hf(active_cs_, dev_frame(st), p, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
-                     hf_streams_per_cta > 0 ? hf_streams_per_cta : 16, stream_);
+                     hf_streams_per_cta > 0 ? hf_streams_per_cta : 16, S());
   end_k();
   const uint64_t* end = static_cast<const uint64_t*>(fetch_result(d_end, jobs.size() * 8));
   const int* status = static_cast<const int*>(fetch_result(d_status, jobs.size() * 4));
@@ -1078,7 +1222,7 @@ void CudaBackend::lf_dequant(VarDctState& st, const std::vector<LfDequantJob>& j
     dj.push_back({{j.rect.bx0, j.rect.by0, j.rect.bw, j.rect.bh}, {j.scale[0], j.scale[1], j.scale[2]}});
   const DevLfDequantJob* d = static_cast<const DevLfDequantJob*>(upload_temp(dj.data(), dj.size() * sizeof(DevLfDequantJob)));
   begin_k("lf_dequant");
-  launch_lf_dequant(dev_frame(st), d, int(dj.size()), stream_);
+  launch_lf_dequant(dev_frame(st), d, int(dj.size()), S());
   end_k();
 }
 
@@ -1088,7 +1232,7 @@ void CudaBackend::lf_chroma_from_luma(VarDctState& st) {
   float kx = g.base_correlation_x + (float(x_factor) / float(g.colour_factor));
   float kb = g.base_correlation_b + (float(b_factor) / float(g.colour_factor));
   begin_k("lf_cfl");
-  launch_lf_cfl(dev_frame(st), kx, kb, stream_);
+  launch_lf_cfl(dev_frame(st), kx, kb, S());
   end_k();
 }
 
@@ -1101,7 +1245,7 @@ void CudaBackend::lf_adaptive_smoothing(VarDctState& st) {
   float* tmp[3];
   for (int c = 0; c < 3; ++c) tmp[c] = static_cast<float*>(dmalloc(size_t(st.bw) * st.bh * 4));
   begin_k("lf_smooth");
-  launch_lf_smooth(dev_frame(st), tmp, lf_x, lf_y, lf_b, stream_);
+  launch_lf_smooth(dev_frame(st), tmp, lf_x, lf_y, lf_b, S());
   end_k();
   for (int c = 0; c < 3; ++c) {  // swap the smoothed planes in
     PlaneRec& r = planes_.at(st.lf[c]);
@@ -1125,12 +1269,12 @@ void CudaBackend::hf_dequant_cfl(VarDctState& st) {
         }
     if (use_default) {
       CUDA_CHECK(cudaMalloc(&d_dequant_default_, all.size() * 4));
-      CUDA_CHECK(cudaMemcpyAsync(d_dequant_default_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, stream_));
-      CUDA_CHECK(cudaStreamSynchronize(stream_));
+      CUDA_CHECK(cudaMemcpyAsync(d_dequant_default_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, S()));
+      CUDA_CHECK(cudaStreamSynchronize(S()));
     } else {
       if (d_dequant_) dfree(d_dequant_);
       d_dequant_ = static_cast<float*>(dmalloc(all.size() * 4));
-      CUDA_CHECK(cudaMemcpyAsync(d_dequant_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, stream_));
+      CUDA_CHECK(cudaMemcpyAsync(d_dequant_, all.data(), all.size() * 4, cudaMemcpyHostToDevice, S()));
       cached_hfg_ = st.hfg;
     }
   }
@@ -1155,14 +1299,14 @@ void CudaBackend::hf_dequant_cfl(VarDctState& st) {
     return;
   }
   begin_k("hf_dequant_cfl");
-  launch_hf_dequant_cfl(dev_frame(st), p, stream_);
+  launch_hf_dequant_cfl(dev_frame(st), p, S());
   end_k();
 }
 
 void CudaBackend::hf_transform(VarDctState& st) {
   void* scratch = dmalloc(hf_transform_scratch_bytes(st.bw, st.bh));
   begin_k("hf_transform");
-  launch_hf_transform(dev_frame(st), scratch, have_pending_dequant_ ? &pending_dequant_ : nullptr, stream_);
+  launch_hf_transform(dev_frame(st), scratch, have_pending_dequant_ ? &pending_dequant_ : nullptr, S());
   end_k();
   have_pending_dequant_ = false;
   dfree(scratch);
@@ -1177,7 +1321,7 @@ void CudaBackend::gaborish(const View v[3], const float weights[3][2]) {
     DevView ov = in;
     ov.ptr = out;
     begin_k("gaborish");
-    launch_gaborish(in, ov, weights[c][0], weights[c][1], stream_);
+    launch_gaborish(in, ov, weights[c][0], weights[c][1], S());
     end_k();
     dfree(r.ptr);
     r.ptr = out;
@@ -1211,7 +1355,7 @@ void CudaBackend::epf(const View v[3], const View& sigma, const EpfParams& p, bo
   bool in_alt = false;
   auto run = [&](int step) {
     begin_k("epf_step");
-    launch_epf_step(in_alt ? alt : cur, in_alt ? cur : alt, d_sigma, sigma_stride, dp, step, stream_);
+    launch_epf_step(in_alt ? alt : cur, in_alt ? cur : alt, d_sigma, sigma_stride, dp, step, S());
     end_k();
     in_alt = !in_alt;
   };
@@ -1276,7 +1420,7 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
     p.col.pq_intensity_target = 0.0f;
   }
   begin_k("filters_fused");
-  launch_filters_fused(in, out, p, stream_);
+  launch_filters_fused(in, out, p, S());
   end_k();
   for (int c = 0; c < 3; ++c) {
     PlaneRec& r = planes_.at(v[c].plane);
@@ -1295,7 +1439,7 @@ void CudaBackend::blend_patches(const std::vector<PatchJob>& jobs) {
     if (batch.empty()) return;
     const DevPatchJob* d = static_cast<const DevPatchJob*>(upload_temp(batch.data(), batch.size() * sizeof(DevPatchJob)));
     begin_k("blend_patches");
-    launch_blend_patches(d, int(batch.size()), stream_);
+    launch_blend_patches(d, int(batch.size()), S());
     end_k();
     batch.clear();
     members.clear();
@@ -1327,7 +1471,7 @@ void CudaBackend::blend_patches(const std::vector<PatchJob>& jobs) {
 void CudaBackend::blend_raw(const DevPatchJob& job) {
   const DevPatchJob* d = static_cast<const DevPatchJob*>(upload_temp(&job, sizeof(job)));
   begin_k("blend_patches");
-  launch_blend_patches(d, 1, stream_);
+  launch_blend_patches(d, 1, S());
   end_k();
   sync();
   release_temps();
@@ -1339,7 +1483,7 @@ void CudaBackend::splat_splines(const View v[3], const std::vector<SplineArc>& a
   DevView dv[3] = {dev_view(v[0]), dev_view(v[1]), dev_view(v[2])};
   const DevSplineArc* d = static_cast<const DevSplineArc*>(upload_temp(arcs.data(), arcs.size() * sizeof(SplineArc)));
   begin_k("splat_splines");
-  launch_splat_splines(dv, d, int(arcs.size()), stream_);
+  launch_splat_splines(dv, d, int(arcs.size()), S());
   end_k();
 }
 
@@ -1361,7 +1505,7 @@ void CudaBackend::add_noise(const View v[3], const float lut[8], uint32_t group_
   p.group_dim = group_dim;
   p.seed0 = seed0;
   begin_k("add_noise");
-  launch_add_noise(dv, field, p, stream_);
+  launch_add_noise(dv, field, p, S());
   end_k();
   for (int c = 0; c < 3; ++c) dfree(field[c]);
 }
@@ -1369,9 +1513,9 @@ void CudaBackend::add_noise(const View v[3], const float lut[8], uint32_t group_
 void CudaBackend::pack_to_host(const DevPackParams& p, void* dst, size_t bytes) {
   void* d = dmalloc(bytes);
   begin_k("pack_interleaved");
-  launch_pack_interleaved(p, d, stream_);
+  launch_pack_interleaved(p, d, S());
   end_k();
-  CUDA_CHECK(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, stream_));
+  CUDA_CHECK(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, S()));
   sync();
   dfree(d);
 }
@@ -1383,7 +1527,7 @@ void CudaBackend::pack_to_device(const DevPackParams& p, void* d_dst) {
     fail(kErrInvalidArg, "destination is not device memory of this decoder's GPU");
   }
   begin_k("pack_interleaved");
-  launch_pack_interleaved(p, d_dst, stream_);
+  launch_pack_interleaved(p, d_dst, S());
   end_k();
   sync();  // the caller may hand the buffer to any stream (NCCL's, torch's) afterwards
 }
@@ -1413,7 +1557,7 @@ int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader
     out.stride = out.w;
     out.ptr = dmalloc(size_t(out.w) * out.h * 4);
     begin_k("upsample");
-    launch_upsample(cur, out, int(k), d_quarter, stream_);
+    launch_upsample(cur, out, int(k), d_quarter, S());
     end_k();
     if (cur_owned) dfree(cur_owned);
     cur = out;
@@ -1437,7 +1581,7 @@ int CudaBackend::upsample(const View& v, uint32_t factor_log2, const ImageHeader
 int CudaBackend::upsample_jpeg(const View& v, bool horizontal, bool vertical, uint32_t out_w, uint32_t out_h) {
   const int id = alloc_plane(out_w, out_h, false);
   begin_k("upsample_jpeg");
-  launch_upsample_jpeg(dev_view(v), dev_view(View{id, 0, 0, out_w, out_h}), horizontal ? 1 : 0, vertical ? 1 : 0, stream_);
+  launch_upsample_jpeg(dev_view(v), dev_view(View{id, 0, 0, out_w, out_h}), horizontal ? 1 : 0, vertical ? 1 : 0, S());
   end_k();
   return id;
 }
@@ -1445,7 +1589,7 @@ int CudaBackend::upsample_jpeg(const View& v, bool horizontal, bool vertical, ui
 void CudaBackend::ycbcr_to_rgb(const View v[3], const YcbcrParams& p) {
   const DevYcbcrParams d{p.y_offset, p.cr_to_r, p.cb_to_g, p.cr_to_g, p.cb_to_b};
   begin_k("ycbcr_to_rgb");
-  launch_ycbcr_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
+  launch_ycbcr_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, S());
   end_k();
 }
 
@@ -1466,7 +1610,7 @@ void CudaBackend::xyb_to_rgb(const View v[3], const ColorParams& p) {
   d.gamma = p.gamma;
   d.pq_intensity_target = p.pq_intensity_target;
   begin_k("xyb_to_rgb");
-  launch_xyb_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, stream_);
+  launch_xyb_to_rgb(dev_view(v[0]), dev_view(v[1]), dev_view(v[2]), d, S());
   end_k();
 }
 

@@ -14,9 +14,36 @@
 
 namespace jxlb {
 
+// One Modular launch handed to a pipeline's LF batch service (csrc/pipeline.cu): copies to make before the kernel, the
+// frame's job tables, copies to make after it. run() blocks the calling (frame) thread until the batch has run.
+struct LfBatchItem {
+  struct Copy {
+    void* dst;
+    const void* src;
+    size_t bytes;
+  };
+  Copy up[2];    // host (pinned) -> device
+  int num_up = 0;
+  DevModularBatchRef ref{};  // .job is filled per CTA by the service
+  int num_jobs = 0;
+  size_t smem_bytes = 0;
+  bool all_staged = false;
+  Copy down[2];  // device -> host (pinned)
+  int num_down = 0;
+  bool want_timing = false;
+  float elapsed_ms = 0.0f;  // device time of the batch kernel this item rode in
+};
+class LfBatchService {
+ public:
+  virtual ~LfBatchService() {}
+  virtual void run(LfBatchItem& item) = 0;  // throws jxlb::Error on a CUDA failure
+};
+
 class CudaBackend : public Backend {
  public:
-  explicit CudaBackend(int device);
+  // own_stream = false: a pipeline decoder. It borrows the stream of a heavy slot (on_heavy_stage -> set_stream) and
+  // runs its LF stage through `lf_service` without any stream.
+  explicit CudaBackend(int device, bool own_stream = true);
   ~CudaBackend() override;
 
   void set_codestream(const uint8_t* data, size_t size) override;
@@ -27,6 +54,7 @@ class CudaBackend : public Backend {
   void copy_rect(const View& src, const View& dst) override;
   void decode_modular(std::vector<ModularStreamJob>& jobs) override;
   int squeeze_inverse(const View& avg, const View& residual, bool horizontal) override;
+  std::vector<int> squeeze_inverse_many(const std::vector<std::pair<View, View>>& avg_res, bool horizontal) override;
   void rct_inverse(const View v[3], uint32_t rct_type) override;
   void palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t, const WpHeader& wp,
                        uint32_t bit_depth) override;
@@ -59,6 +87,7 @@ class CudaBackend : public Backend {
   // and to hand the backend a pre-allocated slab the big planes are carved from (no allocator calls per frame).
   void begin_heavy_stage(size_t bytes_hint) override;
   std::function<void(size_t)> on_heavy_stage;  // called once per frame, before the first big allocation
+  std::function<void()> on_need_stream;        // a stream-less (pipeline) decoder needs its stream now: must set_stream()
   void set_arena(void* base, size_t bytes) {
     arena_base_ = static_cast<uint8_t*>(base);
     arena_cap_ = bytes;
@@ -72,7 +101,11 @@ class CudaBackend : public Backend {
   size_t arena_peak() const { return arena_peak_; }
   size_t arena_spill() const { return arena_spill_; }  // bytes that did not fit the slab (allocated from the pool)
 
-  cudaStream_t stream() const { return stream_; }
+  cudaStream_t stream() { return S(); }
+  void set_stream(cudaStream_t s) { stream_ = s; }
+  bool has_stream() const { return stream_ != nullptr; }
+  void end_lease();  // a pipeline decoder gives its borrowed stream back (everything queued on it has run)
+  LfBatchService* lf_service = nullptr;
   // "inputs resident in HBM": upload once, then point the next decode at the device copy
   uint8_t* upload_resident(const uint8_t* data, size_t size);
   void use_resident_once(const uint8_t* dptr) { resident_next_ = dptr; }
@@ -148,7 +181,17 @@ class CudaBackend : public Backend {
 
  private:
 
+  cudaStream_t S();  // the decoder's stream, leased on first use when it has none of its own
+  void* lf_arena_alloc(size_t bytes);
+  bool in_lf_arena(const void* p) const {
+    return lf_arena_ && p >= static_cast<const void*>(lf_arena_) && p < static_cast<const void*>(lf_arena_ + lf_arena_cap_);
+  }
   int device_;
+  bool own_stream_ = true;
+  uint8_t* lf_arena_ = nullptr;  // device block the LF-stage planes of a pipeline decoder are carved from
+  size_t lf_arena_cap_ = 0, lf_arena_off_ = 0;
+  size_t pending_cs_bytes_ = 0;        // encoded bytes staged in h_input_, not yet copied to d_codestream_
+  std::vector<void*> deferred_free_;   // pool pointers released while the decoder had no stream
   uint8_t* h_stage_ = nullptr;   // pinned
   uint8_t* d_stage_ = nullptr;
   size_t stage_cap_ = 0, stage_off_ = 0, stage_flushed_ = 0;

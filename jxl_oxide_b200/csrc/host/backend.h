@@ -10,6 +10,7 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "frame_syntax.h"
@@ -135,6 +136,12 @@ class Backend {
   virtual void decode_modular(std::vector<ModularStreamJob>& jobs) = 0;
   // returns a new plane holding the merged channel (jxl-modular/src/transform/squeeze.rs)
   virtual int squeeze_inverse(const View& avg, const View& residual, bool horizontal) = 0;
+  // All channels of one Squeeze step (they are independent): a backend may run them as one launch.
+  virtual std::vector<int> squeeze_inverse_many(const std::vector<std::pair<View, View>>& avg_res, bool horizontal) {
+    std::vector<int> ids;
+    for (const auto& p : avg_res) ids.push_back(squeeze_inverse(p.first, p.second, horizontal));
+    return ids;
+  }
   virtual void rct_inverse(const View v[3], uint32_t rct_type) = 0;  // transform/rct.rs
   // palette (transform/palette.rs): `targets[0]` holds indices on entry
   virtual void palette_inverse(const View& palette, const std::vector<View>& targets, const Transform& t,

@@ -339,10 +339,13 @@ void FramePlanner::run_inverse_transforms(const ModularStreamSyntax& s, std::vec
         const SqueezeStep& sp = t.squeeze[si];
         size_t begin = sp.begin_c, n = sp.num_c, end = begin + n;
         size_t res0 = sp.in_place ? end : bufs.size() - n;
+        std::vector<std::pair<View, View>> pairs;
+        for (size_t c = 0; c < n; ++c) pairs.push_back({bufs[begin + c].view, bufs[res0 + c].view});
+        const std::vector<int> merged_ids = be_.squeeze_inverse_many(pairs, sp.horizontal);
         for (size_t c = 0; c < n; ++c) {
           ChanBuf& avg = bufs[begin + c];
           ChanBuf& res = bufs[res0 + c];
-          int merged = be_.squeeze_inverse(avg.view, res.view, sp.horizontal);
+          int merged = merged_ids[c];
           frame_planes_.push_back(merged);
           View mv;
           mv.plane = merged;

@@ -378,12 +378,24 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
     float gw[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) gw[c] = fdiv(1.0f, fadd(fadd(1.0f, fmul(p.gab_w[c][0], 4.0f)), fmul(p.gab_w[c][1], 4.0f)));
-    for_region(r, [&](int lx, int ly) {
+    if (!border_tile) {  // no pixel of the window lies on the image border: the 3x3 formula without the edge cases
+      for_region(r, [&](int lx, int ly) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        alt[c * kPlane + ly * kS + lx] =
-            gab_px(cur + c * kPlane + ly * kS + lx, gx0 + lx, gy0 + ly, width, height, p.gab_w[c][0], p.gab_w[c][1], gw[c]);
-    });
+        for (int c = 0; c < 3; ++c) {
+          const float* a = cur + c * kPlane + ly * kS + lx;
+          const float sum_side = fadd(fadd(fadd(a[-kS], a[-1]), a[1]), a[kS]);
+          const float sum_diag = fadd(fadd(fadd(a[-kS - 1], a[-kS + 1]), a[kS - 1]), a[kS + 1]);
+          alt[c * kPlane + ly * kS + lx] = fmul(fadd(fadd(a[0], fmul(sum_side, p.gab_w[c][0])), fmul(sum_diag, p.gab_w[c][1])), gw[c]);
+        }
+      });
+    } else {
+      for_region(r, [&](int lx, int ly) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          alt[c * kPlane + ly * kS + lx] =
+              gab_px(cur + c * kPlane + ly * kS + lx, gx0 + lx, gy0 + ly, width, height, p.gab_w[c][0], p.gab_w[c][1], gw[c]);
+      });
+    }
     float* t = cur;
     cur = alt;
     alt = t;

@@ -49,6 +49,19 @@ struct DevView {
   uint32_t stride, w, h;
 };
 
+struct DevChannel;
+struct DevChannelPlan;
+// One CTA of a batched Modular launch: job `job` of the frame these tables belong to.
+struct DevModularBatchRef {
+  const uint8_t* cs;
+  const DevModularJob* jobs;
+  const DevChannel* channels;
+  const DevChannelPlan* plans;
+  uint64_t* end_bits;
+  int* status;
+  uint32_t job, pad;
+};
+
 // Modular ------------------------------------------------------------------------------------
 void launch_modular_decode(const uint8_t* codestream, const DevModularJob* jobs, const DevChannel* channels,
                            const DevChannelPlan* plans, uint64_t* end_bits, int* status, int num_jobs,
@@ -56,11 +69,16 @@ void launch_modular_decode(const uint8_t* codestream, const DevModularJob* jobs,
                            unsigned long long* trace = nullptr);
 bool modular_job_all_staged(const DevModularJob& job, uint32_t max_width);
 void launch_signal_word(uint32_t* host_mapped_word, uint32_t value, cudaStream_t stream);
+void launch_modular_decode_batch(const DevModularBatchRef* refs, int total, size_t smem_bytes, bool all_tables_staged,
+                                 cudaStream_t stream);
 // tracing aid: writes the device's %globaltimer (ns)
 void launch_read_globaltimer(unsigned long long* out, cudaStream_t stream);
 // bytes of dynamic shared memory a job wants for its tree / entropy tables / WP rows / LUTs
 size_t modular_job_smem_bytes(const DevModularJob& job, uint32_t max_width);
 void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizontal, cudaStream_t stream);
+// The channels of one Squeeze step in one launch (channels may differ in size; zero-sized outputs are skipped).
+void launch_squeeze_inverse_batch(const DevView* avg, const DevView* res, const DevView* out, int n, bool horizontal,
+                                  cudaStream_t stream);
 void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cudaStream_t stream);
 // Second pass of a delta palette (palette.rs:120-152): every channel is scanned in raster order and the samples marked
 // in `mask` get `d_pred`'s prediction (from already final neighbours) added - a serial recurrence per channel.

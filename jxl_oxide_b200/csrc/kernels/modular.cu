@@ -4,6 +4,8 @@
 // transform/{squeeze,rct,palette}.rs} (i32 samples, wrapping).
 #include "kernels.h"
 
+#include <cstring>
+
 namespace jxlb {
 
 namespace {
@@ -34,7 +36,12 @@ __device__ __forceinline__ int32_t tendency(int32_t a, int32_t b, int32_t c) {  
 // lane then runs its row's recurrence on the shared tile (pitch 33 / 65: conflict-free), and the 64 output columns go
 // back row by row as two coalesced 128-byte writes. `left` and the current average carry over between chunks in registers.
 constexpr int kSqWarps = 2;
-__global__ void __launch_bounds__(kSqWarps * 32) squeeze_h_kernel(DevView avg, DevView res, DevView out) {
+struct SqueezeBatch {  // up to four channels of one Squeeze step, blockIdx.y selects the channel
+  DevView avg[4], res[4], out[4];
+};
+__global__ void __launch_bounds__(kSqWarps * 32) squeeze_h_kernel(SqueezeBatch b) {
+  const DevView avg = b.avg[blockIdx.y], res = b.res[blockIdx.y], out = b.out[blockIdx.y];
+  if (!out.w || !out.h) return;
   __shared__ int32_t s_avg[kSqWarps][32][33], s_res[kSqWarps][32][33], s_out[kSqWarps][32][65];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t y0 = (blockIdx.x * kSqWarps + warp) * 32;
@@ -80,14 +87,39 @@ __global__ void __launch_bounds__(kSqWarps * 32) squeeze_h_kernel(DevView avg, D
   if ((out.w & 1) && lane < rows) ob[size_t(lane) * out.stride + out.w - 1] = ab[size_t(lane) * avg.stride + avg.w - 1];
 }
 
-__global__ void squeeze_v_kernel(DevView avg, DevView res, DevView out) {
+// Vertical inverse Squeeze (squeeze.rs:803-862): one thread per column (adjacent lanes read adjacent columns: every row
+// access of a warp is one 128-byte line), the recurrence runs down the column. The loads of a step do not depend on the
+// recurrence, so four rows of averages / residuals are fetched before the four dependent steps that use them: one
+// global-memory latency per four output row pairs instead of per pair. blockIdx.y selects the channel of a batch.
+__global__ void __launch_bounds__(64) squeeze_v_kernel(SqueezeBatch b) {
+  const DevView avg = b.avg[blockIdx.y], res = b.res[blockIdx.y], out = b.out[blockIdx.y];
   uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= out.w) return;
+  if (x >= out.w || !out.h) return;
   const int32_t* ap = static_cast<const int32_t*>(avg.ptr) + x;
   const int32_t* rp = static_cast<const int32_t*>(res.ptr) + x;
   int32_t* o = static_cast<int32_t*>(out.ptr) + x;
   int32_t a = ap[0], top = a;
-  for (uint32_t y = 0; y < res.h; ++y) {
+  uint32_t y = 0;
+  for (; y + 4 <= res.h; y += 4) {
+    int32_t na[4], r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      r[j] = rp[size_t(y + j) * res.stride];
+      na[j] = (y + j + 1 < avg.h) ? ap[size_t(y + j + 1) * avg.stride] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int32_t next_avg = (y + j + 1 < avg.h) ? na[j] : a;
+      const int32_t diff = wadd(r[j], tendency(top, a, next_avg));
+      const int32_t first = wadd(a, diff / 2);
+      const int32_t second = wsub(first, diff);
+      o[size_t(2 * (y + j)) * out.stride] = first;
+      o[size_t(2 * (y + j) + 1) * out.stride] = second;
+      a = next_avg;
+      top = second;
+    }
+  }
+  for (; y < res.h; ++y) {
     int32_t next_avg = (y + 1 < avg.h) ? ap[size_t(y + 1) * avg.stride] : a;
     int32_t diff = wadd(rp[size_t(y) * res.stride], tendency(top, a, next_avg));
     int32_t first = wadd(a, diff / 2);
@@ -229,10 +261,27 @@ inline dim3 grid2d(uint32_t w, uint32_t h, uint32_t bx = 128) { return dim3((w +
 
 }  // namespace
 
+void launch_squeeze_inverse_batch(const DevView* avg, const DevView* res, const DevView* out, int n, bool horizontal,
+                                  cudaStream_t stream) {
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    SqueezeBatch b;
+    memset(&b, 0, sizeof(b));
+    const int m = n - i0 < 4 ? n - i0 : 4;
+    uint32_t max_w = 0, max_h = 0;
+    for (int i = 0; i < m; ++i) {
+      b.avg[i] = avg[i0 + i], b.res[i] = res[i0 + i], b.out[i] = out[i0 + i];
+      max_w = max_w > out[i0 + i].w ? max_w : out[i0 + i].w;
+      max_h = max_h > out[i0 + i].h ? max_h : out[i0 + i].h;
+    }
+    if (!max_w || !max_h) continue;
+    if (horizontal) squeeze_h_kernel<<<dim3((max_h + kSqWarps * 32 - 1) / (kSqWarps * 32), m), kSqWarps * 32, 0, stream>>>(b);
+    else squeeze_v_kernel<<<dim3((max_w + 63) / 64, m), 64, 0, stream>>>(b);
+  }
+}
+
 void launch_squeeze_inverse(DevView avg, DevView res, DevView out, bool horizontal, cudaStream_t stream) {
   if (!out.w || !out.h) return;
-  if (horizontal) squeeze_h_kernel<<<(out.h + kSqWarps * 32 - 1) / (kSqWarps * 32), kSqWarps * 32, 0, stream>>>(avg, res, out);
-  else squeeze_v_kernel<<<(out.w + 63) / 64, 64, 0, stream>>>(avg, res, out);
+  launch_squeeze_inverse_batch(&avg, &res, &out, 1, horizontal, stream);
 }
 
 void launch_rct_inverse(DevView a, DevView b, DevView c, uint32_t rct_type, cudaStream_t stream) {

@@ -502,15 +502,12 @@ __device__ __forceinline__ void decode_channel(const DevModularJob& job, const D
 // need: a few KB). All table pointers then derive from the shared array unconditionally, so the compiler emits LDS with
 // 32-bit addresses instead of generic loads for the tree nodes, alias buckets, leaf LUT and predictor rows.
 template <bool ALLSM>
-__global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __restrict__ cs,
-                                                            const DevModularJob* __restrict__ jobs,
-                                                            const DevChannel* __restrict__ channels,
-                                                            const DevChannelPlan* __restrict__ plans,
-                                                            uint64_t* __restrict__ end_bits, int* __restrict__ status,
-                                                            int num_jobs, unsigned long long* __restrict__ trace) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int job_idx = blockIdx.x;
-  if (job_idx >= num_jobs) return;
+__device__ __forceinline__ void modular_stream_body(uint8_t* smem, const uint8_t* __restrict__ cs,
+                                                    const DevModularJob* __restrict__ jobs,
+                                                    const DevChannel* __restrict__ channels,
+                                                    const DevChannelPlan* __restrict__ plans,
+                                                    uint64_t* __restrict__ end_bits, int* __restrict__ status,
+                                                    const int job_idx, unsigned long long* __restrict__ trace) {
   const uint32_t lane = threadIdx.x;
   const DevModularJob& job = jobs[job_idx];
   const DevEntropyCode& code = job.code;
@@ -628,6 +625,30 @@ __global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __res
   }
 }
 
+template <bool ALLSM>
+__global__ void __launch_bounds__(32) modular_stream_kernel(const uint8_t* __restrict__ cs,
+                                                            const DevModularJob* __restrict__ jobs,
+                                                            const DevChannel* __restrict__ channels,
+                                                            const DevChannelPlan* __restrict__ plans,
+                                                            uint64_t* __restrict__ end_bits, int* __restrict__ status,
+                                                            int num_jobs, unsigned long long* __restrict__ trace) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (int(blockIdx.x) >= num_jobs) return;
+  modular_stream_body<ALLSM>(smem, cs, jobs, channels, plans, end_bits, status, int(blockIdx.x), trace);
+}
+
+// The same streams for several frames in ONE launch (csrc/pipeline.cu, LF batch service): CTA i decodes job
+// `refs[i].job` of the frame whose tables `refs[i]` points to. A frame's LF stage is two ~80 / ~25 ms kernels of a
+// dozen one-lane warps; launched per frame they pin one CUDA stream (= one of the device's 32 hardware queues) for
+// the whole time, which caps the frames in flight. Batched, a handful of streams carry every frame's LF stage.
+template <bool ALLSM>
+__global__ void __launch_bounds__(32) modular_stream_batch_kernel(const DevModularBatchRef* __restrict__ refs, int total) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  if (int(blockIdx.x) >= total) return;
+  const DevModularBatchRef r = refs[blockIdx.x];
+  modular_stream_body<ALLSM>(smem, r.cs, r.jobs, r.channels, r.plans, r.end_bits, r.status, int(r.job), nullptr);
+}
+
 // Delta-palette prediction pass (palette.rs:120-152): one CTA per channel, thread 0 walks the channel in raster order
 // (every prediction reads the already corrected W / N / NW / NE ... neighbours, a serial recurrence).
 __global__ void __launch_bounds__(32) palette_delta_kernel(DevPaletteDeltaParams p) {
@@ -722,6 +743,19 @@ void launch_modular_decode(const uint8_t* cs, const DevModularJob* jobs, const D
     modular_stream_kernel<true><<<num_jobs, 32, smem_bytes, stream>>>(cs, jobs, channels, plans, end_bits, status, num_jobs, trace);
   else
     modular_stream_kernel<false><<<num_jobs, 32, smem_bytes, stream>>>(cs, jobs, channels, plans, end_bits, status, num_jobs, trace);
+}
+
+void launch_modular_decode_batch(const DevModularBatchRef* refs, int total, size_t smem_bytes, bool all_tables_staged,
+                                 cudaStream_t stream) {
+  if (total <= 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(modular_stream_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(modular_stream_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  if (all_tables_staged) modular_stream_batch_kernel<true><<<total, 32, smem_bytes, stream>>>(refs, total);
+  else modular_stream_batch_kernel<false><<<total, 32, smem_bytes, stream>>>(refs, total);
 }
 
 // Whether modular_stream_kernel stages every table of this job (tree, entropy tables, leaf LUTs, predictor rows).

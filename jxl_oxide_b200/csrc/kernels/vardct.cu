@@ -531,9 +531,17 @@ __device__ void transform_special(Grid c, int type, float* scratch /* 64 + 48 fl
 // Every variant performs exactly the reference's operations per line (rows first, then columns,
 // generic/dct.rs:93-140), so results are bit-identical to the single-threaded formulation.
 
+// Medium class, by shape (width x height in 8x8 cells): 2x1 1x2 2x2 4x1 1x4 4x2 2x4 4x4. The medium kernel walks the shapes
+// one after the other so that the warps of an SM execute the same transform sizes at the same time (its unrolled
+// 8 / 16 / 32-point transforms do not fit the instruction cache together: ncu showed "no instruction" as the top stall).
+constexpr int kMediumShapes = 8;
+__host__ __device__ inline int medium_shape(int w8, int h8) {
+  return w8 == 2 ? (h8 == 1 ? 0 : (h8 == 2 ? 2 : 6)) : (w8 == 1 ? (h8 == 2 ? 1 : 4) : (h8 == 1 ? 3 : (h8 == 2 ? 5 : 7)));
+}
 struct TransformLists {
-  uint32_t* counts;  // [4]: small, medium, large64, large256
+  uint32_t* counts;  // [0..3]: small, medium (unused), large64, large256; [4..11]: medium shapes
   uint32_t* items[4];
+  uint32_t* shape_items[kMediumShapes];
 };
 
 __global__ void classify_varblocks_kernel(DevFrame f, TransformLists L) {
@@ -543,6 +551,12 @@ __global__ void classify_varblocks_kernel(DevFrame f, TransformLists L) {
   if (t < 0) return;
   const int m = max(int(kDevTransformInfo[t][0]), int(kDevTransformInfo[t][1]));
   const int cls = m == 1 ? 0 : (m <= 4 ? 1 : (m == 8 ? 2 : 3));
+  if (cls == 1) {
+    const int sh = medium_shape(kDevTransformInfo[t][0], kDevTransformInfo[t][1]);
+    const uint32_t slot = atomicAdd(L.counts + 4 + sh, 1u);
+    L.shape_items[sh][slot] = bx | (by << 16);
+    return;
+  }
   const uint32_t slot = atomicAdd(L.counts + cls, 1u);
   L.items[cls][slot] = bx | (by << 16);
 }
@@ -894,8 +908,9 @@ __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f
   }
 }
 
+// not inlined: the row pass and the column pass of the medium kernel share one copy of each size's code
 template <int N>
-__device__ __forceinline__ void idct_line_smem(float* p, int stride) {
+__device__ __noinline__ void idct_line_smem(float* p, int stride) {
   float v[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) v[i] = p[i * stride];
@@ -912,17 +927,18 @@ __device__ __forceinline__ void idct_line_dispatch(float* p, int stride, int n) 
 
 constexpr int kMediumWarps = 4;
 template <bool DEQ>
-__global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame f, DevDequantParams dq,
-                                                                        const uint32_t* __restrict__ items,
-                                                                        const uint32_t* __restrict__ count_ptr) {
+__global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
   __shared__ float s_tile[kMediumWarps][32 * 33];
   __shared__ float s_ytile[DEQ ? kMediumWarps : 1][DEQ ? 32 * 33 : 1];  // dequantised Y coefficients (chroma from luma)
   __shared__ float s_llf[kMediumWarps][16 + 12];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t total = DEQ ? *count_ptr : *count_ptr * 3;
   float* tile = s_tile[warp];
   float* ytile = s_ytile[DEQ ? warp : 0];
   float* llf = s_llf[warp];
+#pragma unroll 1
+  for (int shape = 0; shape < kMediumShapes; ++shape) {
+  const uint32_t* __restrict__ items = lists.shape_items[shape];
+  const uint32_t total = DEQ ? lists.counts[4 + shape] : lists.counts[4 + shape] * 3;
   for (uint32_t work = blockIdx.x * kMediumWarps + warp; work < total; work += gridDim.x * kMediumWarps) {
     const uint32_t item = items[DEQ ? work : work / 3];
     const uint32_t sbx = item & 0xffff, sby = item >> 16;
@@ -990,6 +1006,7 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
       }
       __syncwarp();
     }
+  }
   }
 }
 
@@ -1121,7 +1138,8 @@ void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream) 
 
 size_t hf_transform_scratch_bytes(uint32_t bw, uint32_t bh) {
   const size_t cells = size_t(bw) * bh;
-  return 256 + (cells + cells / 2 + 2 * (cells / 32 + 1) + 64) * 4;
+  // counters | small | (former medium list) | large | huge | the eight medium shapes (cells/2 x 2, /4 x 3, /8 x 2, /16)
+  return 256 + (cells + cells / 2 + 2 * (cells / 32 + 1) + 64) * 4 + (cells * 9 / 4 + 64) * 4;
 }
 
 namespace {
@@ -1131,7 +1149,7 @@ void launch_idcts(DevFrame f, const DevDequantParams& dq, const TransformLists& 
   const int small_grid = int(std::min<size_t>((cells * per + kSmallGroups - 1) / kSmallGroups, size_t(num_sms) * 8));
   idct_small_kernel<DEQ><<<small_grid, kSmallGroups * 8, 0, stream>>>(f, dq, L.items[0], L.counts + 0);
   const int medium_grid = int(std::min<size_t>((cells / 2 * per + kMediumWarps) / kMediumWarps, size_t(num_sms) * 8));
-  idct_medium_kernel<DEQ><<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, dq, L.items[1], L.counts + 1);
+  idct_medium_kernel<DEQ><<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, dq, L);
   const int large_grid = int(std::min<size_t>((cells / 32 + 1) * per, size_t(num_sms) * 4));
   idct_large_kernel<DEQ><<<large_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 64 + 1)) * 4, stream>>>(f, dq, L.items[2], L.counts + 2, 64);
   const int huge_grid = int(std::min<size_t>((cells / 128 + 1) * per, size_t(num_sms)));
@@ -1150,7 +1168,15 @@ void launch_hf_transform(DevFrame f, void* scratch, const DevDequantParams* dq, 
   L.items[1] = L.items[0] + cells;                     // <= cells / 2
   L.items[2] = L.items[1] + cells / 2 + 1;             // <= cells / 32
   L.items[3] = L.items[2] + cells / 32 + 1;            // <= cells / 128
-  cudaMemsetAsync(L.counts, 0, 16, stream);
+  {  // a shape's list holds at most cells / (cells per block of that shape) entries
+    static const int kShapeCells[kMediumShapes] = {2, 2, 4, 4, 4, 8, 8, 16};
+    uint32_t* q = L.items[3] + cells / 128 + 1;
+    for (int sh = 0; sh < kMediumShapes; ++sh) {
+      L.shape_items[sh] = q;
+      q += cells / kShapeCells[sh] + 1;
+    }
+  }
+  cudaMemsetAsync(L.counts, 0, 64, stream);
   dim3 cb(32, 8), cg((f.bw + 31) / 32, (f.bh + 7) / 8);
   classify_varblocks_kernel<<<cg, cb, 0, stream>>>(f, L);
   static int num_sms = 0;

@@ -57,10 +57,209 @@ struct Resident {
   uint8_t* dptr = nullptr;
 };
 
-struct Slab {
+struct Slab {  // a heavy slot: HBM for a frame's full-resolution planes + the CUDA stream its kernels run on
   void* base = nullptr;
   size_t bytes = 0;
   bool busy = false;
+  cudaStream_t stream = nullptr;
+};
+
+// LF batch service: the Modular launches of every frame's LF stage (LfCoeff, HfMetadata: ~80 / ~25 ms kernels of a dozen
+// one-lane warps) ride in shared kernels on a few batch streams. A frame in its LF stage therefore holds no CUDA stream
+// and any number of frames can be in flight; the device's 32 hardware queues are left to the batch streams and the heavy
+// slots. One service thread: it launches whatever is pending whenever a batch stream is free (so batches grow by
+// themselves under load), polls the mapped completion words of the batches in flight and wakes the frames' threads.
+class BatchService : public LfBatchService {
+ public:
+  BatchService(int device, int num_streams) : device_(device) {
+    cudaSetDevice(device_);
+    for (int i = 0; i < num_streams; ++i) {
+      Batch b;
+      cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking);
+      cudaHostAlloc(reinterpret_cast<void**>(&b.h_refs), kMaxRefs * sizeof(DevModularBatchRef), cudaHostAllocDefault);
+      cudaMalloc(reinterpret_cast<void**>(&b.d_refs), kMaxRefs * sizeof(DevModularBatchRef));
+      void* f = nullptr;
+      cudaHostAlloc(&f, 64, cudaHostAllocMapped);
+      b.flag = static_cast<volatile uint32_t*>(f);
+      *b.flag = 0;
+      cudaEventCreate(&b.e0);
+      cudaEventCreate(&b.e1);
+      batches_.push_back(b);
+    }
+    thread_ = std::thread([this] { loop(); });
+  }
+  ~BatchService() override {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_pending_.notify_all();
+    thread_.join();
+    cudaSetDevice(device_);
+    for (Batch& b : batches_) {
+      cudaStreamSynchronize(b.stream);
+      cudaStreamDestroy(b.stream);
+      cudaFreeHost(b.h_refs);
+      cudaFree(b.d_refs);
+      cudaFreeHost(const_cast<uint32_t*>(b.flag));
+      cudaEventDestroy(b.e0);
+      cudaEventDestroy(b.e1);
+    }
+  }
+  void run(LfBatchItem& item) override {
+    Waiter w;
+    w.item = &item;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      pending_.push_back(&w);
+    }
+    cv_pending_.notify_one();
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return w.done; });
+    if (w.error != cudaSuccess) fail(kErrCuda, std::string("CUDA error in the LF batch: ") + cudaGetErrorString(w.error));
+  }
+  uint64_t launches() const { return launches_; }
+  uint64_t items() const { return items_; }
+
+ private:
+  static constexpr int kMaxRefs = 4096;
+  struct Waiter {
+    LfBatchItem* item = nullptr;
+    bool done = false;
+    cudaError_t error = cudaSuccess;
+  };
+  struct Batch {
+    cudaStream_t stream = nullptr;
+    DevModularBatchRef* h_refs = nullptr;
+    DevModularBatchRef* d_refs = nullptr;
+    volatile uint32_t* flag = nullptr;
+    uint32_t seq = 0;
+    bool busy = false;
+    bool timed = false;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<Waiter*> riders;
+    std::chrono::steady_clock::time_point t0;
+  };
+
+  void finish(Batch& b, cudaError_t err) {
+    float ms = 0.0f;
+    if (b.timed && err == cudaSuccess) cudaEventElapsedTime(&ms, b.e0, b.e1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (Waiter* w : b.riders) {
+        w->item->elapsed_ms = ms;
+        w->error = err;
+        w->done = true;
+      }
+    }
+    b.riders.clear();
+    b.busy = false;
+    cv_done_.notify_all();
+  }
+
+  void launch(Batch& b, std::vector<Waiter*>& take) {
+    cudaError_t err = cudaSuccess;
+    auto chk = [&](cudaError_t e) {
+      if (err == cudaSuccess && e != cudaSuccess) err = e;
+    };
+    int total = 0;
+    size_t smem = 0;
+    bool all_staged = true, timed = false;
+    for (Waiter* w : take) {
+      LfBatchItem& it = *w->item;
+      for (int i = 0; i < it.num_up; ++i)
+        if (it.up[i].bytes) chk(cudaMemcpyAsync(it.up[i].dst, it.up[i].src, it.up[i].bytes, cudaMemcpyHostToDevice, b.stream));
+      for (int j = 0; j < it.num_jobs; ++j) {
+        DevModularBatchRef r = it.ref;
+        r.job = uint32_t(j);
+        b.h_refs[total++] = r;
+      }
+      smem = std::max(smem, it.smem_bytes);
+      all_staged = all_staged && it.all_staged;
+      timed = timed || it.want_timing;
+    }
+    chk(cudaMemcpyAsync(b.d_refs, b.h_refs, size_t(total) * sizeof(DevModularBatchRef), cudaMemcpyHostToDevice, b.stream));
+    if (timed) chk(cudaEventRecord(b.e0, b.stream));
+    launch_modular_decode_batch(b.d_refs, total, smem, all_staged, b.stream);
+    chk(cudaGetLastError());
+    if (timed) chk(cudaEventRecord(b.e1, b.stream));
+    for (Waiter* w : take) {
+      LfBatchItem& it = *w->item;
+      for (int i = 0; i < it.num_down; ++i)
+        if (it.down[i].bytes) chk(cudaMemcpyAsync(it.down[i].dst, it.down[i].src, it.down[i].bytes, cudaMemcpyDeviceToHost, b.stream));
+    }
+    b.seq += 1;
+    launch_signal_word(const_cast<uint32_t*>(b.flag), b.seq, b.stream);
+    chk(cudaGetLastError());
+    b.riders = take;
+    b.busy = true;
+    b.timed = timed;
+    b.t0 = std::chrono::steady_clock::now();
+    ++launches_;
+    items_ += take.size();
+    if (err != cudaSuccess) {  // nothing useful is in flight: report to the riders right away
+      cudaStreamSynchronize(b.stream);
+      finish(b, err);
+    }
+  }
+
+  void loop() {
+    cudaSetDevice(device_);
+    for (;;) {
+      // completions
+      bool any_busy = false;
+      for (Batch& b : batches_) {
+        if (!b.busy) continue;
+        if (*b.flag == b.seq) {
+          std::atomic_thread_fence(std::memory_order_acquire);
+          finish(b, cudaSuccess);
+        } else if (std::chrono::steady_clock::now() - b.t0 > std::chrono::milliseconds(500)) {
+          cudaError_t e = cudaStreamQuery(b.stream);  // a faulting kernel never writes the word
+          if (e != cudaErrorNotReady && e != cudaSuccess) finish(b, e);
+          else if (e == cudaSuccess && *b.flag == b.seq) finish(b, cudaSuccess);
+          else b.t0 = std::chrono::steady_clock::now();
+        }
+        any_busy = any_busy || b.busy;
+      }
+      // launches: everything pending goes into the next free batch stream
+      std::vector<Waiter*> take;
+      Batch* free_batch = nullptr;
+      for (Batch& b : batches_)
+        if (!b.busy) {
+          free_batch = &b;
+          break;
+        }
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (stop_ && pending_.empty() && !any_busy) return;
+        if (free_batch && !pending_.empty()) {
+          int refs = 0;
+          while (!pending_.empty() && refs + pending_.front()->item->num_jobs <= kMaxRefs) {
+            refs += pending_.front()->item->num_jobs;
+            take.push_back(pending_.front());
+            pending_.pop_front();
+          }
+        } else if (!any_busy) {
+          cv_pending_.wait(lk, [&] { return stop_ || !pending_.empty(); });
+          continue;
+        }
+      }
+      if (!take.empty()) {
+        launch(*free_batch, take);
+        continue;
+      }
+      std::this_thread::sleep_for(std::chrono::microseconds(40));
+    }
+  }
+
+  int device_;
+  std::vector<Batch> batches_;
+  std::thread thread_;
+  std::mutex mu_;
+  std::condition_variable cv_pending_, cv_done_;
+  std::deque<Waiter*> pending_;
+  bool stop_ = false;
+  uint64_t launches_ = 0, items_ = 0;
 };
 
 // CPUs local to the GPU's PCIe root (sysfs), so that worker threads - and whatever they first-touch - sit on the NUMA
@@ -101,14 +300,19 @@ struct jxlb_pipeline {
   bool stopping = false;
   std::map<int32_t, Resident> resident;
   std::vector<Slab> slabs;
+  std::unique_ptr<BatchService> batcher;
   std::vector<HostBuf> hostbufs;
+  size_t host_bytes = 0;  // size every buffer of the output ring has
   std::condition_variable cv_host;
   std::mutex copy_mu;  // one frame's output crosses the host link at a time
   std::string error;
   std::vector<int> cpus;
 
+  size_t max_hint = 0;  // largest heavy-stage request seen: slabs are (re)allocated to it
   int acquire_slab(size_t bytes_hint) {
     std::unique_lock<std::mutex> lk(mu);
+    max_hint = std::max(max_hint, bytes_hint);
+    bytes_hint = max_hint;
     int idx = -1;
     cv_slab.wait(lk, [&] {
       for (size_t i = 0; i < slabs.size(); ++i)
@@ -136,39 +340,49 @@ struct jxlb_pipeline {
     }
     return idx;
   }
+  // The output ring is allocated in one go the first time a frame asks for `bytes` (and again if a larger frame comes):
+  // cudaHostAlloc of a few hundred MB takes tens of milliseconds during which no other thread gets a CUDA call through,
+  // so it must not trickle into steady state buffer by buffer (measured: 12 ms per frame lost that way).
   void* acquire_host(size_t bytes) {
     std::unique_lock<std::mutex> lk(mu);
+    if (bytes > host_bytes) {
+      cv_host.wait(lk, [&] {  // every buffer back in the ring before it is rebuilt
+        for (const HostBuf& b : hostbufs)
+          if (b.busy) return false;
+        return true;
+      });
+      if (bytes > host_bytes) {
+        for (HostBuf& b : hostbufs) {
+          if (b.p) cudaFreeHost(b.p);
+          b.p = nullptr;
+          b.bytes = 0;
+          void* q = nullptr;
+          if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) == cudaSuccess) {
+            std::memset(q, 0, bytes);  // first touch by a (GPU-local) worker thread
+            b.p = q;
+            b.bytes = bytes;
+          } else {
+            cudaGetLastError();
+          }
+        }
+        host_bytes = bytes;
+      }
+    }
     int idx = -1;
     cv_host.wait(lk, [&] {
       for (size_t i = 0; i < hostbufs.size(); ++i)
-        if (!hostbufs[i].busy) {
+        if (!hostbufs[i].busy && hostbufs[i].p) {
           idx = int(i);
           return true;
         }
-      return false;
+      for (const HostBuf& b : hostbufs)
+        if (b.p) return false;  // all busy: wait
+      idx = -2;                  // nothing could be allocated at all
+      return true;
     });
-    HostBuf& b = hostbufs[size_t(idx)];
-    b.busy = true;
-    if (b.bytes < bytes) {
-      lk.unlock();
-      if (b.p) cudaFreeHost(b.p);
-      b.p = nullptr;
-      b.bytes = 0;
-      void* q = nullptr;
-      if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) == cudaSuccess) {
-        std::memset(q, 0, bytes);  // first touch by this (GPU-local) thread
-        b.p = q;
-        b.bytes = bytes;
-      } else {
-        cudaGetLastError();
-        lk.lock();
-        b.busy = false;
-        lk.unlock();
-        cv_host.notify_one();
-        return nullptr;
-      }
-    }
-    return b.p;
+    if (idx < 0) return nullptr;
+    hostbufs[size_t(idx)].busy = true;
+    return hostbufs[size_t(idx)].p;
   }
   bool release_host(void* ptr) {
     bool found = false;
@@ -180,7 +394,7 @@ struct jxlb_pipeline {
           found = true;
         }
     }
-    if (found) cv_host.notify_one();
+    if (found) cv_host.notify_all();
     return found;
   }
   void release_slab(int idx) {
@@ -201,11 +415,22 @@ struct jxlb_pipeline {
     }
     jxlb_decoder* dec = decoders[wi];
     int held = -1;
+    // A heavy slot = slab + stream. The planner's begin_heavy_stage() takes the slot for its memory; the stream is handed
+    // to the decoder only when it first needs one (a Modular frame decodes all its streams through the batch service
+    // and wants the stream for the inverse transforms only).
     dec->be->on_heavy_stage = [&](size_t hint) {
-      if (held >= 0) return;  // a later frame of the same image: it shares the slab (overflow goes to the pool)
+      if (held >= 0) return;  // a later frame of the same image: it shares the slot (overflow goes to the pool)
       held = acquire_slab(hint);
       dec->be->set_arena(slabs[size_t(held)].base, slabs[size_t(held)].bytes);
     };
+    dec->be->on_need_stream = [&] {
+      if (held < 0) {
+        held = acquire_slab(0);
+        dec->be->set_arena(slabs[size_t(held)].base, slabs[size_t(held)].bytes);
+      }
+      dec->be->set_stream(slabs[size_t(held)].stream);
+    };
+    dec->be->lf_service = batcher.get();
     for (;;) {
       Job job;
       {
@@ -278,6 +503,10 @@ struct jxlb_pipeline {
       jxlb_release_frames(dec);
       if (held >= 0) {
         dec->be->end_arena();
+        try {
+          dec->be->end_lease();
+        } catch (const Error&) {
+        }
         release_slab(held);
         held = -1;
       }
@@ -295,16 +524,20 @@ extern "C" {
 int32_t jxlb_pipeline_create(int32_t device, const jxlb_pipeline_config* cfg, jxlb_pipeline** out) {
   if (!out) return JXLB_ERR_INVALID_ARG;
   *out = nullptr;
-  const int workers = cfg && cfg->workers > 0 ? cfg->workers : 32;
-  const int heavy = cfg && cfg->heavy_frames > 0 ? cfg->heavy_frames : 8;
+  const int workers = cfg && cfg->workers > 0 ? cfg->workers : 64;
+  const int heavy = cfg && cfg->heavy_frames > 0 ? cfg->heavy_frames : 16;
   auto p = std::make_unique<jxlb_pipeline>();
   p->device = device;
   p->heavy_frames = heavy;
   p->slabs.resize(size_t(heavy));
-  p->hostbufs.resize(size_t(heavy) + 4);
+  if (cudaSetDevice(device) != cudaSuccess) return JXLB_ERR_CUDA;
+  for (Slab& sl : p->slabs)
+    if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) return JXLB_ERR_CUDA;
+  p->batcher.reset(new BatchService(device, cfg && cfg->batch_streams > 0 ? cfg->batch_streams : 6));
+  p->hostbufs.resize(6);  // outputs cross the host link one at a time; a few buffers cover the consumer's turnaround
   for (int i = 0; i < workers; ++i) {
-    jxlb_decoder* d = nullptr;
-    const int32_t rc = jxlb_decoder_create(device, &d);
+    int32_t rc = JXLB_OK;
+    jxlb_decoder* d = create_decoder_internal(device, 0, false, &rc);
     if (rc != JXLB_OK) {
       for (jxlb_decoder* q : p->decoders) jxlb_decoder_destroy(q);
       return rc;
@@ -329,8 +562,11 @@ void jxlb_pipeline_destroy(jxlb_pipeline* p) {
   for (std::thread& t : p->threads) t.join();
   for (jxlb_decoder* d : p->decoders) jxlb_decoder_destroy(d);
   cudaSetDevice(p->device);
-  for (Slab& s : p->slabs)
+  p->batcher.reset();
+  for (Slab& s : p->slabs) {
     if (s.base) cudaFree(s.base);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
   for (auto& kv : p->resident)
     if (kv.second.dptr) cudaFree(kv.second.dptr);
   for (HostBuf& b : p->hostbufs)
