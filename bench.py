@@ -447,6 +447,13 @@ def run_ours(args, rank, world, local_rank):
             entropy["hf_symbols_per_frame"] = sym.get("hf_symbols")
             entropy["hf_symbols_per_s_solo"] = sym.get("hf_symbols", 0) / (solo["decode_hf"] / 1e3)
             entropy["hf_symbols_per_s_whole_job"] = sym.get("hf_symbols", 0) * len(frames) * world / (ms / args.steps / 1e3)
+        if sym and "modular_decode" in solo:
+            n = sym.get("lf_samples") or sym.get("modular_samples") or 0
+            entropy["modular_samples_per_frame"] = n
+            entropy["modular_samples_per_s_solo"] = n / (solo["modular_decode"] / 1e3)
+            entropy["modular_samples_per_s_whole_job"] = n * len(frames) * world / (ms / args.steps / 1e3)
+        if sym:
+            entropy["symbol_counts"] = "profiles/r02_symbols.json (" + str(sym.get("how")) + ")"
     cpu = cpu_baseline(args, frames, px_per_frame) if not args.no_cpu_baseline else None
     line = {
         "metric": METRIC.get(args.workload, "Megapixels/s decoded"), "value": value, "unit": "MP/s", "n_gpus": world,
@@ -485,50 +492,53 @@ METRIC = {"synth8k": "Megapixels/s decoded (8K VarDCT d1.0)", "synth4k": "Megapi
 
 
 def run_gather(args, torch, dist, J, local_rank, world, rank, frames, total_px, barrier, hf_lanes):
-    """BASELINE config #5's delivery: every frame packed on its GPU (interleaved u8 / u16, 3-6 B/px instead of 12 B/px of
-    f32 planes) and gathered to rank 0 over NCCL (jxl_oxide_b200.sharding.gather_frames); timed like `value`. Decode
-    contexts run in threads; the gather of round r overlaps the decode of round r + 1 (frames packed into a second
-    buffer set)."""
+    """BASELINE config #5's delivery: every frame is packed on its GPU (interleaved u8 / u16: 3-6 B/px instead of the
+    12 B/px of f32 planes) straight into a device tensor by the frame pipeline (out_mode 4 / 5) and gathered to rank 0
+    over NCCL, one `gather` per round of world_size frames (jxl_oxide_b200.sharding.gather_frames). The rounds are
+    fed as the frames come out of the pipeline, so the gather of round r overlaps the decode of the later frames."""
     from jxl_oxide_b200 import sharding
-    gdt = np.uint8 if args.gather == "u8" else np.uint16
-    nthreads = max(1, min(args.gather_contexts, len(frames)))
-    decs = [J.Decoder(local_rank) for _ in range(nthreads)]
-    shares = [list(range(i, len(frames), nthreads)) for i in range(nthreads)]
-    for d, idxs in zip(decs, shares):
-        d.set_hf_streams_per_cta(hf_lanes)
-        for k in idxs:
-            d.preload(k, frames[k])
-    packed = [None] * len(frames)
+    tdt = torch.uint8 if args.gather == "u8" else torch.uint16
+    pipe = J.Pipeline(local_rank, workers=args.contexts, heavy_frames=args.heavy_frames, hf_streams_per_cta=hf_lanes,
+                      batch_streams=args.batch_streams)
+    distinct, slots = {}, []
+    for f in frames:
+        if id(f) not in distinct:
+            distinct[id(f)] = len(distinct)
+            pipe.preload(distinct[id(f)], f)
+        slots.append(distinct[id(f)])
+    d0 = J.Decoder(local_rank)
+    d0.decode(frames[0])
+    shape = tuple(d0.frame_to_buffer(0, np.uint8).shape)
+    d0.close()
+    bufs = [[torch.empty(shape, dtype=tdt, device=f"cuda:{local_rank}") for _ in frames] for _ in range(2)]
+    state = {"step": 0}
 
-    def decode_all():
-        errs = []
+    def decode_step(with_gather):
+        cur = bufs[state["step"] & 1]
+        state["step"] += 1
+        done = set()
+        for k in range(len(frames)):
+            pipe.submit(slot=slots[k], out=cur[k], tag=k)
 
-        def work(d, idxs):
-            try:
-                for k in idxs:
-                    d.decode_slot(k)
-                    packed[k] = d.frame_to_torch(0, gdt, out=packed[k])
-                    d.release_frames()
-            except Exception as e:  # noqa: BLE001
-                errs.append(e)
-        ts = [threading.Thread(target=work, args=(d, idxs)) for d, idxs in zip(decs, shares)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
+        def getter(k):
+            def g():
+                while k not in done:
+                    done.add(pipe.wait())
+                return cur[k]
+            return g
+        if with_gather:
+            got = sharding.gather_frames([getter(k) for k in range(len(frames))], len(frames) * world, dst=0)
+        else:
+            got = None
+        pipe.drain()
+        return got
 
-    def gather_step():
-        decode_all()
-        return sharding.gather_frames(packed, len(frames) * world, dst=0)
-
-    got = gather_step()
+    got = decode_step(True)
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for _ in range(args.steps):
-        got = gather_step()
+        got = decode_step(True)
     torch.cuda.synchronize()
     g1.record()
     g1.synchronize()
@@ -536,28 +546,28 @@ def run_gather(args, torch, dist, J, local_rank, world, rank, frames, total_px, 
     if dist is not None:
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
     ms_g = float(tg.item())
-    # decode + pack without the collective, same threads: what the gather adds
+    # decode + pack without the collective: what the gather adds
     barrier()
-    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d0.record()
+    d0e, d1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d0e.record()
     for _ in range(args.steps):
-        decode_all()
+        decode_step(False)
     torch.cuda.synchronize()
-    d1.record()
-    d1.synchronize()
-    td = torch.tensor([d0.elapsed_time(d1)], device="cuda")
+    d1e.record()
+    d1e.synchronize()
+    td = torch.tensor([d0e.elapsed_time(d1e)], device="cuda")
     if dist is not None:
         dist.all_reduce(td, op=dist.ReduceOp.MAX)
     ms_d = float(td.item())
-    nbytes = int(packed[0].numel() * packed[0].element_size())
-    for d in decs:
-        d.close()
+    nbytes = int(bufs[0][0].numel() * bufs[0][0].element_size())
+    pipe.close()
     return {"value": total_px / (ms_g / args.steps / 1e3) / 1e6, "unit": "MP/s", "ms_per_step": ms_g / args.steps,
             "decode_pack_only": {"value": total_px / (ms_d / args.steps / 1e3) / 1e6, "ms_per_step": ms_d / args.steps},
-            "format": f"{args.gather} interleaved RGB, packed on the device",
+            "format": f"{args.gather} interleaved RGB, packed on the device by the pipeline (out_mode 4/5)",
             "bytes_to_rank0_per_step": nbytes * len(frames) * (world - 1),
             "nvlink_gb_s_into_rank0": nbytes * len(frames) * (world - 1) / (ms_g / args.steps / 1e3) / 1e9,
-            "collective": "torch.distributed gather (nccl), one per round of world_size frames" if world > 1 else "none (1 rank)",
+            "collective": "torch.distributed gather (nccl), one per round of world_size frames, overlapped with the decode of later frames"
+                          if world > 1 else "none (1 rank)",
             "frames_at_rank0": (len([g for g in got if g is not None]) if got is not None else 0) if rank == 0 else None}
 
 
@@ -636,7 +646,6 @@ def main():
     ap.add_argument("--heavy-frames", type=int, default=0,
                     help="heavy slots (HBM slab + CUDA stream) per GPU (0: 20, Modular workloads 26)")
     ap.add_argument("--batch-streams", type=int, default=6, help="CUDA streams of the LF batch service")
-    ap.add_argument("--gather-contexts", type=int, default=8)
     ap.add_argument("--frames-per-step", type=int, default=48, help="independent frames decoded per step per GPU")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (experiments only)")

@@ -163,6 +163,25 @@ int32_t jxlb_squeeze_inverse(jxlb_decoder* dec, const int32_t* avg, uint32_t avg
 int32_t jxlb_blend(jxlb_decoder* dec, float* base, const float* patch, const float* base_alpha, const float* new_alpha,
                    uint32_t width, uint32_t height, uint32_t stride, int32_t mode, int32_t clamp, int32_t premultiplied,
                    int32_t swapped);
+/* ---- Stage entry points of the decode seams. Each decodes the first frame of `data` up to and including
+ * one stage, copies that stage's planes into caller-owned DEVICE buffers (row pitch `stride` 32-bit words, NULL entries
+ * skipped) and stops there: what a Rust-side test of the corresponding reference function compares against.
+ * JXLB_ERR_UNSUPPORTED when the frame has no such stage (e.g. a Modular frame has no HF groups). ---- */
+/* decode_pass_group -> write_hf_coeff for every group and pass (crates/jxl-frame/src/data/pass_group.rs:11-46,
+ * crates/jxl-vardct/src/hf_coeff.rs:21-252): the accumulated quantised coefficients, i32, X / Y / B planes of
+ * (8 * ceil(w / 8)) x (8 * ceil(h / 8)) samples (`width`, `height` out; call with coeff = NULL to size the buffers). */
+int32_t jxlb_decode_hf_groups(jxlb_decoder* dec, const uint8_t* data, size_t size, int32_t* const coeff[3], uint32_t stride,
+                              uint32_t* width, uint32_t* height);
+/* dequant_hf_varblock_grouped + chroma_from_luma_hf_grouped + transform_varblocks
+ * (crates/jxl-render/src/vardct/mod.rs:442-603, 681): the XYB samples before the restoration filters, f32. */
+int32_t jxlb_dequant_idct(jxlb_decoder* dec, const uint8_t* data, size_t size, float* const planes[3], uint32_t stride,
+                          uint32_t* width, uint32_t* height);
+/* Modular channel decode of a frame's Modular image (global, LF-group and pass-group streams,
+ * crates/jxl-modular/src/image.rs:456-593) BEFORE the inverse transforms: the coded channels in coding order, i32.
+ * `dims` receives width, height per coded channel (up to dims_cap / 2), `num_coded` their number; call with
+ * channels = NULL first to size the buffers. */
+int32_t jxlb_modular_decode_groups(jxlb_decoder* dec, const uint8_t* data, size_t size, int32_t* const* channels,
+                                   uint32_t num_channels, uint32_t stride, uint32_t* num_coded, uint32_t* dims, uint32_t dims_cap);
 /* features::upsample (crates/jxl-render/src/features/upsampling.rs:45-132) with the default weight tables
  * (crates/jxl-image/src/lib.rs upsampling weights): `in` (w x h, stride in floats) -> `out` ((w * factor) x (h * factor)),
  * factor 2, 4 or 8; both DEVICE pointers. */
@@ -210,7 +229,9 @@ int32_t jxlb_pipeline_preload(jxlb_pipeline* p, int32_t slot, const uint8_t* dat
  * planar f32 (channel-major, Render::image_planar), 2 / 3: ImageStream::write_to_buffer::<u8 / u16> (interleaved, image
  * orientation, packed on the device). The pixels go to host `dst` or, with dst = NULL, into a pinned buffer of the
  * pipeline's own ring (allocated NUMA-local to the GPU by the worker threads) that jxlb_pipeline_wait hands out and
- * jxlb_pipeline_release_output takes back. `tag` comes back from jxlb_pipeline_wait. Never blocks. */
+ * jxlb_pipeline_release_output takes back. out_mode 4 / 5: the same u8 / u16 packing into DEVICE memory `dst` (of the
+ * pipeline's GPU) - how BASELINE config #5 feeds an NCCL gather without touching the host. `tag` comes back from
+ * jxlb_pipeline_wait. Never blocks. */
 int32_t jxlb_pipeline_submit(jxlb_pipeline* p, const uint8_t* data, size_t size, int32_t slot, int32_t out_mode, void* dst,
                              size_t dst_bytes, uint64_t tag);
 /* Blocks until a submitted frame has finished (its output, if any, is complete in `dst`); returns its tag and decode

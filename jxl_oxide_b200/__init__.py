@@ -25,7 +25,8 @@ OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVI
 
 # every symbol include/jxlb200.h declares
 EXPORTED_SYMBOLS = [
-    "jxlb_decoder_create", "jxlb_decoder_create_ex", "jxlb_decode_frame_sections", "jxlb_upsample", "jxlb_decoder_destroy", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
+    "jxlb_decoder_create", "jxlb_decoder_create_ex", "jxlb_decode_frame_sections", "jxlb_upsample", "jxlb_decoder_destroy",
+    "jxlb_decode_hf_groups", "jxlb_dequant_idct", "jxlb_modular_decode_groups", "jxlb_last_error", "jxlb_decode", "jxlb_preload", "jxlb_decode_slot",
     "jxlb_image_get_info", "jxlb_image_original_icc",
     "jxlb_num_frames", "jxlb_frame_get_info", "jxlb_frame_channel_to_host", "jxlb_frame_stream_channels", "jxlb_frame_write_to_buffer", "jxlb_frame_write_to_device", "jxlb_frame_channel_device",
     "jxlb_release_frames", "jxlb_sync", "jxlb_launch_count", "jxlb_set_profile", "jxlb_profile_get",
@@ -95,6 +96,10 @@ def load_library():
     L.jxlb_decoder_create_ex.restype = i32
     L.jxlb_decode_frame_sections.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(_Section), ctypes.c_size_t, ctypes.POINTER(_Options)]
     L.jxlb_upsample.argtypes = [vp, vp, u32, u32, u32, u32, vp, u32]
+    L.jxlb_decode_hf_groups.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    L.jxlb_dequant_idct.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+    L.jxlb_modular_decode_groups.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), u32, u32, ctypes.POINTER(u32),
+                                             ctypes.POINTER(u32), u32]
     L.jxlb_decoder_destroy.argtypes = [vp]
     L.jxlb_decoder_destroy.restype = None
     L.jxlb_last_error.argtypes = [vp]
@@ -180,6 +185,38 @@ class Decoder:
         arr = (_Section * len(sections))(*[_Section(s, len(s)) for s in sections])
         opt = _Options(output_colour, max_frames)
         self._check(self._L.jxlb_decode_frame_sections(self._h, header, len(header), arr, len(sections), ctypes.byref(opt)))
+
+    def _stage_planes(self, fn, data, dtype):
+        import torch
+        w, h = ctypes.c_uint32(), ctypes.c_uint32()
+        self._check(fn(self._h, data, len(data), None, 0, ctypes.byref(w), ctypes.byref(h)))
+        planes = [torch.empty((h.value, w.value), dtype=dtype, device=f"cuda:{self.device}") for _ in range(3)]
+        ptrs = (ctypes.c_void_p * 3)(*[int(p.data_ptr()) for p in planes])
+        self._check(fn(self._h, data, len(data), ptrs, w.value, ctypes.byref(w), ctypes.byref(h)))
+        return planes
+
+    def decode_hf_groups(self, data):
+        """jxlb_decode_hf_groups: the quantised HF coefficients (X, Y, B; int32 CUDA tensors)."""
+        import torch
+        return self._stage_planes(self._L.jxlb_decode_hf_groups, data, torch.int32)
+
+    def dequant_idct(self, data):
+        """jxlb_dequant_idct: the XYB samples after dequantisation and the inverse transforms (float32 CUDA tensors)."""
+        import torch
+        return self._stage_planes(self._L.jxlb_dequant_idct, data, torch.float32)
+
+    def modular_decode_groups(self, data):
+        """jxlb_modular_decode_groups: the coded channels of the frame's Modular image before the inverse transforms."""
+        import torch
+        n = ctypes.c_uint32()
+        dims = (ctypes.c_uint32 * 2048)()
+        self._check(self._L.jxlb_modular_decode_groups(self._h, data, len(data), None, 0, 0, ctypes.byref(n), dims, 2048))
+        shapes = [(dims[2 * i + 1], dims[2 * i]) for i in range(n.value)]
+        stride = max([s[1] for s in shapes] + [1])
+        chans = [torch.empty((max(s[0], 1), stride), dtype=torch.int32, device=f"cuda:{self.device}") for s in shapes]
+        ptrs = (ctypes.c_void_p * len(chans))(*[int(c.data_ptr()) for c in chans])
+        self._check(self._L.jxlb_modular_decode_groups(self._h, data, len(data), ptrs, len(chans), stride, ctypes.byref(n), dims, 2048))
+        return [c[: s[0], : s[1]] for c, s in zip(chans, shapes)]
 
     def upsample(self, src, factor):
         """features::upsample with the default weights on a device tensor (h, w) float32 -> (h * factor, w * factor)."""
@@ -380,7 +417,7 @@ class Pipeline:
     most `heavy_frames` of them past the LF stage. The analogue of decoding keyframes in a rayon par_iter
     (crates/jxl-oxide-cli/src/decode.rs:285-320)."""
 
-    OUT_NONE, OUT_PLANAR_F32, OUT_U8, OUT_U16 = 0, 1, 2, 3
+    OUT_NONE, OUT_PLANAR_F32, OUT_U8, OUT_U16, OUT_U8_DEVICE, OUT_U16_DEVICE = 0, 1, 2, 3, 4, 5
 
     def __init__(self, device=0, workers=0, heavy_frames=0, hf_streams_per_cta=0, no_affinity=False, batch_streams=0):
         self._L = load_library()
@@ -409,9 +446,14 @@ class Pipeline:
         if tag is None:
             tag = self._next_tag
             self._next_tag += 1
-        if mode is None:  # with out=None pass mode explicitly to get the pixels in a pipeline-owned pinned buffer
+        if mode is None and not hasattr(out, "data_ptr"):  # out=None + explicit mode: pixels in a pipeline-owned pinned buffer
             mode = self.OUT_NONE if out is None else {np.dtype(np.float32): 1, np.dtype(np.uint8): 2, np.dtype(np.uint16): 3}[out.dtype]
-        dst, nbytes = (out.ctypes.data, out.nbytes) if out is not None else (None, 0)
+        if out is not None and hasattr(out, "data_ptr"):  # a torch CUDA tensor: packed on the device, never leaves HBM
+            if mode is None or mode < 4:
+                mode = {1: self.OUT_U8_DEVICE, 2: self.OUT_U16_DEVICE}[out.element_size()]
+            dst, nbytes = int(out.data_ptr()), out.numel() * out.element_size()
+        else:
+            dst, nbytes = (out.ctypes.data, out.nbytes) if out is not None else (None, 0)
         buf = None
         if data is not None:
             buf = ctypes.c_char_p(data)
@@ -438,6 +480,8 @@ class Pipeline:
         if status.value != OK:
             raise JxlError(status.value, msg.value.decode(errors="replace"))
         owned = out.value is not None and (kept is None or kept[2] is None)
+        if kept is not None and kept[2] is not None and hasattr(kept[2], "data_ptr"):
+            owned = False
         if want_output:
             return tag.value, out.value, nbytes.value
         if owned:

@@ -120,6 +120,70 @@ int32_t jxlb_decode_frame_sections(jxlb_decoder* dec, const uint8_t* header, siz
   return jxlb_decode(dec, joined.data(), joined.size(), opt);
 }
 
+namespace {
+// Decodes `data` up to the named stage and copies that stage's planes into the caller's device buffers.
+int32_t decode_until(jxlb_decoder* dec, const uint8_t* data, size_t size, const char* stage, void* const* dst, uint32_t num_dst,
+                     uint32_t dst_stride, uint32_t* num_planes, uint32_t* dims, uint32_t dims_cap) {
+  if (!dec || !data) return JXLB_ERR_INVALID_ARG;
+  CudaBackend& be = *dec->be;
+  be.stop_stage = stage;
+  be.stop_dst.assign(dst ? dst : nullptr, dst ? dst + num_dst : nullptr);
+  be.stop_stride = dst_stride;
+  be.stop_dims.clear();
+  bool reached = false;
+  int32_t rc = guarded(dec, [&] {
+    release(dec);
+    dec->codestream = extract_codestream(data, size);
+    DecodeOptions o;
+    o.max_frames = 1;
+    try {
+      DecodeResult res = decode_codestream(be, dec->codestream.data(), dec->codestream.size(), o);
+      for (DecodedFrame& f : res.frames)  // the stage does not exist in this frame: nothing to hand out
+        for (View& v : f.channels) be.free_plane(v.plane);
+    } catch (const StopDecode&) {
+      reached = true;
+    }
+  });
+  be.stop_stage.clear();
+  be.stop_dst.clear();
+  if (rc != JXLB_OK) return rc;
+  if (!reached) {
+    dec->error = std::string("the frame has no stage '") + stage + "'";
+    return JXLB_ERR_UNSUPPORTED;
+  }
+  if (num_planes) *num_planes = uint32_t(be.stop_dims.size());
+  for (size_t i = 0; dims && i < be.stop_dims.size() && 2 * i + 1 < dims_cap; ++i) {
+    dims[2 * i] = be.stop_dims[i].first;
+    dims[2 * i + 1] = be.stop_dims[i].second;
+  }
+  return JXLB_OK;
+}
+}  // namespace
+
+int32_t jxlb_decode_hf_groups(jxlb_decoder* dec, const uint8_t* data, size_t size, int32_t* const coeff[3], uint32_t stride,
+                              uint32_t* width, uint32_t* height) {
+  uint32_t dims[6] = {0, 0, 0, 0, 0, 0}, n = 0;
+  const int32_t rc = decode_until(dec, data, size, "hf_coeff", reinterpret_cast<void* const*>(coeff), coeff ? 3 : 0, stride, &n, dims, 6);
+  if (rc == JXLB_OK && width) *width = dims[0];
+  if (rc == JXLB_OK && height) *height = dims[1];
+  return rc;
+}
+
+int32_t jxlb_dequant_idct(jxlb_decoder* dec, const uint8_t* data, size_t size, float* const planes[3], uint32_t stride,
+                          uint32_t* width, uint32_t* height) {
+  uint32_t dims[6] = {0, 0, 0, 0, 0, 0}, n = 0;
+  const int32_t rc = decode_until(dec, data, size, "idct", reinterpret_cast<void* const*>(planes), planes ? 3 : 0, stride, &n, dims, 6);
+  if (rc == JXLB_OK && width) *width = dims[0];
+  if (rc == JXLB_OK && height) *height = dims[1];
+  return rc;
+}
+
+int32_t jxlb_modular_decode_groups(jxlb_decoder* dec, const uint8_t* data, size_t size, int32_t* const* channels,
+                                   uint32_t num_channels, uint32_t stride, uint32_t* num_coded, uint32_t* dims, uint32_t dims_cap) {
+  return decode_until(dec, data, size, "modular_coded", reinterpret_cast<void* const*>(channels), channels ? num_channels : 0, stride,
+                      num_coded, dims, dims_cap);
+}
+
 int32_t jxlb_upsample(jxlb_decoder* dec, const float* in, uint32_t width, uint32_t height, uint32_t stride, uint32_t factor,
                       float* out, uint32_t out_stride) {
   if (!dec || !in || !out || (factor != 2 && factor != 4 && factor != 8) || !width || !height) return JXLB_ERR_INVALID_ARG;

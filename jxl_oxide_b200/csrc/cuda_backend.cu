@@ -259,7 +259,8 @@ void CudaBackend::sync() {
   launch_signal_word(const_cast<uint32_t*>(h_flag_), seq, S());
   ++launches;
   uint32_t spins = 0;
-  auto t0 = std::chrono::steady_clock::now();
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto t0 = t_begin;
   while (*h_flag_ != seq) {
     if (++spins < 2000) {
 #if defined(__x86_64__)
@@ -267,8 +268,12 @@ void CudaBackend::sync() {
 #endif
       continue;
     }
-    std::this_thread::sleep_for(std::chrono::microseconds(50));
-    if ((spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) {
+    // naps grow with the time already waited (1/8 of it, 20..200 us): a short kernel is noticed within microseconds, a
+    // 15 ms one costs its thread ~100 wake-ups instead of 300
+    const auto waited = std::chrono::steady_clock::now() - t_begin;
+    const long nap_us = std::min<long>(200, std::max<long>(20, std::chrono::duration_cast<std::chrono::microseconds>(waited).count() / 8));
+    std::this_thread::sleep_for(std::chrono::microseconds(nap_us));
+    if ((spins & 255) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(200)) {
       // a faulting kernel never writes the word: ask the driver from time to time
       cudaError_t e = cudaStreamQuery(S());
       if (e == cudaSuccess) break;
@@ -510,6 +515,22 @@ void CudaBackend::phase_mark(const char* name) {
 }
 
 void CudaBackend::stage_marker(const char* name, const View* views, int n) {
+  if (!stop_stage.empty() && stop_stage == name) {
+    // stage entry points (jxlb_decode_hf_groups, jxlb_dequant_idct, jxlb_modular_decode_groups): hand the stage's planes
+    // to the caller's device buffers and end the decode here
+    stop_dims.clear();
+    for (int i = 0; i < n; ++i) {
+      stop_dims.push_back({views[i].w, views[i].h});
+      if (size_t(i) < stop_dst.size() && stop_dst[size_t(i)] && views[i].w && views[i].h) {
+        JXLB_CHECK(stop_stride >= views[i].w, kErrInvalidArg, "destination stride smaller than the stage's planes");
+        const DevView d = dev_view(views[i]);
+        CUDA_CHECK(cudaMemcpy2DAsync(stop_dst[size_t(i)], size_t(stop_stride) * 4, d.ptr, size_t(d.stride) * 4, size_t(views[i].w) * 4,
+                                     views[i].h, cudaMemcpyDeviceToDevice, S()));
+      }
+    }
+    sync();
+    throw StopDecode();
+  }
   if (!capture) return;
   auto& out = stages[name];
   auto& dims = stage_dims[name];

@@ -39,6 +39,8 @@ class LfBatchService {
   virtual void run(LfBatchItem& item) = 0;  // throws jxlb::Error on a CUDA failure
 };
 
+struct StopDecode {};  // thrown by stage_marker() when a stage entry point has what it asked for
+
 class CudaBackend : public Backend {
  public:
   // own_stream = false: a pipeline decoder. It borrows the stream of a heavy slot (on_heavy_stage -> set_stream) and
@@ -114,6 +116,11 @@ class CudaBackend : public Backend {
   // device pointer + stride (elements) of a view's top-left element
   DevView dev_view(const View& v) const;
 
+  // stage entry points: decode up to `stop_stage`, copy its planes to `stop_dst` (device, row pitch `stop_stride` words)
+  std::string stop_stage;
+  std::vector<void*> stop_dst;
+  uint32_t stop_stride = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> stop_dims;  // out: width, height of every plane of the stage
   // test hook: when on, stage_marker() snapshots planes to host memory
   bool capture = false;
   std::map<std::string, std::vector<std::vector<uint32_t>>> stages;

@@ -739,6 +739,11 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   }
 
   be_.phase_mark("pass_groups");
+  if (lfg_.has_gmodular) {  // the decoded (still transformed) channels of the frame's Modular image, coding order
+    std::vector<View> coded;
+    for (const ChanBuf& c : gm_coded_) coded.push_back(c.view);
+    be_.stage_marker("modular_coded", coded.data(), int(coded.size()));
+  }
   // ---- global inverse transforms ----
   std::vector<ChanBuf> gm_image = gm_coded_;
   if (lfg_.has_gmodular) run_inverse_transforms(lfg_.gmodular, gm_image);

@@ -127,13 +127,14 @@ __device__ __forceinline__ constexpr int plus_y(int step, int i) {
 // map 0 (maps kPlane apart). dist_d(q) = sum_c scale_c * sum_o |a_c[q+d+o] - a_c[q+o]|, accumulated exactly like
 // epf.rs (acc starts at 0.0, so the first addition is exact; likewise dist).
 template <int STEP>
-__device__ __forceinline__ void epf_dist(const float* a, float* d, const DevEpfParams& p) {
+__device__ __forceinline__ void epf_dist(const float* __restrict__ a, float* __restrict__ d, const DevEpfParams& p) {
   constexpr int NM = STEP == 0 ? 6 : 2;
   constexpr int ND = STEP == 2 ? 1 : 5;
+  float dist[NM];  // all maps first, stores last: a store between them would make the compiler reload every sample
 #pragma unroll
   for (int m = 0; m < NM; ++m) {
     const int dx = dplus_x(STEP, m), dy = dplus_y(STEP, m);
-    float dist = 0.0f;
+    dist[m] = 0.0f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float acc = 0.0f;
@@ -142,10 +143,11 @@ __device__ __forceinline__ void epf_dist(const float* a, float* d, const DevEpfP
         const int ox = plus_x(STEP, i), oy = plus_y(STEP, i);
         acc = fadd(acc, fabsf(fsub(a[c * kPlane + (dy + oy) * kS + dx + ox], a[c * kPlane + oy * kS + ox])));
       }
-      dist = fadd(dist, fmul(p.channel_scale[c], acc));
+      dist[m] = fadd(dist[m], fmul(p.channel_scale[c], acc));
     }
-    d[m * kPlane] = dist;
   }
+#pragma unroll
+  for (int m = 0; m < NM; ++m) d[m * kPlane] = dist[m];
 }
 
 // Half-stage 2: weights and weighted sums at pixel p in the reference's neighbour order; `a` points at p in channel 0 of
@@ -266,14 +268,20 @@ __device__ __forceinline__ void xyb_px(float o[3], const DevColorParams& p) {  /
 // Visits every cell of `r` once with all 256 threads busy: the cells are numbered row by row and thread t takes cells
 // t, t + 256, ... (a 35 x 35 region walked as 32-wide column strips would leave the second strip 3 lanes wide). One
 // integer division per call; afterwards (x, y) advance incrementally.
+__device__ __constant__ const uint32_t kRecip16[49] = {
+    0,     65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096,
+    3856,  3641,  3450,  3277,  3121,  2979,  2850,  2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048, 1986,
+    1928,  1873,  1821,  1772,  1725,  1681,  1639,  1599, 1561, 1525, 1490, 1457, 1425, 1395, 1366};
 template <typename F>
 __device__ __forceinline__ void for_region(const Rect& r, F&& f) {
   const int w = r.x1 - r.x0, h = r.y1 - r.y0;
   if (w <= 0 || h <= 0) return;
   const int n = w * h;
   const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
-  int ly = tid / w, lx = tid - ly * w;
-  const int dy = 256 / w, dx = 256 - dy * w;
+  // tid / w and 256 / w without a division: ceil(2^16 / w) * t >> 16 == t / w for t <= 256, w <= 48
+  const uint32_t rcp = kRecip16[w];
+  int ly = int((uint32_t(tid) * rcp) >> 16), lx = tid - ly * w;
+  const int dy = int((256u * rcp) >> 16), dx = 256 - dy * w;
   for (int i = tid; i < n; i += 256) {
     f(r.x0 + lx, r.y0 + ly);
     lx += dx;

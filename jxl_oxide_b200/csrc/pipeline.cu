@@ -248,7 +248,7 @@ class BatchService : public LfBatchService {
         launch(*free_batch, take);
         continue;
       }
-      std::this_thread::sleep_for(std::chrono::microseconds(40));
+      std::this_thread::sleep_for(std::chrono::microseconds(60));
     }
   }
 
@@ -458,7 +458,12 @@ struct jxlb_pipeline {
           rc = decode_resident(dec, r->codestream.data(), r->codestream.size(), r->dptr, nullptr);
         }
       }
-      if (rc == JXLB_OK && job.out_mode != 0) {
+      if (rc == JXLB_OK && (job.out_mode == 4 || job.out_mode == 5)) {
+        // packed straight into the caller's device buffer (input of an NCCL gather): no host link involved
+        rc = jxlb_frame_write_to_device(dec, 0, job.out_mode - 4, 0, job.dst, job.dst_bytes);
+        d.out = job.dst;
+        d.out_bytes = job.dst_bytes;
+      } else if (rc == JXLB_OK && job.out_mode != 0) {
         void* dst = job.dst;
         size_t dst_bytes = job.dst_bytes;
         if (!dst) {  // library-owned pinned staging, sized from the decoded frame
@@ -595,7 +600,7 @@ int32_t jxlb_pipeline_preload(jxlb_pipeline* p, int32_t slot, const uint8_t* dat
 
 int32_t jxlb_pipeline_submit(jxlb_pipeline* p, const uint8_t* data, size_t size, int32_t slot, int32_t out_mode, void* dst,
                              size_t dst_bytes, uint64_t tag) {
-  if (!p || out_mode < 0 || out_mode > 3 || (!data && slot < 0)) return JXLB_ERR_INVALID_ARG;
+  if (!p || out_mode < 0 || out_mode > 5 || (!data && slot < 0) || (out_mode >= 4 && !dst)) return JXLB_ERR_INVALID_ARG;
   Job j;
   j.data = data;
   j.size = size;

@@ -37,16 +37,23 @@ def gather_frames(local_frames, num_frames, dst=0, group=None):
     if len(local_frames) != len(mine):
         raise ValueError(f"rank {rank} holds {len(local_frames)} frames, its share of {num_frames} is {len(mine)}")
     if world == 1:
-        return list(local_frames)
+        return [f() if callable(f) else f for f in local_frames]
     rounds = (num_frames + world - 1) // world
     # a rank without a frame in the last (ragged) round still takes part in the collective with a dummy
     proto = local_frames[0] if local_frames else None
+    if callable(proto):
+        proto = None
     out = [None] * num_frames
     for r in range(rounds):
         have = r < len(local_frames)
         if have:
-            send = local_frames[r].contiguous()
+            f = local_frames[r]
+            if callable(f):  # a frame still being decoded: f() blocks until it is packed (decode overlaps earlier rounds)
+                f = f()
+            send = f.contiguous()
         else:
+            if proto is None and have is False and local_frames and callable(local_frames[0]):
+                proto = local_frames[0]()
             if proto is None:
                 raise ValueError("a rank without any frame cannot size its placeholder; pass at least world_size frames")
             send = torch.empty_like(proto)

@@ -71,6 +71,9 @@ def test_round2_entry_points_reject_bad_arguments_without_a_device():
     assert L.jxlb_pipeline_create(0, None, None) == J.ERR_INVALID_ARG
     assert L.jxlb_decode_frame_sections(None, b"x", 1, None, 0, None) == J.ERR_INVALID_ARG
     assert L.jxlb_upsample(None, None, 1, 1, 1, 2, None, 2) == J.ERR_INVALID_ARG
+    assert L.jxlb_decode_hf_groups(None, b"x", 1, None, 0, None, None) == J.ERR_INVALID_ARG
+    assert L.jxlb_dequant_idct(None, b"x", 1, None, 0, None, None) == J.ERR_INVALID_ARG
+    assert L.jxlb_modular_decode_groups(None, b"x", 1, None, 0, 0, None, None, 0) == J.ERR_INVALID_ARG
     assert L.jxlb_pipeline_submit(None, None, 0, 0, 0, None, 0, 0) == J.ERR_INVALID_ARG
     assert L.jxlb_pipeline_release_output(None, None) == J.ERR_INVALID_ARG
     assert L.jxlb_pipeline_workers(None) == 0 and L.jxlb_pipeline_launch_count(None) == 0

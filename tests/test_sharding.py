@@ -66,6 +66,8 @@ def _gather_worker(rank, world, port, num_frames, out):
     mine = sharding.frames_for_rank(num_frames, rank, world)
     # frame k = a small "packed" u8 image filled with k
     local = [torch.full((4, 6, 3), k, dtype=torch.uint8) for k in mine]
+    if num_frames % 2:  # the streaming form: frames handed over as callables that produce them when their round comes
+        local = [(lambda t=t: t) for t in local]
     got = sharding.gather_frames(local, num_frames, dst=0)
     dist.barrier()
     if rank == 0:
@@ -97,3 +99,5 @@ def test_gather_frames_in_frame_order_gloo(num_frames):
 def test_gather_frames_single_process_is_identity():
     frames = [torch.zeros(2, 2, 3, dtype=torch.uint8) for _ in range(3)]
     assert sharding.gather_frames(frames, 3) == frames
+    got = sharding.gather_frames([(lambda t=t: t) for t in frames], 3)
+    assert all(a is b for a, b in zip(got, frames))

@@ -53,3 +53,41 @@ def test_decode_frame_sections(oracle):
     d.decode_sections(header, sections)
     assert np.array_equal(d.frame_planar(0).view(np.uint32), want.view(np.uint32))
     d.close()
+
+
+def test_stage_entry_points_vardct(oracle):
+    """jxlb_decode_hf_groups / jxlb_dequant_idct: the seams between entropy decode, dequant + IDCT and the filters, on
+    caller-owned device planes, against the same stages of the oracle."""
+    import jxl_oxide_b200 as J
+    data = bench.synth_frame(1000, 600, 5)
+    img = oracle.OracleImage(data, threads=8, capture=True)
+    want_coeff, want_idct, want_px = img.stage("hf_coeff", np.int32), img.stage("idct", np.float32), img.frame(0)[0]
+    img.close()
+    d = J.Decoder(0)
+    coeff = d.decode_hf_groups(data)
+    assert len(coeff) == 3
+    for g, w in zip(coeff, want_coeff):
+        assert tuple(g.shape) == w.shape and np.array_equal(g.cpu().numpy(), w)
+    for g, w in zip(d.dequant_idct(data), want_idct):
+        assert tuple(g.shape) == w.shape and np.array_equal(g.cpu().numpy().view(np.uint32), w.view(np.uint32))
+    assert d.modular_decode_groups(data) == []       # a VarDCT frame without extra channels codes no Modular channel
+    d.decode(data)                                   # the decoder is left usable
+    assert np.array_equal(d.frame_planar(0).view(np.uint32), want_px.view(np.uint32))
+    d.close()
+
+
+def test_stage_entry_point_modular(oracle):
+    import jxl_oxide_b200 as J
+    data = bench.synth_frame(600, 400, 3, extra=("--modular",))
+    img = oracle.OracleImage(data, threads=8, capture=True)
+    want = img.stage("modular_coded", np.int32)
+    img.close()
+    d = J.Decoder(0)
+    got = d.modular_decode_groups(data)
+    assert len(got) == len(want) and len(got) > 3    # squeezed: residual channels besides the three colour channels
+    for g, w in zip(got, want):
+        assert tuple(g.shape) == w.shape and np.array_equal(g.cpu().numpy(), w)
+    with pytest.raises(J.JxlError) as e:
+        d.decode_hf_groups(data)                     # no HF groups in a Modular frame
+    assert e.value.code == J.ERR_UNSUPPORTED
+    d.close()
