@@ -120,7 +120,7 @@ class ClockSampler:
             h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
         pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # raises when unsupported
         bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
-        self.nvml_samples, self.nvml_reasons, self.nvml_max = [], set(), None
+        self.nvml_samples, self.nvml_reasons, self.nvml_max, self.nvml_util = [], set(), None, []
         self._halt = threading.Event()
 
         def poll():
@@ -128,6 +128,7 @@ class ClockSampler:
                 try:
                     self.nvml_samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
                     self.nvml_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+                    self.nvml_util.append(float(pynvml.nvmlDeviceGetUtilizationRates(h).gpu))
                     mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                     for n, b in bits.items():
                         if mask & b:
@@ -170,6 +171,7 @@ class ClockSampler:
             if self.nvml_samples:
                 return {"sm_mhz": float(np.median(self.nvml_samples)), "sm_max_mhz": self.nvml_max,
                         "reasons": sorted(self.nvml_reasons), "samples": len(self.nvml_samples),
+                        "gpu_busy_pct_mean": (float(np.mean(self.nvml_util)) if self.nvml_util else None),
                         "how": "NVML polled every 200 ms during the timed region"}
         if self.proc is not None:
             try:
@@ -246,8 +248,13 @@ def gpu_local_cpus(device_index):
         return []
 
 
-# HF coefficient schedule of the timed run: fixed (ncu evidence in profiles/r02_*), never probed inside the bench.
-HF_STREAMS_PER_CTA = 16
+# HF coefficient schedule of the timed run: fixed, never probed inside the bench. 128 = one THREAD per stream (32 streams per
+# warp): a frame's 510 streams then take 16 warps for ~42 ms instead of 510 one-lane warps for ~14 ms. With ~26 frames
+# in their heavy stage the one-lane form alone asks for more warp slots than the GPU has (26 x 510 > 148 x 64) and starves
+# the pixel kernels; measured whole-job (profiles/r02_progress.md section 6): 185-197 frames/s against 116-167.
+# jxlb_decode (one frame, latency matters) keeps the 16-warp form.
+HF_STREAMS_PER_CTA = 128
+HF_LATENCY_SCHEDULE = 16
 CHAIN = ["hf_dequant_cfl", "hf_transform", "filters_fused", "gaborish", "epf_step", "xyb_to_rgb"]
 # Modular frames: the HBM-bound part is everything after the entropy decode (inverse Squeeze, RCT, sample conversion)
 MODULAR_CHAIN = ["squeeze_inverse", "rct_inverse", "int_to_float", "copy_rect", "modular_xyb", "palette_inverse_simple"]
@@ -272,7 +279,7 @@ def run_ours(args, rank, world, local_rank):
     desc, frames, (w, h) = load_workload(args.workload, args.frames_per_step)
     px_per_frame = w * h
     workers = args.contexts or (64 if "mod" in args.workload else 96)
-    heavy = args.heavy_frames or (26 if "mod" in args.workload else 20)
+    heavy = args.heavy_frames or 26  # + 6 batch streams = the device's 32 hardware queues
     args.contexts, args.heavy_frames = workers, heavy
     pipe = J.Pipeline(local_rank, workers=workers, heavy_frames=heavy, hf_streams_per_cta=hf_lanes, batch_streams=args.batch_streams)
     # encoded frames resident in HBM ("inputs already resident"): one preloaded slot per distinct frame
@@ -380,6 +387,22 @@ def run_ours(args, rank, world, local_rank):
             solo[k] = t / solo_reps
     for d in decs:
         d.set_profile(False)
+    # the same HF streams under the single-frame (latency) schedule, one frame alone
+    hf_latency_ms = None
+    if "decode_hf" in solo and hf_lanes != HF_LATENCY_SCHEDULE:
+        for d in decs:
+            d._L.jxlb_set_hf_streams_per_cta(d._h, HF_LATENCY_SCHEDULE)
+            d.set_profile(True)
+            d.profile_reset()
+        for _ in range(2):
+            pipe.submit(slot=slots[0])
+            pipe.wait()
+        n = sum(d.profile("decode_hf")[0] for d in decs)
+        if n:
+            hf_latency_ms = sum(d.profile("decode_hf")[1] for d in decs) / n
+        for d in decs:
+            d.set_profile(False)
+            d._L.jxlb_set_hf_streams_per_cta(d._h, hf_lanes)
 
     total_px = px_per_frame * len(frames) * world
     gather = None
@@ -443,6 +466,10 @@ def run_ours(args, rank, world, local_rank):
                    "ms_per_frame_under_load": {k: round(prof[k]["ms"] / len(frames), 3) for k in ENTROPY if k in prof},
                    "note": "serial ANS / context chains (one per LF-group stream, one per 256x256 group): reported as "
                            "symbols/s, not against the HBM roofline"}
+        if hf_latency_ms is not None:
+            entropy["decode_hf_ms_solo_latency_schedule"] = round(hf_latency_ms, 3)
+            entropy["hf_schedules"] = ("timed run: one thread per stream (hf_streams_per_cta=%d); latency schedule: one warp per "
+                                       "stream, %d per CTA (what jxlb_decode uses)" % (hf_lanes, HF_LATENCY_SCHEDULE))
         if sym and "decode_hf" in solo:
             entropy["hf_symbols_per_frame"] = sym.get("hf_symbols")
             entropy["hf_symbols_per_s_solo"] = sym.get("hf_symbols", 0) / (solo["decode_hf"] / 1e3)

@@ -126,8 +126,10 @@ int32_t jxlb_set_capture(jxlb_decoder* dec, int32_t on);
 int32_t jxlb_set_fuse_filters(jxlb_decoder* dec, int32_t on);
 /* Scheduling of the HF coefficient streams (one per 256x256 group and pass, jxl-frame/src/data/pass_group.rs:31): how
  * many streams share one CTA and its staged tables. 0 (default, = 16), 8, 16, 32: one warp per stream, all presets'
- * tables staged once per CTA; 4: the round-1 kernel; 64 / 128: one thread per stream (experimental, slower). Results are
- * identical; the process-wide default comes from the environment variable JXLB_HF_LANES. */
+ * tables staged once per CTA - the shortest time for ONE frame (14 ms per 8K frame); 4: the round-1 kernel; 64 / 128:
+ * one thread per stream (32 streams per warp): 42 ms for a frame alone, but 16 warps instead of 510, which is what a
+ * GPU full of frames wants (jxlb_pipeline_create's default). Results are identical; the process-wide default comes
+ * from the environment variable JXLB_HF_LANES. */
 int32_t jxlb_set_hf_streams_per_cta(jxlb_decoder* dec, int32_t streams);
 int32_t jxlb_stage_count(const jxlb_decoder* dec, const char* name);
 int32_t jxlb_stage_get(const jxlb_decoder* dec, const char* name, int32_t idx, uint32_t* width, uint32_t* height,
@@ -214,7 +216,7 @@ typedef struct jxlb_pipeline jxlb_pipeline;
 typedef struct {
   int32_t workers;            /* frames in flight (host threads); 0 = default (64) */
   int32_t heavy_frames;       /* heavy slots = slabs = CUDA streams for everything but the LF stage; 0 = default (16) */
-  int32_t hf_streams_per_cta; /* 0 = library default, see jxlb_set_hf_streams_per_cta */
+  int32_t hf_streams_per_cta; /* 0 = 128 (one thread per HF stream), see jxlb_set_hf_streams_per_cta */
   int32_t no_affinity;        /* 1 = leave the worker threads' CPU affinity alone */
   int32_t batch_streams;      /* CUDA streams of the LF batch service; 0 = default (6). heavy_frames + batch_streams
                                  should stay below 32, the number of hardware queues a process can use concurrently */

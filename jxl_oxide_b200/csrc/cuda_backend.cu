@@ -35,12 +35,13 @@ CudaBackend::CudaBackend(int device, bool own_stream) : device_(device), own_str
   CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_stage_), stage_cap_, cudaHostAllocDefault));
   CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_stage_), stage_cap_));
   result_cap_ = size_t(256) << 10;
-  CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_result_), result_cap_, cudaHostAllocDefault));
+  CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&h_result_), result_cap_, cudaHostAllocMapped));  // batched LF streams write here
   {
     void* f = nullptr;
-    CUDA_CHECK(cudaHostAlloc(&f, 64, cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostAlloc(&f, 128, cudaHostAllocMapped));
     h_flag_ = static_cast<volatile uint32_t*>(f);
-    *h_flag_ = 0;
+    h_flag_[0] = 0;
+    h_flag_[16] = 0;  // second word (own cache line): completion of this decoder's item in a batched LF launch
   }
   ensure_static_tables();
   // A private stream-ordered pool per decoder: freed planes are reused by this decoder's next frame
@@ -514,6 +515,16 @@ void CudaBackend::phase_mark(const char* name) {
   phase_t0_ = now;
 }
 
+// JXLB_DEBUG_SKIP (bit 0: HF decode, 1: dequant + transforms, 2: fused filters): tools/pipe_probe.py's "which stage
+// bounds the pipeline" experiment. The decoded pixels are garbage with any bit set; never set in tests or the bench.
+static int debug_skip() {
+  static const int v = [] {
+    const char* e = std::getenv("JXLB_DEBUG_SKIP");
+    return e ? std::atoi(e) : 0;
+  }();
+  return v;
+}
+
 void CudaBackend::stage_marker(const char* name, const View* views, int n) {
   if (!stop_stage.empty() && stop_stage == name) {
     // stage entry points (jxlb_decode_hf_groups, jxlb_dequant_idct, jxlb_modular_decode_groups): hand the stage's planes
@@ -948,8 +959,21 @@ void CudaBackend::decode_modular(std::vector<ModularStreamJob>& jobs) {
     uint8_t* h_end = h_result_;
     uint8_t* h_status = h_result_ + ((jobs.size() * 8 + 15) & ~size_t(15));
     JXLB_CHECK(size_t(h_status - h_result_) + jobs.size() * 4 <= result_cap_, kErrUnsupported, "too many stream jobs in one launch for the result buffer");
-    item.down[item.num_down++] = {h_end, d_end, jobs.size() * 8};
-    item.down[item.num_down++] = {h_status, d_status, jobs.size() * 4};
+    if (profile || ((stage_off_ + 15) & ~size_t(15)) + 4 > stage_cap_) {  // timing wanted (or no room for the counter):
+      // results come back after the whole launch, with its event times
+      item.down[item.num_down++] = {h_end, d_end, jobs.size() * 8};
+      item.down[item.num_down++] = {h_status, d_status, jobs.size() * 4};
+    } else {  // the streams write their results straight into the mapped block and count themselves off
+      const uint32_t zero = 0;
+      item.ref.counter = static_cast<uint32_t*>(upload_temp(&zero, 4));
+      item.up[item.num_up - 1].bytes = stage_off_;
+      item.ref.end_bits = reinterpret_cast<uint64_t*>(h_end);
+      item.ref.status = reinterpret_cast<int*>(h_status);
+      item.ref.num_jobs = uint32_t(jobs.size());
+      item.ref.done_flag = const_cast<uint32_t*>(h_flag_ + 16);
+      item.ref.done_seq = ++item_seq_;
+      item.done_flag = h_flag_ + 16;
+    }
     item.want_timing = profile;
     lf_service->run(item);
     ++launches;
@@ -1215,7 +1239,10 @@ void CudaBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
     end_k();
   }
   begin_k("decode_hf");
-  if (hf_streams_per_cta >= 64)
+  if (debug_skip() & 1) {  // experiment: what the pipeline does without this kernel (results are garbage)
+    CUDA_CHECK(cudaMemsetAsync(d_end, 0, jobs.size() * 8, S()));
+    CUDA_CHECK(cudaMemsetAsync(d_status, 0, jobs.size() * 4, S()));
+  } else if (hf_streams_per_cta >= 64)
     launch_decode_hf_lanes(active_cs_, dev_frame(st), p, d_blk_ctx, d_jobs, d_end, d_status, int(jobs.size()), pass == 0 ? 1 : 0,
                            hf_streams_per_cta, S());
   else
@@ -1327,7 +1354,7 @@ void CudaBackend::hf_dequant_cfl(VarDctState& st) {
 void CudaBackend::hf_transform(VarDctState& st) {
   void* scratch = dmalloc(hf_transform_scratch_bytes(st.bw, st.bh));
   begin_k("hf_transform");
-  launch_hf_transform(dev_frame(st), scratch, have_pending_dequant_ ? &pending_dequant_ : nullptr, S());
+  if (!(debug_skip() & 2)) launch_hf_transform(dev_frame(st), scratch, have_pending_dequant_ ? &pending_dequant_ : nullptr, S());
   end_k();
   have_pending_dequant_ = false;
   dfree(scratch);
@@ -1441,7 +1468,7 @@ bool CudaBackend::filters_colour_fused(const View v[3], const RestorationFilter&
     p.col.pq_intensity_target = 0.0f;
   }
   begin_k("filters_fused");
-  launch_filters_fused(in, out, p, S());
+  if (!(debug_skip() & 4)) launch_filters_fused(in, out, p, S());
   end_k();
   for (int c = 0; c < 3; ++c) {
     PlaneRec& r = planes_.at(v[c].plane);

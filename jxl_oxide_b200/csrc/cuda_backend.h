@@ -30,6 +30,8 @@ struct LfBatchItem {
   bool all_staged = false;
   Copy down[2];  // device -> host (pinned)
   int num_down = 0;
+  // set when ref.counter / ref.done_flag are: the item is complete as soon as *done_flag == ref.done_seq
+  volatile uint32_t* done_flag = nullptr;
   bool want_timing = false;
   float elapsed_ms = 0.0f;  // device time of the batch kernel this item rode in
 };
@@ -207,7 +209,7 @@ class CudaBackend : public Backend {
   uint8_t* h_input_ = nullptr;   // pinned staging of the encoded bytes
   size_t input_cap_ = 0;
   volatile uint32_t* h_flag_ = nullptr;  // mapped pinned word the stream writes its sync sequence number to
-  uint32_t sync_seq_ = 0;
+  uint32_t sync_seq_ = 0, item_seq_ = 0;
   uint8_t* arena_base_ = nullptr;
   size_t arena_cap_ = 0, arena_off_ = 0, arena_peak_ = 0, arena_spill_ = 0;
   bool heavy_announced_ = false;

@@ -739,9 +739,10 @@ DecodedFrame FramePlanner::decode_frame(size_t frame_begin_byte, size_t* frame_e
   }
 
   be_.phase_mark("pass_groups");
-  if (lfg_.has_gmodular) {  // the decoded (still transformed) channels of the frame's Modular image, coding order
+  {  // the decoded (still transformed) channels of the frame's Modular image, coding order; none when it has no such image
     std::vector<View> coded;
-    for (const ChanBuf& c : gm_coded_) coded.push_back(c.view);
+    if (lfg_.has_gmodular)
+      for (const ChanBuf& c : gm_coded_) coded.push_back(c.view);
     be_.stage_marker("modular_coded", coded.data(), int(coded.size()));
   }
   // ---- global inverse transforms ----

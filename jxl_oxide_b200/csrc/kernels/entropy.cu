@@ -11,6 +11,8 @@
 // Integer semantics are those of crates/jxl-modular/src/{image.rs,predictor.rs,ma.rs} and
 // crates/jxl-vardct/src/hf_coeff.rs (bit-exact, wrapping i32).
 #include "kernels.h"
+
+#include <cstdlib>
 #include "stream_common.cuh"
 #include "hf_lanes.cuh"
 
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(128) decode_hf_lanes_kernel(const uint8_t* __r
                                                               const uint32_t* __restrict__ blk_ctx,
                                                               const DevHfJob* __restrict__ jobs,
                                                               uint64_t* __restrict__ end_bits, int* __restrict__ status,
-                                                              int num_jobs, int first_pass) {
+                                                              int num_jobs, int first_pass, uint32_t lane_stride) {
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t tid = threadIdx.x, nthreads = blockDim.x;
   const HfLaneSmem L = hf_lane_layout(p, nthreads);
@@ -641,7 +643,10 @@ __global__ void __launch_bounds__(128) decode_hf_lanes_kernel(const uint8_t* __r
     T.cv.ans = reinterpret_cast<const uint64_t*>(s_ans);
   }
   __syncthreads();
-  const int job_idx = blockIdx.x * int(nthreads) + int(tid);
+  // lane_stride > 1: only every lane_stride-th lane carries a stream (32 / lane_stride streams per warp). Fewer streams
+  // per warp diverge and collide less, so a stream finishes sooner; more of them per warp cost fewer issue slots.
+  if (tid % lane_stride) return;
+  const int job_idx = blockIdx.x * int(nthreads / lane_stride) + int(tid / lane_stride);
   if (job_idx >= num_jobs) return;
   const DevHfJob job = jobs[job_idx];
   hf_lane_decode<SUB>(cs, f, p, T, blk_ctx, job, smem + L.nz + tid, nthreads, first_pass, end_bits + job_idx,
@@ -666,13 +671,20 @@ void launch_decode_hf_lanes(const uint8_t* cs, DevFrame f, DevHfParams p, const 
     cudaFuncSetAttribute(decode_hf_lanes_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
+  static const uint32_t env_stride = [] {
+    const char* e = std::getenv("JXLB_HF_LANE_STRIDE");
+    const int v = e ? std::atoi(e) : 0;
+    return uint32_t(v == 1 || v == 2 || v == 4 || v == 8 || v == 16 ? v : 0);
+  }();
+  const uint32_t stride = env_stride ? env_stride : 1;
   const int nthreads = streams_per_cta <= 32 ? 32 : (streams_per_cta <= 64 ? 64 : 128);
   const HfLaneSmem L = hf_lane_layout(p, uint32_t(nthreads));
-  const int ctas = (num_jobs + nthreads - 1) / nthreads;
+  const int per_cta = nthreads / int(stride);
+  const int ctas = (num_jobs + per_cta - 1) / per_cta;
   if (f.subsampled)
-    decode_hf_lanes_kernel<true><<<ctas, nthreads, L.total, stream>>>(cs, f, p, blk_ctx, jobs, end_bits, status, num_jobs, first_pass);
+    decode_hf_lanes_kernel<true><<<ctas, nthreads, L.total, stream>>>(cs, f, p, blk_ctx, jobs, end_bits, status, num_jobs, first_pass, stride);
   else
-    decode_hf_lanes_kernel<false><<<ctas, nthreads, L.total, stream>>>(cs, f, p, blk_ctx, jobs, end_bits, status, num_jobs, first_pass);
+    decode_hf_lanes_kernel<false><<<ctas, nthreads, L.total, stream>>>(cs, f, p, blk_ctx, jobs, end_bits, status, num_jobs, first_pass, stride);
 }
 
 namespace {

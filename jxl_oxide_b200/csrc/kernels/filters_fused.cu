@@ -36,10 +36,11 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
-constexpr int kT = 32;            // output tile
-constexpr int kHM = 8;            // shared-memory margin (>= total stencil radius 7)
-constexpr int kS = kT + 2 * kHM;  // 48
-constexpr int kPlane = kS * kS;
+constexpr int kT = 32;  // output tile
+// Shared-memory planes are kS x kS cells with a margin of (kS - kT) / 2 around the tile: 48 (margin 8 >= stencil radius 7) when
+// the frame runs EPF step 0, 40 (margin 4 = Gaborish 1 + step 1's 2 + step 2's 1) otherwise - 8 planes of 40 x 40 are
+// 51 KB, so four CTAs share an SM instead of three. Every device function below is a template on kS.
+__host__ __device__ constexpr int window_size(int nmaps) { return nmaps == 6 ? 48 : 40; }
 
 struct Rect {  // in shared-memory cell coordinates, half-open
   int x0, y0, x1, y1;
@@ -50,6 +51,7 @@ __device__ __forceinline__ int mirror1(int v, int len) {  // single reflection (
 }
 
 // Gaborish at one in-image pixel; `a` points at the pixel in a shared plane (gabor.rs:3-167).
+template <int kS>
 __device__ __forceinline__ float gab_px(const float* a, int x, int y, int width, int height, float w0, float w1, float gw) {
   auto at = [&](int dx, int dy) { return a[dy * kS + dx]; };
   if (height == 1) {
@@ -126,8 +128,9 @@ __device__ __forceinline__ constexpr int plus_y(int step, int i) {
 // Half-stage 1: the distance maps of one EPF step at cell q. `a` points at q in channel 0 of the input buffer, `d` at q in
 // map 0 (maps kPlane apart). dist_d(q) = sum_c scale_c * sum_o |a_c[q+d+o] - a_c[q+o]|, accumulated exactly like
 // epf.rs (acc starts at 0.0, so the first addition is exact; likewise dist).
-template <int STEP>
+template <int STEP, int kS>
 __device__ __forceinline__ void epf_dist(const float* __restrict__ a, float* __restrict__ d, const DevEpfParams& p) {
+  constexpr int kPlane = kS * kS;
   constexpr int NM = STEP == 0 ? 6 : 2;
   constexpr int ND = STEP == 2 ? 1 : 5;
   float dist[NM];  // all maps first, stores last: a store between them would make the compiler reload every sample
@@ -135,15 +138,19 @@ __device__ __forceinline__ void epf_dist(const float* __restrict__ a, float* __r
   for (int m = 0; m < NM; ++m) {
     const int dx = dplus_x(STEP, m), dy = dplus_y(STEP, m);
     dist[m] = 0.0f;
+    // epf.rs starts both sums at 0.0; 0.0 + t == t bit for bit for the non-negative t added first, so the first term is
+    // taken as it is
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float acc = 0.0f;
 #pragma unroll
       for (int i = 0; i < ND; ++i) {
         const int ox = plus_x(STEP, i), oy = plus_y(STEP, i);
-        acc = fadd(acc, fabsf(fsub(a[c * kPlane + (dy + oy) * kS + dx + ox], a[c * kPlane + oy * kS + ox])));
+        const float t = fabsf(fsub(a[c * kPlane + (dy + oy) * kS + dx + ox], a[c * kPlane + oy * kS + ox]));
+        acc = i == 0 ? t : fadd(acc, t);
       }
-      dist[m] = fadd(dist[m], fmul(p.channel_scale[c], acc));
+      const float term = fmul(p.channel_scale[c], acc);
+      dist[m] = c == 0 ? term : fadd(dist[m], term);
     }
   }
 #pragma unroll
@@ -152,9 +159,10 @@ __device__ __forceinline__ void epf_dist(const float* __restrict__ a, float* __r
 
 // Half-stage 2: weights and weighted sums at pixel p in the reference's neighbour order; `a` points at p in channel 0 of
 // the input buffer, `d` at p in distance map 0.
-template <int STEP>
-__device__ __forceinline__ void epf_apply(const float* a, const float* d, int x, int y, float sigma_val, const DevEpfParams& p,
-                                          float o[3]) {
+template <int STEP, int kS>
+__device__ __forceinline__ void epf_apply(const float* a, const float* d, int x, int y, float sigma_val, float inv_sigma,
+                                          const DevEpfParams& p, float o[3]) {
+  constexpr int kPlane = kS * kS;
   if (sigma_val < 0.3f) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) o[c] = a[c * kPlane];
@@ -165,7 +173,7 @@ __device__ __forceinline__ void epf_apply(const float* a, const float* d, int x,
   float sm;
   if (is_y_border) sm = fmul(step_multiplier, p.border_sad_mul);
   else sm = ((x & 7) == 0 || (x & 7) == 7) ? fmul(step_multiplier, p.border_sad_mul) : step_multiplier;
-  const float neg_inv_sigma = fmul(fdiv(fmul(6.6f, fsub(0.70710678118654752440f, 1.0f)), sigma_val), sm);
+  const float neg_inv_sigma = fmul(inv_sigma, sm);  // inv_sigma = 6.6 * (1/sqrt(2) - 1) / sigma, one division per 8x8 block
   float sum_weights = 1.0f;
   float sum_channels[3];
 #pragma unroll
@@ -309,7 +317,9 @@ struct FusedMaps {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 // Cells of `need` that lie outside the image take the value of their mirrored in-image cell.
+template <int kS>
 __device__ __forceinline__ void mirror_fill(float* buf, Rect need, int gx0, int gy0, int width, int height) {
+  constexpr int kPlane = kS * kS;
   for (int ly = need.y0 + int(threadIdx.y); ly < need.y1; ly += int(blockDim.y))
     for (int lx = need.x0 + int(threadIdx.x); lx < need.x1; lx += int(blockDim.x)) {
       const int gx = gx0 + lx, gy = gy0 + ly;
@@ -326,8 +336,10 @@ __device__ __forceinline__ void mirror_fill(float* buf, Rect need, int gx0, int 
 // NMAPS: distance maps kept in shared memory (6 when the frame runs EPF step 0, else 2; 0 without EPF).
 template <int NMAPS>
 __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFusedFilterParams p, const __grid_constant__ FusedMaps maps) {
+  constexpr int kS = window_size(NMAPS), kPlane = kS * kS, kHM = (kS - kT) / 2;
   extern __shared__ __align__(128) float s_buf[];
   __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ float s_sigma[49], s_inv_sigma[49];  // per 8x8 block under the window (at most 7 x 7 of them)
   float* cur = s_buf;               // [3][kS][kS]
   float* alt = s_buf + 3 * kPlane;
   float* dmap = s_buf + 6 * kPlane;  // [NMAPS][kS][kS]
@@ -344,6 +356,20 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
     r.x1 = min(r.x1, width - gx0), r.y1 = min(r.y1, height - gy0);
     return r;
   };
+
+  // sigma and the division it feeds, once per 8x8 block under the window instead of once per pixel and step (same operands,
+  // same result: epf.rs computes 6.6 * (1/sqrt(2) - 1) / sigma for every pixel of the block)
+  const int bx_first = max(gx0, 0) >> 3, by_first = max(gy0, 0) >> 3;
+  if (NMAPS > 0 && p.epf_iters > 0) {
+    const int t = int(threadIdx.y) * 32 + int(threadIdx.x);
+    if (t < 49) {
+      const int bx = bx_first + t % 7, by = by_first + t / 7;
+      float sg = p.epf.sigma_for_modular;
+      if (p.sigma) sg = (bx < ((width + 7) >> 3) && by < ((height + 7) >> 3)) ? __ldg(p.sigma + size_t(by) * p.sigma_stride + bx) : 1.0f;
+      s_sigma[t] = sg;
+      s_inv_sigma[t] = fdiv(fmul(6.6f, fsub(0.70710678118654752440f, 1.0f)), sg);
+    }
+  }
 
   if (v.use_tma) {
     // Tile + halo by TMA: one elected thread arms an mbarrier with the byte count and issues three bulk tensor copies
@@ -401,7 +427,7 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
 #pragma unroll
         for (int c = 0; c < 3; ++c)
           alt[c * kPlane + ly * kS + lx] =
-              gab_px(cur + c * kPlane + ly * kS + lx, gx0 + lx, gy0 + ly, width, height, p.gab_w[c][0], p.gab_w[c][1], gw[c]);
+              gab_px<kS>(cur + c * kPlane + ly * kS + lx, gx0 + lx, gy0 + ly, width, height, p.gab_w[c][0], p.gab_w[c][1], gw[c]);
       });
     }
     float* t = cur;
@@ -410,7 +436,7 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
     __syncthreads();
   }
   if (p.epf_iters > 0 && border_tile) {  // EPF reads mirrored pixels beyond the image border
-    mirror_fill(cur, rect(halo), gx0, gy0, width, height);
+    mirror_fill<kS>(cur, rect(halo), gx0, gy0, width, height);
     __syncthreads();
   }
 
@@ -423,15 +449,15 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
          // (cells beyond the image included: they stand for mirrored pixels)
         constexpr int ex = STEP == 0 ? 2 : 1;  // reach of the negated directions: x - 2 .. x + 1 (step 0), x - 1 .. x
         const Rect q{out.x0 - ex, out.y0 - ex, out.x1 + (STEP == 0 ? 1 : 0), out.y1};
-        for_region(q, [&](int lx, int ly) { epf_dist<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, p.epf); });
+        for_region(q, [&](int lx, int ly) { epf_dist<STEP, kS>(cur + ly * kS + lx, dmap + ly * kS + lx, p.epf); });
       }
       __syncthreads();
       const Rect r = clip(out);
       for_region(r, [&](int lx, int ly) {
         const int x = gx0 + lx, y = gy0 + ly;
-        const float sigma_val = p.sigma ? __ldg(p.sigma + size_t(y >> 3) * p.sigma_stride + (x >> 3)) : p.epf.sigma_for_modular;
+        const int bi = ((y >> 3) - by_first) * 7 + ((x >> 3) - bx_first);
         float o[3];
-        epf_apply<STEP>(cur + ly * kS + lx, dmap + ly * kS + lx, x, y, sigma_val, p.epf, o);
+        epf_apply<STEP, kS>(cur + ly * kS + lx, dmap + ly * kS + lx, x, y, s_sigma[bi], s_inv_sigma[bi], p.epf, o);
         if (last) {
           if (p.colour) xyb_px(o, p.col);
 #pragma unroll
@@ -447,7 +473,7 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
         alt = t;
         __syncthreads();
         if (border_tile) {
-          mirror_fill(cur, rect(halo), gx0, gy0, width, height);
+          mirror_fill<kS>(cur, rect(halo), gx0, gy0, width, height);
           __syncthreads();
         }
       }
@@ -502,6 +528,9 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
   v.width = int(in[0].w);
   v.height = int(in[0].h);
   if (!v.width || !v.height) return;
+  const int nmaps = p.epf_iters == 3 ? 6 : (p.epf_iters > 0 ? 2 : 0);
+  const int ks = window_size(nmaps);
+  const size_t plane_bytes = size_t(ks) * ks * sizeof(float);
   FusedMaps maps;
   std::memset(&maps, 0, sizeof(maps));
   v.use_tma = 0;
@@ -513,7 +542,7 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
       if (!ok) break;
       const cuuint64_t dims[2] = {cuuint64_t(v.width), cuuint64_t(v.height)};
       const cuuint64_t strides[1] = {cuuint64_t(v.in_stride[c]) * 4};
-      const cuuint32_t box[2] = {cuuint32_t(kS), cuuint32_t(kS)};
+      const cuuint32_t box[2] = {cuuint32_t(ks), cuuint32_t(ks)};
       const cuuint32_t estr[2] = {1, 1};
       ok = enc(&maps.map[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(v.in[c]), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -523,16 +552,16 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(fused_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(6 * kPlane * sizeof(float)));
-    cudaFuncSetAttribute(fused_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(8 * kPlane * sizeof(float)));
-    cudaFuncSetAttribute(fused_filter_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(12 * kPlane * sizeof(float)));
+    cudaFuncSetAttribute(fused_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * window_size(0) * window_size(0) * 4);
+    cudaFuncSetAttribute(fused_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * window_size(2) * window_size(2) * 4);
+    cudaFuncSetAttribute(fused_filter_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * window_size(6) * window_size(6) * 4);
     attr_set = true;
   }
   dim3 block(32, 8);
   dim3 grid((v.width + kT - 1) / kT, (v.height + kT - 1) / kT);
-  if (p.epf_iters == 3) fused_filter_kernel<6><<<grid, block, 12 * kPlane * sizeof(float), stream>>>(v, p, maps);
-  else if (p.epf_iters > 0) fused_filter_kernel<2><<<grid, block, 8 * kPlane * sizeof(float), stream>>>(v, p, maps);
-  else fused_filter_kernel<0><<<grid, block, 6 * kPlane * sizeof(float), stream>>>(v, p, maps);
+  if (p.epf_iters == 3) fused_filter_kernel<6><<<grid, block, 12 * plane_bytes, stream>>>(v, p, maps);
+  else if (p.epf_iters > 0) fused_filter_kernel<2><<<grid, block, 8 * plane_bytes, stream>>>(v, p, maps);
+  else fused_filter_kernel<0><<<grid, block, 6 * plane_bytes, stream>>>(v, p, maps);
 }
 
 }  // namespace jxlb

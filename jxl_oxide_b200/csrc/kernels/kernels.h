@@ -57,9 +57,15 @@ struct DevModularBatchRef {
   const DevModularJob* jobs;
   const DevChannel* channels;
   const DevChannelPlan* plans;
-  uint64_t* end_bits;
+  uint64_t* end_bits;   // may be mapped host memory: each stream writes its two result words once, at its end
   int* status;
-  uint32_t job, pad;
+  uint32_t job;
+  // Per-frame completion inside a shared launch: the stream that finishes last (device counter, zero on entry) writes
+  // `done_seq` to the mapped host word `done_flag`. NULL counter: the launch's end is the only signal.
+  uint32_t num_jobs;
+  uint32_t* counter;
+  uint32_t* done_flag;
+  uint32_t done_seq, pad;
 };
 
 // Modular ------------------------------------------------------------------------------------

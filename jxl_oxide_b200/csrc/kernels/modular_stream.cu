@@ -647,6 +647,16 @@ __global__ void __launch_bounds__(32) modular_stream_batch_kernel(const DevModul
   if (int(blockIdx.x) >= total) return;
   const DevModularBatchRef r = refs[blockIdx.x];
   modular_stream_body<ALLSM>(smem, r.cs, r.jobs, r.channels, r.plans, r.end_bits, r.status, int(r.job), nullptr);
+  if (r.counter) {
+    // this frame's streams are done when its last one is: samples and result words first, then the count, then the word
+    // the frame's host thread is woken by (the rest of the launch belongs to other frames and may run for another 80 ms)
+    __threadfence_system();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0 && atomicAdd(r.counter, 1u) == r.num_jobs - 1) {
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t*>(r.done_flag) = r.done_seq;
+    }
+  }
 }
 
 // Delta-palette prediction pass (palette.rs:120-152): one CTA per channel, thread 0 walks the channel in raster order

@@ -538,27 +538,40 @@ constexpr int kMediumShapes = 8;
 __host__ __device__ inline int medium_shape(int w8, int h8) {
   return w8 == 2 ? (h8 == 1 ? 0 : (h8 == 2 ? 2 : 6)) : (w8 == 1 ? (h8 == 2 ? 1 : 4) : (h8 == 1 ? 3 : (h8 == 2 ? 5 : 7)));
 }
+// The ten transform types of one 8x8 cell (DCT8, Hornuss, DCT2, DCT4, DCT4x8, DCT8x4, AFV0-3) each get their own list:
+// the 8-thread groups of a warp then work on the same type and take the same branch of the transform.
+constexpr int kSmallTypes = 10;
+__host__ __device__ inline int small_type_index(int t) { return t < 4 ? t : t - 8; }  // types 0-3 and 12-17
 struct TransformLists {
-  uint32_t* counts;  // [0..3]: small, medium (unused), large64, large256; [4..11]: medium shapes
+  uint32_t* counts;  // [0]: unused, [2], [3]: large64, large256; [4..11]: medium shapes; [12..21]: small types
   uint32_t* items[4];
   uint32_t* shape_items[kMediumShapes];
+  uint32_t* small_items[kSmallTypes];
 };
 
+// One list slot per varblock. The lanes of a warp that append to the same list reserve their slots with ONE atomic
+// (match_any): a frame has half a million cells and a dozen counters, and one atomic per cell serialises on them.
 __global__ void classify_varblocks_kernel(DevFrame f, TransformLists L) {
   const uint32_t bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;
-  if (bx >= f.bw || by >= f.bh) return;
-  const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
-  if (t < 0) return;
-  const int m = max(int(kDevTransformInfo[t][0]), int(kDevTransformInfo[t][1]));
-  const int cls = m == 1 ? 0 : (m <= 4 ? 1 : (m == 8 ? 2 : 3));
-  if (cls == 1) {
-    const int sh = medium_shape(kDevTransformInfo[t][0], kDevTransformInfo[t][1]);
-    const uint32_t slot = atomicAdd(L.counts + 4 + sh, 1u);
-    L.shape_items[sh][slot] = bx | (by << 16);
-    return;
+  int key = -1;  // counter index: 2 / 3 large, 4 + shape medium, 12 + type small
+  if (bx < f.bw && by < f.bh) {
+    const int32_t t = f.blk_type[size_t(by) * f.bw + bx];
+    if (t >= 0) {
+      const int m = max(int(kDevTransformInfo[t][0]), int(kDevTransformInfo[t][1]));
+      const int cls = m == 1 ? 0 : (m <= 4 ? 1 : (m == 8 ? 2 : 3));
+      key = cls == 1 ? 4 + medium_shape(kDevTransformInfo[t][0], kDevTransformInfo[t][1]) : (cls == 0 ? 12 + small_type_index(t) : cls);
+    }
   }
-  const uint32_t slot = atomicAdd(L.counts + cls, 1u);
-  L.items[cls][slot] = bx | (by << 16);
+  const uint32_t peers = __match_any_sync(0xffffffffu, key);
+  if (key < 0) return;
+  const uint32_t lane = (threadIdx.y * blockDim.x + threadIdx.x) & 31;
+  const int leader = __ffs(int(peers)) - 1;
+  uint32_t base = 0;
+  if (int(lane) == leader) base = atomicAdd(L.counts + key, uint32_t(__popc(peers)));
+  base = __shfl_sync(peers, base, leader);
+  const uint32_t slot = base + uint32_t(__popc(peers & ((1u << lane) - 1)));
+  uint32_t* list = key >= 12 ? L.small_items[key - 12] : (key >= 4 ? L.shape_items[key - 4] : L.items[key]);
+  list[slot] = bx | (by << 16);
 }
 
 // Register-resident inverse DCT: the operation sequence of Dct1D<N>::run(inverse).
@@ -836,17 +849,18 @@ __device__ __forceinline__ void cfl_factors(const DevFrame& f, const DevDequantP
 
 constexpr int kSmallGroups = 32;  // 8-thread groups per CTA
 template <bool DEQ>
-__global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f, DevDequantParams dq,
-                                                                      const uint32_t* __restrict__ items,
-                                                                      const uint32_t* __restrict__ count_ptr) {
+__global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
   __shared__ float s_tile[kSmallGroups][72];      // 8 x 9
   __shared__ float s_special[kSmallGroups][192];  // 8 x 8 copy + 128 scratch
   const uint32_t group = threadIdx.x >> 3, r = threadIdx.x & 7;
   const uint32_t gmask = 0xffu << (8 * ((threadIdx.x & 31) >> 3));
   // DEQ: one work item per varblock (the three channels together: Y first, its dequantised row feeds the chroma
   // channels); else one per (varblock, channel)
-  const uint32_t total = DEQ ? *count_ptr : *count_ptr * 3;
   float* tile = s_tile[group];
+#pragma unroll 1
+  for (int list = 0; list < kSmallTypes; ++list) {
+  const uint32_t* __restrict__ items = lists.small_items[list];
+  const uint32_t total = DEQ ? lists.counts[12 + list] : lists.counts[12 + list] * 3;
   for (uint32_t work = blockIdx.x * kSmallGroups + group; work < total; work += gridDim.x * kSmallGroups) {
     const uint32_t item = items[DEQ ? work : work / 3];
     const uint32_t sbx = item & 0xffff, sby = item >> 16;
@@ -906,6 +920,7 @@ __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f
       *reinterpret_cast<float4*>(row + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
+  }
 }
 
 // not inlined: the row pass and the column pass of the medium kernel share one copy of each size's code
@@ -926,87 +941,151 @@ __device__ __forceinline__ void idct_line_dispatch(float* p, int stride, int n) 
 }
 
 constexpr int kMediumWarps = 4;
+// One varblock of a warp's 32 x 32 tile (idct_medium_kernel).
+struct MediumSub {
+  uint32_t bx[3], by[3];  // where channel c keeps the block (8x8 cells); by == 0xffffffff: the channel skips it
+  float mul[3];           // DeqBlock::mul
+  float kx[4], kb[4];     // chroma-from-luma factors of the (at most 2 x 2) 64x64 tiles the block touches
+  uint32_t tx0, ty0;      // the first of those tiles
+};
+// Varblocks of 16x8 ... 32x32 samples, one warp per 32 x 32 TILE of them: a tile holds (32 / w) x (32 / h) blocks of
+// the shape being walked (8 of 16x8, 4 of 16x16, 1 of 32x32), so the row pass (lane = tile row) and the column pass
+// (lane = tile column) keep all 32 lanes busy whatever the shape; with one block per warp a 16x8 block used 8 and 16
+// lanes of 32. Per block nothing changes: same loads, same operation order in the line transforms.
 template <bool DEQ>
 __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
   __shared__ float s_tile[kMediumWarps][32 * 33];
   __shared__ float s_ytile[DEQ ? kMediumWarps : 1][DEQ ? 32 * 33 : 1];  // dequantised Y coefficients (chroma from luma)
-  __shared__ float s_llf[kMediumWarps][16 + 12];
+  __shared__ float s_llf[kMediumWarps][8][16];
+  __shared__ MediumSub s_sub[kMediumWarps][8];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* tile = s_tile[warp];
   float* ytile = s_ytile[DEQ ? warp : 0];
-  float* llf = s_llf[warp];
+  MediumSub* sub = s_sub[warp];
 #pragma unroll 1
   for (int shape = 0; shape < kMediumShapes; ++shape) {
-  const uint32_t* __restrict__ items = lists.shape_items[shape];
-  const uint32_t total = DEQ ? lists.counts[4 + shape] : lists.counts[4 + shape] * 3;
-  for (uint32_t work = blockIdx.x * kMediumWarps + warp; work < total; work += gridDim.x * kMediumWarps) {
-    const uint32_t item = items[DEQ ? work : work / 3];
-    const uint32_t sbx = item & 0xffff, sby = item >> 16;
-    const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
+    const uint32_t* __restrict__ items = lists.shape_items[shape];
+    const uint32_t total = lists.counts[4 + shape];
+    if (total == 0) continue;
+    // every entry of a shape's list has the same transform type
+    const uint32_t item0 = items[0];
+    const int32_t t = f.blk_type[size_t(item0 >> 16) * f.bw + (item0 & 0xffff)];
     const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
     const int w = bw * 8, h = bh * 8;
-    const int logw = 31 - __clz(w);
-    DeqBlock db;
-    // chroma-from-luma factors of the (at most 2 x 2) 64x64 tiles a block of up to 32x32 samples touches
-    float kxt[4], kbt[4];
-    const uint32_t tx0 = (sbx * 8) >> 6, ty0 = (sby * 8) >> 6;
+    const int logw = 31 - __clz(w), logh = 31 - __clz(h);
+    const int lognx = 5 - logw, logny = 5 - logh, logp = lognx + logny;  // blocks across, down, per tile
+    const int ny = 1 << logny;
+    const float* mat[3] = {nullptr, nullptr, nullptr};
     if (DEQ) {
-      db = deq_block(f, dq, t, sbx, sby);
+      const uint32_t set = kDevTransformInfo[t][2], tr = kDevTransformInfo[t][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t tx = min(tx0 + uint32_t(i & 1), f.w64 - 1), ty = min(ty0 + uint32_t(i >> 1), (f.ch + 63) / 64 - 1);
-        cfl_factors(f, dq, tx << 6, ty << 6, kxt[i], kbt[i]);
-      }
+      for (int c = 0; c < 3; ++c) mat[c] = dq.matrices + dq.matrix_offset[(set * 3 + c) * 2 + tr];
     }
+    // this lane's tile column: block column sx, sample column x inside the block
+    const int sx = int(lane) >> logw, x = int(lane) & (w - 1);
 #pragma unroll 1
-    for (int ci = 0; ci < (DEQ ? 3 : 1); ++ci) {
-      const uint32_t c = DEQ ? (ci == 0 ? 1u : (ci == 1 ? 0u : 2u)) : work % 3;
-      uint32_t bx, by;
-      if (!channel_block(f, c, sbx, sby, bx, by)) continue;
-      float* block = reinterpret_cast<float*>(f.coeff[c]) + size_t(by) * 8 * f.cw + size_t(bx) * 8;
-      // w * h is a multiple of 128 (16x8 is the smallest block of this class): four elements per lane and trip, all loads
-      // of a trip issued before the first use, so that a trip costs one global-memory latency instead of four
-      for (int idx0 = int(lane); idx0 < w * h; idx0 += 128) {
-        float raw[4], mat[4];
+    for (uint32_t group = blockIdx.x * kMediumWarps + warp; (group << logp) < total; group += gridDim.x * kMediumWarps) {
+      const uint32_t first = group << logp;
+      const int nb = int(min(uint32_t(1) << logp, total - first));
+      __syncwarp();
+      if (int(lane) < nb) {  // lane s describes block s of the tile
+        MediumSub m;
+        const uint32_t item = items[first + lane];
+        const uint32_t sbx = item & 0xffff, sby = item >> 16;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int idx = idx0 + 32 * j, x = idx & (w - 1), y = idx >> logw;
-          raw[j] = block[size_t(y) * f.cw + x];
-          if (DEQ) mat[j] = __ldg(db.mat[c] + idx);
+        for (uint32_t c = 0; c < 3; ++c) {
+          uint32_t bx, by;
+          const bool has = channel_block(f, c, sbx, sby, bx, by);
+          m.bx[c] = bx;
+          m.by[c] = has ? by : 0xffffffffu;
         }
+        m.tx0 = (sbx * 8) >> 6, m.ty0 = (sby * 8) >> 6;
+        if (DEQ) {
+          const DeqBlock db = deq_block(f, dq, t, sbx, sby);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int idx = idx0 + 32 * j, x = idx & (w - 1), y = idx >> logw;
-          float v = raw[j];
-          if (DEQ) {
-            const float q = deq_one(__float_as_uint(v), mat[j], db.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
-            if (c == 1) {
-              ytile[y * 33 + x] = v = q;
-            } else {
-              const int ti = int(((bx * 8 + uint32_t(x)) >> 6) - tx0) + 2 * int(((by * 8 + uint32_t(y)) >> 6) - ty0);
-              const float k = c == 0 ? (ti == 0 ? kxt[0] : ti == 1 ? kxt[1] : ti == 2 ? kxt[2] : kxt[3])
-                                     : (ti == 0 ? kbt[0] : ti == 1 ? kbt[1] : ti == 2 ? kbt[2] : kbt[3]);
-              v = __fadd_rn(q, __fmul_rn(k, ytile[y * 33 + x]));
-            }
+          for (int c = 0; c < 3; ++c) m.mul[c] = db.mul[c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t tx = min(m.tx0 + uint32_t(i & 1), f.w64 - 1), ty = min(m.ty0 + uint32_t(i >> 1), (f.ch + 63) / 64 - 1);
+            cfl_factors(f, dq, tx << 6, ty << 6, m.kx[i], m.kb[i]);
           }
-          tile[y * 33 + x] = v;
         }
-      }
-      if (lane == 0) compute_llf_small(f, int(c), bx, by, bw, bh, llf);  // overlaps the tile loads in flight
-      __syncwarp();
-      if (int(lane) < bw * bh) tile[(int(lane) / bw) * 33 + (int(lane) % bw)] = llf[lane];
-      __syncwarp();
-      if (int(lane) < h) idct_line_dispatch(tile + lane * 33, 1, w);
-      __syncwarp();
-      if (int(lane) < w) idct_line_dispatch(tile + lane, 33, h);
-      __syncwarp();
-      for (int idx = int(lane); idx < w * h; idx += 32) {
-        const int x = idx & (w - 1), y = idx >> logw;
-        block[size_t(y) * f.cw + x] = tile[y * 33 + x];
+        sub[lane] = m;
       }
       __syncwarp();
+#pragma unroll 1
+      for (int ci = 0; ci < 3; ++ci) {
+        const uint32_t c = DEQ ? (ci == 0 ? 1u : (ci == 1 ? 0u : 2u)) : uint32_t(ci);
+        // the (up to 4) blocks of this lane's tile column
+        float* col[4];
+#pragma unroll
+        for (int sy = 0; sy < 4; ++sy) {
+          const int s = (sy << lognx) + sx;
+          col[sy] = nullptr;
+          if (sy < ny && s < nb && sub[s].by[c] != 0xffffffffu)
+            col[sy] = reinterpret_cast<float*>(f.coeff[c]) + size_t(sub[s].by[c]) * 8 * f.cw + size_t(sub[s].bx[c]) * 8 + x;
+        }
+        // 32 tile rows, four per trip, all loads of a trip issued before the first use
+#pragma unroll 1
+        for (int y0 = 0; y0 < 32; y0 += 4) {
+          float raw[4], mt[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int Y = y0 + j, sy = Y >> logh, y = Y & (h - 1);
+            const float* src = sy == 0 ? col[0] : (sy == 1 ? col[1] : (sy == 2 ? col[2] : col[3]));
+            raw[j] = src ? src[size_t(y) * f.cw] : 0.0f;
+            if (DEQ) mt[j] = __ldg(mat[c] + (y << logw) + x);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int Y = y0 + j, sy = Y >> logh, y = Y & (h - 1);
+            float v = raw[j];
+            if (DEQ) {
+              const MediumSub& m = sub[min((sy << lognx) + sx, nb - 1)];
+              const float q = deq_one(__float_as_uint(v), mt[j], m.mul[c], dq.quant_bias[c], dq.quant_bias_numerator);
+              if (c == 1) {
+                ytile[Y * 33 + int(lane)] = v = q;
+              } else {
+                const int ti = int(((m.bx[c] * 8 + uint32_t(x)) >> 6) - m.tx0) + 2 * int(((m.by[c] * 8 + uint32_t(y)) >> 6) - m.ty0);
+                v = __fadd_rn(q, __fmul_rn(c == 0 ? m.kx[ti & 3] : m.kb[ti & 3], ytile[Y * 33 + int(lane)]));
+              }
+            }
+            tile[Y * 33 + int(lane)] = v;
+          }
+        }
+        // lowest frequencies from the LF image: lane s for block s, then 16 lanes place the (at most) 16 values of the tile
+        if (int(lane) < nb && sub[lane].by[c] != 0xffffffffu) compute_llf_small(f, int(c), sub[lane].bx[c], sub[lane].by[c], bw, bh, s_llf[warp][lane]);
+        __syncwarp();
+        if (lane < 16) {
+          const int cells_log = (logw - 3) + (logh - 3);  // LLF values per block
+          const int s = int(lane) >> cells_log, local = int(lane) & ((1 << cells_log) - 1);
+          if (s < nb && sub[s].by[c] != 0xffffffffu) {
+            const int ly = local >> (logw - 3), lx = local & (bw - 1);
+            tile[(((s >> lognx) << logh) + ly) * 33 + ((s & ((1 << lognx) - 1)) << logw) + lx] = s_llf[warp][s][local];
+          }
+        }
+        __syncwarp();
+        {  // rows: lane = tile row, the row's blocks one after the other
+          const int sy = int(lane) >> logh;
+          for (int bxi = 0; bxi < (1 << lognx); ++bxi)
+            if ((sy << lognx) + bxi < nb) idct_line_dispatch(tile + lane * 33 + (bxi << logw), 1, w);
+        }
+        __syncwarp();
+        for (int sy = 0; sy < ny; ++sy)  // columns: lane = tile column
+          if ((sy << lognx) + sx < nb) idct_line_dispatch(tile + (sy << logh) * 33 + lane, 33, h);
+        __syncwarp();
+#pragma unroll 1
+        for (int y0 = 0; y0 < 32; y0 += 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int Y = y0 + j, sy = Y >> logh, y = Y & (h - 1);
+            float* dst = sy == 0 ? col[0] : (sy == 1 ? col[1] : (sy == 2 ? col[2] : col[3]));
+            if (dst) dst[size_t(y) * f.cw] = tile[Y * 33 + int(lane)];
+          }
+        }
+        __syncwarp();
+      }
     }
-  }
   }
 }
 
@@ -1139,7 +1218,8 @@ void launch_hf_dequant_cfl(DevFrame f, DevDequantParams p, cudaStream_t stream) 
 size_t hf_transform_scratch_bytes(uint32_t bw, uint32_t bh) {
   const size_t cells = size_t(bw) * bh;
   // counters | small | (former medium list) | large | huge | the eight medium shapes (cells/2 x 2, /4 x 3, /8 x 2, /16)
-  return 256 + (cells + cells / 2 + 2 * (cells / 32 + 1) + 64) * 4 + (cells * 9 / 4 + 64) * 4;
+  // ... | the ten small types (cells each)
+  return 256 + (cells + cells / 2 + 2 * (cells / 32 + 1) + 64) * 4 + (cells * 9 / 4 + 64) * 4 + size_t(kSmallTypes) * (cells + 1) * 4;
 }
 
 namespace {
@@ -1147,7 +1227,7 @@ template <bool DEQ>
 void launch_idcts(DevFrame f, const DevDequantParams& dq, const TransformLists& L, size_t cells, int num_sms, cudaStream_t stream) {
   const size_t per = DEQ ? 1 : 3;  // work items per varblock
   const int small_grid = int(std::min<size_t>((cells * per + kSmallGroups - 1) / kSmallGroups, size_t(num_sms) * 8));
-  idct_small_kernel<DEQ><<<small_grid, kSmallGroups * 8, 0, stream>>>(f, dq, L.items[0], L.counts + 0);
+  idct_small_kernel<DEQ><<<small_grid, kSmallGroups * 8, 0, stream>>>(f, dq, L);
   const int medium_grid = int(std::min<size_t>((cells / 2 * per + kMediumWarps) / kMediumWarps, size_t(num_sms) * 8));
   idct_medium_kernel<DEQ><<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, dq, L);
   const int large_grid = int(std::min<size_t>((cells / 32 + 1) * per, size_t(num_sms) * 4));
@@ -1175,8 +1255,12 @@ void launch_hf_transform(DevFrame f, void* scratch, const DevDequantParams* dq, 
       L.shape_items[sh] = q;
       q += cells / kShapeCells[sh] + 1;
     }
+    for (int k = 0; k < kSmallTypes; ++k) {
+      L.small_items[k] = q;
+      q += cells + 1;
+    }
   }
-  cudaMemsetAsync(L.counts, 0, 64, stream);
+  cudaMemsetAsync(L.counts, 0, 128, stream);
   dim3 cb(32, 8), cg((f.bw + 31) / 32, (f.bh + 7) / 8);
   classify_varblocks_kernel<<<cg, cb, 0, stream>>>(f, L);
   static int num_sms = 0;

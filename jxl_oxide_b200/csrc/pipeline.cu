@@ -115,7 +115,7 @@ class BatchService : public LfBatchService {
     }
     cv_pending_.notify_one();
     std::unique_lock<std::mutex> lk(mu_);
-    cv_done_.wait(lk, [&] { return w.done; });
+    w.cv.wait(lk, [&] { return w.done; });
     if (w.error != cudaSuccess) fail(kErrCuda, std::string("CUDA error in the LF batch: ") + cudaGetErrorString(w.error));
   }
   uint64_t launches() const { return launches_; }
@@ -127,6 +127,7 @@ class BatchService : public LfBatchService {
     LfBatchItem* item = nullptr;
     bool done = false;
     cudaError_t error = cudaSuccess;
+    std::condition_variable cv;
   };
   struct Batch {
     cudaStream_t stream = nullptr;
@@ -138,7 +139,7 @@ class BatchService : public LfBatchService {
     bool timed = false;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     std::vector<Waiter*> riders;
-    std::chrono::steady_clock::time_point t0;
+    std::chrono::steady_clock::time_point t0, t_launch;
   };
 
   void finish(Batch& b, cudaError_t err) {
@@ -146,15 +147,32 @@ class BatchService : public LfBatchService {
     if (b.timed && err == cudaSuccess) cudaEventElapsedTime(&ms, b.e0, b.e1);
     {
       std::lock_guard<std::mutex> lk(mu_);
-      for (Waiter* w : b.riders) {
+      for (Waiter* w : b.riders) {  // those not woken by their own completion word
         w->item->elapsed_ms = ms;
         w->error = err;
         w->done = true;
+        w->cv.notify_one();
       }
     }
     b.riders.clear();
     b.busy = false;
-    cv_done_.notify_all();
+  }
+  // Riders whose own streams have all finished leave without waiting for the rest of the launch.
+  void wake_finished(Batch& b) {
+    size_t keep = 0;
+    for (size_t i = 0; i < b.riders.size(); ++i) {
+      Waiter* w = b.riders[i];
+      const LfBatchItem& it = *w->item;
+      if (it.done_flag && *it.done_flag == it.ref.done_seq) {
+        std::atomic_thread_fence(std::memory_order_acquire);
+        std::lock_guard<std::mutex> lk(mu_);
+        w->done = true;
+        w->cv.notify_one();  // `w` lives on its thread's stack: not touched after this
+      } else {
+        b.riders[keep++] = w;
+      }
+    }
+    b.riders.resize(keep);
   }
 
   void launch(Batch& b, std::vector<Waiter*>& take) {
@@ -194,7 +212,7 @@ class BatchService : public LfBatchService {
     b.riders = take;
     b.busy = true;
     b.timed = timed;
-    b.t0 = std::chrono::steady_clock::now();
+    b.t0 = b.t_launch = std::chrono::steady_clock::now();
     ++launches_;
     items_ += take.size();
     if (err != cudaSuccess) {  // nothing useful is in flight: report to the riders right away
@@ -210,8 +228,11 @@ class BatchService : public LfBatchService {
       bool any_busy = false;
       for (Batch& b : batches_) {
         if (!b.busy) continue;
+        wake_finished(b);
         if (*b.flag == b.seq) {
           std::atomic_thread_fence(std::memory_order_acquire);
+          const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - b.t_launch).count();
+          ema_batch_ms_ = ema_batch_ms_ == 0.0 ? ms : 0.8 * ema_batch_ms_ + 0.2 * ms;
           finish(b, cudaSuccess);
         } else if (std::chrono::steady_clock::now() - b.t0 > std::chrono::milliseconds(500)) {
           cudaError_t e = cudaStreamQuery(b.stream);  // a faulting kernel never writes the word
@@ -229,6 +250,14 @@ class BatchService : public LfBatchService {
           free_batch = &b;
           break;
         }
+      // Pacing: with every batch stream free at once, the first arrival would take one stream, the next arrival the next
+      // one ... and everything after that waits a whole kernel (80 ms) for the streams to free up - again all together.
+      // Launches are therefore spaced a stream's share of the typical batch duration apart: the streams stay staggered
+      // and a frame waits that share at most (half of it on average) for its ride.
+      const auto now = std::chrono::steady_clock::now();
+      const double since_ms = std::chrono::duration<double, std::milli>(now - last_launch_).count();
+      const double gap_ms = std::min(30.0, std::max(0.5, ema_batch_ms_ / double(batches_.size())));
+      if (any_busy && since_ms < gap_ms) free_batch = nullptr;
       {
         std::unique_lock<std::mutex> lk(mu_);
         if (stop_ && pending_.empty() && !any_busy) return;
@@ -246,6 +275,7 @@ class BatchService : public LfBatchService {
       }
       if (!take.empty()) {
         launch(*free_batch, take);
+        last_launch_ = std::chrono::steady_clock::now();
         continue;
       }
       std::this_thread::sleep_for(std::chrono::microseconds(60));
@@ -256,10 +286,12 @@ class BatchService : public LfBatchService {
   std::vector<Batch> batches_;
   std::thread thread_;
   std::mutex mu_;
-  std::condition_variable cv_pending_, cv_done_;
+  std::condition_variable cv_pending_;
   std::deque<Waiter*> pending_;
   bool stop_ = false;
   uint64_t launches_ = 0, items_ = 0;
+  std::chrono::steady_clock::time_point last_launch_{};
+  double ema_batch_ms_ = 0.0;  // host clock, launch to completion word
 };
 
 // CPUs local to the GPU's PCIe root (sysfs), so that worker threads - and whatever they first-touch - sit on the NUMA
@@ -547,7 +579,8 @@ int32_t jxlb_pipeline_create(int32_t device, const jxlb_pipeline_config* cfg, jx
       for (jxlb_decoder* q : p->decoders) jxlb_decoder_destroy(q);
       return rc;
     }
-    if (cfg && cfg->hf_streams_per_cta > 0) jxlb_set_hf_streams_per_cta(d, cfg->hf_streams_per_cta);
+    // many frames in flight: one thread per HF stream (16 warps per 8K frame instead of 510 one-lane warps), see bench.py
+    jxlb_set_hf_streams_per_cta(d, cfg && cfg->hf_streams_per_cta > 0 ? cfg->hf_streams_per_cta : 128);
     p->decoders.push_back(d);
   }
   if (!(cfg && cfg->no_affinity)) p->cpus = device_local_cpus(device);

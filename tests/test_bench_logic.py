@@ -16,7 +16,7 @@ def test_workloads_are_seeded_and_sized():
 
 
 def test_fixed_hf_schedule_and_roofline_families():
-    assert bench.HF_STREAMS_PER_CTA in (0, 8, 16)
+    assert bench.HF_STREAMS_PER_CTA in (8, 16, 32, 64, 128) and bench.HF_LATENCY_SCHEDULE in (8, 16, 32)
     assert set(bench.CHAIN) & set(bench.KERNELS) and set(bench.ENTROPY) <= set(bench.KERNELS)
     assert bench.algorithmic_bytes("filters_fused", 7680, 4320, 0) == 7680 * 4320 * 24
 

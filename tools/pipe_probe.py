@@ -24,7 +24,8 @@ def main():
     _, frames, (w, h) = bench.load_workload(workload, 4)
     for st in settings:
         workers, heavy = (int(x) for x in st.split(":"))
-        pipe = J.Pipeline(0, workers=workers, heavy_frames=heavy, hf_streams_per_cta=hf, no_affinity=noaff)
+        pipe = J.Pipeline(0, workers=workers, heavy_frames=heavy, hf_streams_per_cta=hf, no_affinity=noaff,
+                          batch_streams=int(os.environ.get("PROBE_BATCH", "6")))
         for k, f in enumerate(frames):
             pipe.preload(k, f)
 
