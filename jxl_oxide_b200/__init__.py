@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjxlb200.so")
+LIB_PATH = os.environ.get("JXLB_LIB") or os.path.join(_HERE, "libjxlb200.so")  # JXLB_LIB: experiment builds (build.build_variant)
 
 OK, ERR_BITSTREAM, ERR_UNSUPPORTED, ERR_EOF, ERR_CUDA, ERR_INVALID_ARG, ERR_DEVICE_DECODE, ERR_OUT_OF_MEMORY = range(8)
 

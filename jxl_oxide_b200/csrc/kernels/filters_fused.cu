@@ -19,6 +19,7 @@
 // crates/jxl-color/src/xyb.rs). Border semantics: Gaborish uses its own edge formulas on the image
 // border (gabor.rs:119-167); EPF mirrors coordinates (util.rs:376-386) -- after each stage the part
 // of the halo that lies outside the image is filled by mirroring, so the stencils index plainly.
+#include "filter_strip.cuh"
 #include "kernels.h"
 
 #include <cuda.h>  // CUtensorMap (types only: the encoder entry point is fetched from the driver at run time)
@@ -307,7 +308,29 @@ struct FusedViews {
   uint32_t in_stride[3], out_stride[3];
   int width, height;
   int use_tma;  // the three input planes are described by `maps` (row pitch a multiple of 16 bytes)
+  // border_only: the launch is a 1-D grid over the tiles outside [1, bx_last] x [1, by_last] (the strip kernel covers those)
+  int border_only, bx_last, by_last, nbx, nby;
 };
+
+// Tile of a border-only launch: row 0, then the rows below by_last, then the left column and the columns right of bx_last
+// of the rows in between.
+__device__ __forceinline__ void border_tile_of(const FusedViews& v, int i, int& tx, int& ty) {
+  if (i < v.nbx) {
+    tx = i, ty = 0;
+    return;
+  }
+  i -= v.nbx;
+  const int n_bottom = v.nbx * (v.nby - 1 - v.by_last);
+  if (i < n_bottom) {
+    ty = v.by_last + 1 + i / v.nbx, tx = i % v.nbx;
+    return;
+  }
+  i -= n_bottom;
+  const int per_row = 1 + (v.nbx - 1 - v.bx_last);
+  ty = 1 + i / per_row;
+  const int j = i % per_row;
+  tx = j == 0 ? 0 : v.bx_last + j;
+}
 
 // TMA descriptors of the three input planes (2-D, f32, box kS x kS, out-of-bounds cells read as zero).
 struct FusedMaps {
@@ -345,7 +368,9 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
   float* dmap = s_buf + 6 * kPlane;  // [NMAPS][kS][kS]
   const int width = v.width, height = v.height;
   // shared cell (lx, ly) <-> image pixel (gx0 + lx, gy0 + ly)
-  const int gx0 = int(blockIdx.x) * kT - kHM, gy0 = int(blockIdx.y) * kT - kHM;
+  int tile_x = int(blockIdx.x), tile_y = int(blockIdx.y);
+  if (v.border_only) border_tile_of(v, int(blockIdx.x), tile_x, tile_y);
+  const int gx0 = tile_x * kT - kHM, gy0 = tile_y * kT - kHM;
   const bool border_tile = gx0 < 0 || gy0 < 0 || gx0 + kS > width || gy0 + kS > height;
   const int r_gab = p.gab_enabled ? 1 : 0;
   const int r0 = p.epf_iters == 3 ? 3 : 0, r1 = p.epf_iters >= 1 ? 2 : 0, r2 = p.epf_iters >= 2 ? 1 : 0;
@@ -497,6 +522,53 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
   }
 }
 
+
+// Interior of the frame for the default filter chain (Gaborish, EPF steps 1 and 2, colour): kernels/filter_strip.cuh.
+template <int ITERS>
+__global__ void __launch_bounds__(fstrip::kThreads, 3)
+strip_filter_kernel(FusedViews v, DevFusedFilterParams p, const __grid_constant__ FusedMaps maps, fstrip::StripRect r, float gw0,
+                    float gw1, float gw2) {
+  using namespace fstrip;
+  extern __shared__ __align__(128) float s_buf[];
+  __shared__ __align__(8) unsigned long long s_mbar;
+  const int tid = int(threadIdx.x);
+  const StripGeom g = strip_geom(v.width, v.height, r.x0, r.y0, r.x1, r.y1, int(blockIdx.x), int(blockIdx.y));
+  const uint32_t mbar = smem_u32(&s_mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(uint32_t(3 * kPlane * sizeof(float))) : "memory");
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+              smem_u32(s_buf + c * kPlane)),
+          "l"(reinterpret_cast<uint64_t>(&maps.map[c])), "r"(g.gx0), "r"(g.gy0), "r"(mbar)
+          : "memory");
+  }
+  phase_sigma(tid, s_buf, g, p);
+  __syncthreads();  // the barrier is initialised before anybody polls it; sigma table complete
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done && spin < (1u << 24); ++spin)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(mbar), "r"(0u)
+        : "memory");
+  const float gw[3] = {gw0, gw1, gw2};
+  phase_gab(tid, s_buf, p, gw);
+  __syncthreads();
+  phase_dist1(tid, s_buf, p);
+  __syncthreads();
+  if (ITERS == 1) {
+    phase_apply1<true>(tid, s_buf, g, p, v.out, v.out_stride);
+  } else {
+    phase_apply1<false>(tid, s_buf, g, p, v.out, v.out_stride);
+    __syncthreads();
+    phase_apply2(tid, s_buf, g, p, v.out, v.out_stride);
+  }
+}
+
 }  // namespace
 
 bool fused_filters_supported(uint32_t width, uint32_t height) { return width >= 16 && height >= 16; }
@@ -555,10 +627,45 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
     cudaFuncSetAttribute(fused_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * window_size(0) * window_size(0) * 4);
     cudaFuncSetAttribute(fused_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * window_size(2) * window_size(2) * 4);
     cudaFuncSetAttribute(fused_filter_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * window_size(6) * window_size(6) * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
     attr_set = true;
   }
   dim3 block(32, 8);
   dim3 grid((v.width + kT - 1) / kT, (v.height + kT - 1) / kT);
+  v.border_only = 0, v.bx_last = v.by_last = 0, v.nbx = int(grid.x), v.nby = int(grid.y);
+
+  // The default chains (Gaborish + EPF step 1, or steps 1 and 2) run the interior of the frame in the column-strip kernel and only the
+  // tiles that touch the image border (mirroring, Gaborish edge formulas) in the general one.
+  static const bool no_strip = std::getenv("JXLB_NO_STRIP") != nullptr;
+  const fstrip::StripRect r = fstrip::strip_rect(v.width, v.height);
+  if (!no_strip && v.use_tma && p.gab_enabled && (p.epf_iters == 1 || p.epf_iters == 2) && r.x1 > r.x0 && r.y1 > r.y0) {
+    FusedMaps smaps;
+    std::memset(&smaps, 0, sizeof(smaps));
+    bool ok = true;
+    EncodeTiledFn enc = tensor_map_encoder();
+    for (int c = 0; c < 3 && ok; ++c) {
+      const cuuint64_t dims[2] = {cuuint64_t(v.width), cuuint64_t(v.height)};
+      const cuuint64_t strides[1] = {cuuint64_t(v.in_stride[c]) * 4};
+      const cuuint32_t box[2] = {cuuint32_t(fstrip::kWX), cuuint32_t(fstrip::kWY)};
+      const cuuint32_t estr[2] = {1, 1};
+      ok = enc(&smaps.map[c], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(v.in[c]), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    if (ok) {
+      float gw[3];
+      for (int c = 0; c < 3; ++c) gw[c] = 1.0f / ((1.0f + p.gab_w[c][0] * 4.0f) + p.gab_w[c][1] * 4.0f);
+      dim3 sgrid((r.x1 - r.x0 + fstrip::kTX - 1) / fstrip::kTX, (r.y1 - r.y0 + fstrip::kTY - 1) / fstrip::kTY);
+      if (p.epf_iters == 1) strip_filter_kernel<1><<<sgrid, fstrip::kThreads, fstrip::kSmemFloats * 4, stream>>>(v, p, smaps, r, gw[0], gw[1], gw[2]);
+      else strip_filter_kernel<2><<<sgrid, fstrip::kThreads, fstrip::kSmemFloats * 4, stream>>>(v, p, smaps, r, gw[0], gw[1], gw[2]);
+      v.border_only = 1;
+      v.bx_last = r.x1 / 32 - 1, v.by_last = r.y1 / 32 - 1;
+      const int n_border = v.nbx * v.nby - v.bx_last * v.by_last;
+      fused_filter_kernel<2><<<dim3(n_border), block, 8 * plane_bytes, stream>>>(v, p, maps);
+      return;
+    }
+  }
   if (p.epf_iters == 3) fused_filter_kernel<6><<<grid, block, 12 * plane_bytes, stream>>>(v, p, maps);
   else if (p.epf_iters > 0) fused_filter_kernel<2><<<grid, block, 8 * plane_bytes, stream>>>(v, p, maps);
   else fused_filter_kernel<0><<<grid, block, 6 * plane_bytes, stream>>>(v, p, maps);

@@ -847,6 +847,13 @@ __device__ __forceinline__ void cfl_factors(const DevFrame& f, const DevDequantP
   kb = __fadd_rn(p.base_correlation_b, __fdiv_rn(float(f.b_from_y[ti]), p.colour_factor));
 }
 
+// Experiment knobs (build.build_variant): defaults are the measured best.
+#ifndef JXLB_SMALL_PREFETCH
+#define JXLB_SMALL_PREFETCH 1  // idct_small: request the three channels' rows of a block together
+#endif
+#ifndef JXLB_MEDIUM_TRIP
+#define JXLB_MEDIUM_TRIP 8    // idct_medium: tile rows whose loads are in flight together (4, 8, 16, 32)
+#endif
 constexpr int kSmallGroups = 32;  // 8-thread groups per CTA
 template <bool DEQ>
 __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
@@ -867,7 +874,17 @@ __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f
     const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
     DeqBlock db;
     float kx = 0.0f, kb = 0.0f, vy[8];
+    // DEQ (never subsampled: every channel keeps the block at (sbx, sby)): the coefficient rows of the three channels are
+    // requested together, before the first use - one exposed DRAM latency per block instead of three
+    float4 pre[3][2];
+    constexpr bool kPre = DEQ && JXLB_SMALL_PREFETCH;
     if (DEQ) {
+#pragma unroll
+      for (int c = 0; kPre && c < 3; ++c) {
+        const float* prow = reinterpret_cast<const float*>(f.coeff[c]) + (size_t(sby) * 8 + r) * f.cw + size_t(sbx) * 8;
+        pre[c][0] = *reinterpret_cast<const float4*>(prow);
+        pre[c][1] = *reinterpret_cast<const float4*>(prow + 4);
+      }
       db = deq_block(f, dq, t, sbx, sby);
       cfl_factors(f, dq, sbx * 8, sby * 8, kx, kb);
     }
@@ -877,7 +894,13 @@ __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f
       uint32_t bx, by;  // where channel c keeps this block
       if (!channel_block(f, c, sbx, sby, bx, by)) continue;
       float* row = reinterpret_cast<float*>(f.coeff[c]) + (size_t(by) * 8 + r) * f.cw + size_t(bx) * 8;
-      const float4 lo = *reinterpret_cast<const float4*>(row), hi = *reinterpret_cast<const float4*>(row + 4);
+      float4 lo, hi;
+      if (kPre) {
+        lo = ci == 0 ? pre[1][0] : (ci == 1 ? pre[0][0] : pre[2][0]);
+        hi = ci == 0 ? pre[1][1] : (ci == 1 ? pre[0][1] : pre[2][1]);
+      } else {
+        lo = *reinterpret_cast<const float4*>(row), hi = *reinterpret_cast<const float4*>(row + 4);
+      }
       float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
       if (DEQ) {
         const float4 m0 = __ldg(reinterpret_cast<const float4*>(db.mat[c] + r * 8));
@@ -1025,19 +1048,20 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
           if (sy < ny && s < nb && sub[s].by[c] != 0xffffffffu)
             col[sy] = reinterpret_cast<float*>(f.coeff[c]) + size_t(sub[s].by[c]) * 8 * f.cw + size_t(sub[s].bx[c]) * 8 + x;
         }
-        // 32 tile rows, four per trip, all loads of a trip issued before the first use
+        // 32 tile rows, kTrip per trip, all loads of a trip issued before the first use
+        constexpr int kTrip = JXLB_MEDIUM_TRIP;
 #pragma unroll 1
-        for (int y0 = 0; y0 < 32; y0 += 4) {
-          float raw[4], mt[4];
+        for (int y0 = 0; y0 < 32; y0 += kTrip) {
+          float raw[kTrip], mt[kTrip];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kTrip; ++j) {
             const int Y = y0 + j, sy = Y >> logh, y = Y & (h - 1);
             const float* src = sy == 0 ? col[0] : (sy == 1 ? col[1] : (sy == 2 ? col[2] : col[3]));
             raw[j] = src ? src[size_t(y) * f.cw] : 0.0f;
             if (DEQ) mt[j] = __ldg(mat[c] + (y << logw) + x);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kTrip; ++j) {
             const int Y = y0 + j, sy = Y >> logh, y = Y & (h - 1);
             float v = raw[j];
             if (DEQ) {

@@ -22,10 +22,13 @@ inline void emu_trip(bool is_coefficient) {
 }  // namespace
 #define JXLB_LANE_TRIP(c) emu_trip(c)
 #include "../../jxl_oxide_b200/csrc/kernels/hf_lanes.cuh"
+#include "../../jxl_oxide_b200/csrc/kernels/filter_strip.cuh"
 #include "../../oracle/oracle_backend.h"
 #include "../../jxl_oxide_b200/csrc/host/planner.h"
 
 namespace {
+// strip filter emulation: [0] frames that took the path, [1] pixels compared, [2] pixels that differ from the oracle's stages
+std::atomic<uint64_t> g_strip_stats[3];
 std::atomic<uint64_t> g_hf_streams{0};
 // accumulated over all decode_hf() calls since the last reset:
 //   [0] streams, [1] symbols (= lane trips), [2] warp trips (sum over warps of the longest lane), [3] warp trips with
@@ -121,6 +124,8 @@ class EmuBackend : public OracleBackend {
     std::memcpy(storage_.data(), data, size);
   }
   void decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) override;
+  bool filters_colour_fused(const View v[3], const RestorationFilter& rf, const View& sigma, bool sigma_is_constant,
+                            const ColorParams* colour) override;
 
  private:
   std::vector<uint64_t> storage_;  // 8-byte aligned
@@ -271,5 +276,116 @@ void EmuBackend::decode_hf(VarDctState& st, std::vector<HfGroupJob>& jobs) {
 }
 
 OracleBackend* make_emu_backend(int threads) { return new EmuBackend(threads); }
+
+}  // namespace jxlo
+
+// ---- the column-strip filter kernel (kernels/filter_strip.cuh) on the host ------------------------------------------
+// Every CTA of the launch is run thread by thread, phase by phase (the phases are separated by __syncthreads() on the
+// device, so running all threads of a phase before the next one is an admissible schedule); the window is filled the way
+// the TMA copy fills it. The oracle's own stages then process the planes in place, the interior rectangle is compared
+// pixel for pixel (bit patterns) and replaced by the emulated kernel's output.
+extern "C" void jxle_strip_stats(uint64_t out[3], int reset) {
+  for (int i = 0; i < 3; ++i) {
+    out[i] = g_strip_stats[i].load();
+    if (reset) g_strip_stats[i].store(0);
+  }
+}
+
+namespace jxlo {
+
+bool EmuBackend::filters_colour_fused(const View v[3], const RestorationFilter& rf, const View& sigma, bool sigma_is_constant,
+                                      const ColorParams* colour) {
+  using namespace jxlb::fstrip;
+  const int width = int(v[0].w), height = int(v[0].h);
+  const StripRect r = strip_rect(width, height);
+  const bool colour_ok = !colour || (!colour->second_stage && colour->gamma == 0.0f);
+  if (std::getenv("JXLE_TRACE"))
+    std::fprintf(stderr, "[emu] filters: %d x %d, gab %d, epf iters %u, colour %d\n", width, height, int(rf.gab_enabled), rf.epf.iters, int(colour != nullptr));
+  if (!rf.gab_enabled || (rf.epf.iters != 1 && rf.epf.iters != 2) || r.x1 <= r.x0 || r.y1 <= r.y0 || !colour_ok || std::getenv("JXLE_NO_STRIP")) return false;
+  for (int c = 0; c < 3; ++c)
+    if (v[c].x0 != 0 || v[c].y0 != 0 || int(v[c].w) != width || int(v[c].h) != height) return false;
+
+  DevFusedFilterParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.gab_enabled = 1;
+  for (int c = 0; c < 3; ++c) {
+    p.gab_w[c][0] = rf.gab_weights[c][0];
+    p.gab_w[c][1] = rf.gab_weights[c][1];
+    p.epf.channel_scale[c] = rf.epf.channel_scale[c];
+  }
+  p.epf_iters = int(rf.epf.iters);
+  p.epf.pass0_sigma_scale = rf.epf.pass0_sigma_scale;
+  p.epf.pass2_sigma_scale = rf.epf.pass2_sigma_scale;
+  p.epf.border_sad_mul = rf.epf.border_sad_mul;
+  p.epf.sigma_for_modular = rf.epf.sigma_for_modular;
+  if (!sigma_is_constant) {
+    Plane& sp = plane(sigma.plane);
+    p.sigma = sp.f32();
+    p.sigma_stride = sp.w;
+  }
+  if (colour) {
+    p.colour = 1;
+    for (int i = 0; i < 3; ++i) p.col.opsin_bias[i] = colour->opsin_bias[i], p.col.cbrt_opsin_bias[i] = colour->cbrt_opsin_bias[i];
+    p.col.itscale = colour->itscale;
+    for (int i = 0; i < 9; ++i) p.col.matrix[i] = colour->matrix[i];
+    p.col.apply_srgb_tf = colour->apply_srgb_tf ? 1 : 0;
+    p.col.apply_bt709_tf = colour->apply_bt709_tf ? 1 : 0;
+  }
+  float gw[3];
+  for (int c = 0; c < 3; ++c) gw[c] = 1.0f / ((1.0f + p.gab_w[c][0] * 4.0f) + p.gab_w[c][1] * 4.0f);
+
+  const float* in[3];
+  uint32_t in_stride[3], out_stride[3];
+  std::vector<std::vector<float>> out_store(3);
+  float* out[3];
+  for (int c = 0; c < 3; ++c) {
+    Plane& pl_c = plane(v[c].plane);
+    in[c] = pl_c.f32();
+    in_stride[c] = pl_c.w;
+    out_store[c].assign(size_t(width) * height, 0.0f);
+    out[c] = out_store[c].data();
+    out_stride[c] = uint32_t(width);
+  }
+  const int ntx = (r.x1 - r.x0 + kTX - 1) / kTX, nty = (r.y1 - r.y0 + kTY - 1) / kTY;
+  parallel_for(size_t(ntx) * nty, [&](size_t t) {
+    const int tx = int(t % ntx), ty = int(t / ntx);
+    const StripGeom g = strip_geom(width, height, r.x0, r.y0, r.x1, r.y1, tx, ty);
+    std::vector<float> s(kSmemFloats, std::nanf(""));
+    for (int c = 0; c < 3; ++c)  // the TMA box: kWX x kWY cells at (gx0, gy0)
+      for (int y = 0; y < kWY; ++y)
+        for (int x = 0; x < kWX; ++x) s[c * kPlane + y * kWX + x] = in[c][size_t(g.gy0 + y) * in_stride[c] + g.gx0 + x];
+    for (int tid = 0; tid < kThreads; ++tid) phase_sigma(tid, s.data(), g, p);
+    for (int tid = 0; tid < kThreads; ++tid) phase_gab(tid, s.data(), p, gw);
+    for (int tid = 0; tid < kThreads; ++tid) phase_dist1(tid, s.data(), p);
+    if (p.epf_iters == 1) {
+      for (int tid = 0; tid < kThreads; ++tid) phase_apply1<true>(tid, s.data(), g, p, out, out_stride);
+    } else {
+      for (int tid = 0; tid < kThreads; ++tid) phase_apply1<false>(tid, s.data(), g, p, out, out_stride);
+      for (int tid = 0; tid < kThreads; ++tid) phase_apply2(tid, s.data(), g, p, out, out_stride);
+    }
+  });
+
+  OracleBackend::gaborish(v, rf.gab_weights);
+  OracleBackend::epf(v, sigma, rf.epf, sigma_is_constant);
+  if (colour) OracleBackend::xyb_to_rgb(v, *colour);
+  uint64_t compared = 0, differ = 0;
+  for (int c = 0; c < 3; ++c) {
+    Plane& pl_c = plane(v[c].plane);
+    for (int y = r.y0; y < r.y1; ++y)
+      for (int x = r.x0; x < r.x1; ++x) {
+        uint32_t& want = pl_c.data[size_t(y) * pl_c.w + x];
+        uint32_t got;
+        std::memcpy(&got, &out[c][size_t(y) * width + x], 4);
+        ++compared;
+        if (got != want) {
+          if (!differ && std::getenv("JXLE_TRACE")) std::fprintf(stderr, "[emu] strip filter: first difference at c=%d x=%d y=%d: %08x vs %08x\n", c, x, y, got, want);
+          ++differ;
+        }
+        want = got;
+      }
+  }
+  g_strip_stats[0] += 1, g_strip_stats[1] += compared, g_strip_stats[2] += differ;
+  return true;
+}
 
 }  // namespace jxlo
