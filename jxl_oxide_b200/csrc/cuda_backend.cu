@@ -29,6 +29,16 @@ CudaBackend::CudaBackend(int device, bool own_stream) : device_(device), own_str
   if (e != cudaSuccess || count == 0)
     fail(kErrCuda, "no CUDA device available: the jxl_oxide_b200 hot path has no CPU fallback");
   CUDA_CHECK(cudaSetDevice(device_));
+  {
+    // The inverse transforms read 32-byte row segments of varblocks whose neighbours (of another size class) are fetched by
+    // another kernel at another time; with the default L2 fetch granularity every such read drags in the rest of its line
+    // (ncu: idct_small 342 MB read for 108 MB of coefficients). JXLB_L2_FETCH = 32 / 64 / 128 sets the device limit.
+    static const int l2_fetch = [] {
+      const char* e = std::getenv("JXLB_L2_FETCH");
+      return e ? std::atoi(e) : 0;
+    }();
+    if (l2_fetch > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(l2_fetch));
+  }
   if (own_stream_) CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CUDA_CHECK(cudaEventCreateWithFlags(&sync_event_, cudaEventBlockingSync | cudaEventDisableTiming));
   stage_cap_ = size_t(2) << 20;

@@ -847,9 +847,11 @@ __device__ __forceinline__ void cfl_factors(const DevFrame& f, const DevDequantP
   kb = __fadd_rn(p.base_correlation_b, __fdiv_rn(float(f.b_from_y[ti]), p.colour_factor));
 }
 
-// Experiment knobs (build.build_variant): defaults are the measured best.
+// Experiment knobs (build.build_variant): defaults are the measured best (profiles/r02_progress.md, call U: requesting
+// the three channels together costs idct_small 39 registers and a third of its warps: 0.327 ms against 0.239 ms; medium
+// trips of 4 / 8 / 16 rows: 0.599 / 0.503 / 0.572 ms).
 #ifndef JXLB_SMALL_PREFETCH
-#define JXLB_SMALL_PREFETCH 1  // idct_small: request the three channels' rows of a block together
+#define JXLB_SMALL_PREFETCH 0  // idct_small: request the three channels' rows of a block together
 #endif
 #ifndef JXLB_MEDIUM_TRIP
 #define JXLB_MEDIUM_TRIP 8    // idct_medium: tile rows whose loads are in flight together (4, 8, 16, 32)
@@ -1113,6 +1115,153 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
   }
 }
 
+// ---- medium varblocks, dequantising form, one instantiation per shape --------------------------------------------------
+// Same tiling as idct_medium_kernel (one warp per 32 x 32 tile of equally shaped blocks, lane = tile column in the load /
+// column / store passes, lane = tile row in the row pass) and the same per-sample operations in the same order, but the
+// shape is a template parameter: block-row / row loops are static, so the per-sample pointer selection, shifts and table
+// look-ups of the generic body (which spent ~3x more instructions on indexing than on arithmetic, ncu) fold into
+// immediates. The shapes are walked one after the other by all CTAs in step, so one instantiation's code is hot at a time,
+// and the line transforms are the shared idct_line_smem<N>.
+struct MediumBlk {
+  uint32_t bx, by;     // block position in 8x8 cells (dequantising frames are never subsampled: the same for all channels)
+  float mul[3];        // DeqBlock::mul
+  float kx[4], kb[4];  // chroma-from-luma factors of the 2 x 2 64x64 tiles at (tx0, ty0)
+  int xsplit, ysplit;  // first sample column / row of the block that lies in the right / lower 64x64 tile (>= w / h: none)
+};
+
+template <int LOGW, int LOGH>
+__device__ __forceinline__ void medium_walk(const DevFrame& f, const DevDequantParams& dq, const uint32_t* __restrict__ items,
+                                            uint32_t total, float* tile, float* ytile, float (*llf)[16], MediumBlk* sub,
+                                            uint32_t first_group, uint32_t group_stride, uint32_t lane) {
+  constexpr int W = 1 << LOGW, H = 1 << LOGH, NX = 32 / W, NY = 32 / H, LOGP = (5 - LOGW) + (5 - LOGH), NB = 1 << LOGP;
+  constexpr int BW = W / 8, BH = H / 8;
+  const uint32_t item0 = items[0];
+  const int32_t t = f.blk_type[size_t(item0 >> 16) * f.bw + (item0 & 0xffff)];  // one transform type per shape list
+  const uint32_t set = kDevTransformInfo[t][2], tr = kDevTransformInfo[t][4];
+  const int sx = int(lane) >> LOGW, x = int(lane) & (W - 1);
+#pragma unroll 1
+  for (uint32_t group = first_group; (group << LOGP) < total; group += group_stride) {
+    const uint32_t first = group << LOGP;
+    const int nb = int(min(uint32_t(NB), total - first));
+    __syncwarp();
+    if (int(lane) < nb) {  // lane s describes block s of the tile
+      MediumBlk m;
+      const uint32_t item = items[first + lane];
+      m.bx = item & 0xffff, m.by = item >> 16;
+      const DeqBlock db = deq_block(f, dq, t, m.bx, m.by);
+      const uint32_t tx0 = (m.bx * 8) >> 6, ty0 = (m.by * 8) >> 6;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) m.mul[c] = db.mul[c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t tx = min(tx0 + uint32_t(i & 1), f.w64 - 1), ty = min(ty0 + uint32_t(i >> 1), (f.ch + 63) / 64 - 1);
+        cfl_factors(f, dq, tx << 6, ty << 6, m.kx[i], m.kb[i]);
+      }
+      m.xsplit = int((tx0 + 1) * 64 - m.bx * 8);
+      m.ysplit = int((ty0 + 1) * 64 - m.by * 8);
+      sub[lane] = m;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int ci = 0; ci < 3; ++ci) {
+      const uint32_t c = ci == 0 ? 1u : (ci == 1 ? 0u : 2u);  // Y first: its dequantised samples feed the chroma channels
+      const float* __restrict__ matc = dq.matrices + dq.matrix_offset[(set * 3 + c) * 2 + tr] + x;
+      const float qb = dq.quant_bias[c], qbn = dq.quant_bias_numerator;
+      float* const plane = reinterpret_cast<float*>(f.coeff[c]);
+#pragma unroll
+      for (int sy = 0; sy < NY; ++sy) {
+        const int s = sy * NX + sx;
+        const bool have = s < nb;
+        const MediumBlk& m = sub[have ? s : 0];
+        const float* src = plane + size_t(m.by) * 8 * f.cw + size_t(m.bx) * 8 + x;
+        const float mulc = m.mul[c];
+        const int xt = x >= m.xsplit ? 1 : 0;
+        const float k_top = c == 0 ? m.kx[xt] : m.kb[xt], k_bottom = c == 0 ? m.kx[xt + 2] : m.kb[xt + 2];
+        const int ysplit = m.ysplit;
+#pragma unroll
+        for (int y0 = 0; y0 < H; y0 += 8) {
+          float raw[8], mt[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            raw[j] = have ? src[size_t(y0 + j) * f.cw] : 0.0f;
+            mt[j] = __ldg(matc + (y0 + j) * W);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int y = y0 + j, Y = sy * H + y;
+            const float q = deq_one(__float_as_uint(raw[j]), mt[j], mulc, qb, qbn);
+            float v = q;
+            if (c == 1) ytile[Y * 33 + int(lane)] = q;
+            else v = __fadd_rn(q, __fmul_rn(y >= ysplit ? k_bottom : k_top, ytile[Y * 33 + int(lane)]));
+            tile[Y * 33 + int(lane)] = v;
+          }
+        }
+      }
+      // lowest frequencies from the LF image: lane s for block s, then 16 lanes place the (at most) 16 values of the tile
+      if (int(lane) < nb) compute_llf_small(f, int(c), sub[lane].bx, sub[lane].by, BW, BH, llf[lane]);
+      __syncwarp();
+      if (lane < 16) {
+        constexpr int cells_log = (LOGW - 3) + (LOGH - 3);  // LLF values per block
+        const int s = int(lane) >> cells_log, local = int(lane) & ((1 << cells_log) - 1);
+        if (s < nb) {
+          const int ly = local >> (LOGW - 3), lx = local & (BW - 1);
+          tile[(((s >> (5 - LOGW)) << LOGH) + ly) * 33 + ((s & (NX - 1)) << LOGW) + lx] = llf[s][local];
+        }
+      }
+      __syncwarp();
+      {  // rows: lane = tile row, the row's blocks one after the other
+        const int sy = int(lane) >> LOGH;
+#pragma unroll
+        for (int bxi = 0; bxi < NX; ++bxi)
+          if (sy * NX + bxi < nb) idct_line_smem<W>(tile + lane * 33 + bxi * W, 1);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int sy = 0; sy < NY; ++sy)  // columns: lane = tile column
+        if (sy * NX + sx < nb) idct_line_smem<H>(tile + sy * H * 33 + lane, 33);
+      __syncwarp();
+#pragma unroll
+      for (int sy = 0; sy < NY; ++sy) {
+        const int s = sy * NX + sx;
+        if (s < nb) {
+          const MediumBlk& m = sub[s];
+          float* dst = plane + size_t(m.by) * 8 * f.cw + size_t(m.bx) * 8 + x;
+#pragma unroll
+          for (int y = 0; y < H; ++y) dst[size_t(y) * f.cw] = tile[(sy * H + y) * 33 + int(lane)];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMediumWarps * 32, 4) idct_medium_deq_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
+  __shared__ float s_tile[kMediumWarps][32 * 33];
+  __shared__ float s_ytile[kMediumWarps][32 * 33];  // dequantised Y coefficients (chroma from luma)
+  __shared__ float s_llf[kMediumWarps][8][16];
+  __shared__ MediumBlk s_sub[kMediumWarps][8];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t g0 = blockIdx.x * kMediumWarps + warp, gs = gridDim.x * kMediumWarps;
+#pragma unroll 1
+  for (int shape = 0; shape < kMediumShapes; ++shape) {
+    const uint32_t* __restrict__ items = lists.shape_items[shape];
+    const uint32_t total = lists.counts[4 + shape];
+    if (total == 0) continue;
+    float* tile = s_tile[warp];
+    float* yt = s_ytile[warp];
+    switch (shape) {  // medium_shape(): 0: 16x8, 1: 8x16, 2: 16x16, 3: 32x8, 4: 8x32, 5: 32x16, 6: 16x32, 7: 32x32 (w x h samples)
+      case 0: medium_walk<4, 3>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+      case 1: medium_walk<3, 4>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+      case 2: medium_walk<4, 4>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+      case 3: medium_walk<5, 3>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+      case 4: medium_walk<3, 5>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+      case 5: medium_walk<5, 4>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+      case 6: medium_walk<4, 5>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+      default: medium_walk<5, 5>(f, dq, items, total, tile, yt, s_llf[warp], s_sub[warp], g0, gs, lane); break;
+    }
+  }
+}
+
 // dct_2d (general path: both dimensions >= 4) by a CTA; every thread owns 2*nmax floats of `lines`.
 __device__ void dct_2d_coop(float* p, size_t stride, int width, int height, bool forward, float* lines, int nmax) {
   float* line = lines + size_t(threadIdx.x) * (2 * nmax + 1);  // odd stride: conflict-free banks
@@ -1211,6 +1360,114 @@ __global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, D
   }
 }
 
+
+// ---- 64-sample varblocks (64x64, 64x32, 32x64), dequantising form: the block is staged in shared memory ---------------------
+// idct_large_kernel dequantises the three channels in place in global memory and then lets every thread walk a row, later a
+// column, of the block in global memory (one 4-byte request per sample, a warp's requests 64 rows apart). Here a CTA
+// keeps one channel of the block in a 64 x 65 shared tile: coefficients arrive with coalesced loads and are dequantised
+// on the way in (the dequantised Y copy stays in a second tile for chroma from luma), rows are transformed in place,
+// columns through the per-thread line buffers, and the samples leave with coalesced stores - one read and one write
+// of HBM per sample. Per sample the operations and their order are those of idct_large_kernel.
+constexpr int kL64Threads = 128, kL64Pitch = 65, kL64Line = 2 * 64 + 1;
+constexpr int kL64SmemFloats = 2 * 64 * kL64Pitch + 64 + 64 * kL64Line;
+__global__ void __launch_bounds__(kL64Threads) idct_large64_deq_kernel(DevFrame f, DevDequantParams dq, const uint32_t* __restrict__ items,
+                                                                       const uint32_t* __restrict__ count_ptr) {
+  extern __shared__ float s_l64[];
+  float* tile = s_l64;                      // the channel being transformed
+  float* ytile = tile + 64 * kL64Pitch;     // dequantised Y
+  float* llf = ytile + 64 * kL64Pitch;      // <= 8 x 8 LF samples
+  float* lines = llf + 64;                  // 64 per-thread line + scratch buffers (odd pitch: conflict-free banks)
+  __shared__ float s_k[2][25];
+  const int tid = int(threadIdx.x);
+  const uint32_t total = *count_ptr;
+  for (uint32_t work = blockIdx.x; work < total; work += gridDim.x) {
+    const uint32_t item = items[work];
+    const uint32_t sbx = item & 0xffff, sby = item >> 16;
+    const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
+    const int bw = kDevTransformInfo[t][0], bh = kDevTransformInfo[t][1];
+    const int w = bw * 8, h = bh * 8;
+    const int logw = 31 - __clz(w);
+    const DeqBlock db = deq_block(f, dq, t, sbx, sby);
+    const uint32_t tx0 = (sbx * 8) >> 6, ty0 = (sby * 8) >> 6;
+    if (tid < 25) {
+      const uint32_t tx = min(tx0 + uint32_t(tid) % 5, f.w64 - 1), ty = min(ty0 + uint32_t(tid) / 5, (f.ch + 63) / 64 - 1);
+      cfl_factors(f, dq, tx << 6, ty << 6, s_k[0][tid], s_k[1][tid]);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < 3; ++ci) {
+      const uint32_t c = ci == 0 ? 1u : (ci == 1 ? 0u : 2u);
+      float* const block = reinterpret_cast<float*>(f.coeff[c]) + size_t(sby) * 8 * f.cw + size_t(sbx) * 8;
+      const float* __restrict__ matc = db.mat[c];
+      const float mulc = db.mul[c], qb = dq.quant_bias[c], qbn = dq.quant_bias_numerator;
+      // w * h >= 2048: eight samples per thread and trip, their loads in flight together
+      for (int idx0 = tid; idx0 < w * h; idx0 += 8 * kL64Threads) {
+        float raw[8], mt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = idx0 + j * kL64Threads, x = idx & (w - 1), y = idx >> logw;
+          raw[j] = block[size_t(y) * f.cw + x];
+          mt[j] = __ldg(matc + idx);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = idx0 + j * kL64Threads, x = idx & (w - 1), y = idx >> logw;
+          const float q = deq_one(__float_as_uint(raw[j]), mt[j], mulc, qb, qbn);
+          float v = q;
+          if (c == 1) {
+            ytile[y * kL64Pitch + x] = q;
+          } else {
+            const int ti = int(((sbx * 8 + uint32_t(x)) >> 6) - tx0) + 5 * int(((sby * 8 + uint32_t(y)) >> 6) - ty0);
+            v = __fadd_rn(q, __fmul_rn(s_k[c == 0 ? 0 : 1][ti], ytile[y * kL64Pitch + x]));
+          }
+          tile[y * kL64Pitch + x] = v;
+        }
+      }
+      // lowest frequencies: forward DCT of the block's LF samples, rescaled (transform_common.rs:33-58)
+      const float* lf = f.lf[c];
+      for (int i = tid; i < bw * bh; i += kL64Threads) llf[i] = lf[size_t(sby + i / bw) * f.bw + sbx + i % bw];
+      __syncthreads();
+      {
+        float* line = lines + size_t(tid) * kL64Line;
+        if (tid < bh) {
+          float* row = llf + tid * bw;
+          for (int x = 0; x < bw; ++x) line[x] = row[x];
+          dct1d(line, line + 64, bw, true);
+          for (int x = 0; x < bw; ++x) row[x] = line[x];
+        }
+        __syncthreads();
+        if (tid < bw) {
+          for (int y = 0; y < bh; ++y) line[y] = llf[y * bw + tid];
+          dct1d(line, line + 64, bh, true);
+          for (int y = 0; y < bh; ++y) llf[y * bw + tid] = line[y];
+        }
+        __syncthreads();
+      }
+      const int logbw = 31 - __clz(bw), logbh = 31 - __clz(bh);
+      for (int i = tid; i < bw * bh; i += kL64Threads) {
+        const int x = i % bw, y = i / bw;
+        tile[y * kL64Pitch + x] = __fdiv_rn(llf[i], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
+      }
+      __syncthreads();
+      // inverse DCT: rows in place (a tile row is contiguous), then columns through the line buffers
+      if (tid < h) dct1d(tile + tid * kL64Pitch, lines + size_t(tid) * kL64Line, w, false);
+      __syncthreads();
+      if (tid < w) {
+        float* line = lines + size_t(tid) * kL64Line;
+        for (int y = 0; y < h; ++y) line[y] = tile[y * kL64Pitch + tid];
+        dct1d(line, line + 64, h, false);
+        for (int y = 0; y < h; ++y) tile[y * kL64Pitch + tid] = line[y];
+      }
+      __syncthreads();
+      for (int idx = tid; idx < w * h; idx += kL64Threads) {
+        const int x = idx & (w - 1), y = idx >> logw;
+        block[size_t(y) * f.cw + x] = tile[y * kL64Pitch + x];
+      }
+      __syncthreads();
+    }
+  }
+}
+
 }  // namespace
 
 void launch_lf_dequant(DevFrame f, const DevLfDequantJob* jobs, int num_jobs, cudaStream_t stream) {
@@ -1253,9 +1510,13 @@ void launch_idcts(DevFrame f, const DevDequantParams& dq, const TransformLists& 
   const int small_grid = int(std::min<size_t>((cells * per + kSmallGroups - 1) / kSmallGroups, size_t(num_sms) * 8));
   idct_small_kernel<DEQ><<<small_grid, kSmallGroups * 8, 0, stream>>>(f, dq, L);
   const int medium_grid = int(std::min<size_t>((cells / 2 * per + kMediumWarps) / kMediumWarps, size_t(num_sms) * 8));
-  idct_medium_kernel<DEQ><<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, dq, L);
+  static const bool generic_medium = std::getenv("JXLB_MEDIUM_GENERIC") != nullptr;
+  if (DEQ && !generic_medium) idct_medium_deq_kernel<<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, dq, L);
+  else idct_medium_kernel<DEQ><<<medium_grid, kMediumWarps * 32, 0, stream>>>(f, dq, L);
   const int large_grid = int(std::min<size_t>((cells / 32 + 1) * per, size_t(num_sms) * 4));
-  idct_large_kernel<DEQ><<<large_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 64 + 1)) * 4, stream>>>(f, dq, L.items[2], L.counts + 2, 64);
+  static const bool generic_large = std::getenv("JXLB_LARGE_GENERIC") != nullptr;
+  if (DEQ && !generic_large) idct_large64_deq_kernel<<<large_grid, kL64Threads, kL64SmemFloats * 4, stream>>>(f, dq, L.items[2], L.counts + 2);
+  else idct_large_kernel<DEQ><<<large_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 64 + 1)) * 4, stream>>>(f, dq, L.items[2], L.counts + 2, 64);
   const int huge_grid = int(std::min<size_t>((cells / 128 + 1) * per, size_t(num_sms)));
   idct_large_kernel<DEQ><<<huge_grid, kLargeThreads, (1024 + kLargeThreads * (2 * 256 + 1)) * 4, stream>>>(f, dq, L.items[3], L.counts + 3, 256);
 }
@@ -1294,6 +1555,7 @@ void launch_hf_transform(DevFrame f, void* scratch, const DevDequantParams* dq, 
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(idct_large_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
     cudaFuncSetAttribute(idct_large_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+    cudaFuncSetAttribute(idct_large64_deq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL64SmemFloats * 4);
   }
   if (dq && !f.subsampled) {
     launch_idcts<true>(f, *dq, L, cells, num_sms, stream);
