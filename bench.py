@@ -673,7 +673,7 @@ def main():
     ap.add_argument("--heavy-frames", type=int, default=0,
                     help="heavy slots (HBM slab + CUDA stream) per GPU (0: 20, Modular workloads 26)")
     ap.add_argument("--batch-streams", type=int, default=6, help="CUDA streams of the LF batch service")
-    ap.add_argument("--frames-per-step", type=int, default=48, help="independent frames decoded per step per GPU")
+    ap.add_argument("--frames-per-step", type=int, default=96, help="independent frames decoded per step per GPU")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (experiments only)")
     ap.add_argument("--gather", default="none", choices=["none", "u8", "u16"],

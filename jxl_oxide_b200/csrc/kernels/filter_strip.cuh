@@ -57,6 +57,14 @@ JXLB_FS float fs_float(uint32_t a) {
 #endif
 JXLB_FS float fs_absdiff(float a, float b) { return fabsf(fs_sub(a, b)); }
 
+// The Gaborish and distance phases walk the three channels with the same code (a loop, not three unrolled copies): the
+// kernel is straight-line code that every warp executes once, so its size is instruction-fetch traffic (ncu: 2.3 cycles of
+// "no instruction" stall per issue with the fully unrolled 4096-instruction body). JXLB_STRIP_ROLL=0 unrolls them again.
+#ifndef JXLB_STRIP_ROLL
+#define JXLB_STRIP_ROLL 1
+#endif
+constexpr int kChanUnroll = JXLB_STRIP_ROLL ? 1 : 3;
+
 constexpr int kWX = 64, kWY = 32;        // window (shared-memory plane) size
 constexpr int kM = 4;                    // margin
 constexpr int kTX = kWX - 2 * kM;        // 56 output columns
@@ -117,7 +125,7 @@ JXLB_FS void phase_gab(int tid, float* s, const DevFusedFilterParams& p, const f
   constexpr int L = 8;
   const int y0 = 1 + seg * L;
   const int n = (kWY - 1 - y0) < L ? (kWY - 1 - y0) : L;
-#pragma unroll
+#pragma unroll kChanUnroll
   for (int c = 0; c < 3; ++c) {
     const float* a = s + c * kPlane + y0 * kWX + col;
     float* o = s + kOffA + c * kPlane + y0 * kWX + col;
@@ -146,8 +154,11 @@ JXLB_FS void phase_dist1(int tid, float* s, const DevFusedFilterParams& p) {
   constexpr int yend = kWY - 3;  // 29
   const int y0 = 2 + seg * L;
   const int n = (yend - y0) < L ? (yend - y0) : L;
+  // epf.rs starts every distance at 0.0 and adds the channels' terms: the same here (0.0 + t is t for the non-negative t)
   float d01[L], d10[L];
 #pragma unroll
+  for (int i = 0; i < L; ++i) d01[i] = d10[i] = 0.0f;
+#pragma unroll kChanUnroll
   for (int c = 0; c < 3; ++c) {
     const float* a = s + kOffA + c * kPlane + y0 * kWX + col;  // (col, y0)
     const float sc = p.epf.channel_scale[c];
@@ -176,8 +187,8 @@ JXLB_FS void phase_dist1(int tid, float* s, const DevFusedFilterParams& p) {
         const float p01 = fs_add(fs_add(fs_add(fs_add(vc[0], vc[1]), vc[2]), vl), vr);
         const float p10 = fs_add(fs_add(fs_add(fs_add(hc[0], hc[1]), hc[2]), hl), hr);
         const float t01 = fs_mul(sc, p01), t10 = fs_mul(sc, p10);
-        d01[i] = c == 0 ? t01 : fs_add(d01[i], t01);
-        d10[i] = c == 0 ? t10 : fs_add(d10[i], t10);
+        d01[i] = fs_add(d01[i], t01);
+        d10[i] = fs_add(d10[i], t10);
         vc[0] = vc[1], vc[1] = vc[2];
         hc[0] = hc[1], hc[1] = hc[2];
 #pragma unroll
@@ -251,6 +262,9 @@ JXLB_FS float strip_linear_to_bt709(float a) {
   return fs_fma(fs_div(num, den), 1.099f, -0.099f);
 }
 
+// TF: transfer function applied after the matrix - 0 none (linear), 1 sRGB, 2 BT.709; a template parameter so that a kernel
+// carries the code of its own curve only (the row loops are unrolled: every pixel row holds a copy of the colour stage).
+template <int TF>
 JXLB_FS void strip_xyb_px(float o[3], const DevColorParams& p, const float* pow_tab) {
   const float xx = o[0], yy = o[1], bb = o[2];
   const float g_l = fs_sub(fs_add(yy, xx), p.cbrt_opsin_bias[0]);
@@ -263,18 +277,20 @@ JXLB_FS void strip_xyb_px(float o[3], const DevColorParams& p, const float* pow_
   o[0] = fs_add(fs_add(fs_mul(m[0], a), fs_mul(m[1], b)), fs_mul(m[2], c));
   o[1] = fs_add(fs_add(fs_mul(m[3], a), fs_mul(m[4], b)), fs_mul(m[5], c));
   o[2] = fs_add(fs_add(fs_mul(m[6], a), fs_mul(m[7], b)), fs_mul(m[8], c));
-  if (p.apply_srgb_tf) {
+  if (TF == 1) {
 #pragma unroll
     for (int c2 = 0; c2 < 3; ++c2) o[c2] = strip_linear_to_srgb(o[c2], pow_tab);
-  } else if (p.apply_bt709_tf) {
+  } else if (TF == 2) {
 #pragma unroll
     for (int c2 = 0; c2 < 3; ++c2) o[c2] = strip_linear_to_bt709(o[c2]);
   }
 }
+static inline int strip_tf_of(const DevFusedFilterParams& p) {  // host side: which instantiation a frame needs
+  return !p.colour ? 0 : (p.col.apply_srgb_tf ? 1 : (p.col.apply_bt709_tf ? 2 : 0)); }
 
 // ---- phase 3: step-1 weighted sums, A + D -> B (the dead `in` planes) on [3, 61) x [3, 29); when step 1 is the frame's last
 // EPF step (LAST: epf_iters == 1) the output tile [4, 60) x [4, 28) goes through the colour stage to the output planes ----
-template <bool LAST>
+template <bool LAST, int TF>
 JXLB_FS void phase_apply1(int tid, float* s, const StripGeom& g, const DevFusedFilterParams& p, float* const out[3],
                           const uint32_t out_stride[3]) {
   const int col = tid & (kWX - 1), seg = tid / kWX;
@@ -320,7 +336,7 @@ JXLB_FS void phase_apply1(int tid, float* s, const StripGeom& g, const DevFusedF
         epf_combine(du, dd, dl, dr, nis, ce, up, dn, le, ri, res);
       }
       if (LAST) {
-        if (p.colour) strip_xyb_px(res, p.col, s + kOffPow);
+        if (p.colour) strip_xyb_px<TF>(res, p.col, s + kOffPow);
         if (x_in && gy >= g.y0 && gy < g.y1) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) out[c][size_t(gy) * out_stride[c] + gx] = res[c];
@@ -338,6 +354,7 @@ JXLB_FS void phase_apply1(int tid, float* s, const StripGeom& g, const DevFusedF
 
 // ---- phase 4: step 2 (distances on the fly) + colour, B -> the output planes on [4, 60) x [4, 28) ---------------------
 // out[c] points at image pixel (0, 0) of the output plane c, stride in floats.
+template <int TF>
 JXLB_FS void phase_apply2(int tid, float* s, const StripGeom& g, const DevFusedFilterParams& p, float* const out[3],
                           const uint32_t out_stride[3]) {
   const int col = tid & (kWX - 1), seg = tid / kWX;
@@ -380,7 +397,7 @@ JXLB_FS void phase_apply2(int tid, float* s, const StripGeom& g, const DevFusedF
       const float dr = fs_add(fs_add(fs_mul(s0, fs_absdiff(ri[0], ce[0])), fs_mul(s1, fs_absdiff(ri[1], ce[1]))), fs_mul(s2, fs_absdiff(ri[2], ce[2])));
       epf_combine(du, dd, dl, dr, nis, ce, up, dn, le, ri, res);
     }
-    if (p.colour) strip_xyb_px(res, p.col, s + kOffPow);
+    if (p.colour) strip_xyb_px<TF>(res, p.col, s + kOffPow);
     if (x_in && gy >= g.y0 && gy < g.y1) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) out[c][size_t(gy) * out_stride[c] + gx] = res[c];

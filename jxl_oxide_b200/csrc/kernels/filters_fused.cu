@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(256) fused_filter_kernel(FusedViews v, DevFuse
 
 
 // Interior of the frame for the default filter chain (Gaborish, EPF steps 1 and 2, colour): kernels/filter_strip.cuh.
-template <int ITERS>
+template <int ITERS, int TF>
 __global__ void __launch_bounds__(fstrip::kThreads, 3)
 strip_filter_kernel(FusedViews v, DevFusedFilterParams p, const __grid_constant__ FusedMaps maps, fstrip::StripRect r, float gw0,
                     float gw1, float gw2) {
@@ -561,11 +561,11 @@ strip_filter_kernel(FusedViews v, DevFusedFilterParams p, const __grid_constant_
   phase_dist1(tid, s_buf, p);
   __syncthreads();
   if (ITERS == 1) {
-    phase_apply1<true>(tid, s_buf, g, p, v.out, v.out_stride);
+    phase_apply1<true, TF>(tid, s_buf, g, p, v.out, v.out_stride);
   } else {
-    phase_apply1<false>(tid, s_buf, g, p, v.out, v.out_stride);
+    phase_apply1<false, TF>(tid, s_buf, g, p, v.out, v.out_stride);
     __syncthreads();
-    phase_apply2(tid, s_buf, g, p, v.out, v.out_stride);
+    phase_apply2<TF>(tid, s_buf, g, p, v.out, v.out_stride);
   }
 }
 
@@ -627,8 +627,12 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
     cudaFuncSetAttribute(fused_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * window_size(0) * window_size(0) * 4);
     cudaFuncSetAttribute(fused_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * window_size(2) * window_size(2) * 4);
     cudaFuncSetAttribute(fused_filter_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * window_size(6) * window_size(6) * 4);
-    cudaFuncSetAttribute(strip_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
-    cudaFuncSetAttribute(strip_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
+    cudaFuncSetAttribute(strip_filter_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fstrip::kSmemFloats * 4);
     attr_set = true;
   }
   dim3 block(32, 8);
@@ -657,8 +661,19 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
       float gw[3];
       for (int c = 0; c < 3; ++c) gw[c] = 1.0f / ((1.0f + p.gab_w[c][0] * 4.0f) + p.gab_w[c][1] * 4.0f);
       dim3 sgrid((r.x1 - r.x0 + fstrip::kTX - 1) / fstrip::kTX, (r.y1 - r.y0 + fstrip::kTY - 1) / fstrip::kTY);
-      if (p.epf_iters == 1) strip_filter_kernel<1><<<sgrid, fstrip::kThreads, fstrip::kSmemFloats * 4, stream>>>(v, p, smaps, r, gw[0], gw[1], gw[2]);
-      else strip_filter_kernel<2><<<sgrid, fstrip::kThreads, fstrip::kSmemFloats * 4, stream>>>(v, p, smaps, r, gw[0], gw[1], gw[2]);
+      const int tf = fstrip::strip_tf_of(p);
+      const size_t sm = fstrip::kSmemFloats * 4;
+#define JXLB_STRIP_LAUNCH(I, T) strip_filter_kernel<I, T><<<sgrid, fstrip::kThreads, sm, stream>>>(v, p, smaps, r, gw[0], gw[1], gw[2])
+      if (p.epf_iters == 1) {
+        if (tf == 1) JXLB_STRIP_LAUNCH(1, 1);
+        else if (tf == 2) JXLB_STRIP_LAUNCH(1, 2);
+        else JXLB_STRIP_LAUNCH(1, 0);
+      } else {
+        if (tf == 1) JXLB_STRIP_LAUNCH(2, 1);
+        else if (tf == 2) JXLB_STRIP_LAUNCH(2, 2);
+        else JXLB_STRIP_LAUNCH(2, 0);
+      }
+#undef JXLB_STRIP_LAUNCH
       v.border_only = 1;
       v.bx_last = r.x1 / 32 - 1, v.by_last = r.y1 / 32 - 1;
       const int n_border = v.nbx * v.nby - v.bx_last * v.by_last;

@@ -547,7 +547,9 @@ struct TransformLists {
   uint32_t* items[4];
   uint32_t* shape_items[kMediumShapes];
   uint32_t* small_items[kSmallTypes];
+  uint32_t flags;  // bit 0: idct_small prefetches the next block's coefficient rows into L2 (JXLB_NO_L2_PREFETCH clears it)
 };
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // One list slot per varblock. The lanes of a warp that append to the same list reserve their slots with ONE atomic
 // (match_any): a frame has half a million cells and a dozen counters, and one atomic per cell serialises on them.
@@ -856,9 +858,12 @@ __device__ __forceinline__ void cfl_factors(const DevFrame& f, const DevDequantP
 #ifndef JXLB_MEDIUM_TRIP
 #define JXLB_MEDIUM_TRIP 8    // idct_medium: tile rows whose loads are in flight together (4, 8, 16, 32)
 #endif
+#ifndef JXLB_SMALL_MINB
+#define JXLB_SMALL_MINB 3      // idct_small: resident CTAs per SM asked of the register allocator
+#endif
 constexpr int kSmallGroups = 32;  // 8-thread groups per CTA
 template <bool DEQ>
-__global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
+__global__ void __launch_bounds__(kSmallGroups * 8, JXLB_SMALL_MINB) idct_small_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
   __shared__ float s_tile[kSmallGroups][72];      // 8 x 9
   __shared__ float s_special[kSmallGroups][192];  // 8 x 8 copy + 128 scratch
   const uint32_t group = threadIdx.x >> 3, r = threadIdx.x & 7;
@@ -874,6 +879,19 @@ __global__ void __launch_bounds__(kSmallGroups * 8) idct_small_kernel(DevFrame f
     const uint32_t item = items[DEQ ? work : work / 3];
     const uint32_t sbx = item & 0xffff, sby = item >> 16;
     const int32_t t = f.blk_type[size_t(sby) * f.bw + sbx];
+    if (DEQ && (lists.flags & 1)) {
+      // The rows this thread will read for the chroma channels of this block, and for the block it takes next, are
+      // requested into L2 now (no registers held): the loads below and in the next trip then wait for L2, not for DRAM.
+      const size_t here = (size_t(sby) * 8 + r) * f.cw + size_t(sbx) * 8;
+      prefetch_l2(f.coeff[0] + here);
+      prefetch_l2(f.coeff[2] + here);
+      const uint32_t next = work + gridDim.x * kSmallGroups;
+      if (next < total) {
+        const uint32_t ni = items[next];
+        const size_t there = (size_t(ni >> 16) * 8 + r) * f.cw + size_t(ni & 0xffff) * 8;
+        prefetch_l2(f.coeff[1] + there);
+      }
+    }
     DeqBlock db;
     float kx = 0.0f, kb = 0.0f, vy[8];
     // DEQ (never subsampled: every channel keeps the block at (sbx, sby)): the coefficient rows of the three channels are
@@ -1122,6 +1140,10 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
 // look-ups of the generic body (which spent ~3x more instructions on indexing than on arithmetic, ncu) fold into
 // immediates. The shapes are walked one after the other by all CTAs in step, so one instantiation's code is hot at a time,
 // and the line transforms are the shared idct_line_smem<N>.
+#ifndef JXLB_MEDIUM_ROLL
+#define JXLB_MEDIUM_ROLL 1     // medium_walk: block rows / 8-row batches of a tile as loops (code size: ncu showed 5.8 cycles
+#endif                         // of "no instruction" stall per issue with the 28 K-instruction fully unrolled kernel)
+constexpr int kMediumOuterUnroll = JXLB_MEDIUM_ROLL ? 1 : 32;
 struct MediumBlk {
   uint32_t bx, by;     // block position in 8x8 cells (dequantising frames are never subsampled: the same for all channels)
   float mul[3];        // DeqBlock::mul
@@ -1165,10 +1187,12 @@ __device__ __forceinline__ void medium_walk(const DevFrame& f, const DevDequantP
 #pragma unroll 1
     for (int ci = 0; ci < 3; ++ci) {
       const uint32_t c = ci == 0 ? 1u : (ci == 1 ? 0u : 2u);  // Y first: its dequantised samples feed the chroma channels
+      // (requesting the chroma rows into L2 while Y is transformed was measured slower: 0.467 ms against 0.388 ms per 8K frame and
+      // 130 MB more DRAM reads - the tile's three channels already overlap across the SM's warps; profiles/r02_progress.md, call Y)
       const float* __restrict__ matc = dq.matrices + dq.matrix_offset[(set * 3 + c) * 2 + tr] + x;
       const float qb = dq.quant_bias[c], qbn = dq.quant_bias_numerator;
       float* const plane = reinterpret_cast<float*>(f.coeff[c]);
-#pragma unroll
+#pragma unroll kMediumOuterUnroll
       for (int sy = 0; sy < NY; ++sy) {
         const int s = sy * NX + sx;
         const bool have = s < nb;
@@ -1178,7 +1202,7 @@ __device__ __forceinline__ void medium_walk(const DevFrame& f, const DevDequantP
         const int xt = x >= m.xsplit ? 1 : 0;
         const float k_top = c == 0 ? m.kx[xt] : m.kb[xt], k_bottom = c == 0 ? m.kx[xt + 2] : m.kb[xt + 2];
         const int ysplit = m.ysplit;
-#pragma unroll
+#pragma unroll kMediumOuterUnroll
         for (int y0 = 0; y0 < H; y0 += 8) {
           float raw[8], mt[8];
 #pragma unroll
@@ -1220,13 +1244,13 @@ __device__ __forceinline__ void medium_walk(const DevFrame& f, const DevDequantP
       for (int sy = 0; sy < NY; ++sy)  // columns: lane = tile column
         if (sy * NX + sx < nb) idct_line_smem<H>(tile + sy * H * 33 + lane, 33);
       __syncwarp();
-#pragma unroll
+#pragma unroll kMediumOuterUnroll
       for (int sy = 0; sy < NY; ++sy) {
         const int s = sy * NX + sx;
         if (s < nb) {
           const MediumBlk& m = sub[s];
           float* dst = plane + size_t(m.by) * 8 * f.cw + size_t(m.bx) * 8 + x;
-#pragma unroll
+#pragma unroll 8
           for (int y = 0; y < H; ++y) dst[size_t(y) * f.cw] = tile[(sy * H + y) * 33 + int(lane)];
         }
       }
@@ -1235,7 +1259,10 @@ __device__ __forceinline__ void medium_walk(const DevFrame& f, const DevDequantP
   }
 }
 
-__global__ void __launch_bounds__(kMediumWarps * 32, 4) idct_medium_deq_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
+#ifndef JXLB_MEDIUM_MINB
+#define JXLB_MEDIUM_MINB 5  // measured: 4 -> 0.419 ms, 5 -> 0.388 ms, 6 -> 0.447 ms (call W)
+#endif
+__global__ void __launch_bounds__(kMediumWarps * 32, JXLB_MEDIUM_MINB) idct_medium_deq_kernel(DevFrame f, DevDequantParams dq, TransformLists lists) {
   __shared__ float s_tile[kMediumWarps][32 * 33];
   __shared__ float s_ytile[kMediumWarps][32 * 33];  // dequantised Y coefficients (chroma from luma)
   __shared__ float s_llf[kMediumWarps][8][16];
@@ -1366,17 +1393,75 @@ __global__ void __launch_bounds__(kLargeThreads) idct_large_kernel(DevFrame f, D
 // column, of the block in global memory (one 4-byte request per sample, a warp's requests 64 rows apart). Here a CTA
 // keeps one channel of the block in a 64 x 65 shared tile: coefficients arrive with coalesced loads and are dequantised
 // on the way in (the dequantised Y copy stays in a second tile for chroma from luma), rows are transformed in place,
-// columns through the per-thread line buffers, and the samples leave with coalesced stores - one read and one write
+// columns likewise (l64_idct_pass), and the samples leave with coalesced stores - one read and one write
 // of HBM per sample. Per sample the operations and their order are those of idct_large_kernel.
-constexpr int kL64Threads = 128, kL64Pitch = 65, kL64Line = 2 * 64 + 1;
-constexpr int kL64SmemFloats = 2 * 64 * kL64Pitch + 64 + 64 * kL64Line;
-__global__ void __launch_bounds__(kL64Threads) idct_large64_deq_kernel(DevFrame f, DevDequantParams dq, const uint32_t* __restrict__ items,
+// One 1-D inverse-DCT pass over the lines of the shared tile by 128 threads. A 64-point line is split between two threads
+// the way Dct1D<64>::run(inverse) splits it (generic/dct.rs:239-293): even-indexed and odd-indexed samples go through
+// independent 32-point transforms (register-resident RegIdct<32>, the same operation sequence as Dct1D<32>), the
+// odd half after its neighbour additions and the sqrt(2), and is scaled by sec before the final butterfly. Thread
+// (line, half) = (tid & 63, tid >> 6): a warp works on 32 lines of the same half, so its shared accesses hit 32 banks.
+__device__ __forceinline__ void l64_idct_pass(float* tile, int nlines, int len, int line_stride, int elem_stride, int tid) {
+  const int line = tid & 63, half = tid >> 6;
+  const bool act = line < nlines;
+  float* p = tile + line * line_stride;
+  float v[32];
+  if (len == 64) {
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = p[(2 * i + half) * elem_stride];
+      if (half) {
+#pragma unroll
+        for (int i = 31; i >= 1; --i) v[i] = __fadd_rn(v[i], v[i - 1]);  // in1[j] += in1[j - 1], highest j first
+        v[0] = __fmul_rn(v[0], SQRT2F);
+      }
+      RegIdct<32>::run(v);
+      if (half) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __fmul_rn(v[i], kSecLarge[i]);
+      }
+    }
+    __syncthreads();  // every sample of the tile has been read
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) p[(half * 32 + i) * elem_stride] = v[i];
+    }
+    __syncthreads();
+    float o[32];
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = p[((1 - half) * 32 + i) * elem_stride];  // the other half's results
+    }
+    __syncthreads();
+    if (act) {
+      if (!half) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[i * elem_stride] = __fadd_rn(v[i], o[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) p[(63 - i) * elem_stride] = __fsub_rn(o[i], v[i]);
+      }
+    }
+  } else {  // 32-point lines: one thread each
+    if (act && half == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = p[i * elem_stride];
+      RegIdct<32>::run(v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) p[i * elem_stride] = v[i];
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int kL64Threads = 128, kL64Pitch = 65, kL64Line = 2 * 8 + 1;  // line buffers: the forward DCT of the <= 8 x 8 LF samples only
+constexpr int kL64SmemFloats = 2 * 64 * kL64Pitch + 64 + 8 * kL64Line;
+__global__ void __launch_bounds__(kL64Threads, 3) idct_large64_deq_kernel(DevFrame f, DevDequantParams dq, const uint32_t* __restrict__ items,
                                                                        const uint32_t* __restrict__ count_ptr) {
   extern __shared__ float s_l64[];
   float* tile = s_l64;                      // the channel being transformed
   float* ytile = tile + 64 * kL64Pitch;     // dequantised Y
   float* llf = ytile + 64 * kL64Pitch;      // <= 8 x 8 LF samples
-  float* lines = llf + 64;                  // 64 per-thread line + scratch buffers (odd pitch: conflict-free banks)
+  float* lines = llf + 64;                  // 8 per-thread line + scratch buffers for the LF samples' forward DCT
   __shared__ float s_k[2][25];
   const int tid = int(threadIdx.x);
   const uint32_t total = *count_ptr;
@@ -1432,13 +1517,13 @@ __global__ void __launch_bounds__(kL64Threads) idct_large64_deq_kernel(DevFrame 
         if (tid < bh) {
           float* row = llf + tid * bw;
           for (int x = 0; x < bw; ++x) line[x] = row[x];
-          dct1d(line, line + 64, bw, true);
+          dct1d(line, line + 8, bw, true);
           for (int x = 0; x < bw; ++x) row[x] = line[x];
         }
         __syncthreads();
         if (tid < bw) {
           for (int y = 0; y < bh; ++y) line[y] = llf[y * bw + tid];
-          dct1d(line, line + 64, bh, true);
+          dct1d(line, line + 8, bh, true);
           for (int y = 0; y < bh; ++y) llf[y * bw + tid] = line[y];
         }
         __syncthreads();
@@ -1449,16 +1534,9 @@ __global__ void __launch_bounds__(kL64Threads) idct_large64_deq_kernel(DevFrame 
         tile[y * kL64Pitch + x] = __fdiv_rn(llf[i], __fmul_rn(kScaleF[y << (5 - logbh)], kScaleF[x << (5 - logbw)]));
       }
       __syncthreads();
-      // inverse DCT: rows in place (a tile row is contiguous), then columns through the line buffers
-      if (tid < h) dct1d(tile + tid * kL64Pitch, lines + size_t(tid) * kL64Line, w, false);
-      __syncthreads();
-      if (tid < w) {
-        float* line = lines + size_t(tid) * kL64Line;
-        for (int y = 0; y < h; ++y) line[y] = tile[y * kL64Pitch + tid];
-        dct1d(line, line + 64, h, false);
-        for (int y = 0; y < h; ++y) tile[y * kL64Pitch + tid] = line[y];
-      }
-      __syncthreads();
+      // inverse DCT: rows, then columns (generic/dct.rs:93-140)
+      l64_idct_pass(tile, h, w, kL64Pitch, 1, tid);
+      l64_idct_pass(tile, w, h, 1, kL64Pitch, tid);
       for (int idx = tid; idx < w * h; idx += kL64Threads) {
         const int x = idx & (w - 1), y = idx >> logw;
         block[size_t(y) * f.cw + x] = tile[y * kL64Pitch + x];
@@ -1545,6 +1623,8 @@ void launch_hf_transform(DevFrame f, void* scratch, const DevDequantParams* dq, 
       q += cells + 1;
     }
   }
+  static const bool no_l2_prefetch = std::getenv("JXLB_NO_L2_PREFETCH") != nullptr;
+  L.flags = no_l2_prefetch ? 0u : 1u;
   cudaMemsetAsync(L.counts, 0, 128, stream);
   dim3 cb(32, 8), cg((f.bw + 31) / 32, (f.bh + 7) / 8);
   classify_varblocks_kernel<<<cg, cb, 0, stream>>>(f, L);

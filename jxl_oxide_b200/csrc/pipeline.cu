@@ -12,6 +12,7 @@
 // the GPU-filling stages of some frames overlap the latency-bound stages of others.
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <fstream>
@@ -568,6 +569,16 @@ int32_t jxlb_pipeline_create(int32_t device, const jxlb_pipeline_config* cfg, jx
   p->heavy_frames = heavy;
   p->slabs.resize(size_t(heavy));
   if (cudaSetDevice(device) != cudaSuccess) return JXLB_ERR_CUDA;
+  {
+    // A pipeline owns its device's decode work: L2 fetches 32-byte sectors instead of whole 128-byte lines. The inverse
+    // transforms read 32-byte row segments of varblocks whose line neighbours belong to another size class, i.e. to another
+    // kernel at another time; measured on an 8K frame (ncu dram__bytes_read): idct_small 342 -> 121 MB, idct_medium
+    // 533 -> 259 MB, kernel times unchanged (profiles/r02_progress.md, call W). JXLB_L2_FETCH=0 leaves the limit alone,
+    // 64 / 128 set another value (also honoured by stand-alone decoders, which do not touch the limit by default).
+    const char* e = std::getenv("JXLB_L2_FETCH");
+    const int g = e ? std::atoi(e) : 32;
+    if (g > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, size_t(g));
+  }
   for (Slab& sl : p->slabs)
     if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) return JXLB_ERR_CUDA;
   p->batcher.reset(new BatchService(device, cfg && cfg->batch_streams > 0 ? cfg->batch_streams : 6));

@@ -357,12 +357,22 @@ bool EmuBackend::filters_colour_fused(const View v[3], const RestorationFilter& 
     for (int tid = 0; tid < kThreads; ++tid) phase_sigma(tid, s.data(), g, p);
     for (int tid = 0; tid < kThreads; ++tid) phase_gab(tid, s.data(), p, gw);
     for (int tid = 0; tid < kThreads; ++tid) phase_dist1(tid, s.data(), p);
-    if (p.epf_iters == 1) {
-      for (int tid = 0; tid < kThreads; ++tid) phase_apply1<true>(tid, s.data(), g, p, out, out_stride);
-    } else {
-      for (int tid = 0; tid < kThreads; ++tid) phase_apply1<false>(tid, s.data(), g, p, out, out_stride);
-      for (int tid = 0; tid < kThreads; ++tid) phase_apply2(tid, s.data(), g, p, out, out_stride);
+    const int tf = strip_tf_of(p);
+    for (int tid = 0; tid < kThreads; ++tid) {
+      if (p.epf_iters == 1) {
+        if (tf == 1) phase_apply1<true, 1>(tid, s.data(), g, p, out, out_stride);
+        else if (tf == 2) phase_apply1<true, 2>(tid, s.data(), g, p, out, out_stride);
+        else phase_apply1<true, 0>(tid, s.data(), g, p, out, out_stride);
+      } else {
+        phase_apply1<false, 0>(tid, s.data(), g, p, out, out_stride);
+      }
     }
+    if (p.epf_iters == 2)
+      for (int tid = 0; tid < kThreads; ++tid) {
+        if (tf == 1) phase_apply2<1>(tid, s.data(), g, p, out, out_stride);
+        else if (tf == 2) phase_apply2<2>(tid, s.data(), g, p, out, out_stride);
+        else phase_apply2<0>(tid, s.data(), g, p, out, out_stride);
+      }
   });
 
   OracleBackend::gaborish(v, rf.gab_weights);
