@@ -547,7 +547,7 @@ struct TransformLists {
   uint32_t* items[4];
   uint32_t* shape_items[kMediumShapes];
   uint32_t* small_items[kSmallTypes];
-  uint32_t flags;  // bit 0: idct_small prefetches the next block's coefficient rows into L2 (JXLB_NO_L2_PREFETCH clears it)
+  uint32_t flags;  // bit 0: idct_small prefetches the next block's coefficient rows into L2 (JXLB_L2_PREFETCH=1 sets it)
 };
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -1141,8 +1141,8 @@ __global__ void __launch_bounds__(kMediumWarps * 32) idct_medium_kernel(DevFrame
 // immediates. The shapes are walked one after the other by all CTAs in step, so one instantiation's code is hot at a time,
 // and the line transforms are the shared idct_line_smem<N>.
 #ifndef JXLB_MEDIUM_ROLL
-#define JXLB_MEDIUM_ROLL 1     // medium_walk: block rows / 8-row batches of a tile as loops (code size: ncu showed 5.8 cycles
-#endif                         // of "no instruction" stall per issue with the 28 K-instruction fully unrolled kernel)
+#define JXLB_MEDIUM_ROLL 0     // medium_walk: block rows / 8-row batches of a tile as loops instead of unrolled. Measured (call Z):
+#endif                         // 12 968 instead of 28 264 instructions, but 0.462 ms against 0.391 ms - the unrolled form wins
 constexpr int kMediumOuterUnroll = JXLB_MEDIUM_ROLL ? 1 : 32;
 struct MediumBlk {
   uint32_t bx, by;     // block position in 8x8 cells (dequantising frames are never subsampled: the same for all channels)
@@ -1623,8 +1623,9 @@ void launch_hf_transform(DevFrame f, void* scratch, const DevDequantParams* dq, 
       q += cells + 1;
     }
   }
-  static const bool no_l2_prefetch = std::getenv("JXLB_NO_L2_PREFETCH") != nullptr;
-  L.flags = no_l2_prefetch ? 0u : 1u;
+  // measured (calls Y, Z): 0.235 ms against 0.241 ms for idct_small, but 140 MB more DRAM reads per 8K frame: off by default
+  static const bool l2_prefetch = std::getenv("JXLB_L2_PREFETCH") != nullptr;
+  L.flags = l2_prefetch ? 1u : 0u;
   cudaMemsetAsync(L.counts, 0, 128, stream);
   dim3 cb(32, 8), cg((f.bw + 31) / 32, (f.bh + 7) / 8);
   classify_varblocks_kernel<<<cg, cb, 0, stream>>>(f, L);
