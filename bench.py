@@ -485,7 +485,8 @@ def run_ours(args, rank, world, local_rank):
             entropy["modular_samples_per_s_whole_job"] = n * len(frames) * world / (ms / args.steps / 1e3)
         if sym:
             entropy["symbol_counts"] = "profiles/r02_symbols.json (" + str(sym.get("how")) + ")"
-    cpu = cpu_baseline(args, frames, px_per_frame) if not args.no_cpu_baseline else None
+    # the CPU leg runs beside the 1-GPU line only (rank 0, N = 1); the driver's reference arm covers the other N
+    cpu = cpu_baseline(args, frames, px_per_frame) if (not args.no_cpu_baseline and world == 1) else None
     line = {
         "metric": METRIC.get(args.workload, "Megapixels/s decoded"), "value": value, "unit": "MP/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
