@@ -643,7 +643,12 @@ void launch_filters_fused(const DevView in[3], const DevView out[3], DevFusedFil
   // tiles that touch the image border (mirroring, Gaborish edge formulas) in the general one.
   static const bool no_strip = std::getenv("JXLB_NO_STRIP") != nullptr;
   const fstrip::StripRect r = fstrip::strip_rect(v.width, v.height);
-  if (!no_strip && v.use_tma && p.gab_enabled && (p.epf_iters == 1 || p.epf_iters == 2) && r.x1 > r.x0 && r.y1 > r.y0) {
+  // The strip kernel's window origins are 28 + 56 * tx and, for the pulled-back last column of tiles, width - 64: TMA wants the
+  // box to start on a 16-byte boundary in the innermost dimension (cp.async.bulk.tensor with an origin of 325 floats ended in
+  // "illegal instruction": call EE, profiles/r02_raw/r02ee_memcheck_strip3wip.log), so frames whose width is not a multiple of
+  // four samples stay in the general kernel, whose origins are multiples of four by construction.
+  const bool origins_aligned = (v.width & 3) == 0;
+  if (!no_strip && v.use_tma && origins_aligned && p.gab_enabled && (p.epf_iters == 1 || p.epf_iters == 2) && r.x1 > r.x0 && r.y1 > r.y0) {
     FusedMaps smaps;
     std::memset(&smaps, 0, sizeof(smaps));
     bool ok = true;
