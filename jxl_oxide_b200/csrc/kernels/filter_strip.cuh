@@ -421,5 +421,26 @@ static inline StripRect strip_rect(int width, int height) {
   return r;
 }
 
+// The general kernel's launch over the tiles the strip kernel does not cover (a 1-D grid): tile `i` of nbx x nby tiles minus
+// the interior [1, bx_last] x [1, by_last] - row 0, then the rows below by_last, then the left column and the columns right of
+// bx_last of the rows in between. Count: nbx * nby - bx_last * by_last.
+JXLB_FS void border_tile_index(int nbx, int nby, int bx_last, int by_last, int i, int& tx, int& ty) {
+  if (i < nbx) {
+    tx = i, ty = 0;
+    return;
+  }
+  i -= nbx;
+  const int n_bottom = nbx * (nby - 1 - by_last);
+  if (i < n_bottom) {
+    ty = by_last + 1 + i / nbx, tx = i % nbx;
+    return;
+  }
+  i -= n_bottom;
+  const int per_row = 1 + (nbx - 1 - bx_last);
+  ty = 1 + i / per_row;
+  const int j = i % per_row;
+  tx = j == 0 ? 0 : bx_last + j;
+}
+
 }  // namespace fstrip
 }  // namespace jxlb

@@ -312,24 +312,9 @@ struct FusedViews {
   int border_only, bx_last, by_last, nbx, nby;
 };
 
-// Tile of a border-only launch: row 0, then the rows below by_last, then the left column and the columns right of bx_last
-// of the rows in between.
+// Tile of a border-only launch (fstrip::border_tile_index, shared with the host-side check in tests/emu).
 __device__ __forceinline__ void border_tile_of(const FusedViews& v, int i, int& tx, int& ty) {
-  if (i < v.nbx) {
-    tx = i, ty = 0;
-    return;
-  }
-  i -= v.nbx;
-  const int n_bottom = v.nbx * (v.nby - 1 - v.by_last);
-  if (i < n_bottom) {
-    ty = v.by_last + 1 + i / v.nbx, tx = i % v.nbx;
-    return;
-  }
-  i -= n_bottom;
-  const int per_row = 1 + (v.nbx - 1 - v.bx_last);
-  ty = 1 + i / per_row;
-  const int j = i % per_row;
-  tx = j == 0 ? 0 : v.bx_last + j;
+  fstrip::border_tile_index(v.nbx, v.nby, v.bx_last, v.by_last, i, tx, ty);
 }
 
 // TMA descriptors of the three input planes (2-D, f32, box kS x kS, out-of-bounds cells read as zero).

@@ -291,6 +291,55 @@ extern "C" void jxle_strip_stats(uint64_t out[3], int reset) {
   }
 }
 
+// Host-side check of the filter launch geometry (launch_filters_fused): the strip kernel's rectangle is the union of the general
+// kernel's interior tiles, and the 1-D border grid enumerates every other tile exactly once. Returns 0 when the frame size
+// checks out, otherwise a code that says what is wrong.
+extern "C" int jxle_filter_geometry_check(int width, int height) {
+  using namespace jxlb::fstrip;
+  const StripRect r = strip_rect(width, height);
+  const int nbx = (width + 31) / 32, nby = (height + 31) / 32;
+  if (r.x1 <= r.x0 || r.y1 <= r.y0) return 0;  // no strip launch: the general kernel takes the whole frame
+  if (r.x0 != 32 || r.y0 != 32 || r.x1 % 32 || r.y1 % 32) return 1;
+  if (r.x1 + kM > width || r.y1 + kM > height) return 2;  // every pixel of the rectangle is a margin away from the border
+  const int bx_last = r.x1 / 32 - 1, by_last = r.y1 / 32 - 1;
+  // interior tiles are exactly those whose 40 x 40 window lies inside the image
+  for (int ty = 0; ty < nby; ++ty)
+    for (int tx = 0; tx < nbx; ++tx) {
+      const bool inside = tx * 32 - 4 >= 0 && ty * 32 - 4 >= 0 && tx * 32 + 36 <= width && ty * 32 + 36 <= height;
+      const bool in_rect = tx >= 1 && tx <= bx_last && ty >= 1 && ty <= by_last;
+      if (inside != in_rect) return 3;
+    }
+  std::vector<int> seen(size_t(nbx) * nby, 0);
+  const int n_border = nbx * nby - bx_last * by_last;
+  for (int i = 0; i < n_border; ++i) {
+    int tx = -1, ty = -1;
+    border_tile_index(nbx, nby, bx_last, by_last, i, tx, ty);
+    if (tx < 0 || tx >= nbx || ty < 0 || ty >= nby) return 4;
+    if (tx >= 1 && tx <= bx_last && ty >= 1 && ty <= by_last) return 5;  // an interior tile in the border grid
+    if (seen[size_t(ty) * nbx + tx]++) return 6;                            // twice
+  }
+  for (int ty = 0; ty < nby; ++ty)
+    for (int tx = 0; tx < nbx; ++tx) {
+      const bool in_rect = tx >= 1 && tx <= bx_last && ty >= 1 && ty <= by_last;
+      if (!in_rect && !seen[size_t(ty) * nbx + tx]) return 7;  // a border tile nobody takes
+    }
+  // strip tiles: origins inside the image, 16-byte aligned when the width is a multiple of four, outputs cover the rectangle
+  const int ntx = (r.x1 - r.x0 + kTX - 1) / kTX, nty = (r.y1 - r.y0 + kTY - 1) / kTY;
+  std::vector<int> cover(size_t(r.x1 - r.x0) * (r.y1 - r.y0), 0);
+  for (int ty = 0; ty < nty; ++ty)
+    for (int tx = 0; tx < ntx; ++tx) {
+      const StripGeom g = strip_geom(width, height, r.x0, r.y0, r.x1, r.y1, tx, ty);
+      if (g.gx0 < 0 || g.gy0 < 0 || g.gx0 + kWX > width || g.gy0 + kWY > height) return 8;
+      if ((width & 3) == 0 && (g.gx0 & 3)) return 9;
+      for (int y = g.gy0 + kM; y < g.gy0 + kWY - kM; ++y)
+        for (int x = g.gx0 + kM; x < g.gx0 + kWX - kM; ++x)
+          if (x >= r.x0 && x < r.x1 && y >= r.y0 && y < r.y1) cover[size_t(y - r.y0) * (r.x1 - r.x0) + (x - r.x0)] = 1;
+    }
+  for (int c : cover)
+    if (!c) return 10;
+  return 0;
+}
+
 namespace jxlo {
 
 bool EmuBackend::filters_colour_fused(const View v[3], const RestorationFilter& rf, const View& sigma, bool sigma_is_constant,

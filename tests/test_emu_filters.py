@@ -54,3 +54,15 @@ def test_strip_filter_matches_oracle_on_libjxl_frames(name):
     # libjxl's own d1 frames: Gaborish + one EPF step; `noise` leaves the colour stage to a later kernel
     with open(os.path.join(GOLDEN, name), "rb") as f:
         _check(f.read(), 3 * 400 * 500)
+
+
+def test_filter_launch_geometry():
+    """The strip kernel's rectangle + the general kernel's 1-D border grid tile every frame size exactly once; strip windows stay
+    inside the image and start on 16-byte boundaries (TMA) whenever the width is a multiple of four."""
+    L = oracle_lib.emu_lib()
+    L.jxle_filter_geometry_check.restype = ctypes.c_int
+    sizes = [(128, 96), (129, 97), (160, 128), (500, 606), (520, 392), (1000, 600), (1001, 601), (2560, 1440), (3840, 2160), (7680, 4320),
+             (7681, 4319), (4096, 97), (131, 4000)]
+    sizes += [(w, h) for w in range(120, 330, 7) for h in (96, 100, 127, 128, 131, 161)]
+    for w, h in sizes:
+        assert L.jxle_filter_geometry_check(w, h) == 0, (w, h)
